@@ -1,0 +1,180 @@
+/* slamrs_gpu.h -- C ABI of the B200-native grid particle-filter SLAM step.
+ *
+ * This is the drop-in boundary behind slamrs' unchanged `GridMapSlamNode`
+ * (slamrs/slam/src/grid/node.rs:35-60). The reference has no FFI; the seam is the inherent API
+ * of `struct GridMapSlam` (slamrs/slam/src/grid/slam.rs:13-97). Each entry point below names the
+ * Rust item it replaces. INTEGRATION.md shows the Rust `-sys` binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = SLAMRS_OK, negative = error (see enum);
+ *     no C++ exception crosses this boundary;
+ *   - all pointer arguments are HOST pointers borrowed for the duration of the call, unless the
+ *     name says `_device`;
+ *   - a handle is driven by one thread at a time (Send, not Sync in Rust terms);
+ *   - one handle owns ONE GPU and one contiguous shard of the particle population; a
+ *     multi-GPU filter is `world_size` handles (one per GPU, one per process or per thread)
+ *     that call every collective entry point (create / update / step / pose /
+ *     map_probability / destroy) in the same order with the same arguments.
+ *   - grid cells are addressed `index = row * grid_h + column` with column = x, row = y
+ *     (slamrs/slam/src/grid/map.rs:194-204); grids must be square (the reference's index
+ *     formula aliases otherwise).
+ */
+#ifndef SLAMRS_GPU_H
+#define SLAMRS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLAMRS_GPU_ABI_VERSION 1
+#define SLAMRS_NCCL_ID_BYTES 128
+
+enum slamrs_status {
+    SLAMRS_OK = 0,
+    SLAMRS_E_INVALID_ARG = -1,   /* null pointer, zero particles, non-square grid, bad rank ... */
+    SLAMRS_E_CUDA = -2,          /* a CUDA runtime call failed; see slamrs_gpu_last_error */
+    SLAMRS_E_NCCL = -3,          /* NCCL unavailable or a collective failed */
+    SLAMRS_E_OUT_OF_MEMORY = -4, /* device allocation failed */
+    SLAMRS_E_NO_DEVICE = -5,     /* no CUDA device: there is NO CPU fallback */
+    SLAMRS_E_STAGING = -6,       /* cross-GPU migration needed more free grid slots than exist */
+    SLAMRS_E_NOT_LOCAL = -7,     /* debug accessor asked for a particle owned by another rank */
+    SLAMRS_E_INTERNAL = -8
+};
+
+enum slamrs_rng_mode {
+    SLAMRS_RNG_SHARED_STREAM = 0, /* library draws from the Philox4x32-10 shared stream */
+    SLAMRS_RNG_CALLER = 1         /* caller passes the standard-normal draws and the resample uniform */
+};
+
+typedef struct slamrs_gpu_handle slamrs_gpu_handle;
+
+/* Replaces `GridMapSlamConfig` (slam.rs:18-25) plus the placement the YAML cannot carry. */
+typedef struct slamrs_gpu_config {
+    uint32_t struct_size;  /* = sizeof(slamrs_gpu_config) */
+    uint32_t abi_version;  /* = SLAMRS_GPU_ABI_VERSION */
+    float pos_x, pos_y;    /* GridMapSlamConfig.position (world position of cell (0,0)'s corner) */
+    float resolution;      /* metres per cell */
+    uint32_t grid_w;       /* ceil(width / resolution) in f32, map.rs:28-31; see slamrs_gpu_grid_cells */
+    uint32_t grid_h;       /* must equal grid_w */
+    uint64_t n_particles;  /* TOTAL over all ranks; must be divisible by world_size */
+    uint64_t seed;         /* shared-stream key */
+    uint32_t rng_mode;     /* enum slamrs_rng_mode */
+    int32_t device;        /* CUDA ordinal, -1 = current device */
+    uint32_t rank;         /* 0 .. world_size-1 */
+    uint32_t world_size;   /* 1 = single GPU */
+    uint32_t spare_slots;  /* extra physical grid slots per GPU used to stage grids that migrate
+                              between GPUs at resampling; 0 = automatic (none when world_size==1) */
+    uint32_t flags;        /* reserved, 0 */
+    uint8_t nccl_id[SLAMRS_NCCL_ID_BYTES]; /* from slamrs_gpu_nccl_unique_id, same on all ranks */
+} slamrs_gpu_config;
+
+/* Per-step counters for benchmarks and tests (last completed step). */
+typedef struct slamrs_gpu_stats {
+    uint64_t step;             /* number of completed updates */
+    uint64_t grids_copied;     /* local duplicate copies made by the resampler (D) */
+    uint64_t grids_pulled;     /* grids fetched from other GPUs over NVLink */
+    uint64_t distinct_sources; /* distinct surviving particles among this rank's new generation */
+    uint64_t resample_clamped; /* 1 if a resample index ran past N-1 (the reference would panic) */
+    uint64_t counter_saturated;/* cells whose u16 counter hit 65535 in this step */
+    uint64_t spilled_cells;    /* ray cell-steps that fell outside the shared-memory window */
+    uint64_t window_cells;     /* shared-memory window size used by the ray kernel (cells) */
+    uint64_t bytes_per_grid;   /* device bytes of one particle grid */
+} slamrs_gpu_stats;
+
+/* ------------------------------------------------------------------ lifecycle */
+
+/* Map::new's grid sizing, map.rs:28-31: `(extent / resolution).ceil() as usize` in f32. */
+int slamrs_gpu_grid_cells(float extent, float resolution, uint32_t* out_cells);
+
+/* Fill `out` with a fresh NCCL unique id (call on rank 0, distribute to every rank's config). */
+int slamrs_gpu_nccl_unique_id(uint8_t out[SLAMRS_NCCL_ID_BYTES]);
+
+/* GridMapSlam::new, slam.rs:28-43 (Map::new map.rs:26-48, ParticleFilter::new particle.rs:15-28):
+ * N particles at Pose::default() with all-prior maps and weight 1/N. Collective when world_size>1. */
+int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out);
+
+/* Drop. Safe on NULL. A later create in the same process must work (baseui/src/app.rs:121-134). */
+void slamrs_gpu_destroy(slamrs_gpu_handle* h);
+
+/* ------------------------------------------------------------------ the step */
+
+/* GridMapSlam::update(&mut self, z: &Observation, u: Odometry), slam.rs:46-75.
+ *   angle/dist : `m.angle as f32`, `m.distance as f32` per measurement (map.rs:76-77,121-122)
+ *   valid      : Measurement.valid (robot.rs:93)
+ *   dist_left / dist_right / wheel_dist : the three Odometry floats (robot.rs:115-123); the two
+ *                Normal distributions are derived inside exactly as Odometry::new does (:132-150)
+ *   z_draws    : rng_mode CALLER: 2*n_particles standard normals, particle-major
+ *                (centre-distance draw, heading draw -- the draw order of robot.rs:175-176);
+ *                every rank passes the full array. NULL in SHARED_STREAM mode.
+ *   resample_u : rng_mode CALLER: pointer to the uniform [0,1) of particle.rs:84. NULL otherwise.
+ * Synchronous: on return the new generation is complete (reference semantics, node.rs:49-57). */
+int slamrs_gpu_update(slamrs_gpu_handle* h, const float* angle, const float* dist, const uint8_t* valid,
+                      uint32_t n_beams, float dist_left, float dist_right, float wheel_dist,
+                      const double* z_draws, const double* resample_u);
+
+/* The same step split for pipelined callers and for device-resident benchmarking:
+ * upload_scan copies the observation to the device (async on the handle's stream);
+ * step_async enqueues one full SLAM step on the device-resident scan and returns immediately;
+ * sync waits for the handle's stream. update() == upload_scan + step_async + sync. */
+int slamrs_gpu_upload_scan(slamrs_gpu_handle* h, const float* angle, const float* dist, const uint8_t* valid,
+                           uint32_t n_beams);
+int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_right, float wheel_dist,
+                          const double* z_draws, const double* resample_u);
+int slamrs_gpu_sync(slamrs_gpu_handle* h);
+
+/* GridMapSlam::estimated_pose, slam.rs:77-81 -> {x, y, theta}. Reproduces the reference's
+ * indexing: particle `max_particle` (argmax BEFORE resampling) of the NEW generation. */
+int slamrs_gpu_pose(slamrs_gpu_handle* h, float out_xyt[3]);
+
+/* GridMapSlam::estimated_likelihood, slam.rs:83-88 -> grid_w*grid_h probabilities (f64), the
+ * payload of GridMapMessage.data (node.rs:68-72). Collective when world_size>1 (the owning GPU
+ * broadcasts); every rank receives the map. */
+int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells);
+
+/* ------------------------------------------------------------------ introspection (tests, bench) */
+
+const char* slamrs_gpu_last_error(const slamrs_gpu_handle* h); /* never NULL; "" when none */
+int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out);
+/* cudaStream_t the step runs on, for CUDA-event timing by the caller */
+void* slamrs_gpu_stream(slamrs_gpu_handle* h);
+/* number of kernels this handle has launched since create */
+uint64_t slamrs_gpu_launch_count(const slamrs_gpu_handle* h);
+
+/* current generation, this rank's shard: n_local * {x, y, theta} */
+int slamrs_gpu_get_poses(slamrs_gpu_handle* h, float* out_xyt);
+int slamrs_gpu_set_poses(slamrs_gpu_handle* h, const float* xyt);
+/* last step, all N particles in pre-resample order: normalised and raw (un-normalised) weights */
+int slamrs_gpu_get_weights(slamrs_gpu_handle* h, double* out_norm, double* out_raw);
+/* last step's resample source index for every new particle (N entries) and the stored argmax */
+int slamrs_gpu_get_resample_indices(slamrs_gpu_handle* h, uint32_t* out_idx);
+int slamrs_gpu_get_max_particle(slamrs_gpu_handle* h, uint64_t* out);
+/* one particle's grid as packed hit counters: low 16 bits = free updates, high 16 = occupied
+ * updates; log-odds = n_free*ln(0.3/0.7) + n_occ*ln(0.9/0.1) (map.rs:154-156). `particle` is a
+ * GLOBAL logical index and must be owned by this rank. */
+int slamrs_gpu_get_cells(slamrs_gpu_handle* h, uint64_t particle, uint32_t* out_cells);
+int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t* cells);
+/* same grid as f64 log-odds (what the reference stores per cell, math.rs:104) */
+int slamrs_gpu_get_log_odds(slamrs_gpu_handle* h, uint64_t particle, double* out_cells);
+
+/* ------------------------------------------------------------------ kernel-level test hooks */
+
+/* GridRayIterator (ray.rs:21-110) on the device for n_rays rays in grid coordinates.
+ * out_xy holds n_rays * cap * 2 int32 (x, y) pairs, out_count the number of cells each ray
+ * visits (may exceed cap; only the first cap are stored). */
+int slamrs_gpu_debug_raycast(int device, const float* x0, const float* y0, const float* x1, const float* y1,
+                             uint32_t n_rays, uint32_t grid_w, uint32_t grid_h, uint32_t extra_steps,
+                             int32_t* out_xy, uint32_t cap, uint32_t* out_count);
+/* the device's f32 sin/cos used for poses and endpoints (bit-identical to glibc sinf/cosf) */
+int slamrs_gpu_debug_sincos(int device, const float* x, uint32_t n, float* out_sin, float* out_cos);
+/* the shared stream evaluated on the device: 2*count normals for particles first.. and the
+ * resample uniform of `step` */
+int slamrs_gpu_debug_stream(int device, uint64_t seed, uint64_t step, uint64_t first, uint64_t count,
+                            double* out_z, double* out_u);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMRS_GPU_H */

@@ -1,0 +1,700 @@
+// C ABI of the B200-native grid SLAM step (see include/slamrs_gpu.h).
+// Host side: owns device state, sequences the kernels on one stream per GPU, talks NCCL for
+// the weight/pose all-gather and maps peer grid pools for cross-GPU migration.
+#include "../../include/slamrs_gpu.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "comm.h"
+#include "kernels.cuh"
+
+using namespace slamrs;
+
+struct slamrs_gpu_handle {
+    slamrs_gpu_config cfg{};
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+
+    uint32_t n_total = 0, n_local = 0, rank = 0, world = 1, first = 0;
+    uint32_t n_cells = 0;        // grid_w * grid_h
+    size_t cells_per_grid = 0;   // n_cells rounded up to 32 cells (128 B) so every slot is 128 B aligned
+    uint32_t n_slots = 0, n_spare = 0;
+    MapGeom geom{};
+
+    uint32_t* d_cells = nullptr;
+    int32_t* d_slot[2] = {nullptr, nullptr};
+    float* d_pose[2] = {nullptr, nullptr};
+    int cur = 0;
+    ParticleResult* d_results = nullptr;
+    double* d_wnorm = nullptr;
+    double* d_cum = nullptr;
+    uint32_t* d_idx = nullptr;
+    float* d_angle = nullptr;
+    float* d_dist = nullptr;
+    uint8_t* d_valid = nullptr;
+    uint32_t beam_cap = 0, n_beams = 0;
+    int radius_cells = 1;
+    double* d_z = nullptr;
+    double* d_u = nullptr;
+    int32_t *d_keep = nullptr, *d_need = nullptr, *d_free = nullptr, *d_spare = nullptr;
+    CopyItem *d_copies = nullptr, *d_pulls = nullptr;
+    StepCounters* d_counters = nullptr;
+    StepCounters* h_counters = nullptr;  // pinned
+    double* d_export = nullptr;
+    int* d_barrier = nullptr;
+
+    Comm* comm = nullptr;
+    uint32_t** d_peer_cells = nullptr;         // device array [world]
+    std::vector<void*> ipc_opened;             // peer mappings to close
+    uint64_t step = 0;
+    uint64_t launches = 0;
+    uint64_t window_cells = 0;
+    std::string last_error;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(slamrs_gpu_handle* h, int code, const std::string& msg) {
+    if (h) h->last_error = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CU_TRY(h, expr)                                                                               \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            const int _code = (_e == cudaErrorMemoryAllocation) ? SLAMRS_E_OUT_OF_MEMORY : SLAMRS_E_CUDA; \
+            return fail(h, _code, std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+        }                                                                                             \
+    } while (0)
+
+// Odometry::new, slamrs/common/src/robot.rs:132-150
+OdomModel odometry_new(float dl, float dr, float wheel) {
+    OdomModel o;
+    const double delta_center = (double)((dl + dr) / 2.0f);
+    const double delta_theta = (double)((dr - dl) / wheel);
+    o.mean_c = delta_center;
+    o.std_c = (0.01 + fabs(delta_center) * 0.05) / 2.0;
+    const double rads_per_deg = 3.14159265358979323846264338327950288 / 180.0;  // f64::to_radians
+    o.mean_t = delta_theta;
+    o.std_t = 5.0 * rads_per_deg + 0.1 * fabs(delta_theta);
+    return o;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int now = -1;
+        cudaGetDevice(&now);
+        if (prev >= 0 && now != prev) cudaSetDevice(prev);
+    }
+};
+
+struct PeerInfo {  // exchanged between ranks at create
+    cudaIpcMemHandle_t handle;
+    uint64_t pid;
+    uint64_t ptr;
+    int32_t device;
+    int32_t pad;
+};
+
+int setup_peers(slamrs_gpu_handle* h) {
+    const uint32_t W = h->world;
+    std::vector<PeerInfo> all(W);
+    PeerInfo mine;
+    memset(&mine, 0, sizeof(mine));
+    CU_TRY(h, cudaIpcGetMemHandle(&mine.handle, h->d_cells));
+    mine.pid = (uint64_t)getpid();
+    mine.ptr = (uint64_t)(uintptr_t)h->d_cells;
+    mine.device = h->device;
+    PeerInfo* d_all = nullptr;
+    CU_TRY(h, cudaMalloc(&d_all, sizeof(PeerInfo) * W));
+    CU_TRY(h, cudaMemcpyAsync(d_all + h->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+    std::string err;
+    if (comm_all_gather(h->comm, d_all + h->rank, d_all, sizeof(PeerInfo), h->stream, &err)) {
+        cudaFree(d_all);
+        return fail(h, SLAMRS_E_NCCL, err);
+    }
+    CU_TRY(h, cudaMemcpyAsync(all.data(), d_all, sizeof(PeerInfo) * W, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_all);
+
+    std::vector<uint32_t*> peers(W, nullptr);
+    for (uint32_t r = 0; r < W; ++r) {
+        if (r == h->rank) { peers[r] = h->d_cells; continue; }
+        if (all[r].pid == mine.pid) {
+            // same process: plain peer access to the other device's allocation
+            int can = 0;
+            CU_TRY(h, cudaDeviceCanAccessPeer(&can, h->device, all[r].device));
+            if (!can) return fail(h, SLAMRS_E_CUDA, "peer access between GPUs not available");
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(h, SLAMRS_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+            peers[r] = (uint32_t*)(uintptr_t)all[r].ptr;
+        } else {
+            void* p = nullptr;
+            CU_TRY(h, cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened.push_back(p);
+            peers[r] = (uint32_t*)p;
+        }
+    }
+    CU_TRY(h, cudaMalloc(&h->d_peer_cells, sizeof(uint32_t*) * W));
+    CU_TRY(h, cudaMemcpy(h->d_peer_cells, peers.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
+    return SLAMRS_OK;
+}
+
+void free_all(slamrs_gpu_handle* h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && h->d_barrier && h->stream) {
+        // nobody may still be pulling from this pool when it is freed
+        std::string err;
+        if (comm_barrier(h->comm, h->d_barrier, h->stream, &err) == 0) cudaStreamSynchronize(h->stream);
+    }
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
+    comm_destroy(h->comm);
+    h->comm = nullptr;
+    cudaFree(h->d_cells);
+    cudaFree(h->d_slot[0]); cudaFree(h->d_slot[1]);
+    cudaFree(h->d_pose[0]); cudaFree(h->d_pose[1]);
+    cudaFree(h->d_results); cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx);
+    cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
+    cudaFree(h->d_z); cudaFree(h->d_u);
+    cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
+    cudaFree(h->d_copies); cudaFree(h->d_pulls);
+    cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells);
+    if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
+int ensure_beam_capacity(slamrs_gpu_handle* h, uint32_t n) {
+    if (n <= h->beam_cap) return SLAMRS_OK;
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
+    h->d_angle = h->d_dist = nullptr; h->d_valid = nullptr; h->beam_cap = 0;
+    const uint32_t cap = (n + 255u) & ~255u;
+    CU_TRY(h, cudaMalloc(&h->d_angle, sizeof(float) * cap));
+    CU_TRY(h, cudaMalloc(&h->d_dist, sizeof(float) * cap));
+    CU_TRY(h, cudaMalloc(&h->d_valid, cap));
+    h->beam_cap = cap;
+    return SLAMRS_OK;
+}
+
+int fetch_counters(slamrs_gpu_handle* h) {
+    CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(StepCounters), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+}  // namespace
+
+namespace {
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)); }
+    ~DevBuf() { cudaFree(p); }
+};
+int debug_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return SLAMRS_E_NO_DEVICE; }
+    if (device >= n) return SLAMRS_E_INVALID_ARG;
+    return SLAMRS_OK;
+}
+#define DBG_CU(expr)                                                                     \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) return fail(nullptr, SLAMRS_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+}  // namespace
+
+extern "C" {
+
+int slamrs_gpu_grid_cells(float extent, float resolution, uint32_t* out_cells) {
+    if (!out_cells) return SLAMRS_E_INVALID_ARG;
+    const float c = ceilf(extent / resolution);  // map.rs:28-31, f32 division then ceil, `as usize` saturates
+    if (!(c == c) || c <= 0.0f) { *out_cells = 0; return SLAMRS_OK; }
+    if (c >= 4294967296.0f) return SLAMRS_E_INVALID_ARG;
+    *out_cells = (uint32_t)c;
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_nccl_unique_id(uint8_t out[SLAMRS_NCCL_ID_BYTES]) {
+    if (!out) return SLAMRS_E_INVALID_ARG;
+    std::string err;
+    if (comm_unique_id(out, &err)) return fail(nullptr, SLAMRS_E_NCCL, err);
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
+    if (!cfg || !out) return fail(nullptr, SLAMRS_E_INVALID_ARG, "null config or output pointer");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(slamrs_gpu_config) || cfg->abi_version != SLAMRS_GPU_ABI_VERSION)
+        return fail(nullptr, SLAMRS_E_INVALID_ARG, "slamrs_gpu_config size/ABI version mismatch");
+    if (cfg->n_particles == 0)  // ParticleFilter::new asserts, particle.rs:16
+        return fail(nullptr, SLAMRS_E_INVALID_ARG, "Must have at least one particle");
+    if (cfg->world_size == 0 || cfg->rank >= cfg->world_size || cfg->n_particles % cfg->world_size != 0)
+        return fail(nullptr, SLAMRS_E_INVALID_ARG, "bad rank/world_size or n_particles not divisible by world_size");
+    if (cfg->n_particles > 0x7fffffffull) return fail(nullptr, SLAMRS_E_INVALID_ARG, "too many particles");
+    if (cfg->grid_w == 0 || cfg->grid_w != cfg->grid_h)
+        return fail(nullptr, SLAMRS_E_INVALID_ARG,
+                    "grid must be square and non-empty (the reference index row*size.y+column aliases otherwise)");
+    if ((uint64_t)cfg->grid_w * cfg->grid_h > 0x7fffffffull) return fail(nullptr, SLAMRS_E_INVALID_ARG, "grid too large");
+    if (!(cfg->resolution > 0.0f)) return fail(nullptr, SLAMRS_E_INVALID_ARG, "resolution must be positive");
+    if (cfg->rng_mode > SLAMRS_RNG_CALLER) return fail(nullptr, SLAMRS_E_INVALID_ARG, "unknown rng_mode");
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SLAMRS_E_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    }
+    int device = cfg->device;
+    if (device < 0) cudaGetDevice(&device);
+    if (device >= n_dev) return fail(nullptr, SLAMRS_E_INVALID_ARG, "device ordinal out of range");
+
+    slamrs_gpu_handle* h = new (std::nothrow) slamrs_gpu_handle();
+    if (!h) return fail(nullptr, SLAMRS_E_OUT_OF_MEMORY, "host allocation failed");
+    h->cfg = *cfg;
+    h->device = device;
+    h->world = cfg->world_size;
+    h->rank = cfg->rank;
+    h->n_total = (uint32_t)cfg->n_particles;
+    h->n_local = h->n_total / h->world;
+    h->first = h->rank * h->n_local;
+    h->n_cells = cfg->grid_w * cfg->grid_h;
+    h->cells_per_grid = ((size_t)h->n_cells + 31u) & ~(size_t)31u;
+    h->geom = MapGeom{cfg->pos_x, cfg->pos_y, cfg->resolution, cfg->grid_w, cfg->grid_h};
+
+#define CREATE_TRY(expr)                                  \
+    do {                                                  \
+        int _rc = (expr);                                 \
+        if (_rc != SLAMRS_OK) {                           \
+            g_create_error = h->last_error;               \
+            free_all(h);                                  \
+            return _rc;                                   \
+        }                                                 \
+    } while (0)
+#define CREATE_CU(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess) {                                                                          \
+            const int _code = (_e == cudaErrorMemoryAllocation) ? SLAMRS_E_OUT_OF_MEMORY : SLAMRS_E_CUDA; \
+            g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                          \
+            cudaGetLastError();                                                                           \
+            free_all(h);                                                                                  \
+            return _code;                                                                                 \
+        }                                                                                                 \
+    } while (0)
+
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CREATE_CU(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        g_create_error = "this library is built for sm_100a (B200) only";
+        free_all(h);
+        return SLAMRS_E_NO_DEVICE;
+    }
+    CREATE_CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_CU(configure_kernels());
+
+    // spare slots: staging room for grids that migrate between GPUs at resampling
+    const size_t grid_bytes = h->cells_per_grid * sizeof(uint32_t);
+    if (h->world > 1) {
+        uint32_t spare = cfg->spare_slots;
+        if (spare == 0) {
+            size_t free_b = 0, total_b = 0;
+            CREATE_CU(cudaMemGetInfo(&free_b, &total_b));
+            const size_t reserve = (size_t)2 << 30;  // leave room for NCCL buffers and small arrays
+            const size_t live = (size_t)h->n_local * grid_bytes;
+            size_t room = free_b > live + reserve ? (free_b - live - reserve) / grid_bytes : 0;
+            spare = (uint32_t)(room < h->n_local ? room : h->n_local);
+        }
+        h->n_spare = spare;
+    }
+    h->n_slots = h->n_local + h->n_spare;
+
+    CREATE_CU(cudaMalloc(&h->d_cells, (size_t)h->n_slots * grid_bytes));
+    CREATE_CU(cudaMemsetAsync(h->d_cells, 0, (size_t)h->n_slots * grid_bytes, h->stream));  // ln(0.5/0.5) = 0
+    for (int i = 0; i < 2; ++i) {
+        CREATE_CU(cudaMalloc(&h->d_slot[i], sizeof(int32_t) * h->n_local));
+        CREATE_CU(cudaMalloc(&h->d_pose[i], sizeof(float) * 3 * h->n_local));
+        CREATE_CU(cudaMemsetAsync(h->d_pose[i], 0, sizeof(float) * 3 * h->n_local, h->stream));  // Pose::default()
+    }
+    CREATE_CU(cudaMalloc(&h->d_results, sizeof(ParticleResult) * h->n_total));
+    CREATE_CU(cudaMemsetAsync(h->d_results, 0, sizeof(ParticleResult) * h->n_total, h->stream));
+    CREATE_CU(cudaMalloc(&h->d_wnorm, sizeof(double) * h->n_total));
+    CREATE_CU(cudaMalloc(&h->d_cum, sizeof(double) * h->n_total));
+    CREATE_CU(cudaMalloc(&h->d_idx, sizeof(uint32_t) * h->n_total));
+    CREATE_CU(cudaMemsetAsync(h->d_wnorm, 0, sizeof(double) * h->n_total, h->stream));
+    CREATE_CU(cudaMemsetAsync(h->d_idx, 0, sizeof(uint32_t) * h->n_total, h->stream));
+    if (cfg->rng_mode == SLAMRS_RNG_CALLER) {
+        CREATE_CU(cudaMalloc(&h->d_z, sizeof(double) * 2 * h->n_total));
+        CREATE_CU(cudaMalloc(&h->d_u, sizeof(double)));
+    }
+    CREATE_CU(cudaMalloc(&h->d_keep, sizeof(int32_t) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_need, sizeof(int32_t) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_free, sizeof(int32_t) * ((size_t)h->n_local + h->n_spare + 1)));
+    CREATE_CU(cudaMalloc(&h->d_spare, sizeof(int32_t) * ((size_t)h->n_spare + 1)));
+    CREATE_CU(cudaMalloc(&h->d_copies, sizeof(CopyItem) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_pulls, sizeof(CopyItem) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_counters, sizeof(StepCounters)));
+    CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
+    memset(h->h_counters, 0, sizeof(StepCounters));
+    CREATE_CU(cudaMalloc(&h->d_export, sizeof(double) * h->n_cells));
+    CREATE_CU(cudaMalloc(&h->d_barrier, sizeof(int)));
+    CREATE_CU(cudaMemsetAsync(h->d_barrier, 0, sizeof(int), h->stream));
+    launch_init_slots(h->stream, h->d_slot[0], h->n_local, h->d_spare, h->n_spare, h->d_counters, h->rank);
+    h->launches++;
+    CREATE_CU(cudaGetLastError());
+
+    if (h->world > 1) {
+        std::string err;
+        h->comm = comm_create(cfg->nccl_id, (int)h->rank, (int)h->world, &err);
+        if (!h->comm) {
+            g_create_error = err;
+            free_all(h);
+            return SLAMRS_E_NCCL;
+        }
+        CREATE_TRY(setup_peers(h));
+    }
+    CREATE_CU(cudaStreamSynchronize(h->stream));
+    h->h_counters->est_slot = h->rank == 0 ? 0 : -1;
+    h->h_counters->n_spare = h->n_spare;
+#undef CREATE_TRY
+#undef CREATE_CU
+    *out = h;
+    return SLAMRS_OK;
+}
+
+void slamrs_gpu_destroy(slamrs_gpu_handle* h) { free_all(h); }
+
+int slamrs_gpu_upload_scan(slamrs_gpu_handle* h, const float* angle, const float* dist, const uint8_t* valid,
+                           uint32_t n_beams) {
+    if (!h) return SLAMRS_E_INVALID_ARG;
+    if (n_beams > 0 && (!angle || !dist || !valid)) return fail(h, SLAMRS_E_INVALID_ARG, "null scan array");
+    if (n_beams > 65535u) return fail(h, SLAMRS_E_INVALID_ARG, "at most 65535 beams per scan");
+    DeviceGuard g(h->device);
+    int rc = ensure_beam_capacity(h, n_beams ? n_beams : 1);
+    if (rc) return rc;
+    if (n_beams) {
+        CU_TRY(h, cudaMemcpyAsync(h->d_angle, angle, sizeof(float) * n_beams, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->d_dist, dist, sizeof(float) * n_beams, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->d_valid, valid, n_beams, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->n_beams = n_beams;
+    // window radius for the ray kernel: farthest finite measurement, in cells, plus the two extra
+    // steps of apply_measurement (map.rs:97) and rounding slack. Correctness never depends on it:
+    // cells outside the window take the global-atomic path.
+    float maxd = 0.0f;
+    for (uint32_t i = 0; i < n_beams; ++i)
+        if (isfinite(dist[i]) && fabsf(dist[i]) > maxd) maxd = fabsf(dist[i]);
+    const float cells = ceilf(maxd / h->geom.res);
+    h->radius_cells = (cells < 4096.0f ? (int)cells : 4096) + 4;
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_right, float wheel_dist,
+                          const double* z_draws, const double* resample_u) {
+    if (!h) return SLAMRS_E_INVALID_ARG;
+    const bool caller = h->cfg.rng_mode == SLAMRS_RNG_CALLER;
+    if (caller && (!z_draws || !resample_u))
+        return fail(h, SLAMRS_E_INVALID_ARG, "rng_mode CALLER needs z_draws and resample_u");
+    DeviceGuard g(h->device);
+    cudaStream_t s = h->stream;
+    const OdomModel od = odometry_new(dist_left, dist_right, wheel_dist);
+    if (caller) {
+        CU_TRY(h, cudaMemcpyAsync(h->d_z, z_draws, sizeof(double) * 2 * h->n_total, cudaMemcpyHostToDevice, s));
+        CU_TRY(h, cudaMemcpyAsync(h->d_u, resample_u, sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    const ScanDevice scan{h->d_angle, h->d_dist, h->d_valid, h->n_beams};
+    const int cur = h->cur, nxt = cur ^ 1;
+
+    // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
+    launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->cells_per_grid,
+                             h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step);
+    // 2. integrate the scan into every particle's grid
+    CU_TRY(h, cudaMemsetAsync(&h->d_counters->saturated, 0, 2 * sizeof(unsigned long long), s));
+    CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_slot[cur], h->d_cells,
+                                h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells));
+    h->launches += 2;
+    // 3. the one exchange step: every GPU needs every particle's weight, pose and slot
+    if (h->world > 1) {
+        std::string err;
+        if (comm_all_gather(h->comm, h->d_results + h->first, h->d_results, sizeof(ParticleResult) * h->n_local, s, &err))
+            return fail(h, SLAMRS_E_NCCL, err);
+    }
+    // 4. normalise, argmax, running sum; systematic resampling indices (replicated on every GPU)
+    launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
+    launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
+                            h->d_idx, h->d_pose[nxt], h->first, h->n_local, h->d_counters);
+    // 5. plan: which grids stay, which are duplicated locally, which are pulled from a peer
+    PlanArgs pa{};
+    pa.results = h->d_results;
+    pa.idx = h->d_idx;
+    pa.n_total = h->n_total; pa.n_local = h->n_local; pa.rank = h->rank; pa.world = h->world;
+    pa.slot_old = h->d_slot[cur]; pa.slot_new = h->d_slot[nxt];
+    pa.keep = h->d_keep; pa.need = h->d_need; pa.free_list = h->d_free; pa.spare_list = h->d_spare;
+    pa.n_spare_cap = h->n_spare;
+    pa.copies = h->d_copies; pa.pulls = h->d_pulls;
+    pa.cells = h->d_cells; pa.cells_per_grid = h->cells_per_grid;
+    pa.peer_cells = h->d_peer_cells;
+    pa.counters = h->d_counters;
+    launch_plan(s, pa);
+    h->launches += 3;
+    // 6. grid traffic: NVLink pulls first, barrier, then the local duplicate copies
+    if (h->world > 1) {
+        launch_copy(s, h->d_pulls, &h->d_counters->n_pulls, h->cells_per_grid, h->num_sms);
+        h->launches++;
+        std::string err;
+        if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
+    }
+    launch_copy(s, h->d_copies, &h->d_counters->n_copies, h->cells_per_grid, h->num_sms);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+    h->cur = nxt;
+    h->step++;
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_sync(slamrs_gpu_handle* h) {
+    if (!h) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int rc = fetch_counters(h);
+    if (rc) return rc;
+    if (h->h_counters->staging_short)
+        return fail(h, SLAMRS_E_STAGING,
+                    "cross-GPU migration needed more free grid slots than available; raise spare_slots");
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_update(slamrs_gpu_handle* h, const float* angle, const float* dist, const uint8_t* valid,
+                      uint32_t n_beams, float dist_left, float dist_right, float wheel_dist, const double* z_draws,
+                      const double* resample_u) {
+    int rc = slamrs_gpu_upload_scan(h, angle, dist, valid, n_beams);
+    if (rc) return rc;
+    rc = slamrs_gpu_step_async(h, dist_left, dist_right, wheel_dist, z_draws, resample_u);
+    if (rc) return rc;
+    return slamrs_gpu_sync(h);
+}
+
+int slamrs_gpu_pose(slamrs_gpu_handle* h, float out_xyt[3]) {
+    if (!h || !out_xyt) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int rc = fetch_counters(h);
+    if (rc) return rc;
+    out_xyt[0] = h->h_counters->est_pose[0];
+    out_xyt[1] = h->h_counters->est_pose[1];
+    out_xyt[2] = h->h_counters->est_pose[2];
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells) {
+    if (!h || !out_cells) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    cudaStream_t s = h->stream;
+    launch_export(s, h->d_cells, h->cells_per_grid, h->d_counters, h->n_cells, h->d_export);
+    h->launches++;
+    if (h->world > 1) {
+        int rc = fetch_counters(h);  // root = owner of the estimate, identical on every rank
+        if (rc) return rc;
+        std::string err;
+        if (comm_broadcast(h->comm, h->d_export, sizeof(double) * h->n_cells, (int)h->h_counters->est_owner, s, &err))
+            return fail(h, SLAMRS_E_NCCL, err);
+    }
+    CU_TRY(h, cudaMemcpyAsync(out_cells, h->d_export, sizeof(double) * h->n_cells, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+    CU_TRY(h, cudaGetLastError());
+    return SLAMRS_OK;
+}
+
+const char* slamrs_gpu_last_error(const slamrs_gpu_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out) {
+    if (!h || !out) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int rc = fetch_counters(h);
+    if (rc) return rc;
+    const StepCounters& c = *h->h_counters;
+    out->step = h->step;
+    out->grids_copied = c.n_copies;
+    out->grids_pulled = c.n_pulls;
+    out->distinct_sources = c.distinct;
+    out->resample_clamped = c.clamped;
+    out->counter_saturated = c.saturated;
+    out->spilled_cells = c.spilled;
+    out->window_cells = h->window_cells;
+    out->bytes_per_grid = h->cells_per_grid * sizeof(uint32_t);
+    return SLAMRS_OK;
+}
+
+void* slamrs_gpu_stream(slamrs_gpu_handle* h) { return h ? (void*)h->stream : nullptr; }
+uint64_t slamrs_gpu_launch_count(const slamrs_gpu_handle* h) { return h ? h->launches : 0; }
+
+int slamrs_gpu_get_poses(slamrs_gpu_handle* h, float* out_xyt) {
+    if (!h || !out_xyt) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    CU_TRY(h, cudaMemcpyAsync(out_xyt, h->d_pose[h->cur], sizeof(float) * 3 * h->n_local, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_set_poses(slamrs_gpu_handle* h, const float* xyt) {
+    if (!h || !xyt) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    CU_TRY(h, cudaMemcpyAsync(h->d_pose[h->cur], xyt, sizeof(float) * 3 * h->n_local, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_get_weights(slamrs_gpu_handle* h, double* out_norm, double* out_raw) {
+    if (!h) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    if (out_norm)
+        CU_TRY(h, cudaMemcpyAsync(out_norm, h->d_wnorm, sizeof(double) * h->n_total, cudaMemcpyDeviceToHost, h->stream));
+    if (out_raw)
+        CU_TRY(h, cudaMemcpy2DAsync(out_raw, sizeof(double), h->d_results, sizeof(ParticleResult), sizeof(double),
+                                    h->n_total, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_get_resample_indices(slamrs_gpu_handle* h, uint32_t* out_idx) {
+    if (!h || !out_idx) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    CU_TRY(h, cudaMemcpyAsync(out_idx, h->d_idx, sizeof(uint32_t) * h->n_total, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_get_max_particle(slamrs_gpu_handle* h, uint64_t* out) {
+    if (!h || !out) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int rc = fetch_counters(h);
+    if (rc) return rc;
+    *out = h->h_counters->max_particle;
+    return SLAMRS_OK;
+}
+
+static int local_slot(slamrs_gpu_handle* h, uint64_t particle, int32_t* slot) {
+    if (particle < h->first || particle >= (uint64_t)h->first + h->n_local)
+        return fail(h, SLAMRS_E_NOT_LOCAL, "particle is owned by another rank");
+    CU_TRY(h, cudaMemcpyAsync(slot, h->d_slot[h->cur] + (particle - h->first), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_get_cells(slamrs_gpu_handle* h, uint64_t particle, uint32_t* out_cells) {
+    if (!h || !out_cells) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int32_t slot = 0;
+    int rc = local_slot(h, particle, &slot);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(out_cells, h->d_cells + (size_t)slot * h->cells_per_grid, sizeof(uint32_t) * h->n_cells,
+                              cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t* cells) {
+    if (!h || !cells) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int32_t slot = 0;
+    int rc = local_slot(h, particle, &slot);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->d_cells + (size_t)slot * h->cells_per_grid, cells, sizeof(uint32_t) * h->n_cells,
+                              cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_get_log_odds(slamrs_gpu_handle* h, uint64_t particle, double* out_cells) {
+    if (!h || !out_cells) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int32_t slot = 0;
+    int rc = local_slot(h, particle, &slot);
+    if (rc) return rc;
+    launch_export_log_odds(h->stream, h->d_cells + (size_t)slot * h->cells_per_grid, h->n_cells, h->d_export);
+    h->launches++;
+    CU_TRY(h, cudaMemcpyAsync(out_cells, h->d_export, sizeof(double) * h->n_cells, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+// ------------------------------------------------------------------ kernel-level test hooks
+
+int slamrs_gpu_debug_raycast(int device, const float* x0, const float* y0, const float* x1, const float* y1,
+                             uint32_t n_rays, uint32_t grid_w, uint32_t grid_h, uint32_t extra_steps, int32_t* out_xy,
+                             uint32_t cap, uint32_t* out_count) {
+    if (!x0 || !y0 || !x1 || !y1 || !out_xy || !out_count || n_rays == 0 || cap == 0) return SLAMRS_E_INVALID_ARG;
+    int rc = debug_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device < 0 ? 0 : device);
+    DevBuf<float> a, b, c, d;
+    DevBuf<int32_t> o;
+    DevBuf<uint32_t> cnt;
+    DBG_CU(a.alloc(n_rays)); DBG_CU(b.alloc(n_rays)); DBG_CU(c.alloc(n_rays)); DBG_CU(d.alloc(n_rays));
+    DBG_CU(o.alloc((size_t)n_rays * cap * 2)); DBG_CU(cnt.alloc(n_rays));
+    DBG_CU(cudaMemcpy(a.p, x0, 4 * n_rays, cudaMemcpyHostToDevice));
+    DBG_CU(cudaMemcpy(b.p, y0, 4 * n_rays, cudaMemcpyHostToDevice));
+    DBG_CU(cudaMemcpy(c.p, x1, 4 * n_rays, cudaMemcpyHostToDevice));
+    DBG_CU(cudaMemcpy(d.p, y1, 4 * n_rays, cudaMemcpyHostToDevice));
+    DBG_CU(cudaMemset(o.p, 0xff, sizeof(int32_t) * (size_t)n_rays * cap * 2));
+    launch_debug_raycast(nullptr, a.p, b.p, c.p, d.p, n_rays, grid_w, grid_h, extra_steps, o.p, cap, cnt.p);
+    DBG_CU(cudaGetLastError());
+    DBG_CU(cudaMemcpy(out_xy, o.p, sizeof(int32_t) * (size_t)n_rays * cap * 2, cudaMemcpyDeviceToHost));
+    DBG_CU(cudaMemcpy(out_count, cnt.p, 4 * n_rays, cudaMemcpyDeviceToHost));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_debug_sincos(int device, const float* x, uint32_t n, float* out_sin, float* out_cos) {
+    if (!x || !out_sin || !out_cos || n == 0) return SLAMRS_E_INVALID_ARG;
+    int rc = debug_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device < 0 ? 0 : device);
+    DevBuf<float> a, s, c;
+    DBG_CU(a.alloc(n)); DBG_CU(s.alloc(n)); DBG_CU(c.alloc(n));
+    DBG_CU(cudaMemcpy(a.p, x, 4 * (size_t)n, cudaMemcpyHostToDevice));
+    launch_debug_sincos(nullptr, a.p, n, s.p, c.p);
+    DBG_CU(cudaGetLastError());
+    DBG_CU(cudaMemcpy(out_sin, s.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    DBG_CU(cudaMemcpy(out_cos, c.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_debug_stream(int device, uint64_t seed, uint64_t step, uint64_t first, uint64_t count, double* out_z,
+                            double* out_u) {
+    if (!out_u || (count && !out_z)) return SLAMRS_E_INVALID_ARG;
+    int rc = debug_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device < 0 ? 0 : device);
+    DevBuf<double> z, u;
+    DBG_CU(z.alloc(2 * count)); DBG_CU(u.alloc(1));
+    launch_debug_stream(nullptr, seed, step, first, count, z.p, u.p);
+    DBG_CU(cudaGetLastError());
+    if (count) DBG_CU(cudaMemcpy(out_z, z.p, sizeof(double) * 2 * count, cudaMemcpyDeviceToHost));
+    DBG_CU(cudaMemcpy(out_u, u.p, sizeof(double), cudaMemcpyDeviceToHost));
+    return SLAMRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,719 @@
+// Hand-written sm_100a kernels of the grid particle-filter SLAM step.
+//
+//   k_motion_likelihood  robot.rs:170-183 (sample), map.rs:113-145 (beam-endpoint likelihood),
+//                        robot.rs:152-167 (motion pdf)            -> one CTA per particle
+//   k_ray_update         map.rs:71-106 + ray.rs:21-110 + map.rs:148-172 (integrate)
+//                                                                  -> one CTA per particle,
+//                        hit counters accumulated in a shared-memory window, 128-bit write-back
+//   k_weights            particle.rs:49-56 (normalise) + :40-46 (argmax) + the running sum of :85-91
+//   k_resample_indices   particle.rs:78-101 (systematic resampling indices)
+//   k_plan               turns the index vector into "keep in place / copy / pull" work lists
+//   k_copy               particle.rs:97-100 `value.clone()` -> streaming 128-bit grid copies
+//   k_export             slam.rs:83-88 / map.rs:50-52 (counters -> probability grid)
+//
+// No tensor cores anywhere: nothing here is a dense contraction. The step is HBM-bound
+// (grid copies) with a latency-bound cell walk in front of it.
+#include "kernels.cuh"
+#include "shared_stream.cuh"
+
+namespace slamrs {
+
+// =============================================================================== helpers
+
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4(uint4* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+// exclusive prefix sum of one uint32 per thread over a 1024-thread CTA (warp shuffles + one
+// shared array of 32 warp totals). Returns the exclusive prefix; *total gets the CTA sum.
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* warp_tot /*[33]*/, uint32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();  // protect warp_tot reuse across calls
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < nw ? warp_tot[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_tot[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) warp_tot[32] = winc;
+    }
+    __syncthreads();
+    *total = warp_tot[32];
+    return warp_tot[wid] + inc - v;
+}
+
+// same for doubles (fixed combination order => deterministic)
+__device__ __forceinline__ double block_excl_scan_f64(double v, double* warp_tot /*[33]*/, double* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = __dadd_rn(t, inc);
+    }
+    __syncthreads();
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const double w = lane < nw ? warp_tot[lane] : 0.0;
+        double winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc = __dadd_rn(t, winc);
+        }
+        const double excl = __shfl_up_sync(0xffffffffu, winc, 1);
+        warp_tot[lane] = lane == 0 ? 0.0 : excl;
+        if (lane == 31) warp_tot[32] = winc;
+    }
+    __syncthreads();
+    *total = warp_tot[32];
+    // exclusive prefix of this thread = warp offset + (inclusive - own) within the warp
+    const double within = __shfl_up_sync(0xffffffffu, inc, 1);
+    return lane == 0 ? warp_tot[wid] : __dadd_rn(warp_tot[wid], within);
+}
+
+// =============================================================================== k_motion_likelihood
+
+constexpr int ML_THREADS = 128;
+
+__global__ void __launch_bounds__(ML_THREADS)
+k_motion_likelihood(MapGeom geom, OdomModel od, ScanDevice scan, const float* __restrict__ pose_cur,
+                    const int32_t* __restrict__ slot_of, const uint32_t* __restrict__ cells, size_t cells_per_grid,
+                    ParticleResult* __restrict__ results, uint32_t first_particle, const double* __restrict__ z_draws,
+                    uint64_t seed, uint64_t step) {
+    extern __shared__ double s_terms[];  // one log-factor per beam, summed in beam order below
+    __shared__ float s_pose[3];
+    const uint32_t p = blockIdx.x;               // local particle
+    const uint32_t gp = first_particle + p;      // global logical index
+    const float ox = pose_cur[3 * p], oy = pose_cur[3 * p + 1], otheta = pose_cur[3 * p + 2];
+
+    if (threadIdx.x == 0) {
+        // Odometry::sample, robot.rs:170-183. statrs: sample = mean + std_dev * z.
+        double z1, z2;
+        if (z_draws) {
+            z1 = z_draws[2 * (size_t)gp];
+            z2 = z_draws[2 * (size_t)gp + 1];
+        } else {
+            slamrs_stream::motion_normals(seed, step, gp, &z1, &z2);
+        }
+        const float center_distance = (float)__dadd_rn(od.mean_c, __dmul_rn(od.std_c, z1));
+        const float theta = __fadd_rn(otheta, (float)__dadd_rn(od.mean_t, __dmul_rn(od.std_t, z2)));
+        s_pose[0] = __fadd_rn(ox, __fmul_rn(slamrs_libm::cosf_exact(theta), center_distance));
+        s_pose[1] = __fadd_rn(oy, __fmul_rn(slamrs_libm::sinf_exact(theta), center_distance));
+        s_pose[2] = theta;
+    }
+    __syncthreads();
+    const float nx = s_pose[0], ny = s_pose[1], ntheta = s_pose[2];
+    const uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
+
+    // Map::probability_of, map.rs:113-145: one gather per valid beam, pre-update map.
+    for (uint32_t b = threadIdx.x; b < scan.n_beams; b += ML_THREADS) {
+        double term = 0.0;
+        if (scan.valid[b]) {
+            float ex, ey;
+            beam_endpoint(nx, ny, ntheta, scan.angle[b], scan.dist[b], &ex, &ey);
+            const float gx = world_to_grid(ex, geom.pos_x, geom.res);
+            const float gy = world_to_grid(ey, geom.pos_y, geom.res);
+            if (grid_is_valid(gx, gy, geom.gw, geom.gh)) {
+                const size_t column = (size_t)f32_as_usize(gx), row = (size_t)f32_as_usize(gy);
+                const uint32_t cell = __ldg(&grid[row * geom.gh + column]);  // index(): map.rs:201-204
+                const double prob = log_odds_probability(cell_log_odds(cell));
+                // Z_HIT = 0.9, SENSOR_MAXDIST = 1.0 (map.rs:108-109)
+                if (prob == 0.5) {
+                    term = log(1.0 / 1.0);
+                } else {
+                    term = log(__dadd_rn(__dmul_rn(0.9, prob), (1.0 - 0.9) * 1.0 / 1.0));
+                }
+            }
+        }
+        s_terms[b] = term;
+    }
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        // LogProbability product = running sum in beam order (math.rs:96-100); beams that
+        // contribute nothing hold +0.0, which leaves the sum unchanged.
+        double lp = log(1.0);
+        for (uint32_t b = 0; b < scan.n_beams; ++b) lp = __dadd_rn(lp, s_terms[b]);
+        // Odometry::probabiliy_of, robot.rs:152-167
+        const float dx = __fsub_rn(ox, nx), dy = __fsub_rn(oy, ny);
+        const float center_distance = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        const double ad = angle_diff((double)otheta, (double)ntheta);
+        const double motion = __dadd_rn(log(normal_pdf((double)center_distance, od.mean_c, od.std_c)),
+                                        log(normal_pdf(ad, od.mean_t, od.std_t)));
+        ParticleResult r;
+        r.weight = exp(__dadd_rn(lp, motion));  // weight.prob().value(), slam.rs:71
+        r.x = nx; r.y = ny; r.theta = ntheta;
+        r.slot = slot_of[p];                    // physical slot, read by other ranks' planners
+        results[gp] = r;
+    }
+}
+
+void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
+                              const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
+                              size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
+                              uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step) {
+    const size_t smem = (size_t)scan.n_beams * sizeof(double);
+    k_motion_likelihood<<<n_local, ML_THREADS, smem, stream>>>(geom, od, scan, pose_cur, slot_of, cells,
+                                                              cells_per_grid, results, first_particle, z_draws, seed,
+                                                              step);
+}
+
+// =============================================================================== k_ray_update
+
+constexpr int RAY_MAX_SMEM = 220 * 1024;  // window budget; the HW limit is 227 KB per CTA
+
+// saturating packed add straight to global memory, for the (rare) cells outside the window
+__device__ __forceinline__ void global_cell_add(uint32_t* addr, uint32_t inc, bool* saturated) {
+    uint32_t old = *addr;
+    for (;;) {
+        const uint32_t nv = cell_sat_add(old, inc, saturated);
+        if (nv == old) return;
+        const uint32_t seen = atomicCAS(addr, old, nv);
+        if (seen == old) return;
+        old = seen;
+    }
+}
+
+constexpr int RAY_MAX_THREADS = 512;
+
+template <bool kVector>
+__global__ void __launch_bounds__(RAY_MAX_THREADS)
+k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
+             const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, size_t cells_per_grid, int radius,
+             StepCounters* counters) {
+    extern __shared__ __align__(16) uint32_t s_win[];
+    const uint32_t p = blockIdx.x;
+    const ParticleResult r = results[first_particle + p];
+    const float px = r.x, py = r.y, ptheta = r.theta;
+    uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
+
+    // Map::integrate, map.rs:71-73: ray start in grid coordinates
+    const float sx = world_to_grid(px, geom.pos_x, geom.res);
+    const float sy = world_to_grid(py, geom.pos_y, geom.res);
+    const long long cx = f32_as_isize(floorf(sx)), cy = f32_as_isize(floorf(sy));
+    // every ray starts in the same cell; outside the grid nothing is emitted (ray.rs:88-92)
+    if (cx < 0 || cx >= (long long)geom.gw || cy < 0 || cy >= (long long)geom.gh) return;
+
+    // shared-memory window around the start cell, clipped to the grid; x-range aligned to 4 cells
+    int wx0 = max(0, (int)cx - radius), wx1 = min((int)geom.gw, (int)cx + radius + 1);
+    const int wy0 = max(0, (int)cy - radius), wy1 = min((int)geom.gh, (int)cy + radius + 1);
+    if (kVector) {
+        wx0 &= ~3;
+        wx1 = min((int)geom.gw, (wx1 + 3) & ~3);
+    }
+    const int ww = wx1 - wx0, wh = wy1 - wy0;
+    const int wcells = ww * wh;
+
+    for (int i = threadIdx.x; i < wcells; i += blockDim.x) s_win[i] = 0u;
+    __syncthreads();
+
+    bool saturated = false;
+    uint32_t spilled = 0;
+    for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
+        const float dist = scan.dist[b];
+        float ex, ey;
+        beam_endpoint(px, py, ptheta, scan.angle[b], dist, &ex, &ey);
+        const float gx = world_to_grid(ex, geom.pos_x, geom.res);
+        const float gy = world_to_grid(ey, geom.pos_y, geom.res);
+        const float measured = __fdiv_rn(dist, geom.res);  // map.rs:84
+        const bool hit = scan.valid[b] != 0;
+        // apply_measurement, map.rs:88-106 (additional_steps = 2)
+        ray_walk(sx, sy, gx, gy, geom.gw, geom.gh, 2u, [&](int x, int y) {
+            const float d = start_to_cell_distance(sx, sy, x, y);
+            const uint32_t inc = inverse_sensor_increment(d, measured, hit);
+            if (inc != 0u) {
+                const int lx = x - wx0, ly = y - wy0;
+                if ((unsigned)lx < (unsigned)ww && (unsigned)ly < (unsigned)wh) {
+                    atomicAdd(&s_win[ly * ww + lx], inc);
+                } else {
+                    global_cell_add(&grid[(size_t)y * geom.gh + x], inc, &saturated);
+                    spilled++;
+                }
+            }
+        });
+    }
+    __syncthreads();
+
+    // write-back: grid += window, saturating per 16-bit counter, skipping untouched groups
+    if (kVector) {
+        const int ww4 = ww >> 2;
+        const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
+        for (int i = threadIdx.x; i < ww4 * wh; i += blockDim.x) {
+            const uint4 d = win4[i];
+            if ((d.x | d.y | d.z | d.w) != 0u) {
+                const int row = i / ww4, c4 = i - row * ww4;
+                uint4* g = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + row) * geom.gh + wx0) + c4;
+                uint4 v = *g;
+                v.x = cell_sat_add(v.x, d.x, &saturated);
+                v.y = cell_sat_add(v.y, d.y, &saturated);
+                v.z = cell_sat_add(v.z, d.z, &saturated);
+                v.w = cell_sat_add(v.w, d.w, &saturated);
+                *g = v;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < wcells; i += blockDim.x) {
+            const uint32_t d = s_win[i];
+            if (d != 0u) {
+                const int row = i / ww, c = i - row * ww;
+                uint32_t* g = grid + (size_t)(wy0 + row) * geom.gh + wx0 + c;
+                *g = cell_sat_add(*g, d, &saturated);
+            }
+        }
+    }
+    if (saturated) atomicAdd(&counters->saturated, 1ull);
+    if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
+}
+
+cudaError_t configure_kernels() {
+    // per-device opt-in to the large dynamic shared-memory window
+    cudaError_t e = cudaFuncSetAttribute(k_ray_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_ray_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
+}
+
+cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
+                              uint32_t first_particle, uint32_t n_local, const int32_t* slot_of, uint32_t* cells,
+                              size_t cells_per_grid, int radius_cells, StepCounters* counters,
+                              uint64_t* window_cells) {
+    // largest radius whose (aligned) window fits the budget: (2R+1+6) * (2R+1) * 4 bytes
+    int radius = radius_cells < 1 ? 1 : radius_cells;
+    while ((size_t)(2 * radius + 7) * (size_t)(2 * radius + 1) * 4 > (size_t)RAY_MAX_SMEM) radius--;
+    const size_t wmax = (size_t)min(2 * radius + 7, (int)geom.gw) * (size_t)min(2 * radius + 1, (int)geom.gh);
+    const size_t smem = wmax * 4;
+    *window_cells = wmax;
+    int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
+    threads = threads < 128 ? 128 : (threads > RAY_MAX_THREADS ? RAY_MAX_THREADS : threads);
+    const bool vec = (geom.gw % 4u == 0u) && (cells_per_grid % 4u == 0u);
+    if (vec)
+        k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, slot_of, cells,
+                                                               cells_per_grid, radius, counters);
+    else
+        k_ray_update<false><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, slot_of, cells,
+                                                                cells_per_grid, radius, counters);
+    return cudaSuccess;
+}
+
+// =============================================================================== k_weights
+
+constexpr int W_THREADS = 1024;
+
+__global__ void __launch_bounds__(W_THREADS)
+k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __restrict__ w_norm,
+          double* __restrict__ cum, StepCounters* counters) {
+    __shared__ double s_warp[33];
+    __shared__ long long s_key[32];
+    __shared__ uint32_t s_arg[32];
+    const uint32_t chunk = (n + W_THREADS - 1) / W_THREADS;
+    const uint32_t lo = min(n, threadIdx.x * chunk), hi = min(n, lo + chunk);
+
+    // normalize_weights, particle.rs:49-56: sum, then divide. Each thread folds a contiguous
+    // chunk left to right, chunk sums are combined by a fixed shuffle tree.
+    double part = 0.0;
+    for (uint32_t i = lo; i < hi; ++i) part = __dadd_rn(part, results[i].weight);
+    double sum;
+    block_excl_scan_f64(part, s_warp, &sum);
+
+    double npart = 0.0;
+    long long best_key = (long long)0x8000000000000000ull;
+    uint32_t best_i = 0;
+    bool have = false;
+    for (uint32_t i = lo; i < hi; ++i) {
+        const double w = __ddiv_rn(results[i].weight, sum);
+        w_norm[i] = w;
+        npart = __dadd_rn(npart, w);
+        const long long k = total_order_key(w);
+        if (!have || k >= best_key) { best_key = k; best_i = i; have = true; }  // last max wins
+    }
+    // running sum of the normalised weights (the `c += weight[i]` of particle.rs:85-91)
+    double ntotal;
+    const double offset = block_excl_scan_f64(npart, s_warp, &ntotal);
+    double c = offset;
+    for (uint32_t i = lo; i < hi; ++i) {
+        c = __dadd_rn(c, w_norm[i]);
+        cum[i] = c;
+    }
+
+    // argmax by f64::total_cmp, ties -> highest index (Iterator::max_by returns the last maximum)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (!have) { best_key = (long long)0x8000000000000000ull; best_i = 0; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long ok = __shfl_down_sync(0xffffffffu, best_key, o);
+        const uint32_t oi = __shfl_down_sync(0xffffffffu, best_i, o);
+        const bool ohave = __shfl_down_sync(0xffffffffu, (int)have, o) != 0;
+        if (ohave && (!have || ok > best_key || (ok == best_key && oi > best_i))) { best_key = ok; best_i = oi; have = true; }
+    }
+    if (lane == 0) { s_key[wid] = have ? best_key : (long long)0x8000000000000000ull; s_arg[wid] = have ? best_i : 0xffffffffu; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long bk = 0; uint32_t bi = 0; bool h = false;
+        for (int w = 0; w < W_THREADS / 32; ++w) {
+            if (s_arg[w] == 0xffffffffu) continue;
+            if (!h || s_key[w] > bk || (s_key[w] == bk && s_arg[w] > bi)) { bk = s_key[w]; bi = s_arg[w]; h = true; }
+        }
+        counters->max_particle = bi;
+        counters->sum = sum;
+        counters->clamped = 0ull;
+    }
+}
+
+void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
+                    double* cum, StepCounters* counters) {
+    k_weights<<<1, W_THREADS, 0, stream>>>(results, n_total, w_norm, cum, counters);
+}
+
+// =============================================================================== k_resample_indices
+
+__global__ void __launch_bounds__(256)
+k_resample_indices(const ParticleResult* __restrict__ results, const double* __restrict__ cum, uint32_t n,
+                   const double* __restrict__ u01_caller, uint64_t seed, uint64_t step, uint32_t* __restrict__ idx,
+                   float* __restrict__ pose_next, uint32_t first_particle, uint32_t n_local, StepCounters* counters) {
+    const uint32_t m0 = blockIdx.x * blockDim.x + threadIdx.x;  // zero-based new-particle index
+    if (m0 >= n) return;
+    // particle.rs:84: r = rand::random::<f64>() * 1.0 / N
+    const double U = u01_caller ? *u01_caller : slamrs_stream::resample_uniform(seed, step);
+    const double num = (double)n;
+    const double r = __ddiv_rn(__dmul_rn(U, 1.0), num);
+    // particle.rs:89: u = r + (m as f64 - 1.0) * 1.0 / N with m = m0 + 1
+    const double u = __dadd_rn(r, __ddiv_rn(__dmul_rn(__dsub_rn((double)(m0 + 1u), 1.0), 1.0), num));
+    // particle.rs:91-94: advance i while u > c. c is non-decreasing (weights >= 0), so the loop
+    // stops at the first i with !(u > cum[i]); found here by bisection.
+    uint32_t lo = 0, hi = n;  // answer in [lo, hi]; hi == n means "ran off the end"
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (u > cum[mid]) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= n) {  // the reference would index out of bounds and panic; clamp and flag
+        lo = n - 1;
+        atomicAdd(&counters->clamped, 1ull);
+    }
+    idx[m0] = lo;
+    const ParticleResult src = results[lo];
+    if (m0 >= first_particle && m0 < first_particle + n_local) {
+        float* q = pose_next + 3 * (size_t)(m0 - first_particle);
+        q[0] = src.x; q[1] = src.y; q[2] = src.theta;
+    }
+    // estimated_pose(), slam.rs:77-81: new generation indexed by the pre-resample argmax
+    if ((unsigned long long)m0 == counters->max_particle) {
+        counters->est_pose[0] = src.x; counters->est_pose[1] = src.y; counters->est_pose[2] = src.theta;
+    }
+}
+
+void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
+                             uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,
+                             uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
+                             StepCounters* counters) {
+    k_resample_indices<<<(n_total + 255) / 256, 256, 0, stream>>>(results, cum, n_total, u01_caller, seed, step, idx,
+                                                                 pose_next, first_particle, n_local, counters);
+}
+
+// =============================================================================== k_plan
+// Turns the (non-decreasing) index vector into work for this rank's output range [lo, lo+S):
+//   A  source is local and this is its first use here   -> the grid stays where it is
+//   B  source is local, further use                     -> copy from the kept grid into a free slot
+//   C  source lives on another GPU, first use here      -> pull it over NVLink into a free slot
+//   D  source lives on another GPU, further use         -> copy from the pulled grid
+// Free slots = slots of local particles nobody here keeps + the persistent spare slots. Slots whose
+// grid another GPU still has to pull ("unsafe") are handed out last and only to B/D copies, which
+// run after the cross-GPU barrier that follows the pulls.
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t lo, uint32_t hi, uint32_t v) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
+    __shared__ uint32_t s_warp[33];
+    const uint32_t S = a.n_local, lo = a.rank * a.n_local, hi = lo + S;
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    const uint32_t chunk = (S + T - 1) / T;
+    const uint32_t c0 = min(S, t * chunk), c1 = min(S, c0 + chunk);
+    const uint32_t E = (uint32_t)a.counters->n_spare;
+
+    for (uint32_t j = t; j < S; j += T) a.keep[j] = 0;
+    __syncthreads();
+
+    // ---- classify new particles
+    uint32_t nA = 0;
+    for (uint32_t m = t; m < S; m += T) {
+        const uint32_t src = a.idx[lo + m];
+        const bool first = (m == 0) || (a.idx[lo + m - 1] != src);
+        const bool local = (src >= lo && src < hi);
+        int cls;
+        if (local && first) {
+            cls = 0;
+            a.keep[src - lo] = 1;
+            a.slot_new[m] = a.slot_old[src - lo];
+        } else if (local) cls = 1;
+        else if (first) cls = 2;
+        else cls = 3;
+        a.need[m] = cls;
+        nA += (first ? 1u : 0u);
+    }
+    __syncthreads();
+
+    // ---- classify old slots: 0 = kept, 1 = free & safe, 2 = free but still read by another GPU
+    for (uint32_t j = t; j < S; j += T) {
+        int f = 0;
+        if (!a.keep[j]) {
+            f = 1;
+            if (a.world > 1) {
+                const uint32_t v = lo + j;
+                const uint32_t first = lower_bound_u32(a.idx, 0, a.n_total, v);
+                if (first < a.n_total && a.idx[first] == v) {
+                    const uint32_t last = lower_bound_u32(a.idx, first, a.n_total, v + 1) - 1;
+                    if (first < lo || last >= hi) f = 2;
+                }
+            }
+        }
+        a.keep[j] = f;
+    }
+    __syncthreads();
+
+    // ---- ordered compaction of the free slots: [safe | spare | unsafe]
+    uint32_t n_safe_c = 0, n_unsafe_c = 0;
+    for (uint32_t j = c0; j < c1; ++j) { n_safe_c += (a.keep[j] == 1); n_unsafe_c += (a.keep[j] == 2); }
+    uint32_t n_safe, n_unsafe;
+    uint32_t ps = block_excl_scan_u32(n_safe_c, s_warp, &n_safe);
+    uint32_t pu = block_excl_scan_u32(n_unsafe_c, s_warp, &n_unsafe);
+    for (uint32_t j = c0; j < c1; ++j) {
+        if (a.keep[j] == 1) a.free_list[ps++] = a.slot_old[j];
+        else if (a.keep[j] == 2) a.free_list[n_safe + E + pu++] = a.slot_old[j];
+    }
+    for (uint32_t e = t; e < E; e += T) a.free_list[n_safe + e] = a.spare_list[e];
+
+    // ---- ordered ranks of the consumers: pulls (C) first, then copies (B, D)
+    uint32_t nC_c = 0, nBD_c = 0;
+    for (uint32_t m = c0; m < c1; ++m) { nC_c += (a.need[m] == 2); nBD_c += (a.need[m] == 1 || a.need[m] == 3); }
+    uint32_t nC, nBD;
+    uint32_t pc = block_excl_scan_u32(nC_c, s_warp, &nC);
+    uint32_t pbd = block_excl_scan_u32(nBD_c, s_warp, &nBD);
+    __syncthreads();  // free_list complete
+
+    // pass 1: pulls and local duplicates (their sources are already in place)
+    const uint32_t pbd_start = pbd;
+    for (uint32_t m = c0; m < c1; ++m) {
+        const int cls = a.need[m];
+        if (cls == 2) {
+            const uint32_t src = a.idx[lo + m];
+            const uint32_t owner = src / S;
+            const int32_t sslot = a.results[src].slot;
+            const int32_t dslot = a.free_list[pc];
+            a.slot_new[m] = dslot;
+            CopyItem it;
+            it.src = a.peer_cells[owner] + (size_t)sslot * a.cells_per_grid;
+            it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
+            a.pulls[pc] = it;
+            pc++;
+        } else if (cls == 1) {
+            const uint32_t src = a.idx[lo + m];
+            const int32_t dslot = a.free_list[nC + pbd];
+            a.slot_new[m] = dslot;
+            CopyItem it;
+            it.src = a.cells + (size_t)a.slot_old[src - lo] * a.cells_per_grid;
+            it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
+            a.copies[pbd] = it;
+            pbd++;
+        } else if (cls == 3) {
+            pbd++;
+        }
+    }
+    __syncthreads();
+    // pass 2: duplicates of pulled grids (source = where the first use landed)
+    pbd = pbd_start;
+    for (uint32_t m = c0; m < c1; ++m) {
+        const int cls = a.need[m];
+        if (cls == 3) {
+            const uint32_t src = a.idx[lo + m];
+            const uint32_t m_first = lower_bound_u32(a.idx, lo, hi, src) - lo;
+            const int32_t dslot = a.free_list[nC + pbd];
+            a.slot_new[m] = dslot;
+            CopyItem it;
+            it.src = a.cells + (size_t)a.slot_new[m_first] * a.cells_per_grid;
+            it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
+            a.copies[pbd] = it;
+            pbd++;
+        } else if (cls == 1) {
+            pbd++;
+        }
+    }
+    __syncthreads();
+    // ---- the E slots nobody took become the next step's spare list
+    for (uint32_t e = t; e < E; e += T) a.spare_list[e] = a.free_list[nC + nBD + e];
+
+    uint32_t distinct;
+    block_excl_scan_u32(nA, s_warp, &distinct);
+    if (t == 0) {
+        a.counters->n_copies = nBD;
+        a.counters->n_pulls = nC;
+        a.counters->distinct = distinct;
+        a.counters->staging_short = (nC > n_safe + E) ? (unsigned long long)(nC - (n_safe + E)) : 0ull;
+        const unsigned long long mp = a.counters->max_particle;
+        a.counters->est_owner = mp / S;
+        a.counters->est_slot = (mp >= lo && mp < hi) ? (long long)a.slot_new[mp - lo] : -1ll;
+    }
+}
+
+void launch_plan(cudaStream_t stream, const PlanArgs& a) { k_plan<<<1, 1024, 0, stream>>>(a); }
+
+// =============================================================================== k_copy
+// Full-grid copies (the `value.clone()` of particle.rs:97-100). Pure streaming: 128-bit loads
+// that bypass L1, four in flight per thread before the first store. One work item = 16 KiB of
+// one grid; CTAs stride over the item list, whose length is read from device memory so that
+// no host round trip sits between planning and copying.
+
+constexpr int COPY_THREADS = 256;
+constexpr int COPY_UNROLL = 4;
+constexpr uint32_t COPY_ITEM_V4 = COPY_THREADS * COPY_UNROLL;  // uint4 per work item (16 KiB)
+
+__global__ void __launch_bounds__(COPY_THREADS)
+k_copy(const CopyItem* __restrict__ items, const unsigned long long* __restrict__ n_items, uint32_t v4_per_grid) {
+    const unsigned long long n = *n_items;
+    const uint32_t chunks = (v4_per_grid + COPY_ITEM_V4 - 1) / COPY_ITEM_V4;
+    const unsigned long long total = n * chunks;
+    for (unsigned long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const unsigned long long j = w / chunks;
+        const uint32_t c = (uint32_t)(w - j * chunks);
+        const CopyItem it = items[j];
+        const uint4* src = reinterpret_cast<const uint4*>(it.src);
+        uint4* dst = reinterpret_cast<uint4*>(it.dst);
+        const uint32_t base = c * COPY_ITEM_V4 + threadIdx.x;
+        uint4 v[COPY_UNROLL];
+#pragma unroll
+        for (int k = 0; k < COPY_UNROLL; ++k) {
+            const uint32_t i = base + k * COPY_THREADS;
+            if (i < v4_per_grid) v[k] = ld_stream_v4(src + i);
+        }
+#pragma unroll
+        for (int k = 0; k < COPY_UNROLL; ++k) {
+            const uint32_t i = base + k * COPY_THREADS;
+            if (i < v4_per_grid) st_stream_v4(dst + i, v[k]);
+        }
+    }
+}
+
+void launch_copy(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items,
+                 size_t cells_per_grid, int num_sms) {
+    const uint32_t v4 = (uint32_t)(cells_per_grid / 4);
+    k_copy<<<num_sms * 8, COPY_THREADS, 0, stream>>>(items, n_items, v4);
+}
+
+// =============================================================================== k_export
+
+__global__ void __launch_bounds__(256)
+k_export(const uint32_t* __restrict__ cells, size_t cells_per_grid, const StepCounters* __restrict__ counters,
+         uint32_t n_cells, double* __restrict__ out) {
+    const long long slot = counters->est_slot;
+    if (slot < 0) return;  // another GPU owns the estimate
+    const uint32_t* grid = cells + (size_t)slot * cells_per_grid;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += gridDim.x * blockDim.x)
+        out[i] = log_odds_probability(cell_log_odds(grid[i]));  // Map::likelihood, map.rs:50-52
+}
+
+void launch_export(cudaStream_t stream, const uint32_t* cells, size_t cells_per_grid, const StepCounters* counters,
+                   uint32_t n_cells, double* out) {
+    const int blocks = (int)min((n_cells + 255u) / 256u, 148u * 8u);
+    k_export<<<blocks, 256, 0, stream>>>(cells, cells_per_grid, counters, n_cells, out);
+}
+
+__global__ void __launch_bounds__(256)
+k_export_log_odds(const uint32_t* __restrict__ grid, uint32_t n_cells, double* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += gridDim.x * blockDim.x)
+        out[i] = cell_log_odds(grid[i]);
+}
+void launch_export_log_odds(cudaStream_t stream, const uint32_t* grid, uint32_t n_cells, double* out) {
+    const int blocks = (int)min((n_cells + 255u) / 256u, 148u * 8u);
+    k_export_log_odds<<<blocks, 256, 0, stream>>>(grid, n_cells, out);
+}
+
+// =============================================================================== init
+
+__global__ void k_init_slots(int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
+                             StepCounters* counters, uint32_t rank) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_local) slot_of[i] = (int32_t)i;
+    if (i < n_spare) spare_list[i] = (int32_t)(n_local + i);
+    if (i == 0) {
+        StepCounters c;
+        memset(&c, 0, sizeof(c));
+        c.est_slot = rank == 0 ? 0 : -1;  // before the first update: particle 0 (max_particle = 0, particle.rs:26)
+        c.n_spare = n_spare;
+        *counters = c;
+    }
+}
+void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
+                       StepCounters* counters, uint32_t rank) {
+    const uint32_t n = n_local > n_spare ? n_local : n_spare;
+    k_init_slots<<<(n + 255) / 256, 256, 0, stream>>>(slot_of, n_local, spare_list, n_spare, counters, rank);
+}
+
+// =============================================================================== test hooks
+
+__global__ void k_debug_raycast(const float* x0, const float* y0, const float* x1, const float* y1, uint32_t n_rays,
+                                uint32_t gw, uint32_t gh, uint32_t extra, int32_t* out_xy, uint32_t cap,
+                                uint32_t* out_count) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    uint32_t count = 0;
+    int32_t* o = out_xy + (size_t)r * cap * 2;
+    ray_walk(x0[r], y0[r], x1[r], y1[r], gw, gh, extra, [&](int x, int y) {
+        if (count < cap) { o[2 * count] = x; o[2 * count + 1] = y; }
+        count++;
+    });
+    out_count[r] = count;
+}
+void launch_debug_raycast(cudaStream_t stream, const float* x0, const float* y0, const float* x1, const float* y1,
+                          uint32_t n_rays, uint32_t gw, uint32_t gh, uint32_t extra, int32_t* out_xy, uint32_t cap,
+                          uint32_t* out_count) {
+    k_debug_raycast<<<(n_rays + 127) / 128, 128, 0, stream>>>(x0, y0, x1, y1, n_rays, gw, gh, extra, out_xy, cap,
+                                                             out_count);
+}
+
+__global__ void k_debug_sincos(const float* x, uint32_t n, float* s, float* c) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    s[i] = slamrs_libm::sinf_exact(x[i]);
+    c[i] = slamrs_libm::cosf_exact(x[i]);
+}
+void launch_debug_sincos(cudaStream_t stream, const float* x, uint32_t n, float* s, float* c) {
+    k_debug_sincos<<<(n + 255) / 256, 256, 0, stream>>>(x, n, s, c);
+}
+
+__global__ void k_debug_stream(uint64_t seed, uint64_t step, uint64_t first, uint64_t count, double* z, double* u) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) slamrs_stream::motion_normals(seed, step, (uint32_t)(first + i), &z[2 * i], &z[2 * i + 1]);
+    if (i == 0) *u = slamrs_stream::resample_uniform(seed, step);
+}
+void launch_debug_stream(cudaStream_t stream, uint64_t seed, uint64_t step, uint64_t first, uint64_t count, double* z,
+                         double* u) {
+    const uint64_t n = count ? count : 1;
+    k_debug_stream<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seed, step, first, count, z, u);
+}
+
+}  // namespace slamrs

@@ -1,0 +1,108 @@
+// Kernel parameter blocks and launch wrappers of the SLAM step (definitions in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "slam_device.cuh"
+
+namespace slamrs {
+
+// Result of the per-particle motion + likelihood pass, one record per particle of the WHOLE
+// population (each rank fills its shard; an all-gather completes the array on every GPU).
+struct alignas(8) ParticleResult {
+    double weight;        // exp(log p(z|x,m) + log p(x'|x,u)), un-normalised (slam.rs:62,71)
+    float x, y, theta;    // pose sampled from the motion model (robot.rs:170-183)
+    int32_t slot;         // physical grid slot on the owning GPU (read by other ranks' planners)
+};
+static_assert(sizeof(ParticleResult) == 24, "ParticleResult is exchanged between GPUs as 24 bytes");
+
+// Device-resident step state shared by the resampling kernels.
+struct StepCounters {
+    unsigned long long max_particle;     // argmax of the normalised weights, last max wins (particle.rs:40-46)
+    unsigned long long n_copies;         // local duplicate copies planned this step
+    unsigned long long n_pulls;          // remote grids to pull this step
+    unsigned long long distinct;         // distinct sources feeding this rank's new generation
+    unsigned long long clamped;          // resample index clamped to N-1
+    unsigned long long saturated;        // cells that hit the u16 ceiling this step
+    unsigned long long spilled;          // ray cell-steps outside the shared-memory window
+    unsigned long long staging_short;    // free slots missing for cross-GPU pulls (error)
+    long long est_slot;                  // physical slot of new-generation particle max_particle, -1 if remote
+    unsigned long long est_owner;        // rank that owns it
+    unsigned long long n_spare;          // entries of the persistent spare-slot list
+    double sum;                          // sum of raw weights (particle.rs:50)
+    float est_pose[3];                   // estimated_pose(), slam.rs:77-81
+    float pad;
+};
+
+struct ScanDevice {
+    const float* angle;
+    const float* dist;
+    const uint8_t* valid;
+    uint32_t n_beams;
+};
+
+struct CopyItem {
+    const uint32_t* src;  // may be a peer-mapped pointer (grid on another GPU)
+    uint32_t* dst;
+};
+
+// ---- launch wrappers (all asynchronous on `stream`) ----
+void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
+                              const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
+                              size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
+                              uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step);
+
+// returns the shared-memory window size in cells through *window_cells
+cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
+                              uint32_t first_particle, uint32_t n_local, const int32_t* slot_of, uint32_t* cells,
+                              size_t cells_per_grid, int radius_cells, StepCounters* counters,
+                              uint64_t* window_cells);
+
+void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
+                    double* cum, StepCounters* counters);
+
+void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
+                             uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,
+                             uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
+                             StepCounters* counters);
+
+struct PlanArgs {
+    const ParticleResult* results;  // N, after the all-gather (carries every particle's physical slot)
+    const uint32_t* idx;       // N resample sources
+    uint32_t n_total, n_local, rank, world;
+    const int32_t* slot_old;   // n_local
+    int32_t* slot_new;         // n_local
+    int32_t* keep;             // n_local scratch
+    int32_t* need;             // n_local scratch
+    int32_t* free_list;        // n_local + n_spare_cap scratch
+    int32_t* spare_list;       // persistent list of free physical slots beyond the live set
+    uint32_t n_spare_cap;
+    CopyItem* copies;          // n_local
+    CopyItem* pulls;           // n_local
+    uint32_t* cells;           // local pool base
+    size_t cells_per_grid;
+    uint32_t* const* peer_cells;        // world pointers to each rank's pool (device array), may be null when world==1
+    StepCounters* counters;
+};
+void launch_plan(cudaStream_t stream, const PlanArgs& a);
+
+// copies[0..*n_items) full grids; n_items is read on the device
+void launch_copy(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items,
+                 size_t cells_per_grid, int num_sms);
+
+void launch_export(cudaStream_t stream, const uint32_t* cells, size_t cells_per_grid, const StepCounters* counters,
+                   uint32_t n_cells, double* out);
+void launch_export_log_odds(cudaStream_t stream, const uint32_t* grid, uint32_t n_cells, double* out);
+
+void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
+                       StepCounters* counters, uint32_t rank);
+cudaError_t configure_kernels();  // per-device function attributes; call once after cudaSetDevice
+
+// test hooks
+void launch_debug_raycast(cudaStream_t stream, const float* x0, const float* y0, const float* x1, const float* y1,
+                          uint32_t n_rays, uint32_t gw, uint32_t gh, uint32_t extra, int32_t* out_xy, uint32_t cap,
+                          uint32_t* out_count);
+void launch_debug_sincos(cudaStream_t stream, const float* x, uint32_t n, float* s, float* c);
+void launch_debug_stream(cudaStream_t stream, uint64_t seed, uint64_t step, uint64_t first, uint64_t count, double* z,
+                         double* u);
+
+}  // namespace slamrs

@@ -1,0 +1,188 @@
+// Device-side arithmetic of the grid SLAM step. Every f32 operation that decides a cell index
+// is an explicit round-to-nearest intrinsic so that nvcc can never contract a*b+c into an FMA
+// (rustc does not contract); f32 division and sqrt are the IEEE-rounded forms.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "libm_f32.cuh"
+
+namespace slamrs {
+
+// ---------------------------------------------------------------------------- cell format
+// One grid cell = packed hit counters: bits 0..15 = number of P_FREE updates, bits 16..31 =
+// number of P_OCCUPPIED updates (P_PRIOR adds ln(1) = 0 and is dropped). The reference stores an
+// f64 log-odds sum of the same three constants (slamrs/slam/src/grid/map.rs:154-156,
+// common/src/math.rs:30-32), so the integer pair is an exact, order-independent encoding.
+constexpr uint32_t CELL_FREE_INC = 1u;
+constexpr uint32_t CELL_OCC_INC = 0x10000u;
+// Probability(0.30).log_odds() and Probability(0.9).log_odds(), math.rs:30-32, in binary64
+#define SLAMRS_L_FREE (-0.8472978603872036)
+#define SLAMRS_L_OCC (2.1972245773362196)
+
+__device__ __forceinline__ double cell_log_odds(uint32_t cell) {
+    const double nf = (double)(cell & 0xffffu);
+    const double no = (double)(cell >> 16);
+    return __dadd_rn(__dmul_rn(nf, SLAMRS_L_FREE), __dmul_rn(no, SLAMRS_L_OCC));
+}
+// LogOdds::probability, math.rs:135-137
+__device__ __forceinline__ double log_odds_probability(double l) { return 1.0 - 1.0 / (1.0 + exp(l)); }
+
+__device__ __forceinline__ uint32_t cell_sat_add(uint32_t cell, uint32_t delta, bool* saturated) {
+    uint32_t lo = (cell & 0xffffu) + (delta & 0xffffu);
+    uint32_t hi = (cell >> 16) + (delta >> 16);
+    if (lo > 0xffffu) { lo = 0xffffu; *saturated = true; }
+    if (hi > 0xffffu) { hi = 0xffffu; *saturated = true; }
+    return lo | (hi << 16);
+}
+
+// ---------------------------------------------------------------------------- Rust casts
+// `f32 as usize` (saturating, NaN -> 0); only called for v >= 0 or NaN in the reference flow
+__device__ __forceinline__ unsigned long long f32_as_usize(float v) {
+    if (!(v == v)) return 0ull;
+    if (v <= 0.0f) return 0ull;
+    if (v >= 18446744073709551616.0f) return ~0ull;
+    return (unsigned long long)v;
+}
+// `f32 as isize` (saturating, NaN -> 0)
+__device__ __forceinline__ long long f32_as_isize(float v) {
+    if (!(v == v)) return 0ll;
+    if (v >= 9223372036854775808.0f) return 0x7fffffffffffffffll;
+    if (v <= -9223372036854775808.0f) return (long long)0x8000000000000000ull;
+    return (long long)v;
+}
+
+// ---------------------------------------------------------------------------- geometry
+struct MapGeom {
+    float pos_x, pos_y, res;
+    uint32_t gw, gh;
+};
+
+// Map::world_to_grid, map.rs:60-62
+__device__ __forceinline__ float world_to_grid(float w, float pos, float res) {
+    return __fdiv_rn(__fsub_rn(w, pos), res);
+}
+// Map::is_valid, map.rs:64-69
+__device__ __forceinline__ bool grid_is_valid(float gx, float gy, uint32_t gw, uint32_t gh) {
+    return !((gx < 0.0f) || (gy < 0.0f) || (f32_as_usize(gx) >= (unsigned long long)gw) ||
+             (f32_as_usize(gy) >= (unsigned long long)gh));
+}
+
+// beam endpoint in world coordinates, map.rs:75-78 / 120-123
+__device__ __forceinline__ void beam_endpoint(float px, float py, float ptheta, float angle, float dist, float* ex,
+                                              float* ey) {
+    const float a = __fadd_rn(ptheta, angle);
+    *ex = __fadd_rn(px, __fmul_rn(slamrs_libm::cosf_exact(a), dist));
+    *ey = __fadd_rn(py, __fmul_rn(slamrs_libm::sinf_exact(a), dist));
+}
+
+// inverse_sensor_model, map.rs:148-172 with tolerance 2.0 (map.rs:104).
+// returns the packed counter increment: 0 (prior), CELL_FREE_INC or CELL_OCC_INC
+__device__ __forceinline__ uint32_t inverse_sensor_increment(float distance, float measured, bool was_hit) {
+    if (!was_hit) return (distance < measured) ? CELL_FREE_INC : 0u;
+    const float half_tol = __fdiv_rn(2.0f, 2.0f);
+    if (distance < __fsub_rn(measured, half_tol)) return CELL_FREE_INC;
+    if (distance > __fadd_rn(measured, half_tol)) return 0u;
+    return CELL_OCC_INC;
+}
+
+// ---------------------------------------------------------------------------- ray iterator
+// GridRayIterator::new + next, slamrs/slam/src/grid/ray.rs:21-77, 83-110.
+// `visit(x, y)` is called for every emitted cell, in order. The running `error` term is a
+// sequential f32 accumulation and must not be re-associated.
+template <typename Visit>
+__device__ __forceinline__ void ray_walk(float x0, float y0, float x1, float y1, uint32_t size_x, uint32_t size_y,
+                                         uint32_t additional_steps, Visit&& visit) {
+    const float delta_x = fabsf(__fsub_rn(x1, x0));
+    const float delta_y = fabsf(__fsub_rn(y1, y0));
+    const float fx0 = floorf(x0), fy0 = floorf(y0);
+    const long long sx = f32_as_isize(fx0);
+    const long long sy = f32_as_isize(fy0);
+    // A start outside the grid emits nothing (ray.rs:88-92 fails on the first call).
+    if (sx < 0 || sx >= (long long)size_x || sy < 0 || sy >= (long long)size_y) return;
+
+    unsigned long long n = 1ull + additional_steps;  // wrapping isize arithmetic, then `as usize`
+    int x_inc, y_inc;
+    float error;
+    if (delta_x == 0.0f) {
+        x_inc = 0;
+        error = __int_as_float(0x7f800000);
+    } else if (x1 > x0) {
+        x_inc = 1;
+        n += (unsigned long long)f32_as_isize(__fsub_rn(floorf(x1), (float)sx));
+        error = __fmul_rn(__fsub_rn(__fadd_rn(fx0, 1.0f), x0), delta_y);
+    } else {
+        x_inc = -1;
+        n += (unsigned long long)sx - (unsigned long long)f32_as_isize(floorf(x1));
+        error = __fmul_rn(__fsub_rn(x0, fx0), delta_y);
+    }
+    if (delta_y == 0.0f) {
+        y_inc = 0;
+        error = __fsub_rn(error, __int_as_float(0x7f800000));
+    } else if (y1 > y0) {
+        y_inc = 1;
+        n += (unsigned long long)f32_as_isize(floorf(y1)) - (unsigned long long)sy;
+        error = __fsub_rn(error, __fmul_rn(__fsub_rn(__fadd_rn(fy0, 1.0f), y0), delta_x));
+    } else {
+        y_inc = -1;
+        n += (unsigned long long)sy - (unsigned long long)f32_as_isize(floorf(y1));
+        error = __fsub_rn(error, __fmul_rn(__fsub_rn(y0, fy0), delta_x));
+    }
+    // The walk stops at the first cell outside the grid, and a step that cannot move
+    // (increment 0 on the chosen axis) only happens with n <= 3 + size_y, so
+    // size_x + size_y + 8 bounds the trip count without changing the emitted sequence.
+    const unsigned long long cap = (unsigned long long)size_x + size_y + 8ull;
+    int remaining = (int)(n < cap ? n : cap);
+    int x = (int)sx, y = (int)sy;
+    while (remaining > 0 && !(x < 0 || x >= (int)size_x || y < 0 || y >= (int)size_y)) {
+        visit(x, y);
+        if (error > 0.0f) {
+            y += y_inc;
+            error = __fsub_rn(error, delta_x);
+        } else {
+            x += x_inc;
+            error = __fadd_rn(error, delta_y);
+        }
+        remaining -= 1;
+    }
+}
+
+// distance from the ray start to a cell centre: nalgebra EuclideanNorm::metric_distance,
+// a left fold from 0 of squared differences, then sqrt (map.rs:100)
+__device__ __forceinline__ float start_to_cell_distance(float sx, float sy, int x, int y) {
+    const float cx = __fadd_rn((float)x, 0.5f);
+    const float cy = __fadd_rn((float)y, 0.5f);
+    const float dx = __fsub_rn(sx, cx);
+    const float dy = __fsub_rn(sy, cy);
+    float acc = __fadd_rn(0.0f, __fmul_rn(dx, dx));
+    acc = __fadd_rn(acc, __fmul_rn(dy, dy));
+    return __fsqrt_rn(acc);
+}
+
+// ---------------------------------------------------------------------------- motion model
+struct OdomModel {  // Odometry::new, robot.rs:132-150
+    double mean_c, std_c, mean_t, std_t;
+};
+
+// statrs 0.18 Normal::pdf: exp(-0.5 d d) / (sqrt(2 pi) sigma), d = (x - mean) / sigma
+__device__ __forceinline__ double normal_pdf(double x, double mean, double sd) {
+    const double SQRT_2PI = 2.5066282746310005024157652848110452530069867406099;
+    const double d = __ddiv_rn(__dsub_rn(x, mean), sd);
+    return __ddiv_rn(exp(__dmul_rn(__dmul_rn(-0.5, d), d)), __dmul_rn(SQRT_2PI, sd));
+}
+
+// angle_diff, common/src/math.rs:150-157 (Rust % on f64 == fmod)
+__device__ __forceinline__ double angle_diff(double alpha, double beta) {
+    const double PI = 3.14159265358979323846264338327950288;
+    const double diff = __dsub_rn(fmod(__dadd_rn(__dsub_rn(beta, alpha), PI), __dmul_rn(PI, 2.0)), PI);
+    if (diff < -PI) return __dadd_rn(diff, __dmul_rn(2.0, PI));
+    return diff;
+}
+
+// f64::total_cmp key: monotone map from the IEEE bit pattern to a signed integer
+__device__ __forceinline__ long long total_order_key(double v) {
+    long long b = __double_as_longlong(v);
+    b ^= (long long)(((unsigned long long)(b >> 63)) >> 1);
+    return b;
+}
+
+}  // namespace slamrs

