@@ -124,6 +124,11 @@ int slamrs_gpu_upload_scan(slamrs_gpu_handle* h, const float* angle, const float
 int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_right, float wheel_dist,
                           const double* z_draws, const double* resample_u);
 int slamrs_gpu_sync(slamrs_gpu_handle* h);
+/* Use an observation that already lives in device memory (caller-owned, must stay valid until
+ * the steps that use it have completed). max_dist = largest finite distance in the scan (sizes
+ * the ray kernel's shared-memory window; correctness does not depend on it). */
+int slamrs_gpu_set_scan_device(slamrs_gpu_handle* h, const float* angle_device, const float* dist_device,
+                               const uint8_t* valid_device, uint32_t n_beams, float max_dist);
 
 /* GridMapSlam::estimated_pose, slam.rs:77-81 -> {x, y, theta}. Reproduces the reference's
  * indexing: particle `max_particle` (argmax BEFORE resampling) of the NEW generation. */
@@ -142,6 +147,24 @@ int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out);
 void* slamrs_gpu_stream(slamrs_gpu_handle* h);
 /* number of kernels this handle has launched since create */
 uint64_t slamrs_gpu_launch_count(const slamrs_gpu_handle* h);
+
+/* Per-phase device timing (CUDA events on the handle's stream). enable, run steps, then read:
+ * out_ms[SLAMRS_PHASE_COUNT] = summed milliseconds per phase, *out_steps = steps covered.
+ * Reading synchronises the stream and resets the accumulation. */
+enum slamrs_phase {
+    SLAMRS_PHASE_MOTION_LIKELIHOOD = 0,
+    SLAMRS_PHASE_RAY_UPDATE = 1,
+    SLAMRS_PHASE_ALL_GATHER = 2,
+    SLAMRS_PHASE_RESAMPLE = 3, /* weights + indices + plan */
+    SLAMRS_PHASE_PULL = 4,     /* NVLink grid pulls + cross-GPU barrier */
+    SLAMRS_PHASE_COPY = 5,     /* local grid copies */
+    SLAMRS_PHASE_COUNT = 6
+};
+int slamrs_gpu_set_profiling(slamrs_gpu_handle* h, int enabled);
+int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COUNT], uint64_t* out_steps);
+/* Per-step history (ring of the last 256 steps): for step indices first_step .. first_step+count-1
+ * writes {grids_copied, grids_pulled, distinct_sources} triples. */
+int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_triples);
 
 /* current generation, this rank's shard: n_local * {x, y, theta} */
 int slamrs_gpu_get_poses(slamrs_gpu_handle* h, float* out_xyt);

@@ -22,7 +22,10 @@ EXPORTS = [
     "slamrs_gpu_get_weights", "slamrs_gpu_get_resample_indices", "slamrs_gpu_get_max_particle",
     "slamrs_gpu_get_cells", "slamrs_gpu_set_cells", "slamrs_gpu_get_log_odds",
     "slamrs_gpu_debug_raycast", "slamrs_gpu_debug_sincos", "slamrs_gpu_debug_stream",
+    "slamrs_gpu_set_scan_device", "slamrs_gpu_set_profiling", "slamrs_gpu_get_phase_ms",
+    "slamrs_gpu_get_step_history",
 ]
+PHASES = ["motion_likelihood", "ray_update", "all_gather", "resample", "pull", "copy"]
 
 
 class Config(C.Structure):
@@ -92,6 +95,10 @@ def load():
     L.slamrs_gpu_debug_raycast.argtypes = [i, vp, vp, vp, vp, u32, u32, u32, u32, vp, u32, vp]
     L.slamrs_gpu_debug_sincos.restype = i; L.slamrs_gpu_debug_sincos.argtypes = [i, vp, u32, vp, vp]
     L.slamrs_gpu_debug_stream.restype = i; L.slamrs_gpu_debug_stream.argtypes = [i, u64, u64, u64, u64, vp, vp]
+    L.slamrs_gpu_set_scan_device.restype = i; L.slamrs_gpu_set_scan_device.argtypes = [vp, vp, vp, vp, u32, f]
+    L.slamrs_gpu_set_profiling.restype = i; L.slamrs_gpu_set_profiling.argtypes = [vp, i]
+    L.slamrs_gpu_get_phase_ms.restype = i; L.slamrs_gpu_get_phase_ms.argtypes = [vp, vp, C.POINTER(u64)]
+    L.slamrs_gpu_get_step_history.restype = i; L.slamrs_gpu_get_step_history.argtypes = [vp, u64, u32, vp]
     _lib = L
     return L
 

@@ -54,6 +54,17 @@ struct slamrs_gpu_handle {
     Comm* comm = nullptr;
     uint32_t** d_peer_cells = nullptr;         // device array [world]
     std::vector<void*> ipc_opened;             // peer mappings to close
+    StepRecord* d_history = nullptr;
+    bool scan_external = false;
+    const float* ext_angle = nullptr;
+    const float* ext_dist = nullptr;
+    const uint8_t* ext_valid = nullptr;
+    // profiling: per step SLAMRS_PHASE_COUNT+1 boundary events
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // [PROF_RING][SLAMRS_PHASE_COUNT + 1]
+    uint32_t prof_recorded = 0;
+    double prof_ms[SLAMRS_PHASE_COUNT] = {0, 0, 0, 0, 0, 0};
+    uint64_t prof_steps = 0;
     uint64_t step = 0;
     uint64_t launches = 0;
     uint64_t window_cells = 0;
@@ -181,6 +192,9 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
     cudaFree(h->d_copies); cudaFree(h->d_pulls);
     cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells);
+    cudaFree(h->d_history);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    h->prof_events.clear();
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -199,6 +213,30 @@ int ensure_beam_capacity(slamrs_gpu_handle* h, uint32_t n) {
     h->beam_cap = cap;
     return SLAMRS_OK;
 }
+
+constexpr uint32_t PROF_RING = 64;
+constexpr uint32_t PROF_MARKS = SLAMRS_PHASE_COUNT + 1;
+
+int prof_flush(slamrs_gpu_handle* h) {
+    if (h->prof_recorded == 0) return SLAMRS_OK;
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    for (uint32_t r = 0; r < h->prof_recorded; ++r) {
+        for (int p = 0; p < SLAMRS_PHASE_COUNT; ++p) {
+            float ms = 0.f;
+            CU_TRY(h, cudaEventElapsedTime(&ms, h->prof_events[r * PROF_MARKS + p], h->prof_events[r * PROF_MARKS + p + 1]));
+            h->prof_ms[p] += ms;
+        }
+    }
+    h->prof_steps += h->prof_recorded;
+    h->prof_recorded = 0;
+    return SLAMRS_OK;
+}
+
+// records boundary mark `m` of the current step when profiling is on
+#define PROF_MARK(h, m)                                                                                   \
+    do {                                                                                                  \
+        if ((h)->profiling) CU_TRY(h, cudaEventRecord((h)->prof_events[(h)->prof_recorded * PROF_MARKS + (m)], (h)->stream)); \
+    } while (0)
 
 int fetch_counters(slamrs_gpu_handle* h) {
     CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(StepCounters), cudaMemcpyDeviceToHost, h->stream));
@@ -362,6 +400,8 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
     memset(h->h_counters, 0, sizeof(StepCounters));
     CREATE_CU(cudaMalloc(&h->d_export, sizeof(double) * h->n_cells));
+    CREATE_CU(cudaMalloc(&h->d_history, sizeof(StepRecord) * STEP_HISTORY));
+    CREATE_CU(cudaMemsetAsync(h->d_history, 0xff, sizeof(StepRecord) * STEP_HISTORY, h->stream));
     CREATE_CU(cudaMalloc(&h->d_barrier, sizeof(int)));
     CREATE_CU(cudaMemsetAsync(h->d_barrier, 0, sizeof(int), h->stream));
     launch_init_slots(h->stream, h->d_slot[0], h->n_local, h->d_spare, h->n_spare, h->d_counters, h->rank);
@@ -403,6 +443,7 @@ int slamrs_gpu_upload_scan(slamrs_gpu_handle* h, const float* angle, const float
         CU_TRY(h, cudaMemcpyAsync(h->d_valid, valid, n_beams, cudaMemcpyHostToDevice, h->stream));
     }
     h->n_beams = n_beams;
+    h->scan_external = false;
     // window radius for the ray kernel: farthest finite measurement, in cells, plus the two extra
     // steps of apply_measurement (map.rs:97) and rounding slack. Correctness never depends on it:
     // cells outside the window take the global-atomic path.
@@ -411,6 +452,19 @@ int slamrs_gpu_upload_scan(slamrs_gpu_handle* h, const float* angle, const float
         if (isfinite(dist[i]) && fabsf(dist[i]) > maxd) maxd = fabsf(dist[i]);
     const float cells = ceilf(maxd / h->geom.res);
     h->radius_cells = (cells < 4096.0f ? (int)cells : 4096) + 4;
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_set_scan_device(slamrs_gpu_handle* h, const float* angle_device, const float* dist_device,
+                               const uint8_t* valid_device, uint32_t n_beams, float max_dist) {
+    if (!h) return SLAMRS_E_INVALID_ARG;
+    if (n_beams > 0 && (!angle_device || !dist_device || !valid_device)) return fail(h, SLAMRS_E_INVALID_ARG, "null scan array");
+    if (n_beams > 65535u) return fail(h, SLAMRS_E_INVALID_ARG, "at most 65535 beams per scan");
+    h->ext_angle = angle_device; h->ext_dist = dist_device; h->ext_valid = valid_device;
+    h->n_beams = n_beams;
+    h->scan_external = true;
+    const float cells = ceilf(fabsf(max_dist) / h->geom.res);
+    h->radius_cells = ((cells == cells && cells < 4096.0f) ? (int)cells : 4096) + 4;
     return SLAMRS_OK;
 }
 
@@ -427,24 +481,33 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         CU_TRY(h, cudaMemcpyAsync(h->d_z, z_draws, sizeof(double) * 2 * h->n_total, cudaMemcpyHostToDevice, s));
         CU_TRY(h, cudaMemcpyAsync(h->d_u, resample_u, sizeof(double), cudaMemcpyHostToDevice, s));
     }
-    const ScanDevice scan{h->d_angle, h->d_dist, h->d_valid, h->n_beams};
+    const ScanDevice scan = h->scan_external ? ScanDevice{h->ext_angle, h->ext_dist, h->ext_valid, h->n_beams}
+                                             : ScanDevice{h->d_angle, h->d_dist, h->d_valid, h->n_beams};
+    if (h->profiling && h->prof_recorded == PROF_RING) {
+        int prc = prof_flush(h);
+        if (prc) return prc;
+    }
     const int cur = h->cur, nxt = cur ^ 1;
 
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
+    PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->cells_per_grid,
                              h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step);
     // 2. integrate the scan into every particle's grid
+    PROF_MARK(h, 1);
     CU_TRY(h, cudaMemsetAsync(&h->d_counters->saturated, 0, 2 * sizeof(unsigned long long), s));
     CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_slot[cur], h->d_cells,
                                 h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells));
     h->launches += 2;
     // 3. the one exchange step: every GPU needs every particle's weight, pose and slot
+    PROF_MARK(h, 2);
     if (h->world > 1) {
         std::string err;
         if (comm_all_gather(h->comm, h->d_results + h->first, h->d_results, sizeof(ParticleResult) * h->n_local, s, &err))
             return fail(h, SLAMRS_E_NCCL, err);
     }
     // 4. normalise, argmax, running sum; systematic resampling indices (replicated on every GPU)
+    PROF_MARK(h, 3);
     launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, h->d_counters);
@@ -460,8 +523,11 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.cells = h->d_cells; pa.cells_per_grid = h->cells_per_grid;
     pa.peer_cells = h->d_peer_cells;
     pa.counters = h->d_counters;
+    pa.history = h->d_history;
+    pa.step = h->step;
     launch_plan(s, pa);
     h->launches += 3;
+    PROF_MARK(h, 4);
     // 6. grid traffic: NVLink pulls first, barrier, then the local duplicate copies
     if (h->world > 1) {
         launch_copy(s, h->d_pulls, &h->d_counters->n_pulls, h->cells_per_grid, h->num_sms);
@@ -469,8 +535,11 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         std::string err;
         if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
     }
+    PROF_MARK(h, 5);
     launch_copy(s, h->d_copies, &h->d_counters->n_copies, h->cells_per_grid, h->num_sms);
     h->launches++;
+    PROF_MARK(h, 6);
+    if (h->profiling) h->prof_recorded++;
     CU_TRY(h, cudaGetLastError());
     h->cur = nxt;
     h->step++;
@@ -545,6 +614,46 @@ int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out) {
     out->spilled_cells = c.spilled;
     out->window_cells = h->window_cells;
     out->bytes_per_grid = h->cells_per_grid * sizeof(uint32_t);
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_set_profiling(slamrs_gpu_handle* h, int enabled) {
+    if (!h) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    if (enabled && h->prof_events.empty()) {
+        h->prof_events.resize((size_t)PROF_RING * PROF_MARKS);
+        for (auto& e : h->prof_events) CU_TRY(h, cudaEventCreate(&e));
+    }
+    if (!enabled) {
+        int rc = prof_flush(h);
+        if (rc) return rc;
+    }
+    h->profiling = enabled != 0;
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COUNT], uint64_t* out_steps) {
+    if (!h || !out_ms || !out_steps) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int rc = prof_flush(h);
+    if (rc) return rc;
+    for (int p = 0; p < SLAMRS_PHASE_COUNT; ++p) { out_ms[p] = h->prof_ms[p]; h->prof_ms[p] = 0.0; }
+    *out_steps = h->prof_steps;
+    h->prof_steps = 0;
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_triples) {
+    if (!h || !out_triples || count > STEP_HISTORY) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    std::vector<StepRecord> ring(STEP_HISTORY);
+    CU_TRY(h, cudaMemcpyAsync(ring.data(), h->d_history, sizeof(StepRecord) * STEP_HISTORY, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    for (uint32_t i = 0; i < count; ++i) {
+        const StepRecord& r = ring[(first_step + i) % STEP_HISTORY];
+        if (r.step != first_step + i) return fail(h, SLAMRS_E_INVALID_ARG, "step no longer in the history ring");
+        out_triples[3 * i] = r.n_copies; out_triples[3 * i + 1] = r.n_pulls; out_triples[3 * i + 2] = r.distinct;
+    }
     return SLAMRS_OK;
 }
 

@@ -577,6 +577,11 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
         const unsigned long long mp = a.counters->max_particle;
         a.counters->est_owner = mp / S;
         a.counters->est_slot = (mp >= lo && mp < hi) ? (long long)a.slot_new[mp - lo] : -1ll;
+        if (a.history) {
+            StepRecord r;
+            r.step = a.step; r.n_copies = nBD; r.n_pulls = nC; r.distinct = distinct;
+            a.history[a.step % STEP_HISTORY] = r;
+        }
     }
 }
 

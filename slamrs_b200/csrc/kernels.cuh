@@ -33,6 +33,13 @@ struct StepCounters {
     float pad;
 };
 
+// per-step record kept on the device so that a pipelined caller can read, after the fact, how
+// many grids each step really moved (the roofline is computed from moved bytes only)
+struct StepRecord {
+    unsigned long long step, n_copies, n_pulls, distinct;
+};
+constexpr uint32_t STEP_HISTORY = 256;
+
 struct ScanDevice {
     const float* angle;
     const float* dist;
@@ -82,6 +89,8 @@ struct PlanArgs {
     size_t cells_per_grid;
     uint32_t* const* peer_cells;        // world pointers to each rank's pool (device array), may be null when world==1
     StepCounters* counters;
+    StepRecord* history;       // STEP_HISTORY entries, slot = step % STEP_HISTORY
+    unsigned long long step;
 };
 void launch_plan(cudaStream_t stream, const PlanArgs& a);
 

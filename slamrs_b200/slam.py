@@ -236,6 +236,25 @@ class GridMapSlam:
         _lib.check(self._L.slamrs_gpu_step_async(self._h, u.distance_left, u.distance_right, u.wheel_distance,
                                                  _ptr(zd), _ptr(ru)), self._h)
 
+    def set_scan_device(self, angle_ptr: int, dist_ptr: int, valid_ptr: int, n_beams: int, max_dist: float) -> None:
+        """Step on an observation that already lives in device memory (raw device pointers)."""
+        _lib.check(self._L.slamrs_gpu_set_scan_device(self._h, angle_ptr, dist_ptr, valid_ptr, n_beams, max_dist), self._h)
+
+    def set_profiling(self, enabled: bool) -> None:
+        _lib.check(self._L.slamrs_gpu_set_profiling(self._h, int(enabled)), self._h)
+
+    def phase_ms(self):
+        """(dict phase -> summed ms, steps covered) since the last call; synchronises."""
+        ms = np.zeros(len(_lib.PHASES), np.float64); steps = C.c_uint64(0)
+        _lib.check(self._L.slamrs_gpu_get_phase_ms(self._h, _ptr(ms), C.byref(steps)), self._h)
+        return dict(zip(_lib.PHASES, ms.tolist())), int(steps.value)
+
+    def step_history(self, first_step: int, count: int) -> np.ndarray:
+        """count x {grids_copied, grids_pulled, distinct_sources} for steps first_step.."""
+        out = np.zeros((count, 3), np.uint64)
+        _lib.check(self._L.slamrs_gpu_get_step_history(self._h, first_step, count, _ptr(out)), self._h)
+        return out
+
     def sync(self) -> None:
         _lib.check(self._L.slamrs_gpu_sync(self._h), self._h)
 
