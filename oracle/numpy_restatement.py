@@ -66,7 +66,9 @@ def angle_diff(alpha: float, beta: float) -> float:   # A.5
 
 def normal_pdf(x, mean, sd):
     d = (x - mean) / sd
-    return math.exp(-0.5 * d * d) / (2.5066282746310002 * sd)
+    # statrs consts::SQRT_2PI is a 50-digit decimal literal; its nearest f64 is 0x1.40d931ff62706p+1
+    # (NOT sqrt(2*pi) evaluated in f64, which is one ulp lower)
+    return math.exp(-0.5 * d * d) / (float("2.5066282746310005024157652848110452530069867406099") * sd)
 
 
 def ray_cells(x0, y0, x1, y1, w, h, extra=2):
