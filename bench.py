@@ -17,9 +17,9 @@ Legs of the CUDA arm
   e2e    K steps through the reference-facing call sequence of GridMapSlamNode::update
          (node.rs:47-60): update(host scan) -> estimated_pose() -> estimated_likelihood() into a
          pinned host grid; host<->device copies inside the timed region.
-  roofline  the grid-copy kernel (k_copy): algorithmic bytes = 2 * bytes_per_grid * grids
-         actually copied (read on the device per step), divided by the kernel's own CUDA-event
-         time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  roofline  the grid-copy kernel (k_copy): algorithmic bytes = bytes_per_grid * (grids
+         written + source grids read (both counted on the device per step), divided by the
+         kernel's own CUDA-event time, against MEASURED_PEAKS.json's HBM copy bandwidth.
   cpu_baseline  (N=1, rank 0) the CPU oracle on a bounded sample of the same workload.
 """
 from __future__ import annotations
@@ -261,6 +261,7 @@ def run_cuda(args, wl, rank, world, local):
     hist = slam.step_history(W, K)
     copies = hist[:, 0].astype(np.float64)
     pulls = hist[:, 1].astype(np.float64)
+    src_reads = hist[:, 3].astype(np.float64)
     st = slam.stats()
 
     # ---- e2e: the node's call sequence with host buffers
@@ -303,7 +304,9 @@ def run_cuda(args, wl, rank, world, local):
     value = pbu * K / (ms_value * 1e-3)
     # roofline of the dominant kernel (grid copy) on rank 0's own launches
     copy_ms = phase_ms["copy"]
-    copy_bytes = 2.0 * grid_bytes * copies.sum()          # read + write, grids really copied by rank 0
+    # bytes the kernel really moves: every copied grid is written once; a source grid is read once
+    # per fan-out sub-run (<= 16 destinations), not once per copy
+    copy_bytes = float(grid_bytes) * (copies.sum() + src_reads.sum())
     achieved = copy_bytes / (copy_ms * 1e-3) / 1e9 if copy_ms > 0 else 0.0
     # whole-step algorithmic bytes: copies + ray RMW (8 B per cell-step, C_p ~ measured per scan) + gathers
     line = {
@@ -317,7 +320,9 @@ def run_cuda(args, wl, rank, world, local):
             "bound": "hbm", "kernel": "k_copy (resampling grid copies)", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
             "bytes_per_launch": copy_bytes / K, "ms_per_launch": copy_ms / K,
-            "grids_copied_per_step": float(copies.mean()), "bytes_per_grid": int(grid_bytes),
+            "grids_copied_per_step": float(copies.mean()), "source_reads_per_step": float(src_reads.mean()),
+            "bytes_per_grid": int(grid_bytes),
+            "algorithmic_bytes": "bytes_per_grid * (grids written + source grids read), per launch",
         },
         "phases_ms_per_step": {k: v / K for k, v in phase_ms.items()},
         "resample": {"grids_copied_per_step_all_gpus": float(agg[0] / K), "grids_pulled_per_step_all_gpus": float(agg[1] / K),

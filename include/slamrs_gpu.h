@@ -163,8 +163,10 @@ enum slamrs_phase {
 int slamrs_gpu_set_profiling(slamrs_gpu_handle* h, int enabled);
 int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COUNT], uint64_t* out_steps);
 /* Per-step history (ring of the last 256 steps): for step indices first_step .. first_step+count-1
- * writes {grids_copied, grids_pulled, distinct_sources} triples. */
-int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_triples);
+ * writes 4 values per step: {grids_copied, grids_pulled, distinct_sources, source_reads} where
+ * source_reads = number of times the copy kernel read a source grid (one read feeds up to 16
+ * destination grids). */
+int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_values);
 
 /* current generation, this rank's shard: n_local * {x, y, theta} */
 int slamrs_gpu_get_poses(slamrs_gpu_handle* h, float* out_xyt);

@@ -46,6 +46,7 @@ struct slamrs_gpu_handle {
     double* d_u = nullptr;
     int32_t *d_keep = nullptr, *d_need = nullptr, *d_free = nullptr, *d_spare = nullptr;
     CopyItem *d_copies = nullptr, *d_pulls = nullptr;
+    uint32_t* d_leaders = nullptr;
     StepCounters* d_counters = nullptr;
     StepCounters* h_counters = nullptr;  // pinned
     double* d_export = nullptr;
@@ -190,7 +191,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
-    cudaFree(h->d_copies); cudaFree(h->d_pulls);
+    cudaFree(h->d_copies); cudaFree(h->d_pulls); cudaFree(h->d_leaders);
     cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells);
     cudaFree(h->d_history);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -396,6 +397,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_spare, sizeof(int32_t) * ((size_t)h->n_spare + 1)));
     CREATE_CU(cudaMalloc(&h->d_copies, sizeof(CopyItem) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_pulls, sizeof(CopyItem) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_leaders, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_counters, sizeof(StepCounters)));
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
     memset(h->h_counters, 0, sizeof(StepCounters));
@@ -519,7 +521,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.slot_old = h->d_slot[cur]; pa.slot_new = h->d_slot[nxt];
     pa.keep = h->d_keep; pa.need = h->d_need; pa.free_list = h->d_free; pa.spare_list = h->d_spare;
     pa.n_spare_cap = h->n_spare;
-    pa.copies = h->d_copies; pa.pulls = h->d_pulls;
+    pa.copies = h->d_copies; pa.pulls = h->d_pulls; pa.leaders = h->d_leaders;
     pa.cells = h->d_cells; pa.cells_per_grid = h->cells_per_grid;
     pa.peer_cells = h->d_peer_cells;
     pa.counters = h->d_counters;
@@ -530,13 +532,14 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 4);
     // 6. grid traffic: NVLink pulls first, barrier, then the local duplicate copies
     if (h->world > 1) {
-        launch_copy(s, h->d_pulls, &h->d_counters->n_pulls, h->cells_per_grid, h->num_sms);
+        launch_copy(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->cells_per_grid, h->num_sms);
         h->launches++;
         std::string err;
         if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
     }
     PROF_MARK(h, 5);
-    launch_copy(s, h->d_copies, &h->d_counters->n_copies, h->cells_per_grid, h->num_sms);
+    launch_copy(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->cells_per_grid,
+                h->num_sms);
     h->launches++;
     PROF_MARK(h, 6);
     if (h->profiling) h->prof_recorded++;
@@ -644,6 +647,7 @@ int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COU
 }
 
 int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_triples) {
+    // four values per step: grids_copied, grids_pulled, distinct_sources, source_reads
     if (!h || !out_triples || count > STEP_HISTORY) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     std::vector<StepRecord> ring(STEP_HISTORY);
@@ -652,7 +656,8 @@ int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint3
     for (uint32_t i = 0; i < count; ++i) {
         const StepRecord& r = ring[(first_step + i) % STEP_HISTORY];
         if (r.step != first_step + i) return fail(h, SLAMRS_E_INVALID_ARG, "step no longer in the history ring");
-        out_triples[3 * i] = r.n_copies; out_triples[3 * i + 1] = r.n_pulls; out_triples[3 * i + 2] = r.distinct;
+        out_triples[4 * i] = r.n_copies; out_triples[4 * i + 1] = r.n_pulls; out_triples[4 * i + 2] = r.distinct;
+        out_triples[4 * i + 3] = r.n_leaders;
     }
     return SLAMRS_OK;
 }

@@ -197,6 +197,28 @@ __device__ __forceinline__ void global_cell_add(uint32_t* addr, uint32_t inc, bo
 }
 
 constexpr int RAY_MAX_THREADS = 512;
+constexpr int RAY_MAX_RADIUS = 150;                    // rows of the window: 2 * radius + 1
+constexpr int RAY_MAX_ROWS = 2 * RAY_MAX_RADIUS + 1;
+constexpr int RAY_WB_BATCH = 6;                        // write-back: global loads in flight per thread
+
+// exact integer square root of a small non-negative integer (same code on host and device so
+// that the host's shared-memory sizing and the kernel's row table agree)
+__host__ __device__ inline int isqrt_small(int v) {
+    int r = (int)sqrtf((float)v);
+    while (r * r > v) r--;
+    while ((r + 1) * (r + 1) <= v) r++;
+    return r;
+}
+
+// The window is a DISC of cells around the start cell (rays cannot leave it), stored row by row:
+// row dy holds x in [cx - hw, cx + hw], hw = floor(sqrt(R^2 - dy^2)), widened to multiples of 4
+// cells for 128-bit write-back. A disc needs pi/4 of the bounding square, which is what lets a
+// 6 m range at 5 cm cells (radius 124) fit in one CTA's shared memory.
+__host__ __device__ inline int ray_window_cells_upper_bound(int radius, bool vec) {
+    int total = 0;
+    for (int dy = -radius; dy <= radius; ++dy) total += 2 * isqrt_small(radius * radius - dy * dy) + 1 + (vec ? 6 : 0);
+    return total;
+}
 
 template <bool kVector>
 __global__ void __launch_bounds__(RAY_MAX_THREADS)
@@ -204,6 +226,8 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
              const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, size_t cells_per_grid, int radius,
              StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];
+    __shared__ int s_row_off[RAY_MAX_ROWS + 1];   // first window cell of each row (+ total at [wh])
+    __shared__ int s_row_x[RAY_MAX_ROWS];         // x0 | (width << 16)
     const uint32_t p = blockIdx.x;
     const ParticleResult r = results[first_particle + p];
     const float px = r.x, py = r.y, ptheta = r.theta;
@@ -212,21 +236,50 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     // Map::integrate, map.rs:71-73: ray start in grid coordinates
     const float sx = world_to_grid(px, geom.pos_x, geom.res);
     const float sy = world_to_grid(py, geom.pos_y, geom.res);
-    const long long cx = f32_as_isize(floorf(sx)), cy = f32_as_isize(floorf(sy));
+    const long long lcx = f32_as_isize(floorf(sx)), lcy = f32_as_isize(floorf(sy));
     // every ray starts in the same cell; outside the grid nothing is emitted (ray.rs:88-92)
-    if (cx < 0 || cx >= (long long)geom.gw || cy < 0 || cy >= (long long)geom.gh) return;
+    if (lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh) return;
+    const int cx = (int)lcx, cy = (int)lcy;
 
-    // shared-memory window around the start cell, clipped to the grid; x-range aligned to 4 cells
-    int wx0 = max(0, (int)cx - radius), wx1 = min((int)geom.gw, (int)cx + radius + 1);
-    const int wy0 = max(0, (int)cy - radius), wy1 = min((int)geom.gh, (int)cy + radius + 1);
-    if (kVector) {
-        wx0 &= ~3;
-        wx1 = min((int)geom.gw, (wx1 + 3) & ~3);
+    // ---- row table of the disc window, clipped to the grid
+    const int wy0 = max(0, cy - radius), wy1 = min((int)geom.gh, cy + radius + 1);
+    const int wh = wy1 - wy0;
+    for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {
+        const int dy = wy0 + ly - cy;
+        const int hw = isqrt_small(radius * radius - dy * dy);
+        int x0 = max(0, cx - hw), x1 = min((int)geom.gw, cx + hw + 1);
+        if (kVector) {
+            x0 &= ~3;
+            x1 = min((int)geom.gw, (x1 + 3) & ~3);
+        }
+        s_row_x[ly] = x0 | ((x1 - x0) << 16);
     }
-    const int ww = wx1 - wx0, wh = wy1 - wy0;
-    const int wcells = ww * wh;
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive prefix sum of the row widths, 32 rows per round
+        int carry = 0;
+        for (int base = 0; base < wh; base += 32) {
+            const int ly = base + (int)threadIdx.x;
+            const int w = ly < wh ? (s_row_x[ly] >> 16) : 0;
+            int inc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += t;
+            }
+            if (ly < wh) s_row_off[ly] = carry + inc - w;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (threadIdx.x == 0) s_row_off[wh] = carry;
+    }
+    __syncthreads();
+    const int wcells = s_row_off[wh];
 
-    for (int i = threadIdx.x; i < wcells; i += blockDim.x) s_win[i] = 0u;
+    if (kVector) {
+        uint4* w4 = reinterpret_cast<uint4*>(s_win);
+        for (int i = threadIdx.x; i < (wcells >> 2); i += blockDim.x) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        for (int i = threadIdx.x; i < wcells; i += blockDim.x) s_win[i] = 0u;
+    }
     __syncthreads();
 
     bool saturated = false;
@@ -237,17 +290,23 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
         beam_endpoint(px, py, ptheta, scan.angle[b], dist, &ex, &ey);
         const float gx = world_to_grid(ex, geom.pos_x, geom.res);
         const float gy = world_to_grid(ey, geom.pos_y, geom.res);
-        const float measured = __fdiv_rn(dist, geom.res);  // map.rs:84
-        const bool hit = scan.valid[b] != 0;
+        // measured distance in cells (map.rs:84) and the per-ray form of inverse_sensor_model
+        const RayClassifier cls = make_ray_classifier(__fdiv_rn(dist, geom.res), scan.valid[b] != 0);
         // apply_measurement, map.rs:88-106 (additional_steps = 2)
-        ray_walk(sx, sy, gx, gy, geom.gw, geom.gh, 2u, [&](int x, int y) {
-            const float d = start_to_cell_distance(sx, sy, x, y);
-            const uint32_t inc = inverse_sensor_increment(d, measured, hit);
+        ray_walk_acc(sx, sy, gx, gy, geom.gw, geom.gh, 2u, [&](int x, int y, float acc) {
+            const uint32_t inc = classify_cell(cls, acc);
             if (inc != 0u) {
-                const int lx = x - wx0, ly = y - wy0;
-                if ((unsigned)lx < (unsigned)ww && (unsigned)ly < (unsigned)wh) {
-                    atomicAdd(&s_win[ly * ww + lx], inc);
-                } else {
+                const int ly = y - wy0;
+                bool in_window = false;
+                if ((unsigned)ly < (unsigned)wh) {
+                    const int rx = s_row_x[ly];
+                    const int lx = x - (rx & 0xffff);
+                    if ((unsigned)lx < (unsigned)(rx >> 16)) {
+                        atomicAdd(&s_win[s_row_off[ly] + lx], inc);
+                        in_window = true;
+                    }
+                }
+                if (!in_window) {  // beyond the window (range larger than shared memory allows)
                     global_cell_add(&grid[(size_t)y * geom.gh + x], inc, &saturated);
                     spilled++;
                 }
@@ -256,30 +315,56 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     }
     __syncthreads();
 
-    // write-back: grid += window, saturating per 16-bit counter, skipping untouched groups
+    // ---- write-back: grid += window, saturating per 16-bit counter, untouched groups skipped.
+    // RAY_WB_BATCH independent global loads are issued per thread before the first dependent store.
     if (kVector) {
-        const int ww4 = ww >> 2;
+        const int total4 = wcells >> 2;
         const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
-        for (int i = threadIdx.x; i < ww4 * wh; i += blockDim.x) {
-            const uint4 d = win4[i];
-            if ((d.x | d.y | d.z | d.w) != 0u) {
-                const int row = i / ww4, c4 = i - row * ww4;
-                uint4* g = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + row) * geom.gh + wx0) + c4;
-                uint4 v = *g;
-                v.x = cell_sat_add(v.x, d.x, &saturated);
-                v.y = cell_sat_add(v.y, d.y, &saturated);
-                v.z = cell_sat_add(v.z, d.z, &saturated);
-                v.w = cell_sat_add(v.w, d.w, &saturated);
-                *g = v;
+        for (int base = threadIdx.x; base < total4; base += blockDim.x * RAY_WB_BATCH) {
+            uint4 d[RAY_WB_BATCH], v[RAY_WB_BATCH];
+            uint4* gp[RAY_WB_BATCH];
+            bool nz[RAY_WB_BATCH];
+#pragma unroll
+            for (int j = 0; j < RAY_WB_BATCH; ++j) {
+                const int i = base + j * (int)blockDim.x;
+                nz[j] = false;
+                if (i < total4) {
+                    d[j] = win4[i];
+                    nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
+                    if (nz[j]) {
+                        int lo = 0, hi = wh;   // row containing window cell 4*i
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_row_off[mid] <= 4 * i) lo = mid; else hi = mid;
+                        }
+                        const int lx = 4 * i - s_row_off[lo];
+                        gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + (s_row_x[lo] & 0xffff) + lx);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RAY_WB_BATCH; ++j)
+                if (nz[j]) v[j] = *gp[j];
+#pragma unroll
+            for (int j = 0; j < RAY_WB_BATCH; ++j) {
+                if (nz[j]) {
+                    v[j].x = cell_sat_add(v[j].x, d[j].x, &saturated);
+                    v[j].y = cell_sat_add(v[j].y, d[j].y, &saturated);
+                    v[j].z = cell_sat_add(v[j].z, d[j].z, &saturated);
+                    v[j].w = cell_sat_add(v[j].w, d[j].w, &saturated);
+                    *gp[j] = v[j];
+                }
             }
         }
     } else {
-        for (int i = threadIdx.x; i < wcells; i += blockDim.x) {
-            const uint32_t d = s_win[i];
-            if (d != 0u) {
-                const int row = i / ww, c = i - row * ww;
-                uint32_t* g = grid + (size_t)(wy0 + row) * geom.gh + wx0 + c;
-                *g = cell_sat_add(*g, d, &saturated);
+        for (int ly = threadIdx.x >> 5; ly < wh; ly += blockDim.x >> 5) {
+            const int rx = s_row_x[ly], x0 = rx & 0xffff, w = rx >> 16, off = s_row_off[ly];
+            for (int c = threadIdx.x & 31; c < w; c += 32) {
+                const uint32_t d = s_win[off + c];
+                if (d != 0u) {
+                    uint32_t* g = grid + (size_t)(wy0 + ly) * geom.gh + x0 + c;
+                    *g = cell_sat_add(*g, d, &saturated);
+                }
             }
         }
     }
@@ -298,15 +383,15 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
                               uint32_t first_particle, uint32_t n_local, const int32_t* slot_of, uint32_t* cells,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells) {
-    // largest radius whose (aligned) window fits the budget: (2R+1+6) * (2R+1) * 4 bytes
-    int radius = radius_cells < 1 ? 1 : radius_cells;
-    while ((size_t)(2 * radius + 7) * (size_t)(2 * radius + 1) * 4 > (size_t)RAY_MAX_SMEM) radius--;
-    const size_t wmax = (size_t)min(2 * radius + 7, (int)geom.gw) * (size_t)min(2 * radius + 1, (int)geom.gh);
+    const bool vec = (geom.gw % 4u == 0u) && (cells_per_grid % 4u == 0u);
+    // largest disc radius whose row-aligned window fits the shared-memory budget
+    int radius = radius_cells < 1 ? 1 : (radius_cells > RAY_MAX_RADIUS ? RAY_MAX_RADIUS : radius_cells);
+    while (radius > 1 && (size_t)ray_window_cells_upper_bound(radius, vec) * 4 > (size_t)RAY_MAX_SMEM) radius--;
+    const size_t wmax = (size_t)ray_window_cells_upper_bound(radius, vec);
     const size_t smem = wmax * 4;
     *window_cells = wmax;
     int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
     threads = threads < 128 ? 128 : (threads > RAY_MAX_THREADS ? RAY_MAX_THREADS : threads);
-    const bool vec = (geom.gw % 4u == 0u) && (cells_per_grid % 4u == 0u);
     if (vec)
         k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, slot_of, cells,
                                                                cells_per_grid, radius, counters);
@@ -516,8 +601,11 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     uint32_t pbd = block_excl_scan_u32(nBD_c, s_warp, &nBD);
     __syncthreads();  // free_list complete
 
-    // pass 1: pulls and local duplicates (their sources are already in place)
+    // pass 1: pulls and local duplicates (their sources are already in place).
+    // Copies of one source are adjacent in the list; every COPY_FAN-th of them is a "leader":
+    // the copy kernel reads the source once per leader and stores it to the whole sub-run.
     const uint32_t pbd_start = pbd;
+    uint32_t n_lead_c = 0;
     for (uint32_t m = c0; m < c1; ++m) {
         const int cls = a.need[m];
         if (cls == 2) {
@@ -539,6 +627,10 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             it.src = a.cells + (size_t)a.slot_old[src - lo] * a.cells_per_grid;
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
             a.copies[pbd] = it;
+            const uint32_t m_first = lower_bound_u32(a.idx, lo, hi, src) - lo;
+            const bool lead = ((m - m_first - 1u) % COPY_FAN) == 0u;
+            a.need[m] = lead ? 5 : 1;   // remember leadership for the compaction below
+            n_lead_c += lead;
             pbd++;
         } else if (cls == 3) {
             pbd++;
@@ -558,10 +650,22 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             it.src = a.cells + (size_t)a.slot_new[m_first] * a.cells_per_grid;
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
             a.copies[pbd] = it;
+            const bool lead = ((m - m_first - 1u) % COPY_FAN) == 0u;
+            a.need[m] = lead ? 7 : 3;
+            n_lead_c += lead;
             pbd++;
-        } else if (cls == 1) {
+        } else if (cls == 1 || cls == 5) {
             pbd++;
         }
+    }
+    // ordered list of leader positions within copies[]
+    uint32_t n_lead;
+    uint32_t pl = block_excl_scan_u32(n_lead_c, s_warp, &n_lead);
+    pbd = pbd_start;
+    for (uint32_t m = c0; m < c1; ++m) {
+        const int cls = a.need[m];
+        if (cls == 5 || cls == 7) a.leaders[pl++] = pbd;
+        if (cls == 1 || cls == 3 || cls == 5 || cls == 7) pbd++;
     }
     __syncthreads();
     // ---- the E slots nobody took become the next step's spare list
@@ -571,6 +675,7 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     block_excl_scan_u32(nA, s_warp, &distinct);
     if (t == 0) {
         a.counters->n_copies = nBD;
+        a.counters->n_leaders = n_lead;
         a.counters->n_pulls = nC;
         a.counters->distinct = distinct;
         a.counters->staging_short = (nC > n_safe + E) ? (unsigned long long)(nC - (n_safe + E)) : 0ull;
@@ -579,7 +684,7 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
         a.counters->est_slot = (mp >= lo && mp < hi) ? (long long)a.slot_new[mp - lo] : -1ll;
         if (a.history) {
             StepRecord r;
-            r.step = a.step; r.n_copies = nBD; r.n_pulls = nC; r.distinct = distinct;
+            r.step = a.step; r.n_copies = nBD; r.n_pulls = nC; r.distinct = distinct; r.n_leaders = n_lead;
             a.history[a.step % STEP_HISTORY] = r;
         }
     }
@@ -588,45 +693,59 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
 void launch_plan(cudaStream_t stream, const PlanArgs& a) { k_plan<<<1, 1024, 0, stream>>>(a); }
 
 // =============================================================================== k_copy
-// Full-grid copies (the `value.clone()` of particle.rs:97-100). Pure streaming: 128-bit loads
-// that bypass L1, four in flight per thread before the first store. One work item = 16 KiB of
-// one grid; CTAs stride over the item list, whose length is read from device memory so that
-// no host round trip sits between planning and copying.
+// Grid copies (the `value.clone()` of particle.rs:97-100). Pure streaming: 128-bit loads that
+// bypass L1, four in flight per thread, then 128-bit stores. Copies of the same source are
+// adjacent in the list, so one work item = 16 KiB of a source grid fanned out to up to
+// COPY_FAN destinations: the source is read once per sub-run instead of once per copy, which
+// makes the kernel write-bound (D grids written, D / COPY_FAN + distinct sources read).
+// CTAs stride over (leader, chunk) items; list lengths are read from device memory so that no
+// host round trip sits between planning and copying.
 
 constexpr int COPY_THREADS = 256;
 constexpr int COPY_UNROLL = 4;
 constexpr uint32_t COPY_ITEM_V4 = COPY_THREADS * COPY_UNROLL;  // uint4 per work item (16 KiB)
 
 __global__ void __launch_bounds__(COPY_THREADS)
-k_copy(const CopyItem* __restrict__ items, const unsigned long long* __restrict__ n_items, uint32_t v4_per_grid) {
+k_copy(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
+       const unsigned long long* __restrict__ n_items, const unsigned long long* __restrict__ n_leaders,
+       uint32_t v4_per_grid) {
     const unsigned long long n = *n_items;
+    const unsigned long long nl = leaders ? *n_leaders : n;
     const uint32_t chunks = (v4_per_grid + COPY_ITEM_V4 - 1) / COPY_ITEM_V4;
-    const unsigned long long total = n * chunks;
+    const unsigned long long total = nl * chunks;
     for (unsigned long long w = blockIdx.x; w < total; w += gridDim.x) {
-        const unsigned long long j = w / chunks;
-        const uint32_t c = (uint32_t)(w - j * chunks);
-        const CopyItem it = items[j];
+        const unsigned long long q = w / chunks;
+        const uint32_t c = (uint32_t)(w - q * chunks);
+        const unsigned long long k = leaders ? leaders[q] : q;
+        const CopyItem it = items[k];
+        uint32_t fan = 1;
+        if (leaders) {
+            while (fan < COPY_FAN && k + fan < n && items[k + fan].src == it.src) fan++;
+        }
         const uint4* src = reinterpret_cast<const uint4*>(it.src);
-        uint4* dst = reinterpret_cast<uint4*>(it.dst);
         const uint32_t base = c * COPY_ITEM_V4 + threadIdx.x;
         uint4 v[COPY_UNROLL];
 #pragma unroll
-        for (int k = 0; k < COPY_UNROLL; ++k) {
-            const uint32_t i = base + k * COPY_THREADS;
-            if (i < v4_per_grid) v[k] = ld_stream_v4(src + i);
+        for (int u = 0; u < COPY_UNROLL; ++u) {
+            const uint32_t i = base + u * COPY_THREADS;
+            if (i < v4_per_grid) v[u] = ld_stream_v4(src + i);
         }
+        for (uint32_t f = 0; f < fan; ++f) {
+            uint4* dst = reinterpret_cast<uint4*>(items[k + f].dst);
 #pragma unroll
-        for (int k = 0; k < COPY_UNROLL; ++k) {
-            const uint32_t i = base + k * COPY_THREADS;
-            if (i < v4_per_grid) st_stream_v4(dst + i, v[k]);
+            for (int u = 0; u < COPY_UNROLL; ++u) {
+                const uint32_t i = base + u * COPY_THREADS;
+                if (i < v4_per_grid) st_stream_v4(dst + i, v[u]);
+            }
         }
     }
 }
 
-void launch_copy(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items,
-                 size_t cells_per_grid, int num_sms) {
+void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
+                 const unsigned long long* n_items, const unsigned long long* n_leaders, size_t cells_per_grid,
+                 int num_sms) {
     const uint32_t v4 = (uint32_t)(cells_per_grid / 4);
-    k_copy<<<num_sms * 8, COPY_THREADS, 0, stream>>>(items, n_items, v4);
+    k_copy<<<num_sms * 8, COPY_THREADS, 0, stream>>>(items, leaders, n_items, n_leaders, v4);
 }
 
 // =============================================================================== k_export

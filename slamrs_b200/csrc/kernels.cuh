@@ -19,6 +19,7 @@ static_assert(sizeof(ParticleResult) == 24, "ParticleResult is exchanged between
 struct StepCounters {
     unsigned long long max_particle;     // argmax of the normalised weights, last max wins (particle.rs:40-46)
     unsigned long long n_copies;         // local duplicate copies planned this step
+    unsigned long long n_leaders;        // sub-runs of <= COPY_FAN copies sharing one source read
     unsigned long long n_pulls;          // remote grids to pull this step
     unsigned long long distinct;         // distinct sources feeding this rank's new generation
     unsigned long long clamped;          // resample index clamped to N-1
@@ -36,9 +37,10 @@ struct StepCounters {
 // per-step record kept on the device so that a pipelined caller can read, after the fact, how
 // many grids each step really moved (the roofline is computed from moved bytes only)
 struct StepRecord {
-    unsigned long long step, n_copies, n_pulls, distinct;
+    unsigned long long step, n_copies, n_pulls, distinct, n_leaders;
 };
 constexpr uint32_t STEP_HISTORY = 256;
+constexpr uint32_t COPY_FAN = 16;   // destinations written per source read in k_copy
 
 struct ScanDevice {
     const float* angle;
@@ -84,6 +86,7 @@ struct PlanArgs {
     int32_t* spare_list;       // persistent list of free physical slots beyond the live set
     uint32_t n_spare_cap;
     CopyItem* copies;          // n_local
+    uint32_t* leaders;         // n_local: positions in copies[] that start a fan-out sub-run
     CopyItem* pulls;           // n_local
     uint32_t* cells;           // local pool base
     size_t cells_per_grid;
@@ -95,8 +98,10 @@ struct PlanArgs {
 void launch_plan(cudaStream_t stream, const PlanArgs& a);
 
 // copies[0..*n_items) full grids; n_items is read on the device
-void launch_copy(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items,
-                 size_t cells_per_grid, int num_sms);
+// leaders == nullptr: plain item-by-item copy (used for the NVLink pulls)
+void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
+                 const unsigned long long* n_items, const unsigned long long* n_leaders, size_t cells_per_grid,
+                 int num_sms);
 
 void launch_export(cudaStream_t stream, const uint32_t* cells, size_t cells_per_grid, const StepCounters* counters,
                    uint32_t n_cells, double* out);

@@ -86,12 +86,17 @@ __device__ __forceinline__ uint32_t inverse_sensor_increment(float distance, flo
 }
 
 // ---------------------------------------------------------------------------- ray iterator
-// GridRayIterator::new + next, slamrs/slam/src/grid/ray.rs:21-77, 83-110.
-// `visit(x, y)` is called for every emitted cell, in order. The running `error` term is a
-// sequential f32 accumulation and must not be re-associated.
+// GridRayIterator::new + next, slamrs/slam/src/grid/ray.rs:21-77, 83-110, fused with the
+// squared start-to-cell-centre distance that apply_measurement needs (map.rs:99-100).
+// `visit(x, y, acc)` is called for every emitted cell, in order, where
+//     acc = fl(fl(dx*dx) + fl(dy*dy)),  dx = fl(x0 - (x + 0.5)),  dy = fl(y0 - (y + 0.5))
+// is exactly the value nalgebra's EuclideanNorm folds before taking the square root
+// (0 + dx^2 is exact). The running `error` term is a sequential f32 accumulation and is not
+// re-associated. Cell centres x + 0.5 are exact in f32 for |x| < 2^22, so they are carried
+// incrementally (+-1 per step, exact) and only the coordinate that moved is recomputed.
 template <typename Visit>
-__device__ __forceinline__ void ray_walk(float x0, float y0, float x1, float y1, uint32_t size_x, uint32_t size_y,
-                                         uint32_t additional_steps, Visit&& visit) {
+__device__ __forceinline__ void ray_walk_acc(float x0, float y0, float x1, float y1, uint32_t size_x, uint32_t size_y,
+                                             uint32_t additional_steps, Visit&& visit) {
     const float delta_x = fabsf(__fsub_rn(x1, x0));
     const float delta_y = fabsf(__fsub_rn(y1, y0));
     const float fx0 = floorf(x0), fy0 = floorf(y0);
@@ -133,29 +138,95 @@ __device__ __forceinline__ void ray_walk(float x0, float y0, float x1, float y1,
     const unsigned long long cap = (unsigned long long)size_x + size_y + 8ull;
     int remaining = (int)(n < cap ? n : cap);
     int x = (int)sx, y = (int)sy;
-    while (remaining > 0 && !(x < 0 || x >= (int)size_x || y < 0 || y >= (int)size_y)) {
-        visit(x, y);
+    const float x_step = (float)x_inc, y_step = (float)y_inc;
+    float cx = __fadd_rn((float)x, 0.5f), cy = __fadd_rn((float)y, 0.5f);
+    float dx = __fsub_rn(x0, cx), dy = __fsub_rn(y0, cy);
+    float dx2 = __fmul_rn(dx, dx), dy2 = __fmul_rn(dy, dy);
+    bool inside = true;
+    while (remaining > 0 && inside) {
+        visit(x, y, __fadd_rn(dx2, dy2));
         if (error > 0.0f) {
             y += y_inc;
             error = __fsub_rn(error, delta_x);
+            cy = __fadd_rn(cy, y_step);
+            dy = __fsub_rn(y0, cy);
+            dy2 = __fmul_rn(dy, dy);
+            inside = (unsigned)y < size_y;
         } else {
             x += x_inc;
             error = __fadd_rn(error, delta_y);
+            cx = __fadd_rn(cx, x_step);
+            dx = __fsub_rn(x0, cx);
+            dx2 = __fmul_rn(dx, dx);
+            inside = (unsigned)x < size_x;
         }
         remaining -= 1;
     }
 }
 
-// distance from the ray start to a cell centre: nalgebra EuclideanNorm::metric_distance,
-// a left fold from 0 of squared differences, then sqrt (map.rs:100)
-__device__ __forceinline__ float start_to_cell_distance(float sx, float sy, int x, int y) {
-    const float cx = __fadd_rn((float)x, 0.5f);
-    const float cy = __fadd_rn((float)y, 0.5f);
-    const float dx = __fsub_rn(sx, cx);
-    const float dy = __fsub_rn(sy, cy);
-    float acc = __fadd_rn(0.0f, __fmul_rn(dx, dx));
-    acc = __fadd_rn(acc, __fmul_rn(dy, dy));
-    return __fsqrt_rn(acc);
+template <typename Visit>
+__device__ __forceinline__ void ray_walk(float x0, float y0, float x1, float y1, uint32_t size_x, uint32_t size_y,
+                                         uint32_t additional_steps, Visit&& visit) {
+    ray_walk_acc(x0, y0, x1, y1, size_x, size_y, additional_steps, [&](int x, int y, float) { visit(x, y); });
+}
+
+// ---- inverse sensor model without the per-cell square root ---------------------------------
+// inverse_sensor_model (map.rs:148-172) compares distance = fl(sqrt(acc)) with thresholds that
+// are constant along a ray. IEEE sqrt is correctly rounded and monotone, so each comparison
+// can be moved into the acc domain once per ray:
+//     fl(sqrt(a)) <  t   <=>   a <  acc_threshold_below(t)
+//     fl(sqrt(a)) >  t   <=>   a >  acc_threshold_above(t)
+// for every a >= 0 (including +inf); NaN a or NaN t make both sides false, as in the reference.
+__device__ __forceinline__ float f32_next_up(float a) {    // a >= 0, finite or inf
+    return a == __int_as_float(0x7f800000) ? a : __int_as_float(__float_as_int(a) + 1);
+}
+__device__ __forceinline__ float f32_next_down(float a) {  // a > 0
+    return __int_as_float(__float_as_int(a) - 1);
+}
+// smallest A >= 0 with fl(sqrt(A)) >= t  (so that d < t  <=>  acc < A)
+__device__ __forceinline__ float acc_threshold_below(float t) {
+    if (!(t > 0.0f)) return 0.0f;                       // t <= 0 or NaN: d < t never holds
+    if (t == __int_as_float(0x7f800000)) return t;      // d < inf  <=>  acc < inf
+    float a = __fmul_rn(t, t);                          // may be +inf or underflow to 0
+    while (a > 0.0f && __fsqrt_rn(f32_next_down(a)) >= t) a = f32_next_down(a);
+    while (__fsqrt_rn(a) < t) a = f32_next_up(a);       // sqrt(+inf) = +inf >= t terminates
+    return a;
+}
+// largest B with fl(sqrt(B)) <= t  (so that d > t  <=>  acc > B); -1 when every acc >= 0 exceeds it
+__device__ __forceinline__ float acc_threshold_above(float t) {
+    if (t != t) return __int_as_float(0x7f800000);      // NaN: d > t never holds
+    if (t < 0.0f) return -1.0f;                         // d >= 0 > t always
+    if (t == __int_as_float(0x7f800000)) return t;      // d > inf never
+    float b = __fmul_rn(t, t);
+    if (b == __int_as_float(0x7f800000)) b = __int_as_float(0x7f7fffff);
+    while (__fsqrt_rn(b) > t) b = f32_next_down(b);     // t >= 0: sqrt(0) = 0 <= t terminates
+    while (b < __int_as_float(0x7f7fffff) && __fsqrt_rn(f32_next_up(b)) <= t) b = f32_next_up(b);
+    return b;
+}
+
+struct RayClassifier {   // per-ray constants of inverse_sensor_model with tolerance 2.0 (map.rs:104)
+    float free_below;    // acc <  free_below -> P_FREE
+    float prior_above;   // acc >  prior_above -> P_PRIOR
+    uint32_t mid_inc;    // otherwise: P_OCCUPPIED for a hit, P_PRIOR for a miss
+};
+__device__ __forceinline__ RayClassifier make_ray_classifier(float measured, bool was_hit) {
+    RayClassifier c;
+    if (!was_hit) {  // free strictly before the reading, prior from there on
+        c.free_below = acc_threshold_below(measured);
+        c.prior_above = __int_as_float(0x7f800000);
+        c.mid_inc = 0u;
+    } else {
+        const float half_tol = __fdiv_rn(2.0f, 2.0f);
+        c.free_below = acc_threshold_below(__fsub_rn(measured, half_tol));
+        c.prior_above = acc_threshold_above(__fadd_rn(measured, half_tol));
+        c.mid_inc = CELL_OCC_INC;
+    }
+    return c;
+}
+__device__ __forceinline__ uint32_t classify_cell(const RayClassifier& c, float acc) {
+    if (acc < c.free_below) return CELL_FREE_INC;
+    if (acc > c.prior_above) return 0u;
+    return c.mid_inc;
 }
 
 // ---------------------------------------------------------------------------- motion model

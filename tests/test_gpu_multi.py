@@ -1,0 +1,107 @@
+"""Multi-GPU parity: particles sharded over 2+ GPUs must reproduce the single-GPU
+run bit for bit -- the shared stream is indexed by the global particle id, the weight all-gather
+gives every GPU the same index vector, and migrating grids are pulled over NVLink.
+Ranks are driven by threads of this process (same-process peer access); the torchrun bench
+covers the multi-process path (CUDA IPC)."""
+import threading
+
+import numpy as np
+import pytest
+
+from slamrs_b200 import GpuPlacement, GridMapSlam, GridMapSlamConfig, nccl_unique_id
+
+from common import SEED, make_scans, oracle_slam, oracle_step
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _run_sharded(cfg, scans, world, spare_slots=0, collect_cells=()):
+    nid = nccl_unique_id()
+    out = [None] * world
+    errs = []
+
+    def worker(rank):
+        try:
+            g = GridMapSlam(cfg, GpuPlacement(device=rank, rank=rank, world_size=world, nccl_id=nid, seed=SEED,
+                                              spare_slots=spare_slots))
+            rec = []
+            for obs, odo in scans:
+                g.update(obs, odo)
+                ep = g.estimated_pose()
+                m = g.estimated_likelihood().data.copy()
+                st = g.stats()
+                cells = {p: g.cells(p) for p in collect_cells if g.first <= p < g.first + g.n_local}
+                rec.append(dict(poses=g.poses().copy(), idx=g.resample_indices().copy(), w=g.weights()[0].copy(),
+                                maxp=g.max_particle, est=(ep.x, ep.y, ep.theta), map=m, stats=st, cells=cells))
+            out[rank] = rec
+            g.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append((rank, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errs, errs
+    assert all(o is not None for o in out), "a rank hung"
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_equals_single_gpu_and_oracle(oracle, world):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n = 64
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=n)
+    scans = make_scans(1.0, 360, 1.0, 6)
+    probe = (0, 1, n // 2 - 1, n // 2, n - 1)
+    shards = _run_sharded(cfg, scans, world, collect_cells=probe)
+    osl = oracle_slam(oracle, cfg)
+    pulled = 0
+    for step, (obs, odo) in enumerate(scans):
+        rc, _, _ = oracle_step(oracle, osl, obs, odo, step)
+        assert rc == 0
+        idx_ref = osl.indices().astype(np.uint32)
+        poses_ref = osl.poses()
+        for r in range(world):
+            rec = shards[r][step]
+            assert np.array_equal(rec["idx"], idx_ref)                      # replicated, bit-exact
+            assert rec["maxp"] == osl.max_particle
+            lo = r * (n // world)
+            assert np.array_equal(rec["poses"].view(np.uint32), poses_ref[lo:lo + n // world].view(np.uint32))
+            ep = osl.estimated_pose()
+            assert np.array_equal(np.array(rec["est"], np.float32).view(np.uint32), ep.view(np.uint32))
+            assert np.max(np.abs(rec["map"] - osl.estimated_likelihood())) < 1e-12   # broadcast from the owner
+            for p, cells in rec["cells"].items():
+                nf, no = osl.counts(p)
+                assert np.array_equal(cells & 0xFFFF, nf) and np.array_equal(cells >> 16, no), (step, r, p)
+            pulled += rec["stats"]["grids_pulled"]
+    assert pulled > 0, "the test never exercised a cross-GPU grid migration"
+    osl.close()
+
+
+def test_migration_needs_staging_slots():
+    """With a single spare slot the planner must still be correct or report E_STAGING -- never corrupt."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from slamrs_b200 import _lib
+    n = 32
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=n)
+    scans = make_scans(1.0, 360, 1.0, 3)
+    try:
+        shards = _run_sharded(cfg, scans, 2, spare_slots=1)
+    except AssertionError as e:
+        assert "error -6" in str(e) or "E_STAGING" in str(e) or str(_lib.E_STAGING) in str(e)
+        return
+    single = []
+    with GridMapSlam(cfg, GpuPlacement(seed=SEED)) as g:
+        for obs, odo in scans:
+            g.update(obs, odo)
+            single.append(g.poses().copy())
+    for step in range(len(scans)):
+        both = np.concatenate([shards[0][step]["poses"], shards[1][step]["poses"]])
+        assert np.array_equal(both.view(np.uint32), single[step].view(np.uint32))
