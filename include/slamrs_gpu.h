@@ -49,6 +49,12 @@ enum slamrs_rng_mode {
     SLAMRS_RNG_CALLER = 1         /* caller passes the standard-normal draws and the resample uniform */
 };
 
+enum slamrs_flags {
+    /* use the 32-bit-window ray kernel even where the packed 16-bit-window kernel applies
+     * (tests run both; results are identical) */
+    SLAMRS_FLAG_GENERIC_RAY_KERNEL = 1
+};
+
 typedef struct slamrs_gpu_handle slamrs_gpu_handle;
 
 /* Replaces `GridMapSlamConfig` (slam.rs:18-25) plus the placement the YAML cannot carry. */
@@ -67,7 +73,7 @@ typedef struct slamrs_gpu_config {
     uint32_t world_size;   /* 1 = single GPU */
     uint32_t spare_slots;  /* extra physical grid slots per GPU used to stage grids that migrate
                               between GPUs at resampling; 0 = automatic (none when world_size==1) */
-    uint32_t flags;        /* reserved, 0 */
+    uint32_t flags;        /* enum slamrs_flags bits, normally 0 */
     uint8_t nccl_id[SLAMRS_NCCL_ID_BYTES]; /* from slamrs_gpu_nccl_unique_id, same on all ranks */
 } slamrs_gpu_config;
 

@@ -13,6 +13,7 @@ ABI_VERSION = 1
 OK = 0
 E_INVALID_ARG, E_CUDA, E_NCCL, E_OOM, E_NO_DEVICE, E_STAGING, E_NOT_LOCAL, E_INTERNAL = -1, -2, -3, -4, -5, -6, -7, -8
 RNG_SHARED_STREAM, RNG_CALLER = 0, 1
+FLAG_GENERIC_RAY_KERNEL = 1
 
 EXPORTS = [
     "slamrs_gpu_grid_cells", "slamrs_gpu_nccl_unique_id", "slamrs_gpu_create", "slamrs_gpu_destroy",

@@ -499,7 +499,8 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 1);
     CU_TRY(h, cudaMemsetAsync(&h->d_counters->saturated, 0, 2 * sizeof(unsigned long long), s));
     CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_slot[cur], h->d_cells,
-                                h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells));
+                                h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
+                                (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
     h->launches += 2;
     // 3. the one exchange step: every GPU needs every particle's weight, pose and slot
     PROF_MARK(h, 2);

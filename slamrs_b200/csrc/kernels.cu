@@ -372,9 +372,245 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 }
 
+// ------------------------------------------------------------------------------- packed variant
+// Same algorithm with a 2-byte window cell: bits 0..10 = free hits (a cell can be crossed by at
+// most n_beams <= 2047 rays per scan), bits 11..15 = occupied hits (<= 31; a 32nd hit in one scan
+// takes the exact global path). Half the shared memory per particle => two CTAs per SM at a 6 m /
+// 5 cm window, which is what hides the latency of the serial cell walk. Free hits (the vast
+// majority) are single fire-and-forget shared-memory adds; the walk itself is written with the
+// row lookup hoisted to y-steps.
+constexpr uint32_t PK_FREE_BITS = 11;
+constexpr uint32_t PK_FREE_MASK = (1u << PK_FREE_BITS) - 1u;
+constexpr uint32_t PK_OCC_MAX = 31;
+constexpr uint32_t RAY_PACKED_MAX_BEAMS = PK_FREE_MASK;
+
+__host__ __device__ inline int ray_window_cells_upper_bound_packed(int radius) {
+    int total = 0;
+    for (int dy = -radius; dy <= radius; ++dy) total += 2 * isqrt_small(radius * radius - dy * dy) + 1 + 14;
+    return total;
+}
+
+__global__ void __launch_bounds__(RAY_MAX_THREADS)
+k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
+                    const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, size_t cells_per_grid,
+                    int radius, StepCounters* counters) {
+    extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
+    __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
+    const uint32_t p = blockIdx.x;
+    const ParticleResult r = results[first_particle + p];
+    const float px = r.x, py = r.y, ptheta = r.theta;
+    uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
+
+    const float sx = world_to_grid(px, geom.pos_x, geom.res);
+    const float sy = world_to_grid(py, geom.pos_y, geom.res);
+    const long long lcx = f32_as_isize(floorf(sx)), lcy = f32_as_isize(floorf(sy));
+    if (lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh) return;
+    const int cx0 = (int)lcx, cy0 = (int)lcy;
+    const int gw = (int)geom.gw, gh = (int)geom.gh;
+
+    // ---- row table of the disc window (x ranges aligned to 8 cells = one 128-bit group)
+    const int wy0 = max(0, cy0 - radius), wy1 = min(gh, cy0 + radius + 1);
+    const int wh = wy1 - wy0;
+    for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {
+        const int dy = wy0 + ly - cy0;
+        const int hw = isqrt_small(radius * radius - dy * dy);
+        const int x0 = max(0, cx0 - hw) & ~7;
+        const int x1 = min(gw, (min(gw, cx0 + hw + 1) + 7) & ~7);
+        s_row[ly].y = x0 | ((x1 - x0) << 16);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int carry = 0;
+        for (int base = 0; base < wh; base += 32) {
+            const int ly = base + (int)threadIdx.x;
+            const int w = ly < wh ? (s_row[ly].y >> 16) : 0;
+            int inc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += t;
+            }
+            if (ly < wh) s_row[ly].x = carry + inc - w;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (threadIdx.x == 0) s_row[wh] = make_int2(carry, 0);
+    }
+    __syncthreads();
+    const int wcells = s_row[wh].x;
+    {
+        uint4* w4 = reinterpret_cast<uint4*>(s_win);
+        for (int i = threadIdx.x; i < (wcells >> 3); i += blockDim.x) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+
+    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
+    bool saturated = false;
+    uint32_t spilled = 0;
+    for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
+        const float dist = scan.dist[b];
+        float ex, ey;
+        beam_endpoint(px, py, ptheta, scan.angle[b], dist, &ex, &ey);
+        const float x1 = world_to_grid(ex, geom.pos_x, geom.res);
+        const float y1 = world_to_grid(ey, geom.pos_y, geom.res);
+        const RayClassifier cls = make_ray_classifier(__fdiv_rn(dist, geom.res), scan.valid[b] != 0);
+
+        // GridRayIterator::new (ray.rs:21-77) -- identical arithmetic to ray_walk_acc
+        const float delta_x = fabsf(__fsub_rn(x1, sx)), delta_y = fabsf(__fsub_rn(y1, sy));
+        const float fx0 = floorf(sx), fy0 = floorf(sy);
+        unsigned long long n = 1ull + 2ull;   // additional_steps = 2 (map.rs:97)
+        int x_inc, y_inc;
+        float error;
+        if (delta_x == 0.0f) {
+            x_inc = 0;
+            error = __int_as_float(0x7f800000);
+        } else if (x1 > sx) {
+            x_inc = 1;
+            n += (unsigned long long)f32_as_isize(__fsub_rn(floorf(x1), (float)cx0));
+            error = __fmul_rn(__fsub_rn(__fadd_rn(fx0, 1.0f), sx), delta_y);
+        } else {
+            x_inc = -1;
+            n += (unsigned long long)(long long)cx0 - (unsigned long long)f32_as_isize(floorf(x1));
+            error = __fmul_rn(__fsub_rn(sx, fx0), delta_y);
+        }
+        if (delta_y == 0.0f) {
+            y_inc = 0;
+            error = __fsub_rn(error, __int_as_float(0x7f800000));
+        } else if (y1 > sy) {
+            y_inc = 1;
+            n += (unsigned long long)f32_as_isize(floorf(y1)) - (unsigned long long)(long long)cy0;
+            error = __fsub_rn(error, __fmul_rn(__fsub_rn(__fadd_rn(fy0, 1.0f), sy), delta_x));
+        } else {
+            y_inc = -1;
+            n += (unsigned long long)(long long)cy0 - (unsigned long long)f32_as_isize(floorf(y1));
+            error = __fsub_rn(error, __fmul_rn(__fsub_rn(sy, fy0), delta_x));
+        }
+        const unsigned long long cap = (unsigned long long)geom.gw + geom.gh + 8ull;
+        int remaining = (int)(n < cap ? n : cap);
+
+        int x = cx0, y = cy0;
+        const float x_step = (float)x_inc, y_step = (float)y_inc;
+        float cxf = __fadd_rn((float)x, 0.5f), cyf = __fadd_rn((float)y, 0.5f);
+        float dxs = __fsub_rn(sx, cxf), dys = __fsub_rn(sy, cyf);
+        float dx2 = __fmul_rn(dxs, dxs), dy2 = __fmul_rn(dys, dys);
+        // window row of the current y: offset (cells), x0, width (0 when y is outside the window)
+        int ly = y - wy0;
+        int2 row = s_row[ly];                      // the start cell is always inside the window
+        int lx = x - (row.y & 0xffff);
+        int row_w = row.y >> 16;
+        bool inside = true;
+        while (remaining > 0 && inside) {
+            const float acc = __fadd_rn(dx2, dy2);
+            const bool is_free = acc < cls.free_below;
+            const bool is_mid = !is_free && !(acc > cls.prior_above) && (cls.mid_inc != 0u);
+            if (is_free | is_mid) {
+                const bool in_win = (unsigned)lx < (unsigned)row_w;
+                const int cell = row.x + lx;
+                const uint32_t addr = win_base + ((uint32_t)(cell >> 1) << 2);
+                const uint32_t shift = (cell & 1) << 4;
+                if (is_free & in_win) {
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u << shift) : "memory");
+                } else {
+                    bool done = false;
+                    if (in_win) {   // occupied hit: bounded 5-bit field, exact path when it would overflow
+                        uint32_t* wp = &s_win[cell >> 1];
+                        uint32_t old = *wp;
+                        for (;;) {
+                            if (((old >> (shift + PK_FREE_BITS)) & PK_OCC_MAX) == PK_OCC_MAX) break;
+                            const uint32_t seen = atomicCAS(wp, old, old + (1u << (shift + PK_FREE_BITS)));
+                            if (seen == old) { done = true; break; }
+                            old = seen;
+                        }
+                    }
+                    if (!done) {
+                        global_cell_add(&grid[(size_t)y * geom.gh + x], is_free ? CELL_FREE_INC : CELL_OCC_INC, &saturated);
+                        spilled++;
+                    }
+                }
+            }
+            // GridRayIterator::next (ray.rs:96-104)
+            if (error > 0.0f) {
+                y += y_inc;
+                error = __fsub_rn(error, delta_x);
+                cyf = __fadd_rn(cyf, y_step);
+                dys = __fsub_rn(sy, cyf);
+                dy2 = __fmul_rn(dys, dys);
+                inside = (unsigned)y < (unsigned)gh;
+                ly += y_inc;
+                if ((unsigned)ly < (unsigned)wh) {
+                    row = s_row[ly];
+                    row_w = row.y >> 16;
+                    lx = x - (row.y & 0xffff);
+                } else {
+                    row_w = 0;
+                }
+            } else {
+                x += x_inc;
+                error = __fadd_rn(error, delta_y);
+                cxf = __fadd_rn(cxf, x_step);
+                dxs = __fsub_rn(sx, cxf);
+                dx2 = __fmul_rn(dxs, dxs);
+                inside = (unsigned)x < (unsigned)gw;
+                lx += x_inc;
+            }
+            remaining -= 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- write-back: 8 packed cells (one 128-bit shared load) -> two 128-bit global RMWs
+    const int total8 = wcells >> 3;
+    const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
+    constexpr int BATCH = 4;
+    for (int base = threadIdx.x; base < total8; base += blockDim.x * BATCH) {
+        uint4 d[BATCH], va[BATCH], vb[BATCH];
+        uint4* gp[BATCH];
+        bool nz[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int i = base + j * (int)blockDim.x;
+            nz[j] = false;
+            if (i < total8) {
+                d[j] = win4[i];
+                nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
+                if (nz[j]) {
+                    int lo = 0, hi = wh;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_row[mid].x <= 8 * i) lo = mid; else hi = mid;
+                    }
+                    const int lx = 8 * i - s_row[lo].x;
+                    gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + (s_row[lo].y & 0xffff) + lx);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+            if (nz[j]) { va[j] = gp[j][0]; vb[j] = gp[j][1]; }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            if (nz[j]) {
+                auto apply = [&](uint32_t g, uint32_t packed16) {
+                    const uint32_t delta = (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16);
+                    return cell_sat_add(g, delta, &saturated);
+                };
+                va[j].x = apply(va[j].x, d[j].x & 0xffffu); va[j].y = apply(va[j].y, d[j].x >> 16);
+                va[j].z = apply(va[j].z, d[j].y & 0xffffu); va[j].w = apply(va[j].w, d[j].y >> 16);
+                vb[j].x = apply(vb[j].x, d[j].z & 0xffffu); vb[j].y = apply(vb[j].y, d[j].z >> 16);
+                vb[j].z = apply(vb[j].z, d[j].w & 0xffffu); vb[j].w = apply(vb[j].w, d[j].w >> 16);
+                gp[j][0] = va[j];
+                gp[j][1] = vb[j];
+            }
+        }
+    }
+    if (saturated) atomicAdd(&counters->saturated, 1ull);
+    if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
+}
+
 cudaError_t configure_kernels() {
     // per-device opt-in to the large dynamic shared-memory window
     cudaError_t e = cudaFuncSetAttribute(k_ray_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ray_update_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_ray_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
 }
@@ -382,7 +618,19 @@ cudaError_t configure_kernels() {
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const int32_t* slot_of, uint32_t* cells,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
-                              uint64_t* window_cells) {
+                              uint64_t* window_cells, bool force_generic) {
+    int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
+    threads = threads < 128 ? 128 : (threads > RAY_MAX_THREADS ? RAY_MAX_THREADS : threads);
+    // preferred: the packed 16-bit window (two CTAs per SM at long range)
+    if (!force_generic && geom.gw % 8u == 0u && cells_per_grid % 8u == 0u && scan.n_beams <= RAY_PACKED_MAX_BEAMS) {
+        int radius = radius_cells < 1 ? 1 : (radius_cells > RAY_MAX_RADIUS ? RAY_MAX_RADIUS : radius_cells);
+        while (radius > 1 && (size_t)ray_window_cells_upper_bound_packed(radius) * 2 > (size_t)RAY_MAX_SMEM) radius--;
+        const size_t wmax = (size_t)ray_window_cells_upper_bound_packed(radius);
+        *window_cells = wmax;
+        k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, slot_of, cells,
+                                                                  cells_per_grid, radius, counters);
+        return cudaSuccess;
+    }
     const bool vec = (geom.gw % 4u == 0u) && (cells_per_grid % 4u == 0u);
     // largest disc radius whose row-aligned window fits the shared-memory budget
     int radius = radius_cells < 1 ? 1 : (radius_cells > RAY_MAX_RADIUS ? RAY_MAX_RADIUS : radius_cells);
@@ -390,8 +638,6 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
     const size_t wmax = (size_t)ray_window_cells_upper_bound(radius, vec);
     const size_t smem = wmax * 4;
     *window_cells = wmax;
-    int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
-    threads = threads < 128 ? 128 : (threads > RAY_MAX_THREADS ? RAY_MAX_THREADS : threads);
     if (vec)
         k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, slot_of, cells,
                                                                cells_per_grid, radius, counters);
@@ -702,16 +948,34 @@ void launch_plan(cudaStream_t stream, const PlanArgs& a) { k_plan<<<1, 1024, 0, 
 // host round trip sits between planning and copying.
 
 constexpr int COPY_THREADS = 256;
-constexpr int COPY_UNROLL = 4;
-constexpr uint32_t COPY_ITEM_V4 = COPY_THREADS * COPY_UNROLL;  // uint4 per work item (16 KiB)
+constexpr int COPY_UNROLL = 2;
+constexpr uint32_t COPY_ITEM_V8 = COPY_THREADS * COPY_UNROLL;  // 32-byte units per work item (16 KiB)
+constexpr int COPY_CTAS_PER_SM = 32;  // measured on B200: 6.37 TB/s moved at 32/SM vs 5.72 TB/s at 8/SM (tools/bw_probe.cu)
+
+struct alignas(32) V8 {
+    uint4 a, b;
+};
+// 256-bit global accesses (sm_100: ld/st.global.v8.b32). Streaming: no L1 allocation.
+__device__ __forceinline__ V8 ld_stream_v8(const V8* p) {
+    V8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v8(V8* p, const V8& v) {
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.a.x), "r"(v.a.y),
+                 "r"(v.a.z), "r"(v.a.w), "r"(v.b.x), "r"(v.b.y), "r"(v.b.z), "r"(v.b.w)
+                 : "memory");
+}
 
 __global__ void __launch_bounds__(COPY_THREADS)
 k_copy(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
        const unsigned long long* __restrict__ n_items, const unsigned long long* __restrict__ n_leaders,
-       uint32_t v4_per_grid) {
+       uint32_t v8_per_grid) {
     const unsigned long long n = *n_items;
     const unsigned long long nl = leaders ? *n_leaders : n;
-    const uint32_t chunks = (v4_per_grid + COPY_ITEM_V4 - 1) / COPY_ITEM_V4;
+    const uint32_t chunks = (v8_per_grid + COPY_ITEM_V8 - 1) / COPY_ITEM_V8;
     const unsigned long long total = nl * chunks;
     for (unsigned long long w = blockIdx.x; w < total; w += gridDim.x) {
         const unsigned long long q = w / chunks;
@@ -722,20 +986,20 @@ k_copy(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
         if (leaders) {
             while (fan < COPY_FAN && k + fan < n && items[k + fan].src == it.src) fan++;
         }
-        const uint4* src = reinterpret_cast<const uint4*>(it.src);
-        const uint32_t base = c * COPY_ITEM_V4 + threadIdx.x;
-        uint4 v[COPY_UNROLL];
+        const V8* src = reinterpret_cast<const V8*>(it.src);
+        const uint32_t base = c * COPY_ITEM_V8 + threadIdx.x;
+        V8 v[COPY_UNROLL];
 #pragma unroll
         for (int u = 0; u < COPY_UNROLL; ++u) {
             const uint32_t i = base + u * COPY_THREADS;
-            if (i < v4_per_grid) v[u] = ld_stream_v4(src + i);
+            if (i < v8_per_grid) v[u] = ld_stream_v8(src + i);
         }
         for (uint32_t f = 0; f < fan; ++f) {
-            uint4* dst = reinterpret_cast<uint4*>(items[k + f].dst);
+            V8* dst = reinterpret_cast<V8*>(items[k + f].dst);
 #pragma unroll
             for (int u = 0; u < COPY_UNROLL; ++u) {
                 const uint32_t i = base + u * COPY_THREADS;
-                if (i < v4_per_grid) st_stream_v4(dst + i, v[u]);
+                if (i < v8_per_grid) st_stream_v8(dst + i, v[u]);
             }
         }
     }
@@ -744,8 +1008,8 @@ k_copy(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
 void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
                  const unsigned long long* n_items, const unsigned long long* n_leaders, size_t cells_per_grid,
                  int num_sms) {
-    const uint32_t v4 = (uint32_t)(cells_per_grid / 4);
-    k_copy<<<num_sms * 8, COPY_THREADS, 0, stream>>>(items, leaders, n_items, n_leaders, v4);
+    const uint32_t v8 = (uint32_t)(cells_per_grid / 8);  // cells_per_grid is a multiple of 32 cells
+    k_copy<<<num_sms * COPY_CTAS_PER_SM, COPY_THREADS, 0, stream>>>(items, leaders, n_items, n_leaders, v8);
 }
 
 // =============================================================================== k_export

@@ -64,7 +64,7 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const int32_t* slot_of, uint32_t* cells,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
-                              uint64_t* window_cells);
+                              uint64_t* window_cells, bool force_generic);
 
 void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
                     double* cum, StepCounters* counters);

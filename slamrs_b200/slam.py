@@ -116,6 +116,7 @@ class GpuPlacement:
     seed: int = 0x5EED5A11
     rng_mode: int = _lib.RNG_SHARED_STREAM
     spare_slots: int = 0
+    flags: int = 0
 
 
 def grid_cells(extent: float, resolution: float) -> int:
@@ -160,6 +161,7 @@ class GridMapSlam:
         cfg.device = int(pl.device)
         cfg.rank, cfg.world_size = int(pl.rank), int(pl.world_size)
         cfg.spare_slots = int(pl.spare_slots)
+        cfg.flags = int(pl.flags)
         if pl.world_size > 1:
             if pl.nccl_id is None or len(pl.nccl_id) != _lib.NCCL_ID_BYTES:
                 raise ValueError("world_size > 1 needs the 128-byte nccl_id shared by all ranks")

@@ -81,8 +81,8 @@ def compare_step(gpu: GridMapSlam, osl, particles=None, check_map=True):
     return out
 
 
-def lockstep(O, cfg: GridMapSlamConfig, scans, rng_mode=_lib.RNG_SHARED_STREAM, particles=None, seed=SEED):
-    gpu = GridMapSlam(cfg, GpuPlacement(seed=seed, rng_mode=rng_mode))
+def lockstep(O, cfg: GridMapSlamConfig, scans, rng_mode=_lib.RNG_SHARED_STREAM, particles=None, seed=SEED, flags=0):
+    gpu = GridMapSlam(cfg, GpuPlacement(seed=seed, rng_mode=rng_mode, flags=flags))
     osl = oracle_slam(O, cfg)
     errs = []
     try:

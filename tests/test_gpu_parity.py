@@ -60,10 +60,14 @@ def test_raycast_cells_bit_exact(oracle, w, h):
         assert np.array_equal(cells[i, :counts[i]], ref), (i, x0[i], y0[i], x1[i], y1[i])
 
 
-def test_step_parity_default_preset(oracle):
+BOTH_RAY_KERNELS = pytest.mark.parametrize("flags", [0, _lib.FLAG_GENERIC_RAY_KERNEL], ids=["packed-window", "generic-window"])
+
+
+@BOTH_RAY_KERNELS
+def test_step_parity_default_preset(oracle, flags):
     """configs[0]: the shipped preset (200x200 @ 2 cm, 1 m range), 30 particles, 8 scans."""
     cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=30)
-    errs = lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 8))
+    errs = lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 8), flags=flags)
     print(errs[-1])
 
 
@@ -72,13 +76,37 @@ def test_step_parity_caller_supplied_draws(oracle):
     lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 4), rng_mode=_lib.RNG_CALLER)
 
 
-def test_step_parity_long_range_window_spill(oracle):
-    """6 m range at 5 cm cells: the ray window exceeds shared memory, so the spill path runs."""
+@BOTH_RAY_KERNELS
+def test_step_parity_long_range(oracle, flags):
+    """configs[1] geometry: 6 m range at 5 cm cells (disc window of radius 124 cells)."""
     cfg = GridMapSlamConfig(position=(-12.8, -12.8), width=25.6, height=25.6, resolution=0.05, n_particles=24)
-    gpu_stats = {}
     scans = make_scans(5.0, 360, 6.0, 4)
-    errs = lockstep(oracle, cfg, scans, particles=range(0, 24, 5))
+    errs = lockstep(oracle, cfg, scans, particles=range(0, 24, 5), flags=flags)
     print(errs[-1])
+
+
+@BOTH_RAY_KERNELS
+def test_step_parity_range_beyond_window_spills(oracle, flags):
+    """Up to 7 m rays at 2.5 cm cells = 280-cell rays: longer than any shared-memory window, so the
+    exact global-memory path handles the tails; counters must still be exact."""
+    cfg = GridMapSlamConfig(position=(-12.8, -12.8), width=25.6, height=25.6, resolution=0.025, n_particles=6)
+    scans = make_scans(5.0, 360, 12.0, 3)
+    with GridMapSlam(cfg, GpuPlacement(flags=flags)) as g:
+        g.update(*scans[0])
+        assert g.stats()["spilled_cells"] > 0
+    lockstep(oracle, cfg, scans, particles=[0, 3, 5], flags=flags)
+
+
+@BOTH_RAY_KERNELS
+def test_many_hits_in_one_cell(oracle, flags):
+    """Adversarial scan: every beam at the same angle and distance, so single cells collect
+    hundreds of free and occupied hits in one scan (overflows the packed window's 5-bit field)."""
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=4)
+    n = 360
+    same = Observation(0, angle=np.full(n, 0.3), distance=np.full(n, 0.5), valid=np.ones(n, bool))
+    near = Observation(0, angle=np.linspace(0, 2 * np.pi, n, endpoint=False), distance=np.full(n, 0.03), valid=np.ones(n, bool))
+    odo = Odometry.new(0.01, 0.012, 0.1)
+    lockstep(oracle, cfg, [(same, odo), (near, odo), (same, odo)], flags=flags)
 
 
 def test_step_parity_720_beams_odd_grid(oracle):
