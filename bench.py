@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-particles", type=int, default=0, help="particles of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strict", action="store_true", help="skip the strict-order-of-work comparison run")
     return ap.parse_args()
 
 
@@ -189,37 +190,20 @@ def workload_config(wl, n_gpus, n_total):
 
 
 # ------------------------------------------------------------------------------ CUDA arm
-def run_cuda(args, wl, rank, world, local):
+def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2e):
+    """One filter run: W warm-up + K timed device-resident steps (+ K e2e steps). Returns a dict of
+    rank-local measurements; the caller reduces over ranks."""
     import torch
     import torch.distributed as dist
-    from slamrs_b200 import GpuPlacement, GridMapSlam, nccl_unique_id
-    from slamrs_b200 import _lib
+    from slamrs_b200 import GpuPlacement, GridMapSlam
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the CUDA arm has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    nccl_id = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        buf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().numpy().tobytes())
-
-    n_total = wl.n_particles * world
     K, W = args.steps, args.warmup
+    n_total = wl.n_particles * world
     cfg = wl.slam_config(n_total)
-    sim = wl.simulator()
-    n_scans = W + K + (0 if args.no_e2e else K)
-    scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(n_scans)]
-
-    slam = GridMapSlam(cfg, GpuPlacement(device=local, rank=rank, world_size=world, nccl_id=nccl_id))
+    slam = GridMapSlam(cfg, GpuPlacement(device=local, rank=rank, world_size=world, nccl_id=nccl_id, flags=flags))
     stream = torch.cuda.ExternalStream(slam.stream_ptr, device=dev)
     grid_bytes = slam.stats()["bytes_per_grid"]
 
-    # device-resident scans for the `value` leg
     d_scans = []
     for obs, odo in scans[:W + K]:
         a = torch.from_numpy(obs.angle.astype(np.float32)).to(dev)
@@ -242,8 +226,6 @@ def run_cuda(args, wl, rank, world, local):
         device_step(i)
     slam.sync()
 
-    clocks = ClockSampler(local)
-    clocks.start()
     slam.set_profiling(True)
     launches0 = slam.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -254,46 +236,84 @@ def run_cuda(args, wl, rank, world, local):
     e1.record(stream)
     slam.sync()
     barrier()
-    ms_value = e0.elapsed_time(e1)
-    launches = slam.launch_count - launches0
-    phase_ms, psteps = slam.phase_ms()
+    out = {"ms_value": e0.elapsed_time(e1), "launches": slam.launch_count - launches0, "grid_bytes": grid_bytes}
+    out["phase_ms"], _ = slam.phase_ms()
     slam.set_profiling(False)
-    hist = slam.step_history(W, K)
-    copies = hist[:, 0].astype(np.float64)
-    pulls = hist[:, 1].astype(np.float64)
-    src_reads = hist[:, 3].astype(np.float64)
-    st = slam.stats()
+    out["hist"] = slam.step_history(W, K).astype(np.float64)
+    out["stats"] = slam.stats()
+    out["grid"] = (slam.grid_w, slam.grid_h)
 
-    # ---- e2e: the node's call sequence with host buffers
-    e2e = None
-    if not args.no_e2e:
-        pinned = torch.empty(cfg_cells(slam), dtype=torch.float64).pin_memory()
+    if do_e2e:
+        pinned = torch.empty(slam.grid_w * slam.grid_h, dtype=torch.float64).pin_memory()
         out_np = pinned.numpy()
         barrier()
         e0.record(stream)
-        for obs, odo in scans[W + K:]:
-            slam.update(obs, odo)
-            slam.estimated_pose()
-            slam.estimated_likelihood(out_np)
+        for obs, odo in scans[W + K:W + 2 * K]:
+            slam.update(obs, odo)                  # GridMapSlam::update with HOST scan buffers
+            slam.estimated_pose()                  # node.rs:51
+            slam.estimated_likelihood(out_np)      # node.rs:53-57, 8 B/cell map into pinned host memory
         e1.record(stream)
         slam.sync()
         barrier()
-        ms_e2e = e0.elapsed_time(e1)
-        e2e = {"ms": ms_e2e, "h2d": int(wl.n_beams * (4 + 4 + 1)), "d2h": int(12 + 8 * slam.grid_w * slam.grid_h)}
-    clock_info = clocks.stop()
-
-    # ---- max over ranks
-    t = torch.tensor([ms_value, e2e["ms"] if e2e else 0.0, phase_ms["copy"], phase_ms["ray_update"],
-                      phase_ms["motion_likelihood"], phase_ms["resample"], phase_ms["pull"], phase_ms["all_gather"]],
-                     dtype=torch.float64, device=dev)
-    agg = torch.tensor([copies.sum(), pulls.sum()], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    t = t.cpu().numpy(); agg = agg.cpu().numpy()
-    ms_value, ms_e2e = float(t[0]), float(t[1])
-
+        out["ms_e2e"] = e0.elapsed_time(e1)
     slam.close()
+    return out
+
+
+def run_cuda(args, wl, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from slamrs_b200 import nccl_unique_id
+    from slamrs_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CUDA arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def fresh_nccl_id():
+        if world == 1:
+            return None
+        buf = torch.zeros(_lib.NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        return bytes(buf.cpu().numpy().tobytes())
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_total = wl.n_particles * world
+    K, W = args.steps, args.warmup
+    sim = wl.simulator()
+    scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(W + 2 * K)]
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    main = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans, 0, not args.no_e2e)
+    clock_info = clocks.stop()
+    strict = None
+    if not args.no_strict:
+        strict = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans,
+                              _lib.FLAG_UPDATE_ALL_PARTICLES, False)
+
+    def reduce_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    def reduce_sum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    ph = main["phase_ms"]
+    tmax = reduce_max([main["ms_value"], main.get("ms_e2e", 0.0), strict["ms_value"] if strict else 0.0] +
+                      [ph[k] for k in _lib.PHASES])
+    hist = main["hist"]
+    tot = reduce_sum([hist[:, 0].sum(), hist[:, 1].sum(), hist[:, 4].sum()])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -301,38 +321,50 @@ def run_cuda(args, wl, rank, world, local):
 
     peak, peak_src = measured_peaks()
     pbu = n_total * wl.n_beams
-    value = pbu * K / (ms_value * 1e-3)
-    # roofline of the dominant kernel (grid copy) on rank 0's own launches
-    copy_ms = phase_ms["copy"]
-    # bytes the kernel really moves: every copied grid is written once; a source grid is read once
-    # per fan-out sub-run (<= 16 destinations), not once per copy
+    ms_value, ms_e2e, ms_strict = float(tmax[0]), float(tmax[1]), float(tmax[2])
+    grid_bytes = main["grid_bytes"]
+    copies, src_reads = hist[:, 0], hist[:, 3]
+    # roofline of the dominant kernel (grid copy), rank 0's own launches: every copied grid is
+    # written once; a source grid is read once per fan-out sub-run (<= 16 destinations)
+    copy_ms = ph["copy"]
     copy_bytes = float(grid_bytes) * (copies.sum() + src_reads.sum())
     achieved = copy_bytes / (copy_ms * 1e-3) / 1e9 if copy_ms > 0 else 0.0
-    # whole-step algorithmic bytes: copies + ray RMW (8 B per cell-step, C_p ~ measured per scan) + gathers
+    st = main["stats"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC, "value": pbu * K / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 geometry, f64 weights, u16x2 hit-counter cells", "data": "synthetic",
         "config": workload_config(wl, world, n_total),
         "clocks": clock_info,
-        "gpu_launches": int(launches),
+        "gpu_launches": int(main["launches"]),
         "roofline": {
             "bound": "hbm", "kernel": "k_copy (resampling grid copies)", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": ncu_traffic(copy_bytes / K),
+            "peak_source": peak_src,
             "bytes_per_launch": copy_bytes / K, "ms_per_launch": copy_ms / K,
             "grids_copied_per_step": float(copies.mean()), "source_reads_per_step": float(src_reads.mean()),
             "bytes_per_grid": int(grid_bytes),
             "algorithmic_bytes": "bytes_per_grid * (grids written + source grids read), per launch",
         },
-        "phases_ms_per_step": {k: v / K for k, v in phase_ms.items()},
-        "resample": {"grids_copied_per_step_all_gpus": float(agg[0] / K), "grids_pulled_per_step_all_gpus": float(agg[1] / K),
-                     "distinct_sources_last_step_rank0": st["distinct_sources"], "spilled_cells_last_step": st["spilled_cells"],
-                     "window_cells": st["window_cells"], "counter_saturated": st["counter_saturated"]},
+        "phases_ms_per_step": {k: float(tmax[3 + i]) / K for i, k in enumerate(_lib.PHASES)},
+        "resample": {"grids_copied_per_step_all_gpus": float(tot[0] / K), "grids_pulled_per_step_all_gpus": float(tot[1] / K),
+                     "particles_integrated_per_step_all_gpus": float(tot[2] / K),
+                     "distinct_sources_last_step_rank0": st["distinct_sources"],
+                     "spilled_cells_last_step": st["spilled_cells"], "window_cells": st["window_cells"],
+                     "counter_saturated": st["counter_saturated"]},
     }
-    if e2e:
+    if "ms_e2e" in main:
+        gw, gh = main["grid"]
         line["e2e"] = {"value": pbu * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
-                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                       "h2d_bytes_per_step": int(wl.n_beams * (4 + 4 + 1)), "d2h_bytes_per_step": int(12 + 8 * gw * gh),
                        "path": "update(host scan) + estimated_pose() + estimated_likelihood() per step (node.rs:47-60)"}
+    if strict:
+        line["strict_order_of_work"] = {
+            "value": pbu * K / (ms_strict * 1e-3), "unit": UNIT, "ms_per_step": ms_strict / K,
+            "note": "SLAMRS_FLAG_UPDATE_ALL_PARTICLES: the scan is integrated into every particle's grid before "
+                    "resampling, as the reference orders the work; results are identical to the default, which "
+                    "integrates only the grids that survive the step's resampling",
+            "phases_ms_per_step": {k: v / K for k, v in strict["phase_ms"].items()}}
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
@@ -347,6 +379,17 @@ def run_cuda(args, wl, rank, world, local):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(bytes_per_launch):
+    """DRAM bytes per launch of k_copy from the committed ncu --set full capture
+    (profiles/copy_traffic.json holds dram bytes per algorithmic byte of that capture)."""
+    path = os.path.join(ROOT, "profiles", "copy_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        ratio = json.load(f)["dram_bytes_per_algorithmic_byte"]
+    return ratio * bytes_per_launch
 
 
 def cfg_cells(slam):

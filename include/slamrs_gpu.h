@@ -52,7 +52,12 @@ enum slamrs_rng_mode {
 enum slamrs_flags {
     /* use the 32-bit-window ray kernel even where the packed 16-bit-window kernel applies
      * (tests run both; results are identical) */
-    SLAMRS_FLAG_GENERIC_RAY_KERNEL = 1
+    SLAMRS_FLAG_GENERIC_RAY_KERNEL = 1,
+    /* Strict order of work: integrate the scan into EVERY particle's grid, as the reference does
+     * (slam.rs:65-68), instead of only into the grids that survive this step's resampling. The
+     * observable state is identical either way (dropped particles are never read again); the
+     * default skips the unobservable work. */
+    SLAMRS_FLAG_UPDATE_ALL_PARTICLES = 2
 };
 
 typedef struct slamrs_gpu_handle slamrs_gpu_handle;
@@ -88,6 +93,7 @@ typedef struct slamrs_gpu_stats {
     uint64_t spilled_cells;    /* ray cell-steps that fell outside the shared-memory window */
     uint64_t window_cells;     /* shared-memory window size used by the ray kernel (cells) */
     uint64_t bytes_per_grid;   /* device bytes of one particle grid */
+    uint64_t particles_integrated; /* local particles whose grid received the scan this step */
 } slamrs_gpu_stats;
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -159,19 +165,20 @@ uint64_t slamrs_gpu_launch_count(const slamrs_gpu_handle* h);
  * Reading synchronises the stream and resets the accumulation. */
 enum slamrs_phase {
     SLAMRS_PHASE_MOTION_LIKELIHOOD = 0,
-    SLAMRS_PHASE_RAY_UPDATE = 1,
-    SLAMRS_PHASE_ALL_GATHER = 2,
-    SLAMRS_PHASE_RESAMPLE = 3, /* weights + indices + plan */
-    SLAMRS_PHASE_PULL = 4,     /* NVLink grid pulls + cross-GPU barrier */
-    SLAMRS_PHASE_COPY = 5,     /* local grid copies */
-    SLAMRS_PHASE_COUNT = 6
+    SLAMRS_PHASE_ALL_GATHER = 1,
+    SLAMRS_PHASE_RESAMPLE = 2,   /* weights + indices + survivor list */
+    SLAMRS_PHASE_RAY_UPDATE = 3,
+    SLAMRS_PHASE_PLAN = 4,
+    SLAMRS_PHASE_PULL = 5,       /* cross-GPU barriers + NVLink grid pulls */
+    SLAMRS_PHASE_COPY = 6,       /* local fan-out grid copies */
+    SLAMRS_PHASE_COUNT = 7
 };
 int slamrs_gpu_set_profiling(slamrs_gpu_handle* h, int enabled);
 int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COUNT], uint64_t* out_steps);
 /* Per-step history (ring of the last 256 steps): for step indices first_step .. first_step+count-1
- * writes 4 values per step: {grids_copied, grids_pulled, distinct_sources, source_reads} where
- * source_reads = number of times the copy kernel read a source grid (one read feeds up to 16
- * destination grids). */
+ * writes 5 values per step: {grids_copied, grids_pulled, distinct_sources, source_reads,
+ * particles_integrated} where source_reads = number of times the copy kernel read a source grid
+ * (one read feeds up to 16 destination grids). */
 int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_values);
 
 /* current generation, this rank's shard: n_local * {x, y, theta} */

@@ -56,6 +56,7 @@ pub struct slamrs_gpu_stats {
     pub spilled_cells: u64,
     pub window_cells: u64,
     pub bytes_per_grid: u64,
+    pub particles_integrated: u64,
 }
 
 extern "C" {

@@ -14,6 +14,7 @@ OK = 0
 E_INVALID_ARG, E_CUDA, E_NCCL, E_OOM, E_NO_DEVICE, E_STAGING, E_NOT_LOCAL, E_INTERNAL = -1, -2, -3, -4, -5, -6, -7, -8
 RNG_SHARED_STREAM, RNG_CALLER = 0, 1
 FLAG_GENERIC_RAY_KERNEL = 1
+FLAG_UPDATE_ALL_PARTICLES = 2
 
 EXPORTS = [
     "slamrs_gpu_grid_cells", "slamrs_gpu_nccl_unique_id", "slamrs_gpu_create", "slamrs_gpu_destroy",
@@ -26,7 +27,7 @@ EXPORTS = [
     "slamrs_gpu_set_scan_device", "slamrs_gpu_set_profiling", "slamrs_gpu_get_phase_ms",
     "slamrs_gpu_get_step_history",
 ]
-PHASES = ["motion_likelihood", "ray_update", "all_gather", "resample", "pull", "copy"]
+PHASES = ["motion_likelihood", "all_gather", "resample", "ray_update", "plan", "pull", "copy"]
 
 
 class Config(C.Structure):
@@ -45,7 +46,7 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "step", "grids_copied", "grids_pulled", "distinct_sources", "resample_clamped",
-        "counter_saturated", "spilled_cells", "window_cells", "bytes_per_grid")]
+        "counter_saturated", "spilled_cells", "window_cells", "bytes_per_grid", "particles_integrated")]
 
 
 class SlamrsGpuError(RuntimeError):

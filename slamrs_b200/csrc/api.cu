@@ -47,6 +47,7 @@ struct slamrs_gpu_handle {
     int32_t *d_keep = nullptr, *d_need = nullptr, *d_free = nullptr, *d_spare = nullptr;
     CopyItem *d_copies = nullptr, *d_pulls = nullptr;
     uint32_t* d_leaders = nullptr;
+    uint32_t* d_alive = nullptr;
     StepCounters* d_counters = nullptr;
     StepCounters* h_counters = nullptr;  // pinned
     double* d_export = nullptr;
@@ -64,7 +65,7 @@ struct slamrs_gpu_handle {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;   // [PROF_RING][SLAMRS_PHASE_COUNT + 1]
     uint32_t prof_recorded = 0;
-    double prof_ms[SLAMRS_PHASE_COUNT] = {0, 0, 0, 0, 0, 0};
+    double prof_ms[SLAMRS_PHASE_COUNT] = {0, 0, 0, 0, 0, 0, 0};
     uint64_t prof_steps = 0;
     uint64_t step = 0;
     uint64_t launches = 0;
@@ -191,7 +192,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
-    cudaFree(h->d_copies); cudaFree(h->d_pulls); cudaFree(h->d_leaders);
+    cudaFree(h->d_copies); cudaFree(h->d_pulls); cudaFree(h->d_leaders); cudaFree(h->d_alive);
     cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells);
     cudaFree(h->d_history);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -398,6 +399,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_copies, sizeof(CopyItem) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_pulls, sizeof(CopyItem) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_leaders, sizeof(uint32_t) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_alive, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_counters, sizeof(StepCounters)));
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
     memset(h->h_counters, 0, sizeof(StepCounters));
@@ -495,26 +497,34 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->cells_per_grid,
                              h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step);
-    // 2. integrate the scan into every particle's grid
+    h->launches++;
+    // 2. the one exchange step: every GPU needs every particle's weight, pose and slot
     PROF_MARK(h, 1);
-    CU_TRY(h, cudaMemsetAsync(&h->d_counters->saturated, 0, 2 * sizeof(unsigned long long), s));
-    CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_slot[cur], h->d_cells,
-                                h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
-                                (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
-    h->launches += 2;
-    // 3. the one exchange step: every GPU needs every particle's weight, pose and slot
-    PROF_MARK(h, 2);
     if (h->world > 1) {
         std::string err;
         if (comm_all_gather(h->comm, h->d_results + h->first, h->d_results, sizeof(ParticleResult) * h->n_local, s, &err))
             return fail(h, SLAMRS_E_NCCL, err);
     }
-    // 4. normalise, argmax, running sum; systematic resampling indices (replicated on every GPU)
-    PROF_MARK(h, 3);
+    // 3. normalise, argmax, running sum; systematic resampling indices (replicated on every GPU);
+    //    which local particles survive
+    PROF_MARK(h, 2);
+    // zeroes saturated, spilled (adjacent) and n_alive
+    CU_TRY(h, cudaMemsetAsync(&h->d_counters->saturated, 0, 2 * sizeof(unsigned long long), s));
+    CU_TRY(h, cudaMemsetAsync(&h->d_counters->n_alive, 0, sizeof(unsigned long long), s));
     launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, h->d_counters);
+    launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local,
+                      (h->cfg.flags & SLAMRS_FLAG_UPDATE_ALL_PARTICLES) != 0, h->d_alive, h->d_counters);
+    h->launches += 3;
+    // 4. integrate the scan into the grids that survive resampling (all grids in strict mode)
+    PROF_MARK(h, 3);
+    CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive, h->d_slot[cur],
+                                h->d_cells, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
+                                (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
+    h->launches++;
     // 5. plan: which grids stay, which are duplicated locally, which are pulled from a peer
+    PROF_MARK(h, 4);
     PlanArgs pa{};
     pa.results = h->d_results;
     pa.idx = h->d_idx;
@@ -529,20 +539,22 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.history = h->d_history;
     pa.step = h->step;
     launch_plan(s, pa);
-    h->launches += 3;
-    PROF_MARK(h, 4);
-    // 6. grid traffic: NVLink pulls first, barrier, then the local duplicate copies
+    h->launches++;
+    // 6. grid traffic. Across GPUs: barrier (every survivor is integrated), NVLink pulls, barrier
+    //    (nobody still reads a slot that is about to be overwritten), then the local fan-out copies.
+    PROF_MARK(h, 5);
     if (h->world > 1) {
-        launch_copy(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->cells_per_grid, h->num_sms);
-        h->launches++;
         std::string err;
         if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
+        launch_copy(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->cells_per_grid, h->num_sms);
+        h->launches++;
+        if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
     }
-    PROF_MARK(h, 5);
+    PROF_MARK(h, 6);
     launch_copy(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->cells_per_grid,
                 h->num_sms);
     h->launches++;
-    PROF_MARK(h, 6);
+    PROF_MARK(h, 7);
     if (h->profiling) h->prof_recorded++;
     CU_TRY(h, cudaGetLastError());
     h->cur = nxt;
@@ -617,6 +629,7 @@ int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out) {
     out->counter_saturated = c.saturated;
     out->spilled_cells = c.spilled;
     out->window_cells = h->window_cells;
+    out->particles_integrated = c.n_alive;
     out->bytes_per_grid = h->cells_per_grid * sizeof(uint32_t);
     return SLAMRS_OK;
 }
@@ -648,7 +661,7 @@ int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COU
 }
 
 int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_triples) {
-    // four values per step: grids_copied, grids_pulled, distinct_sources, source_reads
+    // five values per step: grids_copied, grids_pulled, distinct_sources, source_reads, particles_integrated
     if (!h || !out_triples || count > STEP_HISTORY) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     std::vector<StepRecord> ring(STEP_HISTORY);
@@ -657,8 +670,8 @@ int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint3
     for (uint32_t i = 0; i < count; ++i) {
         const StepRecord& r = ring[(first_step + i) % STEP_HISTORY];
         if (r.step != first_step + i) return fail(h, SLAMRS_E_INVALID_ARG, "step no longer in the history ring");
-        out_triples[4 * i] = r.n_copies; out_triples[4 * i + 1] = r.n_pulls; out_triples[4 * i + 2] = r.distinct;
-        out_triples[4 * i + 3] = r.n_leaders;
+        out_triples[5 * i] = r.n_copies; out_triples[5 * i + 1] = r.n_pulls; out_triples[5 * i + 2] = r.distinct;
+        out_triples[5 * i + 3] = r.n_leaders; out_triples[5 * i + 4] = r.n_alive;
     }
     return SLAMRS_OK;
 }

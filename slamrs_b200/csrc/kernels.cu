@@ -223,12 +223,14 @@ __host__ __device__ inline int ray_window_cells_upper_bound(int radius, bool vec
 template <bool kVector>
 __global__ void __launch_bounds__(RAY_MAX_THREADS)
 k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
+             const uint32_t* __restrict__ alive_list,
              const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, size_t cells_per_grid, int radius,
              StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];
     __shared__ int s_row_off[RAY_MAX_ROWS + 1];   // first window cell of each row (+ total at [wh])
     __shared__ int s_row_x[RAY_MAX_ROWS];         // x0 | (width << 16)
-    const uint32_t p = blockIdx.x;
+    if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
+    const uint32_t p = alive_list[blockIdx.x];
     const ParticleResult r = results[first_particle + p];
     const float px = r.x, py = r.y, ptheta = r.theta;
     uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
@@ -392,11 +394,13 @@ __host__ __device__ inline int ray_window_cells_upper_bound_packed(int radius) {
 
 __global__ void __launch_bounds__(RAY_MAX_THREADS)
 k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
+             const uint32_t* __restrict__ alive_list,
                     const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, size_t cells_per_grid,
                     int radius, StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
     __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
-    const uint32_t p = blockIdx.x;
+    if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
+    const uint32_t p = alive_list[blockIdx.x];
     const ParticleResult r = results[first_particle + p];
     const float px = r.x, py = r.y, ptheta = r.theta;
     uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
@@ -616,7 +620,8 @@ cudaError_t configure_kernels() {
 }
 
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
-                              uint32_t first_particle, uint32_t n_local, const int32_t* slot_of, uint32_t* cells,
+                              uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
+                              const int32_t* slot_of, uint32_t* cells,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic) {
     int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
@@ -627,7 +632,7 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
         while (radius > 1 && (size_t)ray_window_cells_upper_bound_packed(radius) * 2 > (size_t)RAY_MAX_SMEM) radius--;
         const size_t wmax = (size_t)ray_window_cells_upper_bound_packed(radius);
         *window_cells = wmax;
-        k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, slot_of, cells,
+        k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells,
                                                                   cells_per_grid, radius, counters);
         return cudaSuccess;
     }
@@ -639,10 +644,10 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
     const size_t smem = wmax * 4;
     *window_cells = wmax;
     if (vec)
-        k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, slot_of, cells,
+        k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells,
                                                                cells_per_grid, radius, counters);
     else
-        k_ray_update<false><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, slot_of, cells,
+        k_ray_update<false><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells,
                                                                 cells_per_grid, radius, counters);
     return cudaSuccess;
 }
@@ -759,6 +764,46 @@ void launch_resample_indices(cudaStream_t stream, const ParticleResult* results,
                              StepCounters* counters) {
     k_resample_indices<<<(n_total + 255) / 256, 256, 0, stream>>>(results, cum, n_total, u01_caller, seed, step, idx,
                                                                  pose_next, first_particle, n_local, counters);
+}
+
+// =============================================================================== k_mark_alive
+// A particle that no entry of the index vector selects is dropped by the resampler
+// (particle.rs:88-104 builds the new generation only from old[i]); integrating the scan into its
+// grid would be unobservable work. The ray kernel therefore runs AFTER the indices are known, on
+// the survivors only. With all_particles the list is the identity (the reference's order of work).
+__global__ void __launch_bounds__(256)
+k_mark_alive(const uint32_t* __restrict__ idx, uint32_t n_total, uint32_t first_particle, uint32_t n_local,
+             bool all_particles, uint32_t* __restrict__ alive_list, StepCounters* counters) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false;
+    if (j < n_local) {
+        if (all_particles) {
+            alive = true;
+        } else {
+            const uint32_t v = first_particle + j;
+            uint32_t lo = 0, hi = n_total;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (idx[mid] < v) lo = mid + 1; else hi = mid;
+            }
+            alive = lo < n_total && idx[lo] == v;
+        }
+    }
+    // warp-aggregated append (order is irrelevant: particles are independent)
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&counters->n_alive, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (alive) alive_list[base + __popc(m & ((1u << lane) - 1u))] = j;
+    }
+}
+
+void launch_mark_alive(cudaStream_t stream, const uint32_t* idx, uint32_t n_total, uint32_t first_particle,
+                       uint32_t n_local, bool all_particles, uint32_t* alive_list, StepCounters* counters) {
+    k_mark_alive<<<(n_local + 255) / 256, 256, 0, stream>>>(idx, n_total, first_particle, n_local, all_particles,
+                                                           alive_list, counters);
 }
 
 // =============================================================================== k_plan
@@ -931,6 +976,7 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
         if (a.history) {
             StepRecord r;
             r.step = a.step; r.n_copies = nBD; r.n_pulls = nC; r.distinct = distinct; r.n_leaders = n_lead;
+            r.n_alive = a.counters->n_alive;
             a.history[a.step % STEP_HISTORY] = r;
         }
     }

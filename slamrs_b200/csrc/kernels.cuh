@@ -29,6 +29,7 @@ struct StepCounters {
     long long est_slot;                  // physical slot of new-generation particle max_particle, -1 if remote
     unsigned long long est_owner;        // rank that owns it
     unsigned long long n_spare;          // entries of the persistent spare-slot list
+    unsigned long long n_alive;          // local particles whose grid is integrated this step
     double sum;                          // sum of raw weights (particle.rs:50)
     float est_pose[3];                   // estimated_pose(), slam.rs:77-81
     float pad;
@@ -37,7 +38,7 @@ struct StepCounters {
 // per-step record kept on the device so that a pipelined caller can read, after the fact, how
 // many grids each step really moved (the roofline is computed from moved bytes only)
 struct StepRecord {
-    unsigned long long step, n_copies, n_pulls, distinct, n_leaders;
+    unsigned long long step, n_copies, n_pulls, distinct, n_leaders, n_alive;
 };
 constexpr uint32_t STEP_HISTORY = 256;
 constexpr uint32_t COPY_FAN = 16;   // destinations written per source read in k_copy
@@ -61,8 +62,10 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step);
 
 // returns the shared-memory window size in cells through *window_cells
+// alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive)
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
-                              uint32_t first_particle, uint32_t n_local, const int32_t* slot_of, uint32_t* cells,
+                              uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
+                              const int32_t* slot_of, uint32_t* cells,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic);
 
@@ -96,6 +99,11 @@ struct PlanArgs {
     unsigned long long step;
 };
 void launch_plan(cudaStream_t stream, const PlanArgs& a);
+
+// local particles that appear in the index vector (their grid survives resampling); all_particles
+// lists every local particle instead (reference order of work)
+void launch_mark_alive(cudaStream_t stream, const uint32_t* idx, uint32_t n_total, uint32_t first_particle,
+                       uint32_t n_local, bool all_particles, uint32_t* alive_list, StepCounters* counters);
 
 // copies[0..*n_items) full grids; n_items is read on the device
 // leaders == nullptr: plain item-by-item copy (used for the NVLink pulls)
