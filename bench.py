@@ -17,9 +17,12 @@ Legs of the CUDA arm
   e2e    K steps through the reference-facing call sequence of GridMapSlamNode::update
          (node.rs:47-60): update(host scan) -> estimated_pose() -> estimated_likelihood() into a
          pinned host grid; host<->device copies inside the timed region.
-  roofline  the grid-copy kernel (k_copy): algorithmic bytes = bytes_per_grid * (grids
-         written + source grids read (both counted on the device per step), divided by the
-         kernel's own CUDA-event time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  roofline  the grid-copy kernel (k_copy_boxed): bytes the kernel really read + wrote (counted on
+         the device, per step: the informed extent of every grid written + of every source read,
+         one source read feeding up to 16 destinations), divided by the kernel's own CUDA-event
+         time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  full_grid_copy / strict_order_of_work  the same run with whole-grid copies (what Map::clone
+         moves) and with the reference's order of work; results are identical in all modes.
   cpu_baseline  (N=1, rank 0) the CPU oracle on a bounded sample of the same workload.
 """
 from __future__ import annotations
@@ -53,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-order-of-work comparison run")
+    ap.add_argument("--no-full-copy", action="store_true", help="skip the whole-grid-copy comparison run")
+    ap.add_argument("--flags", type=int, default=0, help="slamrs_flags bits for the main run (profiling)")
     return ap.parse_args()
 
 
@@ -290,8 +295,11 @@ def run_cuda(args, wl, rank, world, local):
 
     clocks = ClockSampler(local)
     clocks.start()
-    main = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans, 0, not args.no_e2e)
+    main = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans, args.flags, not args.no_e2e)
     clock_info = clocks.stop()
+    full = None
+    if not args.no_full_copy:
+        full = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans, _lib.FLAG_FULL_GRID_COPY, False)
     strict = None
     if not args.no_strict:
         strict = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans,
@@ -311,7 +319,7 @@ def run_cuda(args, wl, rank, world, local):
 
     ph = main["phase_ms"]
     tmax = reduce_max([main["ms_value"], main.get("ms_e2e", 0.0), strict["ms_value"] if strict else 0.0] +
-                      [ph[k] for k in _lib.PHASES])
+                      [ph[k] for k in _lib.PHASES] + [full["ms_value"] if full else 0.0])
     hist = main["hist"]
     tot = reduce_sum([hist[:, 0].sum(), hist[:, 1].sum(), hist[:, 4].sum()])
     if rank != 0:
@@ -327,8 +335,10 @@ def run_cuda(args, wl, rank, world, local):
     # roofline of the dominant kernel (grid copy), rank 0's own launches: every copied grid is
     # written once; a source grid is read once per fan-out sub-run (<= 16 destinations)
     copy_ms = ph["copy"]
-    copy_bytes = float(grid_bytes) * (copies.sum() + src_reads.sum())
+    copy_bytes = float(hist[:, 5].sum())           # bytes the copy kernel really moved (device-counted)
+    full_bytes = float(grid_bytes) * (copies.sum() + src_reads.sum())   # what whole-grid copies would move
     achieved = copy_bytes / (copy_ms * 1e-3) / 1e9 if copy_ms > 0 else 0.0
+    boxed = (int(args.flags) & _lib.FLAG_FULL_GRID_COPY) == 0 and wl.grid % 8 == 0
     st = main["stats"]
     line = {
         "metric": METRIC, "value": pbu * K / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -338,13 +348,18 @@ def run_cuda(args, wl, rank, world, local):
         "clocks": clock_info,
         "gpu_launches": int(main["launches"]),
         "roofline": {
-            "bound": "hbm", "kernel": "k_copy (resampling grid copies)", "achieved": achieved, "peak": peak,
+            "bound": "hbm", "kernel": ("k_copy_boxed (resampling grid copies, informed extent only)" if boxed
+                                       else "k_copy (resampling grid copies, whole grids)"),
+            "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": ncu_traffic(copy_bytes / K),
             "peak_source": peak_src,
             "bytes_per_launch": copy_bytes / K, "ms_per_launch": copy_ms / K,
             "grids_copied_per_step": float(copies.mean()), "source_reads_per_step": float(src_reads.mean()),
-            "bytes_per_grid": int(grid_bytes),
-            "algorithmic_bytes": "bytes_per_grid * (grids written + source grids read), per launch",
+            "bytes_per_grid": int(grid_bytes), "whole_grid_bytes_per_launch": full_bytes / K,
+            "algorithmic_bytes": "bytes the kernel read + wrote per launch, counted on the device: informed extent of "
+                                 "(grids written + source grids read); whole_grid_bytes_per_launch is what Map::clone "
+                                 "semantics would move for the same copies",
+            "step_frac": (copy_bytes / (ms_value * 1e-3) / 1e9) / peak if peak else None,
         },
         "phases_ms_per_step": {k: float(tmax[3 + i]) / K for i, k in enumerate(_lib.PHASES)},
         "resample": {"grids_copied_per_step_all_gpus": float(tot[0] / K), "grids_pulled_per_step_all_gpus": float(tot[1] / K),
@@ -358,6 +373,20 @@ def run_cuda(args, wl, rank, world, local):
         line["e2e"] = {"value": pbu * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
                        "h2d_bytes_per_step": int(wl.n_beams * (4 + 4 + 1)), "d2h_bytes_per_step": int(12 + 8 * gw * gh),
                        "path": "update(host scan) + estimated_pose() + estimated_likelihood() per step (node.rs:47-60)"}
+    if full:
+        ms_full = float(tmax[3 + len(_lib.PHASES)])
+        fh, fph = full["hist"], full["phase_ms"]
+        fbytes = float(fh[:, 5].sum())
+        line["full_grid_copy"] = {
+            "value": pbu * K / (ms_full * 1e-3), "unit": UNIT, "ms_per_step": ms_full / K,
+            "note": "SLAMRS_FLAG_FULL_GRID_COPY: every resampling copy moves the whole W*H grid, as Map::clone does "
+                    "(particle.rs:97-100); identical results",
+            "roofline": {"kernel": "k_copy", "achieved": fbytes / (fph["copy"] * 1e-3) / 1e9 if fph["copy"] > 0 else 0.0,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": (fbytes / (fph["copy"] * 1e-3) / 1e9) / peak if peak and fph["copy"] > 0 else None,
+                         "bytes_per_launch": fbytes / K, "ms_per_launch": fph["copy"] / K,
+                         "step_frac": (fbytes / (ms_full * 1e-3) / 1e9) / peak if peak else None},
+            "phases_ms_per_step": {k: v / K for k, v in fph.items()}}
     if strict:
         line["strict_order_of_work"] = {
             "value": pbu * K / (ms_strict * 1e-3), "unit": UNIT, "ms_per_step": ms_strict / K,

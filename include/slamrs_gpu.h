@@ -57,7 +57,12 @@ enum slamrs_flags {
      * (slam.rs:65-68), instead of only into the grids that survive this step's resampling. The
      * observable state is identical either way (dropped particles are never read again); the
      * default skips the unobservable work. */
-    SLAMRS_FLAG_UPDATE_ALL_PARTICLES = 2
+    SLAMRS_FLAG_UPDATE_ALL_PARTICLES = 2,
+    /* Resampling copies whole grids (W*H cells each), as `Map::clone` does (particle.rs:97-100).
+     * The default moves only the informed extent of each grid -- cells outside it are still at
+     * the prior in source and destination alike, so the result is identical. Grids whose side is
+     * not a multiple of 8 cells always use whole-grid copies. */
+    SLAMRS_FLAG_FULL_GRID_COPY = 4
 };
 
 typedef struct slamrs_gpu_handle slamrs_gpu_handle;
@@ -94,6 +99,7 @@ typedef struct slamrs_gpu_stats {
     uint64_t window_cells;     /* shared-memory window size used by the ray kernel (cells) */
     uint64_t bytes_per_grid;   /* device bytes of one particle grid */
     uint64_t particles_integrated; /* local particles whose grid received the scan this step */
+    uint64_t copy_bytes;       /* bytes the resampling copies read + wrote in this step (device-counted) */
 } slamrs_gpu_stats;
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -176,9 +182,11 @@ enum slamrs_phase {
 int slamrs_gpu_set_profiling(slamrs_gpu_handle* h, int enabled);
 int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COUNT], uint64_t* out_steps);
 /* Per-step history (ring of the last 256 steps): for step indices first_step .. first_step+count-1
- * writes 5 values per step: {grids_copied, grids_pulled, distinct_sources, source_reads,
- * particles_integrated} where source_reads = number of times the copy kernel read a source grid
- * (one read feeds up to 16 destination grids). */
+ * writes SLAMRS_HISTORY_VALUES values per step: {grids_copied, grids_pulled, distinct_sources,
+ * source_reads, particles_integrated, copy_bytes} where source_reads = number of times the copy
+ * kernel read a source grid (one read feeds up to 16 destination grids) and copy_bytes = bytes the
+ * copy kernels really read + wrote. */
+#define SLAMRS_HISTORY_VALUES 6
 int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_values);
 
 /* current generation, this rank's shard: n_local * {x, y, theta} */

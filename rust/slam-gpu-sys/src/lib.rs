@@ -57,6 +57,7 @@ pub struct slamrs_gpu_stats {
     pub window_cells: u64,
     pub bytes_per_grid: u64,
     pub particles_integrated: u64,
+    pub copy_bytes: u64,
 }
 
 extern "C" {

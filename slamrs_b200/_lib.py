@@ -15,6 +15,8 @@ E_INVALID_ARG, E_CUDA, E_NCCL, E_OOM, E_NO_DEVICE, E_STAGING, E_NOT_LOCAL, E_INT
 RNG_SHARED_STREAM, RNG_CALLER = 0, 1
 FLAG_GENERIC_RAY_KERNEL = 1
 FLAG_UPDATE_ALL_PARTICLES = 2
+FLAG_FULL_GRID_COPY = 4
+HISTORY_VALUES = 6
 
 EXPORTS = [
     "slamrs_gpu_grid_cells", "slamrs_gpu_nccl_unique_id", "slamrs_gpu_create", "slamrs_gpu_destroy",
@@ -46,7 +48,8 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "step", "grids_copied", "grids_pulled", "distinct_sources", "resample_clamped",
-        "counter_saturated", "spilled_cells", "window_cells", "bytes_per_grid", "particles_integrated")]
+        "counter_saturated", "spilled_cells", "window_cells", "bytes_per_grid", "particles_integrated",
+        "copy_bytes")]
 
 
 class SlamrsGpuError(RuntimeError):

@@ -8,6 +8,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -29,7 +30,11 @@ struct slamrs_gpu_handle {
     uint32_t n_slots = 0, n_spare = 0;
     MapGeom geom{};
 
-    uint32_t* d_cells = nullptr;
+    void* d_pool = nullptr;      // one allocation: [SlotMeta x 2*n_local | grid slots]; peers map it whole
+    size_t pool_header = 0;      // bytes in front of the first grid slot
+    SlotMeta* d_meta = nullptr;  // = d_pool
+    uint32_t* d_cells = nullptr; // = d_pool + pool_header
+    bool boxed_copy = false;     // extent-limited copies (needs rows that are multiples of 32 bytes)
     int32_t* d_slot[2] = {nullptr, nullptr};
     float* d_pose[2] = {nullptr, nullptr};
     int cur = 0;
@@ -55,6 +60,7 @@ struct slamrs_gpu_handle {
 
     Comm* comm = nullptr;
     uint32_t** d_peer_cells = nullptr;         // device array [world]
+    SlotMeta** d_peer_meta = nullptr;          // device array [world]
     std::vector<void*> ipc_opened;             // peer mappings to close
     StepRecord* d_history = nullptr;
     bool scan_external = false;
@@ -131,9 +137,9 @@ int setup_peers(slamrs_gpu_handle* h) {
     std::vector<PeerInfo> all(W);
     PeerInfo mine;
     memset(&mine, 0, sizeof(mine));
-    CU_TRY(h, cudaIpcGetMemHandle(&mine.handle, h->d_cells));
+    CU_TRY(h, cudaIpcGetMemHandle(&mine.handle, h->d_pool));
     mine.pid = (uint64_t)getpid();
-    mine.ptr = (uint64_t)(uintptr_t)h->d_cells;
+    mine.ptr = (uint64_t)(uintptr_t)h->d_pool;
     mine.device = h->device;
     PeerInfo* d_all = nullptr;
     CU_TRY(h, cudaMalloc(&d_all, sizeof(PeerInfo) * W));
@@ -147,9 +153,9 @@ int setup_peers(slamrs_gpu_handle* h) {
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(d_all);
 
-    std::vector<uint32_t*> peers(W, nullptr);
+    std::vector<char*> peers(W, nullptr);   // pool base of every rank (same header size everywhere)
     for (uint32_t r = 0; r < W; ++r) {
-        if (r == h->rank) { peers[r] = h->d_cells; continue; }
+        if (r == h->rank) { peers[r] = (char*)h->d_pool; continue; }
         if (all[r].pid == mine.pid) {
             // same process: plain peer access to the other device's allocation
             int can = 0;
@@ -159,16 +165,24 @@ int setup_peers(slamrs_gpu_handle* h) {
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
                 return fail(h, SLAMRS_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
             cudaGetLastError();
-            peers[r] = (uint32_t*)(uintptr_t)all[r].ptr;
+            peers[r] = (char*)(uintptr_t)all[r].ptr;
         } else {
             void* p = nullptr;
             CU_TRY(h, cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess));
             h->ipc_opened.push_back(p);
-            peers[r] = (uint32_t*)p;
+            peers[r] = (char*)p;
         }
     }
+    std::vector<uint32_t*> pcells(W);
+    std::vector<SlotMeta*> pmeta(W);
+    for (uint32_t r = 0; r < W; ++r) {
+        pmeta[r] = (SlotMeta*)peers[r];
+        pcells[r] = (uint32_t*)(peers[r] + h->pool_header);
+    }
     CU_TRY(h, cudaMalloc(&h->d_peer_cells, sizeof(uint32_t*) * W));
-    CU_TRY(h, cudaMemcpy(h->d_peer_cells, peers.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_peer_cells, pcells.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMalloc(&h->d_peer_meta, sizeof(SlotMeta*) * W));
+    CU_TRY(h, cudaMemcpy(h->d_peer_meta, pmeta.data(), sizeof(SlotMeta*) * W, cudaMemcpyHostToDevice));
     return SLAMRS_OK;
 }
 
@@ -185,7 +199,7 @@ void free_all(slamrs_gpu_handle* h) {
     h->ipc_opened.clear();
     comm_destroy(h->comm);
     h->comm = nullptr;
-    cudaFree(h->d_cells);
+    cudaFree(h->d_pool);
     cudaFree(h->d_slot[0]); cudaFree(h->d_slot[1]);
     cudaFree(h->d_pose[0]); cudaFree(h->d_pose[1]);
     cudaFree(h->d_results); cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx);
@@ -193,7 +207,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
     cudaFree(h->d_copies); cudaFree(h->d_pulls); cudaFree(h->d_leaders); cudaFree(h->d_alive);
-    cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells);
+    cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells); cudaFree(h->d_peer_meta);
     cudaFree(h->d_history);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->prof_events.clear();
@@ -374,8 +388,14 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     }
     h->n_slots = h->n_local + h->n_spare;
 
-    CREATE_CU(cudaMalloc(&h->d_cells, (size_t)h->n_slots * grid_bytes));
-    CREATE_CU(cudaMemsetAsync(h->d_cells, 0, (size_t)h->n_slots * grid_bytes, h->stream));  // ln(0.5/0.5) = 0
+    // the header holds one SlotMeta per possible slot; its size depends on n_local only, so every
+    // rank can locate a peer's slots and extents from the peer's pool base alone
+    h->pool_header = (sizeof(SlotMeta) * 2 * (size_t)h->n_local + 4095) & ~(size_t)4095;
+    CREATE_CU(cudaMalloc(&h->d_pool, h->pool_header + (size_t)h->n_slots * grid_bytes));
+    h->d_meta = (SlotMeta*)h->d_pool;
+    h->d_cells = (uint32_t*)((char*)h->d_pool + h->pool_header);
+    CREATE_CU(cudaMemsetAsync(h->d_pool, 0, h->pool_header + (size_t)h->n_slots * grid_bytes, h->stream));  // ln(0.5/0.5) = 0
+    h->boxed_copy = (cfg->flags & SLAMRS_FLAG_FULL_GRID_COPY) == 0 && cfg->grid_w % 8u == 0u;
     for (int i = 0; i < 2; ++i) {
         CREATE_CU(cudaMalloc(&h->d_slot[i], sizeof(int32_t) * h->n_local));
         CREATE_CU(cudaMalloc(&h->d_pose[i], sizeof(float) * 3 * h->n_local));
@@ -408,7 +428,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMemsetAsync(h->d_history, 0xff, sizeof(StepRecord) * STEP_HISTORY, h->stream));
     CREATE_CU(cudaMalloc(&h->d_barrier, sizeof(int)));
     CREATE_CU(cudaMemsetAsync(h->d_barrier, 0, sizeof(int), h->stream));
-    launch_init_slots(h->stream, h->d_slot[0], h->n_local, h->d_spare, h->n_spare, h->d_counters, h->rank);
+    launch_init_slots(h->stream, h->d_slot[0], h->n_local, h->d_spare, h->n_spare, h->d_counters, h->rank, h->d_meta);
     h->launches++;
     CREATE_CU(cudaGetLastError());
 
@@ -492,6 +512,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         if (prc) return prc;
     }
     const int cur = h->cur, nxt = cur ^ 1;
+    const size_t grid_bytes = h->cells_per_grid * sizeof(uint32_t);
 
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
@@ -510,7 +531,8 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 2);
     // zeroes saturated, spilled (adjacent) and n_alive
     CU_TRY(h, cudaMemsetAsync(&h->d_counters->saturated, 0, 2 * sizeof(unsigned long long), s));
-    CU_TRY(h, cudaMemsetAsync(&h->d_counters->n_alive, 0, sizeof(unsigned long long), s));
+    // n_alive and copy_bytes (adjacent)
+    CU_TRY(h, cudaMemsetAsync(&h->d_counters->n_alive, 0, 2 * sizeof(unsigned long long), s));
     launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, h->d_counters);
@@ -520,7 +542,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     // 4. integrate the scan into the grids that survive resampling (all grids in strict mode)
     PROF_MARK(h, 3);
     CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive, h->d_slot[cur],
-                                h->d_cells, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
+                                h->d_cells, h->d_meta, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
                                 (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
     h->launches++;
     // 5. plan: which grids stay, which are duplicated locally, which are pulled from a peer
@@ -535,6 +557,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.copies = h->d_copies; pa.pulls = h->d_pulls; pa.leaders = h->d_leaders;
     pa.cells = h->d_cells; pa.cells_per_grid = h->cells_per_grid;
     pa.peer_cells = h->d_peer_cells;
+    pa.meta = h->d_meta; pa.peer_meta = h->d_peer_meta;
     pa.counters = h->d_counters;
     pa.history = h->d_history;
     pa.step = h->step;
@@ -546,15 +569,32 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     if (h->world > 1) {
         std::string err;
         if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
-        launch_copy(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->cells_per_grid, h->num_sms);
-        h->launches++;
+        if (h->boxed_copy) {
+            launch_copy_boxed(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->geom.gw, h->d_counters, h->num_sms);
+        } else {
+            launch_copy(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->cells_per_grid, h->num_sms);
+            launch_account_full_copy(s, &h->d_counters->n_pulls, nullptr, grid_bytes, h->d_counters);
+            h->launches++;
+        }
+        launch_commit_boxes(s, h->d_pulls, &h->d_counters->n_pulls, h->n_local, h->d_counters, nullptr);
+        h->launches += 2;
         if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
     }
     PROF_MARK(h, 6);
-    launch_copy(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->cells_per_grid,
-                h->num_sms);
+    if (h->boxed_copy) {
+        launch_copy_boxed(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->geom.gw,
+                          h->d_counters, h->num_sms);
+    } else {
+        launch_copy(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->cells_per_grid,
+                    h->num_sms);
+        launch_account_full_copy(s, &h->d_counters->n_copies, &h->d_counters->n_leaders, grid_bytes, h->d_counters);
+        h->launches++;
+    }
     h->launches++;
     PROF_MARK(h, 7);
+    launch_commit_boxes(s, h->d_copies, &h->d_counters->n_copies, h->n_local, h->d_counters,
+                        h->d_history + (h->step % STEP_HISTORY));
+    h->launches++;
     if (h->profiling) h->prof_recorded++;
     CU_TRY(h, cudaGetLastError());
     h->cur = nxt;
@@ -631,6 +671,7 @@ int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out) {
     out->window_cells = h->window_cells;
     out->particles_integrated = c.n_alive;
     out->bytes_per_grid = h->cells_per_grid * sizeof(uint32_t);
+    out->copy_bytes = c.copy_bytes;
     return SLAMRS_OK;
 }
 
@@ -661,7 +702,7 @@ int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COU
 }
 
 int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_triples) {
-    // five values per step: grids_copied, grids_pulled, distinct_sources, source_reads, particles_integrated
+    // six values per step: grids_copied, grids_pulled, distinct_sources, source_reads, particles_integrated, copy_bytes
     if (!h || !out_triples || count > STEP_HISTORY) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     std::vector<StepRecord> ring(STEP_HISTORY);
@@ -670,8 +711,8 @@ int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint3
     for (uint32_t i = 0; i < count; ++i) {
         const StepRecord& r = ring[(first_step + i) % STEP_HISTORY];
         if (r.step != first_step + i) return fail(h, SLAMRS_E_INVALID_ARG, "step no longer in the history ring");
-        out_triples[5 * i] = r.n_copies; out_triples[5 * i + 1] = r.n_pulls; out_triples[5 * i + 2] = r.distinct;
-        out_triples[5 * i + 3] = r.n_leaders; out_triples[5 * i + 4] = r.n_alive;
+        uint64_t* o = out_triples + (size_t)SLAMRS_HISTORY_VALUES * i;
+        o[0] = r.n_copies; o[1] = r.n_pulls; o[2] = r.distinct; o[3] = r.n_leaders; o[4] = r.n_alive; o[5] = r.copy_bytes;
     }
     return SLAMRS_OK;
 }
@@ -752,6 +793,24 @@ int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t
     if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->d_cells + (size_t)slot * h->cells_per_grid, cells, sizeof(uint32_t) * h->n_cells,
                               cudaMemcpyHostToDevice, h->stream));
+    // extent of the informed cells of the new image
+    const int gw = (int)h->geom.gw, gh = (int)h->geom.gh;
+    int x0 = gw, y0 = gh, x1 = -1, y1 = -1;
+    for (int y = 0; y < gh; ++y) {
+        const uint32_t* row = cells + (size_t)y * gw;
+        int fx = -1, lx = -1;
+        for (int x = 0; x < gw; ++x)
+            if (row[x]) { if (fx < 0) fx = x; lx = x; }
+        if (fx >= 0) {
+            if (fx < x0) x0 = fx;
+            if (lx > x1) x1 = lx;
+            if (y < y0) y0 = y;
+            y1 = y;
+        }
+    }
+    SlotMeta m{0, 0, 0, 0, 0, 0, 0, 0};
+    if (x1 >= 0) { m.x0 = x0 & ~7; m.y0 = y0; m.x1 = std::min(gw, (x1 + 8) & ~7); m.y1 = y1 + 1; }
+    CU_TRY(h, cudaMemcpyAsync(h->d_meta + slot, &m, sizeof(m), cudaMemcpyHostToDevice, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return SLAMRS_OK;
 }

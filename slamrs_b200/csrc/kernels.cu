@@ -197,6 +197,25 @@ __device__ __forceinline__ void global_cell_add(uint32_t* addr, uint32_t inc, bo
 }
 
 constexpr int RAY_MAX_THREADS = 512;
+
+// touched-extent bookkeeping of one CTA: s_ext = {xmin, ymin, xmax, ymax} (inclusive cells)
+__device__ __forceinline__ void ext_init(int* s_ext) {
+    if (threadIdx.x == 0) { s_ext[0] = 0x7fffffff; s_ext[1] = 0x7fffffff; s_ext[2] = -1; s_ext[3] = -1; }
+}
+__device__ __forceinline__ void ext_add(int* s_ext, int xmin, int ymin, int xmax, int ymax) {
+    if (xmax < xmin) return;
+    atomicMin(&s_ext[0], xmin); atomicMin(&s_ext[1], ymin);
+    atomicMax(&s_ext[2], xmax); atomicMax(&s_ext[3], ymax);
+}
+// union the CTA's touched extent into the slot's box (x aligned to 8 cells); one thread, after a barrier
+__device__ __forceinline__ void ext_commit(const int* s_ext, SlotMeta* meta, int gw) {
+    if (s_ext[2] < s_ext[0]) return;
+    SlotMeta b = *meta;
+    const int x0 = s_ext[0] & ~7, x1 = min(gw, (s_ext[2] + 8) & ~7), y0 = s_ext[1], y1 = s_ext[3] + 1;
+    if (b.x1 <= b.x0) { b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; }
+    else { b.x0 = min(b.x0, x0); b.y0 = min(b.y0, y0); b.x1 = max(b.x1, x1); b.y1 = max(b.y1, y1); }
+    *meta = b;
+}
 constexpr int RAY_MAX_RADIUS = 150;                    // rows of the window: 2 * radius + 1
 constexpr int RAY_MAX_ROWS = 2 * RAY_MAX_RADIUS + 1;
 constexpr int RAY_WB_BATCH = 6;                        // write-back: global loads in flight per thread
@@ -224,13 +243,15 @@ template <bool kVector>
 __global__ void __launch_bounds__(RAY_MAX_THREADS)
 k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
              const uint32_t* __restrict__ alive_list,
-             const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, size_t cells_per_grid, int radius,
-             StepCounters* counters) {
+             const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
+             size_t cells_per_grid, int radius, StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];
     __shared__ int s_row_off[RAY_MAX_ROWS + 1];   // first window cell of each row (+ total at [wh])
     __shared__ int s_row_x[RAY_MAX_ROWS];         // x0 | (width << 16)
+    __shared__ int s_ext[4];
     if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
     const uint32_t p = alive_list[blockIdx.x];
+    ext_init(s_ext);
     const ParticleResult r = results[first_particle + p];
     const float px = r.x, py = r.y, ptheta = r.theta;
     uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
@@ -310,6 +331,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                 }
                 if (!in_window) {  // beyond the window (range larger than shared memory allows)
                     global_cell_add(&grid[(size_t)y * geom.gh + x], inc, &saturated);
+                    ext_add(s_ext, x, y, x, y);
                     spilled++;
                 }
             }
@@ -319,6 +341,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
 
     // ---- write-back: grid += window, saturating per 16-bit counter, untouched groups skipped.
     // RAY_WB_BATCH independent global loads are issued per thread before the first dependent store.
+    int exmin = 0x7fffffff, eymin = 0x7fffffff, exmax = -1, eymax = -1;   // this thread's touched extent
     if (kVector) {
         const int total4 = wcells >> 2;
         const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
@@ -340,7 +363,10 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                             if (s_row_off[mid] <= 4 * i) lo = mid; else hi = mid;
                         }
                         const int lx = 4 * i - s_row_off[lo];
-                        gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + (s_row_x[lo] & 0xffff) + lx);
+                        const int gx0 = (s_row_x[lo] & 0xffff) + lx;
+                        exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 3);
+                        eymin = min(eymin, wy0 + lo); eymax = max(eymax, wy0 + lo);
+                        gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + gx0);
                     }
                 }
             }
@@ -366,10 +392,15 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                 if (d != 0u) {
                     uint32_t* g = grid + (size_t)(wy0 + ly) * geom.gh + x0 + c;
                     *g = cell_sat_add(*g, d, &saturated);
+                    exmin = min(exmin, x0 + c); exmax = max(exmax, x0 + c);
+                    eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
                 }
             }
         }
     }
+    ext_add(s_ext, exmin, eymin, exmax, eymax);
+    __syncthreads();
+    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 }
@@ -395,12 +426,14 @@ __host__ __device__ inline int ray_window_cells_upper_bound_packed(int radius) {
 __global__ void __launch_bounds__(RAY_MAX_THREADS)
 k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
              const uint32_t* __restrict__ alive_list,
-                    const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, size_t cells_per_grid,
-                    int radius, StepCounters* counters) {
+                    const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
+                    size_t cells_per_grid, int radius, StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
     __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
+    __shared__ int s_ext[4];
     if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
     const uint32_t p = alive_list[blockIdx.x];
+    ext_init(s_ext);
     const ParticleResult r = results[first_particle + p];
     const float px = r.x, py = r.y, ptheta = r.theta;
     uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
@@ -527,6 +560,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                     }
                     if (!done) {
                         global_cell_add(&grid[(size_t)y * geom.gh + x], is_free ? CELL_FREE_INC : CELL_OCC_INC, &saturated);
+                        ext_add(s_ext, x, y, x, y);
                         spilled++;
                     }
                 }
@@ -565,6 +599,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     const int total8 = wcells >> 3;
     const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
     constexpr int BATCH = 4;
+    int exmin = 0x7fffffff, eymin = 0x7fffffff, exmax = -1, eymax = -1;   // this thread's touched extent
     for (int base = threadIdx.x; base < total8; base += blockDim.x * BATCH) {
         uint4 d[BATCH], va[BATCH], vb[BATCH];
         uint4* gp[BATCH];
@@ -583,7 +618,10 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                         if (s_row[mid].x <= 8 * i) lo = mid; else hi = mid;
                     }
                     const int lx = 8 * i - s_row[lo].x;
-                    gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + (s_row[lo].y & 0xffff) + lx);
+                    const int gx0 = (s_row[lo].y & 0xffff) + lx;
+                    exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
+                    eymin = min(eymin, wy0 + lo); eymax = max(eymax, wy0 + lo);
+                    gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + gx0);
                 }
             }
         }
@@ -606,6 +644,9 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
             }
         }
     }
+    ext_add(s_ext, exmin, eymin, exmax, eymax);
+    __syncthreads();
+    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 }
@@ -621,7 +662,7 @@ cudaError_t configure_kernels() {
 
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
-                              const int32_t* slot_of, uint32_t* cells,
+                              const int32_t* slot_of, uint32_t* cells, SlotMeta* meta,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic) {
     int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
@@ -632,7 +673,7 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
         while (radius > 1 && (size_t)ray_window_cells_upper_bound_packed(radius) * 2 > (size_t)RAY_MAX_SMEM) radius--;
         const size_t wmax = (size_t)ray_window_cells_upper_bound_packed(radius);
         *window_cells = wmax;
-        k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells,
+        k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
                                                                   cells_per_grid, radius, counters);
         return cudaSuccess;
     }
@@ -644,10 +685,10 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
     const size_t smem = wmax * 4;
     *window_cells = wmax;
     if (vec)
-        k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells,
+        k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
                                                                cells_per_grid, radius, counters);
     else
-        k_ray_update<false><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells,
+        k_ray_update<false><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
                                                                 cells_per_grid, radius, counters);
     return cudaSuccess;
 }
@@ -908,6 +949,8 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             CopyItem it;
             it.src = a.peer_cells[owner] + (size_t)sslot * a.cells_per_grid;
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
+            it.src_meta = a.peer_meta[owner] + sslot;
+            it.dst_meta = a.meta + dslot;
             a.pulls[pc] = it;
             pc++;
         } else if (cls == 1) {
@@ -917,6 +960,8 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             CopyItem it;
             it.src = a.cells + (size_t)a.slot_old[src - lo] * a.cells_per_grid;
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
+            it.src_meta = a.meta + a.slot_old[src - lo];
+            it.dst_meta = a.meta + dslot;
             a.copies[pbd] = it;
             const uint32_t m_first = lower_bound_u32(a.idx, lo, hi, src) - lo;
             const bool lead = ((m - m_first - 1u) % COPY_FAN) == 0u;
@@ -940,6 +985,8 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             CopyItem it;
             it.src = a.cells + (size_t)a.slot_new[m_first] * a.cells_per_grid;
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
+            it.src_meta = a.meta + a.slot_new[m_first];
+            it.dst_meta = a.meta + dslot;
             a.copies[pbd] = it;
             const bool lead = ((m - m_first - 1u) % COPY_FAN) == 0u;
             a.need[m] = lead ? 7 : 3;
@@ -977,6 +1024,7 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             StepRecord r;
             r.step = a.step; r.n_copies = nBD; r.n_pulls = nC; r.distinct = distinct; r.n_leaders = n_lead;
             r.n_alive = a.counters->n_alive;
+            r.copy_bytes = 0; r.pad = 0;
             a.history[a.step % STEP_HISTORY] = r;
         }
     }
@@ -1058,6 +1106,140 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
     k_copy<<<num_sms * COPY_CTAS_PER_SM, COPY_THREADS, 0, stream>>>(items, leaders, n_items, n_leaders, v8);
 }
 
+// =============================================================================== k_copy_boxed
+// Extent-limited grid copy. A grid is zero outside its extent (SlotMeta), so cloning it means:
+// copy the source's extent and clear whatever else the destination slot's previous tenant had
+// informed. Work item = (fan-out sub-run, band of rows of the union U of the source extent and
+// the sub-run's destination extents); the number of bands per sub-run is chosen on the device so
+// that every CTA gets several items. Inside a band the (row, 32-byte unit) pairs of U are
+// linearised over the CTA's threads: each thread issues COPY_UNROLL independent 256-bit loads
+// (zero outside the source extent), then stores each value to every destination whose own write
+// region (source extent U destination extent) contains it. Bytes that really moved are counted
+// and are what the roofline in bench.py uses.
+constexpr uint32_t BOX_MAX_BANDS = 128;
+
+__device__ __forceinline__ bool meta_empty(const SlotMeta& m) { return m.x1 <= m.x0 || m.y1 <= m.y0; }
+
+__global__ void __launch_bounds__(COPY_THREADS)
+k_copy_boxed(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
+             const unsigned long long* __restrict__ n_items, const unsigned long long* __restrict__ n_leaders,
+             uint32_t row_units /* 32-byte units per physical grid row */, StepCounters* counters) {
+    __shared__ int4 s_wbox[COPY_FAN];       // write region of each destination, in (unit, row) coordinates
+    __shared__ V8* s_dst[COPY_FAN];
+    const unsigned long long n = *n_items;
+    const unsigned long long nl = leaders ? *n_leaders : n;
+    if (nl == 0) return;
+    // bands per sub-run: about 6 work items per CTA in total
+    unsigned long long want = ((unsigned long long)gridDim.x * 6ull + nl - 1ull) / nl;
+    const uint32_t bands = (uint32_t)(want < 1ull ? 1ull : (want > BOX_MAX_BANDS ? BOX_MAX_BANDS : want));
+    const unsigned long long total = nl * bands;
+    unsigned long long moved = 0;   // 32-byte units read + written by this thread
+    for (unsigned long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const unsigned long long q = w / bands;
+        const uint32_t band = (uint32_t)(w - q * bands);
+        const unsigned long long k = leaders ? leaders[q] : q;
+        const CopyItem it = items[k];
+        const SlotMeta sm = *it.src_meta;
+        const bool s_has = !meta_empty(sm);
+        // source extent in units
+        const int sx0 = sm.x0 >> 3, sx1 = sm.x1 >> 3, sy0 = sm.y0, sy1 = sm.y1;
+        uint32_t fan = 1;
+        if (leaders) {
+            while (fan < COPY_FAN && k + fan < n && items[k + fan].src == it.src) fan++;
+        }
+        __syncthreads();   // previous item's shared boxes are no longer read
+        if (threadIdx.x < fan) {
+            const CopyItem itf = items[k + threadIdx.x];
+            const SlotMeta dm = *itf.dst_meta;
+            int4 wb;
+            if (meta_empty(dm)) wb = s_has ? make_int4(sx0, sy0, sx1, sy1) : make_int4(0, 0, 0, 0);
+            else if (!s_has) wb = make_int4(dm.x0 >> 3, dm.y0, dm.x1 >> 3, dm.y1);
+            else wb = make_int4(min(sx0, dm.x0 >> 3), min(sy0, dm.y0), max(sx1, dm.x1 >> 3), max(sy1, dm.y1));
+            s_wbox[threadIdx.x] = wb;
+            s_dst[threadIdx.x] = reinterpret_cast<V8*>(itf.dst);
+        }
+        __syncthreads();
+        // U = union of the write regions
+        int ux0 = 0x7fffffff, uy0 = 0x7fffffff, ux1 = -1, uy1 = -1;
+        for (uint32_t f = 0; f < fan; ++f) {
+            const int4 wb = s_wbox[f];
+            if (wb.z > wb.x && wb.w > wb.y) { ux0 = min(ux0, wb.x); uy0 = min(uy0, wb.y); ux1 = max(ux1, wb.z); uy1 = max(uy1, wb.w); }
+        }
+        if (ux1 <= ux0) continue;
+        const int rows = uy1 - uy0;
+        const int rows_per_band = (rows + (int)bands - 1) / (int)bands;
+        const int r0 = uy0 + (int)band * rows_per_band, r1 = min(uy1, r0 + rows_per_band);
+        if (r0 >= r1) continue;
+        const uint32_t uw = (uint32_t)(ux1 - ux0);
+        const uint32_t count = (uint32_t)(r1 - r0) * uw;
+        const V8* src = reinterpret_cast<const V8*>(it.src);
+        for (uint32_t base = threadIdx.x; base < count; base += COPY_THREADS * COPY_UNROLL) {
+            V8 v[COPY_UNROLL];
+            int ex[COPY_UNROLL], ey[COPY_UNROLL];
+#pragma unroll
+            for (int u = 0; u < COPY_UNROLL; ++u) {
+                const uint32_t i = base + u * COPY_THREADS;
+                ey[u] = -1; ex[u] = 0;
+                v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
+                if (i < count) {
+                    const uint32_t rr = i / uw;
+                    ey[u] = r0 + (int)rr;
+                    ex[u] = ux0 + (int)(i - rr * uw);
+                    if (s_has && ex[u] >= sx0 && ex[u] < sx1 && ey[u] >= sy0 && ey[u] < sy1) {
+                        v[u] = ld_stream_v8(src + (size_t)ey[u] * row_units + ex[u]);
+                        moved++;
+                    }
+                }
+            }
+            for (uint32_t f = 0; f < fan; ++f) {
+                const int4 wb = s_wbox[f];
+                V8* dst = s_dst[f];
+#pragma unroll
+                for (int u = 0; u < COPY_UNROLL; ++u) {
+                    if (ey[u] >= wb.y && ey[u] < wb.w && ex[u] >= wb.x && ex[u] < wb.z) {
+                        st_stream_v8(dst + (size_t)ey[u] * row_units + ex[u], v[u]);
+                        moved++;
+                    }
+                }
+            }
+        }
+    }
+    // bytes actually moved, for the roofline (one atomic per warp)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
+    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&counters->copy_bytes, moved * 32ull);
+}
+
+void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
+                       const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t row_cells,
+                       StepCounters* counters, int num_sms) {
+    k_copy_boxed<<<num_sms * COPY_CTAS_PER_SM, COPY_THREADS, 0, stream>>>(items, leaders, n_items, n_leaders,
+                                                                         row_cells / 8u, counters);
+}
+
+__global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigned long long* __restrict__ n_items,
+                               StepCounters* counters, StepRecord* record) {
+    const unsigned long long n = *n_items;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (unsigned long long)gridDim.x * blockDim.x)
+        *items[k].dst_meta = *items[k].src_meta;   // sources are never destinations of the same launch
+    if (record && blockIdx.x == 0 && threadIdx.x == 0) record->copy_bytes = counters->copy_bytes;
+}
+void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,
+                         StepCounters* counters, StepRecord* record) {
+    const uint32_t blocks = (max_items + 255u) / 256u;
+    k_commit_boxes<<<blocks ? blocks : 1, 256, 0, stream>>>(items, n_items, counters, record);
+}
+
+__global__ void k_account_full_copy(const unsigned long long* n_items, const unsigned long long* n_leaders,
+                                    unsigned long long bytes_per_grid, StepCounters* counters) {
+    counters->copy_bytes += bytes_per_grid * (*n_items + (n_leaders ? *n_leaders : *n_items));
+}
+void launch_account_full_copy(cudaStream_t stream, const unsigned long long* n_items, const unsigned long long* n_leaders,
+                              size_t bytes_per_grid, StepCounters* counters) {
+    k_account_full_copy<<<1, 1, 0, stream>>>(n_items, n_leaders, (unsigned long long)bytes_per_grid, counters);
+}
+
 // =============================================================================== k_export
 
 __global__ void __launch_bounds__(256)
@@ -1089,8 +1271,9 @@ void launch_export_log_odds(cudaStream_t stream, const uint32_t* grid, uint32_t 
 // =============================================================================== init
 
 __global__ void k_init_slots(int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
-                             StepCounters* counters, uint32_t rank) {
+                             StepCounters* counters, uint32_t rank, SlotMeta* meta) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_local + n_spare) meta[i] = SlotMeta{0, 0, 0, 0, 0, 0, 0, 0};   // empty: every cell is prior
     if (i < n_local) slot_of[i] = (int32_t)i;
     if (i < n_spare) spare_list[i] = (int32_t)(n_local + i);
     if (i == 0) {
@@ -1102,9 +1285,9 @@ __global__ void k_init_slots(int32_t* slot_of, uint32_t n_local, int32_t* spare_
     }
 }
 void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
-                       StepCounters* counters, uint32_t rank) {
-    const uint32_t n = n_local > n_spare ? n_local : n_spare;
-    k_init_slots<<<(n + 255) / 256, 256, 0, stream>>>(slot_of, n_local, spare_list, n_spare, counters, rank);
+                       StepCounters* counters, uint32_t rank, SlotMeta* meta) {
+    const uint32_t n = n_local + n_spare;
+    k_init_slots<<<(n + 255) / 256, 256, 0, stream>>>(slot_of, n_local, spare_list, n_spare, counters, rank, meta);
 }
 
 // =============================================================================== test hooks

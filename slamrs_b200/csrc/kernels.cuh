@@ -30,6 +30,7 @@ struct StepCounters {
     unsigned long long est_owner;        // rank that owns it
     unsigned long long n_spare;          // entries of the persistent spare-slot list
     unsigned long long n_alive;          // local particles whose grid is integrated this step
+    unsigned long long copy_bytes;       // bytes read + written by the copy kernels this step
     double sum;                          // sum of raw weights (particle.rs:50)
     float est_pose[3];                   // estimated_pose(), slam.rs:77-81
     float pad;
@@ -38,7 +39,7 @@ struct StepCounters {
 // per-step record kept on the device so that a pipelined caller can read, after the fact, how
 // many grids each step really moved (the roofline is computed from moved bytes only)
 struct StepRecord {
-    unsigned long long step, n_copies, n_pulls, distinct, n_leaders, n_alive;
+    unsigned long long step, n_copies, n_pulls, distinct, n_leaders, n_alive, copy_bytes, pad;
 };
 constexpr uint32_t STEP_HISTORY = 256;
 constexpr uint32_t COPY_FAN = 16;   // destinations written per source read in k_copy
@@ -50,9 +51,23 @@ struct ScanDevice {
     uint32_t n_beams;
 };
 
+// Per-slot metadata. [x0, x1) x [y0, y1) is the extent (in cells, x0/x1 multiples of 8) of the
+// cells of the slot that may be non-zero: everything outside is guaranteed to be zero
+// (never-informed cells), which is what lets the resampler move only the informed part of a grid.
+// Empty: x1 <= x0. The array lives at the head of the grid pool allocation, so a peer GPU that
+// maps the pool sees the extents of the grids it pulls.
+struct alignas(32) SlotMeta {
+    int x0, y0, x1, y1;
+    int ox, oy;          // reserved: origin of a windowed slot inside the logical grid (0, 0 today)
+    int pad0, pad1;
+};
+static_assert(sizeof(SlotMeta) == 32, "SlotMeta is read by peers as 32 bytes");
+
 struct CopyItem {
     const uint32_t* src;  // may be a peer-mapped pointer (grid on another GPU)
     uint32_t* dst;
+    const SlotMeta* src_meta;  // extent of the source grid (peer-mapped for a pull)
+    SlotMeta* dst_meta;        // extent of the destination slot (what it held before / holds after)
 };
 
 // ---- launch wrappers (all asynchronous on `stream`) ----
@@ -65,7 +80,7 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
 // alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive)
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
-                              const int32_t* slot_of, uint32_t* cells,
+                              const int32_t* slot_of, uint32_t* cells, SlotMeta* meta,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic);
 
@@ -94,6 +109,8 @@ struct PlanArgs {
     uint32_t* cells;           // local pool base
     size_t cells_per_grid;
     uint32_t* const* peer_cells;        // world pointers to each rank's pool (device array), may be null when world==1
+    SlotMeta* meta;                     // local per-slot extents
+    SlotMeta* const* peer_meta;         // world pointers to each rank's extents, may be null when world==1
     StepCounters* counters;
     StepRecord* history;       // STEP_HISTORY entries, slot = step % STEP_HISTORY
     unsigned long long step;
@@ -116,7 +133,20 @@ void launch_export(cudaStream_t stream, const uint32_t* cells, size_t cells_per_
 void launch_export_log_odds(cudaStream_t stream, const uint32_t* grid, uint32_t n_cells, double* out);
 
 void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
-                       StepCounters* counters, uint32_t rank);
+                       StepCounters* counters, uint32_t rank, SlotMeta* meta);
+
+// extent-limited copies: only the informed part of each source grid moves, and the part of the
+// destination slot's previous content that the source does not cover is cleared
+void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
+                       const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t row_cells,
+                       StepCounters* counters, int num_sms);
+// after a copy kernel: every destination slot now has its source's extent. With `record` the
+// step's moved bytes are also written into the history ring (last copy launch of a step).
+void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,
+                         StepCounters* counters, StepRecord* record);
+// add the bytes of a full-grid copy launch to counters->copy_bytes
+void launch_account_full_copy(cudaStream_t stream, const unsigned long long* n_items, const unsigned long long* n_leaders,
+                              size_t bytes_per_grid, StepCounters* counters);
 cudaError_t configure_kernels();  // per-device function attributes; call once after cudaSetDevice
 
 // test hooks

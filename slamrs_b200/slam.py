@@ -252,8 +252,9 @@ class GridMapSlam:
         return dict(zip(_lib.PHASES, ms.tolist())), int(steps.value)
 
     def step_history(self, first_step: int, count: int) -> np.ndarray:
-        """count x {grids_copied, grids_pulled, distinct_sources, source_reads, particles_integrated}."""
-        out = np.zeros((count, 5), np.uint64)
+        """count x {grids_copied, grids_pulled, distinct_sources, source_reads, particles_integrated,
+        copy_bytes}."""
+        out = np.zeros((count, _lib.HISTORY_VALUES), np.uint64)
         _lib.check(self._L.slamrs_gpu_get_step_history(self._h, first_step, count, _ptr(out)), self._h)
         return out
 

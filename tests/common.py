@@ -81,12 +81,15 @@ def compare_step(gpu: GridMapSlam, osl, particles=None, check_map=True):
     return out
 
 
-def lockstep(O, cfg: GridMapSlamConfig, scans, rng_mode=_lib.RNG_SHARED_STREAM, particles=None, seed=SEED, flags=0):
+def lockstep(O, cfg: GridMapSlamConfig, scans, rng_mode=_lib.RNG_SHARED_STREAM, particles=None, seed=SEED, flags=0,
+             pre_step=None):
     gpu = GridMapSlam(cfg, GpuPlacement(seed=seed, rng_mode=rng_mode, flags=flags))
     osl = oracle_slam(O, cfg)
     errs = []
     try:
         for step, (obs, odo) in enumerate(scans):
+            if pre_step is not None:
+                pre_step(step, gpu, osl)
             rc, z, u = oracle_step(O, osl, obs, odo, step, seed)
             assert rc == 0
             if rng_mode == _lib.RNG_CALLER:

@@ -109,6 +109,76 @@ def test_many_hits_in_one_cell(oracle, flags):
     lockstep(oracle, cfg, [(same, odo), (near, odo), (same, odo)], flags=flags)
 
 
+COPY_MODES = pytest.mark.parametrize("copy_flags", [0, _lib.FLAG_FULL_GRID_COPY], ids=["extent-copy", "whole-grid-copy"])
+
+
+@COPY_MODES
+def test_step_parity_scattered_poses_mixed_extents(oracle, copy_flags):
+    """Particles are re-scattered over the room before every scan, so the slots the resampler
+    recycles hold grids with very different informed extents: an extent-limited copy must also
+    clear whatever the destination's previous tenant had informed outside the source's extent."""
+    cfg = GridMapSlamConfig(position=(-6.4, -6.4), width=12.8, height=12.8, resolution=0.05, n_particles=48)
+    scans = make_scans(5.0, 360, 3.0, 6)
+    rng = np.random.default_rng(7)
+
+    def scatter(step, gpu, osl):
+        xyt = np.column_stack([rng.uniform(-4.5, 4.5, 48), rng.uniform(-4.5, 4.5, 48),
+                               rng.uniform(-np.pi, np.pi, 48)]).astype(np.float32)
+        if step % 2 == 0:
+            gpu.set_poses(xyt); osl.set_poses(xyt)
+
+    errs = lockstep(oracle, cfg, scans, flags=copy_flags, pre_step=scatter)
+    print(errs[-1])
+
+
+def test_extent_copy_moves_fewer_bytes_same_result():
+    """Both copy modes give identical grids; the extent-limited one reports the bytes it moved."""
+    cfg = GridMapSlamConfig(position=(-12.8, -12.8), width=25.6, height=25.6, resolution=0.05, n_particles=256)
+    scans = make_scans(5.0, 360, 6.0, 4)
+    out = {}
+    for flags in (0, _lib.FLAG_FULL_GRID_COPY):
+        with GridMapSlam(cfg, GpuPlacement(flags=flags)) as g:
+            for obs, odo in scans:
+                g.update(obs, odo)
+            st = g.stats()
+            hist = g.step_history(0, len(scans))
+            assert hist[-1, 5] == st["copy_bytes"]
+            out[flags] = (st, [g.cells(p).copy() for p in (0, 1, 100, 255)], g.estimated_likelihood().data.copy())
+    (st_box, cells_box, map_box), (st_full, cells_full, map_full) = out[0], out[_lib.FLAG_FULL_GRID_COPY]
+    for a, b in zip(cells_box, cells_full):
+        assert np.array_equal(a, b)
+    assert np.array_equal(map_box, map_full)
+    assert st_box["grids_copied"] == st_full["grids_copied"] > 0
+    assert 0 < st_box["copy_bytes"] < st_full["copy_bytes"] // 4
+    # whole-grid mode: every copy writes a grid, every fan-out sub-run reads one
+    assert st_full["copy_bytes"] >= st_full["grids_copied"] * st_full["bytes_per_grid"]
+
+
+def test_set_cells_then_resample_keeps_extents_consistent(oracle):
+    """set_cells installs an arbitrary image (extent recomputed on the host); later copies of that
+    particle and into its slot must reproduce it exactly."""
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=8)
+    scans = make_scans(1.0, 360, 1.0, 3)
+    rng = np.random.default_rng(3)
+    img = np.zeros((200, 200), np.uint32)
+    img[5:190, 3:199] = rng.integers(0, 4, (185, 196)).astype(np.uint32) * 0x10001
+    with GridMapSlam(cfg) as g:
+        g.update(*scans[0])
+        for p in range(8):
+            g.set_cells(p, img if p % 2 == 0 else np.zeros_like(img))
+        for p in range(8):
+            assert np.array_equal(g.cells(p).reshape(200, 200), img if p % 2 == 0 else 0 * img)
+        g.update(*scans[1])
+        idx = g.resample_indices()
+        g.update(*scans[2])
+        # every particle descends from one of the two images plus the same two scans at its own poses;
+        # all cells outside the scans' reach must still be exactly the installed image
+        for p in range(8):
+            c = g.cells(p).reshape(200, 200)
+            far = np.ones((200, 200), bool); far[40:160, 40:160] = False
+            assert np.array_equal(c[far], img[far]) or np.array_equal(c[far], 0 * img[far])
+
+
 def test_step_parity_720_beams_odd_grid(oracle):
     """720 beams and a grid whose side is not a multiple of 4 (scalar write-back path)."""
     cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.02, height=4.02, resolution=0.02, n_particles=12)
