@@ -52,6 +52,7 @@ struct slamrs_gpu_handle {
     int32_t *d_keep = nullptr, *d_need = nullptr, *d_free = nullptr, *d_spare = nullptr;
     CopyItem *d_copies = nullptr, *d_pulls = nullptr;
     uint32_t* d_leaders = nullptr;
+    void* d_jobs = nullptr;      // CopyJob scratch of the extent-limited copy
     uint32_t* d_alive = nullptr;
     StepCounters* d_counters = nullptr;
     StepCounters* h_counters = nullptr;  // pinned
@@ -206,7 +207,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
-    cudaFree(h->d_copies); cudaFree(h->d_pulls); cudaFree(h->d_leaders); cudaFree(h->d_alive);
+    cudaFree(h->d_copies); cudaFree(h->d_pulls); cudaFree(h->d_leaders); cudaFree(h->d_alive); cudaFree(h->d_jobs);
     cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells); cudaFree(h->d_peer_meta);
     cudaFree(h->d_history);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -419,6 +420,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_copies, sizeof(CopyItem) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_pulls, sizeof(CopyItem) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_leaders, sizeof(uint32_t) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_jobs, copy_job_bytes() * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_alive, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_counters, sizeof(StepCounters)));
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
@@ -531,8 +533,8 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 2);
     // zeroes saturated, spilled (adjacent) and n_alive
     CU_TRY(h, cudaMemsetAsync(&h->d_counters->saturated, 0, 2 * sizeof(unsigned long long), s));
-    // n_alive and copy_bytes (adjacent)
-    CU_TRY(h, cudaMemsetAsync(&h->d_counters->n_alive, 0, 2 * sizeof(unsigned long long), s));
+    // n_alive, copy_bytes and copy_max_rows (adjacent)
+    CU_TRY(h, cudaMemsetAsync(&h->d_counters->n_alive, 0, 3 * sizeof(unsigned long long), s));
     launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, h->d_counters);
@@ -561,6 +563,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.counters = h->d_counters;
     pa.history = h->d_history;
     pa.step = h->step;
+    pa.staged = plan_can_stage(h->n_local, h->n_spare);
     launch_plan(s, pa);
     h->launches++;
     // 6. grid traffic. Across GPUs: barrier (every survivor is integrated), NVLink pulls, barrier
@@ -570,7 +573,9 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         std::string err;
         if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
         if (h->boxed_copy) {
-            launch_copy_boxed(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->geom.gw, h->d_counters, h->num_sms);
+            launch_copy_boxed(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->n_local, h->d_jobs, h->geom.gw,
+                              h->d_counters, h->num_sms);
+            h->launches++;
         } else {
             launch_copy(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->cells_per_grid, h->num_sms);
             launch_account_full_copy(s, &h->d_counters->n_pulls, nullptr, grid_bytes, h->d_counters);
@@ -582,8 +587,9 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     }
     PROF_MARK(h, 6);
     if (h->boxed_copy) {
-        launch_copy_boxed(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->geom.gw,
-                          h->d_counters, h->num_sms);
+        launch_copy_boxed(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->n_local,
+                          h->d_jobs, h->geom.gw, h->d_counters, h->num_sms);
+        h->launches++;
     } else {
         launch_copy(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->cells_per_grid,
                     h->num_sms);

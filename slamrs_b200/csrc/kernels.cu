@@ -208,10 +208,12 @@ __device__ __forceinline__ void ext_add(int* s_ext, int xmin, int ymin, int xmax
     atomicMax(&s_ext[2], xmax); atomicMax(&s_ext[3], ymax);
 }
 // union the CTA's touched extent into the slot's box (x aligned to 8 cells); one thread, after a barrier
+constexpr int BOX_ALIGN = 8;   // x alignment of extents in cells: one 256-bit access
 __device__ __forceinline__ void ext_commit(const int* s_ext, SlotMeta* meta, int gw) {
     if (s_ext[2] < s_ext[0]) return;
     SlotMeta b = *meta;
-    const int x0 = s_ext[0] & ~7, x1 = min(gw, (s_ext[2] + 8) & ~7), y0 = s_ext[1], y1 = s_ext[3] + 1;
+    const int am = BOX_ALIGN - 1;
+    const int x0 = s_ext[0] & ~am, x1 = min(gw, (s_ext[2] + 1 + am) & ~am), y0 = s_ext[1], y1 = s_ext[3] + 1;
     if (b.x1 <= b.x0) { b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; }
     else { b.x0 = min(b.x0, x0); b.y0 = min(b.y0, y0); b.x1 = max(b.x1, x1); b.y1 = max(b.y1, y1); }
     *meta = b;
@@ -651,15 +653,6 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 }
 
-cudaError_t configure_kernels() {
-    // per-device opt-in to the large dynamic shared-memory window
-    cudaError_t e = cudaFuncSetAttribute(k_ray_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_ray_update_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_ray_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
-}
-
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
                               const int32_t* slot_of, uint32_t* cells, SlotMeta* meta,
@@ -865,7 +858,14 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
     return lo;
 }
 
+// With n_local <= PLAN_STAGED_MAX_S the index range, the slot tables, the class bytes and the free
+// list live in shared memory (22 bytes per particle): the planner is a chain of short sequential
+// passes whose cost is load latency, and shared memory cuts that by an order of magnitude.
+constexpr uint32_t PLAN_STAGED_MAX_S = 8192;
+__host__ __device__ inline size_t plan_staged_bytes(uint32_t S) { return (size_t)S * 22u + 64u; }
+
 __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ uint32_t s_warp[33];
     const uint32_t S = a.n_local, lo = a.rank * a.n_local, hi = lo + S;
     const uint32_t T = blockDim.x, t = threadIdx.x;
@@ -873,61 +873,89 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     const uint32_t c0 = min(S, t * chunk), c1 = min(S, c0 + chunk);
     const uint32_t E = (uint32_t)a.counters->n_spare;
 
-    for (uint32_t j = t; j < S; j += T) a.keep[j] = 0;
+    // working arrays: shared memory when staged, the global scratch otherwise
+    uint32_t* idx_l;       // idx[lo .. hi)
+    int32_t* slot_old;     // read-only copy
+    int32_t* slot_new;
+    int32_t* free_list;    // [safe | spare | unsafe]
+    uint8_t* keep;
+    uint8_t* need;
+    if (a.staged) {
+        idx_l = reinterpret_cast<uint32_t*>(s_dyn);
+        slot_old = reinterpret_cast<int32_t*>(idx_l + S);
+        slot_new = slot_old + S;
+        free_list = slot_new + S;          // 2 S + 1 entries (E <= S when staged)
+        keep = reinterpret_cast<uint8_t*>(free_list + 2 * (size_t)S + 4);
+        need = keep + S;
+        for (uint32_t j = t; j < S; j += T) { idx_l[j] = a.idx[lo + j]; slot_old[j] = a.slot_old[j]; keep[j] = 0; }
+    } else {
+        idx_l = const_cast<uint32_t*>(a.idx) + lo;
+        slot_old = const_cast<int32_t*>(a.slot_old);
+        slot_new = a.slot_new;
+        free_list = a.free_list;
+        keep = reinterpret_cast<uint8_t*>(a.keep);
+        need = reinterpret_cast<uint8_t*>(a.need);
+        for (uint32_t j = t; j < S; j += T) keep[j] = 0;
+    }
     __syncthreads();
 
     // ---- classify new particles
     uint32_t nA = 0;
     for (uint32_t m = t; m < S; m += T) {
-        const uint32_t src = a.idx[lo + m];
-        const bool first = (m == 0) || (a.idx[lo + m - 1] != src);
+        const uint32_t src = idx_l[m];
+        const bool first = (m == 0) || (idx_l[m - 1] != src);
         const bool local = (src >= lo && src < hi);
         int cls;
         if (local && first) {
             cls = 0;
-            a.keep[src - lo] = 1;
-            a.slot_new[m] = a.slot_old[src - lo];
+            keep[src - lo] = 1;
+            slot_new[m] = slot_old[src - lo];
         } else if (local) cls = 1;
         else if (first) cls = 2;
         else cls = 3;
-        a.need[m] = cls;
+        need[m] = (uint8_t)cls;
         nA += (first ? 1u : 0u);
     }
     __syncthreads();
 
-    // ---- classify old slots: 0 = kept, 1 = free & safe, 2 = free but still read by another GPU
+    // ---- classify old slots: 0 = kept, 1 = free & safe, 2 = free but still read by another GPU.
+    // A slot that is not kept has no local consumer; idx is non-decreasing, so its consumers (if
+    // any) are all before this rank's range (v < idx[lo]) or all after it (v > idx[hi-1]).
+    const uint32_t idx_first = idx_l[0], idx_last = idx_l[S - 1];
     for (uint32_t j = t; j < S; j += T) {
         int f = 0;
-        if (!a.keep[j]) {
+        if (!keep[j]) {
             f = 1;
             if (a.world > 1) {
                 const uint32_t v = lo + j;
-                const uint32_t first = lower_bound_u32(a.idx, 0, a.n_total, v);
-                if (first < a.n_total && a.idx[first] == v) {
-                    const uint32_t last = lower_bound_u32(a.idx, first, a.n_total, v + 1) - 1;
-                    if (first < lo || last >= hi) f = 2;
+                if (v < idx_first && lo > 0) {
+                    const uint32_t p = lower_bound_u32(a.idx, 0, lo, v);
+                    if (p < lo && a.idx[p] == v) f = 2;
+                } else if (v > idx_last && hi < a.n_total) {
+                    const uint32_t p = lower_bound_u32(a.idx, hi, a.n_total, v);
+                    if (p < a.n_total && a.idx[p] == v) f = 2;
                 }
             }
         }
-        a.keep[j] = f;
+        keep[j] = (uint8_t)f;
     }
     __syncthreads();
 
     // ---- ordered compaction of the free slots: [safe | spare | unsafe]
     uint32_t n_safe_c = 0, n_unsafe_c = 0;
-    for (uint32_t j = c0; j < c1; ++j) { n_safe_c += (a.keep[j] == 1); n_unsafe_c += (a.keep[j] == 2); }
+    for (uint32_t j = c0; j < c1; ++j) { n_safe_c += (keep[j] == 1); n_unsafe_c += (keep[j] == 2); }
     uint32_t n_safe, n_unsafe;
     uint32_t ps = block_excl_scan_u32(n_safe_c, s_warp, &n_safe);
     uint32_t pu = block_excl_scan_u32(n_unsafe_c, s_warp, &n_unsafe);
     for (uint32_t j = c0; j < c1; ++j) {
-        if (a.keep[j] == 1) a.free_list[ps++] = a.slot_old[j];
-        else if (a.keep[j] == 2) a.free_list[n_safe + E + pu++] = a.slot_old[j];
+        if (keep[j] == 1) free_list[ps++] = slot_old[j];
+        else if (keep[j] == 2) free_list[n_safe + E + pu++] = slot_old[j];
     }
-    for (uint32_t e = t; e < E; e += T) a.free_list[n_safe + e] = a.spare_list[e];
+    for (uint32_t e = t; e < E; e += T) free_list[n_safe + e] = a.spare_list[e];
 
     // ---- ordered ranks of the consumers: pulls (C) first, then copies (B, D)
     uint32_t nC_c = 0, nBD_c = 0;
-    for (uint32_t m = c0; m < c1; ++m) { nC_c += (a.need[m] == 2); nBD_c += (a.need[m] == 1 || a.need[m] == 3); }
+    for (uint32_t m = c0; m < c1; ++m) { nC_c += (need[m] == 2); nBD_c += (need[m] == 1 || need[m] == 3); }
     uint32_t nC, nBD;
     uint32_t pc = block_excl_scan_u32(nC_c, s_warp, &nC);
     uint32_t pbd = block_excl_scan_u32(nBD_c, s_warp, &nBD);
@@ -939,13 +967,13 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     const uint32_t pbd_start = pbd;
     uint32_t n_lead_c = 0;
     for (uint32_t m = c0; m < c1; ++m) {
-        const int cls = a.need[m];
+        const int cls = need[m];
         if (cls == 2) {
-            const uint32_t src = a.idx[lo + m];
+            const uint32_t src = idx_l[m];
             const uint32_t owner = src / S;
             const int32_t sslot = a.results[src].slot;
-            const int32_t dslot = a.free_list[pc];
-            a.slot_new[m] = dslot;
+            const int32_t dslot = free_list[pc];
+            slot_new[m] = dslot;
             CopyItem it;
             it.src = a.peer_cells[owner] + (size_t)sslot * a.cells_per_grid;
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
@@ -954,18 +982,18 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             a.pulls[pc] = it;
             pc++;
         } else if (cls == 1) {
-            const uint32_t src = a.idx[lo + m];
-            const int32_t dslot = a.free_list[nC + pbd];
-            a.slot_new[m] = dslot;
+            const uint32_t src = idx_l[m];
+            const int32_t dslot = free_list[nC + pbd];
+            slot_new[m] = dslot;
             CopyItem it;
-            it.src = a.cells + (size_t)a.slot_old[src - lo] * a.cells_per_grid;
+            it.src = a.cells + (size_t)slot_old[src - lo] * a.cells_per_grid;
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
-            it.src_meta = a.meta + a.slot_old[src - lo];
+            it.src_meta = a.meta + slot_old[src - lo];
             it.dst_meta = a.meta + dslot;
             a.copies[pbd] = it;
-            const uint32_t m_first = lower_bound_u32(a.idx, lo, hi, src) - lo;
+            const uint32_t m_first = lower_bound_u32(idx_l, 0, S, src);
             const bool lead = ((m - m_first - 1u) % COPY_FAN) == 0u;
-            a.need[m] = lead ? 5 : 1;   // remember leadership for the compaction below
+            need[m] = lead ? 5 : 1;   // remember leadership for the compaction below
             n_lead_c += lead;
             pbd++;
         } else if (cls == 3) {
@@ -976,20 +1004,20 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     // pass 2: duplicates of pulled grids (source = where the first use landed)
     pbd = pbd_start;
     for (uint32_t m = c0; m < c1; ++m) {
-        const int cls = a.need[m];
+        const int cls = need[m];
         if (cls == 3) {
-            const uint32_t src = a.idx[lo + m];
-            const uint32_t m_first = lower_bound_u32(a.idx, lo, hi, src) - lo;
-            const int32_t dslot = a.free_list[nC + pbd];
-            a.slot_new[m] = dslot;
+            const uint32_t src = idx_l[m];
+            const uint32_t m_first = lower_bound_u32(idx_l, 0, S, src);
+            const int32_t dslot = free_list[nC + pbd];
+            slot_new[m] = dslot;
             CopyItem it;
-            it.src = a.cells + (size_t)a.slot_new[m_first] * a.cells_per_grid;
+            it.src = a.cells + (size_t)slot_new[m_first] * a.cells_per_grid;
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
-            it.src_meta = a.meta + a.slot_new[m_first];
+            it.src_meta = a.meta + slot_new[m_first];
             it.dst_meta = a.meta + dslot;
             a.copies[pbd] = it;
             const bool lead = ((m - m_first - 1u) % COPY_FAN) == 0u;
-            a.need[m] = lead ? 7 : 3;
+            need[m] = lead ? 7 : 3;
             n_lead_c += lead;
             pbd++;
         } else if (cls == 1 || cls == 5) {
@@ -1001,13 +1029,15 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     uint32_t pl = block_excl_scan_u32(n_lead_c, s_warp, &n_lead);
     pbd = pbd_start;
     for (uint32_t m = c0; m < c1; ++m) {
-        const int cls = a.need[m];
+        const int cls = need[m];
         if (cls == 5 || cls == 7) a.leaders[pl++] = pbd;
         if (cls == 1 || cls == 3 || cls == 5 || cls == 7) pbd++;
     }
     __syncthreads();
     // ---- the E slots nobody took become the next step's spare list
-    for (uint32_t e = t; e < E; e += T) a.spare_list[e] = a.free_list[nC + nBD + e];
+    for (uint32_t e = t; e < E; e += T) a.spare_list[e] = free_list[nC + nBD + e];
+    if (a.staged)
+        for (uint32_t m = t; m < S; m += T) a.slot_new[m] = slot_new[m];
 
     uint32_t distinct;
     block_excl_scan_u32(nA, s_warp, &distinct);
@@ -1019,7 +1049,7 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
         a.counters->staging_short = (nC > n_safe + E) ? (unsigned long long)(nC - (n_safe + E)) : 0ull;
         const unsigned long long mp = a.counters->max_particle;
         a.counters->est_owner = mp / S;
-        a.counters->est_slot = (mp >= lo && mp < hi) ? (long long)a.slot_new[mp - lo] : -1ll;
+        a.counters->est_slot = (mp >= lo && mp < hi) ? (long long)slot_new[mp - lo] : -1ll;
         if (a.history) {
             StepRecord r;
             r.step = a.step; r.n_copies = nBD; r.n_pulls = nC; r.distinct = distinct; r.n_leaders = n_lead;
@@ -1030,7 +1060,13 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     }
 }
 
-void launch_plan(cudaStream_t stream, const PlanArgs& a) { k_plan<<<1, 1024, 0, stream>>>(a); }
+bool plan_can_stage(uint32_t n_local, uint32_t n_spare_cap) {
+    return n_local <= PLAN_STAGED_MAX_S && n_spare_cap <= n_local;
+}
+
+void launch_plan(cudaStream_t stream, const PlanArgs& a) {
+    k_plan<<<1, 1024, a.staged ? plan_staged_bytes(a.n_local) : 0, stream>>>(a);
+}
 
 // =============================================================================== k_copy
 // Grid copies (the `value.clone()` of particle.rs:97-100). Pure streaming: 128-bit loads that
@@ -1109,113 +1145,154 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
 // =============================================================================== k_copy_boxed
 // Extent-limited grid copy. A grid is zero outside its extent (SlotMeta), so cloning it means:
 // copy the source's extent and clear whatever else the destination slot's previous tenant had
-// informed. Work item = (fan-out sub-run, band of rows of the union U of the source extent and
-// the sub-run's destination extents); the number of bands per sub-run is chosen on the device so
-// that every CTA gets several items. Inside a band the (row, 32-byte unit) pairs of U are
+// informed. k_copy_prepare turns every fan-out sub-run into one CopyJob (source, source extent,
+// destinations, U = union of the source extent and the destinations' old extents); k_copy_boxed
+// then works on (job, band of rows of U) items, the number of bands per job chosen on the device
+// so that every CTA gets several items. Inside a band the (row, 32-byte unit) pairs of U are
 // linearised over the CTA's threads: each thread issues COPY_UNROLL independent 256-bit loads
-// (zero outside the source extent), then stores each value to every destination whose own write
-// region (source extent U destination extent) contains it. Bytes that really moved are counted
-// and are what the roofline in bench.py uses.
-constexpr uint32_t BOX_MAX_BANDS = 128;
+// (zero outside the source extent) and stores each value to every destination of the sub-run.
+// Bytes that really moved are counted on the device and are what the roofline in bench.py uses.
+
+struct alignas(16) CopyJob {
+    const uint32_t* src;
+    uint32_t fan, pad;
+    int sx0, sy0, sx1, sy1;   // source extent, x in 32-byte units
+    int ux0, uy0, ux1, uy1;   // region written in every destination
+    uint32_t* dst[COPY_FAN];
+};
+static_assert(sizeof(CopyJob) % 16 == 0, "CopyJob is fetched as 16-byte pieces");
+constexpr int COPY_JOB_V4 = (int)(sizeof(CopyJob) / 16);
 
 __device__ __forceinline__ bool meta_empty(const SlotMeta& m) { return m.x1 <= m.x0 || m.y1 <= m.y0; }
 
-__global__ void __launch_bounds__(COPY_THREADS)
-k_copy_boxed(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
-             const unsigned long long* __restrict__ n_items, const unsigned long long* __restrict__ n_leaders,
-             uint32_t row_units /* 32-byte units per physical grid row */, StepCounters* counters) {
-    __shared__ int4 s_wbox[COPY_FAN];       // write region of each destination, in (unit, row) coordinates
-    __shared__ V8* s_dst[COPY_FAN];
+// one warp per job
+__global__ void __launch_bounds__(256)
+k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
+               const unsigned long long* __restrict__ n_items, const unsigned long long* __restrict__ n_leaders,
+               CopyJob* __restrict__ jobs, StepCounters* counters) {
     const unsigned long long n = *n_items;
     const unsigned long long nl = leaders ? *n_leaders : n;
+    const unsigned long long q = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nl) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long k = leaders ? leaders[q] : q;
+    const bool have = lane < (int)COPY_FAN && k + lane < n && (leaders != nullptr || lane == 0);
+    CopyItem it{};
+    if (have) it = items[k + lane];
+    const unsigned long long src0 = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)it.src, 0);
+    const unsigned same = __ballot_sync(0xffffffffu, have && (unsigned long long)(uintptr_t)it.src == src0);
+    const uint32_t fan = (uint32_t)(__ffs(~same) - 1);   // leading run of items that share the source
+    SlotMeta sm{0, 0, 0, 0, 0, 0, 0, 0}, dm{0, 0, 0, 0, 0, 0, 0, 0};
+    if (lane == 0) sm = *it.src_meta;
+    if (lane < (int)fan) dm = *it.dst_meta;
+    int sx0 = __shfl_sync(0xffffffffu, sm.x0, 0) >> 3, sy0 = __shfl_sync(0xffffffffu, sm.y0, 0);
+    int sx1 = __shfl_sync(0xffffffffu, sm.x1, 0) >> 3, sy1 = __shfl_sync(0xffffffffu, sm.y1, 0);
+    if (sx1 <= sx0 || sy1 <= sy0) { sx0 = sy0 = sx1 = sy1 = 0; }
+    int ux0 = 0x7fffffff, uy0 = 0x7fffffff, ux1 = -1, uy1 = -1;
+    if (lane < (int)fan && !meta_empty(dm)) { ux0 = dm.x0 >> 3; uy0 = dm.y0; ux1 = dm.x1 >> 3; uy1 = dm.y1; }
+    if (lane == 0 && sx1 > sx0) { ux0 = min(ux0, sx0); uy0 = min(uy0, sy0); ux1 = max(ux1, sx1); uy1 = max(uy1, sy1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ux0 = min(ux0, __shfl_xor_sync(0xffffffffu, ux0, o)); uy0 = min(uy0, __shfl_xor_sync(0xffffffffu, uy0, o));
+        ux1 = max(ux1, __shfl_xor_sync(0xffffffffu, ux1, o)); uy1 = max(uy1, __shfl_xor_sync(0xffffffffu, uy1, o));
+    }
+    if (ux1 <= ux0) { ux0 = uy0 = ux1 = uy1 = 0; }
+    CopyJob* job = jobs + q;
+    if (lane < (int)COPY_FAN) job->dst[lane] = lane < (int)fan ? it.dst : nullptr;
+    if (lane == 0) {
+        job->src = it.src; job->fan = fan; job->pad = 0;
+        job->sx0 = sx0; job->sy0 = sy0; job->sx1 = sx1; job->sy1 = sy1;
+        job->ux0 = ux0; job->uy0 = uy0; job->ux1 = ux1; job->uy1 = uy1;
+        if (uy1 > uy0) atomicMax(&counters->copy_max_rows, (unsigned long long)(uy1 - uy0));
+    }
+}
+
+// CTA-granular: one work item = (job, band of rows of U); the (row, 32-byte unit) pairs of the
+// band are linearised over the CTA's threads, UNROLL independent 256-bit loads per thread, then
+// every value is stored to each destination of the sub-run. The job of the next item is fetched
+// into registers while the current item is copied.
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(COPY_THREADS, MINB)
+k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restrict__ n_jobs,
+             uint32_t row_units /* 32-byte units per physical grid row */, uint32_t items_per_cta,
+             StepCounters* counters) {
+    __shared__ CopyJob s_job;
+    __shared__ unsigned long long s_moved;
+    if (threadIdx.x == 0) s_moved = 0ull;
+    const unsigned long long nl = *n_jobs;
     if (nl == 0) return;
-    // bands per sub-run: about 6 work items per CTA in total
-    unsigned long long want = ((unsigned long long)gridDim.x * 6ull + nl - 1ull) / nl;
-    const uint32_t bands = (uint32_t)(want < 1ull ? 1ull : (want > BOX_MAX_BANDS ? BOX_MAX_BANDS : want));
-    const unsigned long long total = nl * bands;
-    unsigned long long moved = 0;   // 32-byte units read + written by this thread
-    for (unsigned long long w = blockIdx.x; w < total; w += gridDim.x) {
-        const unsigned long long q = w / bands;
-        const uint32_t band = (uint32_t)(w - q * bands);
-        const unsigned long long k = leaders ? leaders[q] : q;
-        const CopyItem it = items[k];
-        const SlotMeta sm = *it.src_meta;
-        const bool s_has = !meta_empty(sm);
-        // source extent in units
-        const int sx0 = sm.x0 >> 3, sx1 = sm.x1 >> 3, sy0 = sm.y0, sy1 = sm.y1;
-        uint32_t fan = 1;
-        if (leaders) {
-            while (fan < COPY_FAN && k + fan < n && items[k + fan].src == it.src) fan++;
-        }
-        __syncthreads();   // previous item's shared boxes are no longer read
-        if (threadIdx.x < fan) {
-            const CopyItem itf = items[k + threadIdx.x];
-            const SlotMeta dm = *itf.dst_meta;
-            int4 wb;
-            if (meta_empty(dm)) wb = s_has ? make_int4(sx0, sy0, sx1, sy1) : make_int4(0, 0, 0, 0);
-            else if (!s_has) wb = make_int4(dm.x0 >> 3, dm.y0, dm.x1 >> 3, dm.y1);
-            else wb = make_int4(min(sx0, dm.x0 >> 3), min(sy0, dm.y0), max(sx1, dm.x1 >> 3), max(sy1, dm.y1));
-            s_wbox[threadIdx.x] = wb;
-            s_dst[threadIdx.x] = reinterpret_cast<V8*>(itf.dst);
+    // bands per job: about items_per_cta work items per CTA in total, at most one band per row
+    const uint32_t max_rows = (uint32_t)counters->copy_max_rows;
+    const unsigned long long want = ((unsigned long long)gridDim.x * items_per_cta + nl - 1ull) / nl;
+    const uint32_t bands = (uint32_t)(want < 1ull ? 1ull : (want > max_rows ? (max_rows ? max_rows : 1u) : want));
+    const uint32_t total = (uint32_t)min(nl * bands, 0xffffffffull);
+    uint32_t moved = 0;   // 32-byte units read + written by this thread
+    uint4 next_job = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < COPY_JOB_V4 && blockIdx.x < total)
+        next_job = reinterpret_cast<const uint4*>(jobs + blockIdx.x / bands)[threadIdx.x];
+    for (uint32_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const uint32_t q = w / bands;
+        const uint32_t band = w - q * bands;
+        __syncthreads();   // the previous item's job is no longer read
+        if (threadIdx.x < COPY_JOB_V4) {
+            reinterpret_cast<uint4*>(&s_job)[threadIdx.x] = next_job;
+            const unsigned long long wn = (unsigned long long)w + gridDim.x;
+            if (wn < total) next_job = reinterpret_cast<const uint4*>(jobs + (uint32_t)wn / bands)[threadIdx.x];
         }
         __syncthreads();
-        // U = union of the write regions
-        int ux0 = 0x7fffffff, uy0 = 0x7fffffff, ux1 = -1, uy1 = -1;
-        for (uint32_t f = 0; f < fan; ++f) {
-            const int4 wb = s_wbox[f];
-            if (wb.z > wb.x && wb.w > wb.y) { ux0 = min(ux0, wb.x); uy0 = min(uy0, wb.y); ux1 = max(ux1, wb.z); uy1 = max(uy1, wb.w); }
-        }
-        if (ux1 <= ux0) continue;
+        const int ux0 = s_job.ux0, uy0 = s_job.uy0, ux1 = s_job.ux1, uy1 = s_job.uy1;
         const int rows = uy1 - uy0;
+        if (rows <= 0) continue;
         const int rows_per_band = (rows + (int)bands - 1) / (int)bands;
         const int r0 = uy0 + (int)band * rows_per_band, r1 = min(uy1, r0 + rows_per_band);
         if (r0 >= r1) continue;
+        const int sx0 = s_job.sx0, sy0 = s_job.sy0, sx1 = s_job.sx1, sy1 = s_job.sy1;
+        const uint32_t fan = s_job.fan;
         const uint32_t uw = (uint32_t)(ux1 - ux0);
         const uint32_t count = (uint32_t)(r1 - r0) * uw;
-        const V8* src = reinterpret_cast<const V8*>(it.src);
-        for (uint32_t base = threadIdx.x; base < count; base += COPY_THREADS * COPY_UNROLL) {
-            V8 v[COPY_UNROLL];
-            int ex[COPY_UNROLL], ey[COPY_UNROLL];
+        const V8* src = reinterpret_cast<const V8*>(s_job.src);
+        for (uint32_t base = threadIdx.x; base < count; base += COPY_THREADS * UNROLL) {
+            V8 v[UNROLL];
+            uint32_t off[UNROLL];   // unit offset inside a grid (< 2^28)
 #pragma unroll
-            for (int u = 0; u < COPY_UNROLL; ++u) {
+            for (int u = 0; u < UNROLL; ++u) {
                 const uint32_t i = base + u * COPY_THREADS;
-                ey[u] = -1; ex[u] = 0;
+                off[u] = 0xffffffffu;
                 v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
                 if (i < count) {
                     const uint32_t rr = i / uw;
-                    ey[u] = r0 + (int)rr;
-                    ex[u] = ux0 + (int)(i - rr * uw);
-                    if (s_has && ex[u] >= sx0 && ex[u] < sx1 && ey[u] >= sy0 && ey[u] < sy1) {
-                        v[u] = ld_stream_v8(src + (size_t)ey[u] * row_units + ex[u]);
-                        moved++;
-                    }
+                    const int ey = r0 + (int)rr, ex = ux0 + (int)(i - rr * uw);
+                    off[u] = (uint32_t)ey * row_units + (uint32_t)ex;
+                    if (ex >= sx0 && ex < sx1 && ey >= sy0 && ey < sy1) { v[u] = ld_stream_v8(src + off[u]); moved++; }
                 }
             }
             for (uint32_t f = 0; f < fan; ++f) {
-                const int4 wb = s_wbox[f];
-                V8* dst = s_dst[f];
+                V8* dst = reinterpret_cast<V8*>(s_job.dst[f]);
 #pragma unroll
-                for (int u = 0; u < COPY_UNROLL; ++u) {
-                    if (ey[u] >= wb.y && ey[u] < wb.w && ex[u] >= wb.x && ex[u] < wb.z) {
-                        st_stream_v8(dst + (size_t)ey[u] * row_units + ex[u], v[u]);
-                        moved++;
-                    }
-                }
+                for (int u = 0; u < UNROLL; ++u)
+                    if (off[u] != 0xffffffffu) { st_stream_v8(dst + off[u], v[u]); moved++; }
             }
         }
     }
-    // bytes actually moved, for the roofline (one atomic per warp)
+    // bytes actually moved, for the roofline: warp -> CTA -> one global atomic per CTA
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
-    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&counters->copy_bytes, moved * 32ull);
+    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&s_moved, (unsigned long long)moved);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_moved) atomicAdd(&counters->copy_bytes, s_moved * 32ull);
 }
 
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
-                       const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t row_cells,
-                       StepCounters* counters, int num_sms) {
-    k_copy_boxed<<<num_sms * COPY_CTAS_PER_SM, COPY_THREADS, 0, stream>>>(items, leaders, n_items, n_leaders,
-                                                                         row_cells / 8u, counters);
+                       const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t max_items,
+                       void* jobs, uint32_t row_cells, StepCounters* counters, int num_sms) {
+    const uint32_t blocks = (max_items + 7u) / 8u;
+    k_copy_prepare<<<blocks ? blocks : 1, 256, 0, stream>>>(items, leaders, n_items, n_leaders, (CopyJob*)jobs, counters);
+    // measured on B200 (tools/tune_copy.sh, gpurun_out/tune_copy4.log): 4 loads in flight per thread,
+    // 3 CTAs per SM resident, grid oversubscribed 32x per SM for balance, ~6 items per CTA
+    k_copy_boxed<4, 3><<<num_sms * COPY_CTAS_PER_SM, COPY_THREADS, 0, stream>>>(
+        (const CopyJob*)jobs, leaders ? n_leaders : n_items, row_cells / 8u, 6u, counters);
 }
+size_t copy_job_bytes() { return sizeof(CopyJob); }
 
 __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigned long long* __restrict__ n_items,
                                StepCounters* counters, StepRecord* record) {
@@ -1288,6 +1365,18 @@ void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, 
                        StepCounters* counters, uint32_t rank, SlotMeta* meta) {
     const uint32_t n = n_local + n_spare;
     k_init_slots<<<(n + 255) / 256, 256, 0, stream>>>(slot_of, n_local, spare_list, n_spare, counters, rank, meta);
+}
+
+// =============================================================================== per-device setup
+
+cudaError_t configure_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(k_ray_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ray_update_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_staged_bytes(PLAN_STAGED_MAX_S));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_ray_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
 }
 
 // =============================================================================== test hooks

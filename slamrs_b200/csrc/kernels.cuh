@@ -31,6 +31,7 @@ struct StepCounters {
     unsigned long long n_spare;          // entries of the persistent spare-slot list
     unsigned long long n_alive;          // local particles whose grid is integrated this step
     unsigned long long copy_bytes;       // bytes read + written by the copy kernels this step
+    unsigned long long copy_max_rows;    // tallest region any copy job of this step writes (rows)
     double sum;                          // sum of raw weights (particle.rs:50)
     float est_pose[3];                   // estimated_pose(), slam.rs:77-81
     float pad;
@@ -114,8 +115,10 @@ struct PlanArgs {
     StepCounters* counters;
     StepRecord* history;       // STEP_HISTORY entries, slot = step % STEP_HISTORY
     unsigned long long step;
+    bool staged;               // working arrays in shared memory (plan_can_stage)
 };
 void launch_plan(cudaStream_t stream, const PlanArgs& a);
+bool plan_can_stage(uint32_t n_local, uint32_t n_spare_cap);
 
 // local particles that appear in the index vector (their grid survives resampling); all_particles
 // lists every local particle instead (reference order of work)
@@ -138,8 +141,10 @@ void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, 
 // extent-limited copies: only the informed part of each source grid moves, and the part of the
 // destination slot's previous content that the source does not cover is cleared
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
-                       const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t row_cells,
+                       const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t max_items,
+                       void* jobs /* max_items * copy_job_bytes() of scratch */, uint32_t row_cells,
                        StepCounters* counters, int num_sms);
+size_t copy_job_bytes();
 // after a copy kernel: every destination slot now has its source's extent. With `record` the
 // step's moved bytes are also written into the history ring (last copy launch of a step).
 void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,

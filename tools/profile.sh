@@ -1,14 +1,16 @@
 #!/bin/bash
-# ncu evidence for one round. Usage (under gpurun): bash tools/profile.sh r1
+# ncu evidence for one round. Usage (under gpurun): bash tools/profile.sh r1 [kernel regex] [extra bench args]
 # 1) per-launch device times of a short bench run (shares, not absolutes)
-# 2) one --set full capture of the two heavy kernels (k_copy, k_ray_update*)
+# 2) one --set full capture of the heavy kernels
 set -u
 TAG=${1:-r1}
+KRX=${2:-k_copy|k_ray_update}
+EXTRA=${3:-}
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="python bench.py --particles 1024 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-strict"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-strict --no-full-copy $EXTRA"
 $CMD > $OUT/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_launches_${TAG}.log 2>&1
 $CMD > $OUT/plain2_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'k_copy|k_ray_update' -s 8 -c 4 -o $OUT/prof_${TAG} -f $CMD > $OUT/ncu_full_${TAG}.log 2>&1
-ls -la $OUT
+ncu --set full --clock-control none --import-source on -k regex:"$KRX" -s 8 -c 6 -o $OUT/prof_${TAG} -f $CMD > $OUT/ncu_full_${TAG}.log 2>&1
+ls -la $OUT | tail -8
