@@ -23,6 +23,8 @@ struct slamrs_gpu_handle {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;          // the planner runs here, next to the ray update
+    cudaEvent_t ev_indices = nullptr, ev_plan = nullptr;
 
     uint32_t n_total = 0, n_local = 0, rank = 0, world = 1, first = 0;
     uint32_t n_cells = 0;        // grid_w * grid_h
@@ -190,6 +192,7 @@ int setup_peers(slamrs_gpu_handle* h) {
 void free_all(slamrs_gpu_handle* h) {
     if (!h) return;
     DeviceGuard g(h->device);
+    if (h->side_stream) cudaStreamSynchronize(h->side_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && h->d_barrier && h->stream) {
         // nobody may still be pulling from this pool when it is freed
@@ -213,6 +216,9 @@ void free_all(slamrs_gpu_handle* h) {
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->prof_events.clear();
     if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->ev_indices) cudaEventDestroy(h->ev_indices);
+    if (h->ev_plan) cudaEventDestroy(h->ev_plan);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -371,6 +377,9 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
         return SLAMRS_E_NO_DEVICE;
     }
     CREATE_CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    CREATE_CU(cudaEventCreateWithFlags(&h->ev_indices, cudaEventDisableTiming));
+    CREATE_CU(cudaEventCreateWithFlags(&h->ev_plan, cudaEventDisableTiming));
     CREATE_CU(configure_kernels());
 
     // spare slots: staging room for grids that migrate between GPUs at resampling
@@ -520,7 +529,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->cells_per_grid,
                              h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step);
-    h->launches++;
+    h->launches += 2;   // k_motion + k_likelihood
     // 2. the one exchange step: every GPU needs every particle's weight, pose and slot
     PROF_MARK(h, 1);
     if (h->world > 1) {
@@ -538,17 +547,10 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, h->d_counters);
-    launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local,
-                      (h->cfg.flags & SLAMRS_FLAG_UPDATE_ALL_PARTICLES) != 0, h->d_alive, h->d_counters);
-    h->launches += 3;
-    // 4. integrate the scan into the grids that survive resampling (all grids in strict mode)
-    PROF_MARK(h, 3);
-    CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive, h->d_slot[cur],
-                                h->d_cells, h->d_meta, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
-                                (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
-    h->launches++;
-    // 5. plan: which grids stay, which are duplicated locally, which are pulled from a peer
-    PROF_MARK(h, 4);
+    // 4. plan (side stream): which grids stay, which are duplicated locally, which are pulled from a
+    //    peer. It needs only the index vector, so it runs concurrently with the ray update.
+    CU_TRY(h, cudaEventRecord(h->ev_indices, s));
+    CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_indices, 0));
     PlanArgs pa{};
     pa.results = h->d_results;
     pa.idx = h->d_idx;
@@ -564,8 +566,20 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.history = h->d_history;
     pa.step = h->step;
     pa.staged = plan_can_stage(h->n_local, h->n_spare);
-    launch_plan(s, pa);
+    launch_plan(h->side_stream, pa);
+    CU_TRY(h, cudaEventRecord(h->ev_plan, h->side_stream));
     h->launches++;
+    // 5. integrate the scan into the grids that survive resampling (all grids in strict mode)
+    launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local,
+                      (h->cfg.flags & SLAMRS_FLAG_UPDATE_ALL_PARTICLES) != 0, h->d_alive, h->d_counters);
+    h->launches += 3;
+    PROF_MARK(h, 3);
+    CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive, h->d_slot[cur],
+                                h->d_cells, h->d_meta, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
+                                (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
+    h->launches++;
+    PROF_MARK(h, 4);
+    CU_TRY(h, cudaStreamWaitEvent(s, h->ev_plan, 0));   // join: the copy lists are ready
     // 6. grid traffic. Across GPUs: barrier (every survivor is integrated), NVLink pulls, barrier
     //    (nobody still reads a slot that is about to be overwritten), then the local fan-out copies.
     PROF_MARK(h, 5);

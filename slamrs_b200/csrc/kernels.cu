@@ -1,7 +1,7 @@
 // Hand-written sm_100a kernels of the grid particle-filter SLAM step.
 //
-//   k_motion_likelihood  robot.rs:170-183 (sample), map.rs:113-145 (beam-endpoint likelihood),
-//                        robot.rs:152-167 (motion pdf)            -> one CTA per particle
+//   k_motion / k_likelihood  robot.rs:170-183 (sample), map.rs:113-145 (beam-endpoint likelihood),
+//                        robot.rs:152-167 (motion pdf)  -> one thread / one warp per particle
 //   k_ray_update         map.rs:71-106 + ray.rs:21-110 + map.rs:148-172 (integrate)
 //                                                                  -> one CTA per particle,
 //                        hit counters accumulated in a shared-memory window, 128-bit write-back
@@ -93,91 +93,105 @@ __device__ __forceinline__ double block_excl_scan_f64(double v, double* warp_tot
     return lane == 0 ? warp_tot[wid] : __dadd_rn(warp_tot[wid], within);
 }
 
-// =============================================================================== k_motion_likelihood
-
-constexpr int ML_THREADS = 128;
-
-__global__ void __launch_bounds__(ML_THREADS)
-k_motion_likelihood(MapGeom geom, OdomModel od, ScanDevice scan, const float* __restrict__ pose_cur,
-                    const int32_t* __restrict__ slot_of, const uint32_t* __restrict__ cells, size_t cells_per_grid,
-                    ParticleResult* __restrict__ results, uint32_t first_particle, const double* __restrict__ z_draws,
-                    uint64_t seed, uint64_t step) {
-    extern __shared__ double s_terms[];  // one log-factor per beam, summed in beam order below
-    __shared__ float s_pose[3];
-    const uint32_t p = blockIdx.x;               // local particle
+// =============================================================================== k_motion + k_likelihood
+// k_motion: one THREAD per particle. Odometry::sample (robot.rs:170-183) and the motion log-density
+// Odometry::probabiliy_of (robot.rs:152-167) need a few hundred scalar f64 operations per particle
+// and nothing else; giving them a warp or a CTA would multiply the issued instructions by 32.
+// The log-density is parked in ParticleResult::weight until k_likelihood folds it in.
+__global__ void __launch_bounds__(128)
+k_motion(OdomModel od, const float* __restrict__ pose_cur, const int32_t* __restrict__ slot_of,
+         ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
+         const double* __restrict__ z_draws, uint64_t seed, uint64_t step) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_local) return;
     const uint32_t gp = first_particle + p;      // global logical index
     const float ox = pose_cur[3 * p], oy = pose_cur[3 * p + 1], otheta = pose_cur[3 * p + 2];
-
-    if (threadIdx.x == 0) {
-        // Odometry::sample, robot.rs:170-183. statrs: sample = mean + std_dev * z.
-        double z1, z2;
-        if (z_draws) {
-            z1 = z_draws[2 * (size_t)gp];
-            z2 = z_draws[2 * (size_t)gp + 1];
-        } else {
-            slamrs_stream::motion_normals(seed, step, gp, &z1, &z2);
-        }
-        const float center_distance = (float)__dadd_rn(od.mean_c, __dmul_rn(od.std_c, z1));
-        const float theta = __fadd_rn(otheta, (float)__dadd_rn(od.mean_t, __dmul_rn(od.std_t, z2)));
-        s_pose[0] = __fadd_rn(ox, __fmul_rn(slamrs_libm::cosf_exact(theta), center_distance));
-        s_pose[1] = __fadd_rn(oy, __fmul_rn(slamrs_libm::sinf_exact(theta), center_distance));
-        s_pose[2] = theta;
+    // Odometry::sample. statrs: sample = mean + std_dev * z.
+    double z1, z2;
+    if (z_draws) {
+        z1 = z_draws[2 * (size_t)gp];
+        z2 = z_draws[2 * (size_t)gp + 1];
+    } else {
+        slamrs_stream::motion_normals(seed, step, gp, &z1, &z2);
     }
-    __syncthreads();
-    const float nx = s_pose[0], ny = s_pose[1], ntheta = s_pose[2];
-    const uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
+    const float center_distance = (float)__dadd_rn(od.mean_c, __dmul_rn(od.std_c, z1));
+    const float ntheta = __fadd_rn(otheta, (float)__dadd_rn(od.mean_t, __dmul_rn(od.std_t, z2)));
+    float sn, cs;
+    slamrs_libm::sincosf_exact(ntheta, &sn, &cs);
+    const float nx = __fadd_rn(ox, __fmul_rn(cs, center_distance));
+    const float ny = __fadd_rn(oy, __fmul_rn(sn, center_distance));
+    // Odometry::probabiliy_of(old, new)
+    const float dx = __fsub_rn(ox, nx), dy = __fsub_rn(oy, ny);
+    const float moved = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    const double ad = angle_diff((double)otheta, (double)ntheta);
+    ParticleResult r;
+    r.weight = __dadd_rn(log(normal_pdf((double)moved, od.mean_c, od.std_c)), log(normal_pdf(ad, od.mean_t, od.std_t)));
+    r.x = nx; r.y = ny; r.theta = ntheta;
+    r.slot = slot_of[p];                    // physical slot, read by other ranks' planners
+    results[gp] = r;
+}
 
-    // Map::probability_of, map.rs:113-145: one gather per valid beam, pre-update map.
-    for (uint32_t b = threadIdx.x; b < scan.n_beams; b += ML_THREADS) {
-        double term = 0.0;
-        if (scan.valid[b]) {
-            float ex, ey;
-            beam_endpoint(nx, ny, ntheta, scan.angle[b], scan.dist[b], &ex, &ey);
-            const float gx = world_to_grid(ex, geom.pos_x, geom.res);
-            const float gy = world_to_grid(ey, geom.pos_y, geom.res);
-            if (grid_is_valid(gx, gy, geom.gw, geom.gh)) {
-                const size_t column = (size_t)f32_as_usize(gx), row = (size_t)f32_as_usize(gy);
-                const uint32_t cell = __ldg(&grid[row * geom.gh + column]);  // index(): map.rs:201-204
-                const double prob = log_odds_probability(cell_log_odds(cell));
-                // Z_HIT = 0.9, SENSOR_MAXDIST = 1.0 (map.rs:108-109)
-                if (prob == 0.5) {
-                    term = log(1.0 / 1.0);
-                } else {
-                    term = log(__dadd_rn(__dmul_rn(0.9, prob), (1.0 - 0.9) * 1.0 / 1.0));
+// k_likelihood: one WARP per particle, lanes over beams. Map::probability_of (map.rs:113-145): one
+// gather per valid beam from the PRE-update grid. LK_UNROLL gathers are in flight per lane before
+// the first exp/log. A never-informed cell (counters 0 -> log-odds 0 -> p = 0.5) contributes
+// log(1/1) = 0 and skips the transcendental work. Each lane adds its terms in beam order, the 32
+// lane sums are combined by a fixed butterfly: deterministic, order-independent of scheduling.
+constexpr int LK_WARPS = 4;
+constexpr int LK_UNROLL = 4;
+
+__global__ void __launch_bounds__(LK_WARPS * 32)
+k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, size_t cells_per_grid,
+             ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local) {
+    const uint32_t p = blockIdx.x * LK_WARPS + (threadIdx.x >> 5);
+    if (p >= n_local) return;
+    const int lane = threadIdx.x & 31;
+    const ParticleResult r = results[first_particle + p];
+    const float nx = r.x, ny = r.y, ntheta = r.theta;
+    const uint32_t* grid = cells + (size_t)r.slot * cells_per_grid;
+
+    double lp = log(1.0);
+    for (uint32_t base = 0; base < scan.n_beams; base += 32u * LK_UNROLL) {
+        uint32_t cell[LK_UNROLL];
+#pragma unroll
+        for (int u = 0; u < LK_UNROLL; ++u) {
+            const uint32_t b = base + (uint32_t)u * 32u + (uint32_t)lane;
+            cell[u] = 0u;
+            if (b < scan.n_beams && scan.valid[b]) {
+                float ex, ey;
+                beam_endpoint(nx, ny, ntheta, scan.angle[b], scan.dist[b], &ex, &ey);
+                const float gx = world_to_grid(ex, geom.pos_x, geom.res);
+                const float gy = world_to_grid(ey, geom.pos_y, geom.res);
+                if (grid_is_valid(gx, gy, geom.gw, geom.gh)) {
+                    const size_t column = (size_t)f32_as_usize(gx), row = (size_t)f32_as_usize(gy);
+                    cell[u] = __ldg(&grid[row * geom.gh + column]);  // index(): map.rs:201-204
                 }
             }
         }
-        s_terms[b] = term;
+#pragma unroll
+        for (int u = 0; u < LK_UNROLL; ++u) {
+            if (cell[u] != 0u) {
+                const double prob = log_odds_probability(cell_log_odds(cell[u]));
+                // Z_HIT = 0.9, SENSOR_MAXDIST = 1.0 (map.rs:108-109)
+                const double term = (prob == 0.5) ? log(1.0 / 1.0)
+                                                  : log(__dadd_rn(__dmul_rn(0.9, prob), (1.0 - 0.9) * 1.0 / 1.0));
+                lp = __dadd_rn(lp, term);
+            }
+        }
     }
-    __syncthreads();
-
-    if (threadIdx.x == 0) {
-        // LogProbability product = running sum in beam order (math.rs:96-100); beams that
-        // contribute nothing hold +0.0, which leaves the sum unchanged.
-        double lp = log(1.0);
-        for (uint32_t b = 0; b < scan.n_beams; ++b) lp = __dadd_rn(lp, s_terms[b]);
-        // Odometry::probabiliy_of, robot.rs:152-167
-        const float dx = __fsub_rn(ox, nx), dy = __fsub_rn(oy, ny);
-        const float center_distance = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-        const double ad = angle_diff((double)otheta, (double)ntheta);
-        const double motion = __dadd_rn(log(normal_pdf((double)center_distance, od.mean_c, od.std_c)),
-                                        log(normal_pdf(ad, od.mean_t, od.std_t)));
-        ParticleResult r;
-        r.weight = exp(__dadd_rn(lp, motion));  // weight.prob().value(), slam.rs:71
-        r.x = nx; r.y = ny; r.theta = ntheta;
-        r.slot = slot_of[p];                    // physical slot, read by other ranks' planners
-        results[gp] = r;
-    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lp = __dadd_rn(lp, __shfl_xor_sync(0xffffffffu, lp, o));
+    // weight.prob().value(), slam.rs:71: exp(log p(z|x,m) + log p(x'|x,u))
+    if (lane == 0) results[first_particle + p].weight = exp(__dadd_rn(lp, r.weight));
 }
 
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
                               const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
                               size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step) {
-    const size_t smem = (size_t)scan.n_beams * sizeof(double);
-    k_motion_likelihood<<<n_local, ML_THREADS, smem, stream>>>(geom, od, scan, pose_cur, slot_of, cells,
-                                                              cells_per_grid, results, first_particle, z_draws, seed,
-                                                              step);
+    k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
+                                                         z_draws, seed, step);
+    k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, cells, cells_per_grid,
+                                                                                   results, first_particle, n_local);
 }
 
 // =============================================================================== k_ray_update
@@ -1053,8 +1067,7 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
         if (a.history) {
             StepRecord r;
             r.step = a.step; r.n_copies = nBD; r.n_pulls = nC; r.distinct = distinct; r.n_leaders = n_lead;
-            r.n_alive = a.counters->n_alive;
-            r.copy_bytes = 0; r.pad = 0;
+            r.n_alive = 0; r.copy_bytes = 0; r.pad = 0;   // filled in by the step's last kernel (k_commit_boxes)
             a.history[a.step % STEP_HISTORY] = r;
         }
     }
@@ -1300,7 +1313,10 @@ __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigne
     for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
          k += (unsigned long long)gridDim.x * blockDim.x)
         *items[k].dst_meta = *items[k].src_meta;   // sources are never destinations of the same launch
-    if (record && blockIdx.x == 0 && threadIdx.x == 0) record->copy_bytes = counters->copy_bytes;
+    if (record && blockIdx.x == 0 && threadIdx.x == 0) {
+        record->copy_bytes = counters->copy_bytes;
+        record->n_alive = counters->n_alive;
+    }
 }
 void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,
                          StepCounters* counters, StepRecord* record) {
@@ -1404,8 +1420,14 @@ void launch_debug_raycast(cudaStream_t stream, const float* x0, const float* y0,
 __global__ void k_debug_sincos(const float* x, uint32_t n, float* s, float* c) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    s[i] = slamrs_libm::sinf_exact(x[i]);
-    c[i] = slamrs_libm::cosf_exact(x[i]);
+    // the fused form is what the kernels use; the separate forms must agree with it bit for bit
+    float fs, fc;
+    slamrs_libm::sincosf_exact(x[i], &fs, &fc);
+    const float ss = slamrs_libm::sinf_exact(x[i]), cc = slamrs_libm::cosf_exact(x[i]);
+    const bool same = (__float_as_uint(fs) == __float_as_uint(ss) || (fs != fs && ss != ss)) &&
+                      (__float_as_uint(fc) == __float_as_uint(cc) || (fc != fc && cc != cc));
+    s[i] = same ? fs : __int_as_float(0x7fc00001);
+    c[i] = same ? fc : __int_as_float(0x7fc00001);
 }
 void launch_debug_sincos(cudaStream_t stream, const float* x, uint32_t n, float* s, float* c) {
     k_debug_sincos<<<(n + 255) / 256, 256, 0, stream>>>(x, n, s, c);

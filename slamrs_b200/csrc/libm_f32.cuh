@@ -185,4 +185,37 @@ SLAMRS_HD float cosf_exact(float y) {
     return y - y;
 }
 
+// sinf and cosf of the same argument with one shared range reduction (what glibc's sincosf does;
+// the results are bit-identical to the two separate calls above: same reduced argument, same
+// polynomials, the quadrant parity only decides which polynomial feeds which output).
+SLAMRS_HD void sincosf_exact(float y, float* sn, float* cs) {
+    const uint32_t yi = f32_bits(y);
+    const uint32_t top = (yi >> 20) & 0x7ffu;
+    double x = (double)y;
+    int n = 0, tsel = 0;
+    double sg = 1.0;
+    if (top < 0x3f4u) {  // |y| < pi/4
+        if (top < 0x398u) { *sn = y; *cs = 1.0f; return; }  // |y| < 2^-12
+    } else if (top < 0x42fu) {  // |y| < 120
+        x = reduce_fast(x, &n);
+        sg = quadrant_sign(n);
+        tsel = n;
+    } else if (top < 0x7f8u) {
+        const int sign = (int)(yi >> 31);
+        x = reduce_large(yi, &n);
+        sg = quadrant_sign(n + sign);
+        tsel = n + sign;
+    } else {
+        *sn = y - y; *cs = y - y;  // inf/nan -> nan
+        return;
+    }
+    const Poly p = poly_table((tsel & 2) != 0);
+    const double x2 = mul_rn(x, x);
+    const double xs = mul_rn(x, sg);
+    const float s_poly = eval_poly(xs, x2, p, 0);
+    const float c_poly = eval_poly(xs, x2, p, 1);
+    if ((n & 1) == 0) { *sn = s_poly; *cs = c_poly; }
+    else { *sn = c_poly; *cs = s_poly; }
+}
+
 }  // namespace slamrs_libm

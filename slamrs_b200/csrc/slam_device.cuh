@@ -71,8 +71,10 @@ __device__ __forceinline__ bool grid_is_valid(float gx, float gy, uint32_t gw, u
 __device__ __forceinline__ void beam_endpoint(float px, float py, float ptheta, float angle, float dist, float* ex,
                                               float* ey) {
     const float a = __fadd_rn(ptheta, angle);
-    *ex = __fadd_rn(px, __fmul_rn(slamrs_libm::cosf_exact(a), dist));
-    *ey = __fadd_rn(py, __fmul_rn(slamrs_libm::sinf_exact(a), dist));
+    float sn, cs;
+    slamrs_libm::sincosf_exact(a, &sn, &cs);
+    *ex = __fadd_rn(px, __fmul_rn(cs, dist));
+    *ey = __fadd_rn(py, __fmul_rn(sn, dist));
 }
 
 // inverse_sensor_model, map.rs:148-172 with tolerance 2.0 (map.rs:104).

@@ -17,6 +17,10 @@ int main(int argc, char** argv) {
         memcpy(&x, &u, 4);
         float a = sinf(x), b = slamrs_libm::sinf_exact(x);
         float c = cosf(x), d = slamrs_libm::cosf_exact(x);
+        float fs, fc;
+        slamrs_libm::sincosf_exact(x, &fs, &fc);   // the fused form must reproduce the two separate calls
+        if (memcmp(&fs, &b, 4) != 0 && !((fs != fs) && (b != b))) { if (bad_s < 5) printf("fused sin mismatch x=%a\n", x); bad_s++; }
+        if (memcmp(&fc, &d, 4) != 0 && !((fc != fc) && (d != d))) { if (bad_c < 5) printf("fused cos mismatch x=%a\n", x); bad_c++; }
         uint32_t ua, ub, uc, ud;
         memcpy(&ua, &a, 4); memcpy(&ub, &b, 4); memcpy(&uc, &c, 4); memcpy(&ud, &d, 4);
         bool nan_ok_s = (a != a) && (b != b);
