@@ -480,13 +480,14 @@ int slamrs_gpu_upload_scan(slamrs_gpu_handle* h, const float* angle, const float
     h->n_beams = n_beams;
     h->scan_external = false;
     // window radius for the ray kernel: farthest finite measurement, in cells, plus the two extra
-    // steps of apply_measurement (map.rs:97) and rounding slack. Correctness never depends on it:
+    // steps of apply_measurement (map.rs:97) and the slack that lets the ray kernel prove, per ray, that
+    // no cell leaves the window (see k_ray_update_packed). Correctness never depends on it:
     // cells outside the window take the global-atomic path.
     float maxd = 0.0f;
     for (uint32_t i = 0; i < n_beams; ++i)
         if (isfinite(dist[i]) && fabsf(dist[i]) > maxd) maxd = fabsf(dist[i]);
     const float cells = ceilf(maxd / h->geom.res);
-    h->radius_cells = (cells < 4096.0f ? (int)cells : 4096) + 4;
+    h->radius_cells = (cells < 4096.0f ? (int)cells : 4096) + 6;
     return SLAMRS_OK;
 }
 
@@ -499,7 +500,7 @@ int slamrs_gpu_set_scan_device(slamrs_gpu_handle* h, const float* angle_device, 
     h->n_beams = n_beams;
     h->scan_external = true;
     const float cells = ceilf(fabsf(max_dist) / h->geom.res);
-    h->radius_cells = ((cells == cells && cells < 4096.0f) ? (int)cells : 4096) + 4;
+    h->radius_cells = ((cells == cells && cells < 4096.0f) ? (int)cells : 4096) + 6;
     return SLAMRS_OK;
 }
 

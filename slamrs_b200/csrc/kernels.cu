@@ -439,13 +439,24 @@ __host__ __device__ inline int ray_window_cells_upper_bound_packed(int radius) {
     return total;
 }
 
-__global__ void __launch_bounds__(RAY_MAX_THREADS)
+// Facts the packed kernel's fast walk relies on:
+//  * |x0 - centre_x| and |y0 - centre_y| never decrease along a walk (x only moves by x_inc, y
+//    only by y_inc, away from the start cell), IEEE rounding is monotone, so
+//    acc = fl(fl(dx^2) + fl(dy^2)) is non-decreasing along the ray. The inverse sensor model is
+//    therefore a free run (acc < free_below), then an occupied run (acc <= prior_above, hits
+//    only), then prior cells that add nothing: two tight loops and an early exit replace the
+//    per-cell three-way classification.
+//  * a ray whose endpoint cell is (ax, ay) cells away from the start cell visits only cells within
+//    (ax + 2, ay + 2) of it; if that corner is inside the disc window and the disc is inside the
+//    grid, no per-cell window or grid test is needed.
+__global__ void __maxnreg__(80)   // 2 CTAs of 384 threads per SM; blocks have at most RAY_MAX_THREADS threads
 k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
              const uint32_t* __restrict__ alive_list,
                     const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
                     size_t cells_per_grid, int radius, StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
     __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
+    __shared__ uint32_t s_rowb[RAY_MAX_ROWS];           // shared byte address of column x = 0 of the row
     __shared__ int s_ext[4];
     if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
     const uint32_t p = alive_list[blockIdx.x];
@@ -460,6 +471,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     if (lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh) return;
     const int cx0 = (int)lcx, cy0 = (int)lcy;
     const int gw = (int)geom.gw, gh = (int)geom.gh;
+    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
 
     // ---- row table of the disc window (x ranges aligned to 8 cells = one 128-bit group)
     const int wy0 = max(0, cy0 - radius), wy1 = min(gh, cy0 + radius + 1);
@@ -483,7 +495,11 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                 const int t = __shfl_up_sync(0xffffffffu, inc, o);
                 if ((int)threadIdx.x >= o) inc += t;
             }
-            if (ly < wh) s_row[ly].x = carry + inc - w;
+            if (ly < wh) {
+                const int first = carry + inc - w;
+                s_row[ly].x = first;
+                s_rowb[ly] = win_base + 2u * (uint32_t)(first - (s_row[ly].y & 0xffff));
+            }
             carry += __shfl_sync(0xffffffffu, inc, 31);
         }
         if (threadIdx.x == 0) s_row[wh] = make_int2(carry, 0);
@@ -496,7 +512,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     }
     __syncthreads();
 
-    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
+    const bool disc_in_grid = cx0 - radius >= 0 && cx0 + radius < gw && cy0 - radius >= 0 && cy0 + radius < gh;
     bool saturated = false;
     uint32_t spilled = 0;
     for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
@@ -511,6 +527,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         const float delta_x = fabsf(__fsub_rn(x1, sx)), delta_y = fabsf(__fsub_rn(y1, sy));
         const float fx0 = floorf(sx), fy0 = floorf(sy);
         unsigned long long n = 1ull + 2ull;   // additional_steps = 2 (map.rs:97)
+        unsigned long long ax = 0ull, ay = 0ull;   // |endpoint cell - start cell| per axis
         int x_inc, y_inc;
         float error;
         if (delta_x == 0.0f) {
@@ -518,11 +535,11 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
             error = __int_as_float(0x7f800000);
         } else if (x1 > sx) {
             x_inc = 1;
-            n += (unsigned long long)f32_as_isize(__fsub_rn(floorf(x1), (float)cx0));
+            ax = (unsigned long long)f32_as_isize(__fsub_rn(floorf(x1), (float)cx0));
             error = __fmul_rn(__fsub_rn(__fadd_rn(fx0, 1.0f), sx), delta_y);
         } else {
             x_inc = -1;
-            n += (unsigned long long)(long long)cx0 - (unsigned long long)f32_as_isize(floorf(x1));
+            ax = (unsigned long long)(long long)cx0 - (unsigned long long)f32_as_isize(floorf(x1));
             error = __fmul_rn(__fsub_rn(sx, fx0), delta_y);
         }
         if (delta_y == 0.0f) {
@@ -530,22 +547,101 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
             error = __fsub_rn(error, __int_as_float(0x7f800000));
         } else if (y1 > sy) {
             y_inc = 1;
-            n += (unsigned long long)f32_as_isize(floorf(y1)) - (unsigned long long)(long long)cy0;
+            ay = (unsigned long long)f32_as_isize(floorf(y1)) - (unsigned long long)(long long)cy0;
             error = __fsub_rn(error, __fmul_rn(__fsub_rn(__fadd_rn(fy0, 1.0f), sy), delta_x));
         } else {
             y_inc = -1;
-            n += (unsigned long long)(long long)cy0 - (unsigned long long)f32_as_isize(floorf(y1));
+            ay = (unsigned long long)(long long)cy0 - (unsigned long long)f32_as_isize(floorf(y1));
             error = __fsub_rn(error, __fmul_rn(__fsub_rn(sy, fy0), delta_x));
         }
+        n += ax + ay;   // wrapping isize arithmetic, then `as usize`
         const unsigned long long cap = (unsigned long long)geom.gw + geom.gh + 8ull;
         int remaining = (int)(n < cap ? n : cap);
 
-        int x = cx0, y = cy0;
         const float x_step = (float)x_inc, y_step = (float)y_inc;
-        float cxf = __fadd_rn((float)x, 0.5f), cyf = __fadd_rn((float)y, 0.5f);
+        float cxf = __fadd_rn((float)cx0, 0.5f), cyf = __fadd_rn((float)cy0, 0.5f);
         float dxs = __fsub_rn(sx, cxf), dys = __fsub_rn(sy, cyf);
         float dx2 = __fmul_rn(dxs, dxs), dy2 = __fmul_rn(dys, dys);
-        // window row of the current y: offset (cells), x0, width (0 when y is outside the window)
+
+        // every cell of this ray inside the window and the grid?
+        bool fast = false;
+        if (disc_in_grid && ax < 4096ull && ay < 4096ull) {
+            const int cxa = (int)ax + 2, cya = (int)ay + 2;
+            fast = cxa * cxa + cya * cya <= radius * radius;
+        }
+        if (fast) {
+            uint32_t x2 = 2u * (uint32_t)cx0;         // twice the current column
+            const uint32_t x_inc2 = (uint32_t)(2 * x_inc);
+            int ly = cy0 - wy0;
+            uint32_t rb = s_rowb[ly];
+            // free run
+            while (remaining > 0) {
+                const float acc = __fadd_rn(dx2, dy2);
+                if (!(acc < cls.free_below)) break;
+                const uint32_t c2 = rb + x2;           // shared byte address of the 16-bit window cell
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(c2 & ~3u), "r"((c2 & 2u) ? 0x10000u : 1u) : "memory");
+                if (error > 0.0f) {
+                    error = __fsub_rn(error, delta_x);
+                    cyf = __fadd_rn(cyf, y_step);
+                    dys = __fsub_rn(sy, cyf);
+                    dy2 = __fmul_rn(dys, dys);
+                    ly += y_inc;
+                    rb = s_rowb[ly];
+                } else {
+                    error = __fadd_rn(error, delta_y);
+                    cxf = __fadd_rn(cxf, x_step);
+                    dxs = __fsub_rn(sx, cxf);
+                    dx2 = __fmul_rn(dxs, dxs);
+                    x2 += x_inc2;
+                }
+                remaining -= 1;
+            }
+            // occupied run (hits only): bounded 5-bit field per scan, exact global path beyond it
+            if (cls.mid_inc != 0u) {
+                while (remaining > 0) {
+                    const float acc = __fadd_rn(dx2, dy2);
+                    if (acc > cls.prior_above) break;
+                    const uint32_t c2 = rb + x2;
+                    const uint32_t shift = ((c2 & 2u) << 3) + PK_FREE_BITS;
+                    uint32_t old;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(c2 & ~3u) : "memory");
+                    bool done = false;
+                    for (;;) {
+                        if (((old >> shift) & PK_OCC_MAX) == PK_OCC_MAX) break;
+                        uint32_t seen;
+                        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;"
+                                     : "=r"(seen) : "r"(c2 & ~3u), "r"(old), "r"(old + (1u << shift)) : "memory");
+                        if (seen == old) { done = true; break; }
+                        old = seen;
+                    }
+                    if (!done) {
+                        const int x = (int)(x2 >> 1), y = wy0 + ly;
+                        global_cell_add(&grid[(size_t)y * geom.gh + x], CELL_OCC_INC, &saturated);
+                        ext_add(s_ext, x, y, x, y);
+                        spilled++;
+                    }
+                    if (error > 0.0f) {
+                        error = __fsub_rn(error, delta_x);
+                        cyf = __fadd_rn(cyf, y_step);
+                        dys = __fsub_rn(sy, cyf);
+                        dy2 = __fmul_rn(dys, dys);
+                        ly += y_inc;
+                        rb = s_rowb[ly];
+                    } else {
+                        error = __fadd_rn(error, delta_y);
+                        cxf = __fadd_rn(cxf, x_step);
+                        dxs = __fsub_rn(sx, cxf);
+                        dx2 = __fmul_rn(dxs, dxs);
+                        x2 += x_inc2;
+                    }
+                    remaining -= 1;
+                }
+            }
+            continue;
+        }
+
+        // general walk: per-cell window and grid tests (rays that may leave the window or the grid)
+        int x = cx0, y = cy0;
         int ly = y - wy0;
         int2 row = s_row[ly];                      // the start cell is always inside the window
         int lx = x - (row.y & 0xffff);
@@ -611,52 +707,59 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     }
     __syncthreads();
 
-    // ---- write-back: 8 packed cells (one 128-bit shared load) -> two 128-bit global RMWs
-    const int total8 = wcells >> 3;
+    // ---- write-back, row by row: one warp per window row, one lane per 8-cell group (a 128-bit
+    // shared load -> two 128-bit global RMWs); RAY_WB_ROWS rows are in flight per warp. A counter
+    // below 2^15 cannot saturate by one scan's increment, which is the common, branch-free case.
+    constexpr int RAY_WB_ROWS = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
-    constexpr int BATCH = 4;
     int exmin = 0x7fffffff, eymin = 0x7fffffff, exmax = -1, eymax = -1;   // this thread's touched extent
-    for (int base = threadIdx.x; base < total8; base += blockDim.x * BATCH) {
-        uint4 d[BATCH], va[BATCH], vb[BATCH];
-        uint4* gp[BATCH];
-        bool nz[BATCH];
+    for (int ly0 = warp; ly0 < wh; ly0 += n_warps * RAY_WB_ROWS) {
+        for (int g0 = 0; g0 < (RAY_MAX_RADIUS * 2 + 16) / 8; g0 += 32) {
+            uint4 d[RAY_WB_ROWS], va[RAY_WB_ROWS], vb[RAY_WB_ROWS];
+            uint4* gp[RAY_WB_ROWS];
+            bool nz[RAY_WB_ROWS];
+            bool any_row = false;
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-            const int i = base + j * (int)blockDim.x;
-            nz[j] = false;
-            if (i < total8) {
-                d[j] = win4[i];
-                nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
-                if (nz[j]) {
-                    int lo = 0, hi = wh;
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_row[mid].x <= 8 * i) lo = mid; else hi = mid;
+            for (int j = 0; j < RAY_WB_ROWS; ++j) {
+                const int ly = ly0 + j * n_warps;
+                nz[j] = false;
+                if (ly < wh) {
+                    const int2 row = s_row[ly];
+                    const int groups = row.y >> 19;          // width / 8
+                    const int g = g0 + lane;
+                    any_row |= g0 < groups;
+                    if (g < groups) {
+                        d[j] = win4[(row.x >> 3) + g];
+                        nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
+                        if (nz[j]) {
+                            const int gx0 = (row.y & 0xffff) + 8 * g;
+                            exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
+                            eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
+                            gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + ly) * geom.gh + gx0);
+                        }
                     }
-                    const int lx = 8 * i - s_row[lo].x;
-                    const int gx0 = (s_row[lo].y & 0xffff) + lx;
-                    exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
-                    eymin = min(eymin, wy0 + lo); eymax = max(eymax, wy0 + lo);
-                    gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + gx0);
                 }
             }
-        }
+            if (!any_row) break;   // warp-uniform: no row of this batch reaches group g0
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j)
-            if (nz[j]) { va[j] = gp[j][0]; vb[j] = gp[j][1]; }
+            for (int j = 0; j < RAY_WB_ROWS; ++j)
+                if (nz[j]) { va[j] = gp[j][0]; vb[j] = gp[j][1]; }
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-            if (nz[j]) {
-                auto apply = [&](uint32_t g, uint32_t packed16) {
-                    const uint32_t delta = (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16);
-                    return cell_sat_add(g, delta, &saturated);
-                };
-                va[j].x = apply(va[j].x, d[j].x & 0xffffu); va[j].y = apply(va[j].y, d[j].x >> 16);
-                va[j].z = apply(va[j].z, d[j].y & 0xffffu); va[j].w = apply(va[j].w, d[j].y >> 16);
-                vb[j].x = apply(vb[j].x, d[j].z & 0xffffu); vb[j].y = apply(vb[j].y, d[j].z >> 16);
-                vb[j].z = apply(vb[j].z, d[j].w & 0xffffu); vb[j].w = apply(vb[j].w, d[j].w >> 16);
-                gp[j][0] = va[j];
-                gp[j][1] = vb[j];
+            for (int j = 0; j < RAY_WB_ROWS; ++j) {
+                if (nz[j]) {
+                    auto apply = [&](uint32_t g, uint32_t packed16) {
+                        const uint32_t delta = (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16);
+                        if ((g & 0x80008000u) == 0u) return g + delta;
+                        return cell_sat_add(g, delta, &saturated);
+                    };
+                    va[j].x = apply(va[j].x, d[j].x & 0xffffu); va[j].y = apply(va[j].y, d[j].x >> 16);
+                    va[j].z = apply(va[j].z, d[j].y & 0xffffu); va[j].w = apply(va[j].w, d[j].y >> 16);
+                    vb[j].x = apply(vb[j].x, d[j].z & 0xffffu); vb[j].y = apply(vb[j].y, d[j].z >> 16);
+                    vb[j].z = apply(vb[j].z, d[j].w & 0xffffu); vb[j].w = apply(vb[j].w, d[j].w >> 16);
+                    gp[j][0] = va[j];
+                    gp[j][1] = vb[j];
+                }
             }
         }
     }
