@@ -62,7 +62,12 @@ enum slamrs_flags {
      * The default moves only the informed extent of each grid -- cells outside it are still at
      * the prior in source and destination alike, so the result is identical. Grids whose side is
      * not a multiple of 8 cells always use whole-grid copies. */
-    SLAMRS_FLAG_FULL_GRID_COPY = 4
+    SLAMRS_FLAG_FULL_GRID_COPY = 4,
+    /* Multi-GPU only. Exchange the per-particle results with ncclAllGather and synchronise the
+     * ranks with NCCL all-reduces. The default fuses the exchange into the likelihood kernel
+     * (each record is stored straight into every peer's copy over NVLink) and synchronises through
+     * peer-mapped flags, which costs a few microseconds instead of a collective launch. */
+    SLAMRS_FLAG_NCCL_EXCHANGE = 8
 };
 
 typedef struct slamrs_gpu_handle slamrs_gpu_handle;

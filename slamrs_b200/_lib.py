@@ -16,6 +16,7 @@ RNG_SHARED_STREAM, RNG_CALLER = 0, 1
 FLAG_GENERIC_RAY_KERNEL = 1
 FLAG_UPDATE_ALL_PARTICLES = 2
 FLAG_FULL_GRID_COPY = 4
+FLAG_NCCL_EXCHANGE = 8
 HISTORY_VALUES = 6
 
 EXPORTS = [

@@ -32,15 +32,24 @@ struct slamrs_gpu_handle {
     uint32_t n_slots = 0, n_spare = 0;
     MapGeom geom{};
 
-    void* d_pool = nullptr;      // one allocation: [SlotMeta x 2*n_local | grid slots]; peers map it whole
+    // one allocation, mapped whole by the peers:
+    // [SlotMeta x 2*n_local | ParticleResult x n_total | barrier flags | grid slots]
+    void* d_pool = nullptr;
     size_t pool_header = 0;      // bytes in front of the first grid slot
+    size_t off_results = 0, off_flags = 0;
+    unsigned long long* d_flags = nullptr;       // PEER_MAX_WORLD epochs, written by the peers
+    ParticleResult** d_peer_results = nullptr;   // device array [world]
+    unsigned long long** d_peer_flags = nullptr; // device array [world]
+    unsigned long long barrier_epoch = 0;
+    bool p2p_exchange = false;   // fused peer stores + flag barriers instead of NCCL collectives
     SlotMeta* d_meta = nullptr;  // = d_pool
     uint32_t* d_cells = nullptr; // = d_pool + pool_header
     bool boxed_copy = false;     // extent-limited copies (needs rows that are multiples of 32 bytes)
     int32_t* d_slot[2] = {nullptr, nullptr};
     float* d_pose[2] = {nullptr, nullptr};
     int cur = 0;
-    ParticleResult* d_results = nullptr;
+    ParticleResult* d_results_base = nullptr;   // 2 x n_total records inside the pool header
+    ParticleResult* d_results = nullptr;        // the generation of the last issued step
     double* d_wnorm = nullptr;
     double* d_cum = nullptr;
     uint32_t* d_idx = nullptr;
@@ -52,7 +61,7 @@ struct slamrs_gpu_handle {
     double* d_z = nullptr;
     double* d_u = nullptr;
     int32_t *d_keep = nullptr, *d_need = nullptr, *d_free = nullptr, *d_spare = nullptr;
-    CopyItem *d_copies = nullptr, *d_pulls = nullptr;
+    CopyItem* d_copies = nullptr;
     uint32_t* d_leaders = nullptr;
     void* d_jobs = nullptr;      // CopyJob scratch of the extent-limited copy
     uint32_t* d_alive = nullptr;
@@ -178,10 +187,18 @@ int setup_peers(slamrs_gpu_handle* h) {
     }
     std::vector<uint32_t*> pcells(W);
     std::vector<SlotMeta*> pmeta(W);
+    std::vector<ParticleResult*> pres(W);
+    std::vector<unsigned long long*> pflags(W);
     for (uint32_t r = 0; r < W; ++r) {
         pmeta[r] = (SlotMeta*)peers[r];
         pcells[r] = (uint32_t*)(peers[r] + h->pool_header);
+        pres[r] = (ParticleResult*)(peers[r] + h->off_results);
+        pflags[r] = (unsigned long long*)(peers[r] + h->off_flags);
     }
+    CU_TRY(h, cudaMalloc(&h->d_peer_results, sizeof(ParticleResult*) * W));
+    CU_TRY(h, cudaMemcpy(h->d_peer_results, pres.data(), sizeof(ParticleResult*) * W, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMalloc(&h->d_peer_flags, sizeof(unsigned long long*) * W));
+    CU_TRY(h, cudaMemcpy(h->d_peer_flags, pflags.data(), sizeof(unsigned long long*) * W, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMalloc(&h->d_peer_cells, sizeof(uint32_t*) * W));
     CU_TRY(h, cudaMemcpy(h->d_peer_cells, pcells.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMalloc(&h->d_peer_meta, sizeof(SlotMeta*) * W));
@@ -195,9 +212,15 @@ void free_all(slamrs_gpu_handle* h) {
     if (h->side_stream) cudaStreamSynchronize(h->side_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && h->d_barrier && h->stream) {
-        // nobody may still be pulling from this pool when it is freed
-        std::string err;
-        if (comm_barrier(h->comm, h->d_barrier, h->stream, &err) == 0) cudaStreamSynchronize(h->stream);
+        // nobody may still be copying from this pool when it is freed. The peer-flag barrier gives up
+        // after about two seconds, so a rank whose peer died does not hang in destroy.
+        if (h->p2p_exchange && h->d_peer_flags) {
+            launch_peer_barrier(h->stream, h->d_peer_flags, h->d_flags, h->rank, h->world, ++h->barrier_epoch, h->d_counters);
+            cudaStreamSynchronize(h->stream);
+        } else {
+            std::string err;
+            if (comm_barrier(h->comm, h->d_barrier, h->stream, &err) == 0) cudaStreamSynchronize(h->stream);
+        }
     }
     for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     h->ipc_opened.clear();
@@ -206,12 +229,13 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_pool);
     cudaFree(h->d_slot[0]); cudaFree(h->d_slot[1]);
     cudaFree(h->d_pose[0]); cudaFree(h->d_pose[1]);
-    cudaFree(h->d_results); cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx);
+    cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx);
     cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
-    cudaFree(h->d_copies); cudaFree(h->d_pulls); cudaFree(h->d_leaders); cudaFree(h->d_alive); cudaFree(h->d_jobs);
+    cudaFree(h->d_copies); cudaFree(h->d_leaders); cudaFree(h->d_alive); cudaFree(h->d_jobs);
     cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells); cudaFree(h->d_peer_meta);
+    cudaFree(h->d_peer_results); cudaFree(h->d_peer_flags);
     cudaFree(h->d_history);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->prof_events.clear();
@@ -260,6 +284,18 @@ int prof_flush(slamrs_gpu_handle* h) {
     do {                                                                                                  \
         if ((h)->profiling) CU_TRY(h, cudaEventRecord((h)->prof_events[(h)->prof_recorded * PROF_MARKS + (m)], (h)->stream)); \
     } while (0)
+
+// stream-ordered barrier across ranks inside a step: peer flags by default, NCCL on request
+int step_barrier(slamrs_gpu_handle* h) {
+    if (h->p2p_exchange) {
+        launch_peer_barrier(h->stream, h->d_peer_flags, h->d_flags, h->rank, h->world, ++h->barrier_epoch, h->d_counters);
+        h->launches++;
+        return SLAMRS_OK;
+    }
+    std::string err;
+    if (comm_barrier(h->comm, h->d_barrier, h->stream, &err)) return fail(h, SLAMRS_E_NCCL, err);
+    return SLAMRS_OK;
+}
 
 int fetch_counters(slamrs_gpu_handle* h) {
     CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(StepCounters), cudaMemcpyDeviceToHost, h->stream));
@@ -314,6 +350,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
         return fail(nullptr, SLAMRS_E_INVALID_ARG, "slamrs_gpu_config size/ABI version mismatch");
     if (cfg->n_particles == 0)  // ParticleFilter::new asserts, particle.rs:16
         return fail(nullptr, SLAMRS_E_INVALID_ARG, "Must have at least one particle");
+    if (cfg->world_size > PEER_MAX_WORLD) return fail(nullptr, SLAMRS_E_INVALID_ARG, "world_size above 64");
     if (cfg->world_size == 0 || cfg->rank >= cfg->world_size || cfg->n_particles % cfg->world_size != 0)
         return fail(nullptr, SLAMRS_E_INVALID_ARG, "bad rank/world_size or n_particles not divisible by world_size");
     if (cfg->n_particles > 0x7fffffffull) return fail(nullptr, SLAMRS_E_INVALID_ARG, "too many particles");
@@ -400,10 +437,18 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
 
     // the header holds one SlotMeta per possible slot; its size depends on n_local only, so every
     // rank can locate a peer's slots and extents from the peer's pool base alone
-    h->pool_header = (sizeof(SlotMeta) * 2 * (size_t)h->n_local + 4095) & ~(size_t)4095;
+    h->off_results = (sizeof(SlotMeta) * 2 * (size_t)h->n_local + 255) & ~(size_t)255;
+    // two generations of the population array (step parity): a peer that is one step ahead stores
+    // its next records while this rank's host may still be reading the last step's
+    h->off_flags = (h->off_results + 2 * sizeof(ParticleResult) * (size_t)h->n_total + 255) & ~(size_t)255;
+    h->pool_header = (h->off_flags + sizeof(unsigned long long) * PEER_MAX_WORLD + 4095) & ~(size_t)4095;
     CREATE_CU(cudaMalloc(&h->d_pool, h->pool_header + (size_t)h->n_slots * grid_bytes));
     h->d_meta = (SlotMeta*)h->d_pool;
     h->d_cells = (uint32_t*)((char*)h->d_pool + h->pool_header);
+    h->d_results_base = (ParticleResult*)((char*)h->d_pool + h->off_results);   // zeroed with the pool
+    h->d_results = h->d_results_base;
+    h->d_flags = (unsigned long long*)((char*)h->d_pool + h->off_flags);
+    h->p2p_exchange = h->world > 1 && (cfg->flags & SLAMRS_FLAG_NCCL_EXCHANGE) == 0;
     CREATE_CU(cudaMemsetAsync(h->d_pool, 0, h->pool_header + (size_t)h->n_slots * grid_bytes, h->stream));  // ln(0.5/0.5) = 0
     h->boxed_copy = (cfg->flags & SLAMRS_FLAG_FULL_GRID_COPY) == 0 && cfg->grid_w % 8u == 0u;
     for (int i = 0; i < 2; ++i) {
@@ -411,8 +456,6 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
         CREATE_CU(cudaMalloc(&h->d_pose[i], sizeof(float) * 3 * h->n_local));
         CREATE_CU(cudaMemsetAsync(h->d_pose[i], 0, sizeof(float) * 3 * h->n_local, h->stream));  // Pose::default()
     }
-    CREATE_CU(cudaMalloc(&h->d_results, sizeof(ParticleResult) * h->n_total));
-    CREATE_CU(cudaMemsetAsync(h->d_results, 0, sizeof(ParticleResult) * h->n_total, h->stream));
     CREATE_CU(cudaMalloc(&h->d_wnorm, sizeof(double) * h->n_total));
     CREATE_CU(cudaMalloc(&h->d_cum, sizeof(double) * h->n_total));
     CREATE_CU(cudaMalloc(&h->d_idx, sizeof(uint32_t) * h->n_total));
@@ -427,7 +470,6 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_free, sizeof(int32_t) * ((size_t)h->n_local + h->n_spare + 1)));
     CREATE_CU(cudaMalloc(&h->d_spare, sizeof(int32_t) * ((size_t)h->n_spare + 1)));
     CREATE_CU(cudaMalloc(&h->d_copies, sizeof(CopyItem) * h->n_local));
-    CREATE_CU(cudaMalloc(&h->d_pulls, sizeof(CopyItem) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_leaders, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_jobs, copy_job_bytes() * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_alive, sizeof(uint32_t) * h->n_local));
@@ -525,26 +567,33 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     }
     const int cur = h->cur, nxt = cur ^ 1;
     const size_t grid_bytes = h->cells_per_grid * sizeof(uint32_t);
+    const uint32_t res_off = (uint32_t)(h->step & 1ull) * h->n_total;
+    h->d_results = h->d_results_base + res_off;
 
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->cells_per_grid,
-                             h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step);
+                             h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step,
+                             h->p2p_exchange ? h->d_peer_results : nullptr, res_off, h->rank, h->world);
     h->launches += 2;   // k_motion + k_likelihood
-    // 2. the one exchange step: every GPU needs every particle's weight, pose and slot
+    // 2. the one exchange step: every GPU needs every particle's weight, pose and slot. Default:
+    //    k_likelihood has already stored each record into every peer (NVLink), only the barrier is
+    //    left. SLAMRS_FLAG_NCCL_EXCHANGE: ncclAllGather of the shard instead.
     PROF_MARK(h, 1);
     if (h->world > 1) {
-        std::string err;
-        if (comm_all_gather(h->comm, h->d_results + h->first, h->d_results, sizeof(ParticleResult) * h->n_local, s, &err))
-            return fail(h, SLAMRS_E_NCCL, err);
+        if (h->p2p_exchange) {
+            int brc = step_barrier(h);
+            if (brc) return brc;
+        } else {
+            std::string err;
+            if (comm_all_gather(h->comm, h->d_results + h->first, h->d_results, sizeof(ParticleResult) * h->n_local, s, &err))
+                return fail(h, SLAMRS_E_NCCL, err);
+        }
     }
     // 3. normalise, argmax, running sum; systematic resampling indices (replicated on every GPU);
     //    which local particles survive
     PROF_MARK(h, 2);
-    // zeroes saturated, spilled (adjacent) and n_alive
-    CU_TRY(h, cudaMemsetAsync(&h->d_counters->saturated, 0, 2 * sizeof(unsigned long long), s));
-    // n_alive, copy_bytes and copy_max_rows (adjacent)
-    CU_TRY(h, cudaMemsetAsync(&h->d_counters->n_alive, 0, 3 * sizeof(unsigned long long), s));
+    // (k_weights also zeroes the per-step counters)
     launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, h->d_counters);
@@ -559,7 +608,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.slot_old = h->d_slot[cur]; pa.slot_new = h->d_slot[nxt];
     pa.keep = h->d_keep; pa.need = h->d_need; pa.free_list = h->d_free; pa.spare_list = h->d_spare;
     pa.n_spare_cap = h->n_spare;
-    pa.copies = h->d_copies; pa.pulls = h->d_pulls; pa.leaders = h->d_leaders;
+    pa.copies = h->d_copies; pa.leaders = h->d_leaders;
     pa.cells = h->d_cells; pa.cells_per_grid = h->cells_per_grid;
     pa.peer_cells = h->d_peer_cells;
     pa.meta = h->d_meta; pa.peer_meta = h->d_peer_meta;
@@ -581,24 +630,13 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     h->launches++;
     PROF_MARK(h, 4);
     CU_TRY(h, cudaStreamWaitEvent(s, h->ev_plan, 0));   // join: the copy lists are ready
-    // 6. grid traffic. Across GPUs: barrier (every survivor is integrated), NVLink pulls, barrier
-    //    (nobody still reads a slot that is about to be overwritten), then the local fan-out copies.
+    // 6. grid traffic: one launch copies from local and (over NVLink) remote sources alike. Across
+    //    GPUs one barrier first: every source grid, wherever it lives, has received the scan. No
+    //    second barrier: nothing written in this step is a slot a peer reads in this step (k_plan).
     PROF_MARK(h, 5);
     if (h->world > 1) {
-        std::string err;
-        if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
-        if (h->boxed_copy) {
-            launch_copy_boxed(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->n_local, h->d_jobs, h->geom.gw,
-                              h->d_counters, h->num_sms);
-            h->launches++;
-        } else {
-            launch_copy(s, h->d_pulls, nullptr, &h->d_counters->n_pulls, nullptr, h->cells_per_grid, h->num_sms);
-            launch_account_full_copy(s, &h->d_counters->n_pulls, nullptr, grid_bytes, h->d_counters);
-            h->launches++;
-        }
-        launch_commit_boxes(s, h->d_pulls, &h->d_counters->n_pulls, h->n_local, h->d_counters, nullptr);
-        h->launches += 2;
-        if (comm_barrier(h->comm, h->d_barrier, s, &err)) return fail(h, SLAMRS_E_NCCL, err);
+        int brc = step_barrier(h);
+        if (brc) return brc;
     }
     PROF_MARK(h, 6);
     if (h->boxed_copy) {
@@ -628,6 +666,8 @@ int slamrs_gpu_sync(slamrs_gpu_handle* h) {
     DeviceGuard g(h->device);
     int rc = fetch_counters(h);
     if (rc) return rc;
+    if (h->h_counters->barrier_timeout)
+        return fail(h, SLAMRS_E_INTERNAL, "a peer GPU did not reach the step barrier within the time limit");
     if (h->h_counters->staging_short)
         return fail(h, SLAMRS_E_STAGING,
                     "cross-GPU migration needed more free grid slots than available; raise spare_slots");

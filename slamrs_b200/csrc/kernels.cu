@@ -15,8 +15,11 @@
 // (grid copies) with a latency-bound cell walk in front of it.
 #include "kernels.cuh"
 #include "shared_stream.cuh"
+#include <cooperative_groups.h>
 
 namespace slamrs {
+
+namespace cg = cooperative_groups;
 
 // =============================================================================== helpers
 
@@ -141,7 +144,8 @@ constexpr int LK_UNROLL = 4;
 
 __global__ void __launch_bounds__(LK_WARPS * 32)
 k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, size_t cells_per_grid,
-             ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local) {
+             ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
+             ParticleResult* const* __restrict__ peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     const uint32_t p = blockIdx.x * LK_WARPS + (threadIdx.x >> 5);
     if (p >= n_local) return;
     const int lane = threadIdx.x & 31;
@@ -181,17 +185,57 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lp = __dadd_rn(lp, __shfl_xor_sync(0xffffffffu, lp, o));
     // weight.prob().value(), slam.rs:71: exp(log p(z|x,m) + log p(x'|x,u))
-    if (lane == 0) results[first_particle + p].weight = exp(__dadd_rn(lp, r.weight));
+    ParticleResult out = r;
+    out.weight = exp(__dadd_rn(lp, r.weight));
+    if (lane == 0) results[first_particle + p] = out;
+    // The exchange step, fused: lane q stores the finished record straight into GPU q's copy of
+    // the population array over NVLink (24 bytes per particle and peer), so that after one
+    // peer barrier every GPU holds every particle's weight, pose and slot.
+    if (peer_results != nullptr && (uint32_t)lane < world && (uint32_t)lane != rank)
+        peer_results[lane][peer_offset + first_particle + p] = out;
+}
+
+// =============================================================================== k_peer_barrier
+// Stream-ordered barrier across the GPUs of one box through peer-mapped flags: lane q publishes
+// this rank's epoch into GPU q's flag array (release, system scope: every write this GPU issued
+// before, including the peer stores of earlier kernels in the stream, is visible first) and then
+// waits until GPU q's epoch has arrived here (acquire). Epochs only grow, so flags are never reset.
+// A bounded wait (about two seconds) turns a lost peer into an error instead of a hung GPU.
+__global__ void __launch_bounds__(64)
+k_peer_barrier(unsigned long long* const* __restrict__ peer_flags, unsigned long long* my_flags, uint32_t rank,
+               uint32_t world, unsigned long long epoch, StepCounters* counters) {
+    const uint32_t q = threadIdx.x;
+    if (q >= world) return;
+    __threadfence_system();
+    unsigned long long* theirs = peer_flags[q] + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const unsigned long long* mine = my_flags + q;
+    const long long t0 = clock64();
+    unsigned long long seen = 0ull;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        if (seen >= epoch) break;
+        if (clock64() - t0 > 4000000000ll) { counters->barrier_timeout = 1ull; break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
+                         uint32_t rank, uint32_t world, unsigned long long epoch, StepCounters* counters) {
+    k_peer_barrier<<<1, 64, 0, stream>>>(peer_flags, my_flags, rank, world, epoch, counters);
 }
 
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
                               const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
                               size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
-                              uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step) {
+                              uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
+                              ParticleResult* const* peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
                                                          z_draws, seed, step);
     k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, cells, cells_per_grid,
-                                                                                   results, first_particle, n_local);
+                                                                                   results, first_particle, n_local,
+                                                                                   peer_results, peer_offset, rank, world);
 }
 
 // =============================================================================== k_ray_update
@@ -806,23 +850,46 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
 // =============================================================================== k_weights
 
 constexpr int W_THREADS = 1024;
+constexpr int W_CLUSTER = 8;   // CTAs of the (portable-size) thread-block cluster that shares the reduction
 
-__global__ void __launch_bounds__(W_THREADS)
+// normalize_weights (particle.rs:49-56), the argmax of particle.rs:40-46 and the running sum of
+// particle.rs:85-91 over the WHOLE population, on one thread-block cluster: 8 CTAs x 1024
+// threads, each thread folds a contiguous chunk left to right, chunk sums are combined by a fixed
+// shuffle tree inside the CTA and the 8 CTA totals are exchanged through distributed shared
+// memory. The combination order depends only on N: bit-identical on every GPU and every run.
+__global__ void __cluster_dims__(W_CLUSTER, 1, 1) __launch_bounds__(W_THREADS)
 k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __restrict__ w_norm,
           double* __restrict__ cum, StepCounters* counters) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t crank = cluster.block_rank();
     __shared__ double s_warp[33];
+    __shared__ double s_tot[2][W_CLUSTER];          // CTA totals of the two passes, filled by every CTA
     __shared__ long long s_key[32];
     __shared__ uint32_t s_arg[32];
-    const uint32_t chunk = (n + W_THREADS - 1) / W_THREADS;
-    const uint32_t lo = min(n, threadIdx.x * chunk), hi = min(n, lo + chunk);
+    __shared__ long long s_ckey[W_CLUSTER];         // per-CTA argmax candidates (read by CTA 0)
+    __shared__ uint32_t s_carg[W_CLUSTER];
+    cluster.sync();   // every CTA of the cluster is running before its shared memory is written remotely
+    const uint32_t gt = crank * W_THREADS + threadIdx.x;
+    const uint32_t chunk = (n + W_CLUSTER * W_THREADS - 1) / (W_CLUSTER * W_THREADS);
+    const uint32_t lo = min(n, gt * chunk), hi = min(n, lo + chunk);
 
-    // normalize_weights, particle.rs:49-56: sum, then divide. Each thread folds a contiguous
-    // chunk left to right, chunk sums are combined by a fixed shuffle tree.
+    if (gt == 0) {   // per-step counters start from zero
+        counters->clamped = 0ull; counters->saturated = 0ull; counters->spilled = 0ull;
+        counters->n_alive = 0ull; counters->copy_bytes = 0ull; counters->copy_max_rows = 0ull;
+    }
+
+    // pass 1: sum of the raw weights
     double part = 0.0;
     for (uint32_t i = lo; i < hi; ++i) part = __dadd_rn(part, results[i].weight);
-    double sum;
-    block_excl_scan_f64(part, s_warp, &sum);
+    double cta_sum;
+    block_excl_scan_f64(part, s_warp, &cta_sum);
+    if (threadIdx.x < W_CLUSTER) cluster.map_shared_rank(&s_tot[0][0], threadIdx.x)[crank] = cta_sum;
+    cluster.sync();
+    double sum = 0.0;
+#pragma unroll
+    for (int r = 0; r < W_CLUSTER; ++r) sum = __dadd_rn(sum, s_tot[0][r]);
 
+    // pass 2: normalise, argmax candidate, chunk sums of the normalised weights
     double npart = 0.0;
     long long best_key = (long long)0x8000000000000000ull;
     uint32_t best_i = 0;
@@ -834,14 +901,9 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         const long long k = total_order_key(w);
         if (!have || k >= best_key) { best_key = k; best_i = i; have = true; }  // last max wins
     }
-    // running sum of the normalised weights (the `c += weight[i]` of particle.rs:85-91)
-    double ntotal;
-    const double offset = block_excl_scan_f64(npart, s_warp, &ntotal);
-    double c = offset;
-    for (uint32_t i = lo; i < hi; ++i) {
-        c = __dadd_rn(c, w_norm[i]);
-        cum[i] = c;
-    }
+    double cta_n;
+    const double offset = block_excl_scan_f64(npart, s_warp, &cta_n);
+    if (threadIdx.x < W_CLUSTER) cluster.map_shared_rank(&s_tot[1][0], threadIdx.x)[crank] = cta_n;
 
     // argmax by f64::total_cmp, ties -> highest index (Iterator::max_by returns the last maximum)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -856,20 +918,38 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
     if (lane == 0) { s_key[wid] = have ? best_key : (long long)0x8000000000000000ull; s_arg[wid] = have ? best_i : 0xffffffffu; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        long long bk = 0; uint32_t bi = 0; bool h = false;
+        long long bk = 0; uint32_t bi = 0xffffffffu; bool h = false;
         for (int w = 0; w < W_THREADS / 32; ++w) {
             if (s_arg[w] == 0xffffffffu) continue;
             if (!h || s_key[w] > bk || (s_key[w] == bk && s_arg[w] > bi)) { bk = s_key[w]; bi = s_arg[w]; h = true; }
         }
+        cluster.map_shared_rank(&s_ckey[0], 0)[crank] = bk;
+        cluster.map_shared_rank(&s_carg[0], 0)[crank] = bi;
+    }
+    cluster.sync();
+
+    // running sum of the normalised weights (the `c += weight[i]` of particle.rs:85-91)
+    double cta_off = 0.0;
+    for (uint32_t r = 0; r < crank; ++r) cta_off = __dadd_rn(cta_off, s_tot[1][r]);
+    double c = __dadd_rn(cta_off, offset);
+    for (uint32_t i = lo; i < hi; ++i) {
+        c = __dadd_rn(c, w_norm[i]);
+        cum[i] = c;
+    }
+    if (gt == 0) {
+        long long bk = 0; uint32_t bi = 0; bool h = false;
+        for (int r = 0; r < W_CLUSTER; ++r) {
+            if (s_carg[r] == 0xffffffffu) continue;
+            if (!h || s_ckey[r] > bk || (s_ckey[r] == bk && s_carg[r] > bi)) { bk = s_ckey[r]; bi = s_carg[r]; h = true; }
+        }
         counters->max_particle = bi;
         counters->sum = sum;
-        counters->clamped = 0ull;
     }
 }
 
 void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
                     double* cum, StepCounters* counters) {
-    k_weights<<<1, W_THREADS, 0, stream>>>(results, n_total, w_norm, cum, counters);
+    k_weights<<<W_CLUSTER, W_THREADS, 0, stream>>>(results, n_total, w_norm, cum, counters);
 }
 
 // =============================================================================== k_resample_indices
@@ -959,13 +1039,17 @@ void launch_mark_alive(cudaStream_t stream, const uint32_t* idx, uint32_t n_tota
 
 // =============================================================================== k_plan
 // Turns the (non-decreasing) index vector into work for this rank's output range [lo, lo+S):
-//   A  source is local and this is its first use here   -> the grid stays where it is
-//   B  source is local, further use                     -> copy from the kept grid into a free slot
-//   C  source lives on another GPU, first use here      -> pull it over NVLink into a free slot
-//   D  source lives on another GPU, further use         -> copy from the pulled grid
-// Free slots = slots of local particles nobody here keeps + the persistent spare slots. Slots whose
-// grid another GPU still has to pull ("unsafe") are handed out last and only to B/D copies, which
-// run after the cross-GPU barrier that follows the pulls.
+//   0  source is local and this is its first use here   -> the grid stays where it is
+//   1  source is local, further use                     -> copy from the kept grid into a free slot
+//   2  source lives on another GPU, first use here      -> copy over NVLink into a free slot
+//   3  source lives on another GPU, further use         -> likewise (every 16th use re-reads the source)
+// All copies form ONE list in output order; copies of one source are adjacent, and every
+// COPY_FAN-th of them is a "leader": the copy kernel reads the source once per leader and stores it
+// to the whole sub-run. Free slots = slots of local particles nobody here keeps + the persistent
+// spare slots. A dropped slot whose grid another GPU copies from in this step ("unsafe") is not
+// handed out now -- it joins the spare list of the next step -- so no rank ever writes a grid
+// that a peer may still be reading, and one cross-GPU barrier per resampling is enough. That needs
+// n_unsafe <= n_spare; otherwise the step reports SLAMRS_E_STAGING (raise spare_slots).
 
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t lo, uint32_t hi, uint32_t v) {
     while (lo < hi) {
@@ -1017,7 +1101,7 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     __syncthreads();
 
     // ---- classify new particles
-    uint32_t nA = 0;
+    uint32_t nA = 0, nR = 0;
     for (uint32_t m = t; m < S; m += T) {
         const uint32_t src = idx_l[m];
         const bool first = (m == 0) || (idx_l[m - 1] != src);
@@ -1032,10 +1116,11 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
         else cls = 3;
         need[m] = (uint8_t)cls;
         nA += (first ? 1u : 0u);
+        nR += (cls == 2 ? 1u : 0u);
     }
     __syncthreads();
 
-    // ---- classify old slots: 0 = kept, 1 = free & safe, 2 = free but still read by another GPU.
+    // ---- classify old slots: 0 = kept, 1 = free & safe, 2 = free but read by another GPU this step.
     // A slot that is not kept has no local consumer; idx is non-decreasing, so its consumers (if
     // any) are all before this rank's range (v < idx[lo]) or all after it (v > idx[hi-1]).
     const uint32_t idx_first = idx_l[0], idx_last = idx_l[S - 1];
@@ -1069,107 +1154,87 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
         else if (keep[j] == 2) free_list[n_safe + E + pu++] = slot_old[j];
     }
     for (uint32_t e = t; e < E; e += T) free_list[n_safe + e] = a.spare_list[e];
+    const uint32_t usable = n_safe + E;   // slots that may be written in this step
 
-    // ---- ordered ranks of the consumers: pulls (C) first, then copies (B, D)
-    uint32_t nC_c = 0, nBD_c = 0;
-    for (uint32_t m = c0; m < c1; ++m) { nC_c += (need[m] == 2); nBD_c += (need[m] == 1 || need[m] == 3); }
-    uint32_t nC, nBD;
-    uint32_t pc = block_excl_scan_u32(nC_c, s_warp, &nC);
-    uint32_t pbd = block_excl_scan_u32(nBD_c, s_warp, &nBD);
+    // ---- ordered ranks of the consumers (every new particle that does not keep a grid in place)
+    uint32_t n_cons_c = 0;
+    for (uint32_t m = c0; m < c1; ++m) n_cons_c += (need[m] != 0);
+    uint32_t n_cons;
+    uint32_t pos = block_excl_scan_u32(n_cons_c, s_warp, &n_cons);
     __syncthreads();  // free_list complete
 
-    // pass 1: pulls and local duplicates (their sources are already in place).
-    // Copies of one source are adjacent in the list; every COPY_FAN-th of them is a "leader":
-    // the copy kernel reads the source once per leader and stores it to the whole sub-run.
-    const uint32_t pbd_start = pbd;
+    // ---- the copy list. run_first = first position of the current source's run in this range.
+    const uint32_t pos_start = pos;
     uint32_t n_lead_c = 0;
+    uint32_t run_first = c0 < c1 ? lower_bound_u32(idx_l, 0, S, idx_l[c0]) : 0u;
     for (uint32_t m = c0; m < c1; ++m) {
         const int cls = need[m];
-        if (cls == 2) {
-            const uint32_t src = idx_l[m];
-            const uint32_t owner = src / S;
-            const int32_t sslot = a.results[src].slot;
-            const int32_t dslot = free_list[pc];
+        const uint32_t src = idx_l[m];
+        if (m > c0 && idx_l[m - 1] != src) run_first = m;
+        if (cls == 0) continue;
+        if (pos < usable) {
+            const int32_t dslot = free_list[pos];
             slot_new[m] = dslot;
             CopyItem it;
-            it.src = a.peer_cells[owner] + (size_t)sslot * a.cells_per_grid;
+            if (cls == 1) {
+                const int32_t sslot = slot_old[src - lo];
+                it.src = a.cells + (size_t)sslot * a.cells_per_grid;
+                it.src_meta = a.meta + sslot;
+            } else {
+                const uint32_t owner = src / S;
+                const int32_t sslot = a.results[src].slot;
+                it.src = a.peer_cells[owner] + (size_t)sslot * a.cells_per_grid;
+                it.src_meta = a.peer_meta[owner] + sslot;
+            }
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
-            it.src_meta = a.peer_meta[owner] + sslot;
             it.dst_meta = a.meta + dslot;
-            a.pulls[pc] = it;
-            pc++;
-        } else if (cls == 1) {
-            const uint32_t src = idx_l[m];
-            const int32_t dslot = free_list[nC + pbd];
-            slot_new[m] = dslot;
-            CopyItem it;
-            it.src = a.cells + (size_t)slot_old[src - lo] * a.cells_per_grid;
-            it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
-            it.src_meta = a.meta + slot_old[src - lo];
-            it.dst_meta = a.meta + dslot;
-            a.copies[pbd] = it;
-            const uint32_t m_first = lower_bound_u32(idx_l, 0, S, src);
-            const bool lead = ((m - m_first - 1u) % COPY_FAN) == 0u;
-            need[m] = lead ? 5 : 1;   // remember leadership for the compaction below
+            a.copies[pos] = it;
+            // a local run keeps its first use in place, so its copies start one position later
+            const uint32_t k = (cls == 1) ? (m - run_first - 1u) : (m - run_first);
+            const bool lead = (k % COPY_FAN) == 0u;
+            need[m] = (uint8_t)(lead ? 9 : 8);
             n_lead_c += lead;
-            pbd++;
-        } else if (cls == 3) {
-            pbd++;
+        } else {
+            // no writable slot left (SLAMRS_E_STAGING): nothing is copied, the filter state is invalid
+            slot_new[m] = (cls == 1) ? slot_old[src - lo] : slot_old[0];
+            need[m] = 10;
         }
-    }
-    __syncthreads();
-    // pass 2: duplicates of pulled grids (source = where the first use landed)
-    pbd = pbd_start;
-    for (uint32_t m = c0; m < c1; ++m) {
-        const int cls = need[m];
-        if (cls == 3) {
-            const uint32_t src = idx_l[m];
-            const uint32_t m_first = lower_bound_u32(idx_l, 0, S, src);
-            const int32_t dslot = free_list[nC + pbd];
-            slot_new[m] = dslot;
-            CopyItem it;
-            it.src = a.cells + (size_t)slot_new[m_first] * a.cells_per_grid;
-            it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
-            it.src_meta = a.meta + slot_new[m_first];
-            it.dst_meta = a.meta + dslot;
-            a.copies[pbd] = it;
-            const bool lead = ((m - m_first - 1u) % COPY_FAN) == 0u;
-            need[m] = lead ? 7 : 3;
-            n_lead_c += lead;
-            pbd++;
-        } else if (cls == 1 || cls == 5) {
-            pbd++;
-        }
+        pos++;
     }
     // ordered list of leader positions within copies[]
     uint32_t n_lead;
     uint32_t pl = block_excl_scan_u32(n_lead_c, s_warp, &n_lead);
-    pbd = pbd_start;
+    pos = pos_start;
     for (uint32_t m = c0; m < c1; ++m) {
         const int cls = need[m];
-        if (cls == 5 || cls == 7) a.leaders[pl++] = pbd;
-        if (cls == 1 || cls == 3 || cls == 5 || cls == 7) pbd++;
+        if (cls == 9) a.leaders[pl++] = pos;
+        if (cls >= 8) pos++;
     }
     __syncthreads();
-    // ---- the E slots nobody took become the next step's spare list
-    for (uint32_t e = t; e < E; e += T) a.spare_list[e] = free_list[nC + nBD + e];
+    // ---- next step's spare list: the usable slots nobody took, then this step's unsafe slots
+    const uint32_t used = min(n_cons, usable);
+    for (uint32_t e = t; e < E; e += T) {
+        const uint32_t left = usable - used;   // = E - n_unsafe when nothing is short
+        a.spare_list[e] = e < left ? free_list[used + e] : free_list[usable + (e - left)];
+    }
     if (a.staged)
         for (uint32_t m = t; m < S; m += T) a.slot_new[m] = slot_new[m];
 
-    uint32_t distinct;
+    uint32_t distinct, n_remote;
     block_excl_scan_u32(nA, s_warp, &distinct);
+    block_excl_scan_u32(nR, s_warp, &n_remote);
     if (t == 0) {
-        a.counters->n_copies = nBD;
+        a.counters->n_copies = used;
         a.counters->n_leaders = n_lead;
-        a.counters->n_pulls = nC;
+        a.counters->n_pulls = n_remote;
         a.counters->distinct = distinct;
-        a.counters->staging_short = (nC > n_safe + E) ? (unsigned long long)(nC - (n_safe + E)) : 0ull;
+        a.counters->staging_short = (n_cons > usable) ? (unsigned long long)(n_cons - usable) : 0ull;
         const unsigned long long mp = a.counters->max_particle;
         a.counters->est_owner = mp / S;
         a.counters->est_slot = (mp >= lo && mp < hi) ? (long long)slot_new[mp - lo] : -1ll;
         if (a.history) {
             StepRecord r;
-            r.step = a.step; r.n_copies = nBD; r.n_pulls = nC; r.distinct = distinct; r.n_leaders = n_lead;
+            r.step = a.step; r.n_copies = used; r.n_pulls = n_remote; r.distinct = distinct; r.n_leaders = n_lead;
             r.n_alive = 0; r.copy_bytes = 0; r.pad = 0;   // filled in by the step's last kernel (k_commit_boxes)
             a.history[a.step % STEP_HISTORY] = r;
         }

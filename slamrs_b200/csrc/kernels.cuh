@@ -18,9 +18,9 @@ static_assert(sizeof(ParticleResult) == 24, "ParticleResult is exchanged between
 // Device-resident step state shared by the resampling kernels.
 struct StepCounters {
     unsigned long long max_particle;     // argmax of the normalised weights, last max wins (particle.rs:40-46)
-    unsigned long long n_copies;         // local duplicate copies planned this step
+    unsigned long long n_copies;         // grids this rank writes in this step (local and remote sources)
     unsigned long long n_leaders;        // sub-runs of <= COPY_FAN copies sharing one source read
-    unsigned long long n_pulls;          // remote grids to pull this step
+    unsigned long long n_pulls;          // distinct remote sources this rank copies from in this step
     unsigned long long distinct;         // distinct sources feeding this rank's new generation
     unsigned long long clamped;          // resample index clamped to N-1
     unsigned long long saturated;        // cells that hit the u16 ceiling this step
@@ -32,6 +32,7 @@ struct StepCounters {
     unsigned long long n_alive;          // local particles whose grid is integrated this step
     unsigned long long copy_bytes;       // bytes read + written by the copy kernels this step
     unsigned long long copy_max_rows;    // tallest region any copy job of this step writes (rows)
+    unsigned long long barrier_timeout;  // a peer barrier gave up waiting (error)
     double sum;                          // sum of raw weights (particle.rs:50)
     float est_pose[3];                   // estimated_pose(), slam.rs:77-81
     float pad;
@@ -75,7 +76,13 @@ struct CopyItem {
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
                               const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
                               size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
-                              uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step);
+                              uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
+                              ParticleResult* const* peer_results /* null: no fused exchange */,
+                              uint32_t peer_offset /* records in front of this step's generation */, uint32_t rank,
+                              uint32_t world);
+constexpr uint32_t PEER_MAX_WORLD = 64;
+void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
+                         uint32_t rank, uint32_t world, unsigned long long epoch, StepCounters* counters);
 
 // returns the shared-memory window size in cells through *window_cells
 // alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive)
@@ -106,7 +113,6 @@ struct PlanArgs {
     uint32_t n_spare_cap;
     CopyItem* copies;          // n_local
     uint32_t* leaders;         // n_local: positions in copies[] that start a fan-out sub-run
-    CopyItem* pulls;           // n_local
     uint32_t* cells;           // local pool base
     size_t cells_per_grid;
     uint32_t* const* peer_cells;        // world pointers to each rank's pool (device array), may be null when world==1
@@ -126,7 +132,7 @@ void launch_mark_alive(cudaStream_t stream, const uint32_t* idx, uint32_t n_tota
                        uint32_t n_local, bool all_particles, uint32_t* alive_list, StepCounters* counters);
 
 // copies[0..*n_items) full grids; n_items is read on the device
-// leaders == nullptr: plain item-by-item copy (used for the NVLink pulls)
+// leaders == nullptr: plain item-by-item copy
 void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
                  const unsigned long long* n_items, const unsigned long long* n_leaders, size_t cells_per_grid,
                  int num_sms);

@@ -20,17 +20,20 @@ def _gpu_count():
     return torch.cuda.device_count()
 
 
-def _run_sharded(cfg, scans, world, spare_slots=0, collect_cells=()):
+def _run_sharded(cfg, scans, world, spare_slots=0, collect_cells=(), scatter=None, flags=0):
     nid = nccl_unique_id()
     out = [None] * world
     errs = []
 
     def worker(rank):
+        g = None
         try:
             g = GridMapSlam(cfg, GpuPlacement(device=rank, rank=rank, world_size=world, nccl_id=nid, seed=SEED,
-                                              spare_slots=spare_slots))
+                                              spare_slots=spare_slots, flags=flags))
             rec = []
-            for obs, odo in scans:
+            for step, (obs, odo) in enumerate(scans):
+                if scatter is not None and scatter[step] is not None:
+                    g.set_poses(scatter[step][g.first:g.first + g.n_local])
                 g.update(obs, odo)
                 ep = g.estimated_pose()
                 m = g.estimated_likelihood().data.copy()
@@ -39,27 +42,30 @@ def _run_sharded(cfg, scans, world, spare_slots=0, collect_cells=()):
                 rec.append(dict(poses=g.poses().copy(), idx=g.resample_indices().copy(), w=g.weights()[0].copy(),
                                 maxp=g.max_particle, est=(ep.x, ep.y, ep.theta), map=m, stats=st, cells=cells))
             out[rank] = rec
-            g.close()
         except Exception as e:  # noqa: BLE001
             errs.append((rank, repr(e)))
+        finally:
+            if g is not None:
+                g.close()
 
     ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
     [t.start() for t in ts]
-    [t.join(timeout=300) for t in ts]
+    [t.join(timeout=120) for t in ts]
     assert not errs, errs
     assert all(o is not None for o in out), "a rank hung"
     return out
 
 
+@pytest.mark.parametrize("exchange_flags", [0, 8], ids=["peer-store-exchange", "nccl-exchange"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_equals_single_gpu_and_oracle(oracle, world):
+def test_sharded_equals_single_gpu_and_oracle(oracle, world, exchange_flags):
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
     n = 64
     cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=n)
     scans = make_scans(1.0, 360, 1.0, 6)
     probe = (0, 1, n // 2 - 1, n // 2, n - 1)
-    shards = _run_sharded(cfg, scans, world, collect_cells=probe)
+    shards = _run_sharded(cfg, scans, world, collect_cells=probe, flags=exchange_flags)
     osl = oracle_slam(oracle, cfg)
     pulled = 0
     for step, (obs, odo) in enumerate(scans):
@@ -81,6 +87,40 @@ def test_sharded_equals_single_gpu_and_oracle(oracle, world):
                 assert np.array_equal(cells & 0xFFFF, nf) and np.array_equal(cells >> 16, no), (step, r, p)
             pulled += rec["stats"]["grids_pulled"]
     assert pulled > 0, "the test never exercised a cross-GPU grid migration"
+    osl.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("copy_flags", [0, 4], ids=["extent-copy", "whole-grid-copy"])
+def test_sharded_mixed_extents_all_grids(oracle, world, copy_flags):
+    """Particles re-scattered over the room every other scan: the grids that migrate between GPUs
+    and the slots they land in have very different informed extents. Every particle's grid on every
+    rank must equal the oracle's, bit for bit."""
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n = 48
+    cfg = GridMapSlamConfig(position=(-6.4, -6.4), width=12.8, height=12.8, resolution=0.05, n_particles=n)
+    scans = make_scans(5.0, 360, 3.0, 6)
+    rng = np.random.default_rng(11)
+    scatter = [np.column_stack([rng.uniform(-4.5, 4.5, n), rng.uniform(-4.5, 4.5, n),
+                                rng.uniform(-np.pi, np.pi, n)]).astype(np.float32) if s % 2 == 0 else None
+               for s in range(len(scans))]
+    shards = _run_sharded(cfg, scans, world, collect_cells=tuple(range(n)), scatter=scatter, flags=copy_flags)
+    osl = oracle_slam(oracle, cfg)
+    pulled = 0
+    for step, (obs, odo) in enumerate(scans):
+        if scatter[step] is not None:
+            osl.set_poses(scatter[step])
+        rc, _, _ = oracle_step(oracle, osl, obs, odo, step)
+        assert rc == 0
+        for r in range(world):
+            rec = shards[r][step]
+            assert np.array_equal(rec["idx"], osl.indices().astype(np.uint32))
+            for p, cells in rec["cells"].items():
+                nf, no = osl.counts(p)
+                assert np.array_equal(cells & 0xFFFF, nf) and np.array_equal(cells >> 16, no), (step, r, p)
+            pulled += rec["stats"]["grids_pulled"]
+    assert pulled > 0
     osl.close()
 
 
