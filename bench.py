@@ -298,6 +298,10 @@ def run_cuda(args, wl, rank, world, local):
     main = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans, args.flags, not args.no_e2e)
     clock_info = clocks.stop()
     full = None
+    # the two comparison modes are single-GPU diagnostics; the scaling runs time the product path only
+    if world > 1:
+        args.no_full_copy = True
+        args.no_strict = True
     if not args.no_full_copy:
         full = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans, _lib.FLAG_FULL_GRID_COPY, False)
     strict = None

@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -41,6 +42,7 @@ struct slamrs_gpu_handle {
     ParticleResult** d_peer_results = nullptr;   // device array [world]
     unsigned long long** d_peer_flags = nullptr; // device array [world]
     unsigned long long barrier_epoch = 0;
+    unsigned long long barrier_timeout_ns = 60000000000ull;   // SLAMRS_BARRIER_TIMEOUT_MS overrides
     bool p2p_exchange = false;   // fused peer stores + flag barriers instead of NCCL collectives
     SlotMeta* d_meta = nullptr;  // = d_pool
     uint32_t* d_cells = nullptr; // = d_pool + pool_header
@@ -215,7 +217,9 @@ void free_all(slamrs_gpu_handle* h) {
         // nobody may still be copying from this pool when it is freed. The peer-flag barrier gives up
         // after about two seconds, so a rank whose peer died does not hang in destroy.
         if (h->p2p_exchange && h->d_peer_flags) {
-            launch_peer_barrier(h->stream, h->d_peer_flags, h->d_flags, h->rank, h->world, ++h->barrier_epoch, h->d_counters);
+            // short wait at destroy: a peer that already failed must not hold this rank for a minute
+            launch_peer_barrier(h->stream, h->d_peer_flags, h->d_flags, h->rank, h->world, ++h->barrier_epoch,
+                                5000000000ull, h->d_counters);
             cudaStreamSynchronize(h->stream);
         } else {
             std::string err;
@@ -288,7 +292,8 @@ int prof_flush(slamrs_gpu_handle* h) {
 // stream-ordered barrier across ranks inside a step: peer flags by default, NCCL on request
 int step_barrier(slamrs_gpu_handle* h) {
     if (h->p2p_exchange) {
-        launch_peer_barrier(h->stream, h->d_peer_flags, h->d_flags, h->rank, h->world, ++h->barrier_epoch, h->d_counters);
+        launch_peer_barrier(h->stream, h->d_peer_flags, h->d_flags, h->rank, h->world, ++h->barrier_epoch,
+                            h->barrier_timeout_ns, h->d_counters);
         h->launches++;
         return SLAMRS_OK;
     }
@@ -494,6 +499,16 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
             return SLAMRS_E_NCCL;
         }
         CREATE_TRY(setup_peers(h));
+        if (const char* ev = getenv("SLAMRS_BARRIER_TIMEOUT_MS")) {
+            const long long ms = atoll(ev);
+            if (ms > 0) h->barrier_timeout_ns = (unsigned long long)ms * 1000000ull;
+        }
+        // leave create together: mapping the peers' pools takes a rank-dependent time
+        if (comm_barrier(h->comm, h->d_barrier, h->stream, &err)) {
+            g_create_error = err;
+            free_all(h);
+            return SLAMRS_E_NCCL;
+        }
     }
     CREATE_CU(cudaStreamSynchronize(h->stream));
     h->h_counters->est_slot = h->rank == 0 ? 0 : -1;

@@ -200,30 +200,36 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
 // this rank's epoch into GPU q's flag array (release, system scope: every write this GPU issued
 // before, including the peer stores of earlier kernels in the stream, is visible first) and then
 // waits until GPU q's epoch has arrived here (acquire). Epochs only grow, so flags are never reset.
-// A bounded wait (about two seconds) turns a lost peer into an error instead of a hung GPU.
+// A bounded wait (timeout_ns, one minute by default: ranks are driven by independent host threads
+// that may lag) turns a lost peer into an error instead of a hung GPU.
 __global__ void __launch_bounds__(64)
 k_peer_barrier(unsigned long long* const* __restrict__ peer_flags, unsigned long long* my_flags, uint32_t rank,
-               uint32_t world, unsigned long long epoch, StepCounters* counters) {
+               uint32_t world, unsigned long long epoch, unsigned long long timeout_ns, StepCounters* counters) {
     const uint32_t q = threadIdx.x;
     if (q >= world) return;
     __threadfence_system();
     unsigned long long* theirs = peer_flags[q] + rank;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    // once a barrier has given up the handle is poisoned (the error is reported at the next sync):
+    // later barriers publish their epoch, so that healthy peers keep going, but do not wait again
+    if (*reinterpret_cast<volatile unsigned long long*>(&counters->barrier_timeout) != 0ull) return;
     const unsigned long long* mine = my_flags + q;
-    const long long t0 = clock64();
-    unsigned long long seen = 0ull;
+    unsigned long long t0, now, seen = 0ull;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
         if (seen >= epoch) break;
-        if (clock64() - t0 > 4000000000ll) { counters->barrier_timeout = 1ull; break; }
-        __nanosleep(100);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) { counters->barrier_timeout = 1ull; break; }
+        __nanosleep(200);
     }
     __threadfence_system();
 }
 
 void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
-                         uint32_t rank, uint32_t world, unsigned long long epoch, StepCounters* counters) {
-    k_peer_barrier<<<1, 64, 0, stream>>>(peer_flags, my_flags, rank, world, epoch, counters);
+                         uint32_t rank, uint32_t world, unsigned long long epoch, unsigned long long timeout_ns,
+                         StepCounters* counters) {
+    k_peer_barrier<<<1, 64, 0, stream>>>(peer_flags, my_flags, rank, world, epoch, timeout_ns, counters);
 }
 
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,

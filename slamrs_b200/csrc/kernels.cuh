@@ -82,7 +82,8 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               uint32_t world);
 constexpr uint32_t PEER_MAX_WORLD = 64;
 void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
-                         uint32_t rank, uint32_t world, unsigned long long epoch, StepCounters* counters);
+                         uint32_t rank, uint32_t world, unsigned long long epoch, unsigned long long timeout_ns,
+                         StepCounters* counters);
 
 // returns the shared-memory window size in cells through *window_cells
 // alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive)

@@ -8,6 +8,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# failure-path tests let one rank of a multi-GPU filter die: its peers give up after 3 s, not 60
+os.environ.setdefault("SLAMRS_BARRIER_TIMEOUT_MS", "3000")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
