@@ -162,6 +162,35 @@ int slamrs_gpu_pose(slamrs_gpu_handle* h, float out_xyt[3]);
  * broadcasts); every rank receives the map. */
 int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells);
 
+/* Cheaper forms of the same read-out for consumers that do not need 8 bytes per cell of the whole
+ * grid (the visualizer converts every cell to an f32 grey level,
+ * baseui/src/node/visualize.rs:245-256). map_extent returns the informed extent [x0,x1) x [y0,y1)
+ * of the estimate's grid in cells (x0, x1 multiples of 8; all zeros while the map is empty): every
+ * cell outside it is exactly at the prior, 0.5. map_window exports the window [x0,x1) x [y0,y1),
+ * row-major, as f64, f32 or u8 = round(255 p). Collective when world_size>1. */
+enum slamrs_map_format { SLAMRS_MAP_F64 = 0, SLAMRS_MAP_F32 = 1, SLAMRS_MAP_U8 = 2 };
+int slamrs_gpu_map_extent(slamrs_gpu_handle* h, int32_t out_x0y0x1y1[4]);
+int slamrs_gpu_map_window(slamrs_gpu_handle* h, uint32_t format, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
+                          void* out);
+
+/* ParticleFilter::number_of_effective_particles, particle.rs:59-65, evaluated on the normalised
+ * weights of the last update BEFORE resampling (the reference never calls it; after resampling it
+ * is trivially N). N before the first update. */
+int slamrs_gpu_effective_particles(slamrs_gpu_handle* h, double* out);
+
+/* ------------------------------------------------------------------ scan production on the device */
+
+/* The simulator's lidar (slamrs/simulator/src/sim.rs:134-159, scene/ray.rs:55-83) evaluated on the
+ * device, straight into the handle's scan buffers: n_beams rays at 360/n_beams degree steps from
+ * pose {x, y, theta} against n_segments line segments {x1, y1, x2, y2}; rays that hit nothing are
+ * dropped, hits beyond scanner_range become invalid measurements at scanner_range. The next
+ * step_async consumes it; *out_n (optional) receives the number of measurements. */
+int slamrs_gpu_sim_scan(slamrs_gpu_handle* h, const float* segments_xyxy, uint32_t n_segments, const float pose_xyt[3],
+                        uint32_t n_beams, float scanner_range, uint32_t* out_n);
+/* Copy the device-resident observation back (at most cap measurements; *out_n = how many exist). */
+int slamrs_gpu_get_scan(slamrs_gpu_handle* h, float* out_angle, float* out_dist, uint8_t* out_valid, uint32_t cap,
+                        uint32_t* out_n);
+
 /* ------------------------------------------------------------------ introspection (tests, bench) */
 
 const char* slamrs_gpu_last_error(const slamrs_gpu_handle* h); /* never NULL; "" when none */

@@ -62,6 +62,7 @@ def lib():
     L.so_set_poses.restype = None; L.so_set_poses.argtypes = [vp, vp]
     L.so_get_weights.restype = None; L.so_get_weights.argtypes = [vp, vp, vp]
     L.so_get_indices.restype = None; L.so_get_indices.argtypes = [vp, vp]
+    L.so_number_of_effective_particles.restype = C.c_double; L.so_number_of_effective_particles.argtypes = [vp]
     L.so_get_odds.restype = None; L.so_get_odds.argtypes = [vp, u64, vp]
     L.so_get_counts.restype = C.c_int; L.so_get_counts.argtypes = [vp, u64, vp, vp]
     L.so_estimated_pose.restype = _Pose; L.so_estimated_pose.argtypes = [vp]
@@ -208,6 +209,9 @@ class OracleSlam:
     def weights(self):
         w = np.zeros(self.n, np.float64); r = np.zeros(self.n, np.float64)
         lib().so_get_weights(self._h, _p(w), _p(r)); return w, r
+
+    def number_of_effective_particles(self):
+        return float(lib().so_number_of_effective_particles(self._h))
 
     def indices(self):
         i = np.zeros(self.n, np.uint64); lib().so_get_indices(self._h, _p(i)); return i

@@ -499,6 +499,13 @@ void so_get_weights(const struct so_slam* s, double* norm, double* raw) {
     if (norm) memcpy(norm, s->weight, s->n * sizeof(double));
     if (raw) memcpy(raw, s->raw_weight, s->n * sizeof(double));
 }
+/* ParticleFilter::number_of_effective_particles, slamrs/slam/src/grid/particle.rs:59-65, over the
+ * normalised weights of the last update (before resampling resets them to 1/N) */
+double so_number_of_effective_particles(const struct so_slam* s) {
+    double sum = 0.0;
+    for (uint64_t i = 0; i < s->n; ++i) sum += s->weight[i] * s->weight[i];
+    return 1.0 / sum;
+}
 void so_get_indices(const struct so_slam* s, uint64_t* idx) { memcpy(idx, s->last_idx, s->n * sizeof(uint64_t)); }
 void so_get_odds(const struct so_slam* s, uint64_t particle, double* out) {
     memcpy(out, s->map[particle].odds, (size_t)(s->gw * s->gh) * sizeof(double));

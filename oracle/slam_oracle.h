@@ -38,6 +38,7 @@ uint64_t so_max_particle(const struct so_slam* s);
 void so_get_poses(const struct so_slam* s, float* out_xyt);
 void so_set_poses(struct so_slam* s, const float* xyt);
 void so_get_weights(const struct so_slam* s, double* norm, double* raw);
+double so_number_of_effective_particles(const struct so_slam* s);
 void so_get_indices(const struct so_slam* s, uint64_t* idx);
 void so_get_odds(const struct so_slam* s, uint64_t particle, double* out);
 int so_get_counts(const struct so_slam* s, uint64_t particle, uint16_t* n_free, uint16_t* n_occ);

@@ -28,8 +28,10 @@ EXPORTS = [
     "slamrs_gpu_get_cells", "slamrs_gpu_set_cells", "slamrs_gpu_get_log_odds",
     "slamrs_gpu_debug_raycast", "slamrs_gpu_debug_sincos", "slamrs_gpu_debug_stream",
     "slamrs_gpu_set_scan_device", "slamrs_gpu_set_profiling", "slamrs_gpu_get_phase_ms",
-    "slamrs_gpu_get_step_history",
+    "slamrs_gpu_get_step_history", "slamrs_gpu_map_extent", "slamrs_gpu_map_window",
+    "slamrs_gpu_effective_particles", "slamrs_gpu_sim_scan", "slamrs_gpu_get_scan",
 ]
+MAP_F64, MAP_F32, MAP_U8 = 0, 1, 2
 PHASES = ["motion_likelihood", "all_gather", "resample", "ray_update", "plan", "pull", "copy"]
 
 
@@ -105,6 +107,13 @@ def load():
     L.slamrs_gpu_set_profiling.restype = i; L.slamrs_gpu_set_profiling.argtypes = [vp, i]
     L.slamrs_gpu_get_phase_ms.restype = i; L.slamrs_gpu_get_phase_ms.argtypes = [vp, vp, C.POINTER(u64)]
     L.slamrs_gpu_get_step_history.restype = i; L.slamrs_gpu_get_step_history.argtypes = [vp, u64, u32, vp]
+    L.slamrs_gpu_map_extent.restype = i; L.slamrs_gpu_map_extent.argtypes = [vp, vp]
+    L.slamrs_gpu_map_window.restype = i
+    L.slamrs_gpu_map_window.argtypes = [vp, u32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.slamrs_gpu_effective_particles.restype = i
+    L.slamrs_gpu_effective_particles.argtypes = [vp, C.POINTER(C.c_double)]
+    L.slamrs_gpu_sim_scan.restype = i; L.slamrs_gpu_sim_scan.argtypes = [vp, vp, u32, vp, u32, f, C.POINTER(u32)]
+    L.slamrs_gpu_get_scan.restype = i; L.slamrs_gpu_get_scan.argtypes = [vp, vp, vp, vp, u32, C.POINTER(u32)]
     _lib = L
     return L
 

@@ -710,22 +710,116 @@ int slamrs_gpu_pose(slamrs_gpu_handle* h, float out_xyt[3]) {
     return SLAMRS_OK;
 }
 
-int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells) {
-    if (!h || !out_cells) return SLAMRS_E_INVALID_ARG;
-    DeviceGuard g(h->device);
+namespace {
+// exports [x0,x1) x [y0,y1) of the estimate's grid in `format` into the caller's host buffer
+int export_window(slamrs_gpu_handle* h, uint32_t format, int x0, int y0, int x1, int y1, void* out) {
+    if (format > SLAMRS_MAP_U8) return fail(h, SLAMRS_E_INVALID_ARG, "unknown map format");
+    if (x0 < 0 || y0 < 0 || x1 > (int)h->geom.gw || y1 > (int)h->geom.gh || x1 < x0 || y1 < y0)
+        return fail(h, SLAMRS_E_INVALID_ARG, "map window outside the grid");
+    const size_t n = (size_t)(x1 - x0) * (size_t)(y1 - y0);
+    if (n == 0) return SLAMRS_OK;
+    const size_t bytes = n * (format == SLAMRS_MAP_F64 ? 8u : (format == SLAMRS_MAP_F32 ? 4u : 1u));
     cudaStream_t s = h->stream;
-    launch_export(s, h->d_cells, h->cells_per_grid, h->d_counters, h->n_cells, h->d_export);
+    launch_export(s, h->d_cells, h->cells_per_grid, h->d_counters, h->geom.gw, x0, y0, x1, y1, (int)format, h->d_export);
     h->launches++;
     if (h->world > 1) {
         int rc = fetch_counters(h);  // root = owner of the estimate, identical on every rank
         if (rc) return rc;
         std::string err;
-        if (comm_broadcast(h->comm, h->d_export, sizeof(double) * h->n_cells, (int)h->h_counters->est_owner, s, &err))
+        if (comm_broadcast(h->comm, h->d_export, bytes, (int)h->h_counters->est_owner, s, &err))
             return fail(h, SLAMRS_E_NCCL, err);
     }
-    CU_TRY(h, cudaMemcpyAsync(out_cells, h->d_export, sizeof(double) * h->n_cells, cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaMemcpyAsync(out, h->d_export, bytes, cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaStreamSynchronize(s));
     CU_TRY(h, cudaGetLastError());
+    return SLAMRS_OK;
+}
+}  // namespace
+
+int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells) {
+    if (!h || !out_cells) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    return export_window(h, SLAMRS_MAP_F64, 0, 0, (int)h->geom.gw, (int)h->geom.gh, out_cells);
+}
+
+int slamrs_gpu_map_extent(slamrs_gpu_handle* h, int32_t out_x0y0x1y1[4]) {
+    if (!h || !out_x0y0x1y1) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    cudaStream_t s = h->stream;
+    int* d4 = reinterpret_cast<int*>(h->d_export);
+    launch_estimate_extent(s, h->d_meta, h->d_counters, d4);
+    h->launches++;
+    if (h->world > 1) {
+        int rc = fetch_counters(h);
+        if (rc) return rc;
+        std::string err;
+        if (comm_broadcast(h->comm, d4, 4 * sizeof(int), (int)h->h_counters->est_owner, s, &err))
+            return fail(h, SLAMRS_E_NCCL, err);
+    }
+    CU_TRY(h, cudaMemcpyAsync(out_x0y0x1y1, d4, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_map_window(slamrs_gpu_handle* h, uint32_t format, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
+                          void* out) {
+    if (!h || !out) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    return export_window(h, format, x0, y0, x1, y1, out);
+}
+
+int slamrs_gpu_effective_particles(slamrs_gpu_handle* h, double* out) {
+    if (!h || !out) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int rc = fetch_counters(h);
+    if (rc) return rc;
+    *out = h->step == 0 ? (double)h->n_total : h->h_counters->n_eff;   // uniform weights before the first update
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_sim_scan(slamrs_gpu_handle* h, const float* segments_xyxy, uint32_t n_segments, const float pose_xyt[3],
+                        uint32_t n_beams, float scanner_range, uint32_t* out_n) {
+    if (!h || !pose_xyt || (n_segments && !segments_xyxy)) return SLAMRS_E_INVALID_ARG;
+    if (n_beams > 65535u) return fail(h, SLAMRS_E_INVALID_ARG, "at most 65535 beams per scan");
+    DeviceGuard g(h->device);
+    int rc = ensure_beam_capacity(h, n_beams ? n_beams : 1);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    float* d_seg = reinterpret_cast<float*>(h->d_export);              // scratch: 16 bytes per segment
+    if ((size_t)n_segments * 16u + 16u > sizeof(double) * (size_t)h->n_cells)
+        return fail(h, SLAMRS_E_INVALID_ARG, "too many scene segments for the scratch buffer");
+    uint32_t* d_cnt = reinterpret_cast<uint32_t*>(d_seg + 4 * (size_t)n_segments);
+    if (n_segments)
+        CU_TRY(h, cudaMemcpyAsync(d_seg, segments_xyxy, 16 * (size_t)n_segments, cudaMemcpyHostToDevice, s));
+    CU_TRY(h, cudaMemsetAsync(d_cnt, 0, 2 * sizeof(uint32_t), s));
+    launch_sim_scan(s, d_seg, n_segments, pose_xyt[0], pose_xyt[1], pose_xyt[2], n_beams, scanner_range, h->d_angle,
+                    h->d_dist, h->d_valid, d_cnt);
+    h->launches++;
+    uint32_t res[2] = {0, 0};
+    CU_TRY(h, cudaMemcpyAsync(res, d_cnt, sizeof(res), cudaMemcpyDeviceToHost, s));
+    CU_TRY(h, cudaStreamSynchronize(s));
+    CU_TRY(h, cudaGetLastError());
+    h->n_beams = res[0];
+    h->scan_external = false;
+    float maxd;
+    memcpy(&maxd, &res[1], 4);
+    const float cells = ceilf(maxd / h->geom.res);
+    h->radius_cells = ((cells == cells && cells < 4096.0f) ? (int)cells : 4096) + 6;
+    if (out_n) *out_n = res[0];
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_get_scan(slamrs_gpu_handle* h, float* out_angle, float* out_dist, uint8_t* out_valid, uint32_t cap,
+                        uint32_t* out_n) {
+    if (!h || !out_n) return SLAMRS_E_INVALID_ARG;
+    if (h->scan_external) return fail(h, SLAMRS_E_INVALID_ARG, "the current scan lives in caller-owned device memory");
+    DeviceGuard g(h->device);
+    *out_n = h->n_beams;
+    const uint32_t n = h->n_beams < cap ? h->n_beams : cap;
+    if (n && out_angle) CU_TRY(h, cudaMemcpyAsync(out_angle, h->d_angle, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (n && out_dist) CU_TRY(h, cudaMemcpyAsync(out_dist, h->d_dist, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (n && out_valid) CU_TRY(h, cudaMemcpyAsync(out_valid, h->d_valid, n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
     return SLAMRS_OK;
 }
 

@@ -869,7 +869,7 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t crank = cluster.block_rank();
     __shared__ double s_warp[33];
-    __shared__ double s_tot[2][W_CLUSTER];          // CTA totals of the two passes, filled by every CTA
+    __shared__ double s_tot[3][W_CLUSTER];          // CTA totals (raw, normalised, squared), filled by the peers
     __shared__ long long s_key[32];
     __shared__ uint32_t s_arg[32];
     __shared__ long long s_ckey[W_CLUSTER];         // per-CTA argmax candidates (read by CTA 0)
@@ -896,7 +896,7 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
     for (int r = 0; r < W_CLUSTER; ++r) sum = __dadd_rn(sum, s_tot[0][r]);
 
     // pass 2: normalise, argmax candidate, chunk sums of the normalised weights
-    double npart = 0.0;
+    double npart = 0.0, sqpart = 0.0;
     long long best_key = (long long)0x8000000000000000ull;
     uint32_t best_i = 0;
     bool have = false;
@@ -904,12 +904,15 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         const double w = __ddiv_rn(results[i].weight, sum);
         w_norm[i] = w;
         npart = __dadd_rn(npart, w);
+        sqpart = __dadd_rn(sqpart, __dmul_rn(w, w));
         const long long k = total_order_key(w);
         if (!have || k >= best_key) { best_key = k; best_i = i; have = true; }  // last max wins
     }
-    double cta_n;
+    double cta_n, cta_sq;
+    block_excl_scan_f64(sqpart, s_warp, &cta_sq);
     const double offset = block_excl_scan_f64(npart, s_warp, &cta_n);
     if (threadIdx.x < W_CLUSTER) cluster.map_shared_rank(&s_tot[1][0], threadIdx.x)[crank] = cta_n;
+    if (threadIdx.x == 0) cluster.map_shared_rank(&s_tot[2][0], 0)[crank] = cta_sq;
 
     // argmax by f64::total_cmp, ties -> highest index (Iterator::max_by returns the last maximum)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -950,6 +953,10 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         }
         counters->max_particle = bi;
         counters->sum = sum;
+        // number_of_effective_particles (particle.rs:59-65) of the normalised weights, before resampling
+        double sq = 0.0;
+        for (int r = 0; r < W_CLUSTER; ++r) sq = __dadd_rn(sq, s_tot[2][r]);
+        counters->n_eff = __ddiv_rn(1.0, sq);
     }
 }
 
@@ -1508,21 +1515,55 @@ void launch_account_full_copy(cudaStream_t stream, const unsigned long long* n_i
 }
 
 // =============================================================================== k_export
+// estimated_likelihood (slam.rs:83-88 -> Map::likelihood, map.rs:50-52): hit counters of the
+// estimate's grid -> probabilities. Formats: f64 (what GridMapMessage carries, node.rs:68-72),
+// f32 (what the visualizer converts to, visualize.rs:247) and u8 (round(255 p)); `win` restricts
+// the export to a window of the grid (e.g. the informed extent) to cut the D2H copy.
+template <typename T>
+__device__ __forceinline__ T export_value(double p);
+template <> __device__ __forceinline__ double export_value<double>(double p) { return p; }
+template <> __device__ __forceinline__ float export_value<float>(double p) { return (float)p; }
+template <> __device__ __forceinline__ uint8_t export_value<uint8_t>(double p) {
+    return (uint8_t)__double2int_rn(__dmul_rn(p, 255.0));
+}
 
+template <typename T>
 __global__ void __launch_bounds__(256)
 k_export(const uint32_t* __restrict__ cells, size_t cells_per_grid, const StepCounters* __restrict__ counters,
-         uint32_t n_cells, double* __restrict__ out) {
+         uint32_t grid_w, int4 win /* x0, y0, x1, y1 */, T* __restrict__ out) {
     const long long slot = counters->est_slot;
     if (slot < 0) return;  // another GPU owns the estimate
     const uint32_t* grid = cells + (size_t)slot * cells_per_grid;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += gridDim.x * blockDim.x)
-        out[i] = log_odds_probability(cell_log_odds(grid[i]));  // Map::likelihood, map.rs:50-52
+    const uint32_t ww = (uint32_t)(win.z - win.x), wh = (uint32_t)(win.w - win.y);
+    const uint32_t n = ww * wh;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t ry = i / ww, rx = i - ry * ww;
+        const uint32_t cell = grid[(size_t)(win.y + ry) * grid_w + (win.x + rx)];
+        // a never-informed cell is exactly the prior: log-odds 0 -> 1 - 1/(1 + exp(0)) = 0.5
+        out[i] = export_value<T>(cell == 0u ? 0.5 : log_odds_probability(cell_log_odds(cell)));  // Map::likelihood
+    }
 }
 
 void launch_export(cudaStream_t stream, const uint32_t* cells, size_t cells_per_grid, const StepCounters* counters,
-                   uint32_t n_cells, double* out) {
-    const int blocks = (int)min((n_cells + 255u) / 256u, 148u * 8u);
-    k_export<<<blocks, 256, 0, stream>>>(cells, cells_per_grid, counters, n_cells, out);
+                   uint32_t grid_w, int x0, int y0, int x1, int y1, int format, void* out) {
+    const uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+    const int blocks = (int)max(1u, min((n + 255u) / 256u, 148u * 8u));
+    const int4 win = make_int4(x0, y0, x1, y1);
+    if (format == 1) k_export<float><<<blocks, 256, 0, stream>>>(cells, cells_per_grid, counters, grid_w, win, (float*)out);
+    else if (format == 2) k_export<uint8_t><<<blocks, 256, 0, stream>>>(cells, cells_per_grid, counters, grid_w, win, (uint8_t*)out);
+    else k_export<double><<<blocks, 256, 0, stream>>>(cells, cells_per_grid, counters, grid_w, win, (double*)out);
+}
+
+// informed extent of the estimate's grid (empty -> 0,0,0,0)
+__global__ void k_estimate_extent(const SlotMeta* __restrict__ meta, const StepCounters* __restrict__ counters, int* out4) {
+    const long long slot = counters->est_slot;
+    if (slot < 0) { out4[0] = out4[1] = out4[2] = out4[3] = -1; return; }
+    const SlotMeta m = meta[slot];
+    if (m.x1 <= m.x0 || m.y1 <= m.y0) { out4[0] = out4[1] = out4[2] = out4[3] = 0; return; }
+    out4[0] = m.x0; out4[1] = m.y0; out4[2] = m.x1; out4[3] = m.y1;
+}
+void launch_estimate_extent(cudaStream_t stream, const SlotMeta* meta, const StepCounters* counters, int* out4) {
+    k_estimate_extent<<<1, 1, 0, stream>>>(meta, counters, out4);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1555,6 +1596,69 @@ void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, 
                        StepCounters* counters, uint32_t rank, SlotMeta* meta) {
     const uint32_t n = n_local + n_spare;
     k_init_slots<<<(n + 255) / 256, 256, 0, stream>>>(slot_of, n_local, spare_list, n_spare, counters, rank, meta);
+}
+
+// =============================================================================== k_sim_scan
+// The simulator's lidar on the device (slamrs/simulator/src/sim.rs:134-159 against the line
+// segments of scene/ray.rs:55-83): one thread per beam, nearest hit over all segments, beams whose
+// ray hits nothing are dropped (sim.rs:138) by an ordered compaction, so the observation lands in
+// the handle's device scan buffers in exactly the order the reference would publish it. f32
+// throughout, no contraction, glibc-exact sin/cos: bit-identical to the CPU restatement.
+__global__ void __launch_bounds__(1024)
+k_sim_scan(const float* __restrict__ segments, uint32_t n_seg, float px, float py, float ptheta, uint32_t n_beams,
+           float scanner_range, float* __restrict__ angle, float* __restrict__ dist, uint8_t* __restrict__ valid,
+           uint32_t* __restrict__ out_count_maxbits /* [0] = measurements, [1] = bits of the largest distance */) {
+    __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_base;
+    if (threadIdx.x == 0) s_base = 0u;
+    float maxd = 0.0f;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n_beams; b0 += blockDim.x) {
+        const uint32_t b = b0 + threadIdx.x;
+        bool have = false;
+        float best = 0.0f, a = 0.0f;
+        if (b < n_beams) {
+            // (angle as f32).to_radians() = value * (PI_f32 / 180), generalised to 360/n_beams degree steps
+            const float deg = __fmul_rn((float)b, __fdiv_rn(360.0f, (float)n_beams));
+            a = __fmul_rn(deg, __fdiv_rn(3.14159265358979323846264338327950288f, 180.0f));
+            float dx, dy;
+            slamrs_libm::sincosf_exact(__fadd_rn(a, ptheta), &dy, &dx);
+            const float x3 = px, y3 = py, x4 = __fadd_rn(px, dx), y4 = __fadd_rn(py, dy);
+            for (uint32_t k = 0; k < n_seg; ++k) {
+                const float x1 = segments[4 * k], y1 = segments[4 * k + 1], x2 = segments[4 * k + 2], y2 = segments[4 * k + 3];
+                const float denom = __fsub_rn(__fmul_rn(__fsub_rn(x1, x2), __fsub_rn(y3, y4)),
+                                              __fmul_rn(__fsub_rn(y1, y2), __fsub_rn(x3, x4)));
+                if (denom == 0.0f) continue;   // parallel
+                const float t = __fdiv_rn(__fsub_rn(__fmul_rn(__fsub_rn(x1, x3), __fsub_rn(y3, y4)),
+                                                    __fmul_rn(__fsub_rn(y1, y3), __fsub_rn(x3, x4))), denom);
+                const float u = __fdiv_rn(-__fsub_rn(__fmul_rn(__fsub_rn(x1, x2), __fsub_rn(y1, y3)),
+                                                     __fmul_rn(__fsub_rn(y1, y2), __fsub_rn(x1, x3))), denom);
+                if (t >= 0.0f && t <= 1.0f && u > 0.0f) {
+                    if (!have || u < best) { best = u; have = true; }   // min_by keeps the earlier element on ties
+                }
+            }
+        }
+        uint32_t total;
+        const uint32_t pos = s_base + block_excl_scan_u32(have ? 1u : 0u, s_warp, &total);
+        if (have) {
+            const bool hit = best < scanner_range;
+            const float d = hit ? best : scanner_range;
+            angle[pos] = a; dist[pos] = d; valid[pos] = hit ? 1 : 0;
+            maxd = fmaxf(maxd, fabsf(d));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+    atomicMax(&out_count_maxbits[1], __float_as_uint(maxd));   // non-negative floats order like their bits
+    if (threadIdx.x == 0) out_count_maxbits[0] = s_base;
+}
+
+void launch_sim_scan(cudaStream_t stream, const float* segments, uint32_t n_seg, float px, float py, float ptheta,
+                     uint32_t n_beams, float scanner_range, float* angle, float* dist, uint8_t* valid,
+                     uint32_t* out_count_maxbits) {
+    k_sim_scan<<<1, 1024, 0, stream>>>(segments, n_seg, px, py, ptheta, n_beams, scanner_range, angle, dist, valid,
+                                       out_count_maxbits);
 }
 
 // =============================================================================== per-device setup

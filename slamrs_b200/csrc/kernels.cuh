@@ -34,6 +34,7 @@ struct StepCounters {
     unsigned long long copy_max_rows;    // tallest region any copy job of this step writes (rows)
     unsigned long long barrier_timeout;  // a peer barrier gave up waiting (error)
     double sum;                          // sum of raw weights (particle.rs:50)
+    double n_eff;                        // 1 / sum of squared normalised weights (particle.rs:59-65)
     float est_pose[3];                   // estimated_pose(), slam.rs:77-81
     float pad;
 };
@@ -138,8 +139,10 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
                  const unsigned long long* n_items, const unsigned long long* n_leaders, size_t cells_per_grid,
                  int num_sms);
 
+// format: 0 = f64, 1 = f32, 2 = u8; [x0, x1) x [y0, y1) is the exported window of the grid
 void launch_export(cudaStream_t stream, const uint32_t* cells, size_t cells_per_grid, const StepCounters* counters,
-                   uint32_t n_cells, double* out);
+                   uint32_t grid_w, int x0, int y0, int x1, int y1, int format, void* out);
+void launch_estimate_extent(cudaStream_t stream, const SlotMeta* meta, const StepCounters* counters, int* out4);
 void launch_export_log_odds(cudaStream_t stream, const uint32_t* grid, uint32_t n_cells, double* out);
 
 void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
@@ -159,6 +162,10 @@ void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsig
 // add the bytes of a full-grid copy launch to counters->copy_bytes
 void launch_account_full_copy(cudaStream_t stream, const unsigned long long* n_items, const unsigned long long* n_leaders,
                               size_t bytes_per_grid, StepCounters* counters);
+// simulator lidar into device scan buffers; out_count_maxbits must be zeroed before the launch
+void launch_sim_scan(cudaStream_t stream, const float* segments, uint32_t n_seg, float px, float py, float ptheta,
+                     uint32_t n_beams, float scanner_range, float* angle, float* dist, uint8_t* valid,
+                     uint32_t* out_count_maxbits);
 cudaError_t configure_kernels();  // per-device function attributes; call once after cudaSetDevice
 
 // test hooks

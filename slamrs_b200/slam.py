@@ -224,6 +224,47 @@ class GridMapSlam:
         _lib.check(self._L.slamrs_gpu_map_probability(self._h, _ptr(out)), self._h)
         return GridData((self.grid_w, self.grid_h), out)
 
+    def map_extent(self):
+        """(x0, y0, x1, y1): informed extent of the estimate's grid in cells; all zero for an empty map."""
+        out = np.zeros(4, np.int32)
+        _lib.check(self._L.slamrs_gpu_map_extent(self._h, _ptr(out)), self._h)
+        return tuple(int(v) for v in out)
+
+    def estimated_likelihood_window(self, window=None, fmt: int = _lib.MAP_F32) -> tuple:
+        """((x0, y0, x1, y1), array[y1-y0, x1-x0]) of the estimate's map in f64 / f32 / u8; the default
+        window is the informed extent -- every cell outside it is exactly 0.5."""
+        x0, y0, x1, y1 = window if window is not None else self.map_extent()
+        dt = {_lib.MAP_F64: np.float64, _lib.MAP_F32: np.float32, _lib.MAP_U8: np.uint8}[fmt]
+        out = np.empty((max(0, y1 - y0), max(0, x1 - x0)), dt)
+        if out.size:
+            _lib.check(self._L.slamrs_gpu_map_window(self._h, fmt, x0, y0, x1, y1, _ptr(out)), self._h)
+        return (x0, y0, x1, y1), out
+
+    def number_of_effective_particles(self) -> float:
+        """particle.rs:59-65 on the last update's normalised weights (before resampling)."""
+        out = C.c_double(0.0)
+        _lib.check(self._L.slamrs_gpu_effective_particles(self._h, C.byref(out)), self._h)
+        return float(out.value)
+
+    # ------------------------------------------------------------------ scan production on the device
+    def sim_scan(self, segments, pose, n_beams: int, scanner_range: float) -> int:
+        """The simulator's lidar evaluated on the device into the handle's scan buffers; returns the
+        number of measurements. Follow with step_async()."""
+        seg = np.ascontiguousarray(segments, np.float32).reshape(-1, 4)
+        p = np.ascontiguousarray(pose, np.float32).reshape(3)
+        n = C.c_uint32(0)
+        _lib.check(self._L.slamrs_gpu_sim_scan(self._h, _ptr(seg), seg.shape[0], _ptr(p), n_beams, scanner_range,
+                                               C.byref(n)), self._h)
+        return int(n.value)
+
+    def get_scan(self) -> Observation:
+        n = C.c_uint32(0)
+        _lib.check(self._L.slamrs_gpu_get_scan(self._h, None, None, None, 0, C.byref(n)), self._h)
+        a = np.zeros(n.value, np.float32); d = np.zeros(n.value, np.float32); v = np.zeros(n.value, np.uint8)
+        if n.value:
+            _lib.check(self._L.slamrs_gpu_get_scan(self._h, _ptr(a), _ptr(d), _ptr(v), n.value, C.byref(n)), self._h)
+        return Observation(0, angle=a.astype(np.float64), distance=d.astype(np.float64), valid=v.astype(bool))
+
     def map_position(self):
         return tuple(self.config.position)  # slam.rs:90-96: constant, answered from the config
 
