@@ -18,6 +18,16 @@ pub const SLAMRS_E_INTERNAL: c_int = -8;
 pub const SLAMRS_RNG_SHARED_STREAM: u32 = 0;
 pub const SLAMRS_RNG_CALLER: u32 = 1;
 
+pub const SLAMRS_FLAG_GENERIC_RAY_KERNEL: u32 = 1;
+pub const SLAMRS_FLAG_UPDATE_ALL_PARTICLES: u32 = 2;
+pub const SLAMRS_FLAG_FULL_GRID_COPY: u32 = 4;
+pub const SLAMRS_FLAG_NCCL_EXCHANGE: u32 = 8;
+
+pub const SLAMRS_MAP_F64: u32 = 0;
+pub const SLAMRS_MAP_F32: u32 = 1;
+pub const SLAMRS_MAP_U8: u32 = 2;
+pub const SLAMRS_HISTORY_VALUES: usize = 6;
+
 #[repr(C)]
 pub struct slamrs_gpu_handle {
     _private: [u8; 0],
@@ -83,6 +93,11 @@ extern "C" {
     pub fn slamrs_gpu_set_scan_device(h: *mut slamrs_gpu_handle, angle: *const f32, dist: *const f32, valid: *const u8, n_beams: u32, max_dist: f32) -> c_int;
     pub fn slamrs_gpu_pose(h: *mut slamrs_gpu_handle, out_xyt: *mut f32) -> c_int;
     pub fn slamrs_gpu_map_probability(h: *mut slamrs_gpu_handle, out_cells: *mut f64) -> c_int;
+    pub fn slamrs_gpu_map_extent(h: *mut slamrs_gpu_handle, out_x0y0x1y1: *mut i32) -> c_int;
+    pub fn slamrs_gpu_map_window(h: *mut slamrs_gpu_handle, format: u32, x0: i32, y0: i32, x1: i32, y1: i32, out: *mut c_void) -> c_int;
+    pub fn slamrs_gpu_effective_particles(h: *mut slamrs_gpu_handle, out: *mut f64) -> c_int;
+    pub fn slamrs_gpu_sim_scan(h: *mut slamrs_gpu_handle, segments_xyxy: *const f32, n_segments: u32, pose_xyt: *const f32, n_beams: u32, scanner_range: f32, out_n: *mut u32) -> c_int;
+    pub fn slamrs_gpu_get_scan(h: *mut slamrs_gpu_handle, out_angle: *mut f32, out_dist: *mut f32, out_valid: *mut u8, cap: u32, out_n: *mut u32) -> c_int;
     pub fn slamrs_gpu_last_error(h: *const slamrs_gpu_handle) -> *const c_char;
     pub fn slamrs_gpu_get_stats(h: *mut slamrs_gpu_handle, out: *mut slamrs_gpu_stats) -> c_int;
     pub fn slamrs_gpu_stream(h: *mut slamrs_gpu_handle) -> *mut c_void;

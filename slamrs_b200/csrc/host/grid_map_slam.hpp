@@ -65,6 +65,7 @@ struct GpuPlacement {  // what the YAML cannot carry
     uint64_t seed = 0x5EED5A11ull;
     uint32_t rng_mode = SLAMRS_RNG_SHARED_STREAM;
     uint32_t spare_slots = 0;
+    uint32_t flags = 0;  // enum slamrs_flags
     uint8_t nccl_id[SLAMRS_NCCL_ID_BYTES] = {0};
 };
 
@@ -88,6 +89,7 @@ public:
         c.rank = pl.rank;
         c.world_size = pl.world_size;
         c.spare_slots = pl.spare_slots;
+        c.flags = pl.flags;
         for (int i = 0; i < SLAMRS_NCCL_ID_BYTES; ++i) c.nccl_id[i] = pl.nccl_id[i];
         grid_w_ = c.grid_w;
         grid_h_ = c.grid_h;
@@ -125,6 +127,30 @@ public:
         static_assert(sizeof(Probability) == sizeof(double), "Probability is a transparent f64 newtype");
         check(slamrs_gpu_map_probability(h_, reinterpret_cast<double*>(g.data.data())), h_);
         return g;
+    }
+
+    // The informed part of the same map as f32 (what the visualizer converts every cell to,
+    // visualize.rs:247): window = {x0, y0, x1, y1} in cells, values row-major; every cell outside
+    // the window is exactly 0.5. Cuts the per-scan device-to-host copy from 8 B/cell of the whole grid.
+    struct MapWindow {
+        int32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        std::vector<float> data;
+    };
+    MapWindow estimated_likelihood_window() const {
+        MapWindow w;
+        int32_t e[4];
+        check(slamrs_gpu_map_extent(h_, e), h_);
+        w.x0 = e[0]; w.y0 = e[1]; w.x1 = e[2]; w.y1 = e[3];
+        w.data.resize(static_cast<std::size_t>(w.x1 - w.x0) * static_cast<std::size_t>(w.y1 - w.y0));
+        if (!w.data.empty()) check(slamrs_gpu_map_window(h_, SLAMRS_MAP_F32, w.x0, w.y0, w.x1, w.y1, w.data.data()), h_);
+        return w;
+    }
+
+    // ParticleFilter::number_of_effective_particles, particle.rs:59-65 (normalised weights of the last update)
+    double number_of_effective_particles() const {
+        double v = 0.0;
+        check(slamrs_gpu_effective_particles(h_, &v), h_);
+        return v;
     }
 
     std::pair<float, float> map_position() const { return {config_.position[0], config_.position[1]}; }  // slam.rs:90-96

@@ -758,8 +758,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     __syncthreads();
 
     // ---- write-back, row by row: one warp per window row, one lane per 8-cell group (a 128-bit
-    // shared load -> two 128-bit global RMWs); RAY_WB_ROWS rows are in flight per warp. A counter
-    // below 2^15 cannot saturate by one scan's increment, which is the common, branch-free case.
+    // shared load -> two 128-bit global RMWs); RAY_WB_ROWS rows are in flight per warp.
     constexpr int RAY_WB_ROWS = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
@@ -798,15 +797,26 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
 #pragma unroll
             for (int j = 0; j < RAY_WB_ROWS; ++j) {
                 if (nz[j]) {
-                    auto apply = [&](uint32_t g, uint32_t packed16) {
-                        const uint32_t delta = (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16);
-                        if ((g & 0x80008000u) == 0u) return g + delta;
-                        return cell_sat_add(g, delta, &saturated);
-                    };
-                    va[j].x = apply(va[j].x, d[j].x & 0xffffu); va[j].y = apply(va[j].y, d[j].x >> 16);
-                    va[j].z = apply(va[j].z, d[j].y & 0xffffu); va[j].w = apply(va[j].w, d[j].y >> 16);
-                    vb[j].x = apply(vb[j].x, d[j].z & 0xffffu); vb[j].y = apply(vb[j].y, d[j].z >> 16);
-                    vb[j].z = apply(vb[j].z, d[j].w & 0xffffu); vb[j].w = apply(vb[j].w, d[j].w >> 16);
+                    // group-level fast path: no occupied hit among the 8 window cells (a packed value is
+                    // then the free count itself) and no counter of the 8 grid cells at or above 2^15
+                    // (it cannot saturate by one scan's increment): eight plain adds
+                    const uint32_t occ_any = (d[j].x | d[j].y | d[j].z | d[j].w) & 0xF800F800u;
+                    const uint32_t high_any = (va[j].x | va[j].y | va[j].z | va[j].w | vb[j].x | vb[j].y | vb[j].z | vb[j].w) & 0x80008000u;
+                    if ((occ_any | high_any) == 0u) {
+                        va[j].x += d[j].x & 0xffffu; va[j].y += d[j].x >> 16;
+                        va[j].z += d[j].y & 0xffffu; va[j].w += d[j].y >> 16;
+                        vb[j].x += d[j].z & 0xffffu; vb[j].y += d[j].z >> 16;
+                        vb[j].z += d[j].w & 0xffffu; vb[j].w += d[j].w >> 16;
+                    } else {
+                        auto apply = [&](uint32_t g, uint32_t packed16) {
+                            const uint32_t delta = (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16);
+                            return cell_sat_add(g, delta, &saturated);
+                        };
+                        va[j].x = apply(va[j].x, d[j].x & 0xffffu); va[j].y = apply(va[j].y, d[j].x >> 16);
+                        va[j].z = apply(va[j].z, d[j].y & 0xffffu); va[j].w = apply(va[j].w, d[j].y >> 16);
+                        vb[j].x = apply(vb[j].x, d[j].z & 0xffffu); vb[j].y = apply(vb[j].y, d[j].z >> 16);
+                        vb[j].z = apply(vb[j].z, d[j].w & 0xffffu); vb[j].w = apply(vb[j].w, d[j].w >> 16);
+                    }
                     gp[j][0] = va[j];
                     gp[j][1] = vb[j];
                 }
