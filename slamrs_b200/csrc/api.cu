@@ -70,6 +70,7 @@ struct slamrs_gpu_handle {
     StepCounters* d_counters = nullptr;
     StepCounters* h_counters = nullptr;  // pinned
     double* d_export = nullptr;
+    double* d_term_table = nullptr;   // per-beam likelihood factor by hit-counter pair
     int* d_barrier = nullptr;
 
     Comm* comm = nullptr;
@@ -233,6 +234,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_pool);
     cudaFree(h->d_slot[0]); cudaFree(h->d_slot[1]);
     cudaFree(h->d_pose[0]); cudaFree(h->d_pose[1]);
+    cudaFree(h->d_term_table);
     cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx);
     cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
     cudaFree(h->d_z); cudaFree(h->d_u);
@@ -482,6 +484,9 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
     memset(h->h_counters, 0, sizeof(StepCounters));
     CREATE_CU(cudaMalloc(&h->d_export, sizeof(double) * h->n_cells));
+    CREATE_CU(cudaMalloc(&h->d_term_table, sizeof(double) * LK_TABLE_NF * LK_TABLE_NO));
+    launch_fill_term_table(h->stream, h->d_term_table);
+    h->launches++;
     CREATE_CU(cudaMalloc(&h->d_history, sizeof(StepRecord) * STEP_HISTORY));
     CREATE_CU(cudaMemsetAsync(h->d_history, 0xff, sizeof(StepRecord) * STEP_HISTORY, h->stream));
     CREATE_CU(cudaMalloc(&h->d_barrier, sizeof(int)));
@@ -582,13 +587,14 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     }
     const int cur = h->cur, nxt = cur ^ 1;
     const size_t grid_bytes = h->cells_per_grid * sizeof(uint32_t);
+    const bool all_particles = (h->cfg.flags & SLAMRS_FLAG_UPDATE_ALL_PARTICLES) != 0;
     const uint32_t res_off = (uint32_t)(h->step & 1ull) * h->n_total;
     h->d_results = h->d_results_base + res_off;
 
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->cells_per_grid,
-                             h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step,
+                             h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step, h->d_term_table,
                              h->p2p_exchange ? h->d_peer_results : nullptr, res_off, h->rank, h->world);
     h->launches += 2;   // k_motion + k_likelihood
     // 2. the one exchange step: every GPU needs every particle's weight, pose and slot. Default:
@@ -611,7 +617,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     // (k_weights also zeroes the per-step counters)
     launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
-                            h->d_idx, h->d_pose[nxt], h->first, h->n_local, h->d_counters);
+                            h->d_idx, h->d_pose[nxt], h->first, h->n_local, !all_particles, h->d_alive, h->d_counters);
     // 4. plan (side stream): which grids stay, which are duplicated locally, which are pulled from a
     //    peer. It needs only the index vector, so it runs concurrently with the ray update.
     CU_TRY(h, cudaEventRecord(h->ev_indices, s));
@@ -635,9 +641,11 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     CU_TRY(h, cudaEventRecord(h->ev_plan, h->side_stream));
     h->launches++;
     // 5. integrate the scan into the grids that survive resampling (all grids in strict mode)
-    launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local,
-                      (h->cfg.flags & SLAMRS_FLAG_UPDATE_ALL_PARTICLES) != 0, h->d_alive, h->d_counters);
-    h->launches += 3;
+    if (all_particles) {
+        launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local, true, h->d_alive, h->d_counters);
+        h->launches++;
+    }
+    h->launches += 2;
     PROF_MARK(h, 3);
     CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive, h->d_slot[cur],
                                 h->d_cells, h->d_meta, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,

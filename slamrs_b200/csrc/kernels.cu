@@ -142,9 +142,10 @@ k_motion(OdomModel od, const float* __restrict__ pose_cur, const int32_t* __rest
 constexpr int LK_WARPS = 4;
 constexpr int LK_UNROLL = 4;
 
-__global__ void __launch_bounds__(LK_WARPS * 32)
+__global__ void __launch_bounds__(LK_WARPS * 32, 2048 / (LK_WARPS * 32))   // every particle of an 8,192-shard resident at once
 k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, size_t cells_per_grid,
              ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
+             const double* __restrict__ term_table,
              ParticleResult* const* __restrict__ peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     const uint32_t p = blockIdx.x * LK_WARPS + (threadIdx.x >> 5);
     if (p >= n_local) return;
@@ -174,10 +175,9 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
 #pragma unroll
         for (int u = 0; u < LK_UNROLL; ++u) {
             if (cell[u] != 0u) {
-                const double prob = log_odds_probability(cell_log_odds(cell[u]));
-                // Z_HIT = 0.9, SENSOR_MAXDIST = 1.0 (map.rs:108-109)
-                const double term = (prob == 0.5) ? log(1.0 / 1.0)
-                                                  : log(__dadd_rn(__dmul_rn(0.9, prob), (1.0 - 0.9) * 1.0 / 1.0));
+                const uint32_t nf = cell[u] & 0xffffu, no = cell[u] >> 16;
+                const double term = (nf < LK_TABLE_NF && no < LK_TABLE_NO) ? __ldg(&term_table[nf * LK_TABLE_NO + no])
+                                                                           : beam_log_term(cell[u]);
                 lp = __dadd_rn(lp, term);
             }
         }
@@ -236,12 +236,24 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
                               size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
+                              const double* term_table,
                               ParticleResult* const* peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
                                                          z_draws, seed, step);
     k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, cells, cells_per_grid,
                                                                                    results, first_particle, n_local,
-                                                                                   peer_results, peer_offset, rank, world);
+                                                                                   term_table, peer_results, peer_offset,
+                                                                                   rank, world);
+}
+
+__global__ void k_fill_term_table(double* __restrict__ table) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= LK_TABLE_NF * LK_TABLE_NO) return;
+    const uint32_t nf = i / LK_TABLE_NO, no = i % LK_TABLE_NO;
+    table[i] = (nf | no) ? beam_log_term(nf | (no << 16)) : 0.0;   // entry (0,0) is never read (prior cells are skipped)
+}
+void launch_fill_term_table(cudaStream_t stream, double* table) {
+    k_fill_term_table<<<(LK_TABLE_NF * LK_TABLE_NO + 255) / 256, 256, 0, stream>>>(table);
 }
 
 // =============================================================================== k_ray_update
@@ -977,16 +989,11 @@ void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t
 
 // =============================================================================== k_resample_indices
 
-__global__ void __launch_bounds__(256)
-k_resample_indices(const ParticleResult* __restrict__ results, const double* __restrict__ cum, uint32_t n,
-                   const double* __restrict__ u01_caller, uint64_t seed, uint64_t step, uint32_t* __restrict__ idx,
-                   float* __restrict__ pose_next, uint32_t first_particle, uint32_t n_local, StepCounters* counters) {
-    const uint32_t m0 = blockIdx.x * blockDim.x + threadIdx.x;  // zero-based new-particle index
-    if (m0 >= n) return;
-    // particle.rs:84: r = rand::random::<f64>() * 1.0 / N
-    const double U = u01_caller ? *u01_caller : slamrs_stream::resample_uniform(seed, step);
+// first i with !(u_m > cum[i]) for the zero-based new-particle index m0 (particle.rs:84-94)
+__device__ __forceinline__ uint32_t resample_source(const double* __restrict__ cum, uint32_t n, double U, uint32_t m0,
+                                                    bool* ran_off) {
     const double num = (double)n;
-    const double r = __ddiv_rn(__dmul_rn(U, 1.0), num);
+    const double r = __ddiv_rn(__dmul_rn(U, 1.0), num);   // particle.rs:84: r = rand::random::<f64>() * 1.0 / N
     // particle.rs:89: u = r + (m as f64 - 1.0) * 1.0 / N with m = m0 + 1
     const double u = __dadd_rn(r, __ddiv_rn(__dmul_rn(__dsub_rn((double)(m0 + 1u), 1.0), 1.0), num));
     // particle.rs:91-94: advance i while u > c. c is non-decreasing (weights >= 0), so the loop
@@ -996,35 +1003,72 @@ k_resample_indices(const ParticleResult* __restrict__ results, const double* __r
         const uint32_t mid = lo + ((hi - lo) >> 1);
         if (u > cum[mid]) lo = mid + 1; else hi = mid;
     }
-    if (lo >= n) {  // the reference would index out of bounds and panic; clamp and flag
-        lo = n - 1;
-        atomicAdd(&counters->clamped, 1ull);
+    *ran_off = lo >= n;   // the reference would index out of bounds and panic; clamp and flag
+    return lo >= n ? n - 1 : lo;
+}
+
+// Also builds the list of local particles that survive (some index selects them): a particle that
+// no entry of the index vector selects is dropped by the resampler (particle.rs:88-104 builds the
+// new generation only from old[i]); integrating the scan into its grid would be unobservable work,
+// so the ray kernel runs on the survivors only. The thread of the FIRST new particle that selects a
+// local source appends it (the index vector is non-decreasing, so "first" = differs from the
+// predecessor's source, which comes from the neighbouring lane).
+__global__ void __launch_bounds__(256)
+k_resample_indices(const ParticleResult* __restrict__ results, const double* __restrict__ cum, uint32_t n,
+                   const double* __restrict__ u01_caller, uint64_t seed, uint64_t step, uint32_t* __restrict__ idx,
+                   float* __restrict__ pose_next, uint32_t first_particle, uint32_t n_local, bool build_alive,
+                   uint32_t* __restrict__ alive_list, StepCounters* counters) {
+    const uint32_t m0 = blockIdx.x * blockDim.x + threadIdx.x;  // zero-based new-particle index
+    const double U = u01_caller ? *u01_caller : slamrs_stream::resample_uniform(seed, step);
+    const int lane = threadIdx.x & 31;
+    bool ran_off = false;
+    uint32_t src_idx = 0xffffffffu;
+    if (m0 < n) {
+        src_idx = resample_source(cum, n, U, m0, &ran_off);
+        if (ran_off) atomicAdd(&counters->clamped, 1ull);
+        idx[m0] = src_idx;
+        const ParticleResult src = results[src_idx];
+        if (m0 >= first_particle && m0 < first_particle + n_local) {
+            float* q = pose_next + 3 * (size_t)(m0 - first_particle);
+            q[0] = src.x; q[1] = src.y; q[2] = src.theta;
+        }
+        // estimated_pose(), slam.rs:77-81: new generation indexed by the pre-resample argmax
+        if ((unsigned long long)m0 == counters->max_particle) {
+            counters->est_pose[0] = src.x; counters->est_pose[1] = src.y; counters->est_pose[2] = src.theta;
+        }
     }
-    idx[m0] = lo;
-    const ParticleResult src = results[lo];
-    if (m0 >= first_particle && m0 < first_particle + n_local) {
-        float* q = pose_next + 3 * (size_t)(m0 - first_particle);
-        q[0] = src.x; q[1] = src.y; q[2] = src.theta;
+    if (!build_alive) return;   // uniform over the grid
+    uint32_t prev = __shfl_up_sync(0xffffffffu, src_idx, 1);
+    if (lane == 0 && m0 > 0 && m0 < n) {
+        bool dummy;
+        prev = resample_source(cum, n, U, m0 - 1u, &dummy);
     }
-    // estimated_pose(), slam.rs:77-81: new generation indexed by the pre-resample argmax
-    if ((unsigned long long)m0 == counters->max_particle) {
-        counters->est_pose[0] = src.x; counters->est_pose[1] = src.y; counters->est_pose[2] = src.theta;
+    const bool alive = m0 < n && (m0 == 0 || prev != src_idx) && src_idx >= first_particle &&
+                       src_idx < first_particle + n_local;
+    // warp-aggregated append (order is irrelevant: particles are independent)
+    const unsigned mask = __ballot_sync(0xffffffffu, alive);
+    if (mask) {
+        const int leader = __ffs(mask) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&counters->n_alive, (unsigned long long)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (alive) alive_list[base + __popc(mask & ((1u << lane) - 1u))] = src_idx - first_particle;
     }
 }
 
 void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
                              uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,
                              uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
-                             StepCounters* counters) {
+                             bool build_alive, uint32_t* alive_list, StepCounters* counters) {
     k_resample_indices<<<(n_total + 255) / 256, 256, 0, stream>>>(results, cum, n_total, u01_caller, seed, step, idx,
-                                                                 pose_next, first_particle, n_local, counters);
+                                                                 pose_next, first_particle, n_local, build_alive,
+                                                                 alive_list, counters);
 }
 
 // =============================================================================== k_mark_alive
-// A particle that no entry of the index vector selects is dropped by the resampler
-// (particle.rs:88-104 builds the new generation only from old[i]); integrating the scan into its
-// grid would be unobservable work. The ray kernel therefore runs AFTER the indices are known, on
-// the survivors only. With all_particles the list is the identity (the reference's order of work).
+// The survivor list is normally built by k_resample_indices. This kernel builds it on its own:
+// with all_particles the list is the identity (the reference's order of work: every particle's
+// grid receives the scan).
 __global__ void __launch_bounds__(256)
 k_mark_alive(const uint32_t* __restrict__ idx, uint32_t n_total, uint32_t first_particle, uint32_t n_local,
              bool all_particles, uint32_t* __restrict__ alive_list, StepCounters* counters) {

@@ -78,9 +78,11 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
                               size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
+                              const double* term_table /* LK_TABLE_NF x LK_TABLE_NO, launch_fill_term_table */,
                               ParticleResult* const* peer_results /* null: no fused exchange */,
                               uint32_t peer_offset /* records in front of this step's generation */, uint32_t rank,
                               uint32_t world);
+void launch_fill_term_table(cudaStream_t stream, double* table);
 constexpr uint32_t PEER_MAX_WORLD = 64;
 void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
                          uint32_t rank, uint32_t world, unsigned long long epoch, unsigned long long timeout_ns,
@@ -100,7 +102,8 @@ void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t
 void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
                              uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,
                              uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
-                             StepCounters* counters);
+                             bool build_alive /* also append the surviving local particles to alive_list */,
+                             uint32_t* alive_list, StepCounters* counters);
 
 struct PlanArgs {
     const ParticleResult* results;  // N, after the all-gather (carries every particle's physical slot)

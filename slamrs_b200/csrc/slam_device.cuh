@@ -27,6 +27,18 @@ __device__ __forceinline__ double cell_log_odds(uint32_t cell) {
 // LogOdds::probability, math.rs:135-137
 __device__ __forceinline__ double log_odds_probability(double l) { return 1.0 - 1.0 / (1.0 + exp(l)); }
 
+// one factor of Map::probability_of (map.rs:130-141) in log form for an informed cell:
+// log(Z_HIT * p + (1 - Z_HIT) * 1 / SENSOR_MAXDIST), or log(1/1) when p is exactly the prior
+__device__ __forceinline__ double beam_log_term(uint32_t cell) {
+    const double prob = log_odds_probability(cell_log_odds(cell));
+    // Z_HIT = 0.9, SENSOR_MAXDIST = 1.0 (map.rs:108-109)
+    return (prob == 0.5) ? log(1.0 / 1.0) : log(__dadd_rn(__dmul_rn(0.9, prob), (1.0 - 0.9) * 1.0 / 1.0));
+}
+// The factor depends on the cell's two hit counters only. For counters below these bounds it is
+// read from a table that the same function filled on the same device at create (bit-identical
+// to evaluating it in place, without the exp, the division and the log per beam).
+constexpr uint32_t LK_TABLE_NF = 32, LK_TABLE_NO = 256;
+
 __device__ __forceinline__ uint32_t cell_sat_add(uint32_t cell, uint32_t delta, bool* saturated) {
     uint32_t lo = (cell & 0xffffu) + (delta & 0xffffu);
     uint32_t hi = (cell >> 16) + (delta >> 16);
