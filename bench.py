@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-order-of-work comparison run")
     ap.add_argument("--no-full-copy", action="store_true", help="skip the whole-grid-copy comparison run")
     ap.add_argument("--flags", type=int, default=0, help="slamrs_flags bits for the main run (profiling)")
+    ap.add_argument("--shift-x-cells", type=int, default=0, help="experiment: move the map origin by this many cells in x")
     return ap.parse_args()
 
 
@@ -205,6 +206,8 @@ def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2
     K, W = args.steps, args.warmup
     n_total = wl.n_particles * world
     cfg = wl.slam_config(n_total)
+    if getattr(args, "shift_x_cells", 0):
+        cfg.position = (cfg.position[0] - args.shift_x_cells * cfg.resolution, cfg.position[1])
     slam = GridMapSlam(cfg, GpuPlacement(device=local, rank=rank, world_size=world, nccl_id=nccl_id, flags=flags))
     stream = torch.cuda.ExternalStream(slam.stream_ptr, device=dev)
     grid_bytes = slam.stats()["bytes_per_grid"]

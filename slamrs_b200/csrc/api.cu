@@ -388,7 +388,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     h->first = h->rank * h->n_local;
     h->n_cells = cfg->grid_w * cfg->grid_h;
     h->cells_per_grid = ((size_t)h->n_cells + 31u) & ~(size_t)31u;
-    h->geom = MapGeom{cfg->pos_x, cfg->pos_y, cfg->resolution, cfg->grid_w, cfg->grid_h};
+    h->geom = make_map_geom(cfg->pos_x, cfg->pos_y, cfg->resolution, cfg->grid_w, cfg->grid_h);
 
 #define CREATE_TRY(expr)                                  \
     do {                                                  \
@@ -593,7 +593,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
 
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
-    launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->cells_per_grid,
+    launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->d_meta, h->cells_per_grid,
                              h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step, h->d_term_table,
                              h->p2p_exchange ? h->d_peer_results : nullptr, res_off, h->rank, h->world);
     h->launches += 2;   // k_motion + k_likelihood
@@ -664,7 +664,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 6);
     if (h->boxed_copy) {
         launch_copy_boxed(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->n_local,
-                          h->d_jobs, h->geom.gw, h->d_counters, h->num_sms);
+                          h->d_jobs, h->geom, h->d_counters, h->num_sms);
         h->launches++;
     } else {
         launch_copy(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->cells_per_grid,
@@ -674,7 +674,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     }
     h->launches++;
     PROF_MARK(h, 7);
-    launch_commit_boxes(s, h->d_copies, &h->d_counters->n_copies, h->n_local, h->d_counters,
+    launch_commit_boxes(s, h->d_copies, &h->d_counters->n_copies, h->n_local, h->geom, h->boxed_copy, h->d_counters,
                         h->d_history + (h->step % STEP_HISTORY));
     h->launches++;
     if (h->profiling) h->prof_recorded++;
@@ -728,7 +728,7 @@ int export_window(slamrs_gpu_handle* h, uint32_t format, int x0, int y0, int x1,
     if (n == 0) return SLAMRS_OK;
     const size_t bytes = n * (format == SLAMRS_MAP_F64 ? 8u : (format == SLAMRS_MAP_F32 ? 4u : 1u));
     cudaStream_t s = h->stream;
-    launch_export(s, h->d_cells, h->cells_per_grid, h->d_counters, h->geom.gw, x0, y0, x1, y1, (int)format, h->d_export);
+    launch_export(s, h->d_cells, h->d_meta, h->cells_per_grid, h->d_counters, h->geom, x0, y0, x1, y1, (int)format, h->d_export);
     h->launches++;
     if (h->world > 1) {
         int rc = fetch_counters(h);  // root = owner of the estimate, identical on every rank
@@ -957,8 +957,10 @@ int slamrs_gpu_get_cells(slamrs_gpu_handle* h, uint64_t particle, uint32_t* out_
     int32_t slot = 0;
     int rc = local_slot(h, particle, &slot);
     if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(out_cells, h->d_cells + (size_t)slot * h->cells_per_grid, sizeof(uint32_t) * h->n_cells,
-                              cudaMemcpyDeviceToHost, h->stream));
+    // the slot stores its rows rotated; the export kernel undoes that
+    launch_export_slot(h->stream, h->d_cells + (size_t)slot * h->cells_per_grid, h->d_meta + slot, h->geom, false, h->d_export);
+    h->launches++;
+    CU_TRY(h, cudaMemcpyAsync(out_cells, h->d_export, sizeof(uint32_t) * h->n_cells, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return SLAMRS_OK;
 }
@@ -971,7 +973,7 @@ int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t
     if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(h->d_cells + (size_t)slot * h->cells_per_grid, cells, sizeof(uint32_t) * h->n_cells,
                               cudaMemcpyHostToDevice, h->stream));
-    // extent of the informed cells of the new image
+    // extent of the informed cells of the new image (stored unrotated: SlotMeta::ox = 0)
     const int gw = (int)h->geom.gw, gh = (int)h->geom.gh;
     int x0 = gw, y0 = gh, x1 = -1, y1 = -1;
     for (int y = 0; y < gh; ++y) {
@@ -999,7 +1001,7 @@ int slamrs_gpu_get_log_odds(slamrs_gpu_handle* h, uint64_t particle, double* out
     int32_t slot = 0;
     int rc = local_slot(h, particle, &slot);
     if (rc) return rc;
-    launch_export_log_odds(h->stream, h->d_cells + (size_t)slot * h->cells_per_grid, h->n_cells, h->d_export);
+    launch_export_slot(h->stream, h->d_cells + (size_t)slot * h->cells_per_grid, h->d_meta + slot, h->geom, true, h->d_export);
     h->launches++;
     CU_TRY(h, cudaMemcpyAsync(out_cells, h->d_export, sizeof(double) * h->n_cells, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));

@@ -143,8 +143,8 @@ constexpr int LK_WARPS = 4;
 constexpr int LK_UNROLL = 4;
 
 __global__ void __launch_bounds__(LK_WARPS * 32, 2048 / (LK_WARPS * 32))   // every particle of an 8,192-shard resident at once
-k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, size_t cells_per_grid,
-             ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
+k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, const SlotMeta* __restrict__ meta,
+             size_t cells_per_grid, ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
              const double* __restrict__ term_table,
              ParticleResult* const* __restrict__ peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     const uint32_t p = blockIdx.x * LK_WARPS + (threadIdx.x >> 5);
@@ -153,6 +153,7 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
     const ParticleResult r = results[first_particle + p];
     const float nx = r.x, ny = r.y, ntheta = r.theta;
     const uint32_t* grid = cells + (size_t)r.slot * cells_per_grid;
+    const int shift = meta[r.slot].ox;   // row rotation of this particle's slot
 
     double lp = log(1.0);
     for (uint32_t base = 0; base < scan.n_beams; base += 32u * LK_UNROLL) {
@@ -168,7 +169,8 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
                 const float gy = world_to_grid(ey, geom.pos_y, geom.res);
                 if (grid_is_valid(gx, gy, geom.gw, geom.gh)) {
                     const size_t column = (size_t)f32_as_usize(gx), row = (size_t)f32_as_usize(gy);
-                    cell[u] = __ldg(&grid[row * geom.gh + column]);  // index(): map.rs:201-204
+                    // index(): map.rs:201-204, then the slot's row rotation
+                    cell[u] = __ldg(&grid[row * geom.gh + phys_col(geom, (uint32_t)column, shift)]);
                 }
             }
         }
@@ -234,13 +236,13 @@ void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_fl
 
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
                               const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
-                              size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
+                              const SlotMeta* meta, size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
                               const double* term_table,
                               ParticleResult* const* peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
                                                          z_draws, seed, step);
-    k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, cells, cells_per_grid,
+    k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, cells, meta, cells_per_grid,
                                                                                    results, first_particle, n_local,
                                                                                    term_table, peer_results, peer_offset,
                                                                                    rank, world);
@@ -285,9 +287,40 @@ __device__ __forceinline__ void ext_add(int* s_ext, int xmin, int ymin, int xmax
 }
 // union the CTA's touched extent into the slot's box (x aligned to 8 cells); one thread, after a barrier
 constexpr int BOX_ALIGN = 8;   // x alignment of extents in cells: one 256-bit access
-__device__ __forceinline__ void ext_commit(const int* s_ext, SlotMeta* meta, int gw) {
+// Row rotation of the slot a ray kernel writes: the slot's own once it holds a grid; for an empty slot
+// (first scan of a lineage) the one that puts the leftmost cell any ray can reach on a page
+// boundary. s_shift[0] receives it; all threads of the CTA call this, with a barrier inside.
+__device__ __forceinline__ int ray_slot_shift(const MapGeom& geom, const ScanDevice& scan, const SlotMeta* meta, float px,
+                                              float py, float ptheta, int cx0, int* s_shift) {
+    const SlotMeta m = *meta;
+    const bool empty = m.x1 <= m.x0 || m.y1 <= m.y0;
+    if (threadIdx.x == 0) s_shift[0] = empty ? 0x7fffffff : m.ox;
+    __syncthreads();
+    if (empty && geom.page_cells) {   // uniform over the CTA
+        int xmin = cx0;
+        for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
+            float ex, ey;
+            beam_endpoint(px, py, ptheta, scan.angle[b], scan.dist[b], &ex, &ey);
+            const float gx = floorf(world_to_grid(ex, geom.pos_x, geom.res));
+            // a ray reaches at most two cells beyond its endpoint cell (map.rs:97); NaN / far-out -> 0
+            const int reach = (gx >= 2.0f && gx < 1.0e6f) ? (int)gx - 2 : 0;
+            xmin = min(xmin, reach);
+        }
+        atomicMin(&s_shift[0], max(0, xmin));
+        __syncthreads();
+        if (threadIdx.x == 0) s_shift[0] = align_shift(geom, s_shift[0] & ~7);
+        __syncthreads();
+    } else if (empty) {
+        if (threadIdx.x == 0) s_shift[0] = 0;
+        __syncthreads();
+    }
+    return s_shift[0];
+}
+
+__device__ __forceinline__ void ext_commit(const int* s_ext, SlotMeta* meta, int gw, int shift) {
     if (s_ext[2] < s_ext[0]) return;
     SlotMeta b = *meta;
+    b.ox = shift;
     const int am = BOX_ALIGN - 1;
     const int x0 = s_ext[0] & ~am, x1 = min(gw, (s_ext[2] + 1 + am) & ~am), y0 = s_ext[1], y1 = s_ext[3] + 1;
     if (b.x1 <= b.x0) { b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; }
@@ -327,6 +360,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     __shared__ int s_row_off[RAY_MAX_ROWS + 1];   // first window cell of each row (+ total at [wh])
     __shared__ int s_row_x[RAY_MAX_ROWS];         // x0 | (width << 16)
     __shared__ int s_ext[4];
+    __shared__ int s_shift[1];
     if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
     const uint32_t p = alive_list[blockIdx.x];
     ext_init(s_ext);
@@ -341,6 +375,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     // every ray starts in the same cell; outside the grid nothing is emitted (ray.rs:88-92)
     if (lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh) return;
     const int cx = (int)lcx, cy = (int)lcy;
+    const int shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx, s_shift);
 
     // ---- row table of the disc window, clipped to the grid
     const int wy0 = max(0, cy - radius), wy1 = min((int)geom.gh, cy + radius + 1);
@@ -408,7 +443,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                     }
                 }
                 if (!in_window) {  // beyond the window (range larger than shared memory allows)
-                    global_cell_add(&grid[(size_t)y * geom.gh + x], inc, &saturated);
+                    global_cell_add(&grid[(size_t)y * geom.gh + phys_col(geom, (uint32_t)x, shift)], inc, &saturated);
                     ext_add(s_ext, x, y, x, y);
                     spilled++;
                 }
@@ -444,7 +479,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                         const int gx0 = (s_row_x[lo] & 0xffff) + lx;
                         exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 3);
                         eymin = min(eymin, wy0 + lo); eymax = max(eymax, wy0 + lo);
-                        gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + gx0);
+                        gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + phys_col(geom, (uint32_t)gx0, shift));
                     }
                 }
             }
@@ -468,7 +503,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
             for (int c = threadIdx.x & 31; c < w; c += 32) {
                 const uint32_t d = s_win[off + c];
                 if (d != 0u) {
-                    uint32_t* g = grid + (size_t)(wy0 + ly) * geom.gh + x0 + c;
+                    uint32_t* g = grid + (size_t)(wy0 + ly) * geom.gh + phys_col(geom, (uint32_t)(x0 + c), shift);
                     *g = cell_sat_add(*g, d, &saturated);
                     exmin = min(exmin, x0 + c); exmax = max(exmax, x0 + c);
                     eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
@@ -478,7 +513,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     }
     ext_add(s_ext, exmin, eymin, exmax, eymax);
     __syncthreads();
-    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw);
+    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, shift);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 }
@@ -520,6 +555,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
     __shared__ uint32_t s_rowb[RAY_MAX_ROWS];           // shared byte address of column x = 0 of the row
     __shared__ int s_ext[4];
+    __shared__ int s_shift[1];
     if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
     const uint32_t p = alive_list[blockIdx.x];
     ext_init(s_ext);
@@ -534,6 +570,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     const int cx0 = (int)lcx, cy0 = (int)lcy;
     const int gw = (int)geom.gw, gh = (int)geom.gh;
     const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
+    const int slot_shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx0, s_shift);
 
     // ---- row table of the disc window (x ranges aligned to 8 cells = one 128-bit group)
     const int wy0 = max(0, cy0 - radius), wy1 = min(gh, cy0 + radius + 1);
@@ -678,7 +715,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                     }
                     if (!done) {
                         const int x = (int)(x2 >> 1), y = wy0 + ly;
-                        global_cell_add(&grid[(size_t)y * geom.gh + x], CELL_OCC_INC, &saturated);
+                        global_cell_add(&grid[(size_t)y * geom.gh + phys_col(geom, (uint32_t)x, slot_shift)], CELL_OCC_INC, &saturated);
                         ext_add(s_ext, x, y, x, y);
                         spilled++;
                     }
@@ -733,7 +770,8 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                         }
                     }
                     if (!done) {
-                        global_cell_add(&grid[(size_t)y * geom.gh + x], is_free ? CELL_FREE_INC : CELL_OCC_INC, &saturated);
+                        global_cell_add(&grid[(size_t)y * geom.gh + phys_col(geom, (uint32_t)x, slot_shift)],
+                                        is_free ? CELL_FREE_INC : CELL_OCC_INC, &saturated);
                         ext_add(s_ext, x, y, x, y);
                         spilled++;
                     }
@@ -797,7 +835,8 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                             const int gx0 = (row.y & 0xffff) + 8 * g;
                             exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
                             eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
-                            gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + ly) * geom.gh + gx0);
+                            gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + ly) * geom.gh +
+                                                             phys_col(geom, (uint32_t)gx0, slot_shift));
                         }
                     }
                 }
@@ -837,7 +876,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     }
     ext_add(s_ext, exmin, eymin, exmax, eymax);
     __syncthreads();
-    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw);
+    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, slot_shift);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 }
@@ -1401,11 +1440,16 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
 // (zero outside the source extent) and stores each value to every destination of the sub-run.
 // Bytes that really moved are counted on the device and are what the roofline in bench.py uses.
 
+// All x quantities of a job are in 32-byte units on the ring of one physical grid row
+// (ring size = row units when rows rotate, unbounded otherwise): an "arc" is (start, length).
 struct alignas(16) CopyJob {
     const uint32_t* src;
-    uint32_t fan, pad;
-    int sx0, sy0, sx1, sy1;   // source extent, x in 32-byte units
-    int ux0, uy0, ux1, uy1;   // region written in every destination
+    uint32_t fan;
+    uint32_t rot;             // destination unit = (source unit + rot) & umask
+    uint32_t n_start, n_len;  // arc of every destination that receives the source's extent
+    int sy0, sy1;             // ... and its rows
+    uint32_t u_start, u_len;  // arc written in every destination (new extent + old extents to clear)
+    int uy0, uy1;             // ... and its rows
     uint32_t* dst[COPY_FAN];
 };
 static_assert(sizeof(CopyJob) % 16 == 0, "CopyJob is fetched as 16-byte pieces");
@@ -1413,16 +1457,31 @@ constexpr int COPY_JOB_V4 = (int)(sizeof(CopyJob) / 16);
 
 __device__ __forceinline__ bool meta_empty(const SlotMeta& m) { return m.x1 <= m.x0 || m.y1 <= m.y0; }
 
+// smallest arc (of those starting at either operand's start) that covers arcs a and b on the ring
+__device__ __forceinline__ void arc_cover(uint32_t& a_start, uint32_t& a_len, uint32_t b_start, uint32_t b_len,
+                                          uint32_t umask, uint32_t ring) {
+    if (b_len == 0u) return;
+    if (a_len == 0u) { a_start = b_start; a_len = b_len; return; }
+    // 64-bit: with unrotated rows the "ring" is the whole 32-bit range and the sums may exceed it
+    const unsigned long long l1 = max((unsigned long long)a_len, (unsigned long long)((b_start - a_start) & umask) + b_len);
+    const unsigned long long l2 = max((unsigned long long)b_len, (unsigned long long)((a_start - b_start) & umask) + a_len);
+    if (l2 < l1) { a_start = b_start; a_len = (uint32_t)min(l2, (unsigned long long)ring); }
+    else { a_len = (uint32_t)min(l1, (unsigned long long)ring); }
+    if (a_len >= ring) { a_start = 0u; a_len = ring; }
+}
+
 // one warp per job
 __global__ void __launch_bounds__(256)
 k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
                const unsigned long long* __restrict__ n_items, const unsigned long long* __restrict__ n_leaders,
-               CopyJob* __restrict__ jobs, StepCounters* counters) {
+               CopyJob* __restrict__ jobs, MapGeom geom, StepCounters* counters) {
     const unsigned long long n = *n_items;
     const unsigned long long nl = leaders ? *n_leaders : n;
     const unsigned long long q = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nl) return;
     const int lane = threadIdx.x & 31;
+    const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
+    const uint32_t ring = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.gw >> 3);
     const unsigned long long k = leaders ? leaders[q] : q;
     const bool have = lane < (int)COPY_FAN && k + lane < n && (leaders != nullptr || lane == 0);
     CopyItem it{};
@@ -1433,24 +1492,40 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
     SlotMeta sm{0, 0, 0, 0, 0, 0, 0, 0}, dm{0, 0, 0, 0, 0, 0, 0, 0};
     if (lane == 0) sm = *it.src_meta;
     if (lane < (int)fan) dm = *it.dst_meta;
-    int sx0 = __shfl_sync(0xffffffffu, sm.x0, 0) >> 3, sy0 = __shfl_sync(0xffffffffu, sm.y0, 0);
-    int sx1 = __shfl_sync(0xffffffffu, sm.x1, 0) >> 3, sy1 = __shfl_sync(0xffffffffu, sm.y1, 0);
-    if (sx1 <= sx0 || sy1 <= sy0) { sx0 = sy0 = sx1 = sy1 = 0; }
-    int ux0 = 0x7fffffff, uy0 = 0x7fffffff, ux1 = -1, uy1 = -1;
-    if (lane < (int)fan && !meta_empty(dm)) { ux0 = dm.x0 >> 3; uy0 = dm.y0; ux1 = dm.x1 >> 3; uy1 = dm.y1; }
-    if (lane == 0 && sx1 > sx0) { ux0 = min(ux0, sx0); uy0 = min(uy0, sy0); ux1 = max(ux1, sx1); uy1 = max(uy1, sy1); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ux0 = min(ux0, __shfl_xor_sync(0xffffffffu, ux0, o)); uy0 = min(uy0, __shfl_xor_sync(0xffffffffu, uy0, o));
-        ux1 = max(ux1, __shfl_xor_sync(0xffffffffu, ux1, o)); uy1 = max(uy1, __shfl_xor_sync(0xffffffffu, uy1, o));
+    // the destination's old extent as a physical arc
+    uint32_t o_start = 0u, o_len = 0u;
+    int oy0 = 0x7fffffff, oy1 = -1;
+    if (lane < (int)fan && !meta_empty(dm)) {
+        o_start = (phys_col(geom, (uint32_t)dm.x0, dm.ox) >> 3) & umask;
+        o_len = (uint32_t)(dm.x1 - dm.x0) >> 3;
+        oy0 = dm.y0; oy1 = dm.y1;
     }
-    if (ux1 <= ux0) { ux0 = uy0 = ux1 = uy1 = 0; }
+    // lane 0 folds the arcs (at most 17) and writes the job header
+    uint32_t u_start = 0u, u_len = 0u, n_start = 0u, n_len = 0u, rot = 0u;
+    int uy0 = 0x7fffffff, uy1 = -1, sy0 = 0, sy1 = 0;
+    if (lane == 0 && !meta_empty(sm)) {
+        const uint32_t s_start = (phys_col(geom, (uint32_t)sm.x0, sm.ox) >> 3) & umask;
+        n_len = (uint32_t)(sm.x1 - sm.x0) >> 3;
+        n_start = (phys_col(geom, (uint32_t)sm.x0, align_shift(geom, sm.x0)) >> 3) & umask;   // page-aligned
+        rot = (n_start - s_start) & umask;
+        sy0 = sm.y0; sy1 = sm.y1;
+        u_start = n_start; u_len = n_len; uy0 = sy0; uy1 = sy1;
+    }
+    for (uint32_t f = 0; f < fan; ++f) {
+        const uint32_t bs = __shfl_sync(0xffffffffu, o_start, (int)f), bl = __shfl_sync(0xffffffffu, o_len, (int)f);
+        const int by0 = __shfl_sync(0xffffffffu, oy0, (int)f), by1 = __shfl_sync(0xffffffffu, oy1, (int)f);
+        if (lane == 0) {
+            arc_cover(u_start, u_len, bs, bl, umask, ring);
+            if (bl) { uy0 = min(uy0, by0); uy1 = max(uy1, by1); }
+        }
+    }
     CopyJob* job = jobs + q;
     if (lane < (int)COPY_FAN) job->dst[lane] = lane < (int)fan ? it.dst : nullptr;
     if (lane == 0) {
-        job->src = it.src; job->fan = fan; job->pad = 0;
-        job->sx0 = sx0; job->sy0 = sy0; job->sx1 = sx1; job->sy1 = sy1;
-        job->ux0 = ux0; job->uy0 = uy0; job->ux1 = ux1; job->uy1 = uy1;
+        if (u_len == 0u || uy1 <= uy0) { u_start = u_len = 0u; uy0 = uy1 = 0; }
+        job->src = it.src; job->fan = fan; job->rot = rot;
+        job->n_start = n_start; job->n_len = n_len; job->sy0 = sy0; job->sy1 = sy1;
+        job->u_start = u_start; job->u_len = u_len; job->uy0 = uy0; job->uy1 = uy1;
         if (uy1 > uy0) atomicMax(&counters->copy_max_rows, (unsigned long long)(uy1 - uy0));
     }
 }
@@ -1462,7 +1537,7 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
 template <int UNROLL, int MINB>
 __global__ void __launch_bounds__(COPY_THREADS, MINB)
 k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restrict__ n_jobs,
-             uint32_t row_units /* 32-byte units per physical grid row */, uint32_t items_per_cta,
+             uint32_t row_units /* 32-byte units per physical grid row */, uint32_t umask, uint32_t items_per_cta,
              StepCounters* counters) {
     __shared__ CopyJob s_job;
     __shared__ unsigned long long s_moved;
@@ -1488,20 +1563,21 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
             if (wn < total) next_job = reinterpret_cast<const uint4*>(jobs + (uint32_t)wn / bands)[threadIdx.x];
         }
         __syncthreads();
-        const int ux0 = s_job.ux0, uy0 = s_job.uy0, ux1 = s_job.ux1, uy1 = s_job.uy1;
+        const int uy0 = s_job.uy0, uy1 = s_job.uy1;
         const int rows = uy1 - uy0;
         if (rows <= 0) continue;
         const int rows_per_band = (rows + (int)bands - 1) / (int)bands;
         const int r0 = uy0 + (int)band * rows_per_band, r1 = min(uy1, r0 + rows_per_band);
         if (r0 >= r1) continue;
-        const int sx0 = s_job.sx0, sy0 = s_job.sy0, sx1 = s_job.sx1, sy1 = s_job.sy1;
+        const uint32_t u_start = s_job.u_start, uw = s_job.u_len;
+        const uint32_t n_start = s_job.n_start, n_len = s_job.n_len, rot = s_job.rot;
+        const int sy0 = s_job.sy0, sy1 = s_job.sy1;
         const uint32_t fan = s_job.fan;
-        const uint32_t uw = (uint32_t)(ux1 - ux0);
         const uint32_t count = (uint32_t)(r1 - r0) * uw;
         const V8* src = reinterpret_cast<const V8*>(s_job.src);
         for (uint32_t base = threadIdx.x; base < count; base += COPY_THREADS * UNROLL) {
             V8 v[UNROLL];
-            uint32_t off[UNROLL];   // unit offset inside a grid (< 2^28)
+            uint32_t off[UNROLL];   // unit offset inside a destination grid (< 2^28)
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const uint32_t i = base + u * COPY_THREADS;
@@ -1509,9 +1585,13 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
                 v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
                 if (i < count) {
                     const uint32_t rr = i / uw;
-                    const int ey = r0 + (int)rr, ex = ux0 + (int)(i - rr * uw);
-                    off[u] = (uint32_t)ey * row_units + (uint32_t)ex;
-                    if (ex >= sx0 && ex < sx1 && ey >= sy0 && ey < sy1) { v[u] = ld_stream_v8(src + off[u]); moved++; }
+                    const int ey = r0 + (int)rr;
+                    const uint32_t du = (u_start + (i - rr * uw)) & umask;     // destination unit on the ring
+                    off[u] = (uint32_t)ey * row_units + du;
+                    if (((du - n_start) & umask) < n_len && ey >= sy0 && ey < sy1) {
+                        v[u] = ld_stream_v8(src + ((uint32_t)ey * row_units + ((du - rot) & umask)));
+                        moved++;
+                    }
                 }
             }
             for (uint32_t f = 0; f < fan; ++f) {
@@ -1532,31 +1612,35 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
 
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
                        const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t max_items,
-                       void* jobs, uint32_t row_cells, StepCounters* counters, int num_sms) {
+                       void* jobs, MapGeom geom, StepCounters* counters, int num_sms) {
     const uint32_t blocks = (max_items + 7u) / 8u;
-    k_copy_prepare<<<blocks ? blocks : 1, 256, 0, stream>>>(items, leaders, n_items, n_leaders, (CopyJob*)jobs, counters);
-    // measured on B200 (tools/tune_copy.sh, gpurun_out/tune_copy4.log): 4 loads in flight per thread,
-    // 3 CTAs per SM resident, grid oversubscribed 32x per SM for balance, ~6 items per CTA
+    k_copy_prepare<<<blocks ? blocks : 1, 256, 0, stream>>>(items, leaders, n_items, n_leaders, (CopyJob*)jobs, geom, counters);
+    // measured on B200 (gpurun_out/tune_copy4.log): 4 loads in flight per thread, 3 CTAs per SM
+    // resident, grid oversubscribed 32x per SM for balance, ~6 items per CTA
+    const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
     k_copy_boxed<4, 3><<<num_sms * COPY_CTAS_PER_SM, COPY_THREADS, 0, stream>>>(
-        (const CopyJob*)jobs, leaders ? n_leaders : n_items, row_cells / 8u, 6u, counters);
+        (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom.gw / 8u, umask, 6u, counters);
 }
 size_t copy_job_bytes() { return sizeof(CopyJob); }
 
 __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigned long long* __restrict__ n_items,
-                               StepCounters* counters, StepRecord* record) {
+                               MapGeom geom, bool realign, StepCounters* counters, StepRecord* record) {
     const unsigned long long n = *n_items;
     for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
-         k += (unsigned long long)gridDim.x * blockDim.x)
-        *items[k].dst_meta = *items[k].src_meta;   // sources are never destinations of the same launch
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        SlotMeta m = *items[k].src_meta;   // sources are never destinations of the same launch
+        if (realign && m.x1 > m.x0) m.ox = align_shift(geom, m.x0);   // the rotation k_copy_prepare chose
+        *items[k].dst_meta = m;
+    }
     if (record && blockIdx.x == 0 && threadIdx.x == 0) {
         record->copy_bytes = counters->copy_bytes;
         record->n_alive = counters->n_alive;
     }
 }
 void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,
-                         StepCounters* counters, StepRecord* record) {
+                         MapGeom geom, bool realign, StepCounters* counters, StepRecord* record) {
     const uint32_t blocks = (max_items + 255u) / 256u;
-    k_commit_boxes<<<blocks ? blocks : 1, 256, 0, stream>>>(items, n_items, counters, record);
+    k_commit_boxes<<<blocks ? blocks : 1, 256, 0, stream>>>(items, n_items, geom, realign, counters, record);
 }
 
 __global__ void k_account_full_copy(const unsigned long long* n_items, const unsigned long long* n_leaders,
@@ -1583,29 +1667,30 @@ template <> __device__ __forceinline__ uint8_t export_value<uint8_t>(double p) {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_export(const uint32_t* __restrict__ cells, size_t cells_per_grid, const StepCounters* __restrict__ counters,
-         uint32_t grid_w, int4 win /* x0, y0, x1, y1 */, T* __restrict__ out) {
+k_export(const uint32_t* __restrict__ cells, const SlotMeta* __restrict__ meta, size_t cells_per_grid,
+         const StepCounters* __restrict__ counters, MapGeom geom, int4 win /* x0, y0, x1, y1 */, T* __restrict__ out) {
     const long long slot = counters->est_slot;
     if (slot < 0) return;  // another GPU owns the estimate
     const uint32_t* grid = cells + (size_t)slot * cells_per_grid;
+    const int shift = meta[slot].ox;
     const uint32_t ww = (uint32_t)(win.z - win.x), wh = (uint32_t)(win.w - win.y);
     const uint32_t n = ww * wh;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t ry = i / ww, rx = i - ry * ww;
-        const uint32_t cell = grid[(size_t)(win.y + ry) * grid_w + (win.x + rx)];
+        const uint32_t cell = grid[(size_t)(win.y + ry) * geom.gw + phys_col(geom, (uint32_t)win.x + rx, shift)];
         // a never-informed cell is exactly the prior: log-odds 0 -> 1 - 1/(1 + exp(0)) = 0.5
         out[i] = export_value<T>(cell == 0u ? 0.5 : log_odds_probability(cell_log_odds(cell)));  // Map::likelihood
     }
 }
 
-void launch_export(cudaStream_t stream, const uint32_t* cells, size_t cells_per_grid, const StepCounters* counters,
-                   uint32_t grid_w, int x0, int y0, int x1, int y1, int format, void* out) {
+void launch_export(cudaStream_t stream, const uint32_t* cells, const SlotMeta* meta, size_t cells_per_grid,
+                   const StepCounters* counters, MapGeom geom, int x0, int y0, int x1, int y1, int format, void* out) {
     const uint32_t n = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
     const int blocks = (int)max(1u, min((n + 255u) / 256u, 148u * 8u));
     const int4 win = make_int4(x0, y0, x1, y1);
-    if (format == 1) k_export<float><<<blocks, 256, 0, stream>>>(cells, cells_per_grid, counters, grid_w, win, (float*)out);
-    else if (format == 2) k_export<uint8_t><<<blocks, 256, 0, stream>>>(cells, cells_per_grid, counters, grid_w, win, (uint8_t*)out);
-    else k_export<double><<<blocks, 256, 0, stream>>>(cells, cells_per_grid, counters, grid_w, win, (double*)out);
+    if (format == 1) k_export<float><<<blocks, 256, 0, stream>>>(cells, meta, cells_per_grid, counters, geom, win, (float*)out);
+    else if (format == 2) k_export<uint8_t><<<blocks, 256, 0, stream>>>(cells, meta, cells_per_grid, counters, geom, win, (uint8_t*)out);
+    else k_export<double><<<blocks, 256, 0, stream>>>(cells, meta, cells_per_grid, counters, geom, win, (double*)out);
 }
 
 // informed extent of the estimate's grid (empty -> 0,0,0,0)
@@ -1620,14 +1705,24 @@ void launch_estimate_extent(cudaStream_t stream, const SlotMeta* meta, const Ste
     k_estimate_extent<<<1, 1, 0, stream>>>(meta, counters, out4);
 }
 
+// one slot's grid in logical order (the row rotation undone)
 __global__ void __launch_bounds__(256)
-k_export_log_odds(const uint32_t* __restrict__ grid, uint32_t n_cells, double* __restrict__ out) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += gridDim.x * blockDim.x)
-        out[i] = cell_log_odds(grid[i]);
+k_export_slot(const uint32_t* __restrict__ grid, const SlotMeta* __restrict__ slot_meta, MapGeom geom, bool as_log_odds,
+              void* __restrict__ out) {
+    const int shift = slot_meta->ox;
+    const uint32_t n = geom.gw * geom.gh;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t y = i / geom.gw, x = i - y * geom.gw;
+        const uint32_t cell = grid[(size_t)y * geom.gw + phys_col(geom, x, shift)];
+        if (as_log_odds) reinterpret_cast<double*>(out)[i] = cell_log_odds(cell);
+        else reinterpret_cast<uint32_t*>(out)[i] = cell;
+    }
 }
-void launch_export_log_odds(cudaStream_t stream, const uint32_t* grid, uint32_t n_cells, double* out) {
-    const int blocks = (int)min((n_cells + 255u) / 256u, 148u * 8u);
-    k_export_log_odds<<<blocks, 256, 0, stream>>>(grid, n_cells, out);
+void launch_export_slot(cudaStream_t stream, const uint32_t* grid, const SlotMeta* slot_meta, MapGeom geom,
+                        bool as_log_odds, void* out) {
+    const uint32_t n = geom.gw * geom.gh;
+    const int blocks = (int)min((n + 255u) / 256u, 148u * 8u);
+    k_export_slot<<<blocks, 256, 0, stream>>>(grid, slot_meta, geom, as_log_odds, out);
 }
 
 // =============================================================================== init

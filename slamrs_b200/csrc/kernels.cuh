@@ -61,7 +61,8 @@ struct ScanDevice {
 // maps the pool sees the extents of the grids it pulls.
 struct alignas(32) SlotMeta {
     int x0, y0, x1, y1;
-    int ox, oy;          // reserved: origin of a windowed slot inside the logical grid (0, 0 today)
+    int ox;              // row rotation: logical column x lives at physical column (x + ox) & xmask (MapGeom)
+    int oy;              // reserved
     int pad0, pad1;
 };
 static_assert(sizeof(SlotMeta) == 32, "SlotMeta is read by peers as 32 bytes");
@@ -76,7 +77,7 @@ struct CopyItem {
 // ---- launch wrappers (all asynchronous on `stream`) ----
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
                               const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
-                              size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
+                              const SlotMeta* meta, size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
                               const double* term_table /* LK_TABLE_NF x LK_TABLE_NO, launch_fill_term_table */,
                               ParticleResult* const* peer_results /* null: no fused exchange */,
@@ -143,10 +144,12 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
                  int num_sms);
 
 // format: 0 = f64, 1 = f32, 2 = u8; [x0, x1) x [y0, y1) is the exported window of the grid
-void launch_export(cudaStream_t stream, const uint32_t* cells, size_t cells_per_grid, const StepCounters* counters,
-                   uint32_t grid_w, int x0, int y0, int x1, int y1, int format, void* out);
+void launch_export(cudaStream_t stream, const uint32_t* cells, const SlotMeta* meta, size_t cells_per_grid,
+                   const StepCounters* counters, MapGeom geom, int x0, int y0, int x1, int y1, int format, void* out);
 void launch_estimate_extent(cudaStream_t stream, const SlotMeta* meta, const StepCounters* counters, int* out4);
-void launch_export_log_odds(cudaStream_t stream, const uint32_t* grid, uint32_t n_cells, double* out);
+// one slot's grid in logical order: f64 log-odds (as_log_odds) or the raw packed counters
+void launch_export_slot(cudaStream_t stream, const uint32_t* grid, const SlotMeta* slot_meta, MapGeom geom,
+                        bool as_log_odds, void* out);
 
 void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
                        StepCounters* counters, uint32_t rank, SlotMeta* meta);
@@ -155,13 +158,15 @@ void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, 
 // destination slot's previous content that the source does not cover is cleared
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
                        const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t max_items,
-                       void* jobs /* max_items * copy_job_bytes() of scratch */, uint32_t row_cells,
+                       void* jobs /* max_items * copy_job_bytes() of scratch */, MapGeom geom,
                        StepCounters* counters, int num_sms);
 size_t copy_job_bytes();
 // after a copy kernel: every destination slot now has its source's extent. With `record` the
 // step's moved bytes are also written into the history ring (last copy launch of a step).
+// `realign`: the destination's rotation is the page-aligning one the extent copy used; otherwise
+// (whole-grid copies move rows verbatim) it is the source's
 void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,
-                         StepCounters* counters, StepRecord* record);
+                         MapGeom geom, bool realign, StepCounters* counters, StepRecord* record);
 // add the bytes of a full-grid copy launch to counters->copy_bytes
 void launch_account_full_copy(cudaStream_t stream, const unsigned long long* n_items, const unsigned long long* n_leaders,
                               size_t bytes_per_grid, StepCounters* counters);

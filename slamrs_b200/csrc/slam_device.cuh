@@ -67,7 +67,27 @@ __device__ __forceinline__ long long f32_as_isize(float v) {
 struct MapGeom {
     float pos_x, pos_y, res;
     uint32_t gw, gh;
+    // Row rotation of a grid slot. A slot stores logical column x at physical column
+    // (x + shift) & xmask, `shift` per slot (SlotMeta::ox, a multiple of 8 cells). The resampler picks
+    // the shift of every grid it writes so that the informed extent starts on a page_cells boundary
+    // (1 KiB of cells): a ~250-cell-wide extent then occupies one DRAM page per row instead of
+    // straddling two, which is worth 15 % of copy bandwidth (profiles/, tune logs). Needs a
+    // power-of-two width; otherwise xmask = 0xffffffff, page_cells = 0 and every shift is 0.
+    uint32_t xmask, page_cells;
 };
+__host__ __device__ inline MapGeom make_map_geom(float pos_x, float pos_y, float res, uint32_t gw, uint32_t gh) {
+    MapGeom g;
+    g.pos_x = pos_x; g.pos_y = pos_y; g.res = res; g.gw = gw; g.gh = gh;
+    const bool rot = gw >= 256u && (gw & (gw - 1u)) == 0u;
+    g.xmask = rot ? gw - 1u : 0xffffffffu;
+    g.page_cells = rot ? 256u : 0u;
+    return g;
+}
+// shift that puts logical column x0 (a multiple of 8) on a page boundary
+__host__ __device__ inline int align_shift(const MapGeom& g, int x0) {
+    return g.page_cells ? (int)((0u - (uint32_t)x0) & (g.page_cells - 1u)) : 0;
+}
+__host__ __device__ inline uint32_t phys_col(const MapGeom& g, uint32_t x, int shift) { return (x + (uint32_t)shift) & g.xmask; }
 
 // Map::world_to_grid, map.rs:60-62
 __device__ __forceinline__ float world_to_grid(float w, float pos, float res) {

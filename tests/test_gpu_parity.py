@@ -192,6 +192,26 @@ def test_step_parity_robot_near_border(oracle):
     lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 4))
 
 
+@COPY_MODES
+def test_step_parity_rotated_rows_wrap_around(oracle, copy_flags):
+    """Power-of-two grid (rows of a slot are stored rotated so that extents start on a DRAM page) with
+    the robot a few cells from the left border: informed extents start at column 0, grow, and their
+    physical image wraps around the row; particles are re-scattered so that slots change tenants."""
+    cfg = GridMapSlamConfig(position=(-0.4, -2.56), width=5.12, height=5.12, resolution=0.02, n_particles=24)
+    assert S.grid_cells(5.12, 0.02) == 256
+    scans = make_scans(1.0, 360, 1.0, 6)
+    rng = np.random.default_rng(5)
+
+    def scatter(step, gpu, osl):
+        if step in (2, 4):
+            xyt = np.column_stack([rng.uniform(-0.3, 3.5, 24), rng.uniform(-2.0, 2.0, 24),
+                                   rng.uniform(-np.pi, np.pi, 24)]).astype(np.float32)
+            gpu.set_poses(xyt); osl.set_poses(xyt)
+
+    errs = lockstep(oracle, cfg, scans, flags=copy_flags, pre_step=scatter)
+    print(errs[-1])
+
+
 def test_pose_outside_grid_emits_nothing(oracle):
     cfg = GridMapSlamConfig(position=(5.0, 5.0), width=1.0, height=1.0, resolution=0.02, n_particles=4)
     lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 2))
