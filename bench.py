@@ -367,6 +367,7 @@ def run_cuda(args, wl, rank, world, local):
                                  "(grids written + source grids read); whole_grid_bytes_per_launch is what Map::clone "
                                  "semantics would move for the same copies",
             "step_frac": (copy_bytes / (ms_value * 1e-3) / 1e9) / peak if peak else None,
+            "bytes_per_launch_by_step": [float(v) for v in hist[:, 5]],
         },
         "phases_ms_per_step": {k: float(tmax[3 + i]) / K for i, k in enumerate(_lib.PHASES)},
         "resample": {"grids_copied_per_step_all_gpus": float(tot[0] / K), "grids_pulled_per_step_all_gpus": float(tot[1] / K),
@@ -418,8 +419,8 @@ def run_cuda(args, wl, rank, world, local):
 
 
 def ncu_traffic(bytes_per_launch):
-    """DRAM bytes per launch of k_copy from the committed ncu --set full capture
-    (profiles/copy_traffic.json holds dram bytes per algorithmic byte of that capture)."""
+    """DRAM bytes per launch of the copy kernel from the committed ncu --set full capture
+    (profiles/copy_traffic.json holds dram bytes per device-counted byte of that capture)."""
     path = os.path.join(ROOT, "profiles", "copy_traffic.json")
     if not os.path.exists(path):
         return None

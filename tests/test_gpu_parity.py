@@ -212,6 +212,24 @@ def test_step_parity_rotated_rows_wrap_around(oracle, copy_flags):
     print(errs[-1])
 
 
+def test_c5_shape(oracle):
+    """configs[4] shape at reduced particle count: 720 beams at 0.5 degree spacing, 2048 x 2048 grid at
+    5 cm (102.4 m), 6 m range, global-localisation-style uniform initial poses over the 20 m room."""
+    cfg = GridMapSlamConfig(position=(-51.2, -51.2), width=102.4, height=102.4, resolution=0.05, n_particles=20)
+    assert S.grid_cells(102.4, 0.05) == 2048
+    scans = make_scans(10.0, 720, 6.0, 3)
+    rng = np.random.default_rng(42)
+    init = np.column_stack([rng.uniform(-9.0, 9.0, 20), rng.uniform(-9.0, 9.0, 20),
+                            rng.uniform(-np.pi, np.pi, 20)]).astype(np.float32)
+
+    def uniform_init(step, gpu, osl):
+        if step == 0:
+            gpu.set_poses(init); osl.set_poses(init)
+
+    errs = lockstep(oracle, cfg, scans, particles=[0, 7, 19], pre_step=uniform_init)
+    print(errs[-1])
+
+
 def test_pose_outside_grid_emits_nothing(oracle):
     cfg = GridMapSlamConfig(position=(5.0, 5.0), width=1.0, height=1.0, resolution=0.02, n_particles=4)
     lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 2))
