@@ -264,6 +264,21 @@ def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2
         slam.sync()
         barrier()
         out["ms_e2e"] = e0.elapsed_time(e1)
+        # the same loop with the cheaper read-out a visualizer needs: informed window only, f32
+        pinned32 = torch.empty(slam.grid_w * slam.grid_h, dtype=torch.float32).pin_memory().numpy()
+        barrier()
+        e0.record(stream)
+        win_bytes = 0
+        for obs, odo in scans[W + 2 * K:W + 3 * K]:   # the trajectory continues: fresh scans
+            slam.update(obs, odo)
+            slam.estimated_pose()
+            _, w = slam.estimated_likelihood_window(out=pinned32)
+            win_bytes += w.nbytes
+        e1.record(stream)
+        slam.sync()
+        barrier()
+        out["ms_e2e_window"] = e0.elapsed_time(e1)
+        out["e2e_window_bytes"] = win_bytes / max(1, K)
     slam.close()
     return out
 
@@ -294,7 +309,7 @@ def run_cuda(args, wl, rank, world, local):
     n_total = wl.n_particles * world
     K, W = args.steps, args.warmup
     sim = wl.simulator()
-    scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(W + 2 * K)]
+    scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(W + 3 * K)]
 
     clocks = ClockSampler(local)
     clocks.start()
@@ -326,7 +341,7 @@ def run_cuda(args, wl, rank, world, local):
 
     ph = main["phase_ms"]
     tmax = reduce_max([main["ms_value"], main.get("ms_e2e", 0.0), strict["ms_value"] if strict else 0.0] +
-                      [ph[k] for k in _lib.PHASES] + [full["ms_value"] if full else 0.0])
+                      [ph[k] for k in _lib.PHASES] + [full["ms_value"] if full else 0.0, main.get("ms_e2e_window", 0.0)])
     hist = main["hist"]
     tot = reduce_sum([hist[:, 0].sum(), hist[:, 1].sum(), hist[:, 4].sum()])
     if rank != 0:
@@ -381,6 +396,12 @@ def run_cuda(args, wl, rank, world, local):
         line["e2e"] = {"value": pbu * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
                        "h2d_bytes_per_step": int(wl.n_beams * (4 + 4 + 1)), "d2h_bytes_per_step": int(12 + 8 * gw * gh),
                        "path": "update(host scan) + estimated_pose() + estimated_likelihood() per step (node.rs:47-60)"}
+        ms_win = float(tmax[4 + len(_lib.PHASES)])
+        line["e2e_window_readout"] = {
+            "value": pbu * K / (ms_win * 1e-3), "unit": UNIT, "ms_per_step": ms_win / K,
+            "d2h_bytes_per_step": int(12 + 16 + main["e2e_window_bytes"]),
+            "path": "update(host scan) + estimated_pose() + map_extent() + map_window(f32) per step: the informed "
+                    "window of the map instead of 8 B/cell of the whole grid (SURVEY.md 8(f)3)"}
     if full:
         ms_full = float(tmax[3 + len(_lib.PHASES)])
         fh, fph = full["hist"], full["phase_ms"]

@@ -89,6 +89,8 @@ struct slamrs_gpu_handle {
     double prof_ms[SLAMRS_PHASE_COUNT] = {0, 0, 0, 0, 0, 0, 0};
     uint64_t prof_steps = 0;
     uint64_t step = 0;
+    bool counters_fresh = false;   // h_counters mirrors d_counters (no step issued since the last fetch)
+    bool est_box_stale = false;    // set_cells changed a grid after the step recorded the estimate's extent
     uint64_t launches = 0;
     uint64_t window_cells = 0;
     std::string last_error;
@@ -304,9 +306,13 @@ int step_barrier(slamrs_gpu_handle* h) {
     return SLAMRS_OK;
 }
 
+// Host copy of the device counters. They only change when a step is issued, so one fetch (with its
+// stream synchronisation) serves every read-out that follows the same step.
 int fetch_counters(slamrs_gpu_handle* h) {
+    if (h->counters_fresh) return SLAMRS_OK;
     CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(StepCounters), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->counters_fresh = true;
     return SLAMRS_OK;
 }
 
@@ -681,6 +687,8 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     CU_TRY(h, cudaGetLastError());
     h->cur = nxt;
     h->step++;
+    h->counters_fresh = false;
+    h->est_box_stale = false;
     return SLAMRS_OK;
 }
 
@@ -753,6 +761,12 @@ int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells) {
 int slamrs_gpu_map_extent(slamrs_gpu_handle* h, int32_t out_x0y0x1y1[4]) {
     if (!h || !out_x0y0x1y1) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
+    if (h->world == 1 && h->step > 0 && !h->est_box_stale) {   // the step left the extent of the published map in the counters
+        int rc = fetch_counters(h);
+        if (rc) return rc;
+        for (int i = 0; i < 4; ++i) out_x0y0x1y1[i] = h->h_counters->est_box[i];
+        return SLAMRS_OK;
+    }
     cudaStream_t s = h->stream;
     int* d4 = reinterpret_cast<int*>(h->d_export);
     launch_estimate_extent(s, h->d_meta, h->d_counters, d4);
@@ -991,6 +1005,7 @@ int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t
     SlotMeta m{0, 0, 0, 0, 0, 0, 0, 0};
     if (x1 >= 0) { m.x0 = x0 & ~7; m.y0 = y0; m.x1 = std::min(gw, (x1 + 8) & ~7); m.y1 = y1 + 1; }
     CU_TRY(h, cudaMemcpyAsync(h->d_meta + slot, &m, sizeof(m), cudaMemcpyHostToDevice, h->stream));
+    h->est_box_stale = true;
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return SLAMRS_OK;
 }

@@ -1272,12 +1272,18 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     // ---- the copy list. run_first = first position of the current source's run in this range.
     const uint32_t pos_start = pos;
     uint32_t n_lead_c = 0;
+    const unsigned long long est_m = a.counters->max_particle - lo;   // >= S when another rank owns the estimate
+    if (t == 0 && est_m >= S) a.counters->est_meta_ptr = 0ull;
     uint32_t run_first = c0 < c1 ? lower_bound_u32(idx_l, 0, S, idx_l[c0]) : 0u;
     for (uint32_t m = c0; m < c1; ++m) {
         const int cls = need[m];
         const uint32_t src = idx_l[m];
         if (m > c0 && idx_l[m - 1] != src) run_first = m;
-        if (cls == 0) continue;
+        if (cls == 0) {
+            // the published map (slam.rs:83-88) is this particle's grid: it stays in place
+            if (m == est_m) a.counters->est_meta_ptr = (unsigned long long)(uintptr_t)(a.meta + slot_new[m]);
+            continue;
+        }
         if (pos < usable) {
             const int32_t dslot = free_list[pos];
             slot_new[m] = dslot;
@@ -1295,6 +1301,7 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
             it.dst_meta = a.meta + dslot;
             a.copies[pos] = it;
+            if (m == est_m) a.counters->est_meta_ptr = (unsigned long long)(uintptr_t)it.src_meta;   // extent it will have
             // a local run keeps its first use in place, so its copies start one position later
             const uint32_t k = (cls == 1) ? (m - run_first - 1u) : (m - run_first);
             const bool lead = (k % COPY_FAN) == 0u;
@@ -1635,6 +1642,15 @@ __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigne
     if (record && blockIdx.x == 0 && threadIdx.x == 0) {
         record->copy_bytes = counters->copy_bytes;
         record->n_alive = counters->n_alive;
+        // informed extent of the published map, for the windowed read-out (sources are not written here)
+        const SlotMeta* em = reinterpret_cast<const SlotMeta*>((uintptr_t)counters->est_meta_ptr);
+        if (em == nullptr) { counters->est_box[0] = counters->est_box[1] = counters->est_box[2] = counters->est_box[3] = -1; }
+        else {
+            const SlotMeta m = *em;
+            const bool empty = m.x1 <= m.x0 || m.y1 <= m.y0;
+            counters->est_box[0] = empty ? 0 : m.x0; counters->est_box[1] = empty ? 0 : m.y0;
+            counters->est_box[2] = empty ? 0 : m.x1; counters->est_box[3] = empty ? 0 : m.y1;
+        }
     }
 }
 void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,

@@ -33,6 +33,8 @@ struct StepCounters {
     unsigned long long copy_bytes;       // bytes read + written by the copy kernels this step
     unsigned long long copy_max_rows;    // tallest region any copy job of this step writes (rows)
     unsigned long long barrier_timeout;  // a peer barrier gave up waiting (error)
+    unsigned long long est_meta_ptr;     // SlotMeta whose extent the published map has after this step (0: remote)
+    int est_box[4];                      // that extent {x0, y0, x1, y1}; -1 when another rank owns the estimate
     double sum;                          // sum of raw weights (particle.rs:50)
     double n_eff;                        // 1 / sum of squared normalised weights (particle.rs:59-65)
     float est_pose[3];                   // estimated_pose(), slam.rs:77-81

@@ -230,12 +230,19 @@ class GridMapSlam:
         _lib.check(self._L.slamrs_gpu_map_extent(self._h, _ptr(out)), self._h)
         return tuple(int(v) for v in out)
 
-    def estimated_likelihood_window(self, window=None, fmt: int = _lib.MAP_F32) -> tuple:
+    def estimated_likelihood_window(self, window=None, fmt: int = _lib.MAP_F32, out: Optional[np.ndarray] = None) -> tuple:
         """((x0, y0, x1, y1), array[y1-y0, x1-x0]) of the estimate's map in f64 / f32 / u8; the default
-        window is the informed extent -- every cell outside it is exactly 0.5."""
+        window is the informed extent -- every cell outside it is exactly 0.5. `out`: a flat buffer of
+        the right dtype to fill (e.g. pinned host memory), at least window-sized."""
         x0, y0, x1, y1 = window if window is not None else self.map_extent()
         dt = {_lib.MAP_F64: np.float64, _lib.MAP_F32: np.float32, _lib.MAP_U8: np.uint8}[fmt]
-        out = np.empty((max(0, y1 - y0), max(0, x1 - x0)), dt)
+        shape = (max(0, y1 - y0), max(0, x1 - x0))
+        if out is not None:
+            if out.dtype != dt or out.size < shape[0] * shape[1]:
+                raise ValueError("out buffer has the wrong dtype or is too small")
+            out = out.reshape(-1)[:shape[0] * shape[1]].reshape(shape)
+        else:
+            out = np.empty(shape, dt)
         if out.size:
             _lib.check(self._L.slamrs_gpu_map_window(self._h, fmt, x0, y0, x1, y1, _ptr(out)), self._h)
         return (x0, y0, x1, y1), out
