@@ -226,6 +226,9 @@ int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint3
 /* current generation, this rank's shard: n_local * {x, y, theta} */
 int slamrs_gpu_get_poses(slamrs_gpu_handle* h, float* out_xyt);
 int slamrs_gpu_set_poses(slamrs_gpu_handle* h, const float* xyt);
+/* the resampler's bookkeeping: physical grid slot of every local particle (n_local entries) and the
+ * list of spare slots (*out_n_spare entries; pass a buffer of spare_slots entries, or NULL) */
+int slamrs_gpu_get_slots(slamrs_gpu_handle* h, int32_t* out_slot_of, int32_t* out_spare, uint32_t* out_n_spare);
 /* last step, all N particles in pre-resample order: normalised and raw (un-normalised) weights */
 int slamrs_gpu_get_weights(slamrs_gpu_handle* h, double* out_norm, double* out_raw);
 /* last step's resample source index for every new particle (N entries) and the stored argmax */

@@ -107,6 +107,7 @@ extern "C" {
     pub fn slamrs_gpu_get_step_history(h: *mut slamrs_gpu_handle, first_step: u64, count: u32, out_values: *mut u64) -> c_int;
     pub fn slamrs_gpu_get_poses(h: *mut slamrs_gpu_handle, out_xyt: *mut f32) -> c_int;
     pub fn slamrs_gpu_set_poses(h: *mut slamrs_gpu_handle, xyt: *const f32) -> c_int;
+    pub fn slamrs_gpu_get_slots(h: *mut slamrs_gpu_handle, out_slot_of: *mut i32, out_spare: *mut i32, out_n_spare: *mut u32) -> c_int;
     pub fn slamrs_gpu_get_weights(h: *mut slamrs_gpu_handle, out_norm: *mut f64, out_raw: *mut f64) -> c_int;
     pub fn slamrs_gpu_get_resample_indices(h: *mut slamrs_gpu_handle, out_idx: *mut u32) -> c_int;
     pub fn slamrs_gpu_get_max_particle(h: *mut slamrs_gpu_handle, out: *mut u64) -> c_int;

@@ -920,6 +920,18 @@ int slamrs_gpu_get_poses(slamrs_gpu_handle* h, float* out_xyt) {
     return SLAMRS_OK;
 }
 
+int slamrs_gpu_get_slots(slamrs_gpu_handle* h, int32_t* out_slot_of, int32_t* out_spare, uint32_t* out_n_spare) {
+    if (!h) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    if (out_slot_of)
+        CU_TRY(h, cudaMemcpyAsync(out_slot_of, h->d_slot[h->cur], sizeof(int32_t) * h->n_local, cudaMemcpyDeviceToHost, h->stream));
+    if (out_spare && h->n_spare)
+        CU_TRY(h, cudaMemcpyAsync(out_spare, h->d_spare, sizeof(int32_t) * h->n_spare, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (out_n_spare) *out_n_spare = h->n_spare;
+    return SLAMRS_OK;
+}
+
 int slamrs_gpu_set_poses(slamrs_gpu_handle* h, const float* xyt) {
     if (!h || !xyt) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);

@@ -328,6 +328,14 @@ class GridMapSlam:
         _lib.check(self._L.slamrs_gpu_get_poses(self._h, _ptr(out)), self._h)
         return out
 
+    def slots(self):
+        """(slot_of[n_local], spare[n_spare]): the resampler's slot table and spare list."""
+        n = C.c_uint32(0)
+        _lib.check(self._L.slamrs_gpu_get_slots(self._h, None, None, C.byref(n)), self._h)
+        slot_of = np.zeros(self.n_local, np.int32); spare = np.zeros(int(n.value), np.int32)
+        _lib.check(self._L.slamrs_gpu_get_slots(self._h, _ptr(slot_of), _ptr(spare) if spare.size else None, C.byref(n)), self._h)
+        return slot_of, spare
+
     def set_poses(self, xyt) -> None:
         a = np.ascontiguousarray(xyt, np.float32).reshape(self.n_local, 3)
         _lib.check(self._L.slamrs_gpu_set_poses(self._h, _ptr(a)), self._h)
