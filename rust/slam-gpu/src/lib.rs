@@ -110,6 +110,32 @@ impl GridMapSlam {
     }
 
     pub fn map_position(&self) -> Vector2<f32> { self.position }
+
+    /// ParticleFilter::number_of_effective_particles (particle.rs:59-65) of the last update's
+    /// normalised weights, before resampling reset them to 1/N.
+    pub fn number_of_effective_particles(&self) -> f64 {
+        let mut v = 0f64;
+        unsafe { sys::slamrs_gpu_effective_particles(self.h, &mut v) };
+        v
+    }
+
+    /// The informed window of the published map as f32 grey levels: `(x0, y0, x1, y1)` in cells and
+    /// `(y1 - y0) * (x1 - x0)` values, row-major. Every cell outside the window is exactly 0.5.
+    /// What the visualizer needs (baseui/src/node/visualize.rs:245-256) at 1/100 of the bytes of
+    /// `estimated_likelihood()`.
+    pub fn estimated_likelihood_window(&self) -> ((usize, usize, usize, usize), Vec<f32>) {
+        let mut e = [0i32; 4];
+        unsafe { sys::slamrs_gpu_map_extent(self.h, e.as_mut_ptr()) };
+        let (x0, y0, x1, y1) = (e[0].max(0) as usize, e[1].max(0) as usize, e[2].max(0) as usize, e[3].max(0) as usize);
+        let mut data = vec![0f32; (x1 - x0) * (y1 - y0)];
+        if !data.is_empty() {
+            unsafe {
+                sys::slamrs_gpu_map_window(self.h, sys::SLAMRS_MAP_F32, e[0], e[1], e[2], e[3],
+                    data.as_mut_ptr() as *mut core::ffi::c_void)
+            };
+        }
+        ((x0, y0, x1, y1), data)
+    }
 }
 
 impl Drop for GridMapSlam {
