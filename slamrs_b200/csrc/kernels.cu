@@ -1537,12 +1537,15 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
     }
 }
 
-// CTA-granular: one work item = (job, band of rows of U); the (row, 32-byte unit) pairs of the
-// band are linearised over the CTA's threads, UNROLL independent 256-bit loads per thread, then
-// every value is stored to each destination of the sub-run. The job of the next item is fetched
-// into registers while the current item is copied.
-template <int UNROLL, int MINB>
-__global__ void __launch_bounds__(COPY_THREADS, MINB)
+// One work item = (job, band of rows of U); the (row, 32-byte unit) pairs of the band are linearised
+// over the CTA's threads, UNROLL independent 256-bit loads per thread, then every value is stored
+// to each destination of the sub-run. The job of the next item is fetched into registers while the
+// current item is copied. CTAs are single warps (BOX_THREADS): a band of ~7 rows x 32 units is a
+// few hundred elements, and with more warps per CTA the two barriers per item dominate.
+constexpr int BOX_THREADS = 32;
+constexpr int BOX_CTAS_PER_SM = 256;
+template <int UNROLL, int MINB, int THREADS>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restrict__ n_jobs,
              uint32_t row_units /* 32-byte units per physical grid row */, uint32_t umask, uint32_t items_per_cta,
              StepCounters* counters) {
@@ -1582,12 +1585,12 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
         const uint32_t fan = s_job.fan;
         const uint32_t count = (uint32_t)(r1 - r0) * uw;
         const V8* src = reinterpret_cast<const V8*>(s_job.src);
-        for (uint32_t base = threadIdx.x; base < count; base += COPY_THREADS * UNROLL) {
+        for (uint32_t base = threadIdx.x; base < count; base += THREADS * UNROLL) {
             V8 v[UNROLL];
             uint32_t off[UNROLL];   // unit offset inside a destination grid (< 2^28)
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                const uint32_t i = base + u * COPY_THREADS;
+                const uint32_t i = base + u * THREADS;
                 off[u] = 0xffffffffu;
                 v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
                 if (i < count) {
@@ -1625,7 +1628,10 @@ void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_
     // measured on B200 (gpurun_out/tune_copy4.log): 4 loads in flight per thread, 3 CTAs per SM
     // resident, grid oversubscribed 32x per SM for balance, ~6 items per CTA
     const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
-    k_copy_boxed<4, 3><<<num_sms * COPY_CTAS_PER_SM, COPY_THREADS, 0, stream>>>(
+    // measured on B200 (profiles/r1_copy_tuning.md): one-warp CTAs (the per-item barriers cost more than
+    // anything else in larger CTAs), 4 loads in flight per thread, grid oversubscribed for balance,
+    // about 6 items per CTA
+    k_copy_boxed<4, 24, BOX_THREADS><<<num_sms * BOX_CTAS_PER_SM, BOX_THREADS, 0, stream>>>(
         (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom.gw / 8u, umask, 6u, counters);
 }
 size_t copy_job_bytes() { return sizeof(CopyJob); }
