@@ -1,4 +1,16 @@
-// Kernel parameter blocks and launch wrappers of the SLAM step (definitions in kernels.cu).
+// Kernel parameter blocks and launch wrappers of the SLAM step. Hand-written sm_100a kernels, no
+// tensor cores anywhere (nothing here is a dense contraction); the step is HBM-bound (grid copies)
+// with an instruction-bound cell walk in front of it. Definitions:
+//
+//   kernels_likelihood.cu  k_motion        robot.rs:152-183 (sample, motion pdf)   one thread per particle
+//                          k_likelihood    map.rs:113-145 (beam-endpoint likelihood) one warp per particle,
+//                                          results stored into every peer GPU; k_peer_barrier
+//   kernels_ray.cu         k_ray_update*   map.rs:71-106 + ray.rs:21-110 + map.rs:148-172 (integrate):
+//                                          one CTA per surviving particle, shared-memory disc window
+//   kernels_resample.cu    k_weights       particle.rs:40-56, 59-65 + the running sum of :85-91 (8-CTA cluster)
+//                          k_resample_indices  particle.rs:78-101 + survivor list;  k_plan  keep / copy lists
+//   kernels_copy.cu        k_copy, k_copy_prepare / k_copy_boxed / k_commit_boxes   particle.rs:97-100 clone()
+//   kernels_misc.cu        k_export*       slam.rs:83-88 / map.rs:50-52;  k_sim_scan  simulator/src/sim.rs:134-159
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -1,0 +1,169 @@
+// k_motion (robot.rs:152-183) and k_likelihood (map.rs:113-145), with the multi-GPU exchange fused
+// into the likelihood kernel and the peer-flag barrier that completes it.
+#include "kernels_common.cuh"
+
+namespace slamrs {
+
+// =============================================================================== k_motion + k_likelihood
+// k_motion: one THREAD per particle. Odometry::sample (robot.rs:170-183) and the motion log-density
+// Odometry::probabiliy_of (robot.rs:152-167) need a few hundred scalar f64 operations per particle
+// and nothing else; giving them a warp or a CTA would multiply the issued instructions by 32.
+// The log-density is parked in ParticleResult::weight until k_likelihood folds it in.
+__global__ void __launch_bounds__(128)
+k_motion(OdomModel od, const float* __restrict__ pose_cur, const int32_t* __restrict__ slot_of,
+         ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
+         const double* __restrict__ z_draws, uint64_t seed, uint64_t step) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_local) return;
+    const uint32_t gp = first_particle + p;      // global logical index
+    const float ox = pose_cur[3 * p], oy = pose_cur[3 * p + 1], otheta = pose_cur[3 * p + 2];
+    // Odometry::sample. statrs: sample = mean + std_dev * z.
+    double z1, z2;
+    if (z_draws) {
+        z1 = z_draws[2 * (size_t)gp];
+        z2 = z_draws[2 * (size_t)gp + 1];
+    } else {
+        slamrs_stream::motion_normals(seed, step, gp, &z1, &z2);
+    }
+    const float center_distance = (float)__dadd_rn(od.mean_c, __dmul_rn(od.std_c, z1));
+    const float ntheta = __fadd_rn(otheta, (float)__dadd_rn(od.mean_t, __dmul_rn(od.std_t, z2)));
+    float sn, cs;
+    slamrs_libm::sincosf_exact(ntheta, &sn, &cs);
+    const float nx = __fadd_rn(ox, __fmul_rn(cs, center_distance));
+    const float ny = __fadd_rn(oy, __fmul_rn(sn, center_distance));
+    // Odometry::probabiliy_of(old, new)
+    const float dx = __fsub_rn(ox, nx), dy = __fsub_rn(oy, ny);
+    const float moved = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    const double ad = angle_diff((double)otheta, (double)ntheta);
+    ParticleResult r;
+    r.weight = __dadd_rn(log(normal_pdf((double)moved, od.mean_c, od.std_c)), log(normal_pdf(ad, od.mean_t, od.std_t)));
+    r.x = nx; r.y = ny; r.theta = ntheta;
+    r.slot = slot_of[p];                    // physical slot, read by other ranks' planners
+    results[gp] = r;
+}
+
+// k_likelihood: one WARP per particle, lanes over beams. Map::probability_of (map.rs:113-145): one
+// gather per valid beam from the PRE-update grid. LK_UNROLL gathers are in flight per lane before
+// the first exp/log. A never-informed cell (counters 0 -> log-odds 0 -> p = 0.5) contributes
+// log(1/1) = 0 and skips the transcendental work. Each lane adds its terms in beam order, the 32
+// lane sums are combined by a fixed butterfly: deterministic, order-independent of scheduling.
+constexpr int LK_WARPS = 4;
+constexpr int LK_UNROLL = 4;
+
+__global__ void __launch_bounds__(LK_WARPS * 32, 2048 / (LK_WARPS * 32))   // every particle of an 8,192-shard resident at once
+k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, const SlotMeta* __restrict__ meta,
+             size_t cells_per_grid, ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
+             const double* __restrict__ term_table,
+             ParticleResult* const* __restrict__ peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
+    const uint32_t p = blockIdx.x * LK_WARPS + (threadIdx.x >> 5);
+    if (p >= n_local) return;
+    const int lane = threadIdx.x & 31;
+    const ParticleResult r = results[first_particle + p];
+    const float nx = r.x, ny = r.y, ntheta = r.theta;
+    const uint32_t* grid = cells + (size_t)r.slot * cells_per_grid;
+    const int shift = meta[r.slot].ox;   // row rotation of this particle's slot
+
+    double lp = log(1.0);
+    for (uint32_t base = 0; base < scan.n_beams; base += 32u * LK_UNROLL) {
+        uint32_t cell[LK_UNROLL];
+#pragma unroll
+        for (int u = 0; u < LK_UNROLL; ++u) {
+            const uint32_t b = base + (uint32_t)u * 32u + (uint32_t)lane;
+            cell[u] = 0u;
+            if (b < scan.n_beams && scan.valid[b]) {
+                float ex, ey;
+                beam_endpoint(nx, ny, ntheta, scan.angle[b], scan.dist[b], &ex, &ey);
+                const float gx = world_to_grid(ex, geom.pos_x, geom.res);
+                const float gy = world_to_grid(ey, geom.pos_y, geom.res);
+                if (grid_is_valid(gx, gy, geom.gw, geom.gh)) {
+                    const size_t column = (size_t)f32_as_usize(gx), row = (size_t)f32_as_usize(gy);
+                    // index(): map.rs:201-204, then the slot's row rotation
+                    cell[u] = __ldg(&grid[row * geom.gh + phys_col(geom, (uint32_t)column, shift)]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < LK_UNROLL; ++u) {
+            if (cell[u] != 0u) {
+                const uint32_t nf = cell[u] & 0xffffu, no = cell[u] >> 16;
+                const double term = (nf < LK_TABLE_NF && no < LK_TABLE_NO) ? __ldg(&term_table[nf * LK_TABLE_NO + no])
+                                                                           : beam_log_term(cell[u]);
+                lp = __dadd_rn(lp, term);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lp = __dadd_rn(lp, __shfl_xor_sync(0xffffffffu, lp, o));
+    // weight.prob().value(), slam.rs:71: exp(log p(z|x,m) + log p(x'|x,u))
+    ParticleResult out = r;
+    out.weight = exp(__dadd_rn(lp, r.weight));
+    if (lane == 0) results[first_particle + p] = out;
+    // The exchange step, fused: lane q stores the finished record straight into GPU q's copy of
+    // the population array over NVLink (24 bytes per particle and peer), so that after one
+    // peer barrier every GPU holds every particle's weight, pose and slot.
+    if (peer_results != nullptr && (uint32_t)lane < world && (uint32_t)lane != rank)
+        peer_results[lane][peer_offset + first_particle + p] = out;
+}
+
+void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
+                              const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
+                              const SlotMeta* meta, size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
+                              uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
+                              const double* term_table,
+                              ParticleResult* const* peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
+    k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
+                                                         z_draws, seed, step);
+    k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, cells, meta, cells_per_grid,
+                                                                                   results, first_particle, n_local,
+                                                                                   term_table, peer_results, peer_offset,
+                                                                                   rank, world);
+}
+
+__global__ void k_fill_term_table(double* __restrict__ table) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= LK_TABLE_NF * LK_TABLE_NO) return;
+    const uint32_t nf = i / LK_TABLE_NO, no = i % LK_TABLE_NO;
+    table[i] = (nf | no) ? beam_log_term(nf | (no << 16)) : 0.0;   // entry (0,0) is never read (prior cells are skipped)
+}
+void launch_fill_term_table(cudaStream_t stream, double* table) {
+    k_fill_term_table<<<(LK_TABLE_NF * LK_TABLE_NO + 255) / 256, 256, 0, stream>>>(table);
+}
+
+// =============================================================================== k_peer_barrier
+// Stream-ordered barrier across the GPUs of one box through peer-mapped flags: lane q publishes
+// this rank's epoch into GPU q's flag array (release, system scope: every write this GPU issued
+// before, including the peer stores of earlier kernels in the stream, is visible first) and then
+// waits until GPU q's epoch has arrived here (acquire). Epochs only grow, so flags are never reset.
+// A bounded wait (timeout_ns, one minute by default: ranks are driven by independent host threads
+// that may lag) turns a lost peer into an error instead of a hung GPU.
+__global__ void __launch_bounds__(64)
+k_peer_barrier(unsigned long long* const* __restrict__ peer_flags, unsigned long long* my_flags, uint32_t rank,
+               uint32_t world, unsigned long long epoch, unsigned long long timeout_ns, StepCounters* counters) {
+    const uint32_t q = threadIdx.x;
+    if (q >= world) return;
+    __threadfence_system();
+    unsigned long long* theirs = peer_flags[q] + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    // once a barrier has given up the handle is poisoned (the error is reported at the next sync):
+    // later barriers publish their epoch, so that healthy peers keep going, but do not wait again
+    if (*reinterpret_cast<volatile unsigned long long*>(&counters->barrier_timeout) != 0ull) return;
+    const unsigned long long* mine = my_flags + q;
+    unsigned long long t0, now, seen = 0ull;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        if (seen >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) { counters->barrier_timeout = 1ull; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
+                         uint32_t rank, uint32_t world, unsigned long long epoch, unsigned long long timeout_ns,
+                         StepCounters* counters) {
+    k_peer_barrier<<<1, 64, 0, stream>>>(peer_flags, my_flags, rank, world, epoch, timeout_ns, counters);
+}
+
+}  // namespace slamrs

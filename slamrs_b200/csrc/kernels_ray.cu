@@ -1,0 +1,673 @@
+// k_ray_update / k_ray_update_packed: Map::integrate (map.rs:71-106) with GridRayIterator
+// (ray.rs:21-110) and the inverse sensor model (map.rs:148-172); hit counters accumulated in a
+// shared-memory disc window, written back with 128-bit read-modify-writes.
+#include "kernels_common.cuh"
+
+namespace slamrs {
+
+// =============================================================================== k_ray_update
+
+constexpr int RAY_MAX_SMEM = 220 * 1024;  // window budget; the HW limit is 227 KB per CTA
+
+// saturating packed add straight to global memory, for the (rare) cells outside the window
+__device__ __forceinline__ void global_cell_add(uint32_t* addr, uint32_t inc, bool* saturated) {
+    uint32_t old = *addr;
+    for (;;) {
+        const uint32_t nv = cell_sat_add(old, inc, saturated);
+        if (nv == old) return;
+        const uint32_t seen = atomicCAS(addr, old, nv);
+        if (seen == old) return;
+        old = seen;
+    }
+}
+
+constexpr int RAY_MAX_THREADS = 512;
+
+// touched-extent bookkeeping of one CTA: s_ext = {xmin, ymin, xmax, ymax} (inclusive cells)
+__device__ __forceinline__ void ext_init(int* s_ext) {
+    if (threadIdx.x == 0) { s_ext[0] = 0x7fffffff; s_ext[1] = 0x7fffffff; s_ext[2] = -1; s_ext[3] = -1; }
+}
+__device__ __forceinline__ void ext_add(int* s_ext, int xmin, int ymin, int xmax, int ymax) {
+    if (xmax < xmin) return;
+    atomicMin(&s_ext[0], xmin); atomicMin(&s_ext[1], ymin);
+    atomicMax(&s_ext[2], xmax); atomicMax(&s_ext[3], ymax);
+}
+// union the CTA's touched extent into the slot's box (x aligned to 8 cells); one thread, after a barrier
+constexpr int BOX_ALIGN = 8;   // x alignment of extents in cells: one 256-bit access
+// Row rotation of the slot a ray kernel writes: the slot's own once it holds a grid; for an empty slot
+// (first scan of a lineage) the one that puts the leftmost cell any ray can reach on a page
+// boundary. s_shift[0] receives it; all threads of the CTA call this, with a barrier inside.
+__device__ __forceinline__ int ray_slot_shift(const MapGeom& geom, const ScanDevice& scan, const SlotMeta* meta, float px,
+                                              float py, float ptheta, int cx0, int* s_shift) {
+    const SlotMeta m = *meta;
+    const bool empty = m.x1 <= m.x0 || m.y1 <= m.y0;
+    if (threadIdx.x == 0) s_shift[0] = empty ? 0x7fffffff : m.ox;
+    __syncthreads();
+    if (empty && geom.page_cells) {   // uniform over the CTA
+        int xmin = cx0;
+        for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
+            float ex, ey;
+            beam_endpoint(px, py, ptheta, scan.angle[b], scan.dist[b], &ex, &ey);
+            const float gx = floorf(world_to_grid(ex, geom.pos_x, geom.res));
+            // a ray reaches at most two cells beyond its endpoint cell (map.rs:97); NaN / far-out -> 0
+            const int reach = (gx >= 2.0f && gx < 1.0e6f) ? (int)gx - 2 : 0;
+            xmin = min(xmin, reach);
+        }
+        atomicMin(&s_shift[0], max(0, xmin));
+        __syncthreads();
+        if (threadIdx.x == 0) s_shift[0] = align_shift(geom, s_shift[0] & ~7);
+        __syncthreads();
+    } else if (empty) {
+        if (threadIdx.x == 0) s_shift[0] = 0;
+        __syncthreads();
+    }
+    return s_shift[0];
+}
+
+__device__ __forceinline__ void ext_commit(const int* s_ext, SlotMeta* meta, int gw, int shift) {
+    if (s_ext[2] < s_ext[0]) return;
+    SlotMeta b = *meta;
+    b.ox = shift;
+    const int am = BOX_ALIGN - 1;
+    const int x0 = s_ext[0] & ~am, x1 = min(gw, (s_ext[2] + 1 + am) & ~am), y0 = s_ext[1], y1 = s_ext[3] + 1;
+    if (b.x1 <= b.x0) { b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; }
+    else { b.x0 = min(b.x0, x0); b.y0 = min(b.y0, y0); b.x1 = max(b.x1, x1); b.y1 = max(b.y1, y1); }
+    *meta = b;
+}
+constexpr int RAY_MAX_RADIUS = 150;                    // rows of the window: 2 * radius + 1
+constexpr int RAY_MAX_ROWS = 2 * RAY_MAX_RADIUS + 1;
+constexpr int RAY_WB_BATCH = 6;                        // write-back: global loads in flight per thread
+
+// exact integer square root of a small non-negative integer (same code on host and device so
+// that the host's shared-memory sizing and the kernel's row table agree)
+__host__ __device__ inline int isqrt_small(int v) {
+    int r = (int)sqrtf((float)v);
+    while (r * r > v) r--;
+    while ((r + 1) * (r + 1) <= v) r++;
+    return r;
+}
+
+// The window is a DISC of cells around the start cell (rays cannot leave it), stored row by row:
+// row dy holds x in [cx - hw, cx + hw], hw = floor(sqrt(R^2 - dy^2)), widened to multiples of 4
+// cells for 128-bit write-back. A disc needs pi/4 of the bounding square, which is what lets a
+// 6 m range at 5 cm cells (radius 124) fit in one CTA's shared memory.
+__host__ __device__ inline int ray_window_cells_upper_bound(int radius, bool vec) {
+    int total = 0;
+    for (int dy = -radius; dy <= radius; ++dy) total += 2 * isqrt_small(radius * radius - dy * dy) + 1 + (vec ? 6 : 0);
+    return total;
+}
+
+template <bool kVector>
+__global__ void __launch_bounds__(RAY_MAX_THREADS)
+k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
+             const uint32_t* __restrict__ alive_list,
+             const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
+             size_t cells_per_grid, int radius, StepCounters* counters) {
+    extern __shared__ __align__(16) uint32_t s_win[];
+    __shared__ int s_row_off[RAY_MAX_ROWS + 1];   // first window cell of each row (+ total at [wh])
+    __shared__ int s_row_x[RAY_MAX_ROWS];         // x0 | (width << 16)
+    __shared__ int s_ext[4];
+    __shared__ int s_shift[1];
+    if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
+    const uint32_t p = alive_list[blockIdx.x];
+    ext_init(s_ext);
+    const ParticleResult r = results[first_particle + p];
+    const float px = r.x, py = r.y, ptheta = r.theta;
+    uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
+
+    // Map::integrate, map.rs:71-73: ray start in grid coordinates
+    const float sx = world_to_grid(px, geom.pos_x, geom.res);
+    const float sy = world_to_grid(py, geom.pos_y, geom.res);
+    const long long lcx = f32_as_isize(floorf(sx)), lcy = f32_as_isize(floorf(sy));
+    // every ray starts in the same cell; outside the grid nothing is emitted (ray.rs:88-92)
+    if (lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh) return;
+    const int cx = (int)lcx, cy = (int)lcy;
+    const int shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx, s_shift);
+
+    // ---- row table of the disc window, clipped to the grid
+    const int wy0 = max(0, cy - radius), wy1 = min((int)geom.gh, cy + radius + 1);
+    const int wh = wy1 - wy0;
+    for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {
+        const int dy = wy0 + ly - cy;
+        const int hw = isqrt_small(radius * radius - dy * dy);
+        int x0 = max(0, cx - hw), x1 = min((int)geom.gw, cx + hw + 1);
+        if (kVector) {
+            x0 &= ~3;
+            x1 = min((int)geom.gw, (x1 + 3) & ~3);
+        }
+        s_row_x[ly] = x0 | ((x1 - x0) << 16);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive prefix sum of the row widths, 32 rows per round
+        int carry = 0;
+        for (int base = 0; base < wh; base += 32) {
+            const int ly = base + (int)threadIdx.x;
+            const int w = ly < wh ? (s_row_x[ly] >> 16) : 0;
+            int inc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += t;
+            }
+            if (ly < wh) s_row_off[ly] = carry + inc - w;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (threadIdx.x == 0) s_row_off[wh] = carry;
+    }
+    __syncthreads();
+    const int wcells = s_row_off[wh];
+
+    if (kVector) {
+        uint4* w4 = reinterpret_cast<uint4*>(s_win);
+        for (int i = threadIdx.x; i < (wcells >> 2); i += blockDim.x) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        for (int i = threadIdx.x; i < wcells; i += blockDim.x) s_win[i] = 0u;
+    }
+    __syncthreads();
+
+    bool saturated = false;
+    uint32_t spilled = 0;
+    for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
+        const float dist = scan.dist[b];
+        float ex, ey;
+        beam_endpoint(px, py, ptheta, scan.angle[b], dist, &ex, &ey);
+        const float gx = world_to_grid(ex, geom.pos_x, geom.res);
+        const float gy = world_to_grid(ey, geom.pos_y, geom.res);
+        // measured distance in cells (map.rs:84) and the per-ray form of inverse_sensor_model
+        const RayClassifier cls = make_ray_classifier(__fdiv_rn(dist, geom.res), scan.valid[b] != 0);
+        // apply_measurement, map.rs:88-106 (additional_steps = 2)
+        ray_walk_acc(sx, sy, gx, gy, geom.gw, geom.gh, 2u, [&](int x, int y, float acc) {
+            const uint32_t inc = classify_cell(cls, acc);
+            if (inc != 0u) {
+                const int ly = y - wy0;
+                bool in_window = false;
+                if ((unsigned)ly < (unsigned)wh) {
+                    const int rx = s_row_x[ly];
+                    const int lx = x - (rx & 0xffff);
+                    if ((unsigned)lx < (unsigned)(rx >> 16)) {
+                        atomicAdd(&s_win[s_row_off[ly] + lx], inc);
+                        in_window = true;
+                    }
+                }
+                if (!in_window) {  // beyond the window (range larger than shared memory allows)
+                    global_cell_add(&grid[(size_t)y * geom.gh + phys_col(geom, (uint32_t)x, shift)], inc, &saturated);
+                    ext_add(s_ext, x, y, x, y);
+                    spilled++;
+                }
+            }
+        });
+    }
+    __syncthreads();
+
+    // ---- write-back: grid += window, saturating per 16-bit counter, untouched groups skipped.
+    // RAY_WB_BATCH independent global loads are issued per thread before the first dependent store.
+    int exmin = 0x7fffffff, eymin = 0x7fffffff, exmax = -1, eymax = -1;   // this thread's touched extent
+    if (kVector) {
+        const int total4 = wcells >> 2;
+        const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
+        for (int base = threadIdx.x; base < total4; base += blockDim.x * RAY_WB_BATCH) {
+            uint4 d[RAY_WB_BATCH], v[RAY_WB_BATCH];
+            uint4* gp[RAY_WB_BATCH];
+            bool nz[RAY_WB_BATCH];
+#pragma unroll
+            for (int j = 0; j < RAY_WB_BATCH; ++j) {
+                const int i = base + j * (int)blockDim.x;
+                nz[j] = false;
+                if (i < total4) {
+                    d[j] = win4[i];
+                    nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
+                    if (nz[j]) {
+                        int lo = 0, hi = wh;   // row containing window cell 4*i
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_row_off[mid] <= 4 * i) lo = mid; else hi = mid;
+                        }
+                        const int lx = 4 * i - s_row_off[lo];
+                        const int gx0 = (s_row_x[lo] & 0xffff) + lx;
+                        exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 3);
+                        eymin = min(eymin, wy0 + lo); eymax = max(eymax, wy0 + lo);
+                        gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + phys_col(geom, (uint32_t)gx0, shift));
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RAY_WB_BATCH; ++j)
+                if (nz[j]) v[j] = *gp[j];
+#pragma unroll
+            for (int j = 0; j < RAY_WB_BATCH; ++j) {
+                if (nz[j]) {
+                    v[j].x = cell_sat_add(v[j].x, d[j].x, &saturated);
+                    v[j].y = cell_sat_add(v[j].y, d[j].y, &saturated);
+                    v[j].z = cell_sat_add(v[j].z, d[j].z, &saturated);
+                    v[j].w = cell_sat_add(v[j].w, d[j].w, &saturated);
+                    *gp[j] = v[j];
+                }
+            }
+        }
+    } else {
+        for (int ly = threadIdx.x >> 5; ly < wh; ly += blockDim.x >> 5) {
+            const int rx = s_row_x[ly], x0 = rx & 0xffff, w = rx >> 16, off = s_row_off[ly];
+            for (int c = threadIdx.x & 31; c < w; c += 32) {
+                const uint32_t d = s_win[off + c];
+                if (d != 0u) {
+                    uint32_t* g = grid + (size_t)(wy0 + ly) * geom.gh + phys_col(geom, (uint32_t)(x0 + c), shift);
+                    *g = cell_sat_add(*g, d, &saturated);
+                    exmin = min(exmin, x0 + c); exmax = max(exmax, x0 + c);
+                    eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
+                }
+            }
+        }
+    }
+    ext_add(s_ext, exmin, eymin, exmax, eymax);
+    __syncthreads();
+    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, shift);
+    if (saturated) atomicAdd(&counters->saturated, 1ull);
+    if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
+}
+
+// ------------------------------------------------------------------------------- packed variant
+// Same algorithm with a 2-byte window cell: bits 0..10 = free hits (a cell can be crossed by at
+// most n_beams <= 2047 rays per scan), bits 11..15 = occupied hits (<= 31; a 32nd hit in one scan
+// takes the exact global path). Half the shared memory per particle => two CTAs per SM at a 6 m /
+// 5 cm window, which is what hides the latency of the serial cell walk. Free hits (the vast
+// majority) are single fire-and-forget shared-memory adds; the walk itself is written with the
+// row lookup hoisted to y-steps.
+constexpr uint32_t PK_FREE_BITS = 11;
+constexpr uint32_t PK_FREE_MASK = (1u << PK_FREE_BITS) - 1u;
+constexpr uint32_t PK_OCC_MAX = 31;
+constexpr uint32_t RAY_PACKED_MAX_BEAMS = PK_FREE_MASK;
+
+__host__ __device__ inline int ray_window_cells_upper_bound_packed(int radius) {
+    int total = 0;
+    for (int dy = -radius; dy <= radius; ++dy) total += 2 * isqrt_small(radius * radius - dy * dy) + 1 + 14;
+    return total;
+}
+
+// Facts the packed kernel's fast walk relies on:
+//  * |x0 - centre_x| and |y0 - centre_y| never decrease along a walk (x only moves by x_inc, y
+//    only by y_inc, away from the start cell), IEEE rounding is monotone, so
+//    acc = fl(fl(dx^2) + fl(dy^2)) is non-decreasing along the ray. The inverse sensor model is
+//    therefore a free run (acc < free_below), then an occupied run (acc <= prior_above, hits
+//    only), then prior cells that add nothing: two tight loops and an early exit replace the
+//    per-cell three-way classification.
+//  * a ray whose endpoint cell is (ax, ay) cells away from the start cell visits only cells within
+//    (ax + 2, ay + 2) of it; if that corner is inside the disc window and the disc is inside the
+//    grid, no per-cell window or grid test is needed.
+__global__ void __maxnreg__(80)   // 2 CTAs of 384 threads per SM; blocks have at most RAY_MAX_THREADS threads
+k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
+             const uint32_t* __restrict__ alive_list,
+                    const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
+                    size_t cells_per_grid, int radius, StepCounters* counters) {
+    extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
+    __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
+    __shared__ uint32_t s_rowb[RAY_MAX_ROWS];           // shared byte address of column x = 0 of the row
+    __shared__ int s_ext[4];
+    __shared__ int s_shift[1];
+    if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
+    const uint32_t p = alive_list[blockIdx.x];
+    ext_init(s_ext);
+    const ParticleResult r = results[first_particle + p];
+    const float px = r.x, py = r.y, ptheta = r.theta;
+    uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
+
+    const float sx = world_to_grid(px, geom.pos_x, geom.res);
+    const float sy = world_to_grid(py, geom.pos_y, geom.res);
+    const long long lcx = f32_as_isize(floorf(sx)), lcy = f32_as_isize(floorf(sy));
+    if (lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh) return;
+    const int cx0 = (int)lcx, cy0 = (int)lcy;
+    const int gw = (int)geom.gw, gh = (int)geom.gh;
+    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
+    const int slot_shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx0, s_shift);
+
+    // ---- row table of the disc window (x ranges aligned to 8 cells = one 128-bit group)
+    const int wy0 = max(0, cy0 - radius), wy1 = min(gh, cy0 + radius + 1);
+    const int wh = wy1 - wy0;
+    for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {
+        const int dy = wy0 + ly - cy0;
+        const int hw = isqrt_small(radius * radius - dy * dy);
+        const int x0 = max(0, cx0 - hw) & ~7;
+        const int x1 = min(gw, (min(gw, cx0 + hw + 1) + 7) & ~7);
+        s_row[ly].y = x0 | ((x1 - x0) << 16);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int carry = 0;
+        for (int base = 0; base < wh; base += 32) {
+            const int ly = base + (int)threadIdx.x;
+            const int w = ly < wh ? (s_row[ly].y >> 16) : 0;
+            int inc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += t;
+            }
+            if (ly < wh) {
+                const int first = carry + inc - w;
+                s_row[ly].x = first;
+                s_rowb[ly] = win_base + 2u * (uint32_t)(first - (s_row[ly].y & 0xffff));
+            }
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (threadIdx.x == 0) s_row[wh] = make_int2(carry, 0);
+    }
+    __syncthreads();
+    const int wcells = s_row[wh].x;
+    {
+        uint4* w4 = reinterpret_cast<uint4*>(s_win);
+        for (int i = threadIdx.x; i < (wcells >> 3); i += blockDim.x) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+
+    const bool disc_in_grid = cx0 - radius >= 0 && cx0 + radius < gw && cy0 - radius >= 0 && cy0 + radius < gh;
+    bool saturated = false;
+    uint32_t spilled = 0;
+    for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
+        const float dist = scan.dist[b];
+        float ex, ey;
+        beam_endpoint(px, py, ptheta, scan.angle[b], dist, &ex, &ey);
+        const float x1 = world_to_grid(ex, geom.pos_x, geom.res);
+        const float y1 = world_to_grid(ey, geom.pos_y, geom.res);
+        const RayClassifier cls = make_ray_classifier(__fdiv_rn(dist, geom.res), scan.valid[b] != 0);
+
+        // GridRayIterator::new (ray.rs:21-77) -- identical arithmetic to ray_walk_acc
+        const float delta_x = fabsf(__fsub_rn(x1, sx)), delta_y = fabsf(__fsub_rn(y1, sy));
+        const float fx0 = floorf(sx), fy0 = floorf(sy);
+        unsigned long long n = 1ull + 2ull;   // additional_steps = 2 (map.rs:97)
+        unsigned long long ax = 0ull, ay = 0ull;   // |endpoint cell - start cell| per axis
+        int x_inc, y_inc;
+        float error;
+        if (delta_x == 0.0f) {
+            x_inc = 0;
+            error = __int_as_float(0x7f800000);
+        } else if (x1 > sx) {
+            x_inc = 1;
+            ax = (unsigned long long)f32_as_isize(__fsub_rn(floorf(x1), (float)cx0));
+            error = __fmul_rn(__fsub_rn(__fadd_rn(fx0, 1.0f), sx), delta_y);
+        } else {
+            x_inc = -1;
+            ax = (unsigned long long)(long long)cx0 - (unsigned long long)f32_as_isize(floorf(x1));
+            error = __fmul_rn(__fsub_rn(sx, fx0), delta_y);
+        }
+        if (delta_y == 0.0f) {
+            y_inc = 0;
+            error = __fsub_rn(error, __int_as_float(0x7f800000));
+        } else if (y1 > sy) {
+            y_inc = 1;
+            ay = (unsigned long long)f32_as_isize(floorf(y1)) - (unsigned long long)(long long)cy0;
+            error = __fsub_rn(error, __fmul_rn(__fsub_rn(__fadd_rn(fy0, 1.0f), sy), delta_x));
+        } else {
+            y_inc = -1;
+            ay = (unsigned long long)(long long)cy0 - (unsigned long long)f32_as_isize(floorf(y1));
+            error = __fsub_rn(error, __fmul_rn(__fsub_rn(sy, fy0), delta_x));
+        }
+        n += ax + ay;   // wrapping isize arithmetic, then `as usize`
+        const unsigned long long cap = (unsigned long long)geom.gw + geom.gh + 8ull;
+        int remaining = (int)(n < cap ? n : cap);
+
+        const float x_step = (float)x_inc, y_step = (float)y_inc;
+        float cxf = __fadd_rn((float)cx0, 0.5f), cyf = __fadd_rn((float)cy0, 0.5f);
+        float dxs = __fsub_rn(sx, cxf), dys = __fsub_rn(sy, cyf);
+        float dx2 = __fmul_rn(dxs, dxs), dy2 = __fmul_rn(dys, dys);
+
+        // every cell of this ray inside the window and the grid?
+        bool fast = false;
+        if (disc_in_grid && ax < 4096ull && ay < 4096ull) {
+            const int cxa = (int)ax + 2, cya = (int)ay + 2;
+            fast = cxa * cxa + cya * cya <= radius * radius;
+        }
+        if (fast) {
+            uint32_t x2 = 2u * (uint32_t)cx0;         // twice the current column
+            const uint32_t x_inc2 = (uint32_t)(2 * x_inc);
+            int ly = cy0 - wy0;
+            uint32_t rb = s_rowb[ly];
+            // free run
+            while (remaining > 0) {
+                const float acc = __fadd_rn(dx2, dy2);
+                if (!(acc < cls.free_below)) break;
+                const uint32_t c2 = rb + x2;           // shared byte address of the 16-bit window cell
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(c2 & ~3u), "r"((c2 & 2u) ? 0x10000u : 1u) : "memory");
+                if (error > 0.0f) {
+                    error = __fsub_rn(error, delta_x);
+                    cyf = __fadd_rn(cyf, y_step);
+                    dys = __fsub_rn(sy, cyf);
+                    dy2 = __fmul_rn(dys, dys);
+                    ly += y_inc;
+                    rb = s_rowb[ly];
+                } else {
+                    error = __fadd_rn(error, delta_y);
+                    cxf = __fadd_rn(cxf, x_step);
+                    dxs = __fsub_rn(sx, cxf);
+                    dx2 = __fmul_rn(dxs, dxs);
+                    x2 += x_inc2;
+                }
+                remaining -= 1;
+            }
+            // occupied run (hits only): bounded 5-bit field per scan, exact global path beyond it
+            if (cls.mid_inc != 0u) {
+                while (remaining > 0) {
+                    const float acc = __fadd_rn(dx2, dy2);
+                    if (acc > cls.prior_above) break;
+                    const uint32_t c2 = rb + x2;
+                    const uint32_t shift = ((c2 & 2u) << 3) + PK_FREE_BITS;
+                    uint32_t old;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(c2 & ~3u) : "memory");
+                    bool done = false;
+                    for (;;) {
+                        if (((old >> shift) & PK_OCC_MAX) == PK_OCC_MAX) break;
+                        uint32_t seen;
+                        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;"
+                                     : "=r"(seen) : "r"(c2 & ~3u), "r"(old), "r"(old + (1u << shift)) : "memory");
+                        if (seen == old) { done = true; break; }
+                        old = seen;
+                    }
+                    if (!done) {
+                        const int x = (int)(x2 >> 1), y = wy0 + ly;
+                        global_cell_add(&grid[(size_t)y * geom.gh + phys_col(geom, (uint32_t)x, slot_shift)], CELL_OCC_INC, &saturated);
+                        ext_add(s_ext, x, y, x, y);
+                        spilled++;
+                    }
+                    if (error > 0.0f) {
+                        error = __fsub_rn(error, delta_x);
+                        cyf = __fadd_rn(cyf, y_step);
+                        dys = __fsub_rn(sy, cyf);
+                        dy2 = __fmul_rn(dys, dys);
+                        ly += y_inc;
+                        rb = s_rowb[ly];
+                    } else {
+                        error = __fadd_rn(error, delta_y);
+                        cxf = __fadd_rn(cxf, x_step);
+                        dxs = __fsub_rn(sx, cxf);
+                        dx2 = __fmul_rn(dxs, dxs);
+                        x2 += x_inc2;
+                    }
+                    remaining -= 1;
+                }
+            }
+            continue;
+        }
+
+        // general walk: per-cell window and grid tests (rays that may leave the window or the grid)
+        int x = cx0, y = cy0;
+        int ly = y - wy0;
+        int2 row = s_row[ly];                      // the start cell is always inside the window
+        int lx = x - (row.y & 0xffff);
+        int row_w = row.y >> 16;
+        bool inside = true;
+        while (remaining > 0 && inside) {
+            const float acc = __fadd_rn(dx2, dy2);
+            const bool is_free = acc < cls.free_below;
+            const bool is_mid = !is_free && !(acc > cls.prior_above) && (cls.mid_inc != 0u);
+            if (is_free | is_mid) {
+                const bool in_win = (unsigned)lx < (unsigned)row_w;
+                const int cell = row.x + lx;
+                const uint32_t addr = win_base + ((uint32_t)(cell >> 1) << 2);
+                const uint32_t shift = (cell & 1) << 4;
+                if (is_free & in_win) {
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u << shift) : "memory");
+                } else {
+                    bool done = false;
+                    if (in_win) {   // occupied hit: bounded 5-bit field, exact path when it would overflow
+                        uint32_t* wp = &s_win[cell >> 1];
+                        uint32_t old = *wp;
+                        for (;;) {
+                            if (((old >> (shift + PK_FREE_BITS)) & PK_OCC_MAX) == PK_OCC_MAX) break;
+                            const uint32_t seen = atomicCAS(wp, old, old + (1u << (shift + PK_FREE_BITS)));
+                            if (seen == old) { done = true; break; }
+                            old = seen;
+                        }
+                    }
+                    if (!done) {
+                        global_cell_add(&grid[(size_t)y * geom.gh + phys_col(geom, (uint32_t)x, slot_shift)],
+                                        is_free ? CELL_FREE_INC : CELL_OCC_INC, &saturated);
+                        ext_add(s_ext, x, y, x, y);
+                        spilled++;
+                    }
+                }
+            }
+            // GridRayIterator::next (ray.rs:96-104)
+            if (error > 0.0f) {
+                y += y_inc;
+                error = __fsub_rn(error, delta_x);
+                cyf = __fadd_rn(cyf, y_step);
+                dys = __fsub_rn(sy, cyf);
+                dy2 = __fmul_rn(dys, dys);
+                inside = (unsigned)y < (unsigned)gh;
+                ly += y_inc;
+                if ((unsigned)ly < (unsigned)wh) {
+                    row = s_row[ly];
+                    row_w = row.y >> 16;
+                    lx = x - (row.y & 0xffff);
+                } else {
+                    row_w = 0;
+                }
+            } else {
+                x += x_inc;
+                error = __fadd_rn(error, delta_y);
+                cxf = __fadd_rn(cxf, x_step);
+                dxs = __fsub_rn(sx, cxf);
+                dx2 = __fmul_rn(dxs, dxs);
+                inside = (unsigned)x < (unsigned)gw;
+                lx += x_inc;
+            }
+            remaining -= 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- write-back, row by row: one warp per window row, one lane per 8-cell group (a 128-bit
+    // shared load -> two 128-bit global RMWs); RAY_WB_ROWS rows are in flight per warp.
+    constexpr int RAY_WB_ROWS = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
+    int exmin = 0x7fffffff, eymin = 0x7fffffff, exmax = -1, eymax = -1;   // this thread's touched extent
+    for (int ly0 = warp; ly0 < wh; ly0 += n_warps * RAY_WB_ROWS) {
+        for (int g0 = 0; g0 < (RAY_MAX_RADIUS * 2 + 16) / 8; g0 += 32) {
+            uint4 d[RAY_WB_ROWS], va[RAY_WB_ROWS], vb[RAY_WB_ROWS];
+            uint4* gp[RAY_WB_ROWS];
+            bool nz[RAY_WB_ROWS];
+            bool any_row = false;
+#pragma unroll
+            for (int j = 0; j < RAY_WB_ROWS; ++j) {
+                const int ly = ly0 + j * n_warps;
+                nz[j] = false;
+                if (ly < wh) {
+                    const int2 row = s_row[ly];
+                    const int groups = row.y >> 19;          // width / 8
+                    const int g = g0 + lane;
+                    any_row |= g0 < groups;
+                    if (g < groups) {
+                        d[j] = win4[(row.x >> 3) + g];
+                        nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
+                        if (nz[j]) {
+                            const int gx0 = (row.y & 0xffff) + 8 * g;
+                            exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
+                            eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
+                            gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + ly) * geom.gh +
+                                                             phys_col(geom, (uint32_t)gx0, slot_shift));
+                        }
+                    }
+                }
+            }
+            if (!any_row) break;   // warp-uniform: no row of this batch reaches group g0
+#pragma unroll
+            for (int j = 0; j < RAY_WB_ROWS; ++j)
+                if (nz[j]) { va[j] = gp[j][0]; vb[j] = gp[j][1]; }
+#pragma unroll
+            for (int j = 0; j < RAY_WB_ROWS; ++j) {
+                if (nz[j]) {
+                    // group-level fast path: no occupied hit among the 8 window cells (a packed value is
+                    // then the free count itself) and no counter of the 8 grid cells at or above 2^15
+                    // (it cannot saturate by one scan's increment): eight plain adds
+                    const uint32_t occ_any = (d[j].x | d[j].y | d[j].z | d[j].w) & 0xF800F800u;
+                    const uint32_t high_any = (va[j].x | va[j].y | va[j].z | va[j].w | vb[j].x | vb[j].y | vb[j].z | vb[j].w) & 0x80008000u;
+                    if ((occ_any | high_any) == 0u) {
+                        va[j].x += d[j].x & 0xffffu; va[j].y += d[j].x >> 16;
+                        va[j].z += d[j].y & 0xffffu; va[j].w += d[j].y >> 16;
+                        vb[j].x += d[j].z & 0xffffu; vb[j].y += d[j].z >> 16;
+                        vb[j].z += d[j].w & 0xffffu; vb[j].w += d[j].w >> 16;
+                    } else {
+                        auto apply = [&](uint32_t g, uint32_t packed16) {
+                            const uint32_t delta = (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16);
+                            return cell_sat_add(g, delta, &saturated);
+                        };
+                        va[j].x = apply(va[j].x, d[j].x & 0xffffu); va[j].y = apply(va[j].y, d[j].x >> 16);
+                        va[j].z = apply(va[j].z, d[j].y & 0xffffu); va[j].w = apply(va[j].w, d[j].y >> 16);
+                        vb[j].x = apply(vb[j].x, d[j].z & 0xffffu); vb[j].y = apply(vb[j].y, d[j].z >> 16);
+                        vb[j].z = apply(vb[j].z, d[j].w & 0xffffu); vb[j].w = apply(vb[j].w, d[j].w >> 16);
+                    }
+                    gp[j][0] = va[j];
+                    gp[j][1] = vb[j];
+                }
+            }
+        }
+    }
+    ext_add(s_ext, exmin, eymin, exmax, eymax);
+    __syncthreads();
+    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, slot_shift);
+    if (saturated) atomicAdd(&counters->saturated, 1ull);
+    if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
+}
+
+cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
+                              uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
+                              const int32_t* slot_of, uint32_t* cells, SlotMeta* meta,
+                              size_t cells_per_grid, int radius_cells, StepCounters* counters,
+                              uint64_t* window_cells, bool force_generic) {
+    int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
+    threads = threads < 128 ? 128 : (threads > RAY_MAX_THREADS ? RAY_MAX_THREADS : threads);
+    // preferred: the packed 16-bit window (two CTAs per SM at long range)
+    if (!force_generic && geom.gw % 8u == 0u && cells_per_grid % 8u == 0u && scan.n_beams <= RAY_PACKED_MAX_BEAMS) {
+        int radius = radius_cells < 1 ? 1 : (radius_cells > RAY_MAX_RADIUS ? RAY_MAX_RADIUS : radius_cells);
+        while (radius > 1 && (size_t)ray_window_cells_upper_bound_packed(radius) * 2 > (size_t)RAY_MAX_SMEM) radius--;
+        const size_t wmax = (size_t)ray_window_cells_upper_bound_packed(radius);
+        *window_cells = wmax;
+        k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
+                                                                  cells_per_grid, radius, counters);
+        return cudaSuccess;
+    }
+    const bool vec = (geom.gw % 4u == 0u) && (cells_per_grid % 4u == 0u);
+    // largest disc radius whose row-aligned window fits the shared-memory budget
+    int radius = radius_cells < 1 ? 1 : (radius_cells > RAY_MAX_RADIUS ? RAY_MAX_RADIUS : radius_cells);
+    while (radius > 1 && (size_t)ray_window_cells_upper_bound(radius, vec) * 4 > (size_t)RAY_MAX_SMEM) radius--;
+    const size_t wmax = (size_t)ray_window_cells_upper_bound(radius, vec);
+    const size_t smem = wmax * 4;
+    *window_cells = wmax;
+    if (vec)
+        k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
+                                                               cells_per_grid, radius, counters);
+    else
+        k_ray_update<false><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
+                                                                cells_per_grid, radius, counters);
+    return cudaSuccess;
+}
+
+cudaError_t configure_ray_kernels() {
+    // per-device opt-in to the large dynamic shared-memory window
+    cudaError_t e = cudaFuncSetAttribute(k_ray_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ray_update_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_ray_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
+}
+
+}  // namespace slamrs

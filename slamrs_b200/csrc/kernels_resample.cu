@@ -1,0 +1,459 @@
+// The resampler up to the copy lists: k_weights (particle.rs:40-56, 59-65, 85-91), k_resample_indices
+// (particle.rs:78-101) with the survivor list, k_mark_alive, k_plan (slot tables and copy items).
+#include "kernels_common.cuh"
+
+namespace slamrs {
+
+// =============================================================================== k_weights
+
+constexpr int W_THREADS = 1024;
+constexpr int W_CLUSTER = 8;   // CTAs of the (portable-size) thread-block cluster that shares the reduction
+
+// normalize_weights (particle.rs:49-56), the argmax of particle.rs:40-46 and the running sum of
+// particle.rs:85-91 over the WHOLE population, on one thread-block cluster: 8 CTAs x 1024
+// threads, each thread folds a contiguous chunk left to right, chunk sums are combined by a fixed
+// shuffle tree inside the CTA and the 8 CTA totals are exchanged through distributed shared
+// memory. The combination order depends only on N: bit-identical on every GPU and every run.
+__global__ void __cluster_dims__(W_CLUSTER, 1, 1) __launch_bounds__(W_THREADS)
+k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __restrict__ w_norm,
+          double* __restrict__ cum, StepCounters* counters) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t crank = cluster.block_rank();
+    __shared__ double s_warp[33];
+    __shared__ double s_tot[3][W_CLUSTER];          // CTA totals (raw, normalised, squared), filled by the peers
+    __shared__ long long s_key[32];
+    __shared__ uint32_t s_arg[32];
+    __shared__ long long s_ckey[W_CLUSTER];         // per-CTA argmax candidates (read by CTA 0)
+    __shared__ uint32_t s_carg[W_CLUSTER];
+    cluster.sync();   // every CTA of the cluster is running before its shared memory is written remotely
+    const uint32_t gt = crank * W_THREADS + threadIdx.x;
+    const uint32_t chunk = (n + W_CLUSTER * W_THREADS - 1) / (W_CLUSTER * W_THREADS);
+    const uint32_t lo = min(n, gt * chunk), hi = min(n, lo + chunk);
+
+    if (gt == 0) {   // per-step counters start from zero
+        counters->clamped = 0ull; counters->saturated = 0ull; counters->spilled = 0ull;
+        counters->n_alive = 0ull; counters->copy_bytes = 0ull; counters->copy_max_rows = 0ull;
+    }
+
+    // pass 1: sum of the raw weights
+    double part = 0.0;
+    for (uint32_t i = lo; i < hi; ++i) part = __dadd_rn(part, results[i].weight);
+    double cta_sum;
+    block_excl_scan_f64(part, s_warp, &cta_sum);
+    if (threadIdx.x < W_CLUSTER) cluster.map_shared_rank(&s_tot[0][0], threadIdx.x)[crank] = cta_sum;
+    cluster.sync();
+    double sum = 0.0;
+#pragma unroll
+    for (int r = 0; r < W_CLUSTER; ++r) sum = __dadd_rn(sum, s_tot[0][r]);
+
+    // pass 2: normalise, argmax candidate, chunk sums of the normalised weights
+    double npart = 0.0, sqpart = 0.0;
+    long long best_key = (long long)0x8000000000000000ull;
+    uint32_t best_i = 0;
+    bool have = false;
+    for (uint32_t i = lo; i < hi; ++i) {
+        const double w = __ddiv_rn(results[i].weight, sum);
+        w_norm[i] = w;
+        npart = __dadd_rn(npart, w);
+        sqpart = __dadd_rn(sqpart, __dmul_rn(w, w));
+        const long long k = total_order_key(w);
+        if (!have || k >= best_key) { best_key = k; best_i = i; have = true; }  // last max wins
+    }
+    double cta_n, cta_sq;
+    block_excl_scan_f64(sqpart, s_warp, &cta_sq);
+    const double offset = block_excl_scan_f64(npart, s_warp, &cta_n);
+    if (threadIdx.x < W_CLUSTER) cluster.map_shared_rank(&s_tot[1][0], threadIdx.x)[crank] = cta_n;
+    if (threadIdx.x == 0) cluster.map_shared_rank(&s_tot[2][0], 0)[crank] = cta_sq;
+
+    // argmax by f64::total_cmp, ties -> highest index (Iterator::max_by returns the last maximum)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (!have) { best_key = (long long)0x8000000000000000ull; best_i = 0; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long ok = __shfl_down_sync(0xffffffffu, best_key, o);
+        const uint32_t oi = __shfl_down_sync(0xffffffffu, best_i, o);
+        const bool ohave = __shfl_down_sync(0xffffffffu, (int)have, o) != 0;
+        if (ohave && (!have || ok > best_key || (ok == best_key && oi > best_i))) { best_key = ok; best_i = oi; have = true; }
+    }
+    if (lane == 0) { s_key[wid] = have ? best_key : (long long)0x8000000000000000ull; s_arg[wid] = have ? best_i : 0xffffffffu; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long bk = 0; uint32_t bi = 0xffffffffu; bool h = false;
+        for (int w = 0; w < W_THREADS / 32; ++w) {
+            if (s_arg[w] == 0xffffffffu) continue;
+            if (!h || s_key[w] > bk || (s_key[w] == bk && s_arg[w] > bi)) { bk = s_key[w]; bi = s_arg[w]; h = true; }
+        }
+        cluster.map_shared_rank(&s_ckey[0], 0)[crank] = bk;
+        cluster.map_shared_rank(&s_carg[0], 0)[crank] = bi;
+    }
+    cluster.sync();
+
+    // running sum of the normalised weights (the `c += weight[i]` of particle.rs:85-91)
+    double cta_off = 0.0;
+    for (uint32_t r = 0; r < crank; ++r) cta_off = __dadd_rn(cta_off, s_tot[1][r]);
+    double c = __dadd_rn(cta_off, offset);
+    for (uint32_t i = lo; i < hi; ++i) {
+        c = __dadd_rn(c, w_norm[i]);
+        cum[i] = c;
+    }
+    if (gt == 0) {
+        long long bk = 0; uint32_t bi = 0; bool h = false;
+        for (int r = 0; r < W_CLUSTER; ++r) {
+            if (s_carg[r] == 0xffffffffu) continue;
+            if (!h || s_ckey[r] > bk || (s_ckey[r] == bk && s_carg[r] > bi)) { bk = s_ckey[r]; bi = s_carg[r]; h = true; }
+        }
+        counters->max_particle = bi;
+        counters->sum = sum;
+        // number_of_effective_particles (particle.rs:59-65) of the normalised weights, before resampling
+        double sq = 0.0;
+        for (int r = 0; r < W_CLUSTER; ++r) sq = __dadd_rn(sq, s_tot[2][r]);
+        counters->n_eff = __ddiv_rn(1.0, sq);
+    }
+}
+
+void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
+                    double* cum, StepCounters* counters) {
+    k_weights<<<W_CLUSTER, W_THREADS, 0, stream>>>(results, n_total, w_norm, cum, counters);
+}
+
+// =============================================================================== k_resample_indices
+
+// first i with !(u_m > cum[i]) for the zero-based new-particle index m0 (particle.rs:84-94)
+__device__ __forceinline__ uint32_t resample_source(const double* __restrict__ cum, uint32_t n, double U, uint32_t m0,
+                                                    bool* ran_off) {
+    const double num = (double)n;
+    const double r = __ddiv_rn(__dmul_rn(U, 1.0), num);   // particle.rs:84: r = rand::random::<f64>() * 1.0 / N
+    // particle.rs:89: u = r + (m as f64 - 1.0) * 1.0 / N with m = m0 + 1
+    const double u = __dadd_rn(r, __ddiv_rn(__dmul_rn(__dsub_rn((double)(m0 + 1u), 1.0), 1.0), num));
+    // particle.rs:91-94: advance i while u > c. c is non-decreasing (weights >= 0), so the loop
+    // stops at the first i with !(u > cum[i]); found here by bisection.
+    uint32_t lo = 0, hi = n;  // answer in [lo, hi]; hi == n means "ran off the end"
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (u > cum[mid]) lo = mid + 1; else hi = mid;
+    }
+    *ran_off = lo >= n;   // the reference would index out of bounds and panic; clamp and flag
+    return lo >= n ? n - 1 : lo;
+}
+
+// Also builds the list of local particles that survive (some index selects them): a particle that
+// no entry of the index vector selects is dropped by the resampler (particle.rs:88-104 builds the
+// new generation only from old[i]); integrating the scan into its grid would be unobservable work,
+// so the ray kernel runs on the survivors only. The thread of the FIRST new particle that selects a
+// local source appends it (the index vector is non-decreasing, so "first" = differs from the
+// predecessor's source, which comes from the neighbouring lane).
+__global__ void __launch_bounds__(256)
+k_resample_indices(const ParticleResult* __restrict__ results, const double* __restrict__ cum, uint32_t n,
+                   const double* __restrict__ u01_caller, uint64_t seed, uint64_t step, uint32_t* __restrict__ idx,
+                   float* __restrict__ pose_next, uint32_t first_particle, uint32_t n_local, bool build_alive,
+                   uint32_t* __restrict__ alive_list, StepCounters* counters) {
+    const uint32_t m0 = blockIdx.x * blockDim.x + threadIdx.x;  // zero-based new-particle index
+    const double U = u01_caller ? *u01_caller : slamrs_stream::resample_uniform(seed, step);
+    const int lane = threadIdx.x & 31;
+    bool ran_off = false;
+    uint32_t src_idx = 0xffffffffu;
+    if (m0 < n) {
+        src_idx = resample_source(cum, n, U, m0, &ran_off);
+        if (ran_off) atomicAdd(&counters->clamped, 1ull);
+        idx[m0] = src_idx;
+        const ParticleResult src = results[src_idx];
+        if (m0 >= first_particle && m0 < first_particle + n_local) {
+            float* q = pose_next + 3 * (size_t)(m0 - first_particle);
+            q[0] = src.x; q[1] = src.y; q[2] = src.theta;
+        }
+        // estimated_pose(), slam.rs:77-81: new generation indexed by the pre-resample argmax
+        if ((unsigned long long)m0 == counters->max_particle) {
+            counters->est_pose[0] = src.x; counters->est_pose[1] = src.y; counters->est_pose[2] = src.theta;
+        }
+    }
+    if (!build_alive) return;   // uniform over the grid
+    uint32_t prev = __shfl_up_sync(0xffffffffu, src_idx, 1);
+    if (lane == 0 && m0 > 0 && m0 < n) {
+        bool dummy;
+        prev = resample_source(cum, n, U, m0 - 1u, &dummy);
+    }
+    const bool alive = m0 < n && (m0 == 0 || prev != src_idx) && src_idx >= first_particle &&
+                       src_idx < first_particle + n_local;
+    // warp-aggregated append (order is irrelevant: particles are independent)
+    const unsigned mask = __ballot_sync(0xffffffffu, alive);
+    if (mask) {
+        const int leader = __ffs(mask) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&counters->n_alive, (unsigned long long)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (alive) alive_list[base + __popc(mask & ((1u << lane) - 1u))] = src_idx - first_particle;
+    }
+}
+
+void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
+                             uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,
+                             uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
+                             bool build_alive, uint32_t* alive_list, StepCounters* counters) {
+    k_resample_indices<<<(n_total + 255) / 256, 256, 0, stream>>>(results, cum, n_total, u01_caller, seed, step, idx,
+                                                                 pose_next, first_particle, n_local, build_alive,
+                                                                 alive_list, counters);
+}
+
+// =============================================================================== k_mark_alive
+// The survivor list is normally built by k_resample_indices. This kernel builds it on its own:
+// with all_particles the list is the identity (the reference's order of work: every particle's
+// grid receives the scan).
+__global__ void __launch_bounds__(256)
+k_mark_alive(const uint32_t* __restrict__ idx, uint32_t n_total, uint32_t first_particle, uint32_t n_local,
+             bool all_particles, uint32_t* __restrict__ alive_list, StepCounters* counters) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false;
+    if (j < n_local) {
+        if (all_particles) {
+            alive = true;
+        } else {
+            const uint32_t v = first_particle + j;
+            uint32_t lo = 0, hi = n_total;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (idx[mid] < v) lo = mid + 1; else hi = mid;
+            }
+            alive = lo < n_total && idx[lo] == v;
+        }
+    }
+    // warp-aggregated append (order is irrelevant: particles are independent)
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&counters->n_alive, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (alive) alive_list[base + __popc(m & ((1u << lane) - 1u))] = j;
+    }
+}
+
+void launch_mark_alive(cudaStream_t stream, const uint32_t* idx, uint32_t n_total, uint32_t first_particle,
+                       uint32_t n_local, bool all_particles, uint32_t* alive_list, StepCounters* counters) {
+    k_mark_alive<<<(n_local + 255) / 256, 256, 0, stream>>>(idx, n_total, first_particle, n_local, all_particles,
+                                                           alive_list, counters);
+}
+
+// =============================================================================== k_plan
+// Turns the (non-decreasing) index vector into work for this rank's output range [lo, lo+S):
+//   0  source is local and this is its first use here   -> the grid stays where it is
+//   1  source is local, further use                     -> copy from the kept grid into a free slot
+//   2  source lives on another GPU, first use here      -> copy over NVLink into a free slot
+//   3  source lives on another GPU, further use         -> likewise (every 16th use re-reads the source)
+// All copies form ONE list in output order; copies of one source are adjacent, and every
+// COPY_FAN-th of them is a "leader": the copy kernel reads the source once per leader and stores it
+// to the whole sub-run. Free slots = slots of local particles nobody here keeps + the persistent
+// spare slots. A dropped slot whose grid another GPU copies from in this step ("unsafe") is not
+// handed out now -- it joins the spare list of the next step -- so no rank ever writes a grid
+// that a peer may still be reading, and one cross-GPU barrier per resampling is enough. That needs
+// n_unsafe <= n_spare; otherwise the step reports SLAMRS_E_STAGING (raise spare_slots).
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t lo, uint32_t hi, uint32_t v) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// With n_local <= PLAN_STAGED_MAX_S the index range, the slot tables, the class bytes and the free
+// list live in shared memory (22 bytes per particle): the planner is a chain of short sequential
+// passes whose cost is load latency, and shared memory cuts that by an order of magnitude.
+constexpr uint32_t PLAN_STAGED_MAX_S = 8192;
+__host__ __device__ inline size_t plan_staged_bytes(uint32_t S) { return (size_t)S * 22u + 64u; }
+
+__global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ uint32_t s_warp[33];
+    const uint32_t S = a.n_local, lo = a.rank * a.n_local, hi = lo + S;
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    const uint32_t chunk = (S + T - 1) / T;
+    const uint32_t c0 = min(S, t * chunk), c1 = min(S, c0 + chunk);
+    const uint32_t E = (uint32_t)a.counters->n_spare;
+
+    // working arrays: shared memory when staged, the global scratch otherwise
+    uint32_t* idx_l;       // idx[lo .. hi)
+    int32_t* slot_old;     // read-only copy
+    int32_t* slot_new;
+    int32_t* free_list;    // [safe | spare | unsafe]
+    uint8_t* keep;
+    uint8_t* need;
+    if (a.staged) {
+        idx_l = reinterpret_cast<uint32_t*>(s_dyn);
+        slot_old = reinterpret_cast<int32_t*>(idx_l + S);
+        slot_new = slot_old + S;
+        free_list = slot_new + S;          // 2 S + 1 entries (E <= S when staged)
+        keep = reinterpret_cast<uint8_t*>(free_list + 2 * (size_t)S + 4);
+        need = keep + S;
+        for (uint32_t j = t; j < S; j += T) { idx_l[j] = a.idx[lo + j]; slot_old[j] = a.slot_old[j]; keep[j] = 0; }
+    } else {
+        idx_l = const_cast<uint32_t*>(a.idx) + lo;
+        slot_old = const_cast<int32_t*>(a.slot_old);
+        slot_new = a.slot_new;
+        free_list = a.free_list;
+        keep = reinterpret_cast<uint8_t*>(a.keep);
+        need = reinterpret_cast<uint8_t*>(a.need);
+        for (uint32_t j = t; j < S; j += T) keep[j] = 0;
+    }
+    __syncthreads();
+
+    // ---- classify new particles
+    uint32_t nA = 0, nR = 0;
+    for (uint32_t m = t; m < S; m += T) {
+        const uint32_t src = idx_l[m];
+        const bool first = (m == 0) || (idx_l[m - 1] != src);
+        const bool local = (src >= lo && src < hi);
+        int cls;
+        if (local && first) {
+            cls = 0;
+            keep[src - lo] = 1;
+            slot_new[m] = slot_old[src - lo];
+        } else if (local) cls = 1;
+        else if (first) cls = 2;
+        else cls = 3;
+        need[m] = (uint8_t)cls;
+        nA += (first ? 1u : 0u);
+        nR += (cls == 2 ? 1u : 0u);
+    }
+    __syncthreads();
+
+    // ---- classify old slots: 0 = kept, 1 = free & safe, 2 = free but read by another GPU this step.
+    // A slot that is not kept has no local consumer; idx is non-decreasing, so its consumers (if
+    // any) are all before this rank's range (v < idx[lo]) or all after it (v > idx[hi-1]).
+    const uint32_t idx_first = idx_l[0], idx_last = idx_l[S - 1];
+    for (uint32_t j = t; j < S; j += T) {
+        int f = 0;
+        if (!keep[j]) {
+            f = 1;
+            if (a.world > 1) {
+                const uint32_t v = lo + j;
+                if (v < idx_first && lo > 0) {
+                    const uint32_t p = lower_bound_u32(a.idx, 0, lo, v);
+                    if (p < lo && a.idx[p] == v) f = 2;
+                } else if (v > idx_last && hi < a.n_total) {
+                    const uint32_t p = lower_bound_u32(a.idx, hi, a.n_total, v);
+                    if (p < a.n_total && a.idx[p] == v) f = 2;
+                }
+            }
+        }
+        keep[j] = (uint8_t)f;
+    }
+    __syncthreads();
+
+    // ---- ordered compaction of the free slots: [safe | spare | unsafe]
+    uint32_t n_safe_c = 0, n_unsafe_c = 0;
+    for (uint32_t j = c0; j < c1; ++j) { n_safe_c += (keep[j] == 1); n_unsafe_c += (keep[j] == 2); }
+    uint32_t n_safe, n_unsafe;
+    uint32_t ps = block_excl_scan_u32(n_safe_c, s_warp, &n_safe);
+    uint32_t pu = block_excl_scan_u32(n_unsafe_c, s_warp, &n_unsafe);
+    for (uint32_t j = c0; j < c1; ++j) {
+        if (keep[j] == 1) free_list[ps++] = slot_old[j];
+        else if (keep[j] == 2) free_list[n_safe + E + pu++] = slot_old[j];
+    }
+    for (uint32_t e = t; e < E; e += T) free_list[n_safe + e] = a.spare_list[e];
+    const uint32_t usable = n_safe + E;   // slots that may be written in this step
+
+    // ---- ordered ranks of the consumers (every new particle that does not keep a grid in place)
+    uint32_t n_cons_c = 0;
+    for (uint32_t m = c0; m < c1; ++m) n_cons_c += (need[m] != 0);
+    uint32_t n_cons;
+    uint32_t pos = block_excl_scan_u32(n_cons_c, s_warp, &n_cons);
+    __syncthreads();  // free_list complete
+
+    // ---- the copy list. run_first = first position of the current source's run in this range.
+    const uint32_t pos_start = pos;
+    uint32_t n_lead_c = 0;
+    const unsigned long long est_m = a.counters->max_particle - lo;   // >= S when another rank owns the estimate
+    if (t == 0 && est_m >= S) a.counters->est_meta_ptr = 0ull;
+    uint32_t run_first = c0 < c1 ? lower_bound_u32(idx_l, 0, S, idx_l[c0]) : 0u;
+    for (uint32_t m = c0; m < c1; ++m) {
+        const int cls = need[m];
+        const uint32_t src = idx_l[m];
+        if (m > c0 && idx_l[m - 1] != src) run_first = m;
+        if (cls == 0) {
+            // the published map (slam.rs:83-88) is this particle's grid: it stays in place
+            if (m == est_m) a.counters->est_meta_ptr = (unsigned long long)(uintptr_t)(a.meta + slot_new[m]);
+            continue;
+        }
+        if (pos < usable) {
+            const int32_t dslot = free_list[pos];
+            slot_new[m] = dslot;
+            CopyItem it;
+            if (cls == 1) {
+                const int32_t sslot = slot_old[src - lo];
+                it.src = a.cells + (size_t)sslot * a.cells_per_grid;
+                it.src_meta = a.meta + sslot;
+            } else {
+                const uint32_t owner = src / S;
+                const int32_t sslot = a.results[src].slot;
+                it.src = a.peer_cells[owner] + (size_t)sslot * a.cells_per_grid;
+                it.src_meta = a.peer_meta[owner] + sslot;
+            }
+            it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
+            it.dst_meta = a.meta + dslot;
+            a.copies[pos] = it;
+            if (m == est_m) a.counters->est_meta_ptr = (unsigned long long)(uintptr_t)it.src_meta;   // extent it will have
+            // a local run keeps its first use in place, so its copies start one position later
+            const uint32_t k = (cls == 1) ? (m - run_first - 1u) : (m - run_first);
+            const bool lead = (k % COPY_FAN) == 0u;
+            need[m] = (uint8_t)(lead ? 9 : 8);
+            n_lead_c += lead;
+        } else {
+            // no writable slot left (SLAMRS_E_STAGING): nothing is copied, the filter state is invalid
+            slot_new[m] = (cls == 1) ? slot_old[src - lo] : slot_old[0];
+            need[m] = 10;
+        }
+        pos++;
+    }
+    // ordered list of leader positions within copies[]
+    uint32_t n_lead;
+    uint32_t pl = block_excl_scan_u32(n_lead_c, s_warp, &n_lead);
+    pos = pos_start;
+    for (uint32_t m = c0; m < c1; ++m) {
+        const int cls = need[m];
+        if (cls == 9) a.leaders[pl++] = pos;
+        if (cls >= 8) pos++;
+    }
+    __syncthreads();
+    // ---- next step's spare list: the usable slots nobody took, then this step's unsafe slots
+    const uint32_t used = min(n_cons, usable);
+    for (uint32_t e = t; e < E; e += T) {
+        const uint32_t left = usable - used;   // = E - n_unsafe when nothing is short
+        a.spare_list[e] = e < left ? free_list[used + e] : free_list[usable + (e - left)];
+    }
+    if (a.staged)
+        for (uint32_t m = t; m < S; m += T) a.slot_new[m] = slot_new[m];
+
+    uint32_t distinct, n_remote;
+    block_excl_scan_u32(nA, s_warp, &distinct);
+    block_excl_scan_u32(nR, s_warp, &n_remote);
+    if (t == 0) {
+        a.counters->n_copies = used;
+        a.counters->n_leaders = n_lead;
+        a.counters->n_pulls = n_remote;
+        a.counters->distinct = distinct;
+        a.counters->staging_short = (n_cons > usable) ? (unsigned long long)(n_cons - usable) : 0ull;
+        const unsigned long long mp = a.counters->max_particle;
+        a.counters->est_owner = mp / S;
+        a.counters->est_slot = (mp >= lo && mp < hi) ? (long long)slot_new[mp - lo] : -1ll;
+        if (a.history) {
+            StepRecord r;
+            r.step = a.step; r.n_copies = used; r.n_pulls = n_remote; r.distinct = distinct; r.n_leaders = n_lead;
+            r.n_alive = 0; r.copy_bytes = 0; r.pad = 0;   // filled in by the step's last kernel (k_commit_boxes)
+            a.history[a.step % STEP_HISTORY] = r;
+        }
+    }
+}
+
+bool plan_can_stage(uint32_t n_local, uint32_t n_spare_cap) {
+    return n_local <= PLAN_STAGED_MAX_S && n_spare_cap <= n_local;
+}
+
+void launch_plan(cudaStream_t stream, const PlanArgs& a) {
+    k_plan<<<1, 1024, a.staged ? plan_staged_bytes(a.n_local) : 0, stream>>>(a);
+}
+
+cudaError_t configure_resample_kernels() {
+    return cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_staged_bytes(PLAN_STAGED_MAX_S));
+}
+
+}  // namespace slamrs

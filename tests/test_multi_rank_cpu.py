@@ -64,6 +64,10 @@ def _free_port():
 
 
 def _torchrun(args, env_extra=None, timeout=240):
+    # build both libraries here, once, so that the two ranks never race to (re)build them
+    from oracle import oracle as O
+    from slamrs_b200 import _lib
+    O.lib(); _lib.load()
     env = dict(os.environ)
     env.update({"SLAMRS_ROOT": ROOT, "OMP_NUM_THREADS": "1", "CUDA_VISIBLE_DEVICES": ""})
     env.update(env_extra or {})
