@@ -230,6 +230,37 @@ def test_c5_shape(oracle):
     print(errs[-1])
 
 
+@pytest.mark.parametrize("seed", range(32))
+def test_step_parity_randomised_configurations(oracle, seed):
+    """Random grid sizes (power-of-two and not, multiples of 8 and not), resolutions, beam counts,
+    ranges, particle counts, kernel / copy modes and start poses (some next to a border, some
+    re-scattered mid-run): every step in lockstep with the oracle. compute-sanitizer is not available
+    on the GPU pool; out-of-bounds or stale-extent bugs show up here as a counter mismatch."""
+    rng = np.random.default_rng(1000 + seed)
+    cells = int(rng.choice([64, 96, 100, 128, 200, 256, 250, 512]))
+    res = float(rng.choice([0.02, 0.04, 0.05]))
+    width = cells * res
+    n = int(rng.choice([1, 3, 16, 40]))
+    beams = int(rng.choice([45, 180, 360, 720]))
+    scene = float(rng.choice([1.0, 2.0, 5.0]))
+    rng_m = float(rng.choice([0.5, 1.0, 3.0, 6.0]))
+    flags = int(rng.choice([0, _lib.FLAG_GENERIC_RAY_KERNEL, _lib.FLAG_FULL_GRID_COPY, _lib.FLAG_UPDATE_ALL_PARTICLES,
+                            _lib.FLAG_GENERIC_RAY_KERNEL | _lib.FLAG_UPDATE_ALL_PARTICLES]))
+    off = rng.uniform(-0.45, 0.45, 2) * width          # where the robot starts inside the map
+    cfg = GridMapSlamConfig(position=(float(-width / 2 + off[0]), float(-width / 2 + off[1])), width=width, height=width,
+                            resolution=res, n_particles=n)
+    assert S.grid_cells(width, res) in (cells, cells + 1)
+    scans = make_scans(scene, beams, rng_m, 4)
+
+    def scatter(step, gpu, osl):
+        if step == 2 and n > 1:
+            xyt = np.column_stack([rng.uniform(-0.4, 0.4, n) * width - off[0], rng.uniform(-0.4, 0.4, n) * width - off[1],
+                                   rng.uniform(-np.pi, np.pi, n)]).astype(np.float32)
+            gpu.set_poses(xyt); osl.set_poses(xyt)
+
+    lockstep(oracle, cfg, scans, flags=flags, pre_step=scatter, particles=range(0, n, max(1, n // 6)))
+
+
 def test_pose_outside_grid_emits_nothing(oracle):
     cfg = GridMapSlamConfig(position=(5.0, 5.0), width=1.0, height=1.0, resolution=0.02, n_particles=4)
     lockstep(oracle, cfg, make_scans(1.0, 360, 1.0, 2))
