@@ -41,7 +41,8 @@ enum slamrs_status {
     SLAMRS_E_NO_DEVICE = -5,     /* no CUDA device: there is NO CPU fallback */
     SLAMRS_E_STAGING = -6,       /* cross-GPU migration needed more free grid slots than exist */
     SLAMRS_E_NOT_LOCAL = -7,     /* debug accessor asked for a particle owned by another rank */
-    SLAMRS_E_INTERNAL = -8
+    SLAMRS_E_INTERNAL = -8,
+    SLAMRS_E_WINDOW = -9         /* a grid's informed extent outgrew its windowed slot (slot_cells too small) */
 };
 
 enum slamrs_rng_mode {
@@ -89,6 +90,12 @@ typedef struct slamrs_gpu_config {
     uint32_t spare_slots;  /* extra physical grid slots per GPU used to stage grids that migrate
                               between GPUs at resampling; 0 = automatic (none when world_size==1) */
     uint32_t flags;        /* enum slamrs_flags bits, normally 0 */
+    uint32_t slot_cells;   /* 0: every particle's slot holds the whole grid. Otherwise a power of two >= 256:
+                              a slot holds a slot_cells x slot_cells torus of the grid, enough for the informed
+                              extent of one particle's map (everything else is the prior). Memory per particle
+                              drops from 4*W*H to 4*slot_cells^2 bytes; an extent that outgrows it is reported
+                              as SLAMRS_E_WINDOW. */
+    uint32_t reserved0;    /* must be 0 */
     uint8_t nccl_id[SLAMRS_NCCL_ID_BYTES]; /* from slamrs_gpu_nccl_unique_id, same on all ranks */
 } slamrs_gpu_config;
 
@@ -105,6 +112,7 @@ typedef struct slamrs_gpu_stats {
     uint64_t bytes_per_grid;   /* device bytes of one particle grid */
     uint64_t particles_integrated; /* local particles whose grid received the scan this step */
     uint64_t copy_bytes;       /* bytes the resampling copies read + wrote in this step (device-counted) */
+    uint64_t window_overflow;  /* grids whose informed extent would have outgrown a windowed slot (error) */
 } slamrs_gpu_stats;
 
 /* ------------------------------------------------------------------ lifecycle */

@@ -14,6 +14,7 @@ pub const SLAMRS_E_NO_DEVICE: c_int = -5;
 pub const SLAMRS_E_STAGING: c_int = -6;
 pub const SLAMRS_E_NOT_LOCAL: c_int = -7;
 pub const SLAMRS_E_INTERNAL: c_int = -8;
+pub const SLAMRS_E_WINDOW: c_int = -9;
 
 pub const SLAMRS_RNG_SHARED_STREAM: u32 = 0;
 pub const SLAMRS_RNG_CALLER: u32 = 1;
@@ -51,6 +52,8 @@ pub struct slamrs_gpu_config {
     pub world_size: u32,
     pub spare_slots: u32,
     pub flags: u32,
+    pub slot_cells: u32,
+    pub reserved0: u32,
     pub nccl_id: [u8; SLAMRS_NCCL_ID_BYTES],
 }
 
@@ -68,6 +71,7 @@ pub struct slamrs_gpu_stats {
     pub bytes_per_grid: u64,
     pub particles_integrated: u64,
     pub copy_bytes: u64,
+    pub window_overflow: u64,
 }
 
 extern "C" {

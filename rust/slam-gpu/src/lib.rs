@@ -68,6 +68,8 @@ impl GridMapSlam {
             world_size: 1,
             spare_slots: 0,
             flags: 0,
+            slot_cells: std::env::var("SLAMRS_SLOT_CELLS").ok().and_then(|s| s.parse().ok()).unwrap_or(0),
+            reserved0: 0,
             nccl_id: [0; sys::SLAMRS_NCCL_ID_BYTES],
         };
         let mut h = ptr::null_mut();

@@ -12,6 +12,7 @@ ABI_VERSION = 1
 
 OK = 0
 E_INVALID_ARG, E_CUDA, E_NCCL, E_OOM, E_NO_DEVICE, E_STAGING, E_NOT_LOCAL, E_INTERNAL = -1, -2, -3, -4, -5, -6, -7, -8
+E_WINDOW = -9
 RNG_SHARED_STREAM, RNG_CALLER = 0, 1
 FLAG_GENERIC_RAY_KERNEL = 1
 FLAG_UPDATE_ALL_PARTICLES = 2
@@ -44,6 +45,7 @@ class Config(C.Structure):
         ("rng_mode", C.c_uint32), ("device", C.c_int32),
         ("rank", C.c_uint32), ("world_size", C.c_uint32),
         ("spare_slots", C.c_uint32), ("flags", C.c_uint32),
+        ("slot_cells", C.c_uint32), ("reserved0", C.c_uint32),
         ("nccl_id", C.c_uint8 * NCCL_ID_BYTES),
     ]
 
@@ -52,7 +54,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "step", "grids_copied", "grids_pulled", "distinct_sources", "resample_clamped",
         "counter_saturated", "spilled_cells", "window_cells", "bytes_per_grid", "particles_integrated",
-        "copy_bytes")]
+        "copy_bytes", "window_overflow")]
 
 
 class SlamrsGpuError(RuntimeError):

@@ -373,6 +373,8 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     if ((uint64_t)cfg->grid_w * cfg->grid_h > 0x7fffffffull) return fail(nullptr, SLAMRS_E_INVALID_ARG, "grid too large");
     if (!(cfg->resolution > 0.0f)) return fail(nullptr, SLAMRS_E_INVALID_ARG, "resolution must be positive");
     if (cfg->rng_mode > SLAMRS_RNG_CALLER) return fail(nullptr, SLAMRS_E_INVALID_ARG, "unknown rng_mode");
+    if (cfg->slot_cells != 0 && (cfg->slot_cells < 256u || (cfg->slot_cells & (cfg->slot_cells - 1u)) != 0u))
+        return fail(nullptr, SLAMRS_E_INVALID_ARG, "slot_cells must be 0 (whole grid) or a power of two >= 256");
 
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
@@ -393,8 +395,9 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     h->n_local = h->n_total / h->world;
     h->first = h->rank * h->n_local;
     h->n_cells = cfg->grid_w * cfg->grid_h;
-    h->cells_per_grid = ((size_t)h->n_cells + 31u) & ~(size_t)31u;
-    h->geom = make_map_geom(cfg->pos_x, cfg->pos_y, cfg->resolution, cfg->grid_w, cfg->grid_h);
+    h->geom = make_map_geom(cfg->pos_x, cfg->pos_y, cfg->resolution, cfg->grid_w, cfg->grid_h, cfg->slot_cells);
+    // a slot holds pw x ph cells: the whole grid, or (windowed slots) a power-of-two torus of it
+    h->cells_per_grid = ((size_t)h->geom.pw * h->geom.ph + 31u) & ~(size_t)31u;
 
 #define CREATE_TRY(expr)                                  \
     do {                                                  \
@@ -463,7 +466,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     h->d_flags = (unsigned long long*)((char*)h->d_pool + h->off_flags);
     h->p2p_exchange = h->world > 1 && (cfg->flags & SLAMRS_FLAG_NCCL_EXCHANGE) == 0;
     CREATE_CU(cudaMemsetAsync(h->d_pool, 0, h->pool_header + (size_t)h->n_slots * grid_bytes, h->stream));  // ln(0.5/0.5) = 0
-    h->boxed_copy = (cfg->flags & SLAMRS_FLAG_FULL_GRID_COPY) == 0 && cfg->grid_w % 8u == 0u;
+    h->boxed_copy = (cfg->flags & SLAMRS_FLAG_FULL_GRID_COPY) == 0 && cfg->grid_w % 8u == 0u && h->geom.pw % 8u == 0u;
     for (int i = 0; i < 2; ++i) {
         CREATE_CU(cudaMalloc(&h->d_slot[i], sizeof(int32_t) * h->n_local));
         CREATE_CU(cudaMalloc(&h->d_pose[i], sizeof(float) * 3 * h->n_local));
@@ -699,6 +702,10 @@ int slamrs_gpu_sync(slamrs_gpu_handle* h) {
     if (rc) return rc;
     if (h->h_counters->barrier_timeout)
         return fail(h, SLAMRS_E_INTERNAL, "a peer GPU did not reach the step barrier within the time limit");
+    if (h->h_counters->window_overflow)
+        return fail(h, SLAMRS_E_WINDOW,
+                    "a particle's informed extent outgrew its windowed grid slot; raise slot_cells (the scan was not "
+                    "integrated into that grid)");
     if (h->h_counters->staging_short)
         return fail(h, SLAMRS_E_STAGING,
                     "cross-GPU migration needed more free grid slots than available; raise spare_slots");
@@ -863,6 +870,7 @@ int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out) {
     out->window_cells = h->window_cells;
     out->particles_integrated = c.n_alive;
     out->bytes_per_grid = h->cells_per_grid * sizeof(uint32_t);
+    out->window_overflow = c.window_overflow;
     out->copy_bytes = c.copy_bytes;
     return SLAMRS_OK;
 }
@@ -997,8 +1005,6 @@ int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t
     int32_t slot = 0;
     int rc = local_slot(h, particle, &slot);
     if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(h->d_cells + (size_t)slot * h->cells_per_grid, cells, sizeof(uint32_t) * h->n_cells,
-                              cudaMemcpyHostToDevice, h->stream));
     // extent of the informed cells of the new image (stored unrotated: SlotMeta::ox = 0)
     const int gw = (int)h->geom.gw, gh = (int)h->geom.gh;
     int x0 = gw, y0 = gh, x1 = -1, y1 = -1;
@@ -1016,6 +1022,14 @@ int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t
     }
     SlotMeta m{0, 0, 0, 0, 0, 0, 0, 0};
     if (x1 >= 0) { m.x0 = x0 & ~7; m.y0 = y0; m.x1 = std::min(gw, (x1 + 8) & ~7); m.y1 = y1 + 1; }
+    if ((uint32_t)(m.x1 - m.x0) > h->geom.pw || (uint32_t)(m.y1 - m.y0) > h->geom.ph)
+        return fail(h, SLAMRS_E_WINDOW, "the image's informed extent does not fit the windowed grid slot");
+    // dense image -> scratch, then scattered into the slot (whole-grid slots: a plain row copy)
+    CU_TRY(h, cudaMemcpyAsync(h->d_export, cells, sizeof(uint32_t) * h->n_cells, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_cells + (size_t)slot * h->cells_per_grid, 0, sizeof(uint32_t) * h->cells_per_grid, h->stream));
+    launch_import_slot(h->stream, reinterpret_cast<const uint32_t*>(h->d_export), h->d_cells + (size_t)slot * h->cells_per_grid,
+                       m, h->geom);
+    h->launches++;
     CU_TRY(h, cudaMemcpyAsync(h->d_meta + slot, &m, sizeof(m), cudaMemcpyHostToDevice, h->stream));
     h->est_box_stale = true;
     CU_TRY(h, cudaStreamSynchronize(h->stream));

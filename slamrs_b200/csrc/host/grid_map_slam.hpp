@@ -66,6 +66,7 @@ struct GpuPlacement {  // what the YAML cannot carry
     uint32_t rng_mode = SLAMRS_RNG_SHARED_STREAM;
     uint32_t spare_slots = 0;
     uint32_t flags = 0;  // enum slamrs_flags
+    uint32_t slot_cells = 0;  // 0 = whole-grid slots, power of two >= 256 = windowed slots
     uint8_t nccl_id[SLAMRS_NCCL_ID_BYTES] = {0};
 };
 
@@ -90,6 +91,7 @@ public:
         c.world_size = pl.world_size;
         c.spare_slots = pl.spare_slots;
         c.flags = pl.flags;
+        c.slot_cells = pl.slot_cells;
         for (int i = 0; i < SLAMRS_NCCL_ID_BYTES; ++i) c.nccl_id[i] = pl.nccl_id[i];
         grid_w_ = c.grid_w;
         grid_h_ = c.grid_h;

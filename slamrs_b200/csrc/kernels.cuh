@@ -45,6 +45,7 @@ struct StepCounters {
     unsigned long long copy_bytes;       // bytes read + written by the copy kernels this step
     unsigned long long copy_max_rows;    // tallest region any copy job of this step writes (rows)
     unsigned long long barrier_timeout;  // a peer barrier gave up waiting (error)
+    unsigned long long window_overflow;  // grids whose informed extent would outgrow a windowed slot (error)
     unsigned long long est_meta_ptr;     // SlotMeta whose extent the published map has after this step (0: remote)
     int est_box[4];                      // that extent {x0, y0, x1, y1}; -1 when another rank owns the estimate
     double sum;                          // sum of raw weights (particle.rs:50)
@@ -165,6 +166,7 @@ void launch_estimate_extent(cudaStream_t stream, const SlotMeta* meta, const Ste
 void launch_export_slot(cudaStream_t stream, const uint32_t* grid, const SlotMeta* slot_meta, MapGeom geom,
                         bool as_log_odds, void* out);
 
+void launch_import_slot(cudaStream_t stream, const uint32_t* image, uint32_t* grid, SlotMeta m, MapGeom geom);
 void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
                        StepCounters* counters, uint32_t rank, SlotMeta* meta);
 

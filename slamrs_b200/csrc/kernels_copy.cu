@@ -73,16 +73,17 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
 // (zero outside the source extent) and stores each value to every destination of the sub-run.
 // Bytes that really moved are counted on the device and are what the roofline in bench.py uses.
 
-// All x quantities of a job are in 32-byte units on the ring of one physical grid row
-// (ring size = row units when rows rotate, unbounded otherwise): an "arc" is (start, length).
+// A job works in PHYSICAL slot coordinates. x: 32-byte units on the ring of one slot row (ring size =
+// row units when rows rotate, unbounded otherwise); y: rows on the ring of the slot's rows (ring size =
+// slot height for windowed slots, unbounded otherwise). An "arc" is (start, length).
 struct alignas(16) CopyJob {
     const uint32_t* src;
     uint32_t fan;
-    uint32_t rot;             // destination unit = (source unit + rot) & umask
-    uint32_t n_start, n_len;  // arc of every destination that receives the source's extent
-    int sy0, sy1;             // ... and its rows
-    uint32_t u_start, u_len;  // arc written in every destination (new extent + old extents to clear)
-    int uy0, uy1;             // ... and its rows
+    uint32_t rot;               // destination unit = (source unit + rot) & umask
+    uint32_t n_start, n_len;    // x arc of every destination that receives the source's extent
+    uint32_t ny_start, ny_len;  // ... and its row arc (same rows in source and destination)
+    uint32_t u_start, u_len;    // x arc written in every destination (new extent + old extents to clear)
+    uint32_t uy_start, uy_len;  // ... and its row arc
     uint32_t* dst[COPY_FAN];
 };
 static_assert(sizeof(CopyJob) % 16 == 0, "CopyJob is fetched as 16-byte pieces");
@@ -114,7 +115,8 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
     if (q >= nl) return;
     const int lane = threadIdx.x & 31;
     const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
-    const uint32_t ring = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.gw >> 3);
+    const uint32_t ring = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.pw >> 3);
+    const uint32_t ymask = geom.ymask, yring = geom.ymask == 0xffffffffu ? 0xffffffffu : geom.ph;
     const unsigned long long k = leaders ? leaders[q] : q;
     const bool have = lane < (int)COPY_FAN && k + lane < n && (leaders != nullptr || lane == 0);
     CopyItem it{};
@@ -126,40 +128,40 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
     if (lane == 0) sm = *it.src_meta;
     if (lane < (int)fan) dm = *it.dst_meta;
     // the destination's old extent as a physical arc
-    uint32_t o_start = 0u, o_len = 0u;
-    int oy0 = 0x7fffffff, oy1 = -1;
+    uint32_t o_start = 0u, o_len = 0u, oy_start = 0u, oy_len = 0u;
     if (lane < (int)fan && !meta_empty(dm)) {
         o_start = (phys_col(geom, (uint32_t)dm.x0, dm.ox) >> 3) & umask;
         o_len = (uint32_t)(dm.x1 - dm.x0) >> 3;
-        oy0 = dm.y0; oy1 = dm.y1;
+        oy_start = (uint32_t)dm.y0 & ymask;
+        oy_len = (uint32_t)(dm.y1 - dm.y0);
     }
     // lane 0 folds the arcs (at most 17) and writes the job header
     uint32_t u_start = 0u, u_len = 0u, n_start = 0u, n_len = 0u, rot = 0u;
-    int uy0 = 0x7fffffff, uy1 = -1, sy0 = 0, sy1 = 0;
+    uint32_t uy_start = 0u, uy_len = 0u, ny_start = 0u, ny_len = 0u;
     if (lane == 0 && !meta_empty(sm)) {
         const uint32_t s_start = (phys_col(geom, (uint32_t)sm.x0, sm.ox) >> 3) & umask;
         n_len = (uint32_t)(sm.x1 - sm.x0) >> 3;
         n_start = (phys_col(geom, (uint32_t)sm.x0, align_shift(geom, sm.x0)) >> 3) & umask;   // page-aligned
         rot = (n_start - s_start) & umask;
-        sy0 = sm.y0; sy1 = sm.y1;
-        u_start = n_start; u_len = n_len; uy0 = sy0; uy1 = sy1;
+        ny_start = (uint32_t)sm.y0 & ymask; ny_len = (uint32_t)(sm.y1 - sm.y0);
+        u_start = n_start; u_len = n_len; uy_start = ny_start; uy_len = ny_len;
     }
     for (uint32_t f = 0; f < fan; ++f) {
         const uint32_t bs = __shfl_sync(0xffffffffu, o_start, (int)f), bl = __shfl_sync(0xffffffffu, o_len, (int)f);
-        const int by0 = __shfl_sync(0xffffffffu, oy0, (int)f), by1 = __shfl_sync(0xffffffffu, oy1, (int)f);
-        if (lane == 0) {
+        const uint32_t bys = __shfl_sync(0xffffffffu, oy_start, (int)f), byl = __shfl_sync(0xffffffffu, oy_len, (int)f);
+        if (lane == 0 && bl && byl) {
             arc_cover(u_start, u_len, bs, bl, umask, ring);
-            if (bl) { uy0 = min(uy0, by0); uy1 = max(uy1, by1); }
+            arc_cover(uy_start, uy_len, bys, byl, ymask, yring);
         }
     }
     CopyJob* job = jobs + q;
     if (lane < (int)COPY_FAN) job->dst[lane] = lane < (int)fan ? it.dst : nullptr;
     if (lane == 0) {
-        if (u_len == 0u || uy1 <= uy0) { u_start = u_len = 0u; uy0 = uy1 = 0; }
+        if (u_len == 0u || uy_len == 0u) { u_start = u_len = 0u; uy_start = uy_len = 0u; }
         job->src = it.src; job->fan = fan; job->rot = rot;
-        job->n_start = n_start; job->n_len = n_len; job->sy0 = sy0; job->sy1 = sy1;
-        job->u_start = u_start; job->u_len = u_len; job->uy0 = uy0; job->uy1 = uy1;
-        if (uy1 > uy0) atomicMax(&counters->copy_max_rows, (unsigned long long)(uy1 - uy0));
+        job->n_start = n_start; job->n_len = n_len; job->ny_start = ny_start; job->ny_len = ny_len;
+        job->u_start = u_start; job->u_len = u_len; job->uy_start = uy_start; job->uy_len = uy_len;
+        if (uy_len) atomicMax(&counters->copy_max_rows, (unsigned long long)uy_len);
     }
 }
 
@@ -173,8 +175,8 @@ constexpr int BOX_CTAS_PER_SM = 256;
 template <int UNROLL, int MINB, int THREADS>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restrict__ n_jobs,
-             uint32_t row_units /* 32-byte units per physical grid row */, uint32_t umask, uint32_t items_per_cta,
-             StepCounters* counters) {
+             uint32_t row_units /* 32-byte units per physical slot row */, uint32_t umask, uint32_t ymask,
+             uint32_t items_per_cta, StepCounters* counters) {
     __shared__ CopyJob s_job;
     __shared__ unsigned long long s_moved;
     if (threadIdx.x == 0) s_moved = 0ull;
@@ -199,15 +201,14 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
             if (wn < total) next_job = reinterpret_cast<const uint4*>(jobs + (uint32_t)wn / bands)[threadIdx.x];
         }
         __syncthreads();
-        const int uy0 = s_job.uy0, uy1 = s_job.uy1;
-        const int rows = uy1 - uy0;
-        if (rows <= 0) continue;
-        const int rows_per_band = (rows + (int)bands - 1) / (int)bands;
-        const int r0 = uy0 + (int)band * rows_per_band, r1 = min(uy1, r0 + rows_per_band);
+        const uint32_t rows = s_job.uy_len;
+        if (rows == 0u) continue;
+        const uint32_t rows_per_band = (rows + bands - 1u) / bands;
+        const uint32_t r0 = band * rows_per_band, r1 = min(rows, r0 + rows_per_band);   // offsets into the row arc
         if (r0 >= r1) continue;
-        const uint32_t u_start = s_job.u_start, uw = s_job.u_len;
+        const uint32_t u_start = s_job.u_start, uw = s_job.u_len, uy_start = s_job.uy_start;
         const uint32_t n_start = s_job.n_start, n_len = s_job.n_len, rot = s_job.rot;
-        const int sy0 = s_job.sy0, sy1 = s_job.sy1;
+        const uint32_t ny_start = s_job.ny_start, ny_len = s_job.ny_len;
         const uint32_t fan = s_job.fan;
         const uint32_t count = (uint32_t)(r1 - r0) * uw;
         const V8* src = reinterpret_cast<const V8*>(s_job.src);
@@ -221,11 +222,11 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
                 v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
                 if (i < count) {
                     const uint32_t rr = i / uw;
-                    const int ey = r0 + (int)rr;
+                    const uint32_t py = (uy_start + r0 + rr) & ymask;          // physical row (same in source and destination)
                     const uint32_t du = (u_start + (i - rr * uw)) & umask;     // destination unit on the ring
-                    off[u] = (uint32_t)ey * row_units + du;
-                    if (((du - n_start) & umask) < n_len && ey >= sy0 && ey < sy1) {
-                        v[u] = ld_stream_v8(src + ((uint32_t)ey * row_units + ((du - rot) & umask)));
+                    off[u] = py * row_units + du;
+                    if (((du - n_start) & umask) < n_len && ((py - ny_start) & ymask) < ny_len) {
+                        v[u] = ld_stream_v8(src + (py * row_units + ((du - rot) & umask)));
                         moved++;
                     }
                 }
@@ -258,7 +259,7 @@ void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_
     // anything else in larger CTAs), 4 loads in flight per thread, grid oversubscribed for balance,
     // about 6 items per CTA
     k_copy_boxed<4, 24, BOX_THREADS><<<num_sms * BOX_CTAS_PER_SM, BOX_THREADS, 0, stream>>>(
-        (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom.gw / 8u, umask, 6u, counters);
+        (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom.pw / 8u, umask, geom.ymask, 6u, counters);
 }
 size_t copy_job_bytes() { return sizeof(CopyJob); }
 

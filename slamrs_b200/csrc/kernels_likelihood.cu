@@ -61,7 +61,8 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
     const ParticleResult r = results[first_particle + p];
     const float nx = r.x, ny = r.y, ntheta = r.theta;
     const uint32_t* grid = cells + (size_t)r.slot * cells_per_grid;
-    const int shift = meta[r.slot].ox;   // row rotation of this particle's slot
+    const SlotMeta sm = meta[r.slot];    // informed extent (outside it a windowed slot must not be read) ...
+    const int shift = sm.ox;             // ... and row rotation of this particle's slot
 
     double lp = log(1.0);
     for (uint32_t base = 0; base < scan.n_beams; base += 32u * LK_UNROLL) {
@@ -78,7 +79,8 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
                 if (grid_is_valid(gx, gy, geom.gw, geom.gh)) {
                     const size_t column = (size_t)f32_as_usize(gx), row = (size_t)f32_as_usize(gy);
                     // index(): map.rs:201-204, then the slot's row rotation
-                    cell[u] = __ldg(&grid[row * geom.gh + phys_col(geom, (uint32_t)column, shift)]);
+                    if (!geom.windowed || ((int)column >= sm.x0 && (int)column < sm.x1 && (int)row >= sm.y0 && (int)row < sm.y1))
+                        cell[u] = __ldg(&grid[phys_index(geom, (uint32_t)column, (uint32_t)row, shift)]);
                 }
             }
         }

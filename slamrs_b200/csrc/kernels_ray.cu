@@ -64,6 +64,18 @@ __device__ __forceinline__ int ray_slot_shift(const MapGeom& geom, const ScanDev
     return s_shift[0];
 }
 
+// Windowed slots: would the informed extent still fit the slot after this scan? `reach` bounds how far
+// from the start cell a ray can write (measured range in cells + the slack the host adds). The test is
+// conservative (bounding square of the reach) and uniform over the CTA.
+__device__ __forceinline__ bool window_would_overflow(const MapGeom& geom, const SlotMeta* meta, int cx0, int cy0, int reach) {
+    if (!geom.windowed) return false;
+    const SlotMeta m = *meta;
+    int x0 = max(0, cx0 - reach) & ~7, x1 = min((int)geom.gw, (min((int)geom.gw, cx0 + reach + 1) + 7) & ~7);
+    int y0 = max(0, cy0 - reach), y1 = min((int)geom.gh, cy0 + reach + 1);
+    if (m.x1 > m.x0 && m.y1 > m.y0) { x0 = min(x0, m.x0); x1 = max(x1, m.x1); y0 = min(y0, m.y0); y1 = max(y1, m.y1); }
+    return (uint32_t)(x1 - x0) > geom.pw || (uint32_t)(y1 - y0) > geom.ph;
+}
+
 __device__ __forceinline__ void ext_commit(const int* s_ext, SlotMeta* meta, int gw, int shift) {
     if (s_ext[2] < s_ext[0]) return;
     SlotMeta b = *meta;
@@ -102,7 +114,7 @@ __global__ void __launch_bounds__(RAY_MAX_THREADS)
 k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
              const uint32_t* __restrict__ alive_list,
              const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
-             size_t cells_per_grid, int radius, StepCounters* counters) {
+             size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];
     __shared__ int s_row_off[RAY_MAX_ROWS + 1];   // first window cell of each row (+ total at [wh])
     __shared__ int s_row_x[RAY_MAX_ROWS];         // x0 | (width << 16)
@@ -122,6 +134,10 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     // every ray starts in the same cell; outside the grid nothing is emitted (ray.rs:88-92)
     if (lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh) return;
     const int cx = (int)lcx, cy = (int)lcy;
+    if (window_would_overflow(geom, &meta[slot_of[p]], cx, cy, reach)) {
+        if (threadIdx.x == 0) atomicAdd(&counters->window_overflow, 1ull);
+        return;   // the grid is left as it was; the step reports SLAMRS_E_WINDOW
+    }
     const int shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx, s_shift);
 
     // ---- row table of the disc window, clipped to the grid
@@ -190,7 +206,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                     }
                 }
                 if (!in_window) {  // beyond the window (range larger than shared memory allows)
-                    global_cell_add(&grid[(size_t)y * geom.gh + phys_col(geom, (uint32_t)x, shift)], inc, &saturated);
+                    global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, shift)], inc, &saturated);
                     ext_add(s_ext, x, y, x, y);
                     spilled++;
                 }
@@ -226,7 +242,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                         const int gx0 = (s_row_x[lo] & 0xffff) + lx;
                         exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 3);
                         eymin = min(eymin, wy0 + lo); eymax = max(eymax, wy0 + lo);
-                        gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + lo) * geom.gh + phys_col(geom, (uint32_t)gx0, shift));
+                        gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + lo), shift));
                     }
                 }
             }
@@ -250,7 +266,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
             for (int c = threadIdx.x & 31; c < w; c += 32) {
                 const uint32_t d = s_win[off + c];
                 if (d != 0u) {
-                    uint32_t* g = grid + (size_t)(wy0 + ly) * geom.gh + phys_col(geom, (uint32_t)(x0 + c), shift);
+                    uint32_t* g = grid + phys_index(geom, (uint32_t)(x0 + c), (uint32_t)(wy0 + ly), shift);
                     *g = cell_sat_add(*g, d, &saturated);
                     exmin = min(exmin, x0 + c); exmax = max(exmax, x0 + c);
                     eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
@@ -297,7 +313,7 @@ __global__ void __maxnreg__(80)   // 2 CTAs of 384 threads per SM; blocks have a
 k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
              const uint32_t* __restrict__ alive_list,
                     const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
-                    size_t cells_per_grid, int radius, StepCounters* counters) {
+                    size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
     __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
     __shared__ uint32_t s_rowb[RAY_MAX_ROWS];           // shared byte address of column x = 0 of the row
@@ -317,6 +333,10 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     const int cx0 = (int)lcx, cy0 = (int)lcy;
     const int gw = (int)geom.gw, gh = (int)geom.gh;
     const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
+    if (window_would_overflow(geom, &meta[slot_of[p]], cx0, cy0, reach)) {
+        if (threadIdx.x == 0) atomicAdd(&counters->window_overflow, 1ull);
+        return;   // the grid is left as it was; the step reports SLAMRS_E_WINDOW
+    }
     const int slot_shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx0, s_shift);
 
     // ---- row table of the disc window (x ranges aligned to 8 cells = one 128-bit group)
@@ -462,7 +482,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                     }
                     if (!done) {
                         const int x = (int)(x2 >> 1), y = wy0 + ly;
-                        global_cell_add(&grid[(size_t)y * geom.gh + phys_col(geom, (uint32_t)x, slot_shift)], CELL_OCC_INC, &saturated);
+                        global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, slot_shift)], CELL_OCC_INC, &saturated);
                         ext_add(s_ext, x, y, x, y);
                         spilled++;
                     }
@@ -517,7 +537,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                         }
                     }
                     if (!done) {
-                        global_cell_add(&grid[(size_t)y * geom.gh + phys_col(geom, (uint32_t)x, slot_shift)],
+                        global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, slot_shift)],
                                         is_free ? CELL_FREE_INC : CELL_OCC_INC, &saturated);
                         ext_add(s_ext, x, y, x, y);
                         spilled++;
@@ -582,8 +602,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                             const int gx0 = (row.y & 0xffff) + 8 * g;
                             exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
                             eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
-                            gp[j] = reinterpret_cast<uint4*>(grid + (size_t)(wy0 + ly) * geom.gh +
-                                                             phys_col(geom, (uint32_t)gx0, slot_shift));
+                            gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
                         }
                     }
                 }
@@ -642,7 +661,7 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
         const size_t wmax = (size_t)ray_window_cells_upper_bound_packed(radius);
         *window_cells = wmax;
         k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
-                                                                  cells_per_grid, radius, counters);
+                                                                  cells_per_grid, radius, radius_cells, counters);
         return cudaSuccess;
     }
     const bool vec = (geom.gw % 4u == 0u) && (cells_per_grid % 4u == 0u);
@@ -654,10 +673,10 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
     *window_cells = wmax;
     if (vec)
         k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
-                                                               cells_per_grid, radius, counters);
+                                                               cells_per_grid, radius, radius_cells, counters);
     else
         k_ray_update<false><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
-                                                                cells_per_grid, radius, counters);
+                                                                cells_per_grid, radius, radius_cells, counters);
     return cudaSuccess;
 }
 

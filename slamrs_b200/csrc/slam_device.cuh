@@ -66,21 +66,35 @@ __device__ __forceinline__ long long f32_as_isize(float v) {
 // ---------------------------------------------------------------------------- geometry
 struct MapGeom {
     float pos_x, pos_y, res;
-    uint32_t gw, gh;
-    // Row rotation of a grid slot. A slot stores logical column x at physical column
-    // (x + shift) & xmask, `shift` per slot (SlotMeta::ox, a multiple of 8 cells). The resampler picks
-    // the shift of every grid it writes so that the informed extent starts on a page_cells boundary
-    // (1 KiB of cells): a ~250-cell-wide extent then occupies one DRAM page per row instead of
-    // straddling two, which is worth 15 % of copy bandwidth (profiles/, tune logs). Needs a
-    // power-of-two width; otherwise xmask = 0xffffffff, page_cells = 0 and every shift is 0.
-    uint32_t xmask, page_cells;
+    uint32_t gw, gh;           // logical grid, cells
+    // Physical slot. A slot stores logical cell (x, y) at row (y & ymask), column (x + shift) & xmask,
+    // `shift` per slot (SlotMeta::ox, a multiple of 8 cells).
+    //  * Row rotation: the resampler picks the shift of every grid it writes so that the informed
+    //    extent starts on a page_cells boundary (1 KiB of cells): a ~250-cell-wide extent then occupies
+    //    one DRAM page per row instead of straddling two (+15 % copy bandwidth, profiles/r1_copy_tuning.md).
+    //    Needs a power-of-two slot width; otherwise xmask = 0xffffffff, page_cells = 0, every shift is 0.
+    //  * Windowed slots (pw < gw or ph < gh, powers of two): a slot holds only a pw x ph torus of the
+    //    logical grid. The mapping is injective on any extent that fits pw x ph, and a grid's informed
+    //    extent is all a slot has to hold (everything else is the prior). Reads outside the extent
+    //    return the prior without touching memory; an extent that would outgrow the window is an error
+    //    (SLAMRS_E_WINDOW). This is what lets 32,768 particles with 2048 x 2048 maps share one B200.
+    uint32_t pw, ph;           // slot width / height in cells (= gw, gh when not windowed)
+    uint32_t xmask, ymask, page_cells;
+    uint32_t windowed;
 };
-__host__ __device__ inline MapGeom make_map_geom(float pos_x, float pos_y, float res, uint32_t gw, uint32_t gh) {
+__host__ __device__ inline bool is_pow2_u32(uint32_t v) { return v != 0u && (v & (v - 1u)) == 0u; }
+// slot_cells = 0: a slot holds the whole grid; otherwise the slot is slot_cells x slot_cells (power of two)
+__host__ __device__ inline MapGeom make_map_geom(float pos_x, float pos_y, float res, uint32_t gw, uint32_t gh,
+                                                 uint32_t slot_cells = 0u) {
     MapGeom g;
     g.pos_x = pos_x; g.pos_y = pos_y; g.res = res; g.gw = gw; g.gh = gh;
-    const bool rot = gw >= 256u && (gw & (gw - 1u)) == 0u;
-    g.xmask = rot ? gw - 1u : 0xffffffffu;
+    g.windowed = (slot_cells != 0u && (slot_cells < gw || slot_cells < gh)) ? 1u : 0u;
+    g.pw = g.windowed ? (slot_cells < gw ? slot_cells : gw) : gw;
+    g.ph = g.windowed ? (slot_cells < gh ? slot_cells : gh) : gh;
+    const bool rot = g.pw >= 256u && is_pow2_u32(g.pw);
+    g.xmask = rot ? g.pw - 1u : 0xffffffffu;
     g.page_cells = rot ? 256u : 0u;
+    g.ymask = (g.windowed && is_pow2_u32(g.ph)) ? g.ph - 1u : 0xffffffffu;
     return g;
 }
 // shift that puts logical column x0 (a multiple of 8) on a page boundary
@@ -88,6 +102,10 @@ __host__ __device__ inline int align_shift(const MapGeom& g, int x0) {
     return g.page_cells ? (int)((0u - (uint32_t)x0) & (g.page_cells - 1u)) : 0;
 }
 __host__ __device__ inline uint32_t phys_col(const MapGeom& g, uint32_t x, int shift) { return (x + (uint32_t)shift) & g.xmask; }
+// offset of logical cell (x, y) inside a slot
+__host__ __device__ inline size_t phys_index(const MapGeom& g, uint32_t x, uint32_t y, int shift) {
+    return (size_t)(y & g.ymask) * g.pw + phys_col(g, x, shift);
+}
 
 // Map::world_to_grid, map.rs:60-62
 __device__ __forceinline__ float world_to_grid(float w, float pos, float res) {

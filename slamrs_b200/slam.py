@@ -117,6 +117,7 @@ class GpuPlacement:
     rng_mode: int = _lib.RNG_SHARED_STREAM
     spare_slots: int = 0
     flags: int = 0
+    slot_cells: int = 0      # 0 = whole-grid slots; power of two >= 256 = windowed slots (see slamrs_gpu.h)
 
 
 def grid_cells(extent: float, resolution: float) -> int:
@@ -162,6 +163,7 @@ class GridMapSlam:
         cfg.rank, cfg.world_size = int(pl.rank), int(pl.world_size)
         cfg.spare_slots = int(pl.spare_slots)
         cfg.flags = int(pl.flags)
+        cfg.slot_cells = int(pl.slot_cells)
         if pl.world_size > 1:
             if pl.nccl_id is None or len(pl.nccl_id) != _lib.NCCL_ID_BYTES:
                 raise ValueError("world_size > 1 needs the 128-byte nccl_id shared by all ranks")

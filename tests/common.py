@@ -82,8 +82,8 @@ def compare_step(gpu: GridMapSlam, osl, particles=None, check_map=True):
 
 
 def lockstep(O, cfg: GridMapSlamConfig, scans, rng_mode=_lib.RNG_SHARED_STREAM, particles=None, seed=SEED, flags=0,
-             pre_step=None):
-    gpu = GridMapSlam(cfg, GpuPlacement(seed=seed, rng_mode=rng_mode, flags=flags))
+             pre_step=None, slot_cells=0):
+    gpu = GridMapSlam(cfg, GpuPlacement(seed=seed, rng_mode=rng_mode, flags=flags, slot_cells=slot_cells))
     osl = oracle_slam(O, cfg)
     errs = []
     try:

@@ -212,6 +212,55 @@ def test_step_parity_rotated_rows_wrap_around(oracle, copy_flags):
     print(errs[-1])
 
 
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_FULL_GRID_COPY, _lib.FLAG_GENERIC_RAY_KERNEL | _lib.FLAG_UPDATE_ALL_PARTICLES],
+                         ids=["extent-copy", "whole-slot-copy", "generic-strict"])
+def test_windowed_slots_parity(oracle, flags):
+    """1024 x 1024 logical grid, 256 x 256 slots (1/16 of the memory): each slot holds a torus window of
+    the grid, enough for one particle's informed extent. Particles are re-scattered over the map, so
+    slots change tenants whose extents lie in different parts of the grid (the windows alias) -- every
+    read-out must still equal the oracle's full-grid result."""
+    cfg = GridMapSlamConfig(position=(-10.24, -10.24), width=20.48, height=20.48, resolution=0.02, n_particles=20)
+    assert S.grid_cells(20.48, 0.02) == 1024
+    scans = make_scans(1.0, 360, 1.0, 6)      # 1 m range at 2 cm: extents of ~110 cells, growing
+    rng = np.random.default_rng(9)
+
+    def scatter(step, gpu, osl):
+        if step == 0:     # while the maps are empty: a map that already spans two far-apart places cannot fit a window
+            xyt = np.column_stack([rng.uniform(-9.0, 9.0, 20), rng.uniform(-9.0, 9.0, 20),
+                                   rng.uniform(-np.pi, np.pi, 20)]).astype(np.float32)
+            gpu.set_poses(xyt); osl.set_poses(xyt)
+
+    errs = lockstep(oracle, cfg, scans, flags=flags, pre_step=scatter, slot_cells=256, particles=range(0, 20, 3))
+    print(errs[-1])
+
+
+def test_windowed_slots_memory_and_overflow():
+    cfg = GridMapSlamConfig(position=(-10.24, -10.24), width=20.48, height=20.48, resolution=0.02, n_particles=8)
+    (obs, odo), = make_scans(1.0, 360, 1.0, 1)
+    with GridMapSlam(cfg, GpuPlacement(slot_cells=256)) as g:
+        assert g.stats()["bytes_per_grid"] == 256 * 256 * 4          # not 1024 * 1024 * 4
+        g.update(obs, odo)
+        x0, y0, x1, y1 = g.map_extent()
+        assert 0 < x1 - x0 <= 256 and 0 < y1 - y0 <= 256
+        # send the particles far away: old extent + new extent no longer fit one 256 x 256 window
+        g.set_poses(np.tile(np.array([[6.0, 6.0, 0.0]], np.float32), (8, 1)))
+        with pytest.raises(_lib.SlamrsGpuError) as e:
+            g.update(obs, odo)
+        assert e.value.code == _lib.E_WINDOW and g.stats()["window_overflow"] > 0
+    with pytest.raises(_lib.SlamrsGpuError):
+        GridMapSlam(cfg, GpuPlacement(slot_cells=300))               # not a power of two
+    # set_cells / cells round trip through a windowed slot, extent anywhere in the grid
+    img = np.zeros((1024, 1024), np.uint32)
+    img[700:900, 800:1000] = np.random.default_rng(1).integers(1, 5, (200, 200)).astype(np.uint32)
+    with GridMapSlam(cfg, GpuPlacement(slot_cells=256)) as g:
+        g.set_cells(2, img)
+        assert np.array_equal(g.cells(2).reshape(1024, 1024), img)
+        big = img.copy(); big[10, 10] = 1
+        with pytest.raises(_lib.SlamrsGpuError) as e:
+            g.set_cells(3, big)                                      # extent 990 x 890 does not fit
+        assert e.value.code == _lib.E_WINDOW
+
+
 def test_c5_shape(oracle):
     """configs[4] shape at reduced particle count: 720 beams at 0.5 degree spacing, 2048 x 2048 grid at
     5 cm (102.4 m), 6 m range, global-localisation-style uniform initial poses over the 20 m room."""
@@ -227,6 +276,10 @@ def test_c5_shape(oracle):
             gpu.set_poses(init); osl.set_poses(init)
 
     errs = lockstep(oracle, cfg, scans, particles=[0, 7, 19], pre_step=uniform_init)
+    print(errs[-1])
+    # the same with 512 x 512 slots: 1/16 of the memory per particle, which is what makes the full
+    # configuration (32,768 particles per GPU) fit
+    errs = lockstep(oracle, cfg, scans, particles=[0, 7, 19], pre_step=uniform_init, slot_cells=512)
     print(errs[-1])
 
 
