@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
-    ap.add_argument("--workload", default="c3", help="c1 | c2 | c3 (per-GPU shard; default configs[2])")
+    ap.add_argument("--workload", default="c3", help="c1 | c2 | c3 | c5 (per-GPU shard; default configs[2])")
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
     ap.add_argument("--cpu-particles", type=int, default=0, help="particles of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -190,7 +190,7 @@ def time_oracle(O, wl, n_cpu, steps, warmup, threads, dead_likelihood=False):
 def workload_config(wl, n_gpus, n_total):
     return {"workload": f"{n_total} particles x {wl.n_beams} beams, {wl.grid}x{wl.grid} grid @ {wl.resolution} m "
                         f"({wl.name} shard per GPU; simulator scene x{wl.scene_scale:g}, range {wl.scanner_range:g} m)",
-            "particles_per_gpu": wl.n_particles, "beams": wl.n_beams, "grid": wl.grid,
+            "particles_per_gpu": wl.n_particles, "beams": wl.n_beams, "grid": wl.grid, "slot_cells": wl.slot_cells,
             "parallelism": f"particles sharded dp{n_gpus}",
             "l2": "working set (per-particle grids) is far larger than L2; no flush needed"}
 
@@ -208,7 +208,11 @@ def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2
     cfg = wl.slam_config(n_total)
     if getattr(args, "shift_x_cells", 0):
         cfg.position = (cfg.position[0] - args.shift_x_cells * cfg.resolution, cfg.position[1])
-    slam = GridMapSlam(cfg, GpuPlacement(device=local, rank=rank, world_size=world, nccl_id=nccl_id, flags=flags))
+    slam = GridMapSlam(cfg, GpuPlacement(device=local, rank=rank, world_size=world, nccl_id=nccl_id, flags=flags,
+                                         slot_cells=wl.slot_cells))
+    if wl.uniform_init:
+        from slamrs_b200.workloads import uniform_poses
+        slam.set_poses(uniform_poses(wl, slam.first, slam.n_local))
     stream = torch.cuda.ExternalStream(slam.stream_ptr, device=dev)
     grid_bytes = slam.stats()["bytes_per_grid"]
 

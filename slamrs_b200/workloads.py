@@ -20,6 +20,8 @@ class Workload:
     speed_left: float = 0.08
     speed_right: float = 0.10
     update_period: float = 1.0
+    slot_cells: int = 0          # windowed grid slots (GpuPlacement.slot_cells); 0 = whole-grid slots
+    uniform_init: bool = False   # global-localisation-style start: poses uniform over the room
 
     @property
     def width(self) -> float:
@@ -43,4 +45,20 @@ WORKLOADS = {
     # configs[2]: 8,192 particles x 360 beams, 1024^2 grid (grid-copy-bound resampling)
     "c3": Workload("c3_8192x360_1024", 8192, 360, 1024, 0.05, 10.0, 6.0, 0.1),
     # configs[3] is c3's shard on each of 2/4/8 GPUs (65,536 particles at 8 GPUs)
+    # configs[4]: 262,144 particles x 720 beams, 2048^2 grid on 8 GPUs = 32,768 per GPU. A whole 2048^2
+    # grid per particle would need 512 GiB per GPU; 512 x 512 windowed slots (1 MiB) hold the informed
+    # extent of a 6 m lidar with room to grow. Uniform initial poses over the 20 m room.
+    "c5": Workload("c5_32768x720_2048", 32768, 720, 2048, 0.05, 10.0, 6.0, 0.1, slot_cells=512, uniform_init=True),
 }
+
+
+def uniform_poses(wl: Workload, first: int, count: int, seed: int = 0x5EED5A11):
+    """Start poses for `uniform_init` workloads: x, y uniform over the scaled room, theta over [-pi, pi);
+    a function of the GLOBAL particle index, so every sharding gives the same population."""
+    import numpy as np
+    half = 0.9 * wl.scene_scale          # the reference scene's outer rectangle is 2 m x 2 m, scaled
+    out = np.empty((count, 3), np.float32)
+    for i in range(count):
+        rng = np.random.default_rng([seed, first + i])
+        out[i] = (rng.uniform(-half, half), rng.uniform(-half, half), rng.uniform(-np.pi, np.pi))
+    return out
