@@ -574,70 +574,78 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     }
     __syncthreads();
 
-    // ---- write-back, row by row: one warp per window row, one lane per 8-cell group (a 128-bit
-    // shared load -> two 128-bit global RMWs); RAY_WB_ROWS rows are in flight per warp.
+    // ---- write-back. A window row is at most 34 groups of 8 cells (one 128-bit shared load each); a
+    // non-empty group is two 128-bit global read-modify-writes. Main pass: one warp per row, lane g
+    // takes group g < 32, RAY_WB_ROWS rows in flight per warp. Tail pass: the (at most two) groups
+    // beyond the 32nd of each row, one thread per row. One code path per group: the packed window
+    // value is unpacked without a branch; only a grid counter at or above 2^15 (which one scan's
+    // increment could saturate) takes the saturating form.
     constexpr int RAY_WB_ROWS = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
     int exmin = 0x7fffffff, eymin = 0x7fffffff, exmax = -1, eymax = -1;   // this thread's touched extent
+    auto unpack = [](uint32_t packed16) { return (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16); };
+    auto merge_group = [&](uint4& va, uint4& vb, const uint4& d) {
+        const uint32_t high_any = (va.x | va.y | va.z | va.w | vb.x | vb.y | vb.z | vb.w) & 0x80008000u;
+        if (high_any == 0u) {
+            va.x += unpack(d.x & 0xffffu); va.y += unpack(d.x >> 16);
+            va.z += unpack(d.y & 0xffffu); va.w += unpack(d.y >> 16);
+            vb.x += unpack(d.z & 0xffffu); vb.y += unpack(d.z >> 16);
+            vb.z += unpack(d.w & 0xffffu); vb.w += unpack(d.w >> 16);
+        } else {
+            va.x = cell_sat_add(va.x, unpack(d.x & 0xffffu), &saturated); va.y = cell_sat_add(va.y, unpack(d.x >> 16), &saturated);
+            va.z = cell_sat_add(va.z, unpack(d.y & 0xffffu), &saturated); va.w = cell_sat_add(va.w, unpack(d.y >> 16), &saturated);
+            vb.x = cell_sat_add(vb.x, unpack(d.z & 0xffffu), &saturated); vb.y = cell_sat_add(vb.y, unpack(d.z >> 16), &saturated);
+            vb.z = cell_sat_add(vb.z, unpack(d.w & 0xffffu), &saturated); vb.w = cell_sat_add(vb.w, unpack(d.w >> 16), &saturated);
+        }
+    };
     for (int ly0 = warp; ly0 < wh; ly0 += n_warps * RAY_WB_ROWS) {
-        for (int g0 = 0; g0 < (RAY_MAX_RADIUS * 2 + 16) / 8; g0 += 32) {
-            uint4 d[RAY_WB_ROWS], va[RAY_WB_ROWS], vb[RAY_WB_ROWS];
-            uint4* gp[RAY_WB_ROWS];
-            bool nz[RAY_WB_ROWS];
-            bool any_row = false;
+        uint4 d[RAY_WB_ROWS], va[RAY_WB_ROWS], vb[RAY_WB_ROWS];
+        uint4* gp[RAY_WB_ROWS];
+        bool nz[RAY_WB_ROWS];
 #pragma unroll
-            for (int j = 0; j < RAY_WB_ROWS; ++j) {
-                const int ly = ly0 + j * n_warps;
-                nz[j] = false;
-                if (ly < wh) {
-                    const int2 row = s_row[ly];
-                    const int groups = row.y >> 19;          // width / 8
-                    const int g = g0 + lane;
-                    any_row |= g0 < groups;
-                    if (g < groups) {
-                        d[j] = win4[(row.x >> 3) + g];
-                        nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
-                        if (nz[j]) {
-                            const int gx0 = (row.y & 0xffff) + 8 * g;
-                            exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
-                            eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
-                            gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
-                        }
+        for (int j = 0; j < RAY_WB_ROWS; ++j) {
+            const int ly = ly0 + j * n_warps;
+            nz[j] = false;
+            if (ly < wh) {
+                const int2 row = s_row[ly];
+                if (lane < (row.y >> 19)) {          // width / 8 groups in this row
+                    d[j] = win4[(row.x >> 3) + lane];
+                    nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
+                    if (nz[j]) {
+                        const int gx0 = (row.y & 0xffff) + 8 * lane;
+                        exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
+                        eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
+                        gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
                     }
                 }
             }
-            if (!any_row) break;   // warp-uniform: no row of this batch reaches group g0
+        }
 #pragma unroll
-            for (int j = 0; j < RAY_WB_ROWS; ++j)
-                if (nz[j]) { va[j] = gp[j][0]; vb[j] = gp[j][1]; }
+        for (int j = 0; j < RAY_WB_ROWS; ++j)
+            if (nz[j]) { va[j] = gp[j][0]; vb[j] = gp[j][1]; }
 #pragma unroll
-            for (int j = 0; j < RAY_WB_ROWS; ++j) {
-                if (nz[j]) {
-                    // group-level fast path: no occupied hit among the 8 window cells (a packed value is
-                    // then the free count itself) and no counter of the 8 grid cells at or above 2^15
-                    // (it cannot saturate by one scan's increment): eight plain adds
-                    const uint32_t occ_any = (d[j].x | d[j].y | d[j].z | d[j].w) & 0xF800F800u;
-                    const uint32_t high_any = (va[j].x | va[j].y | va[j].z | va[j].w | vb[j].x | vb[j].y | vb[j].z | vb[j].w) & 0x80008000u;
-                    if ((occ_any | high_any) == 0u) {
-                        va[j].x += d[j].x & 0xffffu; va[j].y += d[j].x >> 16;
-                        va[j].z += d[j].y & 0xffffu; va[j].w += d[j].y >> 16;
-                        vb[j].x += d[j].z & 0xffffu; vb[j].y += d[j].z >> 16;
-                        vb[j].z += d[j].w & 0xffffu; vb[j].w += d[j].w >> 16;
-                    } else {
-                        auto apply = [&](uint32_t g, uint32_t packed16) {
-                            const uint32_t delta = (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16);
-                            return cell_sat_add(g, delta, &saturated);
-                        };
-                        va[j].x = apply(va[j].x, d[j].x & 0xffffu); va[j].y = apply(va[j].y, d[j].x >> 16);
-                        va[j].z = apply(va[j].z, d[j].y & 0xffffu); va[j].w = apply(va[j].w, d[j].y >> 16);
-                        vb[j].x = apply(vb[j].x, d[j].z & 0xffffu); vb[j].y = apply(vb[j].y, d[j].z >> 16);
-                        vb[j].z = apply(vb[j].z, d[j].w & 0xffffu); vb[j].w = apply(vb[j].w, d[j].w >> 16);
-                    }
-                    gp[j][0] = va[j];
-                    gp[j][1] = vb[j];
-                }
+        for (int j = 0; j < RAY_WB_ROWS; ++j) {
+            if (nz[j]) {
+                merge_group(va[j], vb[j], d[j]);
+                gp[j][0] = va[j];
+                gp[j][1] = vb[j];
             }
+        }
+    }
+    for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {   // tail pass: groups 32, 33 of each row
+        const int2 row = s_row[ly];
+        for (int g = 32; g < (row.y >> 19); ++g) {
+            const uint4 dd = win4[(row.x >> 3) + g];
+            if ((dd.x | dd.y | dd.z | dd.w) == 0u) continue;
+            const int gx0 = (row.y & 0xffff) + 8 * g;
+            exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
+            eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
+            uint4* gpt = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
+            uint4 ta = gpt[0], tb = gpt[1];
+            merge_group(ta, tb, dd);
+            gpt[0] = ta;
+            gpt[1] = tb;
         }
     }
     ext_add(s_ext, exmin, eymin, exmax, eymax);
