@@ -25,7 +25,9 @@ struct slamrs_gpu_handle {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t side_stream = nullptr;          // the planner runs here, next to the ray update
-    cudaEvent_t ev_indices = nullptr, ev_plan = nullptr;
+    cudaEvent_t ev_indices = nullptr, ev_plan = nullptr, ev_sort = nullptr;
+    uint16_t* d_order = nullptr;   // beam order of the current scan for the ray kernel (SORT_MAX_BEAMS entries)
+    bool order_valid = false, order_pending = false;
 
     uint32_t n_total = 0, n_local = 0, rank = 0, world = 1, first = 0;
     uint32_t n_cells = 0;        // grid_w * grid_h
@@ -250,6 +252,8 @@ void free_all(slamrs_gpu_handle* h) {
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->ev_indices) cudaEventDestroy(h->ev_indices);
     if (h->ev_plan) cudaEventDestroy(h->ev_plan);
+    if (h->ev_sort) cudaEventDestroy(h->ev_sort);
+    cudaFree(h->d_order);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -433,6 +437,8 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     CREATE_CU(cudaEventCreateWithFlags(&h->ev_indices, cudaEventDisableTiming));
     CREATE_CU(cudaEventCreateWithFlags(&h->ev_plan, cudaEventDisableTiming));
+    CREATE_CU(cudaEventCreateWithFlags(&h->ev_sort, cudaEventDisableTiming));
+    CREATE_CU(cudaMalloc(&h->d_order, sizeof(uint16_t) * SORT_MAX_BEAMS));
     CREATE_CU(configure_kernels());
 
     // spare slots: staging room for grids that migrate between GPUs at resampling
@@ -550,6 +556,7 @@ int slamrs_gpu_upload_scan(slamrs_gpu_handle* h, const float* angle, const float
     }
     h->n_beams = n_beams;
     h->scan_external = false;
+    h->order_valid = false;
     // window radius for the ray kernel: farthest finite measurement, in cells, plus the two extra
     // steps of apply_measurement (map.rs:97) and the slack that lets the ray kernel prove, per ray, that
     // no cell leaves the window (see k_ray_update_packed). Correctness never depends on it:
@@ -570,6 +577,7 @@ int slamrs_gpu_set_scan_device(slamrs_gpu_handle* h, const float* angle_device, 
     h->ext_angle = angle_device; h->ext_dist = dist_device; h->ext_valid = valid_device;
     h->n_beams = n_beams;
     h->scan_external = true;
+    h->order_valid = false;
     const float cells = ceilf(fabsf(max_dist) / h->geom.res);
     h->radius_cells = ((cells == cells && cells < 4096.0f) ? (int)cells : 4096) + 6;
     return SLAMRS_OK;
@@ -588,8 +596,23 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         CU_TRY(h, cudaMemcpyAsync(h->d_z, z_draws, sizeof(double) * 2 * h->n_total, cudaMemcpyHostToDevice, s));
         CU_TRY(h, cudaMemcpyAsync(h->d_u, resample_u, sizeof(double), cudaMemcpyHostToDevice, s));
     }
-    const ScanDevice scan = h->scan_external ? ScanDevice{h->ext_angle, h->ext_dist, h->ext_valid, h->n_beams}
-                                             : ScanDevice{h->d_angle, h->d_dist, h->d_valid, h->n_beams};
+    // beam order for the ray kernel (side stream, concurrent with the likelihood kernel); scans with
+    // more beams than the sort handles keep scan order
+    const bool sorted = h->n_beams > 32u && h->n_beams <= SORT_MAX_BEAMS;
+    const ScanDevice scan = h->scan_external
+                                ? ScanDevice{h->ext_angle, h->ext_dist, h->ext_valid, h->n_beams, sorted ? h->d_order : nullptr}
+                                : ScanDevice{h->d_angle, h->d_dist, h->d_valid, h->n_beams, sorted ? h->d_order : nullptr};
+    if (sorted && !h->order_valid) {
+        // everything issued so far (scan upload, the previous step's ray kernel that still reads the old
+        // order) precedes the sort
+        CU_TRY(h, cudaEventRecord(h->ev_indices, s));
+        CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->ev_indices, 0));
+        launch_sort_beams(h->side_stream, scan.dist, h->n_beams, h->d_order);
+        CU_TRY(h, cudaEventRecord(h->ev_sort, h->side_stream));
+        h->launches++;
+        h->order_valid = true;
+        h->order_pending = true;
+    }
     if (h->profiling && h->prof_recorded == PROF_RING) {
         int prc = prof_flush(h);
         if (prc) return prc;
@@ -656,6 +679,10 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     }
     h->launches += 2;
     PROF_MARK(h, 3);
+    if (h->order_pending) {
+        CU_TRY(h, cudaStreamWaitEvent(s, h->ev_sort, 0));
+        h->order_pending = false;
+    }
     CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive, h->d_slot[cur],
                                 h->d_cells, h->d_meta, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
                                 (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
@@ -830,6 +857,7 @@ int slamrs_gpu_sim_scan(slamrs_gpu_handle* h, const float* segments_xyxy, uint32
     CU_TRY(h, cudaGetLastError());
     h->n_beams = res[0];
     h->scan_external = false;
+    h->order_valid = false;
     float maxd;
     memcpy(&maxd, &res[1], 4);
     const float cells = ceilf(maxd / h->geom.res);

@@ -67,7 +67,14 @@ struct ScanDevice {
     const float* dist;
     const uint8_t* valid;
     uint32_t n_beams;
+    // beam order for the ray kernel: indices sorted by decreasing distance, so that the 32 rays of a
+    // warp have similar lengths (a warp walks as long as its longest ray). nullptr = scan order.
+    // The grid update is order-independent (integer counters), so this changes no result.
+    const uint16_t* order;
 };
+constexpr uint32_t SORT_MAX_BEAMS = 2048;
+// order[0..n) = beam indices by decreasing |dist| (NaN last); n <= SORT_MAX_BEAMS
+void launch_sort_beams(cudaStream_t stream, const float* dist, uint32_t n_beams, uint16_t* order);
 
 // Per-slot metadata. [x0, x1) x [y0, y1) is the extent (in cells, x0/x1 multiples of 8) of the
 // cells of the slot that may be non-zero: everything outside is guaranteed to be zero

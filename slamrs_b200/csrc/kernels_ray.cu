@@ -183,7 +183,8 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
 
     bool saturated = false;
     uint32_t spilled = 0;
-    for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
+    for (uint32_t t = threadIdx.x; t < scan.n_beams; t += blockDim.x) {
+        const uint32_t b = scan.order ? scan.order[t] : t;
         const float dist = scan.dist[b];
         float ex, ey;
         beam_endpoint(px, py, ptheta, scan.angle[b], dist, &ex, &ey);
@@ -381,7 +382,8 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     const bool disc_in_grid = cx0 - radius >= 0 && cx0 + radius < gw && cy0 - radius >= 0 && cy0 + radius < gh;
     bool saturated = false;
     uint32_t spilled = 0;
-    for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
+    for (uint32_t t = threadIdx.x; t < scan.n_beams; t += blockDim.x) {
+        const uint32_t b = scan.order ? scan.order[t] : t;   // similar ray lengths within a warp
         const float dist = scan.dist[b];
         float ex, ey;
         beam_endpoint(px, py, ptheta, scan.angle[b], dist, &ex, &ey);
@@ -653,6 +655,43 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, slot_shift);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
+}
+
+// =============================================================================== k_sort_beams
+// Bitonic sort of (|dist|, beam index) in shared memory, descending; one CTA, once per scan, on the side
+// stream while the likelihood kernel runs.
+__global__ void __launch_bounds__(1024)
+k_sort_beams(const float* __restrict__ dist, uint32_t n, uint16_t* __restrict__ order) {
+    __shared__ float s_key[SORT_MAX_BEAMS];
+    __shared__ uint16_t s_idx[SORT_MAX_BEAMS];
+    for (uint32_t i = threadIdx.x; i < SORT_MAX_BEAMS; i += blockDim.x) {
+        float k = -1.0f;                                    // padding and NaN sort last
+        if (i < n) { const float d = fabsf(dist[i]); if (d == d) k = d; }
+        s_key[i] = k;
+        s_idx[i] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= SORT_MAX_BEAMS; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < SORT_MAX_BEAMS / 2; t += blockDim.x) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool descending = (lo & size) == 0;
+                const float a = s_key[lo], b = s_key[hi];
+                // ties keep the lower beam index first: a total order, so the result is deterministic
+                const bool a_first = a > b || (a == b && s_idx[lo] < s_idx[hi]);
+                if (a_first != descending) {
+                    s_key[lo] = b; s_key[hi] = a;
+                    const uint16_t ti = s_idx[lo]; s_idx[lo] = s_idx[hi]; s_idx[hi] = ti;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) order[i] = s_idx[i];   // the n real beams come first
+}
+void launch_sort_beams(cudaStream_t stream, const float* dist, uint32_t n_beams, uint16_t* order) {
+    k_sort_beams<<<1, 1024, 0, stream>>>(dist, n_beams, order);
 }
 
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
