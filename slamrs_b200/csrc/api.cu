@@ -26,6 +26,8 @@ struct slamrs_gpu_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t side_stream = nullptr;          // the planner runs here, next to the ray update
     cudaEvent_t ev_indices = nullptr, ev_plan = nullptr, ev_sort = nullptr;
+    float2* d_valid_list = nullptr;     // (angle, distance) of the scan's valid beams (65,536 entries), filled by k_motion
+    uint32_t* d_n_valid = nullptr;
     uint16_t* d_order = nullptr;   // beam order of the current scan for the ray kernel (SORT_MAX_BEAMS entries)
     bool order_valid = false, order_pending = false;
 
@@ -253,7 +255,7 @@ void free_all(slamrs_gpu_handle* h) {
     if (h->ev_indices) cudaEventDestroy(h->ev_indices);
     if (h->ev_plan) cudaEventDestroy(h->ev_plan);
     if (h->ev_sort) cudaEventDestroy(h->ev_sort);
-    cudaFree(h->d_order);
+    cudaFree(h->d_order); cudaFree(h->d_valid_list); cudaFree(h->d_n_valid);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -439,6 +441,8 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaEventCreateWithFlags(&h->ev_plan, cudaEventDisableTiming));
     CREATE_CU(cudaEventCreateWithFlags(&h->ev_sort, cudaEventDisableTiming));
     CREATE_CU(cudaMalloc(&h->d_order, sizeof(uint16_t) * SORT_MAX_BEAMS));
+    CREATE_CU(cudaMalloc(&h->d_valid_list, sizeof(float2) * 65536));
+    CREATE_CU(cudaMalloc(&h->d_n_valid, sizeof(uint32_t)));
     CREATE_CU(configure_kernels());
 
     // spare slots: staging room for grids that migrate between GPUs at resampling
@@ -626,7 +630,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->d_meta, h->cells_per_grid,
-                             h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step, h->d_term_table,
+                             h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step, h->d_term_table, h->d_valid_list, h->d_n_valid,
                              h->p2p_exchange ? h->d_peer_results : nullptr, res_off, h->rank, h->world);
     h->launches += 2;   // k_motion + k_likelihood
     // 2. the one exchange step: every GPU needs every particle's weight, pose and slot. Default:

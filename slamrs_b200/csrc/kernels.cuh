@@ -102,6 +102,7 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               const SlotMeta* meta, size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
                               const double* term_table /* LK_TABLE_NF x LK_TABLE_NO, launch_fill_term_table */,
+                              float2* valid_beams /* scratch: n_beams entries */, uint32_t* n_valid /* scratch */,
                               ParticleResult* const* peer_results /* null: no fused exchange */,
                               uint32_t peer_offset /* records in front of this step's generation */, uint32_t rank,
                               uint32_t world);

@@ -12,7 +12,33 @@ namespace slamrs {
 __global__ void __launch_bounds__(128)
 k_motion(OdomModel od, const float* __restrict__ pose_cur, const int32_t* __restrict__ slot_of,
          ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
-         const double* __restrict__ z_draws, uint64_t seed, uint64_t step) {
+         const double* __restrict__ z_draws, uint64_t seed, uint64_t step, ScanDevice scan,
+         float2* __restrict__ valid_beams, uint32_t* __restrict__ n_valid) {
+    // Block 0 also compacts the (angle, distance) pairs of the scan's VALID beams, in beam order, for
+    // k_likelihood: only valid measurements contribute to Map::probability_of (map.rs:117-119), and
+    // one coalesced 8-byte load per beam replaces the dependent valid[] -> angle[], dist[] loads that
+    // the likelihood kernel spent most of its stall cycles on.
+    if (blockIdx.x == 0) {
+        __shared__ uint32_t s_cnt[4];
+        __shared__ uint32_t s_base;
+        if (threadIdx.x == 0) s_base = 0u;
+        __syncthreads();
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (uint32_t b0 = 0; b0 < scan.n_beams; b0 += 128u) {
+            const uint32_t b = b0 + threadIdx.x;
+            const bool v = b < scan.n_beams && scan.valid[b] != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, v);
+            if (lane == 0) s_cnt[wid] = __popc(m);
+            __syncthreads();
+            uint32_t off = s_base;
+            for (int w = 0; w < wid; ++w) off += s_cnt[w];
+            if (v) valid_beams[off + __popc(m & ((1u << lane) - 1u))] = make_float2(scan.angle[b], scan.dist[b]);
+            __syncthreads();
+            if (threadIdx.x == 0) s_base += s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) *n_valid = s_base;
+    }
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_local) return;
     const uint32_t gp = first_particle + p;      // global logical index
@@ -43,7 +69,8 @@ k_motion(OdomModel od, const float* __restrict__ pose_cur, const int32_t* __rest
 }
 
 // k_likelihood: one WARP per particle, lanes over beams. Map::probability_of (map.rs:113-145): one
-// gather per valid beam from the PRE-update grid. LK_UNROLL gathers are in flight per lane before
+// gather per valid beam from the PRE-update grid (lanes step through the compacted list of valid
+// beams, so every lane of every batch has work). LK_UNROLL gathers are in flight per lane before
 // the first exp/log. A never-informed cell (counters 0 -> log-odds 0 -> p = 0.5) contributes
 // log(1/1) = 0 and skips the transcendental work. Each lane adds its terms in beam order, the 32
 // lane sums are combined by a fixed butterfly: deterministic, order-independent of scheduling.
@@ -53,7 +80,8 @@ constexpr int LK_UNROLL = 4;
 __global__ void __launch_bounds__(LK_WARPS * 32, 2048 / (LK_WARPS * 32))   // every particle of an 8,192-shard resident at once
 k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, const SlotMeta* __restrict__ meta,
              size_t cells_per_grid, ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
-             const double* __restrict__ term_table,
+             const double* __restrict__ term_table, const float2* __restrict__ valid_beams,
+             const uint32_t* __restrict__ n_valid_ptr,
              ParticleResult* const* __restrict__ peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     const uint32_t p = blockIdx.x * LK_WARPS + (threadIdx.x >> 5);
     if (p >= n_local) return;
@@ -65,15 +93,17 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
     const int shift = sm.ox;             // ... and row rotation of this particle's slot
 
     double lp = log(1.0);
-    for (uint32_t base = 0; base < scan.n_beams; base += 32u * LK_UNROLL) {
+    const uint32_t n_valid = *n_valid_ptr;   // valid beams only, compacted by k_motion (ascending beam index)
+    for (uint32_t base = 0; base < n_valid; base += 32u * LK_UNROLL) {
         uint32_t cell[LK_UNROLL];
 #pragma unroll
         for (int u = 0; u < LK_UNROLL; ++u) {
-            const uint32_t b = base + (uint32_t)u * 32u + (uint32_t)lane;
+            const uint32_t t = base + (uint32_t)u * 32u + (uint32_t)lane;
             cell[u] = 0u;
-            if (b < scan.n_beams && scan.valid[b]) {
+            if (t < n_valid) {
+                const float2 ad = __ldg(&valid_beams[t]);   // (angle, distance) of the t-th valid beam
                 float ex, ey;
-                beam_endpoint(nx, ny, ntheta, scan.angle[b], scan.dist[b], &ex, &ey);
+                beam_endpoint(nx, ny, ntheta, ad.x, ad.y, &ex, &ey);
                 const float gx = world_to_grid(ex, geom.pos_x, geom.res);
                 const float gy = world_to_grid(ey, geom.pos_y, geom.res);
                 if (grid_is_valid(gx, gy, geom.gw, geom.gh)) {
@@ -111,14 +141,14 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
                               const SlotMeta* meta, size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
-                              const double* term_table,
+                              const double* term_table, float2* valid_beams, uint32_t* n_valid,
                               ParticleResult* const* peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
-                                                         z_draws, seed, step);
+                                                         z_draws, seed, step, scan, valid_beams, n_valid);
     k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, cells, meta, cells_per_grid,
                                                                                    results, first_particle, n_local,
-                                                                                   term_table, peer_results, peer_offset,
-                                                                                   rank, world);
+                                                                                   term_table, valid_beams, n_valid,
+                                                                                   peer_results, peer_offset, rank, world);
 }
 
 __global__ void k_fill_term_table(double* __restrict__ table) {
