@@ -117,5 +117,6 @@ extern "C" {
     pub fn slamrs_gpu_get_max_particle(h: *mut slamrs_gpu_handle, out: *mut u64) -> c_int;
     pub fn slamrs_gpu_get_cells(h: *mut slamrs_gpu_handle, particle: u64, out_cells: *mut u32) -> c_int;
     pub fn slamrs_gpu_set_cells(h: *mut slamrs_gpu_handle, particle: u64, cells: *const u32) -> c_int;
+    pub fn slamrs_gpu_get_extents(h: *mut slamrs_gpu_handle, particle: u64, out_box_shift: *mut i32, out_bands: *mut u32, out_n_bands: *mut u32) -> c_int;
     pub fn slamrs_gpu_get_log_odds(h: *mut slamrs_gpu_handle, particle: u64, out_cells: *mut f64) -> c_int;
 }

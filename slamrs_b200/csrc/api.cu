@@ -41,7 +41,10 @@ struct slamrs_gpu_handle {
     // [SlotMeta x 2*n_local | ParticleResult x n_total | barrier flags | grid slots]
     void* d_pool = nullptr;
     size_t pool_header = 0;      // bytes in front of the first grid slot
-    size_t off_results = 0, off_flags = 0;
+    size_t off_results = 0, off_flags = 0, off_bands = 0;
+    uint32_t* d_bands = nullptr;                 // band extents, n_bands entries per slot (inside the pool header)
+    uint32_t n_bands = 0;
+    uint32_t** d_peer_bands = nullptr;           // device array [world]
     unsigned long long* d_flags = nullptr;       // PEER_MAX_WORLD epochs, written by the peers
     ParticleResult** d_peer_results = nullptr;   // device array [world]
     unsigned long long** d_peer_flags = nullptr; // device array [world]
@@ -198,12 +201,16 @@ int setup_peers(slamrs_gpu_handle* h) {
     std::vector<SlotMeta*> pmeta(W);
     std::vector<ParticleResult*> pres(W);
     std::vector<unsigned long long*> pflags(W);
+    std::vector<uint32_t*> pbands(W);
     for (uint32_t r = 0; r < W; ++r) {
         pmeta[r] = (SlotMeta*)peers[r];
         pcells[r] = (uint32_t*)(peers[r] + h->pool_header);
         pres[r] = (ParticleResult*)(peers[r] + h->off_results);
         pflags[r] = (unsigned long long*)(peers[r] + h->off_flags);
+        pbands[r] = (uint32_t*)(peers[r] + h->off_bands);
     }
+    CU_TRY(h, cudaMalloc(&h->d_peer_bands, sizeof(uint32_t*) * W));
+    CU_TRY(h, cudaMemcpy(h->d_peer_bands, pbands.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMalloc(&h->d_peer_results, sizeof(ParticleResult*) * W));
     CU_TRY(h, cudaMemcpy(h->d_peer_results, pres.data(), sizeof(ParticleResult*) * W, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMalloc(&h->d_peer_flags, sizeof(unsigned long long*) * W));
@@ -247,7 +254,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
     cudaFree(h->d_copies); cudaFree(h->d_leaders); cudaFree(h->d_alive); cudaFree(h->d_jobs);
     cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells); cudaFree(h->d_peer_meta);
-    cudaFree(h->d_peer_results); cudaFree(h->d_peer_flags);
+    cudaFree(h->d_peer_results); cudaFree(h->d_peer_flags); cudaFree(h->d_peer_bands);
     cudaFree(h->d_history);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->prof_events.clear();
@@ -467,13 +474,16 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     // two generations of the population array (step parity): a peer that is one step ahead stores
     // its next records while this rank's host may still be reading the last step's
     h->off_flags = (h->off_results + 2 * sizeof(ParticleResult) * (size_t)h->n_total + 255) & ~(size_t)255;
-    h->pool_header = (h->off_flags + sizeof(unsigned long long) * PEER_MAX_WORLD + 4095) & ~(size_t)4095;
+    h->n_bands = bands_per_slot(h->geom);
+    h->off_bands = (h->off_flags + sizeof(unsigned long long) * PEER_MAX_WORLD + 255) & ~(size_t)255;
+    h->pool_header = (h->off_bands + sizeof(uint32_t) * 2 * (size_t)h->n_local * h->n_bands + 4095) & ~(size_t)4095;
     CREATE_CU(cudaMalloc(&h->d_pool, h->pool_header + (size_t)h->n_slots * grid_bytes));
     h->d_meta = (SlotMeta*)h->d_pool;
     h->d_cells = (uint32_t*)((char*)h->d_pool + h->pool_header);
     h->d_results_base = (ParticleResult*)((char*)h->d_pool + h->off_results);   // zeroed with the pool
     h->d_results = h->d_results_base;
     h->d_flags = (unsigned long long*)((char*)h->d_pool + h->off_flags);
+    h->d_bands = (uint32_t*)((char*)h->d_pool + h->off_bands);
     h->p2p_exchange = h->world > 1 && (cfg->flags & SLAMRS_FLAG_NCCL_EXCHANGE) == 0;
     CREATE_CU(cudaMemsetAsync(h->d_pool, 0, h->pool_header + (size_t)h->n_slots * grid_bytes, h->stream));  // ln(0.5/0.5) = 0
     h->boxed_copy = (cfg->flags & SLAMRS_FLAG_FULL_GRID_COPY) == 0 && cfg->grid_w % 8u == 0u && h->geom.pw % 8u == 0u;
@@ -669,6 +679,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.cells = h->d_cells; pa.cells_per_grid = h->cells_per_grid;
     pa.peer_cells = h->d_peer_cells;
     pa.meta = h->d_meta; pa.peer_meta = h->d_peer_meta;
+    pa.bands = h->d_bands; pa.peer_bands = h->d_peer_bands; pa.n_bands = h->n_bands;
     pa.counters = h->d_counters;
     pa.history = h->d_history;
     pa.step = h->step;
@@ -688,7 +699,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         h->order_pending = false;
     }
     CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive, h->d_slot[cur],
-                                h->d_cells, h->d_meta, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
+                                h->d_cells, h->d_meta, h->d_bands, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
                                 (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
     h->launches++;
     PROF_MARK(h, 4);
@@ -1063,8 +1074,41 @@ int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t
                        m, h->geom);
     h->launches++;
     CU_TRY(h, cudaMemcpyAsync(h->d_meta + slot, &m, sizeof(m), cudaMemcpyHostToDevice, h->stream));
+    // band extents of the image (0 for every band without informed cells)
+    std::vector<uint32_t> bands(h->n_bands, 0u);
+    for (int y = 0; y < gh; ++y) {
+        const uint32_t* row = cells + (size_t)y * gw;
+        int fx = -1, lx = -1;
+        for (int x = 0; x < gw; ++x)
+            if (row[x]) { if (fx < 0) fx = x; lx = x; }
+        if (fx < 0) continue;
+        uint32_t& e = bands[phys_band(h->geom, (uint32_t)y)];
+        uint32_t bx0 = (uint32_t)fx & ~7u, bx1 = std::min((uint32_t)gw, ((uint32_t)lx + 8u) & ~7u);
+        if (e) { bx0 = std::min(bx0, e & 0xffffu); bx1 = std::max(bx1, e >> 16); }
+        e = bx0 | (bx1 << 16);
+    }
+    CU_TRY(h, cudaMemcpyAsync(h->d_bands + (size_t)slot * h->n_bands, bands.data(), sizeof(uint32_t) * h->n_bands,
+                              cudaMemcpyHostToDevice, h->stream));
     h->est_box_stale = true;
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_get_extents(slamrs_gpu_handle* h, uint64_t particle, int32_t out_box_shift[5], uint32_t* out_bands,
+                           uint32_t* out_n_bands) {
+    if (!h || !out_box_shift) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    int32_t slot = 0;
+    int rc = local_slot(h, particle, &slot);
+    if (rc) return rc;
+    SlotMeta m;
+    CU_TRY(h, cudaMemcpyAsync(&m, h->d_meta + slot, sizeof(m), cudaMemcpyDeviceToHost, h->stream));
+    if (out_bands)
+        CU_TRY(h, cudaMemcpyAsync(out_bands, h->d_bands + (size_t)slot * h->n_bands, sizeof(uint32_t) * h->n_bands,
+                                  cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    out_box_shift[0] = m.x0; out_box_shift[1] = m.y0; out_box_shift[2] = m.x1; out_box_shift[3] = m.y1; out_box_shift[4] = m.ox;
+    if (out_n_bands) *out_n_bands = h->n_bands;
     return SLAMRS_OK;
 }
 

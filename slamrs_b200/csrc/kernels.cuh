@@ -94,6 +94,8 @@ struct CopyItem {
     uint32_t* dst;
     const SlotMeta* src_meta;  // extent of the source grid (peer-mapped for a pull)
     SlotMeta* dst_meta;        // extent of the destination slot (what it held before / holds after)
+    const uint32_t* src_bands; // band extents of the source grid (peer-mapped for a remote source)
+    uint32_t* dst_bands;       // band extents of the destination slot
 };
 
 // ---- launch wrappers (all asynchronous on `stream`) ----
@@ -116,7 +118,7 @@ void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_fl
 // alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive)
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
-                              const int32_t* slot_of, uint32_t* cells, SlotMeta* meta,
+                              const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic);
 
@@ -147,6 +149,9 @@ struct PlanArgs {
     uint32_t* const* peer_cells;        // world pointers to each rank's pool (device array), may be null when world==1
     SlotMeta* meta;                     // local per-slot extents
     SlotMeta* const* peer_meta;         // world pointers to each rank's extents, may be null when world==1
+    uint32_t* bands;                    // local per-slot band extents, n_bands entries per slot
+    uint32_t* const* peer_bands;        // world pointers to each rank's band extents
+    uint32_t n_bands;
     StepCounters* counters;
     StepRecord* history;       // STEP_HISTORY entries, slot = step % STEP_HISTORY
     unsigned long long step;

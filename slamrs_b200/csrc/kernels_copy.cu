@@ -63,45 +63,56 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
 }
 
 // =============================================================================== k_copy_boxed
-// Extent-limited grid copy. A grid is zero outside its extent (SlotMeta), so cloning it means:
-// copy the source's extent and clear whatever else the destination slot's previous tenant had
-// informed. k_copy_prepare turns every fan-out sub-run into one CopyJob (source, source extent,
-// destinations, U = union of the source extent and the destinations' old extents); k_copy_boxed
-// then works on (job, band of rows of U) items, the number of bands per job chosen on the device
-// so that every CTA gets several items. Inside a band the (row, 32-byte unit) pairs of U are
-// linearised over the CTA's threads: each thread issues COPY_UNROLL independent 256-bit loads
-// (zero outside the source extent) and stores each value to every destination of the sub-run.
-// Bytes that really moved are counted on the device and are what the roofline in bench.py uses.
+// Extent-limited grid copy. A grid is zero outside its informed extent, so cloning it means: copy the
+// source's extent and clear whatever else the destination slot's previous tenant had informed. The
+// extent is kept per band of 8 rows (slam_device.cuh): k_copy_prepare turns every fan-out sub-run into
+// one CopyJob (source, destinations, their band tables and row rotations, the band-aligned arc of
+// slot rows to visit); k_copy_boxed takes one (job, band) item per single-warp CTA: it reads the 17
+// band entries, covers the source's columns and the destinations' old columns with one arc U of
+// 32-byte units on the ring of the rotated row, streams the 8 rows x U of the source (zero outside the
+// source's range) into every destination and writes the destinations' new band entries. UNROLL
+// independent 256-bit loads are in flight per lane; bytes that really moved are counted on the device
+// and are what the roofline in bench.py uses.
 
 // A job works in PHYSICAL slot coordinates. x: 32-byte units on the ring of one slot row (ring size =
 // row units when rows rotate, unbounded otherwise); y: rows on the ring of the slot's rows (ring size =
 // slot height for windowed slots, unbounded otherwise). An "arc" is (start, length).
 struct alignas(16) CopyJob {
     const uint32_t* src;
+    const uint32_t* src_bands;
     uint32_t fan;
-    uint32_t rot;               // destination unit = (source unit + rot) & umask
-    uint32_t n_start, n_len;    // x arc of every destination that receives the source's extent
-    uint32_t ny_start, ny_len;  // ... and its row arc (same rows in source and destination)
-    uint32_t u_start, u_len;    // x arc written in every destination (new extent + old extents to clear)
-    uint32_t uy_start, uy_len;  // ... and its row arc
+    uint32_t src_shift;         // row rotation of the source slot (cells)
+    uint32_t new_shift;         // row rotation every destination gets (page-aligns the source's box)
+    uint32_t uy_start, uy_len;  // arc of slot rows to visit, both multiples of BAND_ROWS
+    uint32_t pad[3];
     uint32_t* dst[COPY_FAN];
+    uint32_t* dst_bands[COPY_FAN];
+    uint16_t dst_old_shift[COPY_FAN];
 };
 static_assert(sizeof(CopyJob) % 16 == 0, "CopyJob is fetched as 16-byte pieces");
 constexpr int COPY_JOB_V4 = (int)(sizeof(CopyJob) / 16);
+static_assert(COPY_JOB_V4 <= 32, "one warp fetches a job");
 
 __device__ __forceinline__ bool meta_empty(const SlotMeta& m) { return m.x1 <= m.x0 || m.y1 <= m.y0; }
 
 // smallest arc (of those starting at either operand's start) that covers arcs a and b on the ring
 __device__ __forceinline__ void arc_cover(uint32_t& a_start, uint32_t& a_len, uint32_t b_start, uint32_t b_len,
-                                          uint32_t umask, uint32_t ring) {
+                                          uint32_t mask, uint32_t ring) {
     if (b_len == 0u) return;
     if (a_len == 0u) { a_start = b_start; a_len = b_len; return; }
-    // 64-bit: with unrotated rows the "ring" is the whole 32-bit range and the sums may exceed it
-    const unsigned long long l1 = max((unsigned long long)a_len, (unsigned long long)((b_start - a_start) & umask) + b_len);
-    const unsigned long long l2 = max((unsigned long long)b_len, (unsigned long long)((a_start - b_start) & umask) + a_len);
+    // 64-bit: with an unbounded "ring" (no rotation / no window) the sums may exceed 32 bits
+    const unsigned long long l1 = max((unsigned long long)a_len, (unsigned long long)((b_start - a_start) & mask) + b_len);
+    const unsigned long long l2 = max((unsigned long long)b_len, (unsigned long long)((a_start - b_start) & mask) + a_len);
     if (l2 < l1) { a_start = b_start; a_len = (uint32_t)min(l2, (unsigned long long)ring); }
     else { a_len = (uint32_t)min(l1, (unsigned long long)ring); }
     if (a_len >= ring) { a_start = 0u; a_len = ring; }
+}
+
+// band-aligned arc of physical rows covered by logical rows [y0, y1)
+__device__ __forceinline__ void row_arc(const MapGeom& geom, int y0, int y1, uint32_t& start, uint32_t& len) {
+    const uint32_t b0 = (uint32_t)y0 / BAND_ROWS * BAND_ROWS, b1 = ((uint32_t)y1 + BAND_ROWS - 1u) / BAND_ROWS * BAND_ROWS;
+    start = b0 & geom.ymask;
+    len = b1 - b0;
 }
 
 // one warp per job
@@ -114,8 +125,6 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
     const unsigned long long q = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nl) return;
     const int lane = threadIdx.x & 31;
-    const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
-    const uint32_t ring = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.pw >> 3);
     const uint32_t ymask = geom.ymask, yring = geom.ymask == 0xffffffffu ? 0xffffffffu : geom.ph;
     const unsigned long long k = leaders ? leaders[q] : q;
     const bool have = lane < (int)COPY_FAN && k + lane < n && (leaders != nullptr || lane == 0);
@@ -127,124 +136,131 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
     SlotMeta sm{0, 0, 0, 0, 0, 0, 0, 0}, dm{0, 0, 0, 0, 0, 0, 0, 0};
     if (lane == 0) sm = *it.src_meta;
     if (lane < (int)fan) dm = *it.dst_meta;
-    // the destination's old extent as a physical arc
-    uint32_t o_start = 0u, o_len = 0u, oy_start = 0u, oy_len = 0u;
-    if (lane < (int)fan && !meta_empty(dm)) {
-        o_start = (phys_col(geom, (uint32_t)dm.x0, dm.ox) >> 3) & umask;
-        o_len = (uint32_t)(dm.x1 - dm.x0) >> 3;
-        oy_start = (uint32_t)dm.y0 & ymask;
-        oy_len = (uint32_t)(dm.y1 - dm.y0);
-    }
-    // lane 0 folds the arcs (at most 17) and writes the job header
-    uint32_t u_start = 0u, u_len = 0u, n_start = 0u, n_len = 0u, rot = 0u;
-    uint32_t uy_start = 0u, uy_len = 0u, ny_start = 0u, ny_len = 0u;
-    if (lane == 0 && !meta_empty(sm)) {
-        const uint32_t s_start = (phys_col(geom, (uint32_t)sm.x0, sm.ox) >> 3) & umask;
-        n_len = (uint32_t)(sm.x1 - sm.x0) >> 3;
-        n_start = (phys_col(geom, (uint32_t)sm.x0, align_shift(geom, sm.x0)) >> 3) & umask;   // page-aligned
-        rot = (n_start - s_start) & umask;
-        ny_start = (uint32_t)sm.y0 & ymask; ny_len = (uint32_t)(sm.y1 - sm.y0);
-        u_start = n_start; u_len = n_len; uy_start = ny_start; uy_len = ny_len;
-    }
+    // rows: the destinations' old rows (to clear) and the source's rows, as band-aligned arcs
+    uint32_t oy_start = 0u, oy_len = 0u;
+    if (lane < (int)fan && !meta_empty(dm)) row_arc(geom, dm.y0, dm.y1, oy_start, oy_len);
+    uint32_t uy_start = 0u, uy_len = 0u;
+    if (lane == 0 && !meta_empty(sm)) row_arc(geom, sm.y0, sm.y1, uy_start, uy_len);
     for (uint32_t f = 0; f < fan; ++f) {
-        const uint32_t bs = __shfl_sync(0xffffffffu, o_start, (int)f), bl = __shfl_sync(0xffffffffu, o_len, (int)f);
         const uint32_t bys = __shfl_sync(0xffffffffu, oy_start, (int)f), byl = __shfl_sync(0xffffffffu, oy_len, (int)f);
-        if (lane == 0 && bl && byl) {
-            arc_cover(u_start, u_len, bs, bl, umask, ring);
-            arc_cover(uy_start, uy_len, bys, byl, ymask, yring);
-        }
+        if (lane == 0) arc_cover(uy_start, uy_len, bys, byl, ymask, yring);
     }
     CopyJob* job = jobs + q;
-    if (lane < (int)COPY_FAN) job->dst[lane] = lane < (int)fan ? it.dst : nullptr;
+    if (lane < (int)COPY_FAN) {
+        job->dst[lane] = lane < (int)fan ? it.dst : nullptr;
+        job->dst_bands[lane] = lane < (int)fan ? it.dst_bands : nullptr;
+        job->dst_old_shift[lane] = (uint16_t)(lane < (int)fan ? dm.ox : 0);
+    }
     if (lane == 0) {
-        if (u_len == 0u || uy_len == 0u) { u_start = u_len = 0u; uy_start = uy_len = 0u; }
-        job->src = it.src; job->fan = fan; job->rot = rot;
-        job->n_start = n_start; job->n_len = n_len; job->ny_start = ny_start; job->ny_len = ny_len;
-        job->u_start = u_start; job->u_len = u_len; job->uy_start = uy_start; job->uy_len = uy_len;
+        job->src = it.src; job->src_bands = it.src_bands; job->fan = fan;
+        job->src_shift = (uint32_t)sm.ox;
+        job->new_shift = meta_empty(sm) ? 0u : (uint32_t)align_shift(geom, sm.x0);
+        job->uy_start = uy_start; job->uy_len = uy_len;
+        job->pad[0] = job->pad[1] = job->pad[2] = 0u;
         if (uy_len) atomicMax(&counters->copy_max_rows, (unsigned long long)uy_len);
     }
 }
 
-// One work item = (job, band of rows of U); the (row, 32-byte unit) pairs of the band are linearised
-// over the CTA's threads, UNROLL independent 256-bit loads per thread, then every value is stored
-// to each destination of the sub-run. The job of the next item is fetched into registers while the
-// current item is copied. CTAs are single warps (BOX_THREADS): a band of ~7 rows x 32 units is a
-// few hundred elements, and with more warps per CTA the two barriers per item dominate.
+// CTAs are single warps: a band is a few hundred 32-byte elements, and with more warps per CTA the
+// barriers per item dominate (profiles/r1_copy_tuning.md).
 constexpr int BOX_THREADS = 32;
 constexpr int BOX_CTAS_PER_SM = 256;
-template <int UNROLL, int MINB, int THREADS>
-__global__ void __launch_bounds__(THREADS, MINB)
-k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restrict__ n_jobs,
-             uint32_t row_units /* 32-byte units per physical slot row */, uint32_t umask, uint32_t ymask,
-             uint32_t items_per_cta, StepCounters* counters) {
+
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(BOX_THREADS, MINB)
+k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restrict__ n_jobs, MapGeom geom,
+             StepCounters* counters) {
     __shared__ CopyJob s_job;
-    __shared__ unsigned long long s_moved;
-    if (threadIdx.x == 0) s_moved = 0ull;
     const unsigned long long nl = *n_jobs;
     if (nl == 0) return;
-    // bands per job: about items_per_cta work items per CTA in total, at most one band per row
-    const uint32_t max_rows = (uint32_t)counters->copy_max_rows;
-    const unsigned long long want = ((unsigned long long)gridDim.x * items_per_cta + nl - 1ull) / nl;
-    const uint32_t bands = (uint32_t)(want < 1ull ? 1ull : (want > max_rows ? (max_rows ? max_rows : 1u) : want));
+    const int lane = threadIdx.x;
+    const uint32_t row_units = geom.pw / 8u;
+    const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
+    const uint32_t uring = geom.xmask == 0xffffffffu ? 0xffffffffu : row_units;
+    const uint32_t bands = max(1u, (uint32_t)counters->copy_max_rows / BAND_ROWS);   // work items per job
     const uint32_t total = (uint32_t)min(nl * bands, 0xffffffffull);
-    uint32_t moved = 0;   // 32-byte units read + written by this thread
+    uint32_t moved = 0;   // 32-byte units read + written by this lane
     uint4 next_job = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x < COPY_JOB_V4 && blockIdx.x < total)
-        next_job = reinterpret_cast<const uint4*>(jobs + blockIdx.x / bands)[threadIdx.x];
+    if (lane < COPY_JOB_V4 && blockIdx.x < total)
+        next_job = reinterpret_cast<const uint4*>(jobs + blockIdx.x / bands)[lane];
     for (uint32_t w = blockIdx.x; w < total; w += gridDim.x) {
         const uint32_t q = w / bands;
-        const uint32_t band = w - q * bands;
-        __syncthreads();   // the previous item's job is no longer read
-        if (threadIdx.x < COPY_JOB_V4) {
-            reinterpret_cast<uint4*>(&s_job)[threadIdx.x] = next_job;
+        const uint32_t bi = w - q * bands;
+        __syncwarp();   // the previous item's job is no longer read
+        if (lane < COPY_JOB_V4) {
+            reinterpret_cast<uint4*>(&s_job)[lane] = next_job;
             const unsigned long long wn = (unsigned long long)w + gridDim.x;
-            if (wn < total) next_job = reinterpret_cast<const uint4*>(jobs + (uint32_t)wn / bands)[threadIdx.x];
+            if (wn < total) next_job = reinterpret_cast<const uint4*>(jobs + (uint32_t)wn / bands)[lane];
         }
-        __syncthreads();
-        const uint32_t rows = s_job.uy_len;
-        if (rows == 0u) continue;
-        const uint32_t rows_per_band = (rows + bands - 1u) / bands;
-        const uint32_t r0 = band * rows_per_band, r1 = min(rows, r0 + rows_per_band);   // offsets into the row arc
-        if (r0 >= r1) continue;
-        const uint32_t u_start = s_job.u_start, uw = s_job.u_len, uy_start = s_job.uy_start;
-        const uint32_t n_start = s_job.n_start, n_len = s_job.n_len, rot = s_job.rot;
-        const uint32_t ny_start = s_job.ny_start, ny_len = s_job.ny_len;
+        __syncwarp();
+        if (bi * BAND_ROWS >= s_job.uy_len) continue;
+        const uint32_t prow0 = (s_job.uy_start + bi * BAND_ROWS) & geom.ymask;   // first slot row of the band
+        const uint32_t pb = prow0 / BAND_ROWS;
         const uint32_t fan = s_job.fan;
-        const uint32_t count = (uint32_t)(r1 - r0) * uw;
-        const V8* src = reinterpret_cast<const V8*>(s_job.src);
-        for (uint32_t base = threadIdx.x; base < count; base += THREADS * UNROLL) {
-            V8 v[UNROLL];
-            uint32_t off[UNROLL];   // unit offset inside a destination grid (< 2^28)
+        // ---- the 17 band entries: lane f < fan = destination f's old columns, lane 31 = the source's
+        uint32_t a_start = 0u, a_len = 0u;      // this lane's arc in destination units
+        uint32_t src_entry = 0u;
+        if ((uint32_t)lane < fan) {
+            const uint32_t e = s_job.dst_bands[lane][pb];
+            if (e) {
+                a_start = (phys_col(geom, e & 0xffffu, (int)s_job.dst_old_shift[lane]) >> 3) & umask;
+                a_len = ((e >> 16) - (e & 0xffffu)) >> 3;
+            }
+        } else if (lane == 31) {
+            src_entry = __ldg(&s_job.src_bands[pb]);
+        }
+        src_entry = __shfl_sync(0xffffffffu, src_entry, 31);
+        uint32_t n_start = 0u, n_len = 0u, rot = 0u;   // where the source's columns land in a destination
+        if (src_entry) {
+            const uint32_t sx0 = src_entry & 0xffffu;
+            n_len = ((src_entry >> 16) - sx0) >> 3;
+            n_start = (phys_col(geom, sx0, (int)s_job.new_shift) >> 3) & umask;
+            rot = (n_start - ((phys_col(geom, sx0, (int)s_job.src_shift) >> 3) & umask)) & umask;
+            if (lane == 31) { a_start = n_start; a_len = n_len; }
+        }
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const uint32_t i = base + u * THREADS;
-                off[u] = 0xffffffffu;
-                v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
-                if (i < count) {
-                    const uint32_t rr = i / uw;
-                    const uint32_t py = (uy_start + r0 + rr) & ymask;          // physical row (same in source and destination)
-                    const uint32_t du = (u_start + (i - rr * uw)) & umask;     // destination unit on the ring
-                    off[u] = py * row_units + du;
-                    if (((du - n_start) & umask) < n_len && ((py - ny_start) & ymask) < ny_len) {
-                        v[u] = ld_stream_v8(src + (py * row_units + ((du - rot) & umask)));
-                        moved++;
+        for (int o = 16; o > 0; o >>= 1) {   // cover of all arcs, reduced to lane 0
+            const uint32_t bs = __shfl_down_sync(0xffffffffu, a_start, o), bl = __shfl_down_sync(0xffffffffu, a_len, o);
+            arc_cover(a_start, a_len, bs, bl, umask, uring);
+        }
+        const uint32_t u_start = __shfl_sync(0xffffffffu, a_start, 0), uw = __shfl_sync(0xffffffffu, a_len, 0);
+        if (uw != 0u) {
+            const uint32_t count = BAND_ROWS * uw;
+            const V8* src = reinterpret_cast<const V8*>(s_job.src);
+            for (uint32_t base = lane; base < count; base += BOX_THREADS * UNROLL) {
+                V8 v[UNROLL];
+                uint32_t off[UNROLL];   // unit offset inside a destination slot (< 2^28)
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const uint32_t i = base + u * BOX_THREADS;
+                    off[u] = 0xffffffffu;
+                    v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
+                    if (i < count) {
+                        const uint32_t rr = i / uw;
+                        const uint32_t py = prow0 + rr;                            // same slot row in source and destination
+                        const uint32_t du = (u_start + (i - rr * uw)) & umask;     // destination unit on the ring
+                        off[u] = py * row_units + du;
+                        if (((du - n_start) & umask) < n_len) {
+                            v[u] = ld_stream_v8(src + (py * row_units + ((du - rot) & umask)));
+                            moved++;
+                        }
                     }
                 }
-            }
-            for (uint32_t f = 0; f < fan; ++f) {
-                V8* dst = reinterpret_cast<V8*>(s_job.dst[f]);
+                for (uint32_t f = 0; f < fan; ++f) {
+                    V8* dst = reinterpret_cast<V8*>(s_job.dst[f]);
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
-                    if (off[u] != 0xffffffffu) { st_stream_v8(dst + off[u], v[u]); moved++; }
+                    for (int u = 0; u < UNROLL; ++u)
+                        if (off[u] != 0xffffffffu) { st_stream_v8(dst + off[u], v[u]); moved++; }
+                }
             }
         }
+        // the destinations now hold the source's columns in this band (or nothing)
+        if ((uint32_t)lane < fan) s_job.dst_bands[lane][pb] = src_entry;
     }
-    // bytes actually moved, for the roofline: warp -> CTA -> one global atomic per CTA
+    // bytes actually moved, for the roofline: one atomic per warp = per CTA
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
-    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&s_moved, (unsigned long long)moved);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_moved) atomicAdd(&counters->copy_bytes, s_moved * 32ull);
+    if (lane == 0 && moved) atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
 }
 
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
@@ -252,25 +268,28 @@ void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_
                        void* jobs, MapGeom geom, StepCounters* counters, int num_sms) {
     const uint32_t blocks = (max_items + 7u) / 8u;
     k_copy_prepare<<<blocks ? blocks : 1, 256, 0, stream>>>(items, leaders, n_items, n_leaders, (CopyJob*)jobs, geom, counters);
-    // measured on B200 (gpurun_out/tune_copy4.log): 4 loads in flight per thread, 3 CTAs per SM
-    // resident, grid oversubscribed 32x per SM for balance, ~6 items per CTA
-    const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
-    // measured on B200 (profiles/r1_copy_tuning.md): one-warp CTAs (the per-item barriers cost more than
-    // anything else in larger CTAs), 4 loads in flight per thread, grid oversubscribed for balance,
-    // about 6 items per CTA
-    k_copy_boxed<4, 24, BOX_THREADS><<<num_sms * BOX_CTAS_PER_SM, BOX_THREADS, 0, stream>>>(
-        (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom.pw / 8u, umask, geom.ymask, 6u, counters);
+    k_copy_boxed<4, 24><<<num_sms * BOX_CTAS_PER_SM, BOX_THREADS, 0, stream>>>(
+        (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom, counters);
 }
 size_t copy_job_bytes() { return sizeof(CopyJob); }
 
 __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigned long long* __restrict__ n_items,
                                MapGeom geom, bool realign, StepCounters* counters, StepRecord* record) {
     const unsigned long long n = *n_items;
-    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
-         k += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long k = tid; k < n; k += stride) {
         SlotMeta m = *items[k].src_meta;   // sources are never destinations of the same launch
         if (realign && m.x1 > m.x0) m.ox = align_shift(geom, m.x0);   // the rotation k_copy_prepare chose
         *items[k].dst_meta = m;
+    }
+    if (!realign) {   // whole-grid copies moved the rows verbatim: the band tables go with them
+        const uint32_t nb = bands_per_slot(geom);
+        for (unsigned long long e = tid; e < n * nb; e += stride) {
+            const unsigned long long k = e / nb;
+            const uint32_t b = (uint32_t)(e - k * nb);
+            items[k].dst_bands[b] = items[k].src_bands[b];
+        }
     }
     if (record && blockIdx.x == 0 && threadIdx.x == 0) {
         record->copy_bytes = counters->copy_bytes;
@@ -288,7 +307,7 @@ __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigne
 }
 void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,
                          MapGeom geom, bool realign, StepCounters* counters, StepRecord* record) {
-    const uint32_t blocks = (max_items + 255u) / 256u;
+    const uint32_t blocks = realign ? (max_items + 255u) / 256u : 148u * 8u;
     k_commit_boxes<<<blocks ? blocks : 1, 256, 0, stream>>>(items, n_items, geom, realign, counters, record);
 }
 

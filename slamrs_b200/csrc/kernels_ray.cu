@@ -86,6 +86,50 @@ __device__ __forceinline__ void ext_commit(const int* s_ext, SlotMeta* meta, int
     else { b.x0 = min(b.x0, x0); b.y0 = min(b.y0, y0); b.x1 = max(b.x1, x1); b.y1 = max(b.y1, y1); }
     *meta = b;
 }
+// Band extents of the cells a CTA touches (slam_device.cuh): shared arrays indexed by the band of the
+// window row, merged into the slot's band table by band_commit.
+constexpr int RAY_MAX_BANDS = (2 * 150 + 1) / BAND_ROWS + 2;
+__device__ __forceinline__ void band_init(int* s_blo, int* s_bhi) {
+    for (int i = threadIdx.x; i < RAY_MAX_BANDS; i += blockDim.x) { s_blo[i] = 0x7fffffff; s_bhi[i] = -1; }
+}
+// x range [xlo, xhi] (cells, inclusive) touched in row y; band0 = band of the window's first row
+__device__ __forceinline__ void band_add(int* s_blo, int* s_bhi, int band0, int y, int xlo, int xhi) {
+    const int lb = y / BAND_ROWS - band0;
+    if ((unsigned)lb < (unsigned)RAY_MAX_BANDS) { atomicMin(&s_blo[lb], xlo); atomicMax(&s_bhi[lb], xhi); }
+}
+// after a barrier: union into the slot's table (8-aligned columns). Rows outside the window's bands
+// (cells written through the global path far from the start) fall back to widening by their own band:
+// band_add ignores them, so the caller adds them with band_add_global below.
+__device__ __forceinline__ void band_commit(const int* s_blo, const int* s_bhi, int band0, uint32_t* bands,
+                                            const MapGeom& geom) {
+    for (int lb = threadIdx.x; lb < RAY_MAX_BANDS; lb += blockDim.x) {
+        if (s_bhi[lb] < s_blo[lb]) continue;
+        const uint32_t y = (uint32_t)(band0 + lb) * BAND_ROWS;
+        if (y >= geom.gh) continue;
+        uint32_t* e = &bands[phys_band(geom, y)];
+        const uint32_t old = *e;
+        uint32_t x0 = (uint32_t)s_blo[lb] & ~7u, x1 = min(geom.gw, ((uint32_t)s_bhi[lb] + 8u) & ~7u);
+        if (old != 0u) { x0 = min(x0, old & 0xffffu); x1 = max(x1, old >> 16); }
+        *e = x0 | (x1 << 16);
+    }
+}
+// a single cell written outside the window's bands: widen its band directly (rare, exact path)
+__device__ __forceinline__ void band_add_global(uint32_t* bands, const MapGeom& geom, int band0, int x, int y) {
+    const int lb = y / BAND_ROWS - band0;
+    if ((unsigned)lb < (unsigned)RAY_MAX_BANDS) return;   // covered by the shared arrays
+    uint32_t* e = &bands[phys_band(geom, (uint32_t)y)];
+    const uint32_t x0n = (uint32_t)x & ~7u, x1n = min(geom.gw, ((uint32_t)x + 8u) & ~7u);
+    uint32_t old = *e;
+    for (;;) {
+        const uint32_t x0 = old ? min(x0n, old & 0xffffu) : x0n, x1 = old ? max(x1n, old >> 16) : x1n;
+        const uint32_t nv = x0 | (x1 << 16);
+        if (nv == old) return;
+        const uint32_t seen = atomicCAS(e, old, nv);
+        if (seen == old) return;
+        old = seen;
+    }
+}
+
 constexpr int RAY_MAX_RADIUS = 150;                    // rows of the window: 2 * radius + 1
 constexpr int RAY_MAX_ROWS = 2 * RAY_MAX_RADIUS + 1;
 constexpr int RAY_WB_BATCH = 6;                        // write-back: global loads in flight per thread
@@ -114,8 +158,9 @@ __global__ void __launch_bounds__(RAY_MAX_THREADS)
 k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
              const uint32_t* __restrict__ alive_list,
              const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
-             size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
+             uint32_t* __restrict__ bands_all, size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];
+    __shared__ int s_blo[RAY_MAX_BANDS], s_bhi[RAY_MAX_BANDS];
     __shared__ int s_row_off[RAY_MAX_ROWS + 1];   // first window cell of each row (+ total at [wh])
     __shared__ int s_row_x[RAY_MAX_ROWS];         // x0 | (width << 16)
     __shared__ int s_ext[4];
@@ -139,9 +184,12 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
         return;   // the grid is left as it was; the step reports SLAMRS_E_WINDOW
     }
     const int shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx, s_shift);
+    uint32_t* bands = bands_all + (size_t)slot_of[p] * bands_per_slot(geom);
+    band_init(s_blo, s_bhi);
 
     // ---- row table of the disc window, clipped to the grid
     const int wy0 = max(0, cy - radius), wy1 = min((int)geom.gh, cy + radius + 1);
+    const int band0 = wy0 / BAND_ROWS;
     const int wh = wy1 - wy0;
     for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {
         const int dy = wy0 + ly - cy;
@@ -209,6 +257,8 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                 if (!in_window) {  // beyond the window (range larger than shared memory allows)
                     global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, shift)], inc, &saturated);
                     ext_add(s_ext, x, y, x, y);
+                    band_add(s_blo, s_bhi, band0, y, x, x);
+                    band_add_global(bands, geom, band0, x, y);
                     spilled++;
                 }
             }
@@ -243,6 +293,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                         const int gx0 = (s_row_x[lo] & 0xffff) + lx;
                         exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 3);
                         eymin = min(eymin, wy0 + lo); eymax = max(eymax, wy0 + lo);
+                        band_add(s_blo, s_bhi, band0, wy0 + lo, gx0, gx0 + 3);
                         gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + lo), shift));
                     }
                 }
@@ -271,12 +322,14 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                     *g = cell_sat_add(*g, d, &saturated);
                     exmin = min(exmin, x0 + c); exmax = max(exmax, x0 + c);
                     eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
+                    band_add(s_blo, s_bhi, band0, wy0 + ly, x0 + c, x0 + c);
                 }
             }
         }
     }
     ext_add(s_ext, exmin, eymin, exmax, eymax);
     __syncthreads();
+    band_commit(s_blo, s_bhi, band0, bands, geom);
     if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, shift);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
@@ -314,8 +367,9 @@ __global__ void __maxnreg__(80)   // 2 CTAs of 384 threads per SM; blocks have a
 k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
              const uint32_t* __restrict__ alive_list,
                     const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
-                    size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
+                    uint32_t* __restrict__ bands_all, size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
     extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
+    __shared__ int s_blo[RAY_MAX_BANDS], s_bhi[RAY_MAX_BANDS];
     __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
     __shared__ uint32_t s_rowb[RAY_MAX_ROWS];           // shared byte address of column x = 0 of the row
     __shared__ int s_ext[4];
@@ -339,9 +393,12 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         return;   // the grid is left as it was; the step reports SLAMRS_E_WINDOW
     }
     const int slot_shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx0, s_shift);
+    uint32_t* bands = bands_all + (size_t)slot_of[p] * bands_per_slot(geom);
+    band_init(s_blo, s_bhi);
 
     // ---- row table of the disc window (x ranges aligned to 8 cells = one 128-bit group)
     const int wy0 = max(0, cy0 - radius), wy1 = min(gh, cy0 + radius + 1);
+    const int band0 = wy0 / BAND_ROWS;
     const int wh = wy1 - wy0;
     for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {
         const int dy = wy0 + ly - cy0;
@@ -486,6 +543,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                         const int x = (int)(x2 >> 1), y = wy0 + ly;
                         global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, slot_shift)], CELL_OCC_INC, &saturated);
                         ext_add(s_ext, x, y, x, y);
+                        band_add(s_blo, s_bhi, band0, y, x, x);
                         spilled++;
                     }
                     if (error > 0.0f) {
@@ -542,6 +600,8 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                         global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, slot_shift)],
                                         is_free ? CELL_FREE_INC : CELL_OCC_INC, &saturated);
                         ext_add(s_ext, x, y, x, y);
+                        band_add(s_blo, s_bhi, band0, y, x, x);
+                        band_add_global(bands, geom, band0, x, y);
                         spilled++;
                     }
                 }
@@ -627,6 +687,15 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         for (int j = 0; j < RAY_WB_ROWS; ++j)
             if (nz[j]) { va[j] = gp[j][0]; vb[j] = gp[j][1]; }
 #pragma unroll
+        for (int j = 0; j < RAY_WB_ROWS; ++j) {   // band extent of the row: first / last non-empty group
+            const unsigned mnz = __ballot_sync(0xffffffffu, nz[j]);
+            const int ly = ly0 + j * n_warps;
+            if (mnz != 0u && lane == 0) {
+                const int rx0 = s_row[ly].y & 0xffff;
+                band_add(s_blo, s_bhi, band0, wy0 + ly, rx0 + 8 * (__ffs(mnz) - 1), rx0 + 8 * (31 - __clz(mnz)) + 7);
+            }
+        }
+#pragma unroll
         for (int j = 0; j < RAY_WB_ROWS; ++j) {
             if (nz[j]) {
                 merge_group(va[j], vb[j], d[j]);
@@ -643,6 +712,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
             const int gx0 = (row.y & 0xffff) + 8 * g;
             exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
             eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
+            band_add(s_blo, s_bhi, band0, wy0 + ly, gx0, gx0 + 7);
             uint4* gpt = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
             uint4 ta = gpt[0], tb = gpt[1];
             merge_group(ta, tb, dd);
@@ -652,6 +722,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     }
     ext_add(s_ext, exmin, eymin, exmax, eymax);
     __syncthreads();
+    band_commit(s_blo, s_bhi, band0, bands, geom);
     if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, slot_shift);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
@@ -696,7 +767,7 @@ void launch_sort_beams(cudaStream_t stream, const float* dist, uint32_t n_beams,
 
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
-                              const int32_t* slot_of, uint32_t* cells, SlotMeta* meta,
+                              const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic) {
     int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
@@ -707,7 +778,7 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
         while (radius > 1 && (size_t)ray_window_cells_upper_bound_packed(radius) * 2 > (size_t)RAY_MAX_SMEM) radius--;
         const size_t wmax = (size_t)ray_window_cells_upper_bound_packed(radius);
         *window_cells = wmax;
-        k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
+        k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta, bands,
                                                                   cells_per_grid, radius, radius_cells, counters);
         return cudaSuccess;
     }
@@ -719,10 +790,10 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
     const size_t smem = wmax * 4;
     *window_cells = wmax;
     if (vec)
-        k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
+        k_ray_update<true><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta, bands,
                                                                cells_per_grid, radius, radius_cells, counters);
     else
-        k_ray_update<false><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta,
+        k_ray_update<false><<<n_local, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta, bands,
                                                                 cells_per_grid, radius, radius_cells, counters);
     return cudaSuccess;
 }

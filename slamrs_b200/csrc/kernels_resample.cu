@@ -382,14 +382,17 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
                 const int32_t sslot = slot_old[src - lo];
                 it.src = a.cells + (size_t)sslot * a.cells_per_grid;
                 it.src_meta = a.meta + sslot;
+                it.src_bands = a.bands + (size_t)sslot * a.n_bands;
             } else {
                 const uint32_t owner = src / S;
                 const int32_t sslot = a.results[src].slot;
                 it.src = a.peer_cells[owner] + (size_t)sslot * a.cells_per_grid;
                 it.src_meta = a.peer_meta[owner] + sslot;
+                it.src_bands = a.peer_bands[owner] + (size_t)sslot * a.n_bands;
             }
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
             it.dst_meta = a.meta + dslot;
+            it.dst_bands = a.bands + (size_t)dslot * a.n_bands;
             a.copies[pos] = it;
             if (m == est_m) a.counters->est_meta_ptr = (unsigned long long)(uintptr_t)it.src_meta;   // extent it will have
             // a local run keeps its first use in place, so its copies start one position later

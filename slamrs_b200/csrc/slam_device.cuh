@@ -102,6 +102,14 @@ __host__ __device__ inline int align_shift(const MapGeom& g, int x0) {
     return g.page_cells ? (int)((0u - (uint32_t)x0) & (g.page_cells - 1u)) : 0;
 }
 __host__ __device__ inline uint32_t phys_col(const MapGeom& g, uint32_t x, int shift) { return (x + (uint32_t)shift) & g.xmask; }
+// Band extents. Besides its bounding box, every slot records per band of 8 rows the column range
+// [x0, x1) (multiples of 8) that may hold informed cells, packed x0 | x1 << 16, 0 = nothing in this
+// band. Walls occlude most of a lidar's disc: summed over the bands the ranges cover ~58 % of the
+// box, and that is all the resampler moves. Entries are indexed by the PHYSICAL band of the slot
+// and are 0 for every band outside the box's rows (invariant kept by init, ray update and copy).
+constexpr int BAND_ROWS = 8;
+__host__ __device__ inline uint32_t bands_per_slot(const MapGeom& g) { return (g.ph + BAND_ROWS - 1u) / BAND_ROWS; }
+__host__ __device__ inline uint32_t phys_band(const MapGeom& g, uint32_t y) { return (y & g.ymask) / BAND_ROWS; }
 // offset of logical cell (x, y) inside a slot
 __host__ __device__ inline size_t phys_index(const MapGeom& g, uint32_t x, uint32_t y, int shift) {
     return (size_t)(y & g.ymask) * g.pw + phys_col(g, x, shift);

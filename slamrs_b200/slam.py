@@ -338,6 +338,15 @@ class GridMapSlam:
         _lib.check(self._L.slamrs_gpu_get_slots(self._h, _ptr(slot_of), _ptr(spare) if spare.size else None, C.byref(n)), self._h)
         return slot_of, spare
 
+    def extents(self, particle: int):
+        """((x0, y0, x1, y1), shift, bands[n_bands, 2]): informed box, row rotation and per-band column ranges
+        (x0, x1) of one particle's grid as the resampler sees them."""
+        box = np.zeros(5, np.int32); n = C.c_uint32(0)
+        _lib.check(self._L.slamrs_gpu_get_extents(self._h, particle, _ptr(box), None, C.byref(n)), self._h)
+        raw = np.zeros(int(n.value), np.uint32)
+        _lib.check(self._L.slamrs_gpu_get_extents(self._h, particle, _ptr(box), _ptr(raw), C.byref(n)), self._h)
+        return tuple(int(v) for v in box[:4]), int(box[4]), np.column_stack([raw & 0xFFFF, raw >> 16]).astype(np.int64)
+
     def set_poses(self, xyt) -> None:
         a = np.ascontiguousarray(xyt, np.float32).reshape(self.n_local, 3)
         _lib.check(self._L.slamrs_gpu_set_poses(self._h, _ptr(a)), self._h)

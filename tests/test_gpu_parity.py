@@ -131,6 +131,41 @@ def test_step_parity_scattered_poses_mixed_extents(oracle, copy_flags):
     print(errs[-1])
 
 
+@pytest.mark.parametrize("slot_cells", [0, 256], ids=["whole-grid-slots", "windowed-slots"])
+def test_band_extents_cover_exactly_what_is_informed(oracle, slot_cells):
+    """The resampler's view of every grid -- bounding box and per-band column ranges -- must contain every
+    informed cell, stay inside the box, and be empty for every band outside the box's rows (the invariant
+    the extent copy relies on). Scattered start poses, so slots change tenants with different extents."""
+    cfg = GridMapSlamConfig(position=(-10.24, -10.24), width=20.48, height=20.48, resolution=0.04, n_particles=32)
+    assert S.grid_cells(20.48, 0.04) == 512
+    scans = make_scans(2.0, 360, 2.0, 5)
+    rng = np.random.default_rng(21)
+    init = np.column_stack([rng.uniform(-8.0, 8.0, 32), rng.uniform(-8.0, 8.0, 32), rng.uniform(-np.pi, np.pi, 32)]).astype(np.float32)
+    with GridMapSlam(cfg, GpuPlacement(slot_cells=slot_cells)) as g:
+        g.set_poses(init)
+        ph = slot_cells or 512
+        for obs, odo in scans:
+            g.update(obs, odo)
+            for p in range(0, 32, 3):
+                cells = g.cells(p).reshape(512, 512)
+                (x0, y0, x1, y1), shift, bands = g.extents(p)
+                assert bands.shape[0] == ph // 8 and shift % 8 == 0
+                ys, xs = np.nonzero(cells)
+                assert ys.size and x0 <= xs.min() and xs.max() < x1 and y0 <= ys.min() and ys.max() < y1
+                assert x0 % 8 == 0 and x1 % 8 == 0 and x1 - x0 <= ph and y1 - y0 <= ph
+                in_box = np.zeros(ph // 8, bool)
+                for y in range(y0, y1):
+                    in_box[(y % ph) // 8] = True
+                    row = np.nonzero(cells[y])[0]
+                    b0, b1 = bands[(y % ph) // 8]
+                    if row.size:
+                        assert b0 <= row.min() and row.max() < b1, (p, y)
+                    assert (b0 == 0 and b1 == 0) or (x0 <= b0 < b1 <= x1)
+                assert np.all(bands[~in_box] == 0), "a band outside the box's rows is not empty"
+                # the ranges are tight enough to matter: well below the box area
+                assert (bands[:, 1] - bands[:, 0]).sum() * 8 <= (x1 - x0) * (((y1 + 7) // 8 - y0 // 8) * 8)
+
+
 def test_extent_copy_moves_fewer_bytes_same_result():
     """Both copy modes give identical grids; the extent-limited one reports the bytes it moved."""
     cfg = GridMapSlamConfig(position=(-12.8, -12.8), width=25.6, height=25.6, resolution=0.05, n_particles=256)
