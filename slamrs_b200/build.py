@@ -36,11 +36,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: str = LIB) -> str:
+    """`defines` / `out`: tuning variants (tools/tune_variants.sh); the product library takes neither."""
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)   # the image's CC wrapper is not a usable nvcc host compiler
     res = subprocess.run(cmd, cwd=HERE, env=env, capture_output=True, text=True)
@@ -53,4 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv or bool(defs or outs), verbose="-v" in sys.argv, defines=defs,
+                out=outs[0] if outs else LIB))

@@ -175,6 +175,8 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
     if (nl == 0) return;
     const int lane = threadIdx.x;
     const uint32_t row_units = geom.pw / 8u;
+    const bool tiled = geom.tiled != 0u;
+    constexpr uint32_t TILE_UNITS = TILE_COLS / 8u;   // 32-byte units per tile row
     const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
     const uint32_t uring = geom.xmask == 0xffffffffu ? 0xffffffffu : row_units;
     const uint32_t bands = max(1u, (uint32_t)counters->copy_max_rows / BAND_ROWS);   // work items per job
@@ -223,7 +225,12 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
             const uint32_t bs = __shfl_down_sync(0xffffffffu, a_start, o), bl = __shfl_down_sync(0xffffffffu, a_len, o);
             arc_cover(a_start, a_len, bs, bl, umask, uring);
         }
-        const uint32_t u_start = __shfl_sync(0xffffffffu, a_start, 0), uw = __shfl_sync(0xffffffffu, a_len, 0);
+        uint32_t u_start = __shfl_sync(0xffffffffu, a_start, 0), uw = __shfl_sync(0xffffffffu, a_len, 0);
+        if (tiled && uw != 0u) {   // whole tiles: every DRAM page the band touches is written in full
+            uw = ((u_start & (TILE_UNITS - 1u)) + uw + TILE_UNITS - 1u) & ~(TILE_UNITS - 1u);
+            u_start &= ~(TILE_UNITS - 1u);
+            if (uw >= uring) { u_start = 0u; uw = uring; }
+        }
         if (uw != 0u) {
             const uint32_t count = BAND_ROWS * uw;
             const V8* src = reinterpret_cast<const V8*>(s_job.src);
@@ -236,12 +243,14 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
                     off[u] = 0xffffffffu;
                     v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
                     if (i < count) {
-                        const uint32_t rr = i / uw;
-                        const uint32_t py = prow0 + rr;                            // same slot row in source and destination
-                        const uint32_t du = (u_start + (i - rr * uw)) & umask;     // destination unit on the ring
-                        off[u] = py * row_units + du;
+                        // row-major slots: a lane walks the band's rows; tiled slots: 32 lanes = one tile (1 KiB)
+                        const uint32_t rr = tiled ? (i / TILE_UNITS) % BAND_ROWS : i / uw;
+                        const uint32_t cu = tiled ? i / (TILE_UNITS * BAND_ROWS) * TILE_UNITS + i % TILE_UNITS : i - rr * uw;
+                        const uint32_t py = prow0 + rr;                  // same slot row in source and destination
+                        const uint32_t du = (u_start + cu) & umask;      // destination unit on the ring
+                        off[u] = phys_unit(geom, py, du);
                         if (((du - n_start) & umask) < n_len) {
-                            v[u] = ld_stream_v8(src + (py * row_units + ((du - rot) & umask)));
+                            v[u] = ld_stream_v8(src + phys_unit(geom, py, (du - rot) & umask));
                             moved++;
                         }
                     }

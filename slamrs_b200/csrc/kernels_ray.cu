@@ -335,6 +335,17 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 }
 
+// one 8-cell group as a single 256-bit access (coherent: the exact path may have written the cell)
+__device__ __forceinline__ void ld_group_v8(const uint4* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_group_v8(uint4* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 // ------------------------------------------------------------------------------- packed variant
 // Same algorithm with a 2-byte window cell: bits 0..10 = free hits (a cell can be crossed by at
 // most n_beams <= 2047 rays per scan), bits 11..15 = occupied hits (<= 31; a 32nd hit in one scan
@@ -439,6 +450,16 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     const bool disc_in_grid = cx0 - radius >= 0 && cx0 + radius < gw && cy0 - radius >= 0 && cy0 + radius < gh;
     bool saturated = false;
     uint32_t spilled = 0;
+    // The row table is read at every y-step of the walk. Its shared address is kept in a register the
+    // compiler cannot re-derive: left to itself ptxas may rebuild it inside the loop (S2UR + ULEA per
+    // step, seen in SASS after an unrelated change elsewhere in the kernel), which costs the walk ~15 %.
+    uint32_t rowb_base = (uint32_t)__cvta_generic_to_shared(s_rowb);
+    asm volatile("" : "+r"(rowb_base));
+    auto load_rowb = [&](int row) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(rowb_base + 4u * (uint32_t)row) : "memory");
+        return v;
+    };
     for (uint32_t t = threadIdx.x; t < scan.n_beams; t += blockDim.x) {
         const uint32_t b = scan.order ? scan.order[t] : t;   // similar ray lengths within a warp
         const float dist = scan.dist[b];
@@ -498,7 +519,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
             uint32_t x2 = 2u * (uint32_t)cx0;         // twice the current column
             const uint32_t x_inc2 = (uint32_t)(2 * x_inc);
             int ly = cy0 - wy0;
-            uint32_t rb = s_rowb[ly];
+            uint32_t rb = load_rowb(ly);
             // free run
             while (remaining > 0) {
                 const float acc = __fadd_rn(dx2, dy2);
@@ -511,7 +532,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                     dys = __fsub_rn(sy, cyf);
                     dy2 = __fmul_rn(dys, dys);
                     ly += y_inc;
-                    rb = s_rowb[ly];
+                    rb = load_rowb(ly);
                 } else {
                     error = __fadd_rn(error, delta_y);
                     cxf = __fadd_rn(cxf, x_step);
@@ -552,7 +573,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                         dys = __fsub_rn(sy, cyf);
                         dy2 = __fmul_rn(dys, dys);
                         ly += y_inc;
-                        rb = s_rowb[ly];
+                        rb = load_rowb(ly);
                     } else {
                         error = __fadd_rn(error, delta_y);
                         cxf = __fadd_rn(cxf, x_step);
@@ -685,7 +706,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         }
 #pragma unroll
         for (int j = 0; j < RAY_WB_ROWS; ++j)
-            if (nz[j]) { va[j] = gp[j][0]; vb[j] = gp[j][1]; }
+            if (nz[j]) ld_group_v8(gp[j], va[j], vb[j]);
 #pragma unroll
         for (int j = 0; j < RAY_WB_ROWS; ++j) {   // band extent of the row: first / last non-empty group
             const unsigned mnz = __ballot_sync(0xffffffffu, nz[j]);
@@ -699,8 +720,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         for (int j = 0; j < RAY_WB_ROWS; ++j) {
             if (nz[j]) {
                 merge_group(va[j], vb[j], d[j]);
-                gp[j][0] = va[j];
-                gp[j][1] = vb[j];
+                st_group_v8(gp[j], va[j], vb[j]);
             }
         }
     }

@@ -81,7 +81,14 @@ struct MapGeom {
     uint32_t pw, ph;           // slot width / height in cells (= gw, gh when not windowed)
     uint32_t xmask, ymask, page_cells;
     uint32_t windowed;
+    //  * Tiled slots (slot width a multiple of 32, height a multiple of 8): cells are stored tile by
+    //    tile, a tile = 8 rows x 32 columns = 1 KiB = one DRAM page, tiles row-major. DRAM cost is per
+    //    page touched, and the informed part of a band of 8 rows (~144 of 1024 columns) is 5 full tiles
+    //    instead of 8 half-used row segments. The resampler copies whole tiles. Tiles make the row
+    //    rotation pointless (every tile is page-aligned), so tiled slots have page_cells = 0.
+    uint32_t tiled, tiles_per_row;
 };
+constexpr uint32_t TILE_COLS = 32, TILE_ROWS = 8, TILE_CELLS = TILE_COLS * TILE_ROWS;
 __host__ __device__ inline bool is_pow2_u32(uint32_t v) { return v != 0u && (v & (v - 1u)) == 0u; }
 // slot_cells = 0: a slot holds the whole grid; otherwise the slot is slot_cells x slot_cells (power of two)
 __host__ __device__ inline MapGeom make_map_geom(float pos_x, float pos_y, float res, uint32_t gw, uint32_t gh,
@@ -91,9 +98,14 @@ __host__ __device__ inline MapGeom make_map_geom(float pos_x, float pos_y, float
     g.windowed = (slot_cells != 0u && (slot_cells < gw || slot_cells < gh)) ? 1u : 0u;
     g.pw = g.windowed ? (slot_cells < gw ? slot_cells : gw) : gw;
     g.ph = g.windowed ? (slot_cells < gh ? slot_cells : gh) : gh;
-    const bool rot = g.pw >= 256u && is_pow2_u32(g.pw);
-    g.xmask = rot ? g.pw - 1u : 0xffffffffu;
-    g.page_cells = rot ? 256u : 0u;
+#ifndef SLAMRS_TILED
+#define SLAMRS_TILED 1
+#endif
+    g.tiled = (SLAMRS_TILED && g.pw % TILE_COLS == 0u && g.ph % TILE_ROWS == 0u) ? 1u : 0u;
+    g.tiles_per_row = g.pw / TILE_COLS;
+    const bool ring = g.pw >= 256u && is_pow2_u32(g.pw);     // columns wrap (windowed slots, row rotation)
+    g.xmask = ring ? g.pw - 1u : 0xffffffffu;
+    g.page_cells = (ring && !g.tiled) ? 256u : 0u;
     g.ymask = (g.windowed && is_pow2_u32(g.ph)) ? g.ph - 1u : 0xffffffffu;
     return g;
 }
@@ -112,7 +124,19 @@ __host__ __device__ inline uint32_t bands_per_slot(const MapGeom& g) { return (g
 __host__ __device__ inline uint32_t phys_band(const MapGeom& g, uint32_t y) { return (y & g.ymask) / BAND_ROWS; }
 // offset of logical cell (x, y) inside a slot
 __host__ __device__ inline size_t phys_index(const MapGeom& g, uint32_t x, uint32_t y, int shift) {
-    return (size_t)(y & g.ymask) * g.pw + phys_col(g, x, shift);
+    const uint32_t py = y & g.ymask, px = phys_col(g, x, shift);
+    if (g.tiled)
+        return ((size_t)(py / TILE_ROWS) * g.tiles_per_row + px / TILE_COLS) * TILE_CELLS + (py % TILE_ROWS) * TILE_COLS +
+               px % TILE_COLS;
+    return (size_t)py * g.pw + px;
+}
+
+// offset, in 32-byte units (8 cells), of unit `u` of slot row `py`
+__host__ __device__ inline uint32_t phys_unit(const MapGeom& g, uint32_t py, uint32_t u) {
+    if (g.tiled)
+        return ((py / TILE_ROWS) * g.tiles_per_row + u / (TILE_COLS / 8u)) * (TILE_CELLS / 8u) +
+               (py % TILE_ROWS) * (TILE_COLS / 8u) + u % (TILE_COLS / 8u);
+    return py * (g.pw / 8u) + u;
 }
 
 // Map::world_to_grid, map.rs:60-62
