@@ -228,12 +228,14 @@ void free_all(slamrs_gpu_handle* h) {
     if (h->side_stream) cudaStreamSynchronize(h->side_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && h->d_barrier && h->stream) {
-        // nobody may still be copying from this pool when it is freed. The peer-flag barrier gives up
-        // after about two seconds, so a rank whose peer died does not hang in destroy.
+        // Nobody may still be reading or writing this pool when it is freed: say goodbye and wait until
+        // every peer has said it too (k_peer_barrier). A peer that is still stepping meets the goodbye at
+        // its next barrier, fails that step and is destroyed by its owner, which releases this rank. The
+        // wait is bounded by the barrier timeout (a dead peer process never answers); a handle that is
+        // already poisoned publishes its goodbye and does not wait.
         if (h->p2p_exchange && h->d_peer_flags) {
-            // short wait at destroy: a peer that already failed must not hold this rank for a minute
-            launch_peer_barrier(h->stream, h->d_peer_flags, h->d_flags, h->rank, h->world, ++h->barrier_epoch,
-                                5000000000ull, h->d_counters);
+            launch_peer_goodbye(h->stream, h->d_peer_flags, h->d_flags, h->rank, h->world, h->barrier_timeout_ns,
+                                h->d_counters);
             cudaStreamSynchronize(h->stream);
         } else {
             std::string err;
@@ -475,7 +477,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     // its next records while this rank's host may still be reading the last step's
     h->off_flags = (h->off_results + 2 * sizeof(ParticleResult) * (size_t)h->n_total + 255) & ~(size_t)255;
     h->n_bands = bands_per_slot(h->geom);
-    h->off_bands = (h->off_flags + sizeof(unsigned long long) * PEER_MAX_WORLD + 255) & ~(size_t)255;
+    h->off_bands = (h->off_flags + sizeof(unsigned long long) * 2 * PEER_MAX_WORLD + 255) & ~(size_t)255;   // epochs | goodbyes
     h->pool_header = (h->off_bands + sizeof(uint32_t) * 2 * (size_t)h->n_local * h->n_bands + 4095) & ~(size_t)4095;
     CREATE_CU(cudaMalloc(&h->d_pool, h->pool_header + (size_t)h->n_slots * grid_bytes));
     h->d_meta = (SlotMeta*)h->d_pool;
@@ -743,7 +745,10 @@ int slamrs_gpu_sync(slamrs_gpu_handle* h) {
     int rc = fetch_counters(h);
     if (rc) return rc;
     if (h->h_counters->barrier_timeout)
-        return fail(h, SLAMRS_E_INTERNAL, "a peer GPU did not reach the step barrier within the time limit");
+        return fail(h, SLAMRS_E_INTERNAL,
+                    h->h_counters->barrier_timeout == 2ull
+                        ? "a peer GPU's handle was destroyed (its step failed or its owner left); this handle can only be destroyed"
+                        : "a peer GPU did not reach the step barrier within the time limit");
     if (h->h_counters->window_overflow)
         return fail(h, SLAMRS_E_WINDOW,
                     "a particle's informed extent outgrew its windowed grid slot; raise slot_cells (the scan was not "

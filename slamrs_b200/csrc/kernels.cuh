@@ -44,7 +44,7 @@ struct StepCounters {
     unsigned long long n_alive;          // local particles whose grid is integrated this step
     unsigned long long copy_bytes;       // bytes read + written by the copy kernels this step
     unsigned long long copy_max_rows;    // tallest region any copy job of this step writes (rows)
-    unsigned long long barrier_timeout;  // a peer barrier gave up waiting (error)
+    unsigned long long barrier_timeout;  // 1: a peer barrier gave up waiting, 2: a peer destroyed its handle (errors)
     unsigned long long window_overflow;  // grids whose informed extent would outgrow a windowed slot (error)
     unsigned long long est_meta_ptr;     // SlotMeta whose extent the published map has after this step (0: remote)
     int est_box[4];                      // that extent {x0, y0, x1, y1}; -1 when another rank owns the estimate
@@ -113,6 +113,8 @@ constexpr uint32_t PEER_MAX_WORLD = 64;
 void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
                          uint32_t rank, uint32_t world, unsigned long long epoch, unsigned long long timeout_ns,
                          StepCounters* counters);
+void launch_peer_goodbye(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
+                         uint32_t rank, uint32_t world, unsigned long long timeout_ns, StepCounters* counters);
 
 // returns the shared-memory window size in cells through *window_cells
 // alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive)

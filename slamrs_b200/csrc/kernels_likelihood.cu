@@ -168,13 +168,22 @@ void launch_fill_term_table(cudaStream_t stream, double* table) {
 // waits until GPU q's epoch has arrived here (acquire). Epochs only grow, so flags are never reset.
 // A bounded wait (timeout_ns, one minute by default: ranks are driven by independent host threads
 // that may lag) turns a lost peer into an error instead of a hung GPU.
+// Leaving: a rank that destroys its handle publishes PEER_GOODBYE instead of an epoch and waits for
+// the same from every peer before it frees the memory they have mapped. A peer that meets the
+// goodbye at one of its own barriers is poisoned (barrier_timeout = 2): its step fails at the next
+// sync, its owner destroys it, and only then does the first rank free its pool -- a rank that fails
+// alone (SLAMRS_E_STAGING, SLAMRS_E_WINDOW) never pulls memory from under kernels its peers have
+// already queued.
+constexpr unsigned long long PEER_GOODBYE = ~0ull;
 __global__ void __launch_bounds__(64)
 k_peer_barrier(unsigned long long* const* __restrict__ peer_flags, unsigned long long* my_flags, uint32_t rank,
                uint32_t world, unsigned long long epoch, unsigned long long timeout_ns, StepCounters* counters) {
     const uint32_t q = threadIdx.x;
     if (q >= world) return;
+    const bool leaving = epoch == PEER_GOODBYE;
     __threadfence_system();
-    unsigned long long* theirs = peer_flags[q] + rank;
+    // a flag array holds PEER_MAX_WORLD epochs, then PEER_MAX_WORLD goodbye words (0 until the peer leaves)
+    unsigned long long* theirs = peer_flags[q] + rank + (leaving ? PEER_MAX_WORLD : 0u);
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
     // once a barrier has given up the handle is poisoned (the error is reported at the next sync):
     // later barriers publish their epoch, so that healthy peers keep going, but do not wait again
@@ -183,8 +192,15 @@ k_peer_barrier(unsigned long long* const* __restrict__ peer_flags, unsigned long
     unsigned long long t0, now, seen = 0ull;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-        if (seen >= epoch) break;
+        if (!leaving) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+            if (seen >= epoch) break;
+        }
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine + PEER_MAX_WORLD) : "memory");
+        if (seen == PEER_GOODBYE) {
+            if (!leaving) counters->barrier_timeout = 2ull;   // the peer is going away without reaching this barrier
+            break;
+        }
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (now - t0 > timeout_ns) { counters->barrier_timeout = 1ull; break; }
         __nanosleep(200);
@@ -196,6 +212,10 @@ void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_fl
                          uint32_t rank, uint32_t world, unsigned long long epoch, unsigned long long timeout_ns,
                          StepCounters* counters) {
     k_peer_barrier<<<1, 64, 0, stream>>>(peer_flags, my_flags, rank, world, epoch, timeout_ns, counters);
+}
+void launch_peer_goodbye(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
+                         uint32_t rank, uint32_t world, unsigned long long timeout_ns, StepCounters* counters) {
+    k_peer_barrier<<<1, 64, 0, stream>>>(peer_flags, my_flags, rank, world, PEER_GOODBYE, timeout_ns, counters);
 }
 
 }  // namespace slamrs

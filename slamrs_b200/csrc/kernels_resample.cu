@@ -430,8 +430,11 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     block_excl_scan_u32(nA, s_warp, &distinct);
     block_excl_scan_u32(nR, s_warp, &n_remote);
     if (t == 0) {
-        a.counters->n_copies = used;
-        a.counters->n_leaders = n_lead;
+        // staging short: positions in copies[] have holes (consumers without a slot), so the list is not
+        // handed to the copy kernels at all -- the step fails with SLAMRS_E_STAGING and copies nothing
+        const bool short_of_slots = n_cons > usable;
+        a.counters->n_copies = short_of_slots ? 0u : used;
+        a.counters->n_leaders = short_of_slots ? 0u : n_lead;
         a.counters->n_pulls = n_remote;
         a.counters->distinct = distinct;
         a.counters->staging_short = (n_cons > usable) ? (unsigned long long)(n_cons - usable) : 0ull;

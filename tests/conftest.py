@@ -22,3 +22,15 @@ def oracle():
     from oracle import oracle as O
     O.lib()
     return O
+
+
+@pytest.fixture(autouse=True)
+def _device_still_healthy(request):
+    """A kernel fault is asynchronous and sticky: without this check it surfaces in whichever test
+    touches the device next. Every gpu test ends with a synchronisation of every device."""
+    yield
+    if request.node.get_closest_marker("gpu") is None:
+        return
+    import torch
+    for d in range(torch.cuda.device_count()):
+        torch.cuda.synchronize(d)
