@@ -68,7 +68,13 @@ enum slamrs_flags {
      * ranks with NCCL all-reduces. The default fuses the exchange into the likelihood kernel
      * (each record is stored straight into every peer's copy over NVLink) and synchronises through
      * peer-mapped flags, which costs a few microseconds instead of a collective launch. */
-    SLAMRS_FLAG_NCCL_EXCHANGE = 8
+    SLAMRS_FLAG_NCCL_EXCHANGE = 8,
+    /* Copy every clone when resampling creates it, as `value.clone()` does (particle.rs:97-100).
+     * The default defers: a clone shares its source's cells until it is written, i.e. until its
+     * particle survives a later resampling and receives a scan -- which, with thousands of particles
+     * and a few hundred survivors per step, most clones never do. The observable state is identical.
+     * Whole-grid copies (SLAMRS_FLAG_FULL_GRID_COPY) are always eager. */
+    SLAMRS_FLAG_EAGER_COPY = 16
 };
 
 typedef struct slamrs_gpu_handle slamrs_gpu_handle;
@@ -102,7 +108,7 @@ typedef struct slamrs_gpu_config {
 /* Per-step counters for benchmarks and tests (last completed step). */
 typedef struct slamrs_gpu_stats {
     uint64_t step;             /* number of completed updates */
-    uint64_t grids_copied;     /* local duplicate copies made by the resampler (D) */
+    uint64_t grids_copied;     /* grids copied in the last step: clones made private + eager copies + pulls (D) */
     uint64_t grids_pulled;     /* grids fetched from other GPUs over NVLink */
     uint64_t distinct_sources; /* distinct surviving particles among this rank's new generation */
     uint64_t resample_clamped; /* 1 if a resample index ran past N-1 (the reference would panic) */
@@ -214,11 +220,11 @@ uint64_t slamrs_gpu_launch_count(const slamrs_gpu_handle* h);
 enum slamrs_phase {
     SLAMRS_PHASE_MOTION_LIKELIHOOD = 0,
     SLAMRS_PHASE_ALL_GATHER = 1,
-    SLAMRS_PHASE_RESAMPLE = 2,   /* weights + indices + survivor list */
-    SLAMRS_PHASE_RAY_UPDATE = 3,
-    SLAMRS_PHASE_PLAN = 4,
-    SLAMRS_PHASE_PULL = 5,       /* cross-GPU barriers + NVLink grid pulls */
-    SLAMRS_PHASE_COPY = 6,       /* local fan-out grid copies */
+    SLAMRS_PHASE_RESAMPLE = 2,   /* weights + indices + survivor list + list of shared grids to make private */
+    SLAMRS_PHASE_MATERIALIZE = 3,/* copies that give the surviving clones their own cells (deferred copies) */
+    SLAMRS_PHASE_RAY_UPDATE = 4,
+    SLAMRS_PHASE_PULL = 5,       /* join with the planner + cross-GPU barrier */
+    SLAMRS_PHASE_COPY = 6,       /* eager fan-out copies / NVLink pulls of remote sources, commit */
     SLAMRS_PHASE_COUNT = 7
 };
 int slamrs_gpu_set_profiling(slamrs_gpu_handle* h, int enabled);

@@ -75,6 +75,53 @@ def plan(idx: np.ndarray, rank: int, world: int, slot_old: np.ndarray, spare: np
     return PlanResult(slot_new, spare_new, classes, copies, leaders, np.array(unsafe, np.int64), short)
 
 
+@dataclass
+class DeferredResult:
+    plan: PlanResult
+    materialized: List[tuple]   # (local particle j, root slot, own slot), in particle order: copies before the ray update
+    mat_leaders: List[int]      # positions in `materialized` that start a fan-out sub-run
+    pulls: List[tuple]          # (m, source particle, destination slot): first local uses of remote sources (real copies)
+    alias: np.ndarray           # alias table after the step
+
+
+def plan_deferred(idx: np.ndarray, rank: int, world: int, slot_old: np.ndarray, spare: np.ndarray, alias: np.ndarray,
+                  all_particles: bool = False, fan: int = 16) -> DeferredResult:
+    """Deferred copies (PlanArgs::alias_of, k_materialize_list): slot tables are those of plan(); a clone is an
+    alias of its source's slot until its particle is about to be written."""
+    idx = np.asarray(idx, np.int64)
+    s = idx.size // world
+    lo, hi = rank * s, (rank + 1) * s
+    slot_old = np.asarray(slot_old, np.int64)
+    alias = np.array(alias, np.int64)
+    selected = np.ones(s, bool) if all_particles else np.isin(np.arange(lo, hi), idx)
+    mat, leaders = [], []
+    run_start = 0
+    for j in range(s):
+        own = int(slot_old[j])
+        if selected[j] and alias[own] != own:
+            if not mat or mat[-1][1] != int(alias[own]):
+                run_start = len(mat)
+            if (len(mat) - run_start) % fan == 0:
+                leaders.append(len(mat))
+            mat.append((j, int(alias[own]), own))
+    for _, _, own in mat:
+        alias[own] = own
+    p = plan(idx, rank, world, slot_old, spare, fan)
+    pulls = []
+    first_copy = {}
+    for m, src, dslot in p.copies:
+        cls = p.classes[m]
+        if cls == 1:
+            alias[dslot] = slot_old[src - lo]
+        elif cls == 2:
+            alias[dslot] = dslot
+            first_copy[src] = dslot
+            pulls.append((m, src, dslot))
+        else:
+            alias[dslot] = first_copy[src]
+    return DeferredResult(p, mat, leaders, pulls, alias)
+
+
 def systematic_indices(weights: np.ndarray, u01: float) -> np.ndarray:
     """particle.rs:78-101 on normalised weights (sequential form)."""
     n = weights.size

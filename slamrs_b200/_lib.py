@@ -18,6 +18,7 @@ FLAG_GENERIC_RAY_KERNEL = 1
 FLAG_UPDATE_ALL_PARTICLES = 2
 FLAG_FULL_GRID_COPY = 4
 FLAG_NCCL_EXCHANGE = 8
+FLAG_EAGER_COPY = 16
 HISTORY_VALUES = 6
 
 EXPORTS = [
@@ -34,7 +35,7 @@ EXPORTS = [
     "slamrs_gpu_get_extents",
 ]
 MAP_F64, MAP_F32, MAP_U8 = 0, 1, 2
-PHASES = ["motion_likelihood", "all_gather", "resample", "ray_update", "plan", "pull", "copy"]
+PHASES = ["motion_likelihood", "all_gather", "resample", "materialize", "ray_update", "pull", "copy"]
 
 
 class Config(C.Structure):

@@ -54,6 +54,11 @@ struct slamrs_gpu_handle {
     SlotMeta* d_meta = nullptr;  // = d_pool
     uint32_t* d_cells = nullptr; // = d_pool + pool_header
     bool boxed_copy = false;     // extent-limited copies (needs rows that are multiples of 32 bytes)
+    bool defer = false;          // clones share their source's cells until written (PlanArgs::alias_of)
+    int32_t* d_alias = nullptr;  // n_slots
+    CopyItem* d_mat_items = nullptr;     // n_local: shared grids made private before the ray update
+    uint32_t* d_mat_leaders = nullptr;   // n_local
+    uint32_t* d_mat_roots = nullptr;     // n_local scratch
     int32_t* d_slot[2] = {nullptr, nullptr};
     float* d_pose[2] = {nullptr, nullptr};
     int cur = 0;
@@ -255,6 +260,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
     cudaFree(h->d_copies); cudaFree(h->d_leaders); cudaFree(h->d_alive); cudaFree(h->d_jobs);
+    cudaFree(h->d_alias); cudaFree(h->d_mat_items); cudaFree(h->d_mat_leaders); cudaFree(h->d_mat_roots);
     cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells); cudaFree(h->d_peer_meta);
     cudaFree(h->d_peer_results); cudaFree(h->d_peer_flags); cudaFree(h->d_peer_bands);
     cudaFree(h->d_history);
@@ -307,6 +313,28 @@ int prof_flush(slamrs_gpu_handle* h) {
     do {                                                                                                  \
         if ((h)->profiling) CU_TRY(h, cudaEventRecord((h)->prof_events[(h)->prof_recorded * PROF_MARKS + (m)], (h)->stream)); \
     } while (0)
+
+// the copies k_materialize_list has listed: shared grids get their own cells (extent copies)
+int materialize_copies(slamrs_gpu_handle* h, bool grouped) {
+    launch_copy_boxed(h->stream, h->d_mat_items, grouped ? h->d_mat_leaders : nullptr, &h->d_counters->n_mat,
+                      &h->d_counters->n_mat_leaders, h->n_local, h->d_jobs, h->geom, h->d_counters, h->num_sms, !grouped);
+    launch_commit_boxes(h->stream, h->d_mat_items, &h->d_counters->n_mat, h->n_local, h->geom, true, h->d_counters, nullptr);
+    h->launches += 3;
+    return SLAMRS_OK;
+}
+// every local grid private again (before a grid is overwritten from the host: its clones must not follow)
+int unshare_all(slamrs_gpu_handle* h) {
+    if (!h->defer) return SLAMRS_OK;
+    launch_materialize_list(h->stream, nullptr, h->n_total, h->first, h->n_local, h->d_slot[h->cur], h->d_alias, h->d_cells,
+                            h->cells_per_grid, h->d_meta, h->d_bands, h->n_bands, h->d_mat_items, h->d_mat_leaders,
+                            h->d_mat_roots, h->d_counters);
+    h->launches++;
+    int rc = materialize_copies(h, true);
+    if (rc) return rc;
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->counters_fresh = false;
+    return SLAMRS_OK;
+}
 
 // stream-ordered barrier across ranks inside a step: peer flags by default, NCCL on request
 int step_barrier(slamrs_gpu_handle* h) {
@@ -489,6 +517,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     h->p2p_exchange = h->world > 1 && (cfg->flags & SLAMRS_FLAG_NCCL_EXCHANGE) == 0;
     CREATE_CU(cudaMemsetAsync(h->d_pool, 0, h->pool_header + (size_t)h->n_slots * grid_bytes, h->stream));  // ln(0.5/0.5) = 0
     h->boxed_copy = (cfg->flags & SLAMRS_FLAG_FULL_GRID_COPY) == 0 && cfg->grid_w % 8u == 0u && h->geom.pw % 8u == 0u;
+    h->defer = h->boxed_copy && (cfg->flags & SLAMRS_FLAG_EAGER_COPY) == 0;
     for (int i = 0; i < 2; ++i) {
         CREATE_CU(cudaMalloc(&h->d_slot[i], sizeof(int32_t) * h->n_local));
         CREATE_CU(cudaMalloc(&h->d_pose[i], sizeof(float) * 3 * h->n_local));
@@ -510,6 +539,10 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_copies, sizeof(CopyItem) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_leaders, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_jobs, copy_job_bytes() * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_alias, sizeof(int32_t) * h->n_slots));
+    CREATE_CU(cudaMalloc(&h->d_mat_items, sizeof(CopyItem) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_mat_leaders, sizeof(uint32_t) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_mat_roots, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_alive, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_counters, sizeof(StepCounters)));
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
@@ -522,7 +555,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMemsetAsync(h->d_history, 0xff, sizeof(StepRecord) * STEP_HISTORY, h->stream));
     CREATE_CU(cudaMalloc(&h->d_barrier, sizeof(int)));
     CREATE_CU(cudaMemsetAsync(h->d_barrier, 0, sizeof(int), h->stream));
-    launch_init_slots(h->stream, h->d_slot[0], h->n_local, h->d_spare, h->n_spare, h->d_counters, h->rank, h->d_meta);
+    launch_init_slots(h->stream, h->d_slot[0], h->n_local, h->d_spare, h->n_spare, h->d_counters, h->rank, h->d_meta, h->d_alias);
     h->launches++;
     CREATE_CU(cudaGetLastError());
 
@@ -641,7 +674,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
 
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
-    launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->d_cells, h->d_meta, h->cells_per_grid,
+    launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->defer ? h->d_alias : nullptr, h->d_cells, h->d_meta, h->cells_per_grid,
                              h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step, h->d_term_table, h->d_valid_list, h->d_n_valid,
                              h->p2p_exchange ? h->d_peer_results : nullptr, res_off, h->rank, h->world);
     h->launches += 2;   // k_motion + k_likelihood
@@ -666,6 +699,22 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, !all_particles, h->d_alive, h->d_counters);
+    if (all_particles) {
+        launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local, true, h->d_alive, h->d_counters);
+        h->launches++;
+    }
+    // 3b. deferred copies: the clones among the particles about to be written get their own cells
+    //     (list now, copies after PROF_MARK 3). Before the planner starts: both write the alias table.
+    if (h->defer) {
+        if (all_particles)   // every clone: ordered list with fan-out sub-runs
+            launch_materialize_list(s, nullptr, h->n_total, h->first, h->n_local, h->d_slot[cur], h->d_alias, h->d_cells,
+                                    h->cells_per_grid, h->d_meta, h->d_bands, h->n_bands, h->d_mat_items, h->d_mat_leaders,
+                                    h->d_mat_roots, h->d_counters);
+        else                 // the clones among the survivors: a few hundred, listed in parallel
+            launch_materialize_alive(s, h->d_alive, h->n_local, h->d_slot[cur], h->d_alias, h->d_cells, h->cells_per_grid,
+                                     h->d_meta, h->d_bands, h->n_bands, h->d_mat_items, h->d_counters);
+        h->launches++;
+    }
     // 4. plan (side stream): which grids stay, which are duplicated locally, which are pulled from a
     //    peer. It needs only the index vector, so it runs concurrently with the ray update.
     CU_TRY(h, cudaEventRecord(h->ev_indices, s));
@@ -686,16 +735,18 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.history = h->d_history;
     pa.step = h->step;
     pa.staged = plan_can_stage(h->n_local, h->n_spare);
+    pa.alias_of = h->d_alias; pa.defer = h->defer;
     launch_plan(h->side_stream, pa);
     CU_TRY(h, cudaEventRecord(h->ev_plan, h->side_stream));
     h->launches++;
-    // 5. integrate the scan into the grids that survive resampling (all grids in strict mode)
-    if (all_particles) {
-        launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local, true, h->d_alive, h->d_counters);
-        h->launches++;
-    }
     h->launches += 2;
     PROF_MARK(h, 3);
+    if (h->defer) {
+        int mrc = materialize_copies(h, all_particles);
+        if (mrc) return mrc;
+    }
+    // 5. integrate the scan into the grids that survive resampling (all grids in strict mode)
+    PROF_MARK(h, 4);
     if (h->order_pending) {
         CU_TRY(h, cudaStreamWaitEvent(s, h->ev_sort, 0));
         h->order_pending = false;
@@ -704,18 +755,19 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
                                 h->d_cells, h->d_meta, h->d_bands, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
                                 (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
     h->launches++;
-    PROF_MARK(h, 4);
+    PROF_MARK(h, 5);
     CU_TRY(h, cudaStreamWaitEvent(s, h->ev_plan, 0));   // join: the copy lists are ready
     // 6. grid traffic: one launch copies from local and (over NVLink) remote sources alike. Across
     //    GPUs one barrier first: every source grid, wherever it lives, has received the scan. No
     //    second barrier: nothing written in this step is a slot a peer reads in this step (k_plan).
-    PROF_MARK(h, 5);
     if (h->world > 1) {
         int brc = step_barrier(h);
         if (brc) return brc;
     }
     PROF_MARK(h, 6);
-    if (h->boxed_copy) {
+    if (h->defer && h->world == 1) {
+        // deferred copies on one GPU: the planner's list is empty (no remote sources), nothing to launch
+    } else if (h->boxed_copy) {
         launch_copy_boxed(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->n_local,
                           h->d_jobs, h->geom, h->d_counters, h->num_sms);
         h->launches++;
@@ -725,7 +777,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         launch_account_full_copy(s, &h->d_counters->n_copies, &h->d_counters->n_leaders, grid_bytes, h->d_counters);
         h->launches++;
     }
-    h->launches++;
+    if (!(h->defer && h->world == 1)) h->launches++;
     PROF_MARK(h, 7);
     launch_commit_boxes(s, h->d_copies, &h->d_counters->n_copies, h->n_local, h->geom, h->boxed_copy, h->d_counters,
                         h->d_history + (h->step % STEP_HISTORY));
@@ -909,7 +961,7 @@ int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out) {
     if (rc) return rc;
     const StepCounters& c = *h->h_counters;
     out->step = h->step;
-    out->grids_copied = c.n_copies;
+    out->grids_copied = c.n_copies + c.n_mat;
     out->grids_pulled = c.n_pulls;
     out->distinct_sources = c.distinct;
     out->resample_clamped = c.clamped;
@@ -1032,12 +1084,20 @@ static int local_slot(slamrs_gpu_handle* h, uint64_t particle, int32_t* slot) {
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return SLAMRS_OK;
 }
+// the slot whose cells the particle's grid is read from: its own, or its source's while it is an unwritten clone
+static int local_root_slot(slamrs_gpu_handle* h, uint64_t particle, int32_t* slot) {
+    int rc = local_slot(h, particle, slot);
+    if (rc || !h->defer) return rc;
+    CU_TRY(h, cudaMemcpyAsync(slot, h->d_alias + *slot, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return SLAMRS_OK;
+}
 
 int slamrs_gpu_get_cells(slamrs_gpu_handle* h, uint64_t particle, uint32_t* out_cells) {
     if (!h || !out_cells) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     int32_t slot = 0;
-    int rc = local_slot(h, particle, &slot);
+    int rc = local_root_slot(h, particle, &slot);
     if (rc) return rc;
     // the slot stores its rows rotated; the export kernel undoes that
     launch_export_slot(h->stream, h->d_cells + (size_t)slot * h->cells_per_grid, h->d_meta + slot, h->geom, false, h->d_export);
@@ -1051,7 +1111,9 @@ int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t
     if (!h || !cells) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     int32_t slot = 0;
-    int rc = local_slot(h, particle, &slot);
+    int rc = unshare_all(h);
+    if (rc) return rc;
+    rc = local_slot(h, particle, &slot);
     if (rc) return rc;
     // extent of the informed cells of the new image (stored unrotated: SlotMeta::ox = 0)
     const int gw = (int)h->geom.gw, gh = (int)h->geom.gh;
@@ -1104,7 +1166,7 @@ int slamrs_gpu_get_extents(slamrs_gpu_handle* h, uint64_t particle, int32_t out_
     if (!h || !out_box_shift) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     int32_t slot = 0;
-    int rc = local_slot(h, particle, &slot);
+    int rc = local_root_slot(h, particle, &slot);
     if (rc) return rc;
     SlotMeta m;
     CU_TRY(h, cudaMemcpyAsync(&m, h->d_meta + slot, sizeof(m), cudaMemcpyDeviceToHost, h->stream));
@@ -1121,7 +1183,7 @@ int slamrs_gpu_get_log_odds(slamrs_gpu_handle* h, uint64_t particle, double* out
     if (!h || !out_cells) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     int32_t slot = 0;
-    int rc = local_slot(h, particle, &slot);
+    int rc = local_root_slot(h, particle, &slot);
     if (rc) return rc;
     launch_export_slot(h->stream, h->d_cells + (size_t)slot * h->cells_per_grid, h->d_meta + slot, h->geom, true, h->d_export);
     h->launches++;

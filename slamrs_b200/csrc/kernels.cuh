@@ -47,6 +47,8 @@ struct StepCounters {
     unsigned long long barrier_timeout;  // 1: a peer barrier gave up waiting, 2: a peer destroyed its handle (errors)
     unsigned long long window_overflow;  // grids whose informed extent would outgrow a windowed slot (error)
     unsigned long long est_meta_ptr;     // SlotMeta whose extent the published map has after this step (0: remote)
+    unsigned long long n_mat;            // shared grids made private before this step's ray update (copies)
+    unsigned long long n_mat_leaders;    // fan-out sub-runs among them
     int est_box[4];                      // that extent {x0, y0, x1, y1}; -1 when another rank owns the estimate
     double sum;                          // sum of raw weights (particle.rs:50)
     double n_eff;                        // 1 / sum of squared normalised weights (particle.rs:59-65)
@@ -100,7 +102,8 @@ struct CopyItem {
 
 // ---- launch wrappers (all asynchronous on `stream`) ----
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
-                              const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
+                              const float* pose_cur, const int32_t* slot_of, const int32_t* alias_of /* may be null */,
+                              const uint32_t* cells,
                               const SlotMeta* meta, size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
                               const double* term_table /* LK_TABLE_NF x LK_TABLE_NO, launch_fill_term_table */,
@@ -158,9 +161,30 @@ struct PlanArgs {
     StepRecord* history;       // STEP_HISTORY entries, slot = step % STEP_HISTORY
     unsigned long long step;
     bool staged;               // working arrays in shared memory (plan_can_stage)
+    // Shared grids (deferred copies). alias_of[slot] = the slot whose cells `slot` logically holds:
+    // itself for a private grid, the source's slot for a clone that has not been written since
+    // resampling created it. With `defer` the planner turns every further use of a source into such
+    // an alias instead of a copy (only the first use of a REMOTE source is copied, over NVLink);
+    // k_materialize_list makes a shared grid private when its particle is about to be written.
+    int32_t* alias_of;         // n_local + n_spare_cap
+    bool defer;
 };
 void launch_plan(cudaStream_t stream, const PlanArgs& a);
+// Shared grids that are about to be written (local particles selected by the index vector, or all
+// of them): one CopyItem (root slot -> the particle's own slot) each, in particle order, fan-out
+// leaders as in k_plan; the particles' alias entries become the identity. Counts go to
+// counters->n_mat / n_mat_leaders. idx == nullptr: every local particle (also used to un-share
+// everything before a grid is overwritten from the host).
+void launch_materialize_list(cudaStream_t stream, const uint32_t* idx, uint32_t n_total, uint32_t first_particle,
+                             uint32_t n_local, const int32_t* slot_of, int32_t* alias_of, uint32_t* cells,
+                             size_t cells_per_grid, SlotMeta* meta, uint32_t* bands, uint32_t n_bands, CopyItem* items,
+                             uint32_t* leaders, uint32_t* roots_scratch /* n_local */, StepCounters* counters);
 bool plan_can_stage(uint32_t n_local, uint32_t n_spare_cap);
+
+// the same for the particles of the survivor list (counters->n_alive entries): unordered, no fan-out grouping
+void launch_materialize_alive(cudaStream_t stream, const uint32_t* alive_list, uint32_t n_local, const int32_t* slot_of,
+                              int32_t* alias_of, uint32_t* cells, size_t cells_per_grid, SlotMeta* meta, uint32_t* bands,
+                              uint32_t n_bands, CopyItem* items, StepCounters* counters);
 
 // local particles that appear in the index vector (their grid survives resampling); all_particles
 // lists every local particle instead (reference order of work)
@@ -183,14 +207,14 @@ void launch_export_slot(cudaStream_t stream, const uint32_t* grid, const SlotMet
 
 void launch_import_slot(cudaStream_t stream, const uint32_t* image, uint32_t* grid, SlotMeta m, MapGeom geom);
 void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
-                       StepCounters* counters, uint32_t rank, SlotMeta* meta);
+                       StepCounters* counters, uint32_t rank, SlotMeta* meta, int32_t* alias_of);
 
 // extent-limited copies: only the informed part of each source grid moves, and the part of the
 // destination slot's previous content that the source does not cover is cleared
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
                        const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t max_items,
                        void* jobs /* max_items * copy_job_bytes() of scratch */, MapGeom geom,
-                       StepCounters* counters, int num_sms);
+                       StepCounters* counters, int num_sms, bool short_list = false /* a few hundred items: one wave of CTAs */);
 size_t copy_job_bytes();
 // after a copy kernel: every destination slot now has its source's extent. With `record` the
 // step's moved bytes are also written into the history ring (last copy launch of a step).

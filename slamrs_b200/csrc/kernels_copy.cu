@@ -164,7 +164,14 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
 // CTAs are single warps: a band is a few hundred 32-byte elements, and with more warps per CTA the
 // barriers per item dominate (profiles/r1_copy_tuning.md).
 constexpr int BOX_THREADS = 32;
-constexpr int BOX_CTAS_PER_SM = 256;
+#ifndef BOX_CTAS
+#define BOX_CTAS 256
+#endif
+#ifndef BOX_UNROLL
+#define BOX_UNROLL 4
+#define BOX_MINB 24
+#endif
+constexpr int BOX_CTAS_PER_SM = BOX_CTAS;
 
 template <int UNROLL, int MINB>
 __global__ void __launch_bounds__(BOX_THREADS, MINB)
@@ -274,10 +281,12 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
 
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
                        const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t max_items,
-                       void* jobs, MapGeom geom, StepCounters* counters, int num_sms) {
+                       void* jobs, MapGeom geom, StepCounters* counters, int num_sms, bool short_list) {
     const uint32_t blocks = (max_items + 7u) / 8u;
     k_copy_prepare<<<blocks ? blocks : 1, 256, 0, stream>>>(items, leaders, n_items, n_leaders, (CopyJob*)jobs, geom, counters);
-    k_copy_boxed<4, 24><<<num_sms * BOX_CTAS_PER_SM, BOX_THREADS, 0, stream>>>(
+    // the list length is only known on the device; a CTA without work still costs its launch, and a short
+    // list (the clones made private before the ray update) is served by the resident CTAs alone
+    k_copy_boxed<BOX_UNROLL, BOX_MINB><<<num_sms * (short_list ? BOX_MINB * 2 : BOX_CTAS_PER_SM), BOX_THREADS, 0, stream>>>(
         (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom, counters);
 }
 size_t copy_job_bytes() { return sizeof(CopyJob); }
@@ -303,6 +312,8 @@ __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigne
     if (record && blockIdx.x == 0 && threadIdx.x == 0) {
         record->copy_bytes = counters->copy_bytes;
         record->n_alive = counters->n_alive;
+        record->n_copies += counters->n_mat;          // clones made private before the ray update
+        record->n_leaders += counters->n_mat_leaders;
         // informed extent of the published map, for the windowed read-out (sources are not written here)
         const SlotMeta* em = reinterpret_cast<const SlotMeta*>((uintptr_t)counters->est_meta_ptr);
         if (em == nullptr) { counters->est_box[0] = counters->est_box[1] = counters->est_box[2] = counters->est_box[3] = -1; }

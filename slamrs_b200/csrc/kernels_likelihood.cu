@@ -78,7 +78,8 @@ constexpr int LK_WARPS = 4;
 constexpr int LK_UNROLL = 4;
 
 __global__ void __launch_bounds__(LK_WARPS * 32, 2048 / (LK_WARPS * 32))   // every particle of an 8,192-shard resident at once
-k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, const SlotMeta* __restrict__ meta,
+k_likelihood(MapGeom geom, ScanDevice scan, const int32_t* __restrict__ alias_of, const uint32_t* __restrict__ cells,
+             const SlotMeta* __restrict__ meta,
              size_t cells_per_grid, ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
              const double* __restrict__ term_table, const float2* __restrict__ valid_beams,
              const uint32_t* __restrict__ n_valid_ptr,
@@ -88,8 +89,10 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
     const int lane = threadIdx.x & 31;
     const ParticleResult r = results[first_particle + p];
     const float nx = r.x, ny = r.y, ntheta = r.theta;
-    const uint32_t* grid = cells + (size_t)r.slot * cells_per_grid;
-    const SlotMeta sm = meta[r.slot];    // informed extent (outside it a windowed slot must not be read) ...
+    // a clone that has not been written since resampling shares its source's cells (PlanArgs::alias_of)
+    const int32_t root = alias_of ? alias_of[r.slot] : r.slot;
+    const uint32_t* grid = cells + (size_t)root * cells_per_grid;
+    const SlotMeta sm = meta[root];      // informed extent (outside it a windowed slot must not be read) ...
     const int shift = sm.ox;             // ... and row rotation of this particle's slot
 
     double lp = log(1.0);
@@ -138,14 +141,15 @@ k_likelihood(MapGeom geom, ScanDevice scan, const uint32_t* __restrict__ cells, 
 }
 
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
-                              const float* pose_cur, const int32_t* slot_of, const uint32_t* cells,
+                              const float* pose_cur, const int32_t* slot_of, const int32_t* alias_of,
+                              const uint32_t* cells,
                               const SlotMeta* meta, size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
                               const double* term_table, float2* valid_beams, uint32_t* n_valid,
                               ParticleResult* const* peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
                                                          z_draws, seed, step, scan, valid_beams, n_valid);
-    k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, cells, meta, cells_per_grid,
+    k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, alias_of, cells, meta, cells_per_grid,
                                                                                    results, first_particle, n_local,
                                                                                    term_table, valid_beams, n_valid,
                                                                                    peer_results, peer_offset, rank, world);

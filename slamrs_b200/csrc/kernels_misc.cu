@@ -102,9 +102,12 @@ void launch_import_slot(cudaStream_t stream, const uint32_t* image, uint32_t* gr
 // =============================================================================== init
 
 __global__ void k_init_slots(int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
-                             StepCounters* counters, uint32_t rank, SlotMeta* meta) {
+                             StepCounters* counters, uint32_t rank, SlotMeta* meta, int32_t* alias_of) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_local + n_spare) meta[i] = SlotMeta{0, 0, 0, 0, 0, 0, 0, 0};   // empty: every cell is prior
+    if (i < n_local + n_spare) {
+        meta[i] = SlotMeta{0, 0, 0, 0, 0, 0, 0, 0};   // empty: every cell is prior
+        alias_of[i] = (int32_t)i;                     // every grid is private
+    }
     if (i < n_local) slot_of[i] = (int32_t)i;
     if (i < n_spare) spare_list[i] = (int32_t)(n_local + i);
     if (i == 0) {
@@ -116,9 +119,9 @@ __global__ void k_init_slots(int32_t* slot_of, uint32_t n_local, int32_t* spare_
     }
 }
 void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, int32_t* spare_list, uint32_t n_spare,
-                       StepCounters* counters, uint32_t rank, SlotMeta* meta) {
+                       StepCounters* counters, uint32_t rank, SlotMeta* meta, int32_t* alias_of) {
     const uint32_t n = n_local + n_spare;
-    k_init_slots<<<(n + 255) / 256, 256, 0, stream>>>(slot_of, n_local, spare_list, n_spare, counters, rank, meta);
+    k_init_slots<<<(n + 255) / 256, 256, 0, stream>>>(slot_of, n_local, spare_list, n_spare, counters, rank, meta, alias_of);
 }
 
 // =============================================================================== k_sim_scan

@@ -33,6 +33,7 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
     if (gt == 0) {   // per-step counters start from zero
         counters->clamped = 0ull; counters->saturated = 0ull; counters->spilled = 0ull;
         counters->n_alive = 0ull; counters->copy_bytes = 0ull; counters->copy_max_rows = 0ull;
+        counters->n_mat = 0ull; counters->n_mat_leaders = 0ull;
     }
 
     // pass 1: sum of the raw weights
@@ -353,14 +354,18 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     const uint32_t usable = n_safe + E;   // slots that may be written in this step
 
     // ---- ordered ranks of the consumers (every new particle that does not keep a grid in place)
-    uint32_t n_cons_c = 0;
-    for (uint32_t m = c0; m < c1; ++m) n_cons_c += (need[m] != 0);
-    uint32_t n_cons;
+    // Every consumer takes a free slot. Eager: every consumer is also a copy. Deferred: only the first
+    // local use of a remote source is copied (over NVLink, after the barrier); every other consumer
+    // becomes an alias of its source's slot (PlanArgs::alias_of) and moves no bytes now.
+    uint32_t n_cons_c = 0, n_item_c = 0;
+    for (uint32_t m = c0; m < c1; ++m) { n_cons_c += (need[m] != 0); n_item_c += (need[m] == 2); }
+    uint32_t n_cons, n_items = 0;
     uint32_t pos = block_excl_scan_u32(n_cons_c, s_warp, &n_cons);
+    uint32_t ipos = a.defer ? block_excl_scan_u32(n_item_c, s_warp, &n_items) : pos;   // position in copies[]
     __syncthreads();  // free_list complete
 
     // ---- the copy list. run_first = first position of the current source's run in this range.
-    const uint32_t pos_start = pos;
+    const uint32_t ipos_start = ipos;
     uint32_t n_lead_c = 0;
     const unsigned long long est_m = a.counters->max_particle - lo;   // >= S when another rank owns the estimate
     if (t == 0 && est_m >= S) a.counters->est_meta_ptr = 0ull;
@@ -374,7 +379,11 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             if (m == est_m) a.counters->est_meta_ptr = (unsigned long long)(uintptr_t)(a.meta + slot_new[m]);
             continue;
         }
-        if (pos < usable) {
+        if (pos < usable && a.defer && cls != 2) {
+            slot_new[m] = free_list[pos];
+            need[m] = (uint8_t)(cls == 1 ? 11 : 12);   // alias of a local source / of this rank's copy of a remote one
+            if (m == est_m && cls == 1) a.counters->est_meta_ptr = (unsigned long long)(uintptr_t)(a.meta + slot_old[src - lo]);
+        } else if (pos < usable) {
             const int32_t dslot = free_list[pos];
             slot_new[m] = dslot;
             CopyItem it;
@@ -393,28 +402,47 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
             it.dst = a.cells + (size_t)dslot * a.cells_per_grid;
             it.dst_meta = a.meta + dslot;
             it.dst_bands = a.bands + (size_t)dslot * a.n_bands;
-            a.copies[pos] = it;
+            a.copies[ipos] = it;
             if (m == est_m) a.counters->est_meta_ptr = (unsigned long long)(uintptr_t)it.src_meta;   // extent it will have
             // a local run keeps its first use in place, so its copies start one position later
             const uint32_t k = (cls == 1) ? (m - run_first - 1u) : (m - run_first);
-            const bool lead = (k % COPY_FAN) == 0u;
+            const bool lead = a.defer || (k % COPY_FAN) == 0u;
             need[m] = (uint8_t)(lead ? 9 : 8);
             n_lead_c += lead;
+            if (a.defer) ipos++;
         } else {
             // no writable slot left (SLAMRS_E_STAGING): nothing is copied, the filter state is invalid
             slot_new[m] = (cls == 1) ? slot_old[src - lo] : slot_old[0];
             need[m] = 10;
         }
         pos++;
+        if (!a.defer) ipos = pos;
     }
     // ordered list of leader positions within copies[]
     uint32_t n_lead;
     uint32_t pl = block_excl_scan_u32(n_lead_c, s_warp, &n_lead);
-    pos = pos_start;
+    ipos = ipos_start;
     for (uint32_t m = c0; m < c1; ++m) {
         const int cls = need[m];
-        if (cls == 9) a.leaders[pl++] = pos;
-        if (cls >= 8) pos++;
+        if (cls == 9) a.leaders[pl++] = ipos;
+        if (cls == 8 || cls == 9 || (!a.defer && cls == 10)) ipos++;
+    }
+    __syncthreads();   // slot_new complete
+    // ---- deferred copies: the new particle's slot stands for its source's slot until it is written
+    long long est_root = -1ll;
+    if (a.defer) {
+        for (uint32_t m = c0; m < c1; ++m) {
+            const int cls = need[m];
+            int32_t root = slot_new[m];
+            if (cls == 11) root = slot_old[idx_l[m] - lo];
+            else if (cls == 12) root = slot_new[lower_bound_u32(idx_l, 0, S, idx_l[m])];   // this rank's first use: the copy
+            if (cls == 8 || cls == 9 || cls == 11 || cls == 12) a.alias_of[slot_new[m]] = root;
+            if (m == est_m) {
+                est_root = root;
+                if (cls == 12) a.counters->est_meta_ptr = (unsigned long long)(uintptr_t)(a.meta + root);
+            }
+        }
+        if (est_root >= 0) a.counters->est_slot = est_root;   // the published map is read from the cells it shares
     }
     __syncthreads();
     // ---- next step's spare list: the usable slots nobody took, then this step's unsafe slots
@@ -433,21 +461,169 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
         // staging short: positions in copies[] have holes (consumers without a slot), so the list is not
         // handed to the copy kernels at all -- the step fails with SLAMRS_E_STAGING and copies nothing
         const bool short_of_slots = n_cons > usable;
-        a.counters->n_copies = short_of_slots ? 0u : used;
+        const uint32_t n_copied = a.defer ? n_items : used;
+        a.counters->n_copies = short_of_slots ? 0u : n_copied;
         a.counters->n_leaders = short_of_slots ? 0u : n_lead;
         a.counters->n_pulls = n_remote;
         a.counters->distinct = distinct;
         a.counters->staging_short = (n_cons > usable) ? (unsigned long long)(n_cons - usable) : 0ull;
         const unsigned long long mp = a.counters->max_particle;
         a.counters->est_owner = mp / S;
-        a.counters->est_slot = (mp >= lo && mp < hi) ? (long long)slot_new[mp - lo] : -1ll;
+        if (!a.defer || !(mp >= lo && mp < hi))   // deferred: set above by the thread that owns the estimate
+            a.counters->est_slot = (mp >= lo && mp < hi) ? (long long)slot_new[mp - lo] : -1ll;
         if (a.history) {
             StepRecord r;
-            r.step = a.step; r.n_copies = used; r.n_pulls = n_remote; r.distinct = distinct; r.n_leaders = n_lead;
+            r.step = a.step; r.n_copies = n_copied; r.n_pulls = n_remote; r.distinct = distinct; r.n_leaders = n_lead;
             r.n_alive = 0; r.copy_bytes = 0; r.pad = 0;   // filled in by the step's last kernel (k_commit_boxes)
             a.history[a.step % STEP_HISTORY] = r;
         }
     }
+}
+
+// =============================================================================== k_materialize_list
+// exclusive running maximum of one uint32 per thread over a 1024-thread CTA (0 = nothing before)
+__device__ __forceinline__ uint32_t block_excl_scan_max_u32(uint32_t v, uint32_t* warp_tot /*[33]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = max(inc, t);
+    }
+    __syncthreads();  // protect warp_tot reuse across calls
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t w = lane < nw ? warp_tot[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc = max(winc, t);
+        }
+        const uint32_t excl = __shfl_up_sync(0xffffffffu, winc, 1);
+        warp_tot[lane] = lane == 0 ? 0u : excl;   // maximum over the earlier warps
+    }
+    __syncthreads();
+    const uint32_t within = __shfl_up_sync(0xffffffffu, inc, 1);
+    return max(warp_tot[wid], lane == 0 ? 0u : within);
+}
+
+// A clone that resampling created is an alias of its source's slot until somebody writes it
+// (PlanArgs::alias_of). The particles whose grids this step writes -- the local particles the index
+// vector selects, or all of them -- get their own cells first: one CopyItem (root slot -> own slot)
+// per shared grid, in particle order. Clones of one source are neighbours in that order, so the
+// fan-out leaders are found as in k_plan: the head of each run of equal roots and every COPY_FAN-th
+// item after it. One CTA: the work is three short ordered passes over n_local entries.
+__global__ void __launch_bounds__(1024)
+k_materialize_list(const uint32_t* __restrict__ idx, uint32_t n_total, uint32_t first_particle, uint32_t S,
+                   const int32_t* __restrict__ slot_of, int32_t* alias_of, uint32_t* cells, size_t cells_per_grid,
+                   SlotMeta* meta, uint32_t* bands, uint32_t n_bands, CopyItem* __restrict__ items,
+                   uint32_t* __restrict__ leaders, uint32_t* roots, StepCounters* counters) {
+    __shared__ uint32_t s_warp[33];
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    const uint32_t chunk = (S + T - 1) / T;
+    const uint32_t c0 = min(S, t * chunk), c1 = min(S, c0 + chunk);
+    auto shared_and_written = [&](uint32_t j, int32_t* slot, int32_t* root) {
+        if (idx != nullptr) {   // is local particle j selected by the index vector?
+            const uint32_t v = first_particle + j;
+            const uint32_t q = lower_bound_u32(idx, 0, n_total, v);
+            if (q >= n_total || idx[q] != v) return false;
+        }
+        *slot = slot_of[j];
+        *root = alias_of[*slot];
+        return *root != *slot;
+    };
+    uint32_t cnt = 0;
+    int32_t slot, root;
+    for (uint32_t j = c0; j < c1; ++j) cnt += shared_and_written(j, &slot, &root) ? 1u : 0u;
+    uint32_t total;
+    uint32_t pos = block_excl_scan_u32(cnt, s_warp, &total);
+    for (uint32_t j = c0; j < c1; ++j) {
+        if (!shared_and_written(j, &slot, &root)) continue;
+        CopyItem it;
+        it.src = cells + (size_t)root * cells_per_grid;
+        it.src_meta = meta + root;
+        it.src_bands = bands + (size_t)root * n_bands;
+        it.dst = cells + (size_t)slot * cells_per_grid;
+        it.dst_meta = meta + slot;
+        it.dst_bands = bands + (size_t)slot * n_bands;
+        items[pos] = it;
+        roots[pos] = (uint32_t)root;
+        alias_of[slot] = slot;   // private from here on (the copy is issued right after this kernel)
+        pos++;
+    }
+    __syncthreads();
+    // leaders: run heads and every COPY_FAN-th item of a run
+    const uint32_t ichunk = (total + T - 1) / T;
+    const uint32_t i0 = min(total, t * ichunk), i1 = min(total, i0 + ichunk);
+    uint32_t last_head = 0u;   // position + 1 of the last run head in this thread's items
+    for (uint32_t i = i0; i < i1; ++i)
+        if (i == 0u || roots[i] != roots[i - 1u]) last_head = i + 1u;
+    const uint32_t before = block_excl_scan_max_u32(last_head, s_warp);
+    uint32_t run_start = before ? before - 1u : 0u, n_lead_c = 0u;
+    for (uint32_t i = i0; i < i1; ++i) {
+        if (i == 0u || roots[i] != roots[i - 1u]) run_start = i;
+        n_lead_c += ((i - run_start) % COPY_FAN) == 0u;
+    }
+    uint32_t n_lead;
+    uint32_t pl = block_excl_scan_u32(n_lead_c, s_warp, &n_lead);
+    run_start = before ? before - 1u : 0u;
+    for (uint32_t i = i0; i < i1; ++i) {
+        if (i == 0u || roots[i] != roots[i - 1u]) run_start = i;
+        if (((i - run_start) % COPY_FAN) == 0u) leaders[pl++] = i;
+    }
+    if (t == 0) { counters->n_mat = total; counters->n_mat_leaders = n_lead; }
+}
+
+// The common case (survivors only): the survivor list is a few hundred entries long and already on the
+// device, so the shared grids among them are listed by one thread per survivor, in no particular order
+// and without fan-out grouping (every item reads its own source; the list is short).
+__global__ void __launch_bounds__(256)
+k_materialize_alive(const uint32_t* __restrict__ alive_list, const int32_t* __restrict__ slot_of, int32_t* alias_of,
+                    uint32_t* cells, size_t cells_per_grid, SlotMeta* meta, uint32_t* bands, uint32_t n_bands,
+                    CopyItem* __restrict__ items, StepCounters* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = false;
+    int32_t slot = 0, root = 0;
+    if ((unsigned long long)i < counters->n_alive) {
+        slot = slot_of[alive_list[i]];
+        root = alias_of[slot];
+        take = root != slot;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, take);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) {
+        base = atomicAdd(&counters->n_mat, (unsigned long long)__popc(mask));
+        atomicAdd(&counters->n_mat_leaders, (unsigned long long)__popc(mask));   // every item reads its source itself
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!take) return;
+    CopyItem it;
+    it.src = cells + (size_t)root * cells_per_grid;
+    it.src_meta = meta + root;
+    it.src_bands = bands + (size_t)root * n_bands;
+    it.dst = cells + (size_t)slot * cells_per_grid;
+    it.dst_meta = meta + slot;
+    it.dst_bands = bands + (size_t)slot * n_bands;
+    items[base + __popc(mask & ((1u << lane) - 1u))] = it;
+    alias_of[slot] = slot;
+}
+void launch_materialize_alive(cudaStream_t stream, const uint32_t* alive_list, uint32_t n_local, const int32_t* slot_of,
+                              int32_t* alias_of, uint32_t* cells, size_t cells_per_grid, SlotMeta* meta, uint32_t* bands,
+                              uint32_t n_bands, CopyItem* items, StepCounters* counters) {
+    k_materialize_alive<<<(n_local + 255) / 256, 256, 0, stream>>>(alive_list, slot_of, alias_of, cells, cells_per_grid, meta,
+                                                                   bands, n_bands, items, counters);
+}
+
+void launch_materialize_list(cudaStream_t stream, const uint32_t* idx, uint32_t n_total, uint32_t first_particle,
+                             uint32_t n_local, const int32_t* slot_of, int32_t* alias_of, uint32_t* cells,
+                             size_t cells_per_grid, SlotMeta* meta, uint32_t* bands, uint32_t n_bands, CopyItem* items,
+                             uint32_t* leaders, uint32_t* roots_scratch, StepCounters* counters) {
+    k_materialize_list<<<1, 1024, 0, stream>>>(idx, n_total, first_particle, n_local, slot_of, alias_of, cells, cells_per_grid,
+                                               meta, bands, n_bands, items, leaders, roots_scratch, counters);
 }
 
 bool plan_can_stage(uint32_t n_local, uint32_t n_spare_cap) {

@@ -91,7 +91,7 @@ def test_sharded_equals_single_gpu_and_oracle(oracle, world, exchange_flags):
 
 
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("copy_flags", [0, 4], ids=["extent-copy", "whole-grid-copy"])
+@pytest.mark.parametrize("copy_flags", [0, 16, 4], ids=["deferred-extent-copy", "eager-extent-copy", "whole-grid-copy"])
 def test_sharded_mixed_extents_all_grids(oracle, world, copy_flags):
     """Particles re-scattered over the room every other scan: the grids that migrate between GPUs
     and the slots they land in have very different informed extents. Every particle's grid on every

@@ -109,7 +109,8 @@ def test_many_hits_in_one_cell(oracle, flags):
     lockstep(oracle, cfg, [(same, odo), (near, odo), (same, odo)], flags=flags)
 
 
-COPY_MODES = pytest.mark.parametrize("copy_flags", [0, _lib.FLAG_FULL_GRID_COPY], ids=["extent-copy", "whole-grid-copy"])
+COPY_MODES = pytest.mark.parametrize("copy_flags", [0, _lib.FLAG_EAGER_COPY, _lib.FLAG_FULL_GRID_COPY],
+                                     ids=["deferred-extent-copy", "eager-extent-copy", "whole-grid-copy"])
 
 
 @COPY_MODES
@@ -171,7 +172,7 @@ def test_extent_copy_moves_fewer_bytes_same_result():
     cfg = GridMapSlamConfig(position=(-12.8, -12.8), width=25.6, height=25.6, resolution=0.05, n_particles=256)
     scans = make_scans(5.0, 360, 6.0, 4)
     out = {}
-    for flags in (0, _lib.FLAG_FULL_GRID_COPY):
+    for flags in (0, _lib.FLAG_EAGER_COPY, _lib.FLAG_FULL_GRID_COPY):
         with GridMapSlam(cfg, GpuPlacement(flags=flags)) as g:
             for obs, odo in scans:
                 g.update(obs, odo)
@@ -179,12 +180,16 @@ def test_extent_copy_moves_fewer_bytes_same_result():
             hist = g.step_history(0, len(scans))
             assert hist[-1, 5] == st["copy_bytes"]
             out[flags] = (st, [g.cells(p).copy() for p in (0, 1, 100, 255)], g.estimated_likelihood().data.copy())
-    (st_box, cells_box, map_box), (st_full, cells_full, map_full) = out[0], out[_lib.FLAG_FULL_GRID_COPY]
-    for a, b in zip(cells_box, cells_full):
-        assert np.array_equal(a, b)
-    assert np.array_equal(map_box, map_full)
+    (st_box, cells_box, map_box), (st_full, cells_full, map_full) = out[_lib.FLAG_EAGER_COPY], out[_lib.FLAG_FULL_GRID_COPY]
+    st_def, cells_def, map_def = out[0]
+    for a, b, c in zip(cells_box, cells_full, cells_def):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert np.array_equal(map_box, map_full) and np.array_equal(map_box, map_def)
     assert st_box["grids_copied"] == st_full["grids_copied"] > 0
     assert 0 < st_box["copy_bytes"] < st_full["copy_bytes"] // 4
+    # deferred copies: only the clones that survive the next resampling are ever copied
+    assert 0 < st_def["grids_copied"] <= st_def["particles_integrated"] < st_box["grids_copied"]
+    assert 0 < st_def["copy_bytes"] < st_box["copy_bytes"]
     # whole-grid mode: every copy writes a grid, every fan-out sub-run reads one
     assert st_full["copy_bytes"] >= st_full["grids_copied"] * st_full["bytes_per_grid"]
 
@@ -332,7 +337,8 @@ def test_step_parity_randomised_configurations(oracle, seed):
     beams = int(rng.choice([45, 180, 360, 720]))
     scene = float(rng.choice([1.0, 2.0, 5.0]))
     rng_m = float(rng.choice([0.5, 1.0, 3.0, 6.0]))
-    flags = int(rng.choice([0, _lib.FLAG_GENERIC_RAY_KERNEL, _lib.FLAG_FULL_GRID_COPY, _lib.FLAG_UPDATE_ALL_PARTICLES,
+    flags = int(rng.choice([0, 0, _lib.FLAG_EAGER_COPY, _lib.FLAG_GENERIC_RAY_KERNEL, _lib.FLAG_FULL_GRID_COPY,
+                            _lib.FLAG_UPDATE_ALL_PARTICLES, _lib.FLAG_EAGER_COPY | _lib.FLAG_UPDATE_ALL_PARTICLES,
                             _lib.FLAG_GENERIC_RAY_KERNEL | _lib.FLAG_UPDATE_ALL_PARTICLES]))
     off = rng.uniform(-0.45, 0.45, 2) * width          # where the robot starts inside the map
     cfg = GridMapSlamConfig(position=(float(-width / 2 + off[0]), float(-width / 2 + off[1])), width=width, height=width,
@@ -397,13 +403,14 @@ def test_invalid_arguments_are_errors_not_crashes():
             g.update(obs, odo)  # draws missing in CALLER mode
 
 
-def test_resampling_conserves_grids_at_scale():
+@pytest.mark.parametrize("copy_flags", [0, _lib.FLAG_EAGER_COPY], ids=["deferred", "eager"])
+def test_resampling_conserves_grids_at_scale(copy_flags):
     """configs[1] shape (1,024 particles, 512^2 grid): size-independent properties of one step --
     every new particle's grid equals its source's post-update grid, indices are sorted,
     copies + distinct survivors == N, weights normalise to 1."""
     cfg = GridMapSlamConfig(position=(-12.8, -12.8), width=25.6, height=25.6, resolution=0.05, n_particles=1024)
     scans = make_scans(5.0, 360, 6.0, 3)
-    with GridMapSlam(cfg) as g:
+    with GridMapSlam(cfg, GpuPlacement(flags=copy_flags)) as g:
         for obs, odo in scans[:2]:
             g.update(obs, odo)
         probe = [0, 1, 2, 511, 1023]
@@ -414,7 +421,10 @@ def test_resampling_conserves_grids_at_scale():
         st = g.stats()
         assert np.all(np.diff(idx) >= 0)
         assert abs(w.sum() - 1.0) < 1e-12
-        assert st["grids_copied"] + st["distinct_sources"] == 1024
+        if copy_flags & _lib.FLAG_EAGER_COPY:
+            assert st["grids_copied"] + st["distinct_sources"] == 1024
+        else:   # a clone is copied only when it is about to be written
+            assert st["grids_copied"] <= st["particles_integrated"] == st["distinct_sources"]
         assert st["distinct_sources"] == len(np.unique(idx))
         # duplicates of one source hold identical grids
         dup = np.nonzero(np.diff(idx) == 0)[0]
