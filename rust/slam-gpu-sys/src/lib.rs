@@ -27,7 +27,7 @@ pub const SLAMRS_FLAG_NCCL_EXCHANGE: u32 = 8;
 pub const SLAMRS_MAP_F64: u32 = 0;
 pub const SLAMRS_MAP_F32: u32 = 1;
 pub const SLAMRS_MAP_U8: u32 = 2;
-pub const SLAMRS_HISTORY_VALUES: usize = 6;
+pub const SLAMRS_HISTORY_VALUES: usize = 7;
 
 #[repr(C)]
 pub struct slamrs_gpu_handle {

@@ -768,8 +768,9 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     if (h->defer && h->world == 1) {
         // deferred copies on one GPU: the planner's list is empty (no remote sources), nothing to launch
     } else if (h->boxed_copy) {
+        // deferred copies: what is left here are the first uses of remote sources, a short list
         launch_copy_boxed(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->n_local,
-                          h->d_jobs, h->geom, h->d_counters, h->num_sms);
+                          h->d_jobs, h->geom, h->d_counters, h->num_sms, h->defer);
         h->launches++;
     } else {
         launch_copy(s, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders, h->cells_per_grid,
@@ -1002,7 +1003,8 @@ int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COU
 }
 
 int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_triples) {
-    // six values per step: grids_copied, grids_pulled, distinct_sources, source_reads, particles_integrated, copy_bytes
+    // seven values per step: grids_copied, grids_pulled, distinct_sources, source_reads, particles_integrated,
+    // copy_bytes, ray_cell_steps
     if (!h || !out_triples || count > STEP_HISTORY) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     std::vector<StepRecord> ring(STEP_HISTORY);
@@ -1013,6 +1015,7 @@ int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint3
         if (r.step != first_step + i) return fail(h, SLAMRS_E_INVALID_ARG, "step no longer in the history ring");
         uint64_t* o = out_triples + (size_t)SLAMRS_HISTORY_VALUES * i;
         o[0] = r.n_copies; o[1] = r.n_pulls; o[2] = r.distinct; o[3] = r.n_leaders; o[4] = r.n_alive; o[5] = r.copy_bytes;
+        o[6] = r.ray_cell_steps;
     }
     return SLAMRS_OK;
 }

@@ -49,6 +49,7 @@ struct StepCounters {
     unsigned long long est_meta_ptr;     // SlotMeta whose extent the published map has after this step (0: remote)
     unsigned long long n_mat;            // shared grids made private before this step's ray update (copies)
     unsigned long long n_mat_leaders;    // fan-out sub-runs among them
+    unsigned long long ray_cell_steps;   // ray-iterator steps integrated this step (packed ray kernel), for the roofline
     int est_box[4];                      // that extent {x0, y0, x1, y1}; -1 when another rank owns the estimate
     double sum;                          // sum of raw weights (particle.rs:50)
     double n_eff;                        // 1 / sum of squared normalised weights (particle.rs:59-65)
@@ -59,7 +60,7 @@ struct StepCounters {
 // per-step record kept on the device so that a pipelined caller can read, after the fact, how
 // many grids each step really moved (the roofline is computed from moved bytes only)
 struct StepRecord {
-    unsigned long long step, n_copies, n_pulls, distinct, n_leaders, n_alive, copy_bytes, pad;
+    unsigned long long step, n_copies, n_pulls, distinct, n_leaders, n_alive, copy_bytes, ray_cell_steps;
 };
 constexpr uint32_t STEP_HISTORY = 256;
 constexpr uint32_t COPY_FAN = 16;   // destinations written per source read in k_copy

@@ -168,10 +168,13 @@ constexpr int BOX_THREADS = 32;
 #define BOX_CTAS 256
 #endif
 #ifndef BOX_UNROLL
-#define BOX_UNROLL 4
-#define BOX_MINB 24
+#define BOX_UNROLL 8   // loads in flight per lane: 8 x 12 resident warps measured 2.5 % above 4 x 24 (same bytes in flight,
+#define BOX_MINB 12    // half the dependent round trips per item)
 #endif
 constexpr int BOX_CTAS_PER_SM = BOX_CTAS;
+#ifndef BOX_SHORT_CTAS
+#define BOX_SHORT_CTAS 48   // CTAs per SM for a short list (a few hundred jobs)
+#endif
 
 template <int UNROLL, int MINB>
 __global__ void __launch_bounds__(BOX_THREADS, MINB)
@@ -284,10 +287,16 @@ void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_
                        void* jobs, MapGeom geom, StepCounters* counters, int num_sms, bool short_list) {
     const uint32_t blocks = (max_items + 7u) / 8u;
     k_copy_prepare<<<blocks ? blocks : 1, 256, 0, stream>>>(items, leaders, n_items, n_leaders, (CopyJob*)jobs, geom, counters);
-    // the list length is only known on the device; a CTA without work still costs its launch, and a short
-    // list (the clones made private before the ray update) is served by the resident CTAs alone
-    k_copy_boxed<BOX_UNROLL, BOX_MINB><<<num_sms * (short_list ? BOX_MINB * 2 : BOX_CTAS_PER_SM), BOX_THREADS, 0, stream>>>(
-        (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom, counters);
+    // The list length is only known on the device, and a CTA without work still costs its launch.
+    // A short list (the clones made private before the ray update, NVLink pulls) is bound by the dependent
+    // round trips of its few items: more resident warps with fewer loads each (4 x 24 per SM) and one wave of
+    // CTAs; the long list of eager copies prefers 8 x 12 (measured, profiles/r1_copy_tuning.md).
+    if (short_list)
+        k_copy_boxed<4, 24><<<num_sms * BOX_SHORT_CTAS, BOX_THREADS, 0, stream>>>(
+            (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom, counters);
+    else
+        k_copy_boxed<BOX_UNROLL, BOX_MINB><<<num_sms * BOX_CTAS_PER_SM, BOX_THREADS, 0, stream>>>(
+            (const CopyJob*)jobs, leaders ? n_leaders : n_items, geom, counters);
 }
 size_t copy_job_bytes() { return sizeof(CopyJob); }
 
@@ -312,6 +321,7 @@ __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigne
     if (record && blockIdx.x == 0 && threadIdx.x == 0) {
         record->copy_bytes = counters->copy_bytes;
         record->n_alive = counters->n_alive;
+        record->ray_cell_steps = counters->ray_cell_steps;
         record->n_copies += counters->n_mat;          // clones made private before the ray update
         record->n_leaders += counters->n_mat_leaders;
         // informed extent of the published map, for the windowed read-out (sources are not written here)

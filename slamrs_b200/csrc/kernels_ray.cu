@@ -450,6 +450,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     const bool disc_in_grid = cx0 - radius >= 0 && cx0 + radius < gw && cy0 - radius >= 0 && cy0 + radius < gh;
     bool saturated = false;
     uint32_t spilled = 0;
+    uint32_t cell_steps = 0;   // iterator steps of this thread's rays (C_p, the unit of the ray update's bytes)
     // The row table is read at every y-step of the walk. Its shared address is kept in a register the
     // compiler cannot re-derive: left to itself ptxas may rebuild it inside the loop (S2UR + ULEA per
     // step, seen in SASS after an unrelated change elsewhere in the kernel), which costs the walk ~15 %.
@@ -503,6 +504,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         n += ax + ay;   // wrapping isize arithmetic, then `as usize`
         const unsigned long long cap = (unsigned long long)geom.gw + geom.gh + 8ull;
         int remaining = (int)(n < cap ? n : cap);
+        cell_steps += (uint32_t)remaining;   // what the reference's iterator would visit; minus the rest if the ray leaves the grid
 
         const float x_step = (float)x_inc, y_step = (float)y_inc;
         float cxf = __fadd_rn((float)cx0, 0.5f), cyf = __fadd_rn((float)cy0, 0.5f);
@@ -654,6 +656,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
             }
             remaining -= 1;
         }
+        cell_steps -= (uint32_t)remaining;   // the walk ended at the grid border
     }
     __syncthreads();
 
@@ -746,6 +749,9 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, slot_shift);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cell_steps += __shfl_down_sync(0xffffffffu, cell_steps, o);
+    if ((threadIdx.x & 31) == 0 && cell_steps) atomicAdd(&counters->ray_cell_steps, (unsigned long long)cell_steps);
 }
 
 // =============================================================================== k_sort_beams

@@ -8,7 +8,7 @@ KRX=${2:-k_copy|k_ray_update}
 EXTRA=${3:-}
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-strict --no-full-copy $EXTRA"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-strict --no-full-copy --no-eager $EXTRA"
 $CMD > $OUT/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_launches_${TAG}.log 2>&1
 $CMD > $OUT/plain2_${TAG}.log 2>&1 &&

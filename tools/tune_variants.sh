@@ -10,7 +10,7 @@ cp $LIB variants/main.so
 for v in main "$@"; do
   cp variants/$v.so $LIB
   echo "== $v" >> $OUT
-  python bench.py --steps 16 --warmup 3 --no-cpu-baseline --no-e2e --no-full-copy --no-strict ${BENCH_EXTRA:-} 2>> $OUT.err | python -c '
+  python bench.py --steps 16 --warmup 3 --no-cpu-baseline --no-e2e --no-full-copy --no-strict --no-eager ${BENCH_EXTRA:-} 2>> $OUT.err | python -c '
 import sys, json
 for l in sys.stdin:
     if l.startswith("{"):
