@@ -23,6 +23,7 @@ pub const SLAMRS_FLAG_GENERIC_RAY_KERNEL: u32 = 1;
 pub const SLAMRS_FLAG_UPDATE_ALL_PARTICLES: u32 = 2;
 pub const SLAMRS_FLAG_FULL_GRID_COPY: u32 = 4;
 pub const SLAMRS_FLAG_NCCL_EXCHANGE: u32 = 8;
+pub const SLAMRS_FLAG_EAGER_COPY: u32 = 16;
 
 pub const SLAMRS_MAP_F64: u32 = 0;
 pub const SLAMRS_MAP_F32: u32 = 1;

@@ -12,5 +12,5 @@ CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-strict
 $CMD > $OUT/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_launches_${TAG}.log 2>&1
 $CMD > $OUT/plain2_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"$KRX" -s 8 -c 6 -o $OUT/prof_${TAG} -f $CMD > $OUT/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"$KRX" -s ${NCU_SKIP:-8} -c ${NCU_COUNT:-6} -o $OUT/prof_${TAG} -f $CMD > $OUT/ncu_full_${TAG}.log 2>&1
 ls -la $OUT | tail -8
