@@ -1,5 +1,6 @@
 // The grid copies of resampling (`value.clone()`, particle.rs:97-100): k_copy (whole grids),
-// k_copy_prepare / k_copy_boxed / k_commit_boxes (informed extents, rotated rows).
+// k_copy_prepare / k_copy_boxed / k_commit_boxes (informed extents, whole tiles). With deferred copies
+// (PlanArgs::alias_of) the same kernels run on the short list of clones that are about to be written.
 #include "kernels_common.cuh"
 
 namespace slamrs {
@@ -66,16 +67,17 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
 // Extent-limited grid copy. A grid is zero outside its informed extent, so cloning it means: copy the
 // source's extent and clear whatever else the destination slot's previous tenant had informed. The
 // extent is kept per band of 8 rows (slam_device.cuh): k_copy_prepare turns every fan-out sub-run into
-// one CopyJob (source, destinations, their band tables and row rotations, the band-aligned arc of
-// slot rows to visit); k_copy_boxed takes one (job, band) item per single-warp CTA: it reads the 17
-// band entries, covers the source's columns and the destinations' old columns with one arc U of
-// 32-byte units on the ring of the rotated row, streams the 8 rows x U of the source (zero outside the
-// source's range) into every destination and writes the destinations' new band entries. UNROLL
-// independent 256-bit loads are in flight per lane; bytes that really moved are counted on the device
-// and are what the roofline in bench.py uses.
+// one CopyJob (source, destinations, their band tables, the band-aligned arc of slot rows to visit);
+// k_copy_boxed takes one (job, band) item per single-warp CTA: it reads the 17 band entries, covers the
+// source's columns and the destinations' old columns with one arc U of 32-byte units, rounds U outward
+// to whole tiles when the slot is tiled (one instruction of the warp = one 1 KiB tile = one DRAM page),
+// streams the 8 rows x U of the source (zero outside the source's range) into every destination and
+// writes the destinations' new band entries. UNROLL independent 256-bit loads are in flight per lane;
+// bytes that really moved are counted on the device and are what bench.py's roofline_copy uses.
 
-// A job works in PHYSICAL slot coordinates. x: 32-byte units on the ring of one slot row (ring size =
-// row units when rows rotate, unbounded otherwise); y: rows on the ring of the slot's rows (ring size =
+// A job works in PHYSICAL slot coordinates. x: 32-byte units of one slot row, on a ring when the slot
+// width is a power of two >= 256 (windowed slots wrap; the per-slot row rotation that also used the
+// ring is disabled since tiles -- every shift is 0); y: rows on the ring of the slot's rows (ring size =
 // slot height for windowed slots, unbounded otherwise). An "arc" is (start, length).
 struct alignas(16) CopyJob {
     const uint32_t* src;

@@ -69,10 +69,10 @@ struct MapGeom {
     uint32_t gw, gh;           // logical grid, cells
     // Physical slot. A slot stores logical cell (x, y) at row (y & ymask), column (x + shift) & xmask,
     // `shift` per slot (SlotMeta::ox, a multiple of 8 cells).
-    //  * Row rotation: the resampler picks the shift of every grid it writes so that the informed
-    //    extent starts on a page_cells boundary (1 KiB of cells): a ~250-cell-wide extent then occupies
-    //    one DRAM page per row instead of straddling two (+15 % copy bandwidth, profiles/r1_copy_tuning.md).
-    //    Needs a power-of-two slot width; otherwise xmask = 0xffffffff, page_cells = 0, every shift is 0.
+    //  * Row rotation (superseded by tiles, kept for row-major power-of-two slots, of which there are none
+    //    today: every power of two >= 256 is tiled, so page_cells = 0 and every shift is 0): the resampler
+    //    picks the shift of every grid it writes so that the informed extent starts on a page_cells
+    //    boundary (1 KiB of cells), +15 % copy bandwidth on row-major slots (profiles/r1_copy_tuning.md).
     //  * Windowed slots (pw < gw or ph < gh, powers of two): a slot holds only a pw x ph torus of the
     //    logical grid. The mapping is injective on any extent that fits pw x ph, and a grid's informed
     //    extent is all a slot has to hold (everything else is the prior). Reads outside the extent

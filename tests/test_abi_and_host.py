@@ -119,3 +119,20 @@ def test_ray_walk_loop_compiled_to_the_tight_form():
     r = hot_loop(os.path.join(ROOT, "slamrs_b200", "libslamrs_gpu.so"))
     assert not r["s2ur"] and not r["local_memory"], r["body"]
     assert r["instructions"] <= 27, r["instructions"]
+
+
+def test_bindings_agree_with_the_header_on_flags_phases_and_history():
+    text = open(os.path.join(ROOT, "include", "slamrs_gpu.h")).read()
+    flags = dict(re.findall(r"SLAMRS_FLAG_(\w+)\s*=\s*(\d+)", text))
+    assert {k: int(v) for k, v in flags.items()} == {
+        "GENERIC_RAY_KERNEL": _lib.FLAG_GENERIC_RAY_KERNEL, "UPDATE_ALL_PARTICLES": _lib.FLAG_UPDATE_ALL_PARTICLES,
+        "FULL_GRID_COPY": _lib.FLAG_FULL_GRID_COPY, "NCCL_EXCHANGE": _lib.FLAG_NCCL_EXCHANGE,
+        "EAGER_COPY": _lib.FLAG_EAGER_COPY}
+    phases = re.findall(r"SLAMRS_PHASE_(\w+)\s*=\s*(\d+)", text)
+    names = [n.lower() for n, v in sorted(phases, key=lambda nv: int(nv[1])) if n != "COUNT"]
+    assert names == _lib.PHASES
+    assert int(re.search(r"#define SLAMRS_HISTORY_VALUES (\d+)", text).group(1)) == _lib.HISTORY_VALUES
+    rust = open(os.path.join(ROOT, "rust", "slam-gpu-sys", "src", "lib.rs")).read()
+    assert int(re.search(r"SLAMRS_HISTORY_VALUES: usize = (\d+)", rust).group(1)) == _lib.HISTORY_VALUES
+    for name, value in flags.items():
+        assert re.search(rf"SLAMRS_FLAG_{name}: u32 = {value};", rust), name
