@@ -277,6 +277,18 @@ int slamrs_gpu_debug_sincos(int device, const float* x, uint32_t n, float* out_s
 int slamrs_gpu_debug_stream(int device, uint64_t seed, uint64_t step, uint64_t first, uint64_t count,
                             double* out_z, double* out_u);
 
+/* normalize_weights, the argmax and the resample indices (particle.rs:40-56, 78-101) for n caller-supplied
+ * raw weights and the uniform u01, by the two kernels the step itself runs (k_weights, k_resample_indices).
+ * The sums are the reference's strict left folds, reproduced bit for bit, so
+ * out_idx, out_norm and out_cum (the running sum `c` of particle.rs:85-93 after each weight) equal what
+ * the reference computes from the same weights. out_info = {indices clamped to n-1 (the reference would
+ * panic), rounds the exact fold needed, chunks resolved by its sequential chain, fallback bits (1: sum,
+ * 2: running sum folded by a single thread)}; out_us (optional) = mean device time in microseconds of
+ * {k_weights, k_resample_indices} over 20 launches. */
+int slamrs_gpu_debug_resample(int device, const double* raw_weights, uint32_t n, double u01, uint32_t* out_idx,
+                              uint64_t* out_max_particle, double* out_norm, double* out_cum, uint64_t out_info[4],
+                              float out_us[2]);
+
 #ifdef __cplusplus
 }
 #endif

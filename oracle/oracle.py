@@ -55,6 +55,7 @@ def lib():
     L.so_set_threads.restype = None; L.so_set_threads.argtypes = [vp, C.c_int]
     L.so_set_dead_likelihood.restype = None; L.so_set_dead_likelihood.argtypes = [vp, C.c_int]
     L.so_set_trace.restype = None; L.so_set_trace.argtypes = [vp, i64, i64]
+    L.so_resample_fold.restype = C.c_int; L.so_resample_fold.argtypes = [vp, u64, d, vp, vp, vp, vp]
     L.so_update.restype = C.c_int; L.so_update.argtypes = [vp, vp, vp, vp, u64, f, f, f, vp, d]
     for name in ("so_n", "so_grid_w", "so_grid_h", "so_max_particle"):
         getattr(L, name).restype = u64; getattr(L, name).argtypes = [vp]
@@ -153,6 +154,17 @@ def resample_uniform(seed: int, step: int) -> float:
 
 
 # ---------------------------------------------------------------- simulator restatement
+def resample_fold(raw_weights, u01: float):
+    """normalize_weights + argmax + resample indices (particle.rs:40-56, 78-101) on given raw weights:
+    dict(norm, cum, idx, max_particle, clamped)."""
+    w = np.ascontiguousarray(raw_weights, np.float64).reshape(-1)
+    n = w.size
+    norm = np.zeros(n, np.float64); cum = np.zeros(n, np.float64); idx = np.zeros(n, np.uint64)
+    mp = C.c_uint64(0)
+    clamped = lib().so_resample_fold(_p(w), n, float(u01), _p(norm), _p(cum), _p(idx), C.byref(mp))
+    return dict(norm=norm, cum=cum, idx=idx, max_particle=int(mp.value), clamped=int(clamped))
+
+
 def sim_scan(segments, pose, n_beams, scanner_range):
     seg = np.ascontiguousarray(segments, np.float32).reshape(-1, 4)
     angle = np.zeros(n_beams, np.float64); dist = np.zeros(n_beams, np.float64); valid = np.zeros(n_beams, np.uint8)

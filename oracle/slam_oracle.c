@@ -428,6 +428,46 @@ static inline int total_cmp(double a, double b) {
     return (x > y) - (x < y);
 }
 
+/* ParticleFilter::update's tail and ParticleFilter::resample up to the index vector, on caller-supplied raw
+ * weights: normalize_weights (particle.rs:49-56: sequential sum, divide), argmax by total_cmp with the
+ * last maximum winning (particle.rs:40-46), systematic resampling (particle.rs:78-101). cum (optional)
+ * receives the value of `c` after weight i has been added (c = weights[0] for i = 0). Returns 1 if the
+ * index ran past N-1 (the reference would panic with an out-of-bounds index), else 0. */
+int so_resample_fold(const double* raw, uint64_t n_particles, double u01, double* norm, double* cum, uint64_t* idx,
+                     uint64_t* max_particle) {
+    const int64_t n = (int64_t)n_particles;
+    /* normalize_weights, particle.rs:49-56 */
+    double sum = 0.0;
+    for (int64_t p = 0; p < n; ++p) sum += raw[p];
+    for (int64_t p = 0; p < n; ++p) norm[p] = raw[p] / sum;
+    /* max_by(total_cmp): last maximum wins, particle.rs:40-46 */
+    uint64_t best = 0;
+    for (int64_t p = 1; p < n; ++p)
+        if (total_cmp(norm[p], norm[best]) >= 0) best = (uint64_t)p;
+    *max_particle = best;
+
+    /* resample, particle.rs:78-105 */
+    int clamped = 0;
+    double num = (double)n_particles;
+    double r = u01 * 1.0 / num;
+    double c = norm[0];
+    uint64_t i = 0;
+    if (cum) cum[0] = c;
+    for (uint64_t mm = 1; mm <= n_particles; ++mm) {
+        double u = r + ((double)mm - 1.0) * 1.0 / num;
+        while (u > c) {
+            if (i + 1 >= n_particles) { clamped = 1; break; } /* reference: index-out-of-bounds panic */
+            i += 1;
+            c += norm[i];
+            if (cum) cum[i] = c;
+        }
+        idx[mm - 1] = i;
+    }
+    if (cum) /* the loop stops adding once every threshold is met; the remaining prefixes for inspection */
+        for (uint64_t k = i + 1; k < n_particles; ++k) { c += norm[k]; cum[k] = c; }
+    return clamped;
+}
+
 /* GridMapSlam::update, slam.rs:46-75 with externalised draws:
  * z = 2*N standard normals (per particle: centre draw, heading draw), u01 = resample uniform */
 int so_update(struct so_slam* s, const double* angle, const double* dist, const uint8_t* valid, uint64_t nb,
@@ -441,31 +481,8 @@ int so_update(struct so_slam* s, const double* angle, const double* dist, const 
 #pragma omp parallel for schedule(dynamic, 1) num_threads(s->threads) if (s->threads > 1)
     for (int64_t p = 0; p < n; ++p) particle_step(s, (uint64_t)p, angle, dist, valid, nb, od, z);
 
-    /* normalize_weights, particle.rs:49-56 */
-    double sum = 0.0;
-    for (int64_t p = 0; p < n; ++p) sum += s->raw_weight[p];
-    for (int64_t p = 0; p < n; ++p) s->weight[p] = s->raw_weight[p] / sum;
-    /* max_by(total_cmp): last maximum wins, particle.rs:40-46 */
-    uint64_t best = 0;
-    for (int64_t p = 1; p < n; ++p)
-        if (total_cmp(s->weight[p], s->weight[best]) >= 0) best = (uint64_t)p;
-    s->max_particle = best;
-
-    /* resample, particle.rs:78-105 */
-    s->clamped = 0;
-    double num = (double)s->n;
-    double r = u01 * 1.0 / num;
-    double c = s->weight[0];
-    uint64_t i = 0;
-    for (uint64_t mm = 1; mm <= s->n; ++mm) {
-        double u = r + ((double)mm - 1.0) * 1.0 / num;
-        while (u > c) {
-            if (i + 1 >= s->n) { s->clamped = 1; break; } /* reference: index-out-of-bounds panic */
-            i += 1;
-            c += s->weight[i];
-        }
-        s->last_idx[mm - 1] = i;
-    }
+    /* normalize_weights, argmax, resample indices: particle.rs:40-56, 78-101 */
+    s->clamped = so_resample_fold(s->raw_weight, s->n, u01, s->weight, NULL, s->last_idx, &s->max_particle);
     /* new generation: clone(old[i]) for every slot (deep copy of Pose + Map) */
     struct so_map* new_map = (struct so_map*)calloc(s->n, sizeof(struct so_map));
     so_pose* new_pose = (so_pose*)malloc(s->n * sizeof(so_pose));

@@ -31,6 +31,8 @@ void so_set_dead_likelihood(struct so_slam* s, int on);
 void so_set_trace(struct so_slam* s, int64_t particle, int64_t cap);
 int so_update(struct so_slam* s, const double* angle, const double* dist, const uint8_t* valid, uint64_t nb,
               float dl, float dr, float wheel, const double* z, double u01);
+int so_resample_fold(const double* raw, uint64_t n_particles, double u01, double* norm, double* cum, uint64_t* idx,
+                     uint64_t* max_particle);
 uint64_t so_n(const struct so_slam* s);
 uint64_t so_grid_w(const struct so_slam* s);
 uint64_t so_grid_h(const struct so_slam* s);

@@ -32,7 +32,7 @@ EXPORTS = [
     "slamrs_gpu_set_scan_device", "slamrs_gpu_set_profiling", "slamrs_gpu_get_phase_ms",
     "slamrs_gpu_get_step_history", "slamrs_gpu_map_extent", "slamrs_gpu_map_window",
     "slamrs_gpu_effective_particles", "slamrs_gpu_sim_scan", "slamrs_gpu_get_scan", "slamrs_gpu_get_slots",
-    "slamrs_gpu_get_extents",
+    "slamrs_gpu_get_extents", "slamrs_gpu_debug_resample",
 ]
 MAP_F64, MAP_F32, MAP_U8 = 0, 1, 2
 PHASES = ["motion_likelihood", "all_gather", "resample", "materialize", "ray_update", "pull", "copy"]
@@ -120,6 +120,8 @@ def load():
     L.slamrs_gpu_get_scan.restype = i; L.slamrs_gpu_get_scan.argtypes = [vp, vp, vp, vp, u32, C.POINTER(u32)]
     L.slamrs_gpu_get_slots.restype = i; L.slamrs_gpu_get_slots.argtypes = [vp, vp, vp, C.POINTER(u32)]
     L.slamrs_gpu_get_extents.restype = i; L.slamrs_gpu_get_extents.argtypes = [vp, u64, vp, vp, C.POINTER(u32)]
+    L.slamrs_gpu_debug_resample.restype = i
+    L.slamrs_gpu_debug_resample.argtypes = [i, vp, u32, C.c_double, vp, C.POINTER(u64), vp, vp, vp, vp]
     _lib = L
     return L
 

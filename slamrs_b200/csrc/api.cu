@@ -66,6 +66,7 @@ struct slamrs_gpu_handle {
     ParticleResult* d_results = nullptr;        // the generation of the last issued step
     double* d_wnorm = nullptr;
     double* d_cum = nullptr;
+    double* d_fold = nullptr;    // scratch of k_weights' exact left fold
     uint32_t* d_idx = nullptr;
     float* d_angle = nullptr;
     float* d_dist = nullptr;
@@ -255,7 +256,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_slot[0]); cudaFree(h->d_slot[1]);
     cudaFree(h->d_pose[0]); cudaFree(h->d_pose[1]);
     cudaFree(h->d_term_table);
-    cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx);
+    cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx); cudaFree(h->d_fold);
     cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
@@ -526,6 +527,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_wnorm, sizeof(double) * h->n_total));
     CREATE_CU(cudaMalloc(&h->d_cum, sizeof(double) * h->n_total));
     CREATE_CU(cudaMalloc(&h->d_idx, sizeof(uint32_t) * h->n_total));
+    CREATE_CU(cudaMalloc(&h->d_fold, sizeof(double) * weights_scratch_doubles()));
     CREATE_CU(cudaMemsetAsync(h->d_wnorm, 0, sizeof(double) * h->n_total, h->stream));
     CREATE_CU(cudaMemsetAsync(h->d_idx, 0, sizeof(uint32_t) * h->n_total, h->stream));
     if (cfg->rng_mode == SLAMRS_RNG_CALLER) {
@@ -696,7 +698,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     //    which local particles survive
     PROF_MARK(h, 2);
     // (k_weights also zeroes the per-step counters)
-    launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_counters);
+    launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_fold, h->d_counters);
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, !all_particles, h->d_alive, h->d_counters);
     if (all_particles) {
@@ -1248,6 +1250,53 @@ int slamrs_gpu_debug_stream(int device, uint64_t seed, uint64_t step, uint64_t f
     DBG_CU(cudaGetLastError());
     if (count) DBG_CU(cudaMemcpy(out_z, z.p, sizeof(double) * 2 * count, cudaMemcpyDeviceToHost));
     DBG_CU(cudaMemcpy(out_u, u.p, sizeof(double), cudaMemcpyDeviceToHost));
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_debug_resample(int device, const double* raw_weights, uint32_t n, double u01, uint32_t* out_idx,
+                              uint64_t* out_max_particle, double* out_norm, double* out_cum, uint64_t out_info[4],
+                              float out_us[2]) {
+    if (!raw_weights || !out_idx || n == 0 || n > 0x7fffffffu) return SLAMRS_E_INVALID_ARG;
+    int rc = debug_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device < 0 ? 0 : device);
+    DBG_CU(configure_kernels());
+    DevBuf<ParticleResult> res;
+    DevBuf<double> wn, cum, fold, u;
+    DevBuf<uint32_t> idx;
+    DevBuf<StepCounters> cnt;
+    DBG_CU(res.alloc(n)); DBG_CU(wn.alloc(n)); DBG_CU(cum.alloc(n)); DBG_CU(fold.alloc(weights_scratch_doubles()));
+    DBG_CU(u.alloc(1)); DBG_CU(idx.alloc(n)); DBG_CU(cnt.alloc(1));
+    std::vector<ParticleResult> host(n);
+    for (uint32_t i = 0; i < n; ++i) { host[i].weight = raw_weights[i]; host[i].x = host[i].y = host[i].theta = 0.0f; host[i].slot = 0; }
+    DBG_CU(cudaMemcpy(res.p, host.data(), sizeof(ParticleResult) * (size_t)n, cudaMemcpyHostToDevice));
+    DBG_CU(cudaMemcpy(u.p, &u01, sizeof(double), cudaMemcpyHostToDevice));
+    DBG_CU(cudaMemset(cnt.p, 0, sizeof(StepCounters)));
+    cudaEvent_t ev[3];
+    for (auto& e : ev) DBG_CU(cudaEventCreate(&e));
+    const int reps = out_us ? 20 : 1;
+    float us[2] = {0.f, 0.f};
+    for (int r = 0; r < reps; ++r) {
+        cudaEventRecord(ev[0], nullptr);
+        launch_weights(nullptr, res.p, n, wn.p, cum.p, fold.p, cnt.p);
+        cudaEventRecord(ev[1], nullptr);
+        launch_resample_indices(nullptr, res.p, cum.p, n, u.p, 0, 0, idx.p, nullptr, 0, 0, false, nullptr, cnt.p);
+        cudaEventRecord(ev[2], nullptr);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { for (auto& x : ev) cudaEventDestroy(x); return fail(nullptr, SLAMRS_E_CUDA, cudaGetErrorString(e)); }
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
+        if (r > 0 || reps == 1) { us[0] += a * 1000.f; us[1] += b * 1000.f; }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (out_us) { out_us[0] = us[0] / (float)(reps > 1 ? reps - 1 : 1); out_us[1] = us[1] / (float)(reps > 1 ? reps - 1 : 1); }
+    StepCounters c;
+    DBG_CU(cudaMemcpy(&c, cnt.p, sizeof(c), cudaMemcpyDeviceToHost));
+    DBG_CU(cudaMemcpy(out_idx, idx.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (out_norm) DBG_CU(cudaMemcpy(out_norm, wn.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (out_cum) DBG_CU(cudaMemcpy(out_cum, cum.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (out_max_particle) *out_max_particle = c.max_particle;
+    if (out_info) { out_info[0] = c.clamped; out_info[1] = c.fold_rounds; out_info[2] = c.fold_heads; out_info[3] = c.fold_fallback; }
     return SLAMRS_OK;
 }
 

@@ -50,6 +50,9 @@ struct StepCounters {
     unsigned long long n_mat;            // shared grids made private before this step's ray update (copies)
     unsigned long long n_mat_leaders;    // fan-out sub-runs among them
     unsigned long long ray_cell_steps;   // ray-iterator steps integrated this step (packed ray kernel), for the roofline
+    unsigned long long fold_rounds;      // k_weights: rounds the exact left fold needed (1 = proven at once)
+    unsigned long long fold_heads;       // k_weights: chunks resolved by the sequential chain (binade changes)
+    unsigned long long fold_fallback;    // k_weights: bit 0 / 1 = the raw-weight sum / the running sum fell back to one thread
     int est_box[4];                      // that extent {x0, y0, x1, y1}; -1 when another rank owns the estimate
     double sum;                          // sum of raw weights (particle.rs:50)
     double n_eff;                        // 1 / sum of squared normalised weights (particle.rs:59-65)
@@ -128,8 +131,10 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic);
 
+// fold_scratch: weights_scratch_doubles() doubles
 void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
-                    double* cum, StepCounters* counters);
+                    double* cum, double* fold_scratch, StepCounters* counters);
+size_t weights_scratch_doubles();
 
 void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
                              uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,

@@ -8,26 +8,332 @@ namespace slamrs {
 
 constexpr int W_THREADS = 1024;
 constexpr int W_CLUSTER = 8;   // CTAs of the (portable-size) thread-block cluster that shares the reduction
+constexpr uint32_t W_CHUNKS = W_THREADS * W_CLUSTER;
+
+// ------------------------------------------------------------------------------- the exact left fold
+// The reference adds weights strictly left to right (`iter().sum()`, particle.rs:50; `c += weight[i]`,
+// particle.rs:91-93), and a resample threshold that lands within a few ulps of a prefix value selects a
+// different particle if the sum is re-associated. The cluster reproduces the sequential fold bit for
+// bit, in parallel (oracle/fold_model.py models the same steps on the CPU, tests/test_fold_model.py):
+//
+//  * While the running sum s stays inside one binade [2^e, 2^(e+1)], s = S * 2^(e-52) with S an integer
+//    and fl(s + w) - s depends on s only through the parity of S (round-half-even ties). A chunk of
+//    elements is therefore a two-state transducer: (d0, d1) = the total increment for an even / odd S at
+//    entry, q = whether each flips the parity. Transducers compose associatively -> prefix scan.
+//  * A chunk in which the sum changes binade is a "head": its output comes from a short sequential
+//    chain over the heads (thread 0 of every CTA, operands staged in shared memory).
+//  * The binade of each chunk's incoming sum is GUESSED from an ordinary re-associated prefix sum. The
+//    result is PROVED by induction: every thread folds its chunk from its incoming value with real
+//    additions, and the outcome must equal, bit for bit, the incoming value its successor derived
+//    independently through the scan. Everything in front of the first mismatch is proven; the
+//    procedure restarts behind it from the now exact value (the "anchor"), which also settles on which
+//    side of a binade edge a sum that creeps along the edge lies -- normalised weights end within a few
+//    ulps of 1.0. After FOLD_MAX_ROUNDS rounds, or with more heads than the tables hold (NaN, inf,
+//    adversarial inputs), thread 0 folds sequentially. Either way the result is the reference's.
+constexpr uint32_t FOLD_HEADS_PER_CTA = 48;
+constexpr uint32_t FOLD_HEADS_MAX = FOLD_HEADS_PER_CTA * W_CLUSTER;
+constexpr uint32_t FOLD_STAGE = 2048;     // head operands staged in shared memory for the chain
+constexpr int FOLD_MAX_ROUNDS = 4;
+constexpr int FOLD_MARGIN_BITS = 40;      // "near a binade edge": within 2^-40 relative
+
+struct FoldTd {       // transducer of a range of chunks; a range that contains a head forgets what precedes its last head
+    double d0, d1;
+    uint32_t qc;      // bits 0-1: parity flips for even / odd entry, bits 2..: heads in the range
+};
+struct FoldRec {      // one head, as the chain sees it
+    double d0, d1;    // transducer of the regular chunks between the previous head of the same CTA (or the CTA's first chunk) and this one
+    uint32_t q_prev;  // bits 0-1: q of that transducer, bit 2: an earlier head exists in the same CTA
+    uint32_t chunk;
+};
+struct FoldShared {
+    double warp_f64[33];
+    FoldTd warp_td[33];
+    double cta_part[W_CLUSTER];                        // written by the peers (distributed shared memory)
+    FoldTd cta_tot[W_CLUSTER];                         // "
+    FoldRec rec[W_CLUSTER][FOLD_HEADS_PER_CTA];        // "
+    uint32_t cta_bad[W_CLUSTER];                       // "  first unproven chunk seen by each CTA
+    uint32_t cta_overflow[W_CLUSTER];                  // "
+    FoldTd cta_excl[W_CLUSTER + 1];                    // exclusive composition over the CTAs (local copy)
+    double head_out[FOLD_HEADS_MAX];                   // the chain's results
+    uint32_t head_chunk[FOLD_HEADS_MAX];
+    double vals[FOLD_STAGE];
+    double warp_first[33];                             // incoming value of each warp's first chunk
+    uint32_t bad;                                      // this CTA's first unproven chunk
+    uint32_t overflow;
+    double fallback_total;
+};
+
+__device__ __forceinline__ long long f64_bits(double x) { return __double_as_longlong(x); }
+__device__ __forceinline__ int f64_exponent(double x) { return (int)((f64_bits(x) >> 52) & 0x7ff) - 1023; }
+__device__ __forceinline__ double f64_pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
+
+__device__ __forceinline__ FoldTd fold_compose(const FoldTd& a, const FoldTd& b) {
+    FoldTd r;
+    const uint32_t cnt = (a.qc >> 2) + (b.qc >> 2);
+    if ((b.qc >> 2) != 0u) { r.d0 = b.d0; r.d1 = b.d1; r.qc = (b.qc & 3u) | (cnt << 2); return r; }
+    const uint32_t p0 = a.qc & 1u;                    // parity after `a` for an even entry
+    r.d0 = __dadd_rn(a.d0, p0 ? b.d1 : b.d0);
+    const uint32_t q0 = p0 ^ ((b.qc >> p0) & 1u);
+    const uint32_t a1 = (a.qc >> 1) & 1u;
+    const uint32_t p1 = 1u ^ a1;                      // parity after `a` for an odd entry
+    r.d1 = __dadd_rn(a.d1, p1 ? b.d1 : b.d0);
+    const uint32_t q1 = a1 ^ ((b.qc >> p1) & 1u);
+    r.qc = q0 | (q1 << 1) | (cnt << 2);
+    return r;
+}
+__device__ __forceinline__ FoldTd fold_identity() { FoldTd t; t.d0 = 0.0; t.d1 = 0.0; t.qc = 0u; return t; }
+__device__ __forceinline__ double fold_apply(const FoldTd& t, double s) {
+    return __dadd_rn(s, (f64_bits(s) & 1ll) ? t.d1 : t.d0);
+}
+__device__ __forceinline__ FoldTd fold_shfl_up(const FoldTd& v, int o) {
+    FoldTd r;
+    r.d0 = __shfl_up_sync(0xffffffffu, v.d0, o);
+    r.d1 = __shfl_up_sync(0xffffffffu, v.d1, o);
+    r.qc = __shfl_up_sync(0xffffffffu, v.qc, o);
+    return r;
+}
+// exclusive scan of one transducer per thread over the CTA (fold_compose is associative)
+__device__ __forceinline__ FoldTd block_excl_scan_td(const FoldTd& v, FoldTd* warp_tot /*[33]*/, FoldTd* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    FoldTd inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const FoldTd t = fold_shfl_up(inc, o);
+        if (lane >= o) inc = fold_compose(t, inc);
+    }
+    __syncthreads();
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        FoldTd winc = lane < nw ? warp_tot[lane] : fold_identity();
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const FoldTd t = fold_shfl_up(winc, o);
+            if (lane >= o) winc = fold_compose(t, winc);
+        }
+        const FoldTd excl = fold_shfl_up(winc, 1);
+        if (lane == 31) warp_tot[32] = winc;
+        warp_tot[lane] = lane == 0 ? fold_identity() : excl;
+    }
+    __syncthreads();
+    *total = warp_tot[32];
+    const FoldTd within = fold_shfl_up(inc, 1);
+    return lane == 0 ? warp_tot[wid] : fold_compose(warp_tot[wid], within);
+}
+
+// Binade the running sum is assumed to be in when the re-associated prefix says `a` (> 0, finite). Away
+// from the binade edges: a's own. Within the margin of an edge 2^k the sum may be on either side: the
+// side of the anchor (the last exactly known value) if the anchor lies in the same zone, else the lower
+// one (a sum creeping up to an edge is below it until proven otherwise). *zone = near an edge.
+__device__ __forceinline__ int fold_guess_binade(double a, double anchor, bool* zone) {
+    const int e = f64_exponent(a);
+    if (e < -960 || e > 1000) { *zone = false; return e; }   // callers reject these exponents
+    const double x0 = f64_pow2(e);
+    int k;
+    if (a < __dadd_rn(x0, f64_pow2(e - FOLD_MARGIN_BITS))) k = e;
+    else if (a > __dsub_rn(__dmul_rn(2.0, x0), f64_pow2(e + 1 - FOLD_MARGIN_BITS))) k = e + 1;
+    else { *zone = false; return e; }
+    *zone = true;
+    const double edge = f64_pow2(k);
+    if (anchor > 0.0 && fabs(__dsub_rn(anchor, edge)) <= f64_pow2(k - FOLD_MARGIN_BITS)) return anchor >= edge ? k : k - 1;
+    return k - 1;
+}
+
+struct FoldInfo { uint32_t rounds, heads, fallback; };
+
+// prefix[i] = the reference's running sum after element i (prefix may be null); returns the total.
+// `load(i)` yields element i; first_is_assignment: the fold starts with s = v[0] (particle.rs:85)
+// instead of 0.0 + v[0] (particle.rs:50). sout: W_CHUNKS doubles of global scratch. Cluster-uniform.
+template <typename Load>
+__device__ double exact_left_fold(cg::cluster_group& cluster, FoldShared& sh, uint32_t n, Load load, bool first_is_assignment,
+                                  double* __restrict__ prefix, double* __restrict__ sout, FoldInfo* info) {
+    const uint32_t crank = cluster.block_rank();
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t gt = crank * W_THREADS + tid;
+    const uint32_t L = (n + W_CHUNKS - 1u) / W_CHUNKS;
+    const uint32_t lo = min(n, gt * L), hi = min(n, lo + L);
+    const uint32_t last = (n - 1u) / L;               // last non-empty chunk (n >= 1)
+    info->rounds = 0u; info->heads = 0u; info->fallback = 0u;
+
+    double part = 0.0;
+    bool all_zero = true;
+    for (uint32_t i = lo; i < hi; ++i) {
+        const double x = load(i);
+        part = __dadd_rn(part, x);
+        all_zero = all_zero && x == 0.0;
+    }
+    auto fold_chunk = [&](double s, bool write) {
+        for (uint32_t i = lo; i < hi; ++i) {
+            const double x = load(i);
+            s = (i == 0u && first_is_assignment) ? x : __dadd_rn(s, x);
+            if (write && prefix) prefix[i] = s;
+        }
+        return s;
+    };
+
+    uint32_t t0 = 0u;      // anchor: chunks < t0 are proven ...
+    double s0 = 0.0;       // ... and s0 is the exact incoming value of chunk t0
+    bool proven = false;
+    for (int rnd = 0; rnd < FOLD_MAX_ROUNDS && !proven; ++rnd) {
+        info->rounds = (uint32_t)rnd + 1u;
+        // ---- 1. re-associated prefix behind the anchor
+        double cta_sum;
+        const double offset = block_excl_scan_f64(gt >= t0 ? part : 0.0, sh.warp_f64, &cta_sum);
+        if (tid < W_CLUSTER) cluster.map_shared_rank(&sh.cta_part[0], tid)[crank] = cta_sum;
+        if (tid == 0) { sh.bad = 0xffffffffu; sh.overflow = 0u; }
+        cluster.sync();
+        double a_in = s0;
+        for (uint32_t r = 0; r < crank; ++r) a_in = __dadd_rn(a_in, sh.cta_part[r]);
+        a_in = __dadd_rn(a_in, offset);
+        const double a_out = __dadd_rn(a_in, part);
+        // ---- 2. this chunk's transducer in the guessed binade
+        FoldTd td = fold_identity();
+        if (gt >= t0 && lo < hi && !all_zero) {        // (adding zeros changes nothing, whatever the binade)
+            bool head = true;
+            if (a_in > 0.0 && a_out < __longlong_as_double(0x7ff0000000000000ll)) {
+                bool zone_in, zone_out;
+                const int e = fold_guess_binade(a_in, s0, &zone_in);
+                const int e_out = fold_guess_binade(a_out, s0, &zone_out);
+                // regular: assumed to stay inside binade e. A chunk that enters an edge zone from outside is a head.
+                if (e == e_out && (zone_in || !zone_out) && e >= -960 && e <= 1000) {
+                    const double x0 = f64_pow2(e), x1 = __dadd_rn(x0, f64_pow2(e - 52));
+                    double r0 = x0, r1 = x1;
+                    for (uint32_t i = lo; i < hi; ++i) {
+                        const double x = load(i);
+                        r0 = __dadd_rn(r0, x); r1 = __dadd_rn(r1, x);
+                    }
+                    if (r1 <= __dmul_rn(2.0, x0)) {
+                        td.d0 = __dsub_rn(r0, x0); td.d1 = __dsub_rn(r1, x1);
+                        td.qc = (uint32_t)(f64_bits(r0) & 1ll) | ((uint32_t)((f64_bits(r1) & 1ll) ^ 1ll) << 1);
+                        head = false;
+                    }
+                }
+            }
+            if (head) td.qc = 1u << 2;
+        }
+        // ---- 3. scan; every head leaves a record in every CTA of the cluster
+        FoldTd cta_total;
+        const FoldTd excl = block_excl_scan_td(td, sh.warp_td, &cta_total);
+        if ((td.qc >> 2) != 0u) {
+            const uint32_t k = excl.qc >> 2;
+            if (k >= FOLD_HEADS_PER_CTA) sh.overflow = 1u;
+            else {
+                FoldRec rec;
+                rec.d0 = excl.d0; rec.d1 = excl.d1; rec.q_prev = (excl.qc & 3u) | (k ? 4u : 0u); rec.chunk = gt;
+                for (uint32_t r = 0; r < W_CLUSTER; ++r) cluster.map_shared_rank(&sh.rec[0][0], r)[crank * FOLD_HEADS_PER_CTA + k] = rec;
+            }
+        }
+        __syncthreads();
+        if (tid < W_CLUSTER) {
+            cluster.map_shared_rank(&sh.cta_tot[0], tid)[crank] = cta_total;
+            cluster.map_shared_rank(&sh.cta_overflow[0], tid)[crank] = sh.overflow;
+        }
+        cluster.sync();
+        uint32_t overflow = 0u;
+#pragma unroll
+        for (int r = 0; r < W_CLUSTER; ++r) overflow |= sh.cta_overflow[r];
+        if (overflow) break;                           // cluster-uniform
+        // ---- 4. the chain over the heads (same computation in every CTA: no further exchange needed)
+        if (tid == 0) {
+            FoldTd run = fold_identity();
+            for (int r = 0; r < W_CLUSTER; ++r) { sh.cta_excl[r] = run; run = fold_compose(run, sh.cta_tot[r]); }
+            sh.cta_excl[W_CLUSTER] = run;
+        }
+        __syncthreads();
+        const uint32_t H = sh.cta_excl[W_CLUSTER].qc >> 2;
+        if (rnd == 0) info->heads = H;
+        for (uint32_t g = tid; g < H; g += W_THREADS) {
+            uint32_t c = 0u;
+            while (c + 1u < W_CLUSTER && (sh.cta_excl[c + 1u].qc >> 2) <= g) c++;
+            sh.head_chunk[g] = sh.rec[c][g - (sh.cta_excl[c].qc >> 2)].chunk;
+        }
+        __syncthreads();
+        const bool staged = H * L <= FOLD_STAGE;
+        if (staged) {
+            for (uint32_t j = tid; j < H * L; j += W_THREADS) {
+                const uint32_t i = sh.head_chunk[j / L] * L + j % L;
+                sh.vals[j] = i < n ? load(i) : 0.0;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t g = 0u;
+            for (uint32_t c = 0; c < W_CLUSTER; ++c) {
+                const uint32_t nc = sh.cta_tot[c].qc >> 2;
+                for (uint32_t k = 0; k < nc; ++k, ++g) {
+                    const FoldRec rec = sh.rec[c][k];
+                    FoldTd tail; tail.d0 = rec.d0; tail.d1 = rec.d1; tail.qc = rec.q_prev & 3u;
+                    if ((rec.q_prev & 4u) == 0u) tail = fold_compose(sh.cta_excl[c], tail);
+                    double s = fold_apply(tail, g ? sh.head_out[g - 1u] : s0);
+                    const uint32_t i0 = rec.chunk * L, i1 = min(n, i0 + L);
+                    for (uint32_t i = i0; i < i1; ++i) {
+                        const double x = staged ? sh.vals[g * L + (i - i0)] : load(i);
+                        s = (i == 0u && first_is_assignment) ? x : __dadd_rn(s, x);
+                    }
+                    sh.head_out[g] = s;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 5. every chunk: incoming value through the scan, real fold, comparison with the successor
+        auto incoming = [&](const FoldTd& p) { return fold_apply(p, (p.qc >> 2) ? sh.head_out[(p.qc >> 2) - 1u] : s0); };
+        const double s_in = incoming(fold_compose(sh.cta_excl[crank], excl));
+        if (lane == 0) sh.warp_first[wid] = s_in;
+        if (tid == 0) sh.warp_first[32] = incoming(sh.cta_excl[crank + 1u]);   // first chunk of the next CTA
+        __syncthreads();
+        double next_in = __shfl_down_sync(0xffffffffu, s_in, 1);
+        if (lane == 31u) next_in = sh.warp_first[wid + 1u];
+        if (gt >= t0 && gt <= last) {
+            const double s_out = fold_chunk(s_in, true);
+            sout[gt] = s_out;
+            if (gt < last && f64_bits(s_out) != f64_bits(next_in)) atomicMin(&sh.bad, gt + 1u);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid < W_CLUSTER) cluster.map_shared_rank(&sh.cta_bad[0], tid)[crank] = sh.bad;
+        cluster.sync();
+        uint32_t bad = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < W_CLUSTER; ++r) bad = min(bad, sh.cta_bad[r]);
+        if (bad == 0xffffffffu) { proven = true; break; }
+        t0 = bad;
+        s0 = __ldcg(&sout[bad - 1u]);                  // exact: every boundary in front of it matched
+        if (!(s0 < __longlong_as_double(0x7ff0000000000000ll))) break;   // NaN / inf: sequential
+    }
+    if (proven) return __ldcg(&sout[last]);
+    // ---- sequential fallback (NaN / inf weights, adversarial inputs): the reference's loop as it stands
+    info->fallback = 1u;
+    if (tid == 0) {
+        double s = 0.0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const double x = load(i);
+            s = (i == 0u && first_is_assignment) ? x : __dadd_rn(s, x);
+            if (prefix && crank == 0u) prefix[i] = s;
+        }
+        sh.fallback_total = s;
+    }
+    __syncthreads();
+    return sh.fallback_total;
+}
 
 // normalize_weights (particle.rs:49-56), the argmax of particle.rs:40-46 and the running sum of
-// particle.rs:85-91 over the WHOLE population, on one thread-block cluster: 8 CTAs x 1024
-// threads, each thread folds a contiguous chunk left to right, chunk sums are combined by a fixed
-// shuffle tree inside the CTA and the 8 CTA totals are exchanged through distributed shared
-// memory. The combination order depends only on N: bit-identical on every GPU and every run.
+// particle.rs:85-91 over the WHOLE population, on one thread-block cluster: 8 CTAs x 1024 threads,
+// each thread owns a contiguous chunk. Both sums are the reference's strict left folds
+// (exact_left_fold); every GPU computes the same bits.
 __global__ void __cluster_dims__(W_CLUSTER, 1, 1) __launch_bounds__(W_THREADS)
 k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __restrict__ w_norm,
-          double* __restrict__ cum, StepCounters* counters) {
+          double* __restrict__ cum, double* __restrict__ fold_scratch, StepCounters* counters) {
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t crank = cluster.block_rank();
-    __shared__ double s_warp[33];
-    __shared__ double s_tot[3][W_CLUSTER];          // CTA totals (raw, normalised, squared), filled by the peers
+    __shared__ FoldShared sh;
+    __shared__ double s_sq[W_CLUSTER];              // per-CTA sums of squared normalised weights (read by CTA 0)
     __shared__ long long s_key[32];
     __shared__ uint32_t s_arg[32];
     __shared__ long long s_ckey[W_CLUSTER];         // per-CTA argmax candidates (read by CTA 0)
     __shared__ uint32_t s_carg[W_CLUSTER];
     cluster.sync();   // every CTA of the cluster is running before its shared memory is written remotely
     const uint32_t gt = crank * W_THREADS + threadIdx.x;
-    const uint32_t chunk = (n + W_CLUSTER * W_THREADS - 1) / (W_CLUSTER * W_THREADS);
+    const uint32_t chunk = (n + W_CHUNKS - 1) / W_CHUNKS;
     const uint32_t lo = min(n, gt * chunk), hi = min(n, lo + chunk);
 
     if (gt == 0) {   // per-step counters start from zero
@@ -36,35 +342,26 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         counters->n_mat = 0ull; counters->n_mat_leaders = 0ull; counters->ray_cell_steps = 0ull;
     }
 
-    // pass 1: sum of the raw weights
-    double part = 0.0;
-    for (uint32_t i = lo; i < hi; ++i) part = __dadd_rn(part, results[i].weight);
-    double cta_sum;
-    block_excl_scan_f64(part, s_warp, &cta_sum);
-    if (threadIdx.x < W_CLUSTER) cluster.map_shared_rank(&s_tot[0][0], threadIdx.x)[crank] = cta_sum;
-    cluster.sync();
-    double sum = 0.0;
-#pragma unroll
-    for (int r = 0; r < W_CLUSTER; ++r) sum = __dadd_rn(sum, s_tot[0][r]);
+    // pass 1: sum of the raw weights, `self.weights.iter().sum()` (particle.rs:50)
+    FoldInfo info_sum, info_cum;
+    const double sum = exact_left_fold(cluster, sh, n, [&](uint32_t i) { return results[i].weight; }, false, nullptr,
+                                       fold_scratch, &info_sum);
 
-    // pass 2: normalise, argmax candidate, chunk sums of the normalised weights
-    double npart = 0.0, sqpart = 0.0;
+    // pass 2: normalise, argmax candidate, sum of squares
+    double sqpart = 0.0;
     long long best_key = (long long)0x8000000000000000ull;
     uint32_t best_i = 0;
     bool have = false;
     for (uint32_t i = lo; i < hi; ++i) {
         const double w = __ddiv_rn(results[i].weight, sum);
         w_norm[i] = w;
-        npart = __dadd_rn(npart, w);
         sqpart = __dadd_rn(sqpart, __dmul_rn(w, w));
         const long long k = total_order_key(w);
         if (!have || k >= best_key) { best_key = k; best_i = i; have = true; }  // last max wins
     }
-    double cta_n, cta_sq;
-    block_excl_scan_f64(sqpart, s_warp, &cta_sq);
-    const double offset = block_excl_scan_f64(npart, s_warp, &cta_n);
-    if (threadIdx.x < W_CLUSTER) cluster.map_shared_rank(&s_tot[1][0], threadIdx.x)[crank] = cta_n;
-    if (threadIdx.x == 0) cluster.map_shared_rank(&s_tot[2][0], 0)[crank] = cta_sq;
+    double cta_sq;
+    block_excl_scan_f64(sqpart, sh.warp_f64, &cta_sq);
+    if (threadIdx.x == 0) cluster.map_shared_rank(&s_sq[0], 0)[crank] = cta_sq;
 
     // argmax by f64::total_cmp, ties -> highest index (Iterator::max_by returns the last maximum)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -87,17 +384,12 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         cluster.map_shared_rank(&s_ckey[0], 0)[crank] = bk;
         cluster.map_shared_rank(&s_carg[0], 0)[crank] = bi;
     }
-    cluster.sync();
+    __threadfence();   // w_norm is read across CTAs by the fold below (ordered by its cluster barriers)
 
-    // running sum of the normalised weights (the `c += weight[i]` of particle.rs:85-91)
-    double cta_off = 0.0;
-    for (uint32_t r = 0; r < crank; ++r) cta_off = __dadd_rn(cta_off, s_tot[1][r]);
-    double c = __dadd_rn(cta_off, offset);
-    for (uint32_t i = lo; i < hi; ++i) {
-        c = __dadd_rn(c, w_norm[i]);
-        cum[i] = c;
-    }
-    if (gt == 0) {
+    // pass 3: running sum of the normalised weights, `c = weights[0]; ... c += weights[i]` (particle.rs:85-93)
+    exact_left_fold(cluster, sh, n, [&](uint32_t i) { return __ldcg(&w_norm[i]); }, true, cum, fold_scratch, &info_cum);
+
+    if (gt == 0) {   // (the fold's cluster barriers ordered the peers' candidates before this point)
         long long bk = 0; uint32_t bi = 0; bool h = false;
         for (int r = 0; r < W_CLUSTER; ++r) {
             if (s_carg[r] == 0xffffffffu) continue;
@@ -107,15 +399,19 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         counters->sum = sum;
         // number_of_effective_particles (particle.rs:59-65) of the normalised weights, before resampling
         double sq = 0.0;
-        for (int r = 0; r < W_CLUSTER; ++r) sq = __dadd_rn(sq, s_tot[2][r]);
+        for (int r = 0; r < W_CLUSTER; ++r) sq = __dadd_rn(sq, s_sq[r]);
         counters->n_eff = __ddiv_rn(1.0, sq);
+        counters->fold_rounds = (unsigned long long)max(info_sum.rounds, info_cum.rounds);
+        counters->fold_heads = (unsigned long long)max(info_sum.heads, info_cum.heads);
+        counters->fold_fallback = (unsigned long long)(info_sum.fallback | (info_cum.fallback << 1));
     }
 }
 
 void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
-                    double* cum, StepCounters* counters) {
-    k_weights<<<W_CLUSTER, W_THREADS, 0, stream>>>(results, n_total, w_norm, cum, counters);
+                    double* cum, double* fold_scratch, StepCounters* counters) {
+    k_weights<<<W_CLUSTER, W_THREADS, 0, stream>>>(results, n_total, w_norm, cum, fold_scratch, counters);
 }
+size_t weights_scratch_doubles() { return W_CHUNKS; }
 
 // =============================================================================== k_resample_indices
 

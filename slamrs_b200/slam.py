@@ -410,3 +410,20 @@ def debug_stream(seed, step, first, count, device=0):
     z = np.zeros(2 * count, np.float64); u = np.zeros(1, np.float64)
     _lib.check(_lib.load().slamrs_gpu_debug_stream(device, seed, step, first, count, _ptr(z), _ptr(u)))
     return z, float(u[0])
+
+
+def debug_resample(raw_weights, u01: float, device=0, timing=False):
+    """normalize_weights + argmax + resample indices on the device for caller-supplied raw weights
+    (the step's own k_weights / k_resample_indices). Returns a dict: idx, max_particle, norm, cum,
+    clamped, fold_rounds, fold_heads, fold_fallback (+ us = (k_weights, k_resample_indices) with timing)."""
+    w = np.ascontiguousarray(raw_weights, np.float64).reshape(-1)
+    n = w.size
+    idx = np.zeros(n, np.uint32); norm = np.zeros(n, np.float64); cum = np.zeros(n, np.float64)
+    info = np.zeros(4, np.uint64); us = np.zeros(2, np.float32); mp = C.c_uint64(0)
+    _lib.check(_lib.load().slamrs_gpu_debug_resample(device, _ptr(w), n, float(u01), _ptr(idx), C.byref(mp), _ptr(norm),
+                                                     _ptr(cum), _ptr(info), _ptr(us) if timing else None))
+    out = dict(idx=idx, max_particle=int(mp.value), norm=norm, cum=cum, clamped=int(info[0]), fold_rounds=int(info[1]),
+               fold_heads=int(info[2]), fold_fallback=int(info[3]))
+    if timing:
+        out["us"] = (float(us[0]), float(us[1]))
+    return out
