@@ -30,7 +30,7 @@ import struct
 
 import numpy as np
 
-HEADS_PER_CTA = 48     # per 1024-thread CTA (the records travel through distributed shared memory)
+HEADS_PER_CTA = 32     # per 1024-thread CTA (the records travel through distributed shared memory)
 CTA_THREADS = 1024
 MARGIN_BITS = 40       # "near a binade edge": within this relative distance (the sequential fold may differ
                        # from the re-associated prefix by a few thousand ulps at most for 2^18 elements)

@@ -51,6 +51,9 @@ def lib():
     L.so_inverse_sensor_model.restype = C.c_int; L.so_inverse_sensor_model.argtypes = [f, f, C.c_int, f]
     L.so_grid_cells.restype = u64; L.so_grid_cells.argtypes = [f, f]
     L.so_create.restype = vp; L.so_create.argtypes = [f, f, f, f, f, u64, C.c_int]
+    L.so_create_ex.restype = vp; L.so_create_ex.argtypes = [f, f, f, f, f, u64, C.c_int, C.c_int]
+    L.so_set_weight_override.restype = None; L.so_set_weight_override.argtypes = [vp, vp]
+    L.so_get_own_raw.restype = None; L.so_get_own_raw.argtypes = [vp, vp]
     L.so_destroy.restype = None; L.so_destroy.argtypes = [vp]
     L.so_set_threads.restype = None; L.so_set_threads.argtypes = [vp, C.c_int]
     L.so_set_dead_likelihood.restype = None; L.so_set_dead_likelihood.argtypes = [vp, C.c_int]
@@ -183,8 +186,12 @@ def sim_motion(pose, sl, sr, wheel_base):
 class OracleSlam:
     """GridMapSlam (slam.rs:13-97) restated on the CPU with externalised random draws."""
 
-    def __init__(self, position, width, height, resolution, n_particles, track_counts=True):
-        self._h = lib().so_create(position[0], position[1], width, height, resolution, n_particles, int(track_counts))
+    def __init__(self, position, width, height, resolution, n_particles, track_counts=True, sparse=False):
+        """sparse: tile storage with copy-on-write clones (same arithmetic; for populations whose dense f64
+        grids would not fit in host memory)."""
+        self._h = lib().so_create_ex(position[0], position[1], width, height, resolution, n_particles, int(track_counts),
+                                     int(sparse))
+        self._override = None
         if not self._h:
             raise MemoryError("oracle allocation failed")
         self.n = int(lib().so_n(self._h))
@@ -202,6 +209,15 @@ class OracleSlam:
     def set_threads(self, t): lib().so_set_threads(self._h, t)
     def set_dead_likelihood(self, on): lib().so_set_dead_likelihood(self._h, int(on))
     def set_trace(self, particle, cap): lib().so_set_trace(self._h, particle, cap)
+
+    def set_weight_override(self, raw):
+        """The next update resamples on these raw weights (see so_set_weight_override in slam_oracle.c)."""
+        self._override = np.ascontiguousarray(raw, np.float64).copy()
+        assert self._override.size == self.n
+        lib().so_set_weight_override(self._h, _p(self._override))
+
+    def own_raw_weights(self):
+        out = np.zeros(self.n, np.float64); lib().so_get_own_raw(self._h, _p(out)); return out
 
     def update(self, angle, dist, valid, dl, dr, wheel, z, u01) -> int:
         angle = np.ascontiguousarray(angle, np.float64); dist = np.ascontiguousarray(dist, np.float64)

@@ -195,12 +195,29 @@ int so_inverse_sensor_model(float distance, float measured_distance, int was_hit
     return 2;
 }
 
+/* Sparse storage (tests at BASELINE.json's full populations only; so_create_ex(..., sparse = 1)): the grid
+ * is cut into SO_TILE x SO_TILE tiles that exist only once a cell in them has been written, and
+ * `clone()` shares tiles by reference count until one side writes (copy on write). Cell values, the
+ * order of the additions and every index computation are the dense path's; only where a cell lives
+ * changes. 8,192 particles with 1024^2 f64 grids need 64 GiB dense (twice that during resample) and a
+ * few GiB this way. The dense layout stays the default and is what the CPU baseline times. */
+#define SO_TILE 32
+struct so_tile {
+    int refs;
+    double odds[SO_TILE * SO_TILE];
+    uint16_t n_free[SO_TILE * SO_TILE];
+    uint16_t n_occ[SO_TILE * SO_TILE];
+};
+
 struct so_map {
     float pos_x, pos_y, res;
     uint64_t gw, gh;
     double* odds;      /* gw*gh f64 log-odds, index = row*gh + column (map.rs:201-204) */
     uint16_t* n_free;  /* optional exact counters for integer parity checks */
     uint16_t* n_occ;
+    struct so_tile** tiles; /* sparse storage: tiles_x * tiles_y pointers, NULL = every cell still at the prior */
+    uint64_t tiles_x, tiles_y;
+    double prior;
 };
 
 struct so_slam {
@@ -214,6 +231,9 @@ struct so_slam {
     uint64_t* last_idx;
     uint64_t max_particle;
     int track_counts;
+    int sparse;            /* tile storage with copy-on-write clones (so_create_ex) */
+    const double* weight_override; /* next update resamples on these raw weights (so_set_weight_override) */
+    double* own_raw;       /* the raw weights this oracle computed in the last update */
     int run_dead_likelihood;
     int clamped; /* resample index ran past N-1 (reference would panic) */
     int threads;
@@ -225,6 +245,37 @@ struct so_slam {
 };
 
 static inline size_t cell_index(const struct so_map* m, uint64_t column, uint64_t row) { return row * m->gh + column; }
+
+/* sparse storage: tile of a cell and the cell's place inside it */
+static inline size_t tile_of(const struct so_map* m, uint64_t column, uint64_t row) { return (row / SO_TILE) * m->tiles_x + column / SO_TILE; }
+static inline size_t in_tile(uint64_t column, uint64_t row) { return (row % SO_TILE) * SO_TILE + column % SO_TILE; }
+static inline double map_read_odds(const struct so_map* m, uint64_t column, uint64_t row) {
+    if (!m->tiles) return m->odds[cell_index(m, column, row)];
+    const struct so_tile* t = m->tiles[tile_of(m, column, row)];
+    return t ? t->odds[in_tile(column, row)] : m->prior;
+}
+static void tile_release(struct so_tile* t) {
+    if (t && __atomic_sub_fetch(&t->refs, 1, __ATOMIC_ACQ_REL) == 0) free(t);
+}
+/* the tile of a cell, private to this map and ready to be written */
+static struct so_tile* map_write_tile(struct so_map* m, uint64_t column, uint64_t row) {
+    struct so_tile** slot = &m->tiles[tile_of(m, column, row)];
+    struct so_tile* t = *slot;
+    if (t && __atomic_load_n(&t->refs, __ATOMIC_ACQUIRE) == 1) return t;
+    struct so_tile* fresh = (struct so_tile*)malloc(sizeof(struct so_tile));
+    if (!fresh) abort();
+    if (t) {
+        memcpy(fresh, t, sizeof(*fresh));       /* copy first, release after: the last holder frees */
+    } else {
+        for (int c = 0; c < SO_TILE * SO_TILE; ++c) fresh->odds[c] = m->prior;
+        memset(fresh->n_free, 0, sizeof(fresh->n_free));
+        memset(fresh->n_occ, 0, sizeof(fresh->n_occ));
+    }
+    fresh->refs = 1;
+    *slot = fresh;
+    tile_release(t);
+    return fresh;
+}
 
 /* Map::world_to_grid, map.rs:60-62 */
 static inline void world_to_grid(const struct so_map* m, float wx, float wy, float* gx, float* gy) {
@@ -249,7 +300,7 @@ static double map_log_probability_of(const struct so_map* m, const double* angle
         float gx, gy;
         world_to_grid(m, ex, ey, &gx, &gy);
         if (is_valid(m, gx, gy)) {
-            double odds = m->odds[cell_index(m, f32_as_usize(gx), f32_as_usize(gy))];
+            double odds = map_read_odds(m, f32_as_usize(gx), f32_as_usize(gy));
             double p = so_log_odds_probability(odds);
             if (p == 0.5) {
                 product += log(1.0 / SENSOR_MAXDIST);
@@ -280,12 +331,20 @@ static void integrate_visit(int64_t x, int64_t y, void* c) {
     acc = acc + dyy * dyy;
     float distance = sqrtf(acc);
     int kind = so_inverse_sensor_model(distance, ic->measured, ic->was_hit, 2.0f);
-    size_t idx = cell_index(m, (uint64_t)x, (uint64_t)y);
     double inc = kind == 1 ? ic->s->l_free : (kind == 2 ? ic->s->l_occ : ic->s->l_prior);
-    m->odds[idx] += inc;
-    if (m->n_free) {
-        if (kind == 1 && m->n_free[idx] != UINT16_MAX) m->n_free[idx]++;
-        if (kind == 2 && m->n_occ[idx] != UINT16_MAX) m->n_occ[idx]++;
+    if (m->tiles) {
+        struct so_tile* t = map_write_tile(m, (uint64_t)x, (uint64_t)y);
+        size_t idx = in_tile((uint64_t)x, (uint64_t)y);
+        t->odds[idx] += inc;
+        if (kind == 1 && t->n_free[idx] != UINT16_MAX) t->n_free[idx]++;
+        if (kind == 2 && t->n_occ[idx] != UINT16_MAX) t->n_occ[idx]++;
+    } else {
+        size_t idx = cell_index(m, (uint64_t)x, (uint64_t)y);
+        m->odds[idx] += inc;
+        if (m->n_free) {
+            if (kind == 1 && m->n_free[idx] != UINT16_MAX) m->n_free[idx]++;
+            if (kind == 2 && m->n_occ[idx] != UINT16_MAX) m->n_occ[idx]++;
+        }
     }
     if (ic->tracing) {
         struct so_slam* s = ic->s;
@@ -317,6 +376,13 @@ static void map_integrate(struct so_slam* s, struct so_map* m, const double* ang
 /* ---------------------------------------------------------------- lifecycle */
 static int map_alloc(struct so_map* m, const struct so_slam* s) {
     m->pos_x = s->pos_x; m->pos_y = s->pos_y; m->res = s->res; m->gw = s->gw; m->gh = s->gh;
+    m->tiles = NULL; m->prior = s->l_prior;
+    if (s->sparse) {
+        m->odds = NULL; m->n_free = m->n_occ = NULL;
+        m->tiles_x = (s->gw + SO_TILE - 1) / SO_TILE; m->tiles_y = (s->gh + SO_TILE - 1) / SO_TILE;
+        m->tiles = (struct so_tile**)calloc((size_t)(m->tiles_x * m->tiles_y), sizeof(struct so_tile*));
+        return m->tiles ? 0 : -1;
+    }
     size_t cells = (size_t)(s->gw * s->gh);
     m->odds = (double*)malloc(cells * sizeof(double));
     m->n_free = m->n_occ = NULL;
@@ -329,10 +395,23 @@ static int map_alloc(struct so_map* m, const struct so_slam* s) {
     return 0;
 }
 static void map_free(struct so_map* m) {
+    if (m->tiles) {
+        for (size_t t = 0; t < (size_t)(m->tiles_x * m->tiles_y); ++t) tile_release(m->tiles[t]);
+        free(m->tiles);
+        m->tiles = NULL;
+    }
     free(m->odds); free(m->n_free); free(m->n_occ);
     m->odds = NULL; m->n_free = m->n_occ = NULL;
 }
 static void map_copy(struct so_map* dst, const struct so_map* src) {
+    if (src->tiles) {   /* clone(): share every tile until one side writes it */
+        for (size_t t = 0; t < (size_t)(src->tiles_x * src->tiles_y); ++t) {
+            struct so_tile* tile = src->tiles[t];
+            if (tile) __atomic_add_fetch(&tile->refs, 1, __ATOMIC_ACQ_REL);
+            dst->tiles[t] = tile;
+        }
+        return;
+    }
     size_t cells = (size_t)(src->gw * src->gh);
     memcpy(dst->odds, src->odds, cells * sizeof(double));
     if (src->n_free) {
@@ -347,9 +426,15 @@ uint64_t so_grid_cells(float extent, float resolution) { return f32_as_usize(cei
 /* GridMapSlam::new, slam.rs:28-43 (+ Map::new map.rs:26-48, ParticleFilter::new particle.rs:15-28) */
 struct so_slam* so_create(float pos_x, float pos_y, float width, float height, float resolution,
                           uint64_t n_particles, int track_counts) {
+    return so_create_ex(pos_x, pos_y, width, height, resolution, n_particles, track_counts, 0);
+}
+
+struct so_slam* so_create_ex(float pos_x, float pos_y, float width, float height, float resolution,
+                             uint64_t n_particles, int track_counts, int sparse) {
     if (n_particles == 0) return NULL; /* reference asserts */
     struct so_slam* s = (struct so_slam*)calloc(1, sizeof(*s));
     if (!s) return NULL;
+    s->sparse = sparse;
     s->n = n_particles;
     s->pos_x = pos_x; s->pos_y = pos_y; s->res = resolution;
     s->gw = so_grid_cells(width, resolution);
@@ -365,12 +450,13 @@ struct so_slam* so_create(float pos_x, float pos_y, float width, float height, f
     s->weight = (double*)malloc(n_particles * sizeof(double));
     s->raw_weight = (double*)malloc(n_particles * sizeof(double));
     s->last_idx = (uint64_t*)calloc(n_particles, sizeof(uint64_t));
-    if (!s->pose || !s->map || !s->weight || !s->raw_weight || !s->last_idx) { so_destroy(s); return NULL; }
+    s->own_raw = (double*)calloc(n_particles, sizeof(double));
+    if (!s->pose || !s->map || !s->weight || !s->raw_weight || !s->last_idx || !s->own_raw) { so_destroy(s); return NULL; }
     size_t cells = (size_t)(s->gw * s->gh);
     double init = so_prob_log_odds(0.5);
     for (uint64_t i = 0; i < n_particles; ++i) {
         if (map_alloc(&s->map[i], s)) { so_destroy(s); return NULL; }
-        for (size_t c = 0; c < cells; ++c) s->map[i].odds[c] = init;
+        if (!s->sparse) for (size_t c = 0; c < cells; ++c) s->map[i].odds[c] = init;
         s->weight[i] = 1.0 / (double)n_particles;
         s->raw_weight[i] = s->weight[i];
         s->last_idx[i] = i;
@@ -382,7 +468,7 @@ struct so_slam* so_create(float pos_x, float pos_y, float width, float height, f
 void so_destroy(struct so_slam* s) {
     if (!s) return;
     if (s->map) for (uint64_t i = 0; i < s->n; ++i) map_free(&s->map[i]);
-    free(s->map); free(s->pose); free(s->weight); free(s->raw_weight); free(s->last_idx); free(s->trace);
+    free(s->map); free(s->pose); free(s->weight); free(s->raw_weight); free(s->last_idx); free(s->trace); free(s->own_raw);
     free(s);
 }
 
@@ -405,7 +491,7 @@ static void particle_step(struct so_slam* s, uint64_t p, const double* angle, co
     so_pose initial = s->pose[p];
     so_pose np = so_odometry_sample(od, initial, z[2 * p], z[2 * p + 1]);
     struct so_map* m = &s->map[p];
-    if (s->run_dead_likelihood) {
+    if (s->run_dead_likelihood && !s->sparse) {
         /* slam.rs:58 `let likelihood = map.likelihood();` -- result unused in the reference */
         size_t cells = (size_t)(m->gw * m->gh);
         double* tmp = (double*)malloc(cells * sizeof(double));
@@ -481,6 +567,11 @@ int so_update(struct so_slam* s, const double* angle, const double* dist, const 
 #pragma omp parallel for schedule(dynamic, 1) num_threads(s->threads) if (s->threads > 1)
     for (int64_t p = 0; p < n; ++p) particle_step(s, (uint64_t)p, angle, dist, valid, nb, od, z);
 
+    memcpy(s->own_raw, s->raw_weight, s->n * sizeof(double));
+    if (s->weight_override) {   /* resample on the weights the device computed (see so_set_weight_override) */
+        memcpy(s->raw_weight, s->weight_override, s->n * sizeof(double));
+        s->weight_override = NULL;
+    }
     /* normalize_weights, argmax, resample indices: particle.rs:40-56, 78-101 */
     s->clamped = so_resample_fold(s->raw_weight, s->n, u01, s->weight, NULL, s->last_idx, &s->max_particle);
     /* new generation: clone(old[i]) for every slot (deep copy of Pose + Map) */
@@ -525,9 +616,33 @@ double so_number_of_effective_particles(const struct so_slam* s) {
 }
 void so_get_indices(const struct so_slam* s, uint64_t* idx) { memcpy(idx, s->last_idx, s->n * sizeof(uint64_t)); }
 void so_get_odds(const struct so_slam* s, uint64_t particle, double* out) {
-    memcpy(out, s->map[particle].odds, (size_t)(s->gw * s->gh) * sizeof(double));
+    const struct so_map* m = &s->map[particle];
+    if (m->tiles) {
+        for (uint64_t row = 0; row < s->gh; ++row)
+            for (uint64_t col = 0; col < s->gw; ++col) out[cell_index(m, col, row)] = map_read_odds(m, col, row);
+        return;
+    }
+    memcpy(out, m->odds, (size_t)(s->gw * s->gh) * sizeof(double));
 }
+/* Resample the NEXT update on these raw weights instead of the oracle's own (which stay readable through
+ * so_get_own_raw). The device's exp/log differ from glibc's in the last bit, so its raw weights agree
+ * with the oracle's to ~1e-12 relative, not bit for bit; with tens of thousands of particles a resampling
+ * threshold lands that close to a prefix sum once in a few hundred steps and the two populations would
+ * part ways. Lockstep tests at those sizes check the weights against the tolerance, then let both sides
+ * resample on identical numbers -- where the index vector must match bit for bit. */
+void so_set_weight_override(struct so_slam* s, const double* raw) { s->weight_override = raw; }
+void so_get_own_raw(const struct so_slam* s, double* out) { memcpy(out, s->own_raw, s->n * sizeof(double)); }
 int so_get_counts(const struct so_slam* s, uint64_t particle, uint16_t* n_free, uint16_t* n_occ) {
+    if (s->sparse) {
+        const struct so_map* m = &s->map[particle];
+        for (uint64_t row = 0; row < s->gh; ++row)
+            for (uint64_t col = 0; col < s->gw; ++col) {
+                const struct so_tile* t = m->tiles[tile_of(m, col, row)];
+                n_free[cell_index(m, col, row)] = t ? t->n_free[in_tile(col, row)] : 0;
+                n_occ[cell_index(m, col, row)] = t ? t->n_occ[in_tile(col, row)] : 0;
+            }
+        return 0;
+    }
     if (!s->track_counts) return -1;
     size_t cells = (size_t)(s->gw * s->gh);
     memcpy(n_free, s->map[particle].n_free, cells * 2);
@@ -540,6 +655,12 @@ so_pose so_estimated_pose(const struct so_slam* s) { return s->pose[s->max_parti
 void so_estimated_likelihood(const struct so_slam* s, double* out) {
     const struct so_map* m = &s->map[s->max_particle];
     size_t cells = (size_t)(s->gw * s->gh);
+    if (m->tiles) {
+        for (uint64_t row = 0; row < s->gh; ++row)
+            for (uint64_t col = 0; col < s->gw; ++col)
+                out[cell_index(m, col, row)] = so_log_odds_probability(map_read_odds(m, col, row));
+        return;
+    }
     for (size_t c = 0; c < cells; ++c) out[c] = so_log_odds_probability(m->odds[c]);
 }
 int64_t so_get_trace(const struct so_slam* s, int32_t* out, int64_t cap) {

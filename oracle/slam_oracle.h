@@ -25,7 +25,11 @@ uint64_t so_grid_cells(float extent, float resolution);
 /* slam.rs */
 struct so_slam* so_create(float pos_x, float pos_y, float width, float height, float resolution,
                           uint64_t n_particles, int track_counts);
+struct so_slam* so_create_ex(float pos_x, float pos_y, float width, float height, float resolution,
+                             uint64_t n_particles, int track_counts, int sparse);
 void so_destroy(struct so_slam* s);
+void so_set_weight_override(struct so_slam* s, const double* raw);
+void so_get_own_raw(const struct so_slam* s, double* out);
 void so_set_threads(struct so_slam* s, int threads);
 void so_set_dead_likelihood(struct so_slam* s, int on);
 void so_set_trace(struct so_slam* s, int64_t particle, int64_t cap);

@@ -78,6 +78,7 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.build() if _build.needs_build() else _build.LIB
+    path = os.environ.get("SLAMRS_GPU_LIB", path)   # tuning variants built by `python slamrs_b200/build.py -D... --out=...`
     L = C.CDLL(path, mode=C.RTLD_GLOBAL)
     vp, u32, u64, f, i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.c_int
     L.slamrs_gpu_grid_cells.restype = i; L.slamrs_gpu_grid_cells.argtypes = [f, f, C.POINTER(u32)]

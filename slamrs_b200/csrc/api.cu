@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
@@ -1296,6 +1297,14 @@ int slamrs_gpu_debug_resample(int device, const double* raw_weights, uint32_t n,
     if (out_norm) DBG_CU(cudaMemcpy(out_norm, wn.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
     if (out_cum) DBG_CU(cudaMemcpy(out_cum, cum.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
     if (out_max_particle) *out_max_particle = c.max_particle;
+    if (out_us && getenv("SLAMRS_FOLD_TRACE_PRINT")) {
+        long long tr[64];
+        if (weights_trace(tr) == 0) {
+            fprintf(stderr, "k_weights clock stamps (cycles from start):");
+            for (int k = 0; k < 44; ++k) fprintf(stderr, " [%d]%lld", k, tr[k] ? tr[k] - tr[0] : -1);
+            fprintf(stderr, "\n");
+        }
+    }
     if (out_info) { out_info[0] = c.clamped; out_info[1] = c.fold_rounds; out_info[2] = c.fold_heads; out_info[3] = c.fold_fallback; }
     return SLAMRS_OK;
 }

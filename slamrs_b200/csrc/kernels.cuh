@@ -135,6 +135,7 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
 void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
                     double* cum, double* fold_scratch, StepCounters* counters);
 size_t weights_scratch_doubles();
+int weights_trace(long long* out64);   // tuning builds (-DSLAMRS_FOLD_TRACE): clock stamps of the last k_weights
 
 void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
                              uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,

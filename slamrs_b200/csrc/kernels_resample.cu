@@ -6,9 +6,7 @@ namespace slamrs {
 
 // =============================================================================== k_weights
 
-constexpr int W_THREADS = 1024;
-constexpr int W_CLUSTER = 8;   // CTAs of the (portable-size) thread-block cluster that shares the reduction
-constexpr uint32_t W_CHUNKS = W_THREADS * W_CLUSTER;
+constexpr int W_CLUSTER = 8;   // largest (portable-size) thread-block cluster that shares the reduction
 
 // ------------------------------------------------------------------------------- the exact left fold
 // The reference adds weights strictly left to right (`iter().sum()`, particle.rs:50; `c += weight[i]`,
@@ -21,7 +19,7 @@ constexpr uint32_t W_CHUNKS = W_THREADS * W_CLUSTER;
 //    elements is therefore a two-state transducer: (d0, d1) = the total increment for an even / odd S at
 //    entry, q = whether each flips the parity. Transducers compose associatively -> prefix scan.
 //  * A chunk in which the sum changes binade is a "head": its output comes from a short sequential
-//    chain over the heads (thread 0 of every CTA, operands staged in shared memory).
+//    chain over the heads (thread 0 of every CTA, operands prepared in shared memory by their owners).
 //  * The binade of each chunk's incoming sum is GUESSED from an ordinary re-associated prefix sum. The
 //    result is PROVED by induction: every thread folds its chunk from its incoming value with real
 //    additions, and the outcome must equal, bit for bit, the incoming value its successor derived
@@ -30,42 +28,56 @@ constexpr uint32_t W_CHUNKS = W_THREADS * W_CLUSTER;
 //    side of a binade edge a sum that creeps along the edge lies -- normalised weights end within a few
 //    ulps of 1.0. After FOLD_MAX_ROUNDS rounds, or with more heads than the tables hold (NaN, inf,
 //    adversarial inputs), thread 0 folds sequentially. Either way the result is the reference's.
-constexpr uint32_t FOLD_HEADS_PER_CTA = 48;
+//
+// Shape (measured, profiles/r2_resample_exact.md): the kernel is bound by instruction issue -- every
+// thread runs ~3,000 instructions of scans and bit tests whatever its chunk length -- so it uses few
+// threads with long chunks: 512 threads x 16 elements per CTA, in registers, and as few CTAs as the
+// population needs (one up to 8,192 particles: no cluster traffic at all).
+constexpr uint32_t FOLD_HEADS_PER_CTA = 32;
 constexpr uint32_t FOLD_HEADS_MAX = FOLD_HEADS_PER_CTA * W_CLUSTER;
-constexpr uint32_t FOLD_STAGE = 2048;     // head operands staged in shared memory for the chain
+constexpr uint32_t FOLD_STAGE = 2048;     // generic path: head operands staged in shared memory for the chain
 constexpr int FOLD_MAX_ROUNDS = 4;
 constexpr int FOLD_MARGIN_BITS = 40;      // "near a binade edge": within 2^-40 relative
+constexpr int FOLD_LREG = 16;             // register path: elements per thread ...
+constexpr int FOLD_THREADS = 512;         // ... and threads per CTA (up to 65,536 particles on 8 CTAs)
+constexpr int FOLD_GENERIC_THREADS = 1024;
+constexpr uint32_t FOLD_MAX_CHUNKS = FOLD_GENERIC_THREADS * W_CLUSTER;
 
 struct FoldTd {       // transducer of a range of chunks; a range that contains a head forgets what precedes its last head
     double d0, d1;
     uint32_t qc;      // bits 0-1: parity flips for even / odd entry, bits 2..: heads in the range
 };
+template <int LREG>
 struct FoldRec {      // one head, as the chain sees it
     double d0, d1;    // transducer of the regular chunks between the previous head of the same CTA (or the CTA's first chunk) and this one
     uint32_t q_prev;  // bits 0-1: q of that transducer, bit 2: an earlier head exists in the same CTA
     uint32_t chunk;
+    double vals[LREG ? LREG : 1];   // the chunk's elements, zero-padded (register path)
 };
+template <int LREG>
 struct FoldShared {
     double warp_f64[33];
     FoldTd warp_td[33];
-    double cta_part[W_CLUSTER];                        // written by the peers (distributed shared memory)
-    FoldTd cta_tot[W_CLUSTER];                         // "
-    FoldRec rec[W_CLUSTER][FOLD_HEADS_PER_CTA];        // "
-    uint32_t cta_bad[W_CLUSTER];                       // "  first unproven chunk seen by each CTA
-    uint32_t cta_overflow[W_CLUSTER];                  // "
-    FoldTd cta_excl[W_CLUSTER + 1];                    // exclusive composition over the CTAs (local copy)
-    double head_out[FOLD_HEADS_MAX];                   // the chain's results
-    uint32_t head_chunk[FOLD_HEADS_MAX];
-    double vals[FOLD_STAGE];
-    double warp_first[33];                             // incoming value of each warp's first chunk
-    uint32_t bad;                                      // this CTA's first unproven chunk
+    double cta_part[W_CLUSTER];                              // written by the peers (distributed shared memory)
+    FoldTd cta_tot[W_CLUSTER];                               // "
+    FoldRec<LREG> rec[W_CLUSTER][FOLD_HEADS_PER_CTA];        // "
+    uint32_t cta_bad[W_CLUSTER];                             // "  first unproven chunk seen by each CTA
+    uint32_t cta_overflow[W_CLUSTER];                        // "
+    double total;                                            // "  the last chunk's outcome
+    FoldTd cta_excl[W_CLUSTER + 1];                          // exclusive composition over the CTAs (local copy)
+    double head_d0[FOLD_HEADS_MAX], head_d1[FOLD_HEADS_MAX]; // per head: the transducer in front of it, ready for the chain
+    uint16_t head_rec[FOLD_HEADS_MAX];                       // per head: c * FOLD_HEADS_PER_CTA + k of its record
+    double head_out[FOLD_HEADS_MAX];                         // the chain's results
+    double vals[LREG ? 1 : FOLD_STAGE];                      // generic path: the heads' elements
+    double warp_first[33];                                   // incoming value of each warp's first chunk
+    uint32_t bad;                                            // this CTA's first unproven chunk
     uint32_t overflow;
-    double fallback_total;
 };
 
 __device__ __forceinline__ long long f64_bits(double x) { return __double_as_longlong(x); }
 __device__ __forceinline__ int f64_exponent(double x) { return (int)((f64_bits(x) >> 52) & 0x7ff) - 1023; }
 __device__ __forceinline__ double f64_pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
+__device__ __forceinline__ bool f64_finite(double x) { return ((f64_bits(x) >> 52) & 0x7ff) != 0x7ff; }
 
 __device__ __forceinline__ FoldTd fold_compose(const FoldTd& a, const FoldTd& b) {
     FoldTd r;
@@ -122,75 +134,76 @@ __device__ __forceinline__ FoldTd block_excl_scan_td(const FoldTd& v, FoldTd* wa
 }
 
 // Binade the running sum is assumed to be in when the re-associated prefix says `a` (> 0, finite). Away
-// from the binade edges: a's own. Within the margin of an edge 2^k the sum may be on either side: the
-// side of the anchor (the last exactly known value) if the anchor lies in the same zone, else the lower
-// one (a sum creeping up to an edge is below it until proven otherwise). *zone = near an edge.
+// from the binade edges: a's own. Within the margin of an edge 2^k (the top FOLD_MARGIN_BITS mantissa bits
+// all 0 or all 1) the sum may be on either side: the side of the anchor (the last exactly known value) if
+// the anchor lies in the same zone, else the lower one (a sum creeping up to an edge is below it until
+// proven otherwise). *zone = near an edge.
 __device__ __forceinline__ int fold_guess_binade(double a, double anchor, bool* zone) {
-    const int e = f64_exponent(a);
-    if (e < -960 || e > 1000) { *zone = false; return e; }   // callers reject these exponents
-    const double x0 = f64_pow2(e);
+    const long long bits = f64_bits(a);
+    const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    const unsigned long long top = ((unsigned long long)bits & 0x000fffffffffffffull) >> (52 - FOLD_MARGIN_BITS);
     int k;
-    if (a < __dadd_rn(x0, f64_pow2(e - FOLD_MARGIN_BITS))) k = e;
-    else if (a > __dsub_rn(__dmul_rn(2.0, x0), f64_pow2(e + 1 - FOLD_MARGIN_BITS))) k = e + 1;
+    if (top == 0ull) k = e;
+    else if (top == (1ull << FOLD_MARGIN_BITS) - 1ull) k = e + 1;
     else { *zone = false; return e; }
     *zone = true;
+    if (k < -960 || k > 1000) return k - 1;           // callers reject these exponents
     const double edge = f64_pow2(k);
     if (anchor > 0.0 && fabs(__dsub_rn(anchor, edge)) <= f64_pow2(k - FOLD_MARGIN_BITS)) return anchor >= edge ? k : k - 1;
     return k - 1;
 }
 
 struct FoldInfo { uint32_t rounds, heads, fallback; };
+// SLAMRS_FOLD_TRACE: thread 0 of CTA 0 leaves clock64 stamps (tuning builds; SLAMRS_FOLD_TRACE_PRINT=1 prints them)
+#ifdef SLAMRS_FOLD_TRACE
+#define FOLD_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<long long*>(g_fold_trace)[k] = clock64(); } while (0)
+__device__ long long g_fold_trace[64];
+#else
+#define FOLD_STAMP(k) do { } while (0)
+#endif
 
-// prefix[i] = the reference's running sum after element i (prefix may be null); returns the total.
-// `load(i)` yields element i; first_is_assignment: the fold starts with s = v[0] (particle.rs:85)
-// instead of 0.0 + v[0] (particle.rs:50). sout: W_CHUNKS doubles of global scratch. Cluster-uniform.
-template <typename Load>
-__device__ double exact_left_fold(cg::cluster_group& cluster, FoldShared& sh, uint32_t n, Load load, bool first_is_assignment,
-                                  double* __restrict__ prefix, double* __restrict__ sout, FoldInfo* info) {
-    const uint32_t crank = cluster.block_rank();
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    const uint32_t gt = crank * W_THREADS + tid;
-    const uint32_t L = (n + W_CHUNKS - 1u) / W_CHUNKS;
-    const uint32_t lo = min(n, gt * L), hi = min(n, lo + L);
+// barrier over the cluster; a single CTA needs no more than its own barrier
+__device__ __forceinline__ void fold_sync(cg::cluster_group& cluster, uint32_t C) {
+    if (C == 1u) __syncthreads(); else cluster.sync();
+}
+
+// One exact left fold over the cluster. The caller supplies this thread's chunk (L elements from index
+// gt * L, `cnt` of them inside the population, through v[] (register path, zero-padded) or get_global(i))
+// and a re-associated estimate (a_in0, a_out0) of the running sum in front of and behind the chunk. On
+// return *s_in / *s_out hold the reference's running sum in front of / behind the chunk, put(j, s) has
+// been called with the running sum after every element, *total is the grand total. Returns false if the
+// fold could not be proven (too many heads, non-finite sums, rounds exhausted): the caller then folds
+// sequentially. Cluster-uniform. scratch: 2 * FOLD_MAX_CHUNKS doubles.
+template <int LREG, typename Put, typename GetGlobal>
+__device__ bool exact_left_fold(cg::cluster_group& cluster, FoldShared<LREG>& sh, uint32_t n, uint32_t L, uint32_t cnt,
+                                bool all_zero, double a_in0, double a_out0, const double (&v)[LREG ? LREG : 1], Put put,
+                                GetGlobal get_global, bool first_is_assignment, double* __restrict__ scratch,
+                                double* s_in_out, double* s_out_out, double* total, FoldInfo* info, int tb = 0) {
+    (void)tb;
+    const uint32_t crank = cluster.block_rank(), C = cluster.num_blocks();
+    const uint32_t T = blockDim.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t gt = crank * T + tid;
+    const uint32_t lo = gt * L;
     const uint32_t last = (n - 1u) / L;               // last non-empty chunk (n >= 1)
+    const bool assign_first = first_is_assignment && gt == 0u;
+    double* __restrict__ sout = scratch;              // per chunk: the outcome of its fold (for the anchor)
+    double* __restrict__ ain = scratch + FOLD_MAX_CHUNKS;   // per chunk: a_in0 (to re-base the estimate on the anchor)
     info->rounds = 0u; info->heads = 0u; info->fallback = 0u;
-
-    double part = 0.0;
-    bool all_zero = true;
-    for (uint32_t i = lo; i < hi; ++i) {
-        const double x = load(i);
-        part = __dadd_rn(part, x);
-        all_zero = all_zero && x == 0.0;
-    }
-    auto fold_chunk = [&](double s, bool write) {
-        for (uint32_t i = lo; i < hi; ++i) {
-            const double x = load(i);
-            s = (i == 0u && first_is_assignment) ? x : __dadd_rn(s, x);
-            if (write && prefix) prefix[i] = s;
-        }
-        return s;
-    };
+    ain[gt] = a_in0;
 
     uint32_t t0 = 0u;      // anchor: chunks < t0 are proven ...
     double s0 = 0.0;       // ... and s0 is the exact incoming value of chunk t0
-    bool proven = false;
-    for (int rnd = 0; rnd < FOLD_MAX_ROUNDS && !proven; ++rnd) {
+    double a_base = 0.0;   // a_in0 of chunk t0
+    for (int rnd = 0; rnd < FOLD_MAX_ROUNDS; ++rnd) {
         info->rounds = (uint32_t)rnd + 1u;
-        // ---- 1. re-associated prefix behind the anchor
-        double cta_sum;
-        const double offset = block_excl_scan_f64(gt >= t0 ? part : 0.0, sh.warp_f64, &cta_sum);
-        if (tid < W_CLUSTER) cluster.map_shared_rank(&sh.cta_part[0], tid)[crank] = cta_sum;
         if (tid == 0) { sh.bad = 0xffffffffu; sh.overflow = 0u; }
-        cluster.sync();
-        double a_in = s0;
-        for (uint32_t r = 0; r < crank; ++r) a_in = __dadd_rn(a_in, sh.cta_part[r]);
-        a_in = __dadd_rn(a_in, offset);
-        const double a_out = __dadd_rn(a_in, part);
-        // ---- 2. this chunk's transducer in the guessed binade
+        const double a_in = rnd ? __dadd_rn(s0, __dsub_rn(a_in0, a_base)) : a_in0;
+        const double a_out = rnd ? __dadd_rn(s0, __dsub_rn(a_out0, a_base)) : a_out0;
+        // ---- 1. this chunk's transducer in the guessed binade
         FoldTd td = fold_identity();
-        if (gt >= t0 && lo < hi && !all_zero) {        // (adding zeros changes nothing, whatever the binade)
+        if (gt >= t0 && cnt != 0u && !all_zero) {        // (adding zeros changes nothing, whatever the binade)
             bool head = true;
-            if (a_in > 0.0 && a_out < __longlong_as_double(0x7ff0000000000000ll)) {
+            if (a_in > 0.0 && f64_finite(a_out)) {
                 bool zone_in, zone_out;
                 const int e = fold_guess_binade(a_in, s0, &zone_in);
                 const int e_out = fold_guess_binade(a_out, s0, &zone_out);
@@ -198,9 +211,11 @@ __device__ double exact_left_fold(cg::cluster_group& cluster, FoldShared& sh, ui
                 if (e == e_out && (zone_in || !zone_out) && e >= -960 && e <= 1000) {
                     const double x0 = f64_pow2(e), x1 = __dadd_rn(x0, f64_pow2(e - 52));
                     double r0 = x0, r1 = x1;
-                    for (uint32_t i = lo; i < hi; ++i) {
-                        const double x = load(i);
-                        r0 = __dadd_rn(r0, x); r1 = __dadd_rn(r1, x);
+                    if (LREG) {
+#pragma unroll
+                        for (int j = 0; j < (LREG ? LREG : 1); ++j) { r0 = __dadd_rn(r0, v[j]); r1 = __dadd_rn(r1, v[j]); }
+                    } else {
+                        for (uint32_t j = 0; j < cnt; ++j) { const double x = get_global(lo + j); r0 = __dadd_rn(r0, x); r1 = __dadd_rn(r1, x); }
                     }
                     if (r1 <= __dmul_rn(2.0, x0)) {
                         td.d0 = __dsub_rn(r0, x0); td.d1 = __dsub_rn(r1, x1);
@@ -211,187 +226,316 @@ __device__ double exact_left_fold(cg::cluster_group& cluster, FoldShared& sh, ui
             }
             if (head) td.qc = 1u << 2;
         }
-        // ---- 3. scan; every head leaves a record in every CTA of the cluster
+        FOLD_STAMP(tb + 0);
+        // ---- 2. scan; every head leaves a record in every CTA of the cluster
         FoldTd cta_total;
         const FoldTd excl = block_excl_scan_td(td, sh.warp_td, &cta_total);
         if ((td.qc >> 2) != 0u) {
             const uint32_t k = excl.qc >> 2;
             if (k >= FOLD_HEADS_PER_CTA) sh.overflow = 1u;
             else {
-                FoldRec rec;
-                rec.d0 = excl.d0; rec.d1 = excl.d1; rec.q_prev = (excl.qc & 3u) | (k ? 4u : 0u); rec.chunk = gt;
-                for (uint32_t r = 0; r < W_CLUSTER; ++r) cluster.map_shared_rank(&sh.rec[0][0], r)[crank * FOLD_HEADS_PER_CTA + k] = rec;
-            }
-        }
-        __syncthreads();
-        if (tid < W_CLUSTER) {
-            cluster.map_shared_rank(&sh.cta_tot[0], tid)[crank] = cta_total;
-            cluster.map_shared_rank(&sh.cta_overflow[0], tid)[crank] = sh.overflow;
-        }
-        cluster.sync();
-        uint32_t overflow = 0u;
+                for (uint32_t r = 0; r < C; ++r) {
+                    FoldRec<LREG>* dst = C == 1u ? &sh.rec[0][k] : cluster.map_shared_rank(&sh.rec[0][0], r) + crank * FOLD_HEADS_PER_CTA + k;
+                    dst->d0 = excl.d0; dst->d1 = excl.d1; dst->q_prev = (excl.qc & 3u) | (k ? 4u : 0u); dst->chunk = gt;
+                    if (LREG) {
 #pragma unroll
-        for (int r = 0; r < W_CLUSTER; ++r) overflow |= sh.cta_overflow[r];
-        if (overflow) break;                           // cluster-uniform
-        // ---- 4. the chain over the heads (same computation in every CTA: no further exchange needed)
-        if (tid == 0) {
-            FoldTd run = fold_identity();
-            for (int r = 0; r < W_CLUSTER; ++r) { sh.cta_excl[r] = run; run = fold_compose(run, sh.cta_tot[r]); }
-            sh.cta_excl[W_CLUSTER] = run;
-        }
-        __syncthreads();
-        const uint32_t H = sh.cta_excl[W_CLUSTER].qc >> 2;
-        if (rnd == 0) info->heads = H;
-        for (uint32_t g = tid; g < H; g += W_THREADS) {
-            uint32_t c = 0u;
-            while (c + 1u < W_CLUSTER && (sh.cta_excl[c + 1u].qc >> 2) <= g) c++;
-            sh.head_chunk[g] = sh.rec[c][g - (sh.cta_excl[c].qc >> 2)].chunk;
-        }
-        __syncthreads();
-        const bool staged = H * L <= FOLD_STAGE;
-        if (staged) {
-            for (uint32_t j = tid; j < H * L; j += W_THREADS) {
-                const uint32_t i = sh.head_chunk[j / L] * L + j % L;
-                sh.vals[j] = i < n ? load(i) : 0.0;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t g = 0u;
-            for (uint32_t c = 0; c < W_CLUSTER; ++c) {
-                const uint32_t nc = sh.cta_tot[c].qc >> 2;
-                for (uint32_t k = 0; k < nc; ++k, ++g) {
-                    const FoldRec rec = sh.rec[c][k];
-                    FoldTd tail; tail.d0 = rec.d0; tail.d1 = rec.d1; tail.qc = rec.q_prev & 3u;
-                    if ((rec.q_prev & 4u) == 0u) tail = fold_compose(sh.cta_excl[c], tail);
-                    double s = fold_apply(tail, g ? sh.head_out[g - 1u] : s0);
-                    const uint32_t i0 = rec.chunk * L, i1 = min(n, i0 + L);
-                    for (uint32_t i = i0; i < i1; ++i) {
-                        const double x = staged ? sh.vals[g * L + (i - i0)] : load(i);
-                        s = (i == 0u && first_is_assignment) ? x : __dadd_rn(s, x);
+                        for (int j = 0; j < (LREG ? LREG : 1); ++j) dst->vals[j] = v[j];
                     }
-                    sh.head_out[g] = s;
                 }
             }
         }
+        FOLD_STAMP(tb + 1);
         __syncthreads();
-        // ---- 5. every chunk: incoming value through the scan, real fold, comparison with the successor
+        if (tid < C) {
+            if (C == 1u) { sh.cta_tot[0] = cta_total; sh.cta_overflow[0] = sh.overflow; }
+            else {
+                cluster.map_shared_rank(&sh.cta_tot[0], tid)[crank] = cta_total;
+                cluster.map_shared_rank(&sh.cta_overflow[0], tid)[crank] = sh.overflow;
+            }
+        }
+        fold_sync(cluster, C);
+        FOLD_STAMP(tb + 2);
+        uint32_t overflow = 0u;
+        for (uint32_t r = 0; r < C; ++r) overflow |= sh.cta_overflow[r];
+        if (overflow) return false;                    // cluster-uniform
+        // ---- 3. the chain over the heads (same computation in every CTA: no further exchange needed)
+        if (tid == 0) {
+            FoldTd run = fold_identity();
+            for (uint32_t r = 0; r < C; ++r) { sh.cta_excl[r] = run; run = fold_compose(run, sh.cta_tot[r]); }
+            sh.cta_excl[C] = run;
+        }
+        __syncthreads();
+        const uint32_t H = sh.cta_excl[C].qc >> 2;
+        for (uint32_t g = tid; g < H; g += T) {         // per head: where its record is and the transducer in front of it
+            uint32_t c = 0u;
+            while (c + 1u < C && (sh.cta_excl[c + 1u].qc >> 2) <= g) c++;
+            const uint32_t k = g - (sh.cta_excl[c].qc >> 2);
+            const FoldRec<LREG>& rec = sh.rec[c][k];
+            FoldTd tail; tail.d0 = rec.d0; tail.d1 = rec.d1; tail.qc = rec.q_prev & 3u;
+            if ((rec.q_prev & 4u) == 0u) tail = fold_compose(sh.cta_excl[c], tail);
+            sh.head_d0[g] = tail.d0; sh.head_d1[g] = tail.d1;
+            sh.head_rec[g] = (uint16_t)(c * FOLD_HEADS_PER_CTA + k);
+        }
+        bool staged = false;
+        if (!LREG) {   // generic path: the heads' elements come from global memory, staged when they fit
+            __syncthreads();
+            staged = H * L <= FOLD_STAGE;
+            if (staged)
+                for (uint32_t j = tid; j < H * L; j += T) {
+                    const uint32_t i = (&sh.rec[0][0])[sh.head_rec[j / L]].chunk * L + j % L;
+                    sh.vals[j] = i < n ? get_global(i) : 0.0;
+                }
+        }
+        __syncthreads();
+        FOLD_STAMP(tb + 7);
+        if (tid == 0) {
+            double s = s0;
+            for (uint32_t g = 0; g < H; ++g) {
+                const FoldRec<LREG>& rec = (&sh.rec[0][0])[sh.head_rec[g]];
+                s = __dadd_rn(s, (f64_bits(s) & 1ll) ? sh.head_d1[g] : sh.head_d0[g]);
+                const bool assign = first_is_assignment && rec.chunk == 0u;
+                if (LREG) {
+                    s = assign ? rec.vals[0] : __dadd_rn(s, rec.vals[0]);
+#pragma unroll
+                    for (int j = 1; j < (LREG ? LREG : 1); ++j) s = __dadd_rn(s, rec.vals[j]);
+                } else {
+                    const uint32_t i0 = rec.chunk * L, m = min(n, i0 + L) - i0;
+                    for (uint32_t j = 0; j < m; ++j) {
+                        const double x = staged ? sh.vals[g * L + j] : get_global(i0 + j);
+                        s = (assign && j == 0u) ? x : __dadd_rn(s, x);
+                    }
+                }
+                sh.head_out[g] = s;
+            }
+            if (rnd == 0) info->heads = H;
+        }
+        FOLD_STAMP(tb + 3);
+        __syncthreads();
+        // ---- 4. every chunk: incoming value through the scan, real fold, comparison with the successor
         auto incoming = [&](const FoldTd& p) { return fold_apply(p, (p.qc >> 2) ? sh.head_out[(p.qc >> 2) - 1u] : s0); };
         const double s_in = incoming(fold_compose(sh.cta_excl[crank], excl));
         if (lane == 0) sh.warp_first[wid] = s_in;
-        if (tid == 0) sh.warp_first[32] = incoming(sh.cta_excl[crank + 1u]);   // first chunk of the next CTA
+        if (tid == 0) sh.warp_first[T >> 5] = incoming(sh.cta_excl[crank + 1u]);   // first chunk of the next CTA
         __syncthreads();
+        FOLD_STAMP(tb + 4);
         double next_in = __shfl_down_sync(0xffffffffu, s_in, 1);
         if (lane == 31u) next_in = sh.warp_first[wid + 1u];
         if (gt >= t0 && gt <= last) {
-            const double s_out = fold_chunk(s_in, true);
-            sout[gt] = s_out;
-            if (gt < last && f64_bits(s_out) != f64_bits(next_in)) atomicMin(&sh.bad, gt + 1u);
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid < W_CLUSTER) cluster.map_shared_rank(&sh.cta_bad[0], tid)[crank] = sh.bad;
-        cluster.sync();
-        uint32_t bad = 0xffffffffu;
+            double s = s_in;
+            if (LREG) {
+                s = assign_first ? v[0] : __dadd_rn(s, v[0]);
+                put(0, s);
 #pragma unroll
-        for (int r = 0; r < W_CLUSTER; ++r) bad = min(bad, sh.cta_bad[r]);
-        if (bad == 0xffffffffu) { proven = true; break; }
+                for (int j = 1; j < (LREG ? LREG : 1); ++j) { s = __dadd_rn(s, v[j]); if ((uint32_t)j < cnt) put(j, s); }
+            } else {
+                for (uint32_t j = 0; j < cnt; ++j) { const double x = get_global(lo + j); s = (assign_first && j == 0u) ? x : __dadd_rn(s, x); put(j, s); }
+            }
+            *s_in_out = s_in; *s_out_out = s;
+            sout[gt] = s;
+            if (gt < last && f64_bits(s) != f64_bits(next_in)) atomicMin(&sh.bad, gt + 1u);
+            if (gt == last) {
+                if (C == 1u) sh.total = s;
+                else for (uint32_t r = 0; r < C; ++r) *cluster.map_shared_rank(&sh.total, r) = s;
+            }
+        }
+        FOLD_STAMP(tb + 5);
+        __syncthreads();
+        if (tid < C) {
+            if (C == 1u) sh.cta_bad[0] = sh.bad;
+            else cluster.map_shared_rank(&sh.cta_bad[0], tid)[crank] = sh.bad;
+        }
+        fold_sync(cluster, C);    // (release / acquire at cluster scope: sout and ain of the other CTAs are visible)
+        FOLD_STAMP(tb + 6);
+        uint32_t bad = 0xffffffffu;
+        for (uint32_t r = 0; r < C; ++r) bad = min(bad, sh.cta_bad[r]);
+        if (bad == 0xffffffffu) { *total = sh.total; return true; }
         t0 = bad;
         s0 = __ldcg(&sout[bad - 1u]);                  // exact: every boundary in front of it matched
-        if (!(s0 < __longlong_as_double(0x7ff0000000000000ll))) break;   // NaN / inf: sequential
+        a_base = __ldcg(&ain[bad]);
+        if (!f64_finite(s0)) return false;             // NaN / inf: sequential
     }
-    if (proven) return __ldcg(&sout[last]);
-    // ---- sequential fallback (NaN / inf weights, adversarial inputs): the reference's loop as it stands
-    info->fallback = 1u;
-    if (tid == 0) {
-        double s = 0.0;
-        for (uint32_t i = 0; i < n; ++i) {
-            const double x = load(i);
-            s = (i == 0u && first_is_assignment) ? x : __dadd_rn(s, x);
-            if (prefix && crank == 0u) prefix[i] = s;
-        }
-        sh.fallback_total = s;
-    }
-    __syncthreads();
-    return sh.fallback_total;
+    return false;
 }
 
 // normalize_weights (particle.rs:49-56), the argmax of particle.rs:40-46 and the running sum of
-// particle.rs:85-91 over the WHOLE population, on one thread-block cluster: 8 CTAs x 1024 threads,
-// each thread owns a contiguous chunk. Both sums are the reference's strict left folds
-// (exact_left_fold); every GPU computes the same bits.
-__global__ void __cluster_dims__(W_CLUSTER, 1, 1) __launch_bounds__(W_THREADS)
+// particle.rs:85-91 over the WHOLE population, on one thread-block cluster of 1 to 8 CTAs; each thread
+// owns a contiguous chunk of the population (in registers: LREG elements; LREG = 0: re-read from global
+// memory, any length). Both sums are the reference's strict left folds (exact_left_fold); every GPU
+// computes the same bits.
+template <int LREG, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __restrict__ w_norm,
           double* __restrict__ cum, double* __restrict__ fold_scratch, StepCounters* counters) {
     cg::cluster_group cluster = cg::this_cluster();
-    const uint32_t crank = cluster.block_rank();
-    __shared__ FoldShared sh;
+    const uint32_t crank = cluster.block_rank(), C = cluster.num_blocks();
+    __shared__ FoldShared<LREG> sh;
     __shared__ double s_sq[W_CLUSTER];              // per-CTA sums of squared normalised weights (read by CTA 0)
     __shared__ long long s_key[32];
     __shared__ uint32_t s_arg[32];
     __shared__ long long s_ckey[W_CLUSTER];         // per-CTA argmax candidates (read by CTA 0)
     __shared__ uint32_t s_carg[W_CLUSTER];
-    cluster.sync();   // every CTA of the cluster is running before its shared memory is written remotely
-    const uint32_t gt = crank * W_THREADS + threadIdx.x;
-    const uint32_t chunk = (n + W_CHUNKS - 1) / W_CHUNKS;
-    const uint32_t lo = min(n, gt * chunk), hi = min(n, lo + chunk);
+    __shared__ double s_seq[2];
+    FOLD_STAMP(0);
+    const uint32_t gt = crank * THREADS + threadIdx.x;
+    const uint32_t L = LREG ? (uint32_t)LREG : (n + C * THREADS - 1u) / (C * THREADS);
+    const uint32_t lo = min(n, gt * L), hi = min(n, lo + L), cnt = hi - lo;
 
+    // This thread's raw weights (zero-padded: adding +0.0 changes no non-negative sum). A thread owns LREG
+    // consecutive elements, so direct accesses would touch 32 cache lines per warp instruction: loads and
+    // stores go through a padded shared-memory tile instead, lanes striding over consecutive elements.
+    extern __shared__ __align__(16) double s_tile[];   // register path: THREADS * (LREG + 1) doubles
+    auto tile_of = [](uint32_t e) { return e + e / (uint32_t)(LREG ? LREG : 1); };
+    const uint32_t warp_e0 = (threadIdx.x >> 5) * 32u * (uint32_t)(LREG ? LREG : 1);   // first element (within the CTA) of this warp
+    const uint32_t cta_e0 = crank * THREADS * (uint32_t)(LREG ? LREG : 1);
+    double v[LREG ? LREG : 1];
+    double part = 0.0;
+    bool all_zero = true;
+    if (LREG) {
+#pragma unroll
+        for (int i = 0; i < (LREG ? LREG : 1); ++i) {
+            const uint32_t e = warp_e0 + 32u * (uint32_t)i + (threadIdx.x & 31u);
+            s_tile[tile_of(e)] = cta_e0 + e < n ? results[cta_e0 + e].weight : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < (LREG ? LREG : 1); ++j) v[j] = s_tile[threadIdx.x * (LREG + 1) + j];
+#pragma unroll
+        for (int j = 0; j < (LREG ? LREG : 1); ++j) { part = __dadd_rn(part, v[j]); all_zero = all_zero && v[j] == 0.0; }
+    } else {
+        v[0] = 0.0;
+        for (uint32_t j = 0; j < cnt; ++j) { const double x = results[lo + j].weight; part = __dadd_rn(part, x); all_zero = all_zero && x == 0.0; }
+    }
+    // the warp's LREG * 32 values of the tile -> dst, coalesced
+    auto flush_tile = [&](double* __restrict__ dst) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < (LREG ? LREG : 1); ++i) {
+            const uint32_t e = warp_e0 + 32u * (uint32_t)i + (threadIdx.x & 31u);
+            if (cta_e0 + e < n) dst[cta_e0 + e] = s_tile[tile_of(e)];
+        }
+        __syncwarp();
+    };
     if (gt == 0) {   // per-step counters start from zero
         counters->clamped = 0ull; counters->saturated = 0ull; counters->spilled = 0ull;
         counters->n_alive = 0ull; counters->copy_bytes = 0ull; counters->copy_max_rows = 0ull;
         counters->n_mat = 0ull; counters->n_mat_leaders = 0ull; counters->ray_cell_steps = 0ull;
     }
+    FOLD_STAMP(1);
+    // re-associated prefix of the raw weights: the only ordinary scan of the kernel
+    double cta_sum;
+    const double offset = block_excl_scan_f64(part, sh.warp_f64, &cta_sum);
+    double a_in = offset;
+    if (C > 1u) {
+        cluster.sync();   // every CTA of the cluster is running before its shared memory is written remotely
+        if (threadIdx.x < C) cluster.map_shared_rank(&sh.cta_part[0], threadIdx.x)[crank] = cta_sum;
+        cluster.sync();
+        a_in = 0.0;
+        for (uint32_t r = 0; r < crank; ++r) a_in = __dadd_rn(a_in, sh.cta_part[r]);
+        a_in = __dadd_rn(a_in, offset);
+    }
+    const double a_out = __dadd_rn(a_in, part);
+    FOLD_STAMP(2);
 
     // pass 1: sum of the raw weights, `self.weights.iter().sum()` (particle.rs:50)
     FoldInfo info_sum, info_cum;
-    const double sum = exact_left_fold(cluster, sh, n, [&](uint32_t i) { return results[i].weight; }, false, nullptr,
-                                       fold_scratch, &info_sum);
+    double r_in = 0.0, r_out = 0.0, sum = 0.0;
+    bool ok = exact_left_fold<LREG>(cluster, sh, n, L, cnt, all_zero, a_in, a_out, v, [](uint32_t, double) {},
+                                    [&](uint32_t i) { return results[i].weight; }, false, fold_scratch, &r_in, &r_out, &sum,
+                                    &info_sum, 8);
+    FOLD_STAMP(3);
+    if (!ok) {   // the reference's loop as it stands, by one thread per CTA
+        info_sum.fallback = 1u;
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (uint32_t i = 0; i < n; ++i) s = __dadd_rn(s, results[i].weight);
+            s_seq[0] = s;
+        }
+        __syncthreads();
+        sum = s_seq[0];
+    }
 
     // pass 2: normalise, argmax candidate, sum of squares
     double sqpart = 0.0;
     long long best_key = (long long)0x8000000000000000ull;
     uint32_t best_i = 0;
     bool have = false;
-    for (uint32_t i = lo; i < hi; ++i) {
-        const double w = __ddiv_rn(results[i].weight, sum);
-        w_norm[i] = w;
+    all_zero = true;
+    auto norm_one = [&](uint32_t j, double x) {
+        const double w = __ddiv_rn(x, sum);
+        if (LREG) s_tile[threadIdx.x * (LREG + 1) + j] = w; else w_norm[lo + j] = w;
         sqpart = __dadd_rn(sqpart, __dmul_rn(w, w));
+        all_zero = all_zero && w == 0.0;
         const long long k = total_order_key(w);
-        if (!have || k >= best_key) { best_key = k; best_i = i; have = true; }  // last max wins
+        if (!have || k >= best_key) { best_key = k; best_i = lo + j; have = true; }  // last max wins
+        return w;
+    };
+    if (LREG) {
+#pragma unroll
+        for (int j = 0; j < (LREG ? LREG : 1); ++j) v[j] = (uint32_t)j < cnt ? norm_one(j, v[j]) : 0.0;
+        flush_tile(w_norm);
+    } else {
+        for (uint32_t j = 0; j < cnt; ++j) norm_one(j, results[lo + j].weight);
     }
+    FOLD_STAMP(4);
     double cta_sq;
     block_excl_scan_f64(sqpart, sh.warp_f64, &cta_sq);
-    if (threadIdx.x == 0) cluster.map_shared_rank(&s_sq[0], 0)[crank] = cta_sq;
 
     // argmax by f64::total_cmp, ties -> highest index (Iterator::max_by returns the last maximum)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (!have) { best_key = (long long)0x8000000000000000ull; best_i = 0; }
+    auto argmax_warp = [&]() {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long ok = __shfl_down_sync(0xffffffffu, best_key, o);
-        const uint32_t oi = __shfl_down_sync(0xffffffffu, best_i, o);
-        const bool ohave = __shfl_down_sync(0xffffffffu, (int)have, o) != 0;
-        if (ohave && (!have || ok > best_key || (ok == best_key && oi > best_i))) { best_key = ok; best_i = oi; have = true; }
-    }
-    if (lane == 0) { s_key[wid] = have ? best_key : (long long)0x8000000000000000ull; s_arg[wid] = have ? best_i : 0xffffffffu; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long bk = 0; uint32_t bi = 0xffffffffu; bool h = false;
-        for (int w = 0; w < W_THREADS / 32; ++w) {
-            if (s_arg[w] == 0xffffffffu) continue;
-            if (!h || s_key[w] > bk || (s_key[w] == bk && s_arg[w] > bi)) { bk = s_key[w]; bi = s_arg[w]; h = true; }
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long okey = __shfl_down_sync(0xffffffffu, best_key, o);
+            const uint32_t oi = __shfl_down_sync(0xffffffffu, best_i, o);
+            const bool ohave = __shfl_down_sync(0xffffffffu, (int)have, o) != 0;
+            if (ohave && (!have || okey > best_key || (okey == best_key && oi > best_i))) { best_key = okey; best_i = oi; have = true; }
         }
-        cluster.map_shared_rank(&s_ckey[0], 0)[crank] = bk;
-        cluster.map_shared_rank(&s_carg[0], 0)[crank] = bi;
+    };
+    argmax_warp();
+    if (lane == 0) { s_key[wid] = best_key; s_arg[wid] = have ? best_i : 0xffffffffu; }
+    __syncthreads();
+    if (wid == 0) {
+        have = lane < (THREADS >> 5) && s_arg[lane] != 0xffffffffu;
+        best_key = have ? s_key[lane] : (long long)0x8000000000000000ull;
+        best_i = have ? s_arg[lane] : 0u;
+        argmax_warp();
+        if (lane == 0) {
+            if (C == 1u) { s_ckey[0] = best_key; s_carg[0] = have ? best_i : 0xffffffffu; s_sq[0] = cta_sq; }
+            else {
+                cluster.map_shared_rank(&s_ckey[0], 0)[crank] = best_key;
+                cluster.map_shared_rank(&s_carg[0], 0)[crank] = have ? best_i : 0xffffffffu;
+                cluster.map_shared_rank(&s_sq[0], 0)[crank] = cta_sq;
+            }
+        }
     }
-    __threadfence();   // w_norm is read across CTAs by the fold below (ordered by its cluster barriers)
+    FOLD_STAMP(5);
 
-    // pass 3: running sum of the normalised weights, `c = weights[0]; ... c += weights[i]` (particle.rs:85-93)
-    exact_left_fold(cluster, sh, n, [&](uint32_t i) { return __ldcg(&w_norm[i]); }, true, cum, fold_scratch, &info_cum);
-
-    if (gt == 0) {   // (the fold's cluster barriers ordered the peers' candidates before this point)
+    // pass 3: running sum of the normalised weights, `c = weights[0]; ... c += weights[i]` (particle.rs:85-93).
+    // The exact raw prefixes of pass 1, divided by the sum, are the estimate that guesses the binades.
+    if (ok) {
+        double c_in, c_out, c_total;
+        ok = exact_left_fold<LREG>(cluster, sh, n, L, cnt, all_zero, __ddiv_rn(r_in, sum), __ddiv_rn(r_out, sum), v,
+                                   [&](uint32_t j, double s) { if (LREG) s_tile[threadIdx.x * (LREG + 1) + j] = s; else cum[lo + j] = s; },
+                                   [&](uint32_t i) { return __ldcg(&w_norm[i]); }, true, fold_scratch, &c_in, &c_out, &c_total,
+                                   &info_cum, 16);
+        if (!ok) info_cum.fallback = 1u;
+        else if (LREG) flush_tile(cum);
+    } else {
+        info_cum.rounds = 0u; info_cum.heads = 0u; info_cum.fallback = 1u;
+    }
+    FOLD_STAMP(6);
+    if (!ok) {
+        fold_sync(cluster, C);                          // every CTA's w_norm is written
+        if (gt == 0) {
+            double c = 0.0;
+            for (uint32_t i = 0; i < n; ++i) { const double w = __ldcg(&w_norm[i]); c = i ? __dadd_rn(c, w) : w; cum[i] = c; }
+        }
+        fold_sync(cluster, C);
+    }
+    // (a proven pass 3 ended with a cluster barrier: the peers' argmax candidates and sums of squares are in CTA 0)
+    if (gt == 0) {
         long long bk = 0; uint32_t bi = 0; bool h = false;
-        for (int r = 0; r < W_CLUSTER; ++r) {
+        for (uint32_t r = 0; r < C; ++r) {
             if (s_carg[r] == 0xffffffffu) continue;
             if (!h || s_ckey[r] > bk || (s_ckey[r] == bk && s_carg[r] > bi)) { bk = s_ckey[r]; bi = s_carg[r]; h = true; }
         }
@@ -399,19 +543,45 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         counters->sum = sum;
         // number_of_effective_particles (particle.rs:59-65) of the normalised weights, before resampling
         double sq = 0.0;
-        for (int r = 0; r < W_CLUSTER; ++r) sq = __dadd_rn(sq, s_sq[r]);
+        for (uint32_t r = 0; r < C; ++r) sq = __dadd_rn(sq, s_sq[r]);
         counters->n_eff = __ddiv_rn(1.0, sq);
         counters->fold_rounds = (unsigned long long)max(info_sum.rounds, info_cum.rounds);
         counters->fold_heads = (unsigned long long)max(info_sum.heads, info_cum.heads);
         counters->fold_fallback = (unsigned long long)(info_sum.fallback | (info_cum.fallback << 1));
     }
+    FOLD_STAMP(7);
 }
 
+static size_t weights_tile_bytes() { return sizeof(double) * FOLD_THREADS * (FOLD_LREG + 1); }
+// cluster size by population: 512 threads x 16 elements per CTA, 1 / 2 / 4 / 8 CTAs up to 65,536 particles;
+// beyond that the generic kernel (8 CTAs x 1024 threads, chunks re-read from global memory)
 void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
                     double* cum, double* fold_scratch, StepCounters* counters) {
-    k_weights<<<W_CLUSTER, W_THREADS, 0, stream>>>(results, n_total, w_norm, cum, fold_scratch, counters);
+    uint32_t c = 1u;
+    while (c < (uint32_t)W_CLUSTER && (uint64_t)c * FOLD_THREADS * FOLD_LREG < n_total) c <<= 1;
+    const bool regs = (uint64_t)c * FOLD_THREADS * FOLD_LREG >= n_total;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(c, 1, 1);
+    cfg.blockDim = dim3(regs ? FOLD_THREADS : FOLD_GENERIC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = regs ? weights_tile_bytes() : 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (regs) cudaLaunchKernelEx(&cfg, k_weights<FOLD_LREG, FOLD_THREADS>, results, n_total, w_norm, cum, fold_scratch, counters);
+    else cudaLaunchKernelEx(&cfg, k_weights<0, FOLD_GENERIC_THREADS>, results, n_total, w_norm, cum, fold_scratch, counters);
 }
-size_t weights_scratch_doubles() { return W_CHUNKS; }
+size_t weights_scratch_doubles() { return 2u * FOLD_MAX_CHUNKS; }
+int weights_trace(long long* out64) {
+#ifdef SLAMRS_FOLD_TRACE
+    return (int)cudaMemcpyFromSymbol(out64, g_fold_trace, sizeof(long long) * 64);
+#else
+    (void)out64;
+    return -1;
+#endif
+}
 
 // =============================================================================== k_resample_indices
 
@@ -931,6 +1101,9 @@ void launch_plan(cudaStream_t stream, const PlanArgs& a) {
 }
 
 cudaError_t configure_resample_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(k_weights<FOLD_LREG, FOLD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)weights_tile_bytes());
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_staged_bytes(PLAN_STAGED_MAX_S));
 }
 
