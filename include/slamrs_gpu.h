@@ -119,6 +119,9 @@ typedef struct slamrs_gpu_stats {
     uint64_t particles_integrated; /* local particles whose grid received the scan this step */
     uint64_t copy_bytes;       /* bytes the resampling copies read + wrote in this step (device-counted) */
     uint64_t window_overflow;  /* grids whose informed extent would have outgrown a windowed slot (error) */
+    uint64_t resample_exact_fallback; /* bit 0 / 1: the weight sum / the running sum of the last step was folded by a
+                                         single thread (NaN, inf or hostile weights; the result is the same) */
+    uint64_t resample_fold_rounds;    /* rounds the parallel exact fold needed (1 = proven at once) */
 } slamrs_gpu_stats;
 
 /* ------------------------------------------------------------------ lifecycle */

@@ -73,6 +73,8 @@ pub struct slamrs_gpu_stats {
     pub particles_integrated: u64,
     pub copy_bytes: u64,
     pub window_overflow: u64,
+    pub resample_exact_fallback: u64,
+    pub resample_fold_rounds: u64,
 }
 
 extern "C" {

@@ -56,7 +56,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "step", "grids_copied", "grids_pulled", "distinct_sources", "resample_clamped",
         "counter_saturated", "spilled_cells", "window_cells", "bytes_per_grid", "particles_integrated",
-        "copy_bytes", "window_overflow")]
+        "copy_bytes", "window_overflow", "resample_exact_fallback", "resample_fold_rounds")]
 
 
 class SlamrsGpuError(RuntimeError):

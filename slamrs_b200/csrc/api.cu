@@ -976,6 +976,8 @@ int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out) {
     out->bytes_per_grid = h->cells_per_grid * sizeof(uint32_t);
     out->window_overflow = c.window_overflow;
     out->copy_bytes = c.copy_bytes;
+    out->resample_exact_fallback = c.fold_fallback;
+    out->resample_fold_rounds = c.fold_rounds;
     return SLAMRS_OK;
 }
 

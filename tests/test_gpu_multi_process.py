@@ -1,0 +1,74 @@
+"""Multi-GPU parity with one PROCESS per GPU -- the configuration torchrun benchmarks run: ranks map each
+other's grid pools through CUDA IPC handles, publish their records with peer stores over that mapping
+and meet at system-scope flag barriers (slamrs_b200/csrc/api.cu setup_peers). Every rank's index vector,
+poses, published map and probed grids must equal the oracle's (particle.rs:78-105, slam.rs:77-88)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from slamrs_b200 import GridMapSlamConfig, nccl_unique_id
+
+from common import make_scans, oracle_slam, oracle_step
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("flags", [0, 8], ids=["peer-store-exchange", "nccl-exchange"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ranks_as_processes_equal_the_oracle(oracle, tmp_path, world, flags):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    n, steps = 64, 5
+    nid = nccl_unique_id().hex()
+    procs = []
+    for r in range(world):
+        out = str(tmp_path / f"rank{r}.npz")
+        procs.append((out, subprocess.Popen([sys.executable, os.path.join(HERE, "mp_rank_worker.py"), str(r), str(world), str(n),
+                                             str(steps), str(flags), nid, out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                            text=True)))
+    logs = []
+    for out, p in procs:
+        try:
+            o, _ = p.communicate(timeout=180)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            o, _ = p.communicate()
+            o += "\n[timeout]"
+        logs.append((p.returncode, o))
+    assert all(rc == 0 for rc, _ in logs), logs
+    shards = [np.load(out) for out, _ in procs]
+
+    cfg = GridMapSlamConfig(position=(-2.0, -2.0), width=4.0, height=4.0, resolution=0.02, n_particles=n)
+    scans = make_scans(1.0, 360, 1.0, steps)
+    osl = oracle_slam(oracle, cfg)
+    pulled = 0
+    S = n // world
+    for step, (obs, odo) in enumerate(scans):
+        rc, _, _ = oracle_step(oracle, osl, obs, odo, step)
+        assert rc == 0
+        idx_ref = osl.indices().astype(np.uint32)
+        poses_ref = osl.poses()
+        for r, sh in enumerate(shards):
+            assert np.array_equal(sh[f"idx{step}"], idx_ref), (step, r)
+            assert int(sh[f"maxp{step}"][0]) == osl.max_particle
+            assert np.array_equal(sh[f"poses{step}"].view(np.uint32), poses_ref[r * S:(r + 1) * S].view(np.uint32))
+            assert np.array_equal(sh[f"est{step}"].view(np.uint32), osl.estimated_pose().view(np.uint32))
+            assert np.max(np.abs(sh[f"map{step}"] - osl.estimated_likelihood())) < 1e-12
+            for key in sh.files:
+                if key.startswith(f"cells{step}_"):
+                    p = int(key.split("_")[1])
+                    nf, no = osl.counts(p)
+                    cells = sh[key]
+                    assert np.array_equal(cells & 0xFFFF, nf) and np.array_equal(cells >> 16, no), (step, r, p)
+            pulled += int(sh[f"pulled{step}"][0])
+    assert pulled > 0, "no grid migrated between the processes"
+    osl.close()
