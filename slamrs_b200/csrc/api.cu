@@ -81,6 +81,9 @@ struct slamrs_gpu_handle {
     uint32_t* d_leaders = nullptr;
     void* d_jobs = nullptr;      // CopyJob scratch of the extent-limited copy
     uint32_t* d_alive = nullptr;
+    RayItem* d_ray_items = nullptr;      // work list of the fused ray update (n_local)
+    uint32_t* d_readers = nullptr;       // per slot: clones that read it in this step | per slot: clones that have (2 x n_slots)
+    uint32_t* d_ray_spill = nullptr;     // scratch of the fused ray update
     StepCounters* d_counters = nullptr;
     StepCounters* h_counters = nullptr;  // pinned
     double* d_export = nullptr;
@@ -262,6 +265,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
     cudaFree(h->d_copies); cudaFree(h->d_leaders); cudaFree(h->d_alive); cudaFree(h->d_jobs);
+    cudaFree(h->d_ray_items); cudaFree(h->d_readers); cudaFree(h->d_ray_spill);
     cudaFree(h->d_alias); cudaFree(h->d_mat_items); cudaFree(h->d_mat_leaders); cudaFree(h->d_mat_roots);
     cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells); cudaFree(h->d_peer_meta);
     cudaFree(h->d_peer_results); cudaFree(h->d_peer_flags); cudaFree(h->d_peer_bands);
@@ -547,6 +551,9 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_mat_leaders, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_mat_roots, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_alive, sizeof(uint32_t) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_ray_items, sizeof(RayItem) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_readers, sizeof(uint32_t) * 2 * (size_t)h->n_slots));
+    CREATE_CU(cudaMalloc(&h->d_ray_spill, sizeof(uint32_t) * ray_spill_scratch_words(h->num_sms)));
     CREATE_CU(cudaMalloc(&h->d_counters, sizeof(StepCounters)));
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
     memset(h->h_counters, 0, sizeof(StepCounters));
@@ -591,7 +598,18 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     return SLAMRS_OK;
 }
 
-void slamrs_gpu_destroy(slamrs_gpu_handle* h) { free_all(h); }
+void slamrs_gpu_destroy(slamrs_gpu_handle* h) {
+    if (h && getenv("SLAMRS_RAY_TRACE_PRINT")) {
+        unsigned long long tr[18];
+        DeviceGuard g(h->device);
+        cudaStreamSynchronize(h->stream);
+        if (ray_trace(tr) == 0) {
+            fprintf(stderr, "ray trace: items fused %llu in-place %llu; cycles pop %llu setup %llu walk %llu fused_total %llu wait %llu inplace_wb %llu | fused: prepass %llu loop %llu barrier %llu\n",
+                    tr[16], tr[17], tr[0], tr[1], tr[2], tr[3], tr[4], tr[5], tr[8], tr[9], tr[10]);
+        }
+    }
+    free_all(h);
+}
 
 int slamrs_gpu_upload_scan(slamrs_gpu_handle* h, const float* angle, const float* dist, const uint8_t* valid,
                            uint32_t n_beams) {
@@ -706,9 +724,18 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local, true, h->d_alive, h->d_counters);
         h->launches++;
     }
-    // 3b. deferred copies: the clones among the particles about to be written get their own cells
-    //     (list now, copies after PROF_MARK 3). Before the planner starts: both write the alias table.
-    if (h->defer) {
+    // 3b. deferred copies: the clones among the particles about to be written get their own cells. Either the
+    //     ray kernel does it while it integrates the scan (fused: work list with the clones in front, no copy
+    //     kernels), or they are listed now and copied after PROF_MARK 3. Before the planner starts: both write
+    //     the alias table.
+    const bool force_generic = (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0;
+    const bool fuse = h->defer && !all_particles &&
+                      ray_update_can_fuse(h->geom, h->n_beams, h->cells_per_grid, force_generic, h->radius_cells);
+    if (fuse) {
+        CU_TRY(h, cudaMemsetAsync(h->d_readers, 0, sizeof(uint32_t) * 2 * (size_t)h->n_slots, s));
+        launch_ray_items(s, h->d_alive, h->n_local, h->d_slot[cur], h->d_alias, h->d_readers, h->d_ray_items, h->d_counters);
+        h->launches++;
+    } else if (h->defer) {
         if (all_particles)   // every clone: ordered list with fan-out sub-runs
             launch_materialize_list(s, nullptr, h->n_total, h->first, h->n_local, h->d_slot[cur], h->d_alias, h->d_cells,
                                     h->cells_per_grid, h->d_meta, h->d_bands, h->n_bands, h->d_mat_items, h->d_mat_leaders,
@@ -744,7 +771,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     h->launches++;
     h->launches += 2;
     PROF_MARK(h, 3);
-    if (h->defer) {
+    if (h->defer && !fuse) {
         int mrc = materialize_copies(h, all_particles);
         if (mrc) return mrc;
     }
@@ -754,9 +781,11 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         CU_TRY(h, cudaStreamWaitEvent(s, h->ev_sort, 0));
         h->order_pending = false;
     }
-    CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive, h->d_slot[cur],
+    CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive,
+                                fuse ? h->d_ray_items : nullptr, fuse ? h->d_readers : nullptr,
+                                fuse ? h->d_readers + h->n_slots : nullptr, h->d_ray_spill, h->d_slot[cur],
                                 h->d_cells, h->d_meta, h->d_bands, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
-                                (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0));
+                                force_generic, h->num_sms));
     h->launches++;
     PROF_MARK(h, 5);
     CU_TRY(h, cudaStreamWaitEvent(s, h->ev_plan, 0));   // join: the copy lists are ready
@@ -805,6 +834,8 @@ int slamrs_gpu_sync(slamrs_gpu_handle* h) {
                     h->h_counters->barrier_timeout == 2ull
                         ? "a peer GPU's handle was destroyed (its step failed or its owner left); this handle can only be destroyed"
                         : "a peer GPU did not reach the step barrier within the time limit");
+    if (h->h_counters->fuse_overflow)
+        return fail(h, SLAMRS_E_INTERNAL, "fused ray update: more window-bypassing hits than its scratch holds");
     if (h->h_counters->window_overflow)
         return fail(h, SLAMRS_E_WINDOW,
                     "a particle's informed extent outgrew its windowed grid slot; raise slot_cells (the scan was not "

@@ -50,6 +50,10 @@ struct StepCounters {
     unsigned long long n_mat;            // shared grids made private before this step's ray update (copies)
     unsigned long long n_mat_leaders;    // fan-out sub-runs among them
     unsigned long long ray_cell_steps;   // ray-iterator steps integrated this step (packed ray kernel), for the roofline
+    unsigned long long ray_work_head;    // next item of the ray update's work list (popped by its resident CTAs)
+    unsigned long long ray_items_front;  // k_ray_items: clones listed so far (front of the list)
+    unsigned long long ray_items_back;   // k_ray_items: slot owners listed so far (back of the list)
+    unsigned long long fuse_overflow;    // fused ray update: more parked hits than its scratch holds (error, cannot happen by its bound)
     unsigned long long fold_rounds;      // k_weights: rounds the exact left fold needed (1 = proven at once)
     unsigned long long fold_heads;       // k_weights: chunks resolved by the sequential chain (binade changes)
     unsigned long long fold_fallback;    // k_weights: bit 0 / 1 = the raw-weight sum / the running sum fell back to one thread
@@ -123,13 +127,27 @@ void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_fl
 void launch_peer_goodbye(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
                          uint32_t rank, uint32_t world, unsigned long long timeout_ns, StepCounters* counters);
 
+// One work item of the ray update: a surviving local particle, its slot and the slot whose cells it
+// logically holds (root != slot: a clone that k_ray_update_packed makes private while it integrates the scan)
+struct RayItem { uint32_t particle; int32_t slot; int32_t root; uint32_t pad; };
+// the fused path applies (packed window kernel, whole-grid tiled slots)
+bool ray_update_can_fuse(const MapGeom& geom, uint32_t n_beams, size_t cells_per_grid, bool force_generic, int radius_cells);
+size_t ray_spill_scratch_words(int num_sms);
+int ray_trace(unsigned long long* out18);   // tuning builds (-DSLAMRS_RAY_TRACE): cycles per phase, summed over CTAs   // scratch of the fused path (uint32 words)
+// items[0 .. counters->n_alive): clones first, slot owners last; readers[root]++ per clone (zeroed by the caller);
+// every listed clone's alias entry becomes the identity and counters->n_mat counts them
+void launch_ray_items(cudaStream_t stream, const uint32_t* alive_list, uint32_t n_local, const int32_t* slot_of,
+                      int32_t* alias_of, uint32_t* readers, RayItem* items, StepCounters* counters);
 // returns the shared-memory window size in cells through *window_cells
-// alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive)
+// alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive); with `items`
+// (launch_ray_items) the packed kernel fuses the clones' copies into its write-back (readers / done: per-slot
+// counters, zeroed by the caller before launch_ray_items)
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
+                              const RayItem* items, const uint32_t* readers, uint32_t* done, uint32_t* spill_scratch,
                               const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
-                              uint64_t* window_cells, bool force_generic);
+                              uint64_t* window_cells, bool force_generic, int num_sms);
 
 // fold_scratch: weights_scratch_doubles() doubles
 void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,

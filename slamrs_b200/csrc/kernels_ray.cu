@@ -374,83 +374,43 @@ __host__ __device__ inline int ray_window_cells_upper_bound_packed(int radius) {
 //  * a ray whose endpoint cell is (ax, ay) cells away from the start cell visits only cells within
 //    (ax + 2, ay + 2) of it; if that corner is inside the disc window and the disc is inside the
 //    grid, no per-cell window or grid test is needed.
-__global__ void __maxnreg__(80)   // 2 CTAs of 384 threads per SM; blocks have at most RAY_MAX_THREADS threads
-k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
-             const uint32_t* __restrict__ alive_list,
-                    const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
-                    uint32_t* __restrict__ bands_all, size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
-    extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
-    __shared__ int s_blo[RAY_MAX_BANDS], s_bhi[RAY_MAX_BANDS];
-    __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
-    __shared__ uint32_t s_rowb[RAY_MAX_ROWS];           // shared byte address of column x = 0 of the row
-    __shared__ int s_ext[4];
-    __shared__ int s_shift[1];
-    if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
-    const uint32_t p = alive_list[blockIdx.x];
-    ext_init(s_ext);
-    const ParticleResult r = results[first_particle + p];
-    const float px = r.x, py = r.y, ptheta = r.theta;
-    uint32_t* grid = cells + (size_t)slot_of[p] * cells_per_grid;
+constexpr uint32_t RAY_SPILL_CAP = 4u * RAY_PACKED_MAX_BEAMS;
+// SLAMRS_RAY_TRACE (tuning builds): thread 0 of every CTA adds the cycles it spent per phase of an item
+#ifdef SLAMRS_RAY_TRACE
+__device__ unsigned long long g_ray_trace[16];
+#define RAY_STAMP(k) do { if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(&g_ray_trace[k], (unsigned long long)(_t - t_prev)); t_prev = _t; } } while (0)
+#else
+#define RAY_STAMP(k) do { } while (0)
+#endif
+#ifdef SLAMRS_RAY_TRACE
+__device__ unsigned long long g_ray_trace_items[2];
+#endif
 
-    const float sx = world_to_grid(px, geom.pos_x, geom.res);
-    const float sy = world_to_grid(py, geom.pos_y, geom.res);
-    const long long lcx = f32_as_isize(floorf(sx)), lcy = f32_as_isize(floorf(sy));
-    if (lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh) return;
-    const int cx0 = (int)lcx, cy0 = (int)lcy;
+// The walk of every beam of one particle into the shared-memory window (GridRayIterator, ray.rs:21-110, with
+// the inverse sensor model of map.rs:148-172). Out of line on purpose: compiled on its own the free-run
+// loop stays the 25-instruction predicated block tools/sass_hot_loop.py checks for.
+__device__ __noinline__ void ray_walk_beams(const MapGeom& geom, const ScanDevice& scan, float px, float py, float ptheta, float sx,
+                                            float sy, int cx0, int cy0, int rad, int wy0, int wh, int band0, uint32_t* s_win,
+                                            const int2* s_row, const uint32_t* s_rowb, int* s_blo, int* s_bhi, int* s_ext,
+                                            uint32_t* __restrict__ grid, uint32_t* __restrict__ bands, int slot_shift, bool fused,
+                                            uint32_t* s_nspill_p, uint32_t* __restrict__ my_spill, bool* saturated_p,
+                                            uint32_t* spilled_p, uint32_t* cell_steps_p) {
     const int gw = (int)geom.gw, gh = (int)geom.gh;
     const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
-    if (window_would_overflow(geom, &meta[slot_of[p]], cx0, cy0, reach)) {
-        if (threadIdx.x == 0) atomicAdd(&counters->window_overflow, 1ull);
-        return;   // the grid is left as it was; the step reports SLAMRS_E_WINDOW
-    }
-    const int slot_shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx0, s_shift);
-    uint32_t* bands = bands_all + (size_t)slot_of[p] * bands_per_slot(geom);
-    band_init(s_blo, s_bhi);
-
-    // ---- row table of the disc window (x ranges aligned to 8 cells = one 128-bit group)
-    const int wy0 = max(0, cy0 - radius), wy1 = min(gh, cy0 + radius + 1);
-    const int band0 = wy0 / BAND_ROWS;
-    const int wh = wy1 - wy0;
-    for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {
-        const int dy = wy0 + ly - cy0;
-        const int hw = isqrt_small(radius * radius - dy * dy);
-        const int x0 = max(0, cx0 - hw) & ~7;
-        const int x1 = min(gw, (min(gw, cx0 + hw + 1) + 7) & ~7);
-        s_row[ly].y = x0 | ((x1 - x0) << 16);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        int carry = 0;
-        for (int base = 0; base < wh; base += 32) {
-            const int ly = base + (int)threadIdx.x;
-            const int w = ly < wh ? (s_row[ly].y >> 16) : 0;
-            int inc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((int)threadIdx.x >= o) inc += t;
-            }
-            if (ly < wh) {
-                const int first = carry + inc - w;
-                s_row[ly].x = first;
-                s_rowb[ly] = win_base + 2u * (uint32_t)(first - (s_row[ly].y & 0xffff));
-            }
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (threadIdx.x == 0) s_row[wh] = make_int2(carry, 0);
-    }
-    __syncthreads();
-    const int wcells = s_row[wh].x;
-    {
-        uint4* w4 = reinterpret_cast<uint4*>(s_win);
-        for (int i = threadIdx.x; i < (wcells >> 3); i += blockDim.x) w4[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    __syncthreads();
-
-    const bool disc_in_grid = cx0 - radius >= 0 && cx0 + radius < gw && cy0 - radius >= 0 && cy0 + radius < gh;
     bool saturated = false;
-    uint32_t spilled = 0;
-    uint32_t cell_steps = 0;   // iterator steps of this thread's rays (SURVEY.md 8(d): C_p, the unit of the ray update's bytes)
+    uint32_t spilled = 0, cell_steps = 0;
+    // A clone's own slot receives its cells only at write-back, so the (rare) hits that bypass the window --
+    // the 32nd occupied hit of a cell in one scan -- are parked and applied after the write-back.
+    // At most 4 occupied cells per ray: RAY_SPILL_CAP = 4 * RAY_PACKED_MAX_BEAMS entries always suffice.
+    auto exact_add = [&](int x, int y, uint32_t inc) {
+        if (fused) {
+            const uint32_t k = atomicAdd(s_nspill_p, 1u);
+            if (k < RAY_SPILL_CAP) my_spill[k] = (uint32_t)x | ((uint32_t)y << 15) | (inc == CELL_OCC_INC ? 0x40000000u : 0u);
+        } else {
+            global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, slot_shift)], inc, &saturated);
+        }
+    };
+    const bool disc_in_grid = cx0 - rad >= 0 && cx0 + rad < gw && cy0 - rad >= 0 && cy0 + rad < gh;
     // The row table is read at every y-step of the walk. Its shared address is kept in a register the
     // compiler cannot re-derive: left to itself ptxas may rebuild it inside the loop (S2UR + ULEA per
     // step, seen in SASS after an unrelated change elsewhere in the kernel), which costs the walk ~15 %.
@@ -461,7 +421,8 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(rowb_base + 4u * (uint32_t)row) : "memory");
         return v;
     };
-    for (uint32_t t = threadIdx.x; t < scan.n_beams; t += blockDim.x) {
+    const uint32_t n_beams_walk = scan.n_beams;
+    for (uint32_t t = threadIdx.x; t < n_beams_walk; t += blockDim.x) {
         const uint32_t b = scan.order ? scan.order[t] : t;   // similar ray lengths within a warp
         const float dist = scan.dist[b];
         float ex, ey;
@@ -515,7 +476,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         bool fast = false;
         if (disc_in_grid && ax < 4096ull && ay < 4096ull) {
             const int cxa = (int)ax + 2, cya = (int)ay + 2;
-            fast = cxa * cxa + cya * cya <= radius * radius;
+            fast = cxa * cxa + cya * cya <= rad * rad;
         }
         if (fast) {
             uint32_t x2 = 2u * (uint32_t)cx0;         // twice the current column
@@ -553,18 +514,18 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                     const uint32_t shift = ((c2 & 2u) << 3) + PK_FREE_BITS;
                     uint32_t old;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(c2 & ~3u) : "memory");
-                    bool done = false;
+                    bool done_here = false;
                     for (;;) {
                         if (((old >> shift) & PK_OCC_MAX) == PK_OCC_MAX) break;
                         uint32_t seen;
                         asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;"
                                      : "=r"(seen) : "r"(c2 & ~3u), "r"(old), "r"(old + (1u << shift)) : "memory");
-                        if (seen == old) { done = true; break; }
+                        if (seen == old) { done_here = true; break; }
                         old = seen;
                     }
-                    if (!done) {
+                    if (!done_here) {
                         const int x = (int)(x2 >> 1), y = wy0 + ly;
-                        global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, slot_shift)], CELL_OCC_INC, &saturated);
+                        exact_add(x, y, CELL_OCC_INC);
                         ext_add(s_ext, x, y, x, y);
                         band_add(s_blo, s_bhi, band0, y, x, x);
                         spilled++;
@@ -608,20 +569,19 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                 if (is_free & in_win) {
                     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u << shift) : "memory");
                 } else {
-                    bool done = false;
+                    bool done_here = false;
                     if (in_win) {   // occupied hit: bounded 5-bit field, exact path when it would overflow
                         uint32_t* wp = &s_win[cell >> 1];
                         uint32_t old = *wp;
                         for (;;) {
                             if (((old >> (shift + PK_FREE_BITS)) & PK_OCC_MAX) == PK_OCC_MAX) break;
                             const uint32_t seen = atomicCAS(wp, old, old + (1u << (shift + PK_FREE_BITS)));
-                            if (seen == old) { done = true; break; }
+                            if (seen == old) { done_here = true; break; }
                             old = seen;
                         }
                     }
-                    if (!done) {
-                        global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, slot_shift)],
-                                        is_free ? CELL_FREE_INC : CELL_OCC_INC, &saturated);
+                    if (!done_here) {
+                        exact_add(x, y, is_free ? CELL_FREE_INC : CELL_OCC_INC);
                         ext_add(s_ext, x, y, x, y);
                         band_add(s_blo, s_bhi, band0, y, x, x);
                         band_add_global(bands, geom, band0, x, y);
@@ -658,18 +618,32 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         }
         cell_steps -= (uint32_t)remaining;   // the walk ended at the grid border
     }
-    __syncthreads();
+    if (saturated) *saturated_p = true;
+    *spilled_p += spilled;
+    *cell_steps_p += cell_steps;
+}
 
-    // ---- write-back. A window row is at most 34 groups of 8 cells (one 128-bit shared load each); a
-    // non-empty group is two 128-bit global read-modify-writes. Main pass: one warp per row, lane g
-    // takes group g < 32, RAY_WB_ROWS rows in flight per warp. Tail pass: the (at most two) groups
-    // beyond the 32nd of each row, one thread per row. One code path per group: the packed window
-    // value is unpacked without a branch; only a grid counter at or above 2^15 (which one scan's
-    // increment could saturate) takes the saturating form.
-    constexpr int RAY_WB_ROWS = 4;
+// Fused copy + write-back of one clone (see k_ray_update_packed): reads the root slot's tiles, adds the
+// window, writes the clone's own slot, clears what the slot's previous tenant had informed elsewhere,
+// applies the parked exact-path hits, commits extents and announces that the root has been read.
+// Kept out of line: inlined, its live ranges push the ray walk's loop off its tight form.
+__device__ __noinline__ void ray_fused_writeback(const MapGeom& geom, int32_t slot, int32_t root, uint32_t* __restrict__ cells,
+                                                 SlotMeta* __restrict__ meta, uint32_t* __restrict__ bands_all,
+                                                 size_t cells_per_grid, const uint32_t* s_win, const int2* s_row, int* s_blo,
+                                                 int* s_bhi, int* s_ext, const uint32_t* s_nspill_p, const uint32_t* my_spill,
+                                                 int wy0, int wh, int band0, uint32_t* __restrict__ done, StepCounters* counters,
+                                                 bool* saturated_p, uint32_t* moved_p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int gw = (int)geom.gw;
+    const uint32_t n_bands_slot = bands_per_slot(geom);
+    uint32_t* grid = cells + (size_t)slot * cells_per_grid;
+    uint32_t* bands = bands_all + (size_t)slot * n_bands_slot;
+    bool saturated = false;
+    uint32_t moved = 0;
+#ifdef SLAMRS_RAY_TRACE
+    long long t_prev = clock64();
+#endif
     const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
-    int exmin = 0x7fffffff, eymin = 0x7fffffff, exmax = -1, eymax = -1;   // this thread's touched extent
     auto unpack = [](uint32_t packed16) { return (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16); };
     auto merge_group = [&](uint4& va, uint4& vb, const uint4& d) {
         const uint32_t high_any = (va.x | va.y | va.z | va.w | vb.x | vb.y | vb.z | vb.w) & 0x80008000u;
@@ -685,73 +659,421 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
             vb.z = cell_sat_add(vb.z, unpack(d.w & 0xffffu), &saturated); vb.w = cell_sat_add(vb.w, unpack(d.w >> 16), &saturated);
         }
     };
-    for (int ly0 = warp; ly0 < wh; ly0 += n_warps * RAY_WB_ROWS) {
-        uint4 d[RAY_WB_ROWS], va[RAY_WB_ROWS], vb[RAY_WB_ROWS];
-        uint4* gp[RAY_WB_ROWS];
-        bool nz[RAY_WB_ROWS];
+    // ---- fused copy + write-back (whole-grid tiled slots: logical cell = physical cell).
+    // Pre-pass: per band of the window the columns that really received hits. A lane scans one window row,
+    // a warp four bands at a time; the eight lanes of a band combine their ranges with shuffles.
+    {
+        const int rr = lane & 7, bq = lane >> 3;
+        int wxmin = 0x7fffffff, wymin = 0x7fffffff, wxmax = -1, wymax = -1;
+        const int n_wbands = (wy0 + wh - 1) / BAND_ROWS - band0 + 1;
+        for (int q = warp; 4 * q < n_wbands; q += n_warps) {
+            const int lb = 4 * q + bq;
+            const int y = (band0 + lb) * BAND_ROWS + rr, ly = y - wy0;
+            int first = 0x7fffffff, last = -1, rx0 = 0;
+            int2 row = make_int2(0, 0);
+            if (lb < n_wbands && (unsigned)ly < (unsigned)wh) { row = s_row[ly]; rx0 = row.y & 0xffff; }
+            const int groups = row.y >> 19;
+            for (int g = 0; g < 34; ++g) {                 // (a window row is at most 34 groups wide)
+                if (__all_sync(0xffffffffu, g >= groups)) break;
+                if (g < groups) {
+                    const uint4 d = win4[(row.x >> 3) + g];
+                    if ((d.x | d.y | d.z | d.w) != 0u) { first = min(first, g); last = g; }
+                }
+            }
+            int xlo = last >= 0 ? rx0 + 8 * first : 0x7fffffff, xhi = last >= 0 ? rx0 + 8 * last + 7 : -1;
+            const int ylo = last >= 0 ? y : 0x7fffffff, yhi = last >= 0 ? y : -1;
+            wymin = min(wymin, ylo); wymax = max(wymax, yhi);
 #pragma unroll
-        for (int j = 0; j < RAY_WB_ROWS; ++j) {
-            const int ly = ly0 + j * n_warps;
-            nz[j] = false;
-            if (ly < wh) {
-                const int2 row = s_row[ly];
-                if (lane < (row.y >> 19)) {          // width / 8 groups in this row
-                    d[j] = win4[(row.x >> 3) + lane];
-                    nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
-                    if (nz[j]) {
-                        const int gx0 = (row.y & 0xffff) + 8 * lane;
-                        exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
-                        eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
-                        gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
+            for (int o = 1; o < 8; o <<= 1) {
+                xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+                xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+            }
+            wxmin = min(wxmin, xlo); wxmax = max(wxmax, xhi);
+            if (rr == 0 && xhi >= xlo && (unsigned)lb < (unsigned)RAY_MAX_BANDS) { atomicMin(&s_blo[lb], xlo); atomicMax(&s_bhi[lb], xhi); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wxmin = min(wxmin, __shfl_xor_sync(0xffffffffu, wxmin, o)); wxmax = max(wxmax, __shfl_xor_sync(0xffffffffu, wxmax, o));
+            wymin = min(wymin, __shfl_xor_sync(0xffffffffu, wymin, o)); wymax = max(wymax, __shfl_xor_sync(0xffffffffu, wymax, o));
+        }
+        if (lane == 0) ext_add(s_ext, wxmin, wymin, wxmax, wymax);
+    }
+    __syncthreads();
+    RAY_STAMP(8);
+    const uint32_t* src = cells + (size_t)root * cells_per_grid;
+    const uint32_t* src_bands = bands_all + (size_t)root * n_bands_slot;
+    const SlotMeta sm = meta[root], om = meta[slot];
+    // bands to visit: the source's rows, the rows the slot's previous tenant had informed, the touched window rows
+    int by0 = 0x7fffffff, by1 = -1;
+    if (sm.x1 > sm.x0 && sm.y1 > sm.y0) { by0 = min(by0, sm.y0 / BAND_ROWS); by1 = max(by1, (sm.y1 - 1) / BAND_ROWS); }
+    if (om.x1 > om.x0 && om.y1 > om.y0) { by0 = min(by0, om.y0 / BAND_ROWS); by1 = max(by1, (om.y1 - 1) / BAND_ROWS); }
+    if (s_ext[3] >= s_ext[1] && s_ext[2] >= s_ext[0]) { by0 = min(by0, s_ext[1] / BAND_ROWS); by1 = max(by1, s_ext[3] / BAND_ROWS); }
+    const uint32_t tpr = geom.tiles_per_row;
+    constexpr int FUSE_DEPTH = 4;              // tiles in flight per warp
+    const int rr = lane >> 2, uu = lane & 3;   // this lane's row of the band and 32-byte unit of the tile row
+    // bands go to the warps round-robin: every warp gets narrow (top, bottom) and wide (middle) bands alike
+    for (int bnd = by0 + warp; bnd <= by1; bnd += n_warps) {
+        const uint32_t es = src_bands[bnd], eo = bands[bnd];
+        const int lb = bnd - band0;
+        const bool touched = (unsigned)lb < (unsigned)RAY_MAX_BANDS && s_bhi[lb] >= s_blo[lb];
+        uint32_t n0 = es ? (es & 0xffffu) : 0xffffu, n1 = es ? (es >> 16) : 0u;     // new extent: source + touched
+        if (touched) { n0 = min(n0, (uint32_t)s_blo[lb] & ~7u); n1 = max(n1, min(geom.gw, ((uint32_t)s_bhi[lb] + 8u) & ~7u)); }
+        uint32_t u0 = n0, u1 = n1;                                                   // to write: new + old (to clear)
+        if (eo) { u0 = min(u0, eo & 0xffffu); u1 = max(u1, eo >> 16); }
+        __syncwarp();                                   // every lane has read the old entry
+        if (lane == 0) bands[bnd] = n1 > n0 ? (n0 | (n1 << 16)) : 0u;
+        if (u1 <= u0) continue;
+        const int t_lo = (int)(u0 / TILE_COLS), t_hi = (int)((u1 + TILE_COLS - 1u) / TILE_COLS);
+        // this lane's window row, if the band has one
+        const int y = bnd * BAND_ROWS + rr, ly = y - wy0;
+        int wfirst = 0, wx0 = 0, ww = 0;
+        if (touched && (unsigned)ly < (unsigned)wh) { const int2 row = s_row[ly]; wfirst = row.x; wx0 = row.y & 0xffff; ww = row.y >> 16; }
+        const uint32_t sx0 = es & 0xffffu, sx1 = es >> 16;                           // (0, 0 when the source has nothing here)
+        const size_t band_off = (size_t)bnd * tpr * TILE_CELLS + 8u * (uint32_t)lane;
+        for (int t0 = t_lo; t0 < t_hi; t0 += FUSE_DEPTH) {
+            uint4 va[FUSE_DEPTH], vb[FUSE_DEPTH];
+#pragma unroll
+            for (int k = 0; k < FUSE_DEPTH; ++k) {
+                const int t = t0 + k;
+                const uint32_t x = (uint32_t)t * TILE_COLS + 8u * (uint32_t)uu;
+                va[k] = make_uint4(0u, 0u, 0u, 0u); vb[k] = va[k];
+                if (t < t_hi && x >= sx0 && x < sx1) {
+                    const V8 s8 = ld_stream_v8(reinterpret_cast<const V8*>(src + band_off + (size_t)t * TILE_CELLS));
+                    va[k] = s8.a; vb[k] = s8.b;
+                    moved++;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < FUSE_DEPTH; ++k) {
+                const int t = t0 + k;
+                if (t >= t_hi) break;
+                const int lx = t * (int)TILE_COLS + 8 * uu - wx0;
+                if ((unsigned)lx < (unsigned)ww) {
+                    const uint4 d = win4[(wfirst + lx) >> 3];
+                    if ((d.x | d.y | d.z | d.w) != 0u) merge_group(va[k], vb[k], d);
+                }
+                V8 o8; o8.a = va[k]; o8.b = vb[k];
+                st_stream_v8(reinterpret_cast<V8*>(grid + band_off + (size_t)t * TILE_CELLS), o8);
+                moved++;
+            }
+        }
+    }
+    RAY_STAMP(9);
+    __syncthreads();
+    RAY_STAMP(10);
+    {   // the parked exact-path hits, now that the slot holds its cells
+        const uint32_t ns = *s_nspill_p;
+        if (ns > RAY_SPILL_CAP && threadIdx.x == 0) atomicAdd(&counters->fuse_overflow, 1ull);
+        for (uint32_t k = threadIdx.x; k < min(ns, RAY_SPILL_CAP); k += blockDim.x) {
+            const uint32_t e = my_spill[k];
+            global_cell_add(&grid[phys_index(geom, e & 0x7fffu, (e >> 15) & 0x7fffu, 0)],
+                            (e & 0x40000000u) ? CELL_OCC_INC : CELL_FREE_INC, &saturated);
+        }
+    }
+    if (threadIdx.x == 0) {
+        // the slot now holds the source's extent plus what this scan touched
+        SlotMeta nm = sm;
+        nm.ox = 0;
+        if (!(nm.x1 > nm.x0 && nm.y1 > nm.y0)) { nm.x0 = nm.y0 = nm.x1 = nm.y1 = 0; }
+        meta[slot] = nm;
+        ext_commit(s_ext, &meta[slot], gw, 0);
+        __threadfence();
+        atomicAdd(&done[root], 1u);        // the root has been read: its owner may write it
+    }
+    if (saturated) *saturated_p = true;
+    *moved_p += moved;
+}
+
+// Work distribution. The kernel is launched with as many CTAs as are resident at once (two per SM at a
+// 6 m / 5 cm window) and every CTA pops work items from an atomic counter until the list is empty: the
+// list holds the few hundred particles that survive this step's resampling, not the whole population.
+//
+// Fused copies (deferred copies, whole-grid tiled slots). A surviving particle whose grid is still an
+// alias of its source's slot ("clone") would first need its own copy of the source's cells (k_copy_boxed)
+// and then read them again to add the scan. Here its CTA does both in one pass: it reads the ROOT slot's
+// tiles, adds the window, writes its OWN slot (and clears what the slot's previous tenant had informed
+// outside the new extent). The copy kernels and their pass over the grids disappear from the step.
+// The hazard is the root's owner integrating the scan in place while a clone still reads the root:
+// k_ray_items puts the clones at the front of the list and the particles that own their slot at the
+// back, counts the clones per root (readers[]), every clone announces when it has read its root
+// (done[]), and an owner waits for its readers before it writes. Items are popped in list order by CTAs
+// that are all resident, so every reader an owner waits for is already running: no deadlock.
+struct RayJob {      // what a CTA works on, resolved once per item
+    uint32_t particle;
+    int32_t slot, root;   // root != slot: fused copy
+};
+
+__global__ void __maxnreg__(80)   // 2 CTAs of 384 threads per SM; blocks have at most RAY_MAX_THREADS threads
+k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
+                    const uint32_t* __restrict__ alive_list, const RayItem* __restrict__ items,
+                    const uint32_t* __restrict__ readers, uint32_t* __restrict__ done, uint32_t* __restrict__ spill_scratch,
+                    const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
+                    uint32_t* __restrict__ bands_all, size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
+    extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
+    __shared__ uint32_t s_nspill;
+    __shared__ int s_blo[RAY_MAX_BANDS], s_bhi[RAY_MAX_BANDS];
+    __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
+    __shared__ uint32_t s_rowb[RAY_MAX_ROWS];           // shared byte address of column x = 0 of the row
+    __shared__ int s_ext[4];
+    __shared__ int s_shift[1];
+    __shared__ unsigned long long s_next;
+    const unsigned long long n_items = counters->n_alive;
+    const int gw = (int)geom.gw, gh = (int)geom.gh;
+    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t n_bands_slot = bands_per_slot(geom);
+    bool saturated = false;
+    uint32_t spilled = 0;
+    uint32_t cell_steps = 0;   // iterator steps of this thread's rays (SURVEY.md 8(d): C_p, the unit of the ray update's bytes)
+    uint32_t moved = 0;        // 32-byte units read + written by the fused copies (this thread)
+
+#ifdef SLAMRS_RAY_TRACE
+    long long t_prev = clock64();
+#endif
+    for (;;) {
+        __syncthreads();       // the previous item's shared state is no longer read
+        RAY_STAMP(0);
+        if (threadIdx.x == 0) s_next = atomicAdd(&counters->ray_work_head, 1ull);
+        __syncthreads();
+        const unsigned long long item = s_next;
+        if (item >= n_items) break;
+        RayJob job;
+        if (items) { const RayItem it = items[item]; job.particle = it.particle; job.slot = it.slot; job.root = it.root; }
+        else { job.particle = alive_list[item]; job.slot = slot_of[job.particle]; job.root = job.slot; }
+        const bool fused = job.root != job.slot;
+        const uint32_t p = job.particle;
+        uint32_t* grid = cells + (size_t)job.slot * cells_per_grid;
+        ext_init(s_ext);
+        if (threadIdx.x == 0) s_nspill = 0u;
+        uint32_t* my_spill = spill_scratch + (size_t)blockIdx.x * RAY_SPILL_CAP;
+        const ParticleResult r = results[first_particle + p];
+        const float px = r.x, py = r.y, ptheta = r.theta;
+
+        const float sx = world_to_grid(px, geom.pos_x, geom.res);
+        const float sy = world_to_grid(py, geom.pos_y, geom.res);
+        const long long lcx = f32_as_isize(floorf(sx)), lcy = f32_as_isize(floorf(sy));
+        // every ray starts in the same cell; outside the grid nothing is emitted (ray.rs:88-92)
+        const bool start_inside = !(lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh);
+        if (!start_inside && !fused) continue;
+        // (a clone whose pose left the grid integrates nothing but still gets its own cells: window of radius 0 at cell 0)
+        const int cx0 = start_inside ? (int)lcx : 0, cy0 = start_inside ? (int)lcy : 0;
+        const int rad = start_inside ? radius : 0;
+        if (window_would_overflow(geom, &meta[job.slot], cx0, cy0, reach)) {   // windowed slots only (never fused)
+            if (threadIdx.x == 0) atomicAdd(&counters->window_overflow, 1ull);
+            continue;   // the grid is left as it was; the step reports SLAMRS_E_WINDOW
+        }
+        const int slot_shift = fused ? 0 : ray_slot_shift(geom, scan, &meta[job.slot], px, py, ptheta, cx0, s_shift);
+        uint32_t* bands = bands_all + (size_t)job.slot * n_bands_slot;
+        band_init(s_blo, s_bhi);
+
+        // ---- row table of the disc window (x ranges aligned to 8 cells = one 128-bit group)
+        const int wy0 = max(0, cy0 - rad), wy1 = min(gh, cy0 + rad + 1);
+        const int band0 = wy0 / BAND_ROWS;
+        const int wh = wy1 - wy0;
+        for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {
+            const int dy = wy0 + ly - cy0;
+            const int hw = isqrt_small(rad * rad - dy * dy);
+            const int x0 = max(0, cx0 - hw) & ~7;
+            const int x1 = min(gw, (min(gw, cx0 + hw + 1) + 7) & ~7);
+            s_row[ly].y = x0 | ((x1 - x0) << 16);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int carry = 0;
+            for (int base = 0; base < wh; base += 32) {
+                const int ly = base + (int)threadIdx.x;
+                const int w = ly < wh ? (s_row[ly].y >> 16) : 0;
+                int inc = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if ((int)threadIdx.x >= o) inc += t;
+                }
+                if (ly < wh) {
+                    const int first = carry + inc - w;
+                    s_row[ly].x = first;
+                    s_rowb[ly] = win_base + 2u * (uint32_t)(first - (s_row[ly].y & 0xffff));
+                }
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (threadIdx.x == 0) s_row[wh] = make_int2(carry, 0);
+        }
+        __syncthreads();
+        const int wcells = s_row[wh].x;
+        {
+            uint4* w4 = reinterpret_cast<uint4*>(s_win);
+            for (int i = threadIdx.x; i < (wcells >> 3); i += blockDim.x) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+
+        RAY_STAMP(1);
+        if (start_inside)
+            ray_walk_beams(geom, scan, px, py, ptheta, sx, sy, cx0, cy0, rad, wy0, wh, band0, s_win, s_row, s_rowb, s_blo, s_bhi, s_ext,
+                           grid, bands, slot_shift, fused, &s_nspill, my_spill, &saturated, &spilled, &cell_steps);
+        __syncthreads();
+        RAY_STAMP(2);
+
+        const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
+        auto unpack = [](uint32_t packed16) { return (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16); };
+        auto merge_group = [&](uint4& va, uint4& vb, const uint4& d) {
+            const uint32_t high_any = (va.x | va.y | va.z | va.w | vb.x | vb.y | vb.z | vb.w) & 0x80008000u;
+            if (high_any == 0u) {
+                va.x += unpack(d.x & 0xffffu); va.y += unpack(d.x >> 16);
+                va.z += unpack(d.y & 0xffffu); va.w += unpack(d.y >> 16);
+                vb.x += unpack(d.z & 0xffffu); vb.y += unpack(d.z >> 16);
+                vb.z += unpack(d.w & 0xffffu); vb.w += unpack(d.w >> 16);
+            } else {
+                va.x = cell_sat_add(va.x, unpack(d.x & 0xffffu), &saturated); va.y = cell_sat_add(va.y, unpack(d.x >> 16), &saturated);
+                va.z = cell_sat_add(va.z, unpack(d.y & 0xffffu), &saturated); va.w = cell_sat_add(va.w, unpack(d.y >> 16), &saturated);
+                vb.x = cell_sat_add(vb.x, unpack(d.z & 0xffffu), &saturated); vb.y = cell_sat_add(vb.y, unpack(d.z >> 16), &saturated);
+                vb.z = cell_sat_add(vb.z, unpack(d.w & 0xffffu), &saturated); vb.w = cell_sat_add(vb.w, unpack(d.w >> 16), &saturated);
+            }
+        };
+
+        if (fused) {
+            ray_fused_writeback(geom, job.slot, job.root, cells, meta, bands_all, cells_per_grid, s_win, s_row, s_blo, s_bhi, s_ext,
+                                &s_nspill, my_spill, wy0, wh, band0, done, counters, &saturated, &moved);
+            RAY_STAMP(3);
+#ifdef SLAMRS_RAY_TRACE
+            if (threadIdx.x == 0) atomicAdd(&g_ray_trace_items[0], 1ull);
+#endif
+            continue;
+        }
+
+        // ---- in-place write-back. The owner of a slot that clones read in this step waits for them first.
+        if (readers != nullptr) {
+            if (threadIdx.x == 0) {
+                const uint32_t want = readers[job.slot];
+                if (want != 0u) {
+                    uint32_t seen;
+                    for (;;) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + job.slot) : "memory");
+                        if (seen >= want) break;
+                        __nanosleep(100);
                     }
                 }
             }
+            __syncthreads();
+            RAY_STAMP(4);
         }
+        // A window row is at most 34 groups of 8 cells (one 128-bit shared load each); a
+        // non-empty group is two 128-bit global read-modify-writes. Main pass: one warp per row, lane g
+        // takes group g < 32, RAY_WB_ROWS rows in flight per warp. Tail pass: the (at most two) groups
+        // beyond the 32nd of each row, one thread per row. One code path per group: the packed window
+        // value is unpacked without a branch; only a grid counter at or above 2^15 (which one scan's
+        // increment could saturate) takes the saturating form.
+        constexpr int RAY_WB_ROWS = 4;
+        int exmin = 0x7fffffff, eymin = 0x7fffffff, exmax = -1, eymax = -1;   // this thread's touched extent
+        for (int ly0 = warp; ly0 < wh; ly0 += n_warps * RAY_WB_ROWS) {
+            uint4 d[RAY_WB_ROWS], va[RAY_WB_ROWS], vb[RAY_WB_ROWS];
+            uint4* gp[RAY_WB_ROWS];
+            bool nz[RAY_WB_ROWS];
 #pragma unroll
-        for (int j = 0; j < RAY_WB_ROWS; ++j)
-            if (nz[j]) ld_group_v8(gp[j], va[j], vb[j]);
+            for (int j = 0; j < RAY_WB_ROWS; ++j) {
+                const int ly = ly0 + j * n_warps;
+                nz[j] = false;
+                if (ly < wh) {
+                    const int2 row = s_row[ly];
+                    if (lane < (row.y >> 19)) {          // width / 8 groups in this row
+                        d[j] = win4[(row.x >> 3) + lane];
+                        nz[j] = (d[j].x | d[j].y | d[j].z | d[j].w) != 0u;
+                        if (nz[j]) {
+                            const int gx0 = (row.y & 0xffff) + 8 * lane;
+                            exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
+                            eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
+                            gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
+                        }
+                    }
+                }
+            }
 #pragma unroll
-        for (int j = 0; j < RAY_WB_ROWS; ++j) {   // band extent of the row: first / last non-empty group
-            const unsigned mnz = __ballot_sync(0xffffffffu, nz[j]);
-            const int ly = ly0 + j * n_warps;
-            if (mnz != 0u && lane == 0) {
-                const int rx0 = s_row[ly].y & 0xffff;
-                band_add(s_blo, s_bhi, band0, wy0 + ly, rx0 + 8 * (__ffs(mnz) - 1), rx0 + 8 * (31 - __clz(mnz)) + 7);
+            for (int j = 0; j < RAY_WB_ROWS; ++j)
+                if (nz[j]) ld_group_v8(gp[j], va[j], vb[j]);
+#pragma unroll
+            for (int j = 0; j < RAY_WB_ROWS; ++j) {   // band extent of the row: first / last non-empty group
+                const unsigned mnz = __ballot_sync(0xffffffffu, nz[j]);
+                const int ly = ly0 + j * n_warps;
+                if (mnz != 0u && lane == 0) {
+                    const int rx0 = s_row[ly].y & 0xffff;
+                    band_add(s_blo, s_bhi, band0, wy0 + ly, rx0 + 8 * (__ffs(mnz) - 1), rx0 + 8 * (31 - __clz(mnz)) + 7);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RAY_WB_ROWS; ++j) {
+                if (nz[j]) {
+                    merge_group(va[j], vb[j], d[j]);
+                    st_group_v8(gp[j], va[j], vb[j]);
+                }
             }
         }
-#pragma unroll
-        for (int j = 0; j < RAY_WB_ROWS; ++j) {
-            if (nz[j]) {
-                merge_group(va[j], vb[j], d[j]);
-                st_group_v8(gp[j], va[j], vb[j]);
+        for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {   // tail pass: groups 32, 33 of each row
+            const int2 row = s_row[ly];
+            for (int g = 32; g < (row.y >> 19); ++g) {
+                const uint4 dd = win4[(row.x >> 3) + g];
+                if ((dd.x | dd.y | dd.z | dd.w) == 0u) continue;
+                const int gx0 = (row.y & 0xffff) + 8 * g;
+                exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
+                eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
+                band_add(s_blo, s_bhi, band0, wy0 + ly, gx0, gx0 + 7);
+                uint4* gpt = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
+                uint4 ta = gpt[0], tb = gpt[1];
+                merge_group(ta, tb, dd);
+                gpt[0] = ta;
+                gpt[1] = tb;
             }
         }
+        ext_add(s_ext, exmin, eymin, exmax, eymax);
+        __syncthreads();
+        band_commit(s_blo, s_bhi, band0, bands, geom);
+        if (threadIdx.x == 0) ext_commit(s_ext, &meta[job.slot], (int)geom.gw, slot_shift);
+        RAY_STAMP(5);
+#ifdef SLAMRS_RAY_TRACE
+        if (threadIdx.x == 0) atomicAdd(&g_ray_trace_items[1], 1ull);
+#endif
     }
-    for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {   // tail pass: groups 32, 33 of each row
-        const int2 row = s_row[ly];
-        for (int g = 32; g < (row.y >> 19); ++g) {
-            const uint4 dd = win4[(row.x >> 3) + g];
-            if ((dd.x | dd.y | dd.z | dd.w) == 0u) continue;
-            const int gx0 = (row.y & 0xffff) + 8 * g;
-            exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
-            eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
-            band_add(s_blo, s_bhi, band0, wy0 + ly, gx0, gx0 + 7);
-            uint4* gpt = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
-            uint4 ta = gpt[0], tb = gpt[1];
-            merge_group(ta, tb, dd);
-            gpt[0] = ta;
-            gpt[1] = tb;
-        }
-    }
-    ext_add(s_ext, exmin, eymin, exmax, eymax);
-    __syncthreads();
-    band_commit(s_blo, s_bhi, band0, bands, geom);
-    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, slot_shift);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cell_steps += __shfl_down_sync(0xffffffffu, cell_steps, o);
+    for (int o = 16; o > 0; o >>= 1) { cell_steps += __shfl_down_sync(0xffffffffu, cell_steps, o); moved += __shfl_down_sync(0xffffffffu, moved, o); }
     if ((threadIdx.x & 31) == 0 && cell_steps) atomicAdd(&counters->ray_cell_steps, (unsigned long long)cell_steps);
+    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
+}
+
+// The work list of the fused ray update (see k_ray_update_packed): one item per surviving local particle.
+// Clones (grid still an alias of its source's slot) go to the front, count themselves as readers of their
+// root and become private; particles that own their slot go to the back.
+__global__ void __launch_bounds__(256)
+k_ray_items(const uint32_t* __restrict__ alive_list, const int32_t* __restrict__ slot_of, int32_t* alias_of,
+            uint32_t* __restrict__ readers, RayItem* __restrict__ items, StepCounters* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long n_alive = counters->n_alive;
+    bool live = (unsigned long long)i < n_alive, clone = false;
+    RayItem it{0u, 0, 0, 0u};
+    if (live) {
+        it.particle = alive_list[i];
+        it.slot = slot_of[it.particle];
+        it.root = alias_of[it.slot];
+        clone = it.root != it.slot;
+        if (clone) { atomicAdd(&readers[it.root], 1u); alias_of[it.slot] = it.slot; }
+    }
+    const unsigned mc = __ballot_sync(0xffffffffu, live && clone), mo = __ballot_sync(0xffffffffu, live && !clone);
+    const int lane = threadIdx.x & 31;
+    unsigned long long bc = 0, bo = 0;
+    if (lane == 0) {
+        if (mc) {
+            bc = atomicAdd(&counters->ray_items_front, (unsigned long long)__popc(mc));
+            atomicAdd(&counters->n_mat, (unsigned long long)__popc(mc));
+            atomicAdd(&counters->n_mat_leaders, (unsigned long long)__popc(mc));   // every clone reads its source itself
+        }
+        if (mo) bo = atomicAdd(&counters->ray_items_back, (unsigned long long)__popc(mo));
+    }
+    bc = __shfl_sync(0xffffffffu, bc, 0); bo = __shfl_sync(0xffffffffu, bo, 0);
+    if (live && clone) items[bc + __popc(mc & ((1u << lane) - 1u))] = it;
+    if (live && !clone) items[n_alive - 1ull - (bo + __popc(mo & ((1u << lane) - 1u)))] = it;
+}
+void launch_ray_items(cudaStream_t stream, const uint32_t* alive_list, uint32_t n_local, const int32_t* slot_of,
+                      int32_t* alias_of, uint32_t* readers, RayItem* items, StepCounters* counters) {
+    k_ray_items<<<(n_local + 255) / 256, 256, 0, stream>>>(alive_list, slot_of, alias_of, readers, items, counters);
 }
 
 // =============================================================================== k_sort_beams
@@ -791,21 +1113,57 @@ void launch_sort_beams(cudaStream_t stream, const float* dist, uint32_t n_beams,
     k_sort_beams<<<1, 1024, 0, stream>>>(dist, n_beams, order);
 }
 
+static int ray_packed_radius(int radius_cells) {
+    int radius = radius_cells < 1 ? 1 : (radius_cells > RAY_MAX_RADIUS ? RAY_MAX_RADIUS : radius_cells);
+    while (radius > 1 && (size_t)ray_window_cells_upper_bound_packed(radius) * 2 > (size_t)RAY_MAX_SMEM) radius--;
+    return radius;
+}
+// The fused path needs the packed kernel, whole-grid tiled slots (logical cell = physical cell) and a window
+// that holds every cell a ray can reach (then only a 32nd occupied hit bypasses the window).
+bool ray_update_can_fuse(const MapGeom& geom, uint32_t n_beams, size_t cells_per_grid, bool force_generic, int radius_cells) {
+    return !force_generic && geom.gw % 8u == 0u && cells_per_grid % 8u == 0u && n_beams <= RAY_PACKED_MAX_BEAMS &&
+           geom.tiled != 0u && geom.windowed == 0u && geom.gw < 32768u && geom.gh < 32768u &&
+           ray_packed_radius(radius_cells) >= radius_cells;
+}
+int ray_trace(unsigned long long* out18) {
+#ifdef SLAMRS_RAY_TRACE
+    cudaError_t e = cudaMemcpyFromSymbol(out18, g_ray_trace, sizeof(unsigned long long) * 16);
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out18 + 16, g_ray_trace_items, sizeof(unsigned long long) * 2);
+    unsigned long long z[18] = {0};
+    cudaMemcpyToSymbol(g_ray_trace, z, sizeof(unsigned long long) * 16);
+    cudaMemcpyToSymbol(g_ray_trace_items, z, sizeof(unsigned long long) * 2);
+    return (int)e;
+#else
+    (void)out18;
+    return -1;
+#endif
+}
+size_t ray_spill_scratch_words(int num_sms) { return (size_t)num_sms * 4u * RAY_SPILL_CAP; }   // <= 4 CTAs per SM
+
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
+                              const RayItem* items, const uint32_t* readers, uint32_t* done, uint32_t* spill_scratch,
                               const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
-                              uint64_t* window_cells, bool force_generic) {
+                              uint64_t* window_cells, bool force_generic, int num_sms) {
     int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
     threads = threads < 128 ? 128 : (threads > RAY_MAX_THREADS ? RAY_MAX_THREADS : threads);
     // preferred: the packed 16-bit window (two CTAs per SM at long range)
     if (!force_generic && geom.gw % 8u == 0u && cells_per_grid % 8u == 0u && scan.n_beams <= RAY_PACKED_MAX_BEAMS) {
-        int radius = radius_cells < 1 ? 1 : (radius_cells > RAY_MAX_RADIUS ? RAY_MAX_RADIUS : radius_cells);
-        while (radius > 1 && (size_t)ray_window_cells_upper_bound_packed(radius) * 2 > (size_t)RAY_MAX_SMEM) radius--;
+        const int radius = ray_packed_radius(radius_cells);
         const size_t wmax = (size_t)ray_window_cells_upper_bound_packed(radius);
         *window_cells = wmax;
-        k_ray_update_packed<<<n_local, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, slot_of, cells, meta, bands,
-                                                                  cells_per_grid, radius, radius_cells, counters);
+        // as many CTAs as are resident at once (every CTA must be running for the owners' waits to be safe),
+        // never more than there can be items
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ray_update_packed, threads, wmax * 2);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;   // (the spill scratch is sized for 4 CTAs per SM)
+        uint32_t grid = (uint32_t)(per_sm * num_sms);
+        if (grid > n_local) grid = n_local;
+        k_ray_update_packed<<<grid, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, items, readers, done, spill_scratch,
+                                                                 slot_of, cells, meta, bands, cells_per_grid, radius, radius_cells, counters);
         return cudaSuccess;
     }
     const bool vec = (geom.gw % 4u == 0u) && (cells_per_grid % 4u == 0u);

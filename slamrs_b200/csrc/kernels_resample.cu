@@ -419,6 +419,7 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         counters->clamped = 0ull; counters->saturated = 0ull; counters->spilled = 0ull;
         counters->n_alive = 0ull; counters->copy_bytes = 0ull; counters->copy_max_rows = 0ull;
         counters->n_mat = 0ull; counters->n_mat_leaders = 0ull; counters->ray_cell_steps = 0ull;
+        counters->ray_work_head = 0ull; counters->ray_items_front = 0ull; counters->ray_items_back = 0ull;
     }
     FOLD_STAMP(1);
     // re-associated prefix of the raw weights: the only ordinary scan of the kernel
