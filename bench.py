@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-order-of-work comparison run")
     ap.add_argument("--no-full-copy", action="store_true", help="skip the whole-grid-copy comparison run")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-copy comparison run")
+    ap.add_argument("--no-aged", action="store_true", help="skip the aged-map leg (timed steps after 160 more scans)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] leg of an 8-GPU run")
+    ap.add_argument("--c5-leg", action="store_true", help="run the configs[4] shard leg at any GPU count")
     ap.add_argument("--flags", type=int, default=0, help="slamrs_flags bits for the main run (profiling)")
     ap.add_argument("--shift-x-cells", type=int, default=0, help="experiment: move the map origin by this many cells in x")
     return ap.parse_args()
@@ -199,7 +202,27 @@ def workload_config(wl, n_gpus, n_total):
 
 
 # ------------------------------------------------------------------------------ CUDA arm
-def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2e):
+def state_hash(slam, world, dev):
+    """SHA-256 over what a step leaves behind: the resample index vector, the argmax, the poses of the whole
+    population, the published pose and the published map. Equal hashes = identical filter state."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    idx = slam.resample_indices()
+    poses = torch.from_numpy(slam.poses()).to(dev)
+    if world > 1:
+        parts = [torch.empty_like(poses) for _ in range(world)]
+        dist.all_gather(parts, poses)
+        poses = torch.cat(parts)
+    ep = slam.estimated_pose()
+    m = slam.estimated_likelihood().data          # collective: every rank reads the owner's grid
+    h = hashlib.sha256()
+    h.update(idx.tobytes()); h.update(np.uint64(slam.max_particle).tobytes()); h.update(poses.cpu().numpy().tobytes())
+    h.update(np.array([ep.x, ep.y, ep.theta], np.float32).tobytes()); h.update(m.tobytes())
+    return h.hexdigest()
+
+
+def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2e, do_aged=False):
     """One filter run: W warm-up + K timed device-resident steps (+ K e2e steps). Returns a dict of
     rank-local measurements; the caller reduces over ranks."""
     import torch
@@ -257,6 +280,7 @@ def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2
     out["hist"] = slam.step_history(W, K).astype(np.float64)
     out["stats"] = slam.stats()
     out["grid"] = (slam.grid_w, slam.grid_h)
+    out["state_sha256"] = state_hash(slam, world, dev)
 
     if do_e2e:
         pinned = torch.empty(slam.grid_w * slam.grid_h, dtype=torch.float64).pin_memory()
@@ -266,7 +290,10 @@ def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2
         for obs, odo in scans[W + K:W + 2 * K]:
             slam.update(obs, odo)                  # GridMapSlam::update with HOST scan buffers
             slam.estimated_pose()                  # node.rs:51
-            slam.estimated_likelihood(out_np)      # node.rs:53-57, 8 B/cell map into pinned host memory
+            if rank == 0:
+                slam.estimated_likelihood(out_np)  # node.rs:53-57, 8 B/cell map into pinned host memory
+            else:
+                slam.skip_estimated_likelihood()   # one consumer (the node); the other ranks only take part
         e1.record(stream)
         slam.sync()
         barrier()
@@ -279,13 +306,46 @@ def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2
         for obs, odo in scans[W + 2 * K:W + 3 * K]:   # the trajectory continues: fresh scans
             slam.update(obs, odo)
             slam.estimated_pose()
-            _, w = slam.estimated_likelihood_window(out=pinned32)
-            win_bytes += w.nbytes
+            if rank == 0:
+                _, w = slam.estimated_likelihood_window(out=pinned32)
+                win_bytes += w.nbytes
+            else:
+                slam.skip_estimated_likelihood_window()
         e1.record(stream)
         slam.sync()
         barrier()
         out["ms_e2e_window"] = e0.elapsed_time(e1)
         out["e2e_window_bytes"] = win_bytes / max(1, K)
+    if do_aged:
+        # the same filter after AGED more scans: informed extents and survivor counts have grown
+        base = W + 3 * K if do_e2e else W + K
+        n_more = len(scans) - base - K
+        d_more = []
+        for obs, odo in scans[base:]:
+            a = torch.from_numpy(obs.angle.astype(np.float32)).to(dev)
+            d = torch.from_numpy(obs.distance.astype(np.float32)).to(dev)
+            v = torch.from_numpy(obs.valid.astype(np.uint8)).to(dev)
+            d_more.append((a, d, v, float(obs.distance.max()) if len(obs) else 0.0, odo))
+        torch.cuda.synchronize()
+
+        def more_step(i):
+            a, d, v, maxd, odo = d_more[i]
+            slam.set_scan_device(a.data_ptr(), d.data_ptr(), v.data_ptr(), a.numel(), maxd)
+            slam.step_async(odo)
+        for i in range(n_more):
+            more_step(i)
+        slam.sync()
+        step0 = slam.stats()["step"]
+        barrier()
+        e0.record(stream)
+        for i in range(n_more, n_more + K):
+            more_step(i)
+        e1.record(stream)
+        slam.sync()
+        barrier()
+        hist = slam.step_history(step0, K).astype(np.float64)
+        out["aged"] = {"ms": e0.elapsed_time(e1), "scans_before": int(step0), "extent": slam.map_extent(),
+                       "particles_integrated_per_step": float(hist[:, 4].mean()), "copy_bytes_per_step": float(hist[:, 5].mean())}
     slam.close()
     return out
 
@@ -295,6 +355,7 @@ def run_cuda(args, wl, rank, world, local):
     import torch.distributed as dist
     from slamrs_b200 import nccl_unique_id
     from slamrs_b200 import _lib
+    from slamrs_b200.workloads import WORKLOADS
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the CUDA arm has no CPU fallback")
@@ -316,16 +377,18 @@ def run_cuda(args, wl, rank, world, local):
     n_total = wl.n_particles * world
     K, W = args.steps, args.warmup
     sim = wl.simulator()
-    scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(W + 3 * K)]
+    AGED = 160
+    do_aged = not args.no_aged
+    scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(W + 3 * K + ((AGED + K) if do_aged else 0))]
 
     clocks = ClockSampler(local)
     clocks.start()
-    main = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans, args.flags, not args.no_e2e)
+    main = measure_cuda(args, wl, rank, world, local, dev, fresh_nccl_id(), scans, args.flags, not args.no_e2e, do_aged)
     clock_info = clocks.stop()
     full = None
-    # the two comparison modes are single-GPU diagnostics; the scaling runs time the product path only
+    # eager / strict are single-GPU diagnostics; the whole-grid-copy leg (the reference's bytes, what the north
+    # star's "% of aggregate HBM roofline" describes) also runs sharded
     if world > 1:
-        args.no_full_copy = True
         args.no_strict = True
         args.no_eager = True
     if not args.no_full_copy:
@@ -351,14 +414,39 @@ def run_cuda(args, wl, rank, world, local):
         return t.cpu().numpy()
 
     ph = main["phase_ms"]
+    # configs[4] (262,144 x 720 x 2048^2 on 8 GPUs, windowed 512^2 slots, uniform start poses): its own leg
+    c5 = None
+    if (world == 8 and not args.no_c5) or args.c5_leg:
+        wl5 = WORKLOADS["c5"]
+        sim5 = wl5.simulator()
+        scans5 = [sim5.next_scan(wl5.speed_left, wl5.speed_right) for _ in range(W + K)]
+        clocks5 = ClockSampler(local)
+        clocks5.start()
+        c5 = measure_cuda(args, wl5, rank, world, local, dev, fresh_nccl_id(), scans5, 0, False)
+        c5["clocks"] = clocks5.stop()
+
+    # identical state in every mode, or the numbers mean nothing
+    hashes = {"default": main["state_sha256"]}
+    for name, leg in (("full_grid_copy", full), ("eager_copy", eager), ("strict_order_of_work", strict)):
+        if leg:
+            hashes[name] = leg["state_sha256"]
+    parity_ok = len(set(hashes.values())) == 1
+
     tmax = reduce_max([main["ms_value"], main.get("ms_e2e", 0.0), strict["ms_value"] if strict else 0.0] +
                       [ph[k] for k in _lib.PHASES] + [full["ms_value"] if full else 0.0, main.get("ms_e2e_window", 0.0),
-                                                      eager["ms_value"] if eager else 0.0])
+                                                      eager["ms_value"] if eager else 0.0,
+                                                      main["aged"]["ms"] if "aged" in main else 0.0,
+                                                      c5["ms_value"] if c5 else 0.0,
+                                                      full["phase_ms"]["copy"] if full else 0.0])
     hist = main["hist"]
-    tot = reduce_sum([hist[:, 0].sum(), hist[:, 1].sum(), hist[:, 4].sum()])
+    tot = reduce_sum([hist[:, 0].sum(), hist[:, 1].sum(), hist[:, 4].sum(),
+                      float(full["hist"][:, 5].sum()) if full else 0.0, float(hist[:, 5].sum()), 8.0 * float(hist[:, 6].sum()),
+                      float(c5["hist"][:, 5].sum() + 8.0 * c5["hist"][:, 6].sum()) if c5 else 0.0])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if not parity_ok:
+            raise SystemExit(3)
         return
 
     peak, peak_src = measured_peaks()
@@ -424,6 +512,29 @@ def run_cuda(args, wl, rank, world, local):
         line["roofline"] = dict(line["roofline_copy"], step_frac=(copy_bytes / (ms_value * 1e-3) / 1e9) / peak if peak else None)
         line["roofline_ray_update"] = ray_roofline
     line["deferred_copies"] = bool(deferred)
+    line["parity_check"] = {"ok": parity_ok, "state_sha256": hashes,
+                            "what": "sha256 over resample indices, argmax, all poses, published pose and published map after the "
+                                    "timed steps; every mode must leave the same state (non-zero exit otherwise)"}
+    # the whole step against the aggregate roofline of the GPUs it ran on
+    line["roofline"]["step_frac_aggregate"] = ((float(tot[4]) + float(tot[5])) / (ms_value * 1e-3) / 1e9) / (peak * world) if peak else None
+    if "aged" in main:
+        ms_aged = float(tmax[6 + len(_lib.PHASES)])
+        line["aged_map"] = {"value": pbu * K / (ms_aged * 1e-3), "unit": UNIT, "ms_per_step": ms_aged / K,
+                            "scans_before": main["aged"]["scans_before"], "informed_extent_cells": main["aged"]["extent"],
+                            "particles_integrated_per_step_rank0": main["aged"]["particles_integrated_per_step"],
+                            "copy_bytes_per_step_rank0": main["aged"]["copy_bytes_per_step"],
+                            "note": "the same filter after 160 more scans of the trajectory: informed extents and survivor "
+                                    "counts have grown"}
+    if c5:
+        ms_c5 = float(tmax[7 + len(_lib.PHASES)])
+        n5 = WORKLOADS["c5"].n_particles * world
+        line["configs4_leg"] = {
+            "value": n5 * WORKLOADS["c5"].n_beams * K / (ms_c5 * 1e-3), "unit": UNIT, "ms_per_step": ms_c5 / K,
+            "config": workload_config(WORKLOADS["c5"], world, n5), "clocks": c5["clocks"], "state_sha256": c5["state_sha256"],
+            "step_frac_aggregate": (float(tot[6]) / (ms_c5 * 1e-3) / 1e9) / (peak * world) if peak else None,
+            "phases_ms_per_step_rank0": {k: v / K for k, v in c5["phase_ms"].items()},
+            "note": "BASELINE.json configs[4] (one 32,768-particle shard per GPU, 512x512 windowed slots of the 2048^2 grid, "
+                    "uniform start poses); complete at 8 GPUs"}
     if "ms_e2e" in main:
         gw, gh = main["grid"]
         line["e2e"] = {"value": pbu * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
@@ -443,8 +554,11 @@ def run_cuda(args, wl, rank, world, local):
             "value": pbu * K / (ms_full * 1e-3), "unit": UNIT, "ms_per_step": ms_full / K,
             "note": "SLAMRS_FLAG_FULL_GRID_COPY: every resampling copy moves the whole W*H grid, as Map::clone does "
                     "(particle.rs:97-100); identical results",
-            "roofline": dict(copy_roofline(fbytes, fph["copy"], "k_copy"),
-                             step_frac=(fbytes / (ms_full * 1e-3) / 1e9) / peak if peak else None),
+            "roofline": dict(copy_roofline(fbytes, float(tmax[8 + len(_lib.PHASES)]) if world > 1 else fph["copy"], "k_copy"),
+                             step_frac=(fbytes / (ms_full * 1e-3) / 1e9) / peak if peak else None,
+                             step_frac_aggregate=(float(tot[3]) / (ms_full * 1e-3) / 1e9) / (peak * world) if peak else None,
+                             note="step_frac_aggregate = bytes all ranks moved per step / step time / (n_gpus x measured HBM "
+                                  "peak): the north star's '% of aggregate HBM roofline per SLAM step'"),
             "phases_ms_per_step": {k: v / K for k, v in fph.items()}}
     if eager:
         ms_eager = float(tmax[5 + len(_lib.PHASES)])
@@ -470,14 +584,23 @@ def run_cuda(args, wl, rank, world, local):
         n_cpu = args.cpu_particles or max(cores * 8, 64)
         res = time_oracle(O, wl, n_cpu, steps=6, warmup=2, threads=cores)
         res1 = time_oracle(O, wl, max(16, n_cpu // 8), steps=4, warmup=1, threads=1)
+        resd = time_oracle(O, wl, max(16, n_cpu // 8), steps=3, warmup=1, threads=1, dead_likelihood=True)
         line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": res["sample"], "single_thread_value": res1["value"],
                                 "single_thread_sample": res1["sample"],
-                                "note": "C restatement of the Rust reference (no Rust toolchain in the image); the "
-                                        "reference itself is single-threaded"}
+                                "single_thread_with_dead_likelihood_value": resd["value"],
+                                "single_thread_with_dead_likelihood_sample": resd["sample"],
+                                "note": "C restatement of the Rust reference (no Rust toolchain in the image). The reference "
+                                        "itself is single-threaded (particle.rs:32-35) and, unless rustc elides it, also runs "
+                                        "the dead Map::likelihood() transform per particle (slam.rs:58): the two single_thread "
+                                        "values bracket it. `value` (all host threads, no dead transform) is the generous "
+                                        "figure and the one the --impl reference arm reports, i.e. what the driver's "
+                                        "vs_reference ratio divides by"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit("bench.py: the comparison modes left different filter states: " + json.dumps(hashes))
 
 
 def ncu_traffic(name, bytes_per_launch):

@@ -175,8 +175,10 @@ int slamrs_gpu_set_scan_device(slamrs_gpu_handle* h, const float* angle_device, 
 int slamrs_gpu_pose(slamrs_gpu_handle* h, float out_xyt[3]);
 
 /* GridMapSlam::estimated_likelihood, slam.rs:83-88 -> grid_w*grid_h probabilities (f64), the
- * payload of GridMapMessage.data (node.rs:68-72). Collective when world_size>1 (the owning GPU
- * broadcasts); every rank receives the map. */
+ * payload of GridMapMessage.data (node.rs:68-72). Collective when world_size>1: every rank calls it
+ * (one barrier); a rank that passes a buffer converts the estimate straight out of the owning GPU's
+ * pool over NVLink, a rank that passes NULL takes part without receiving the map (the reference has
+ * one consumer, node.rs:53-57). */
 int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells);
 
 /* Cheaper forms of the same read-out for consumers that do not need 8 bytes per cell of the whole
@@ -184,7 +186,8 @@ int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells);
  * baseui/src/node/visualize.rs:245-256). map_extent returns the informed extent [x0,x1) x [y0,y1)
  * of the estimate's grid in cells (x0, x1 multiples of 8; all zeros while the map is empty): every
  * cell outside it is exactly at the prior, 0.5. map_window exports the window [x0,x1) x [y0,y1),
- * row-major, as f64, f32 or u8 = round(255 p). Collective when world_size>1. */
+ * row-major, as f64, f32 or u8 = round(255 p). Collective when world_size>1 (map_window: out may be NULL
+ * on ranks that only take part). */
 enum slamrs_map_format { SLAMRS_MAP_F64 = 0, SLAMRS_MAP_F32 = 1, SLAMRS_MAP_U8 = 2 };
 int slamrs_gpu_map_extent(slamrs_gpu_handle* h, int32_t out_x0y0x1y1[4]);
 int slamrs_gpu_map_window(slamrs_gpu_handle* h, uint32_t format, int32_t x0, int32_t y0, int32_t x1, int32_t y1,

@@ -42,12 +42,13 @@ struct slamrs_gpu_handle {
     // [SlotMeta x 2*n_local | ParticleResult x n_total | barrier flags | grid slots]
     void* d_pool = nullptr;
     size_t pool_header = 0;      // bytes in front of the first grid slot
-    size_t off_results = 0, off_flags = 0, off_bands = 0;
+    size_t off_results = 0, off_flags = 0, off_bands = 0, off_counters = 0;
     uint32_t* d_bands = nullptr;                 // band extents, n_bands entries per slot (inside the pool header)
     uint32_t n_bands = 0;
     uint32_t** d_peer_bands = nullptr;           // device array [world]
     unsigned long long* d_flags = nullptr;       // PEER_MAX_WORLD epochs, written by the peers
     ParticleResult** d_peer_results = nullptr;   // device array [world]
+    std::vector<StepCounters*> peer_counters;    // host array [world]: every rank's step counters (inside its pool)
     unsigned long long** d_peer_flags = nullptr; // device array [world]
     unsigned long long barrier_epoch = 0;
     unsigned long long barrier_timeout_ns = 60000000000ull;   // SLAMRS_BARRIER_TIMEOUT_MS overrides
@@ -94,6 +95,8 @@ struct slamrs_gpu_handle {
     uint32_t** d_peer_cells = nullptr;         // device array [world]
     SlotMeta** d_peer_meta = nullptr;          // device array [world]
     std::vector<void*> ipc_opened;             // peer mappings to close
+    std::vector<uint32_t*> host_peer_cells;    // host copies of d_peer_cells / d_peer_meta
+    std::vector<SlotMeta*> host_peer_meta;
     StepRecord* d_history = nullptr;
     bool scan_external = false;
     const float* ext_angle = nullptr;
@@ -218,7 +221,10 @@ int setup_peers(slamrs_gpu_handle* h) {
         pres[r] = (ParticleResult*)(peers[r] + h->off_results);
         pflags[r] = (unsigned long long*)(peers[r] + h->off_flags);
         pbands[r] = (uint32_t*)(peers[r] + h->off_bands);
+        h->peer_counters[r] = (StepCounters*)(peers[r] + h->off_counters);
     }
+    h->host_peer_cells = pcells;
+    h->host_peer_meta = pmeta;
     CU_TRY(h, cudaMalloc(&h->d_peer_bands, sizeof(uint32_t*) * W));
     CU_TRY(h, cudaMemcpy(h->d_peer_bands, pbands.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMalloc(&h->d_peer_results, sizeof(ParticleResult*) * W));
@@ -267,7 +273,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_copies); cudaFree(h->d_leaders); cudaFree(h->d_alive); cudaFree(h->d_jobs);
     cudaFree(h->d_ray_items); cudaFree(h->d_readers); cudaFree(h->d_ray_spill);
     cudaFree(h->d_alias); cudaFree(h->d_mat_items); cudaFree(h->d_mat_leaders); cudaFree(h->d_mat_roots);
-    cudaFree(h->d_counters); cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells); cudaFree(h->d_peer_meta);
+    cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells); cudaFree(h->d_peer_meta);
     cudaFree(h->d_peer_results); cudaFree(h->d_peer_flags); cudaFree(h->d_peer_bands);
     cudaFree(h->d_history);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -512,7 +518,9 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     h->off_flags = (h->off_results + 2 * sizeof(ParticleResult) * (size_t)h->n_total + 255) & ~(size_t)255;
     h->n_bands = bands_per_slot(h->geom);
     h->off_bands = (h->off_flags + sizeof(unsigned long long) * 2 * PEER_MAX_WORLD + 255) & ~(size_t)255;   // epochs | goodbyes
-    h->pool_header = (h->off_bands + sizeof(uint32_t) * 2 * (size_t)h->n_local * h->n_bands + 4095) & ~(size_t)4095;
+    // the step counters live in the header too: a peer that reads out the published map finds the estimate's slot there
+    h->off_counters = (h->off_bands + sizeof(uint32_t) * 2 * (size_t)h->n_local * h->n_bands + 255) & ~(size_t)255;
+    h->pool_header = (h->off_counters + sizeof(StepCounters) + 4095) & ~(size_t)4095;
     CREATE_CU(cudaMalloc(&h->d_pool, h->pool_header + (size_t)h->n_slots * grid_bytes));
     h->d_meta = (SlotMeta*)h->d_pool;
     h->d_cells = (uint32_t*)((char*)h->d_pool + h->pool_header);
@@ -520,6 +528,9 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     h->d_results = h->d_results_base;
     h->d_flags = (unsigned long long*)((char*)h->d_pool + h->off_flags);
     h->d_bands = (uint32_t*)((char*)h->d_pool + h->off_bands);
+    h->d_counters = (StepCounters*)((char*)h->d_pool + h->off_counters);
+    h->peer_counters.assign(h->world, nullptr);
+    h->peer_counters[h->rank] = h->d_counters;
     h->p2p_exchange = h->world > 1 && (cfg->flags & SLAMRS_FLAG_NCCL_EXCHANGE) == 0;
     CREATE_CU(cudaMemsetAsync(h->d_pool, 0, h->pool_header + (size_t)h->n_slots * grid_bytes, h->stream));  // ln(0.5/0.5) = 0
     h->boxed_copy = (cfg->flags & SLAMRS_FLAG_FULL_GRID_COPY) == 0 && cfg->grid_w % 8u == 0u && h->geom.pw % 8u == 0u;
@@ -554,7 +565,6 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_ray_items, sizeof(RayItem) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_readers, sizeof(uint32_t) * 2 * (size_t)h->n_slots));
     CREATE_CU(cudaMalloc(&h->d_ray_spill, sizeof(uint32_t) * ray_spill_scratch_words(h->num_sms)));
-    CREATE_CU(cudaMalloc(&h->d_counters, sizeof(StepCounters)));
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
     memset(h->h_counters, 0, sizeof(StepCounters));
     CREATE_CU(cudaMalloc(&h->d_export, sizeof(double) * h->n_cells));
@@ -874,18 +884,24 @@ int export_window(slamrs_gpu_handle* h, uint32_t format, int x0, int y0, int x1,
     if (x0 < 0 || y0 < 0 || x1 > (int)h->geom.gw || y1 > (int)h->geom.gh || x1 < x0 || y1 < y0)
         return fail(h, SLAMRS_E_INVALID_ARG, "map window outside the grid");
     const size_t n = (size_t)(x1 - x0) * (size_t)(y1 - y0);
-    if (n == 0) return SLAMRS_OK;
+    if (n == 0 && h->world == 1) return SLAMRS_OK;
     const size_t bytes = n * (format == SLAMRS_MAP_F64 ? 8u : (format == SLAMRS_MAP_F32 ? 4u : 1u));
     cudaStream_t s = h->stream;
-    launch_export(s, h->d_cells, h->d_meta, h->cells_per_grid, h->d_counters, h->geom, x0, y0, x1, y1, (int)format, h->d_export);
-    h->launches++;
     if (h->world > 1) {
-        int rc = fetch_counters(h);  // root = owner of the estimate, identical on every rank
+        // The estimate's grid lives on one GPU. After a barrier (its step, pulls included, is complete) the rank
+        // that asked converts it straight out of the owner's pool over NVLink: no broadcast, one D2H copy.
+        int rc = fetch_counters(h);  // owner of the estimate, identical on every rank
         if (rc) return rc;
-        std::string err;
-        if (comm_broadcast(h->comm, h->d_export, bytes, (int)h->h_counters->est_owner, s, &err))
-            return fail(h, SLAMRS_E_NCCL, err);
+        rc = step_barrier(h);
+        if (rc) return rc;
+        if (out == nullptr) return SLAMRS_OK;   // took part, does not want the map
+        const uint32_t owner = (uint32_t)h->h_counters->est_owner;
+        launch_export(s, h->host_peer_cells[owner], h->host_peer_meta[owner], h->cells_per_grid, h->peer_counters[owner], h->geom,
+                      x0, y0, x1, y1, (int)format, h->d_export);
+    } else {
+        launch_export(s, h->d_cells, h->d_meta, h->cells_per_grid, h->d_counters, h->geom, x0, y0, x1, y1, (int)format, h->d_export);
     }
+    h->launches++;
     CU_TRY(h, cudaMemcpyAsync(out, h->d_export, bytes, cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaStreamSynchronize(s));
     CU_TRY(h, cudaGetLastError());
@@ -894,7 +910,7 @@ int export_window(slamrs_gpu_handle* h, uint32_t format, int x0, int y0, int x1,
 }  // namespace
 
 int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells) {
-    if (!h || !out_cells) return SLAMRS_E_INVALID_ARG;
+    if (!h || (!out_cells && h->world == 1)) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     return export_window(h, SLAMRS_MAP_F64, 0, 0, (int)h->geom.gw, (int)h->geom.gh, out_cells);
 }
@@ -910,15 +926,17 @@ int slamrs_gpu_map_extent(slamrs_gpu_handle* h, int32_t out_x0y0x1y1[4]) {
     }
     cudaStream_t s = h->stream;
     int* d4 = reinterpret_cast<int*>(h->d_export);
-    launch_estimate_extent(s, h->d_meta, h->d_counters, d4);
-    h->launches++;
     if (h->world > 1) {
         int rc = fetch_counters(h);
         if (rc) return rc;
-        std::string err;
-        if (comm_broadcast(h->comm, d4, 4 * sizeof(int), (int)h->h_counters->est_owner, s, &err))
-            return fail(h, SLAMRS_E_NCCL, err);
+        rc = step_barrier(h);
+        if (rc) return rc;
+        const uint32_t owner = (uint32_t)h->h_counters->est_owner;
+        launch_estimate_extent(s, h->host_peer_meta[owner], h->peer_counters[owner], d4);
+    } else {
+        launch_estimate_extent(s, h->d_meta, h->d_counters, d4);
     }
+    h->launches++;
     CU_TRY(h, cudaMemcpyAsync(out_x0y0x1y1, d4, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaStreamSynchronize(s));
     return SLAMRS_OK;
@@ -926,7 +944,7 @@ int slamrs_gpu_map_extent(slamrs_gpu_handle* h, int32_t out_x0y0x1y1[4]) {
 
 int slamrs_gpu_map_window(slamrs_gpu_handle* h, uint32_t format, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
                           void* out) {
-    if (!h || !out) return SLAMRS_E_INVALID_ARG;
+    if (!h || (!out && h->world == 1)) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     return export_window(h, format, x0, y0, x1, y1, out);
 }

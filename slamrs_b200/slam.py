@@ -226,6 +226,15 @@ class GridMapSlam:
         _lib.check(self._L.slamrs_gpu_map_probability(self._h, _ptr(out)), self._h)
         return GridData((self.grid_w, self.grid_h), out)
 
+    def skip_estimated_likelihood(self) -> None:
+        """Multi-GPU: take part in the other ranks' estimated_likelihood() without receiving the map."""
+        _lib.check(self._L.slamrs_gpu_map_probability(self._h, None), self._h)
+
+    def skip_estimated_likelihood_window(self) -> None:
+        """Multi-GPU: take part in the other ranks' estimated_likelihood_window() (extent + window) without the map."""
+        self.map_extent()
+        _lib.check(self._L.slamrs_gpu_map_window(self._h, _lib.MAP_F32, 0, 0, 0, 0, None), self._h)
+
     def map_extent(self):
         """(x0, y0, x1, y1): informed extent of the estimate's grid in cells; all zero for an empty map."""
         out = np.zeros(4, np.int32)
