@@ -419,6 +419,9 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     if (cfg->n_particles == 0)  // ParticleFilter::new asserts, particle.rs:16
         return fail(nullptr, SLAMRS_E_INVALID_ARG, "Must have at least one particle");
     if (cfg->world_size > PEER_MAX_WORLD) return fail(nullptr, SLAMRS_E_INVALID_ARG, "world_size above 64");
+    // the fused exchange stores one record per lane of the likelihood warp: at most 32 peers
+    if (cfg->world_size > 32u && (cfg->flags & SLAMRS_FLAG_NCCL_EXCHANGE) == 0)
+        return fail(nullptr, SLAMRS_E_INVALID_ARG, "world_size above 32 needs SLAMRS_FLAG_NCCL_EXCHANGE (the peer-store exchange serves 32 GPUs)");
     if (cfg->world_size == 0 || cfg->rank >= cfg->world_size || cfg->n_particles % cfg->world_size != 0)
         return fail(nullptr, SLAMRS_E_INVALID_ARG, "bad rank/world_size or n_particles not divisible by world_size");
     if (cfg->n_particles > 0x7fffffffull) return fail(nullptr, SLAMRS_E_INVALID_ARG, "too many particles");
@@ -562,7 +565,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_mat_leaders, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_mat_roots, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_alive, sizeof(uint32_t) * h->n_local));
-    CREATE_CU(cudaMalloc(&h->d_ray_items, sizeof(RayItem) * h->n_local));
+    CREATE_CU(cudaMalloc(&h->d_ray_items, sizeof(RayItem) * 2 * (size_t)h->n_local));   // clones | owners
     CREATE_CU(cudaMalloc(&h->d_readers, sizeof(uint32_t) * 2 * (size_t)h->n_slots));
     CREATE_CU(cudaMalloc(&h->d_ray_spill, sizeof(uint32_t) * ray_spill_scratch_words(h->num_sms)));
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
@@ -703,6 +706,11 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     const uint32_t res_off = (uint32_t)(h->step & 1ull) * h->n_total;
     h->d_results = h->d_results_base + res_off;
 
+    const bool force_generic = (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0;
+    const bool fuse = h->defer && !all_particles &&
+                      ray_update_can_fuse(h->geom, h->n_beams, h->cells_per_grid, force_generic, h->radius_cells);
+    if (fuse)   // per-slot reader / done counters of the fused ray update (off the critical path: long before their use)
+        CU_TRY(h, cudaMemsetAsync(h->d_readers, 0, sizeof(uint32_t) * 2 * (size_t)h->n_slots, s));
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->defer ? h->d_alias : nullptr, h->d_cells, h->d_meta, h->cells_per_grid,
@@ -728,24 +736,19 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 2);
     // (k_weights also zeroes the per-step counters)
     launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_fold, h->d_counters);
+    // 3b. deferred copies: the clones among the particles about to be written get their own cells. Either the
+    //     ray kernel does it while it integrates the scan (fused: k_resample_indices lists the survivors as
+    //     clones | owners, no copy kernels), or they are listed now and copied after PROF_MARK 3. Before the
+    //     planner starts: both write the alias table.
+    RayLists ray{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (fuse) ray = RayLists{h->d_ray_items, h->d_ray_items + h->n_local, h->d_slot[cur], h->d_alias, h->d_readers};
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
-                            h->d_idx, h->d_pose[nxt], h->first, h->n_local, !all_particles, h->d_alive, h->d_counters);
+                            h->d_idx, h->d_pose[nxt], h->first, h->n_local, !all_particles, h->d_alive, ray, h->d_counters);
     if (all_particles) {
         launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local, true, h->d_alive, h->d_counters);
         h->launches++;
     }
-    // 3b. deferred copies: the clones among the particles about to be written get their own cells. Either the
-    //     ray kernel does it while it integrates the scan (fused: work list with the clones in front, no copy
-    //     kernels), or they are listed now and copied after PROF_MARK 3. Before the planner starts: both write
-    //     the alias table.
-    const bool force_generic = (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0;
-    const bool fuse = h->defer && !all_particles &&
-                      ray_update_can_fuse(h->geom, h->n_beams, h->cells_per_grid, force_generic, h->radius_cells);
-    if (fuse) {
-        CU_TRY(h, cudaMemsetAsync(h->d_readers, 0, sizeof(uint32_t) * 2 * (size_t)h->n_slots, s));
-        launch_ray_items(s, h->d_alive, h->n_local, h->d_slot[cur], h->d_alias, h->d_readers, h->d_ray_items, h->d_counters);
-        h->launches++;
-    } else if (h->defer) {
+    if (h->defer && !fuse) {
         if (all_particles)   // every clone: ordered list with fan-out sub-runs
             launch_materialize_list(s, nullptr, h->n_total, h->first, h->n_local, h->d_slot[cur], h->d_alias, h->d_cells,
                                     h->cells_per_grid, h->d_meta, h->d_bands, h->n_bands, h->d_mat_items, h->d_mat_leaders,
@@ -792,7 +795,8 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         h->order_pending = false;
     }
     CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive,
-                                fuse ? h->d_ray_items : nullptr, fuse ? h->d_readers : nullptr,
+                                fuse ? h->d_ray_items : nullptr, fuse ? h->d_ray_items + h->n_local : nullptr,
+                                fuse ? h->d_readers : nullptr,
                                 fuse ? h->d_readers + h->n_slots : nullptr, h->d_ray_spill, h->d_slot[cur],
                                 h->d_cells, h->d_meta, h->d_bands, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
                                 force_generic, h->num_sms));
@@ -1332,7 +1336,8 @@ int slamrs_gpu_debug_resample(int device, const double* raw_weights, uint32_t n,
         cudaEventRecord(ev[0], nullptr);
         launch_weights(nullptr, res.p, n, wn.p, cum.p, fold.p, cnt.p);
         cudaEventRecord(ev[1], nullptr);
-        launch_resample_indices(nullptr, res.p, cum.p, n, u.p, 0, 0, idx.p, nullptr, 0, 0, false, nullptr, cnt.p);
+        launch_resample_indices(nullptr, res.p, cum.p, n, u.p, 0, 0, idx.p, nullptr, 0, 0, false, nullptr,
+                                RayLists{nullptr, nullptr, nullptr, nullptr, nullptr}, cnt.p);
         cudaEventRecord(ev[2], nullptr);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { for (auto& x : ev) cudaEventDestroy(x); return fail(nullptr, SLAMRS_E_CUDA, cudaGetErrorString(e)); }

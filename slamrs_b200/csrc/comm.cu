@@ -1,6 +1,7 @@
 #include "comm.h"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <nccl.h>
 #include <mutex>
 
@@ -24,13 +25,18 @@ NcclApi* nccl_api() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
-        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        // SLAMRS_NCCL_LIB (tests): load this library instead, e.g. a path that does not exist
+        const char* forced = getenv("SLAMRS_NCCL_LIB");
+        const char* names[] = {forced ? forced : "libnccl.so.2", forced ? forced : "libnccl.so"};
+        std::string first_error;
         for (const char* n : names) {
             api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
             if (api.lib) break;
+            const char* e = dlerror();   // (a second dlerror() call returns NULL: read it once)
+            if (first_error.empty()) first_error = e ? e : "?";
         }
         if (!api.lib) {
-            api.load_error = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?");
+            api.load_error = std::string("dlopen(") + names[0] + ") failed: " + first_error;
             return;
         }
 #define SLAMRS_SYM(field, name)                                                   \

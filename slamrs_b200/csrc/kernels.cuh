@@ -108,6 +108,20 @@ struct CopyItem {
     uint32_t* dst_bands;       // band extents of the destination slot
 };
 
+// One work item of the ray update: a surviving local particle, its slot and the slot whose cells it
+// logically holds (root != slot: a clone that k_ray_update_packed makes private while it integrates the scan)
+struct RayItem { uint32_t particle; int32_t slot; int32_t root; uint32_t pad; };
+// Work lists of the fused ray update, filled by k_resample_indices: clones first (counters->ray_items_front of
+// them), then the particles that own their slot (counters->ray_items_back); readers[root]++ per clone (zeroed by
+// the caller); every listed clone's alias entry becomes the identity and counters->n_mat counts them.
+// clones == nullptr: plain survivor list (alive_list) instead.
+struct RayLists {
+    RayItem* clones;
+    RayItem* owners;
+    const int32_t* slot_of;
+    int32_t* alias_of;
+    uint32_t* readers;
+};
 // ---- launch wrappers (all asynchronous on `stream`) ----
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
                               const float* pose_cur, const int32_t* slot_of, const int32_t* alias_of /* may be null */,
@@ -127,24 +141,18 @@ void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_fl
 void launch_peer_goodbye(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
                          uint32_t rank, uint32_t world, unsigned long long timeout_ns, StepCounters* counters);
 
-// One work item of the ray update: a surviving local particle, its slot and the slot whose cells it
-// logically holds (root != slot: a clone that k_ray_update_packed makes private while it integrates the scan)
-struct RayItem { uint32_t particle; int32_t slot; int32_t root; uint32_t pad; };
 // the fused path applies (packed window kernel, whole-grid tiled slots)
 bool ray_update_can_fuse(const MapGeom& geom, uint32_t n_beams, size_t cells_per_grid, bool force_generic, int radius_cells);
 size_t ray_spill_scratch_words(int num_sms);
 int ray_trace(unsigned long long* out18);   // tuning builds (-DSLAMRS_RAY_TRACE): cycles per phase, summed over CTAs   // scratch of the fused path (uint32 words)
-// items[0 .. counters->n_alive): clones first, slot owners last; readers[root]++ per clone (zeroed by the caller);
-// every listed clone's alias entry becomes the identity and counters->n_mat counts them
-void launch_ray_items(cudaStream_t stream, const uint32_t* alive_list, uint32_t n_local, const int32_t* slot_of,
-                      int32_t* alias_of, uint32_t* readers, RayItem* items, StepCounters* counters);
 // returns the shared-memory window size in cells through *window_cells
-// alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive); with `items`
-// (launch_ray_items) the packed kernel fuses the clones' copies into its write-back (readers / done: per-slot
-// counters, zeroed by the caller before launch_ray_items)
+// alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive); with the work
+// lists of RayLists (clones, owners) the packed kernel fuses the clones' copies into its write-back (readers /
+// done: per-slot counters, zeroed by the caller before launch_resample_indices)
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
-                              const RayItem* items, const uint32_t* readers, uint32_t* done, uint32_t* spill_scratch,
+                              const RayItem* clones, const RayItem* owners, const uint32_t* readers, uint32_t* done,
+                              uint32_t* spill_scratch,
                               const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic, int num_sms);
@@ -158,8 +166,8 @@ int weights_trace(long long* out64);   // tuning builds (-DSLAMRS_FOLD_TRACE): c
 void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
                              uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,
                              uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
-                             bool build_alive /* also append the surviving local particles to alive_list */,
-                             uint32_t* alive_list, StepCounters* counters);
+                             bool build_alive /* also list the surviving local particles */,
+                             uint32_t* alive_list, RayLists ray, StepCounters* counters);
 
 struct PlanArgs {
     const ParticleResult* results;  // N, after the all-gather (carries every particle's physical slot)

@@ -794,8 +794,7 @@ __device__ __noinline__ void ray_fused_writeback(const MapGeom& geom, int32_t sl
 // tiles, adds the window, writes its OWN slot (and clears what the slot's previous tenant had informed
 // outside the new extent). The copy kernels and their pass over the grids disappear from the step.
 // The hazard is the root's owner integrating the scan in place while a clone still reads the root:
-// k_ray_items puts the clones at the front of the list and the particles that own their slot at the
-// back, counts the clones per root (readers[]), every clone announces when it has read its root
+// k_resample_indices lists the clones first and the particles that own their slot after them, counts the clones per root (readers[]), every clone announces when it has read its root
 // (done[]), and an owner waits for its readers before it writes. Items are popped in list order by CTAs
 // that are all resident, so every reader an owner waits for is already running: no deadlock.
 struct RayJob {      // what a CTA works on, resolved once per item
@@ -805,7 +804,7 @@ struct RayJob {      // what a CTA works on, resolved once per item
 
 __global__ void __maxnreg__(80)   // 2 CTAs of 384 threads per SM; blocks have at most RAY_MAX_THREADS threads
 k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
-                    const uint32_t* __restrict__ alive_list, const RayItem* __restrict__ items,
+                    const uint32_t* __restrict__ alive_list, const RayItem* __restrict__ clones, const RayItem* __restrict__ owners,
                     const uint32_t* __restrict__ readers, uint32_t* __restrict__ done, uint32_t* __restrict__ spill_scratch,
                     const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
                     uint32_t* __restrict__ bands_all, size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
@@ -838,7 +837,11 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         const unsigned long long item = s_next;
         if (item >= n_items) break;
         RayJob job;
-        if (items) { const RayItem it = items[item]; job.particle = it.particle; job.slot = it.slot; job.root = it.root; }
+        if (clones) {   // clones first: an owner is popped only after every clone that reads its slot
+            const unsigned long long n_clones = counters->ray_items_front;
+            const RayItem it = item < n_clones ? clones[item] : owners[item - n_clones];
+            job.particle = it.particle; job.slot = it.slot; job.root = it.root;
+        }
         else { job.particle = alive_list[item]; job.slot = slot_of[job.particle]; job.root = job.slot; }
         const bool fused = job.root != job.slot;
         const uint32_t p = job.particle;
@@ -1039,43 +1042,6 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
 }
 
-// The work list of the fused ray update (see k_ray_update_packed): one item per surviving local particle.
-// Clones (grid still an alias of its source's slot) go to the front, count themselves as readers of their
-// root and become private; particles that own their slot go to the back.
-__global__ void __launch_bounds__(256)
-k_ray_items(const uint32_t* __restrict__ alive_list, const int32_t* __restrict__ slot_of, int32_t* alias_of,
-            uint32_t* __restrict__ readers, RayItem* __restrict__ items, StepCounters* counters) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long n_alive = counters->n_alive;
-    bool live = (unsigned long long)i < n_alive, clone = false;
-    RayItem it{0u, 0, 0, 0u};
-    if (live) {
-        it.particle = alive_list[i];
-        it.slot = slot_of[it.particle];
-        it.root = alias_of[it.slot];
-        clone = it.root != it.slot;
-        if (clone) { atomicAdd(&readers[it.root], 1u); alias_of[it.slot] = it.slot; }
-    }
-    const unsigned mc = __ballot_sync(0xffffffffu, live && clone), mo = __ballot_sync(0xffffffffu, live && !clone);
-    const int lane = threadIdx.x & 31;
-    unsigned long long bc = 0, bo = 0;
-    if (lane == 0) {
-        if (mc) {
-            bc = atomicAdd(&counters->ray_items_front, (unsigned long long)__popc(mc));
-            atomicAdd(&counters->n_mat, (unsigned long long)__popc(mc));
-            atomicAdd(&counters->n_mat_leaders, (unsigned long long)__popc(mc));   // every clone reads its source itself
-        }
-        if (mo) bo = atomicAdd(&counters->ray_items_back, (unsigned long long)__popc(mo));
-    }
-    bc = __shfl_sync(0xffffffffu, bc, 0); bo = __shfl_sync(0xffffffffu, bo, 0);
-    if (live && clone) items[bc + __popc(mc & ((1u << lane) - 1u))] = it;
-    if (live && !clone) items[n_alive - 1ull - (bo + __popc(mo & ((1u << lane) - 1u)))] = it;
-}
-void launch_ray_items(cudaStream_t stream, const uint32_t* alive_list, uint32_t n_local, const int32_t* slot_of,
-                      int32_t* alias_of, uint32_t* readers, RayItem* items, StepCounters* counters) {
-    k_ray_items<<<(n_local + 255) / 256, 256, 0, stream>>>(alive_list, slot_of, alias_of, readers, items, counters);
-}
-
 // =============================================================================== k_sort_beams
 // Bitonic sort of (|dist|, beam index) in shared memory, descending; one CTA, once per scan, on the side
 // stream while the likelihood kernel runs.
@@ -1142,8 +1108,8 @@ size_t ray_spill_scratch_words(int num_sms) { return (size_t)num_sms * 4u * RAY_
 
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
-                              const RayItem* items, const uint32_t* readers, uint32_t* done, uint32_t* spill_scratch,
-                              const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
+                              const RayItem* clones, const RayItem* owners, const uint32_t* readers, uint32_t* done,
+                              uint32_t* spill_scratch, const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic, int num_sms) {
     int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
@@ -1162,7 +1128,7 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
         if (per_sm > 4) per_sm = 4;   // (the spill scratch is sized for 4 CTAs per SM)
         uint32_t grid = (uint32_t)(per_sm * num_sms);
         if (grid > n_local) grid = n_local;
-        k_ray_update_packed<<<grid, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, items, readers, done, spill_scratch,
+        k_ray_update_packed<<<grid, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, clones, owners, readers, done, spill_scratch,
                                                                  slot_of, cells, meta, bands, cells_per_grid, radius, radius_cells, counters);
         return cudaSuccess;
     }

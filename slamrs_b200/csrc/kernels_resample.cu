@@ -586,42 +586,63 @@ int weights_trace(long long* out64) {
 
 // =============================================================================== k_resample_indices
 
-// first i with !(u_m > cum[i]) for the zero-based new-particle index m0 (particle.rs:84-94)
-__device__ __forceinline__ uint32_t resample_source(const double* __restrict__ cum, uint32_t n, double U, uint32_t m0,
-                                                    bool* ran_off) {
+// u_m of particle.rs:84, 89 for the zero-based new-particle index m0
+__device__ __forceinline__ double resample_threshold(uint32_t n, double U, uint32_t m0) {
     const double num = (double)n;
     const double r = __ddiv_rn(__dmul_rn(U, 1.0), num);   // particle.rs:84: r = rand::random::<f64>() * 1.0 / N
     // particle.rs:89: u = r + (m as f64 - 1.0) * 1.0 / N with m = m0 + 1
-    const double u = __dadd_rn(r, __ddiv_rn(__dmul_rn(__dsub_rn((double)(m0 + 1u), 1.0), 1.0), num));
-    // particle.rs:91-94: advance i while u > c. c is non-decreasing (weights >= 0), so the loop
-    // stops at the first i with !(u > cum[i]); found here by bisection.
-    uint32_t lo = 0, hi = n;  // answer in [lo, hi]; hi == n means "ran off the end"
+    return __dadd_rn(r, __ddiv_rn(__dmul_rn(__dsub_rn((double)(m0 + 1u), 1.0), 1.0), num));
+}
+// first i in [lo, hi) with !(u > cum[i]), hi if none. particle.rs:91-94 advances i while u > c; c is
+// non-decreasing (weights >= 0; NaN compares false from its first occurrence on), so the loop stops at
+// the first i with !(u > cum[i]).
+__device__ __forceinline__ uint32_t first_not_below(const double* __restrict__ cum, uint32_t lo, uint32_t hi, double u) {
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         if (u > cum[mid]) lo = mid + 1; else hi = mid;
     }
-    *ran_off = lo >= n;   // the reference would index out of bounds and panic; clamp and flag
-    return lo >= n ? n - 1 : lo;
+    return lo;
 }
+
+// Two-level search: a CTA first loads every RS_STRIDE-th running sum (the last of each block of RS_STRIDE
+// weights, at most RS_COARSE of them) into shared memory in one round trip; a thread bisects there and
+// finishes inside one block of the global array (one or two cache lines) instead of making log2(N)
+// dependent trips to L2.
+constexpr uint32_t RS_COARSE = 2048;
 
 // Also builds the list of local particles that survive (some index selects them): a particle that
 // no entry of the index vector selects is dropped by the resampler (particle.rs:88-104 builds the
 // new generation only from old[i]); integrating the scan into its grid would be unobservable work,
 // so the ray kernel runs on the survivors only. The thread of the FIRST new particle that selects a
 // local source appends it (the index vector is non-decreasing, so "first" = differs from the
-// predecessor's source, which comes from the neighbouring lane).
+// predecessor's source, which comes from the neighbouring lane). With `ray` the survivors go straight
+// into the fused ray update's work lists (kernels_ray.cu): a clone (grid still an alias of its source's
+// slot) is listed in ray.clones, counts itself as a reader of its root and becomes private; a particle
+// that owns its slot is listed in ray.owners.
 __global__ void __launch_bounds__(256)
 k_resample_indices(const ParticleResult* __restrict__ results, const double* __restrict__ cum, uint32_t n,
                    const double* __restrict__ u01_caller, uint64_t seed, uint64_t step, uint32_t* __restrict__ idx,
                    float* __restrict__ pose_next, uint32_t first_particle, uint32_t n_local, bool build_alive,
-                   uint32_t* __restrict__ alive_list, StepCounters* counters) {
+                   uint32_t* __restrict__ alive_list, RayLists ray, StepCounters* counters) {
+    __shared__ double s_coarse[RS_COARSE];
+    const uint32_t stride = (n + RS_COARSE - 1u) / RS_COARSE;      // weights per block
+    const uint32_t n_coarse = (n + stride - 1u) / stride;
+    for (uint32_t j = threadIdx.x; j < n_coarse; j += blockDim.x) s_coarse[j] = cum[min(n, (j + 1u) * stride) - 1u];
+    __syncthreads();
     const uint32_t m0 = blockIdx.x * blockDim.x + threadIdx.x;  // zero-based new-particle index
     const double U = u01_caller ? *u01_caller : slamrs_stream::resample_uniform(seed, step);
     const int lane = threadIdx.x & 31;
+    auto source_of = [&](uint32_t m, bool* ran_off) {
+        const double u = resample_threshold(n, U, m);
+        const uint32_t blk = first_not_below(s_coarse, 0u, n_coarse, u);
+        *ran_off = blk >= n_coarse;   // the reference would index out of bounds and panic; clamp and flag
+        if (blk >= n_coarse) return n - 1u;
+        return first_not_below(cum, blk * stride, min(n, (blk + 1u) * stride) - 1u, u);   // (the block's last element qualifies)
+    };
     bool ran_off = false;
     uint32_t src_idx = 0xffffffffu;
     if (m0 < n) {
-        src_idx = resample_source(cum, n, U, m0, &ran_off);
+        src_idx = source_of(m0, &ran_off);
         if (ran_off) atomicAdd(&counters->clamped, 1ull);
         idx[m0] = src_idx;
         const ParticleResult src = results[src_idx];
@@ -638,28 +659,54 @@ k_resample_indices(const ParticleResult* __restrict__ results, const double* __r
     uint32_t prev = __shfl_up_sync(0xffffffffu, src_idx, 1);
     if (lane == 0 && m0 > 0 && m0 < n) {
         bool dummy;
-        prev = resample_source(cum, n, U, m0 - 1u, &dummy);
+        prev = source_of(m0 - 1u, &dummy);
     }
     const bool alive = m0 < n && (m0 == 0 || prev != src_idx) && src_idx >= first_particle &&
                        src_idx < first_particle + n_local;
-    // warp-aggregated append (order is irrelevant: particles are independent)
-    const unsigned mask = __ballot_sync(0xffffffffu, alive);
-    if (mask) {
-        const int leader = __ffs(mask) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(&counters->n_alive, (unsigned long long)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (alive) alive_list[base + __popc(mask & ((1u << lane) - 1u))] = src_idx - first_particle;
+    // warp-aggregated appends (order is irrelevant: particles are independent)
+    if (ray.clones == nullptr) {
+        const unsigned mask = __ballot_sync(0xffffffffu, alive);
+        if (mask) {
+            const int leader = __ffs(mask) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&counters->n_alive, (unsigned long long)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (alive) alive_list[base + __popc(mask & ((1u << lane) - 1u))] = src_idx - first_particle;
+        }
+        return;
     }
+    RayItem it{0u, 0, 0, 0u};
+    bool clone = false;
+    if (alive) {
+        it.particle = src_idx - first_particle;
+        it.slot = ray.slot_of[it.particle];
+        it.root = ray.alias_of[it.slot];
+        clone = it.root != it.slot;
+        if (clone) { atomicAdd(&ray.readers[it.root], 1u); ray.alias_of[it.slot] = it.slot; }
+    }
+    const unsigned mc = __ballot_sync(0xffffffffu, alive && clone), mo = __ballot_sync(0xffffffffu, alive && !clone);
+    unsigned long long bc = 0, bo = 0;
+    if (lane == 0) {
+        if (mc | mo) atomicAdd(&counters->n_alive, (unsigned long long)__popc(mc | mo));
+        if (mc) {
+            bc = atomicAdd(&counters->ray_items_front, (unsigned long long)__popc(mc));
+            atomicAdd(&counters->n_mat, (unsigned long long)__popc(mc));
+            atomicAdd(&counters->n_mat_leaders, (unsigned long long)__popc(mc));   // every clone reads its source itself
+        }
+        if (mo) bo = atomicAdd(&counters->ray_items_back, (unsigned long long)__popc(mo));
+    }
+    bc = __shfl_sync(0xffffffffu, bc, 0); bo = __shfl_sync(0xffffffffu, bo, 0);
+    if (alive && clone) ray.clones[bc + __popc(mc & ((1u << lane) - 1u))] = it;
+    if (alive && !clone) ray.owners[bo + __popc(mo & ((1u << lane) - 1u))] = it;
 }
 
 void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
                              uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,
                              uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
-                             bool build_alive, uint32_t* alive_list, StepCounters* counters) {
+                             bool build_alive, uint32_t* alive_list, RayLists ray, StepCounters* counters) {
     k_resample_indices<<<(n_total + 255) / 256, 256, 0, stream>>>(results, cum, n_total, u01_caller, seed, step, idx,
                                                                  pose_next, first_particle, n_local, build_alive,
-                                                                 alive_list, counters);
+                                                                 alive_list, ray, counters);
 }
 
 // =============================================================================== k_mark_alive

@@ -14,6 +14,13 @@
 // glibc 2.39's FMA-enabled x86-64 build executes (checked by disassembling libm.so.6;
 // tools/check_libm_f32.c compares all 2^32 inputs against the host libm).
 //
+// Provenance and licence: the algorithm and its constants (the reduction constant 2^24 / pi-ish `hpi_inv`,
+// `hpi`, and the two sets of minimax coefficients) are those of glibc's sysdeps/ieee754/flt-32/s_sincosf.h and
+// s_sincosf_data.c (contributed by Szabolcs Nagy / Arm, also published in ARM-software/optimized-routines under
+// MIT OR Apache-2.0 WITH LLVM-exception); glibc itself is LGPL-2.1-or-later. They are restated here from the
+// disassembly of the installed libm.so.6, because bit-equality with that library is the requirement; a
+// redistributor should treat this header as derived from optimized-routines' sincosf (MIT).
+//
 // This file compiles for host (gcc/g++) and device (nvcc).
 #pragma once
 #include <stdint.h>
