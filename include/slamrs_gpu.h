@@ -101,7 +101,11 @@ typedef struct slamrs_gpu_config {
                               extent of one particle's map (everything else is the prior). Memory per particle
                               drops from 4*W*H to 4*slot_cells^2 bytes; an extent that outgrows it is reported
                               as SLAMRS_E_WINDOW. */
-    uint32_t reserved0;    /* must be 0 */
+    float resample_threshold; /* 0 (default): resample after every update, as the reference does (slam.rs:74).
+                                 tau in (0, 1]: resample only when the effective number of particles
+                                 (particle.rs:59-65) is below tau * N; otherwise every particle stays in place and
+                                 carries its normalised weight into the next update (not a
+                                 reference feature) */
     uint8_t nccl_id[SLAMRS_NCCL_ID_BYTES]; /* from slamrs_gpu_nccl_unique_id, same on all ranks */
 } slamrs_gpu_config;
 
@@ -122,6 +126,7 @@ typedef struct slamrs_gpu_stats {
     uint64_t resample_exact_fallback; /* bit 0 / 1: the weight sum / the running sum of the last step was folded by a
                                          single thread (NaN, inf or hostile weights; the result is the same) */
     uint64_t resample_fold_rounds;    /* rounds the parallel exact fold needed (1 = proven at once) */
+    uint64_t resampled;               /* 1 if the last update resampled (always, unless resample_threshold > 0) */
 } slamrs_gpu_stats;
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -197,6 +202,12 @@ int slamrs_gpu_map_window(slamrs_gpu_handle* h, uint32_t format, int32_t x0, int
  * weights of the last update BEFORE resampling (the reference never calls it; after resampling it
  * is trivially N). N before the first update. */
 int slamrs_gpu_effective_particles(slamrs_gpu_handle* h, double* out);
+
+/* Global-localisation-style start (README.md:45 lists it as an idea): every particle of this
+ * rank's shard gets a pose drawn uniformly over the box {x0, y0, x1, y1} (metres), heading in [-pi, pi), from
+ * the shared stream keyed by the config's seed and the GLOBAL particle index (any sharding gives the same
+ * population). Maps are untouched. Call before the first update (or any time between updates). */
+int slamrs_gpu_init_uniform(slamrs_gpu_handle* h, const float box_x0y0x1y1[4]);
 
 /* ------------------------------------------------------------------ scan production on the device */
 

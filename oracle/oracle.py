@@ -55,6 +55,9 @@ def lib():
     L.so_set_weight_override.restype = None; L.so_set_weight_override.argtypes = [vp, vp]
     L.so_get_own_raw.restype = None; L.so_get_own_raw.argtypes = [vp, vp]
     L.so_destroy.restype = None; L.so_destroy.argtypes = [vp]
+    L.so_set_adaptive_resampling.restype = None; L.so_set_adaptive_resampling.argtypes = [vp, d]
+    L.so_resampled.restype = C.c_int; L.so_resampled.argtypes = [vp]
+    L.ss_fill_uniform_poses.restype = None; L.ss_fill_uniform_poses.argtypes = [u64, u64, u64, d, d, d, d, vp]
     L.so_set_threads.restype = None; L.so_set_threads.argtypes = [vp, C.c_int]
     L.so_set_dead_likelihood.restype = None; L.so_set_dead_likelihood.argtypes = [vp, C.c_int]
     L.so_set_trace.restype = None; L.so_set_trace.argtypes = [vp, i64, i64]
@@ -152,6 +155,12 @@ def motion_normals(seed: int, step: int, first: int, count: int) -> np.ndarray:
     return z
 
 
+def uniform_poses(seed: int, first: int, count: int, box) -> np.ndarray:
+    out = np.zeros((count, 3), np.float32)
+    lib().ss_fill_uniform_poses(seed, first, count, float(box[0]), float(box[1]), float(box[2]), float(box[3]), _p(out))
+    return out
+
+
 def resample_uniform(seed: int, step: int) -> float:
     return lib().ss_resample_uniform(seed, step)
 
@@ -207,6 +216,8 @@ class OracleSlam:
         self.close()
 
     def set_threads(self, t): lib().so_set_threads(self._h, t)
+    def set_adaptive_resampling(self, tau): lib().so_set_adaptive_resampling(self._h, float(tau))
+    def resampled(self): return bool(lib().so_resampled(self._h))
     def set_dead_likelihood(self, on): lib().so_set_dead_likelihood(self._h, int(on))
     def set_trace(self, particle, cap): lib().so_set_trace(self._h, particle, cap)
 

@@ -124,3 +124,21 @@ double ss_resample_uniform(uint64_t seed, uint64_t step) {
     ss_philox4x32_10(ctr, key, x);
     return u53(x[0], x[1]);
 }
+
+/* start pose of `particle` for a uniform initialisation (counter domains 2 and 3 of the stream) */
+void ss_uniform_pose(uint64_t seed, uint64_t particle, double x0, double y0, double x1, double y1, float* out_xyt) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ca[4] = {(uint32_t)particle, 0u, 0u, 2u}, cb[4] = {(uint32_t)particle, 0u, 0u, 3u};
+    uint32_t a[4], b[4];
+    ss_philox4x32_10(ca, key, a);
+    ss_philox4x32_10(cb, key, b);
+    double d = x1 + -x0;
+    out_xyt[0] = (float)(x0 + u53(a[0], a[1]) * d);
+    d = y1 + -y0;
+    out_xyt[1] = (float)(y0 + u53(a[2], a[3]) * d);
+    out_xyt[2] = (float)(-0x1.921fb54442d18p+1 + u53(b[0], b[1]) * 0x1.921fb54442d18p+2);
+}
+void ss_fill_uniform_poses(uint64_t seed, uint64_t first, uint64_t count, double x0, double y0, double x1, double y1,
+                           float* out_xyt) {
+    for (uint64_t i = 0; i < count; ++i) ss_uniform_pose(seed, first + i, x0, y0, x1, y1, out_xyt + 3 * i);
+}

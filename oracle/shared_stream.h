@@ -34,6 +34,10 @@ void ss_motion_normals(uint64_t seed, uint64_t step, uint64_t particle, double* 
 /* fills z[2*i], z[2*i+1] for particles first..first+count-1 */
 void ss_fill_motion_normals(uint64_t seed, uint64_t step, uint64_t first, uint64_t count, double* z);
 double ss_resample_uniform(uint64_t seed, uint64_t step);
+/* uniform start poses over [x0,x1) x [y0,y1), heading in [-pi, pi) (global-localisation-style initialisation) */
+void ss_uniform_pose(uint64_t seed, uint64_t particle, double x0, double y0, double x1, double y1, float* out_xyt);
+void ss_fill_uniform_poses(uint64_t seed, uint64_t first, uint64_t count, double x0, double y0, double x1, double y1,
+                           float* out_xyt);
 
 #ifdef __cplusplus
 }

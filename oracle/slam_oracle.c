@@ -234,6 +234,9 @@ struct so_slam {
     int sparse;            /* tile storage with copy-on-write clones (so_create_ex) */
     const double* weight_override; /* next update resamples on these raw weights (so_set_weight_override) */
     double* own_raw;       /* the raw weights this oracle computed in the last update */
+    double adaptive_tau;   /* > 0: resample only when N_eff < tau * N (extension, see so_set_adaptive_resampling) */
+    double* carry;         /* weights carried over a step that did not resample; NULL after a resampling */
+    int resampled;         /* did the last update resample? */
     int run_dead_likelihood;
     int clamped; /* resample index ran past N-1 (reference would panic) */
     int threads;
@@ -468,10 +471,13 @@ struct so_slam* so_create_ex(float pos_x, float pos_y, float width, float height
 void so_destroy(struct so_slam* s) {
     if (!s) return;
     if (s->map) for (uint64_t i = 0; i < s->n; ++i) map_free(&s->map[i]);
-    free(s->map); free(s->pose); free(s->weight); free(s->raw_weight); free(s->last_idx); free(s->trace); free(s->own_raw);
+    free(s->map); free(s->pose); free(s->weight); free(s->raw_weight); free(s->last_idx); free(s->trace); free(s->own_raw); free(s->carry);
     free(s);
 }
 
+/* extension: resample only when N_eff < tau * N; 0 restores the reference's behaviour */
+void so_set_adaptive_resampling(struct so_slam* s, double tau) { s->adaptive_tau = tau; }
+int so_resampled(const struct so_slam* s) { return s->resampled; }
 void so_set_threads(struct so_slam* s, int threads) { s->threads = threads < 1 ? 1 : threads; }
 void so_set_dead_likelihood(struct so_slam* s, int on) { s->run_dead_likelihood = on; }
 void so_set_trace(struct so_slam* s, int64_t particle, int64_t cap) {
@@ -567,6 +573,8 @@ int so_update(struct so_slam* s, const double* angle, const double* dist, const 
 #pragma omp parallel for schedule(dynamic, 1) num_threads(s->threads) if (s->threads > 1)
     for (int64_t p = 0; p < n; ++p) particle_step(s, (uint64_t)p, angle, dist, valid, nb, od, z);
 
+    if (s->carry)   /* adaptive resampling: weights accumulate over the steps that did not resample */
+        for (int64_t p = 0; p < n; ++p) s->raw_weight[p] = s->carry[p] * s->raw_weight[p];
     memcpy(s->own_raw, s->raw_weight, s->n * sizeof(double));
     if (s->weight_override) {   /* resample on the weights the device computed (see so_set_weight_override) */
         memcpy(s->raw_weight, s->weight_override, s->n * sizeof(double));
@@ -574,6 +582,24 @@ int so_update(struct so_slam* s, const double* angle, const double* dist, const 
     }
     /* normalize_weights, argmax, resample indices: particle.rs:40-56, 78-101 */
     s->clamped = so_resample_fold(s->raw_weight, s->n, u01, s->weight, NULL, s->last_idx, &s->max_particle);
+    s->resampled = 1;
+    if (s->adaptive_tau > 0.0) {
+        /* NOT in the reference (which resamples after every scan, slam.rs:74): resample only when the effective
+         * number of particles (particle.rs:59-65) drops below tau * N; otherwise every particle stays where it
+         * is and carries its normalised weight into the next update. */
+        double sq = 0.0;
+        for (int64_t p = 0; p < n; ++p) sq += s->weight[p] * s->weight[p];
+        if (!(1.0 / sq < s->adaptive_tau * (double)s->n)) {
+            if (!s->carry) s->carry = (double*)malloc(s->n * sizeof(double));
+            memcpy(s->carry, s->weight, s->n * sizeof(double));
+            for (int64_t p = 0; p < n; ++p) s->last_idx[p] = (uint64_t)p;
+            s->clamped = 0;
+            s->resampled = 0;
+            return 0;
+        }
+        free(s->carry);
+        s->carry = NULL;
+    }
     /* new generation: clone(old[i]) for every slot (deep copy of Pose + Map) */
     struct so_map* new_map = (struct so_map*)calloc(s->n, sizeof(struct so_map));
     so_pose* new_pose = (so_pose*)malloc(s->n * sizeof(so_pose));

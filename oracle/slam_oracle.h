@@ -31,6 +31,8 @@ void so_destroy(struct so_slam* s);
 void so_set_weight_override(struct so_slam* s, const double* raw);
 void so_get_own_raw(const struct so_slam* s, double* out);
 void so_set_threads(struct so_slam* s, int threads);
+void so_set_adaptive_resampling(struct so_slam* s, double tau);
+int so_resampled(const struct so_slam* s);
 void so_set_dead_likelihood(struct so_slam* s, int on);
 void so_set_trace(struct so_slam* s, int64_t particle, int64_t cap);
 int so_update(struct so_slam* s, const double* angle, const double* dist, const uint8_t* valid, uint64_t nb,

@@ -54,7 +54,7 @@ pub struct slamrs_gpu_config {
     pub spare_slots: u32,
     pub flags: u32,
     pub slot_cells: u32,
-    pub reserved0: u32,
+    pub resample_threshold: f32,
     pub nccl_id: [u8; SLAMRS_NCCL_ID_BYTES],
 }
 
@@ -75,6 +75,7 @@ pub struct slamrs_gpu_stats {
     pub window_overflow: u64,
     pub resample_exact_fallback: u64,
     pub resample_fold_rounds: u64,
+    pub resampled: u64,
 }
 
 extern "C" {

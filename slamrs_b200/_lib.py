@@ -32,7 +32,7 @@ EXPORTS = [
     "slamrs_gpu_set_scan_device", "slamrs_gpu_set_profiling", "slamrs_gpu_get_phase_ms",
     "slamrs_gpu_get_step_history", "slamrs_gpu_map_extent", "slamrs_gpu_map_window",
     "slamrs_gpu_effective_particles", "slamrs_gpu_sim_scan", "slamrs_gpu_get_scan", "slamrs_gpu_get_slots",
-    "slamrs_gpu_get_extents", "slamrs_gpu_debug_resample",
+    "slamrs_gpu_get_extents", "slamrs_gpu_debug_resample", "slamrs_gpu_init_uniform",
 ]
 MAP_F64, MAP_F32, MAP_U8 = 0, 1, 2
 PHASES = ["motion_likelihood", "all_gather", "resample", "materialize", "ray_update", "pull", "copy"]
@@ -47,7 +47,7 @@ class Config(C.Structure):
         ("rng_mode", C.c_uint32), ("device", C.c_int32),
         ("rank", C.c_uint32), ("world_size", C.c_uint32),
         ("spare_slots", C.c_uint32), ("flags", C.c_uint32),
-        ("slot_cells", C.c_uint32), ("reserved0", C.c_uint32),
+        ("slot_cells", C.c_uint32), ("resample_threshold", C.c_float),
         ("nccl_id", C.c_uint8 * NCCL_ID_BYTES),
     ]
 
@@ -56,7 +56,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "step", "grids_copied", "grids_pulled", "distinct_sources", "resample_clamped",
         "counter_saturated", "spilled_cells", "window_cells", "bytes_per_grid", "particles_integrated",
-        "copy_bytes", "window_overflow", "resample_exact_fallback", "resample_fold_rounds")]
+        "copy_bytes", "window_overflow", "resample_exact_fallback", "resample_fold_rounds", "resampled")]
 
 
 class SlamrsGpuError(RuntimeError):
@@ -121,6 +121,7 @@ def load():
     L.slamrs_gpu_get_scan.restype = i; L.slamrs_gpu_get_scan.argtypes = [vp, vp, vp, vp, u32, C.POINTER(u32)]
     L.slamrs_gpu_get_slots.restype = i; L.slamrs_gpu_get_slots.argtypes = [vp, vp, vp, C.POINTER(u32)]
     L.slamrs_gpu_get_extents.restype = i; L.slamrs_gpu_get_extents.argtypes = [vp, u64, vp, vp, C.POINTER(u32)]
+    L.slamrs_gpu_init_uniform.restype = i; L.slamrs_gpu_init_uniform.argtypes = [vp, vp]
     L.slamrs_gpu_debug_resample.restype = i
     L.slamrs_gpu_debug_resample.argtypes = [i, vp, u32, C.c_double, vp, C.POINTER(u64), vp, vp, vp, vp]
     _lib = L

@@ -69,6 +69,7 @@ struct slamrs_gpu_handle {
     double* d_wnorm = nullptr;
     double* d_cum = nullptr;
     double* d_fold = nullptr;    // scratch of k_weights' exact left fold
+    double* d_carry = nullptr;   // adaptive resampling: weights carried over a step that did not resample (n_total)
     uint32_t* d_idx = nullptr;
     float* d_angle = nullptr;
     float* d_dist = nullptr;
@@ -266,7 +267,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_slot[0]); cudaFree(h->d_slot[1]);
     cudaFree(h->d_pose[0]); cudaFree(h->d_pose[1]);
     cudaFree(h->d_term_table);
-    cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx); cudaFree(h->d_fold);
+    cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx); cudaFree(h->d_fold); cudaFree(h->d_carry);
     cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
@@ -431,6 +432,8 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     if ((uint64_t)cfg->grid_w * cfg->grid_h > 0x7fffffffull) return fail(nullptr, SLAMRS_E_INVALID_ARG, "grid too large");
     if (!(cfg->resolution > 0.0f)) return fail(nullptr, SLAMRS_E_INVALID_ARG, "resolution must be positive");
     if (cfg->rng_mode > SLAMRS_RNG_CALLER) return fail(nullptr, SLAMRS_E_INVALID_ARG, "unknown rng_mode");
+    if (!(cfg->resample_threshold >= 0.0f && cfg->resample_threshold <= 1.0f))
+        return fail(nullptr, SLAMRS_E_INVALID_ARG, "resample_threshold must be 0 (always resample) or in (0, 1]");
     if (cfg->slot_cells != 0 && (cfg->slot_cells < 256u || (cfg->slot_cells & (cfg->slot_cells - 1u)) != 0u))
         return fail(nullptr, SLAMRS_E_INVALID_ARG, "slot_cells must be 0 (whole grid) or a power of two >= 256");
 
@@ -547,6 +550,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_cum, sizeof(double) * h->n_total));
     CREATE_CU(cudaMalloc(&h->d_idx, sizeof(uint32_t) * h->n_total));
     CREATE_CU(cudaMalloc(&h->d_fold, sizeof(double) * weights_scratch_doubles()));
+    if (cfg->resample_threshold > 0.0f) CREATE_CU(cudaMalloc(&h->d_carry, sizeof(double) * h->n_total));
     CREATE_CU(cudaMemsetAsync(h->d_wnorm, 0, sizeof(double) * h->n_total, h->stream));
     CREATE_CU(cudaMemsetAsync(h->d_idx, 0, sizeof(uint32_t) * h->n_total, h->stream));
     if (cfg->rng_mode == SLAMRS_RNG_CALLER) {
@@ -715,7 +719,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->defer ? h->d_alias : nullptr, h->d_cells, h->d_meta, h->cells_per_grid,
                              h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step, h->d_term_table, h->d_valid_list, h->d_n_valid,
-                             h->p2p_exchange ? h->d_peer_results : nullptr, res_off, h->rank, h->world);
+                             h->d_carry, h->d_counters, h->p2p_exchange ? h->d_peer_results : nullptr, res_off, h->rank, h->world);
     h->launches += 2;   // k_motion + k_likelihood
     // 2. the one exchange step: every GPU needs every particle's weight, pose and slot. Default:
     //    k_likelihood has already stored each record into every peer (NVLink), only the barrier is
@@ -735,7 +739,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     //    which local particles survive
     PROF_MARK(h, 2);
     // (k_weights also zeroes the per-step counters)
-    launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_fold, h->d_counters);
+    launch_weights(s, h->d_results, h->n_total, h->d_wnorm, h->d_cum, h->d_fold, (double)h->cfg.resample_threshold, h->d_counters);
     // 3b. deferred copies: the clones among the particles about to be written get their own cells. Either the
     //     ray kernel does it while it integrates the scan (fused: k_resample_indices lists the survivors as
     //     clones | owners, no copy kernels), or they are listed now and copied after PROF_MARK 3. Before the
@@ -743,7 +747,8 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     RayLists ray{nullptr, nullptr, nullptr, nullptr, nullptr};
     if (fuse) ray = RayLists{h->d_ray_items, h->d_ray_items + h->n_local, h->d_slot[cur], h->d_alias, h->d_readers};
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
-                            h->d_idx, h->d_pose[nxt], h->first, h->n_local, !all_particles, h->d_alive, ray, h->d_counters);
+                            h->d_idx, h->d_pose[nxt], h->first, h->n_local, !all_particles, h->d_alive, ray, h->d_wnorm, h->d_carry,
+                            h->d_counters);
     if (all_particles) {
         launch_mark_alive(s, h->d_idx, h->n_total, h->first, h->n_local, true, h->d_alive, h->d_counters);
         h->launches++;
@@ -1031,6 +1036,7 @@ int slamrs_gpu_get_stats(slamrs_gpu_handle* h, slamrs_gpu_stats* out) {
     out->copy_bytes = c.copy_bytes;
     out->resample_exact_fallback = c.fold_fallback;
     out->resample_fold_rounds = c.fold_rounds;
+    out->resampled = h->step == 0 ? 0 : c.do_resample;
     return SLAMRS_OK;
 }
 
@@ -1098,6 +1104,17 @@ int slamrs_gpu_get_slots(slamrs_gpu_handle* h, int32_t* out_slot_of, int32_t* ou
         CU_TRY(h, cudaMemcpyAsync(out_spare, h->d_spare, sizeof(int32_t) * h->n_spare, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     if (out_n_spare) *out_n_spare = h->n_spare;
+    return SLAMRS_OK;
+}
+
+int slamrs_gpu_init_uniform(slamrs_gpu_handle* h, const float box[4]) {
+    if (!h || !box) return SLAMRS_E_INVALID_ARG;
+    if (!(box[2] >= box[0] && box[3] >= box[1])) return fail(h, SLAMRS_E_INVALID_ARG, "empty box");
+    DeviceGuard g(h->device);
+    launch_init_uniform(h->stream, h->cfg.seed, h->first, h->n_local, box[0], box[1], box[2], box[3], h->d_pose[h->cur]);
+    h->launches++;
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaGetLastError());
     return SLAMRS_OK;
 }
 
@@ -1334,10 +1351,10 @@ int slamrs_gpu_debug_resample(int device, const double* raw_weights, uint32_t n,
     float us[2] = {0.f, 0.f};
     for (int r = 0; r < reps; ++r) {
         cudaEventRecord(ev[0], nullptr);
-        launch_weights(nullptr, res.p, n, wn.p, cum.p, fold.p, cnt.p);
+        launch_weights(nullptr, res.p, n, wn.p, cum.p, fold.p, 0.0, cnt.p);
         cudaEventRecord(ev[1], nullptr);
         launch_resample_indices(nullptr, res.p, cum.p, n, u.p, 0, 0, idx.p, nullptr, 0, 0, false, nullptr,
-                                RayLists{nullptr, nullptr, nullptr, nullptr, nullptr}, cnt.p);
+                                RayLists{nullptr, nullptr, nullptr, nullptr, nullptr}, wn.p, nullptr, cnt.p);
         cudaEventRecord(ev[2], nullptr);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { for (auto& x : ev) cudaEventDestroy(x); return fail(nullptr, SLAMRS_E_CUDA, cudaGetErrorString(e)); }

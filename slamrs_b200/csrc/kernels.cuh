@@ -54,6 +54,8 @@ struct StepCounters {
     unsigned long long ray_items_front;  // k_ray_items: clones listed so far (front of the list)
     unsigned long long ray_items_back;   // k_ray_items: slot owners listed so far (back of the list)
     unsigned long long fuse_overflow;    // fused ray update: more parked hits than its scratch holds (error, cannot happen by its bound)
+    unsigned long long do_resample;      // k_weights: this step resamples (always 1 unless adaptive resampling is on)
+    unsigned long long carry_active;     // the weights of the last step were carried over (it did not resample)
     unsigned long long fold_rounds;      // k_weights: rounds the exact left fold needed (1 = proven at once)
     unsigned long long fold_heads;       // k_weights: chunks resolved by the sequential chain (binade changes)
     unsigned long long fold_fallback;    // k_weights: bit 0 / 1 = the raw-weight sum / the running sum fell back to one thread
@@ -130,6 +132,8 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
                               const double* term_table /* LK_TABLE_NF x LK_TABLE_NO, launch_fill_term_table */,
                               float2* valid_beams /* scratch: n_beams entries */, uint32_t* n_valid /* scratch */,
+                              const double* carry /* adaptive resampling: carried weights (n_total), else null */,
+                              const StepCounters* counters,
                               ParticleResult* const* peer_results /* null: no fused exchange */,
                               uint32_t peer_offset /* records in front of this step's generation */, uint32_t rank,
                               uint32_t world);
@@ -158,8 +162,9 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
                               uint64_t* window_cells, bool force_generic, int num_sms);
 
 // fold_scratch: weights_scratch_doubles() doubles
+// resample_tau > 0: counters->do_resample = N_eff < tau * N (adaptive resampling), else 1
 void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
-                    double* cum, double* fold_scratch, StepCounters* counters);
+                    double* cum, double* fold_scratch, double resample_tau, StepCounters* counters);
 size_t weights_scratch_doubles();
 int weights_trace(long long* out64);   // tuning builds (-DSLAMRS_FOLD_TRACE): clock stamps of the last k_weights
 
@@ -167,7 +172,8 @@ void launch_resample_indices(cudaStream_t stream, const ParticleResult* results,
                              uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,
                              uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
                              bool build_alive /* also list the surviving local particles */,
-                             uint32_t* alive_list, RayLists ray, StepCounters* counters);
+                             uint32_t* alive_list, RayLists ray, const double* w_norm, double* carry /* may be null */,
+                             StepCounters* counters);
 
 struct PlanArgs {
     const ParticleResult* results;  // N, after the all-gather (carries every particle's physical slot)
@@ -258,6 +264,9 @@ void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsig
 // add the bytes of a full-grid copy launch to counters->copy_bytes
 void launch_account_full_copy(cudaStream_t stream, const unsigned long long* n_items, const unsigned long long* n_leaders,
                               size_t bytes_per_grid, StepCounters* counters);
+// poses of the local shard drawn uniformly over a box (slamrs_stream::uniform_pose)
+void launch_init_uniform(cudaStream_t stream, uint64_t seed, uint32_t first_particle, uint32_t n_local, float x0, float y0,
+                         float x1, float y1, float* pose);
 // simulator lidar into device scan buffers; out_count_maxbits must be zeroed before the launch
 void launch_sim_scan(cudaStream_t stream, const float* segments, uint32_t n_seg, float px, float py, float ptheta,
                      uint32_t n_beams, float scanner_range, float* angle, float* dist, uint8_t* valid,

@@ -82,7 +82,7 @@ k_likelihood(MapGeom geom, ScanDevice scan, const int32_t* __restrict__ alias_of
              const SlotMeta* __restrict__ meta,
              size_t cells_per_grid, ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
              const double* __restrict__ term_table, const float2* __restrict__ valid_beams,
-             const uint32_t* __restrict__ n_valid_ptr,
+             const uint32_t* __restrict__ n_valid_ptr, const double* __restrict__ carry, const StepCounters* __restrict__ counters,
              ParticleResult* const* __restrict__ peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     const uint32_t p = blockIdx.x * LK_WARPS + (threadIdx.x >> 5);
     if (p >= n_local) return;
@@ -132,6 +132,8 @@ k_likelihood(MapGeom geom, ScanDevice scan, const int32_t* __restrict__ alias_of
     // weight.prob().value(), slam.rs:71: exp(log p(z|x,m) + log p(x'|x,u))
     ParticleResult out = r;
     out.weight = exp(__dadd_rn(lp, r.weight));
+    // adaptive resampling (not in the reference): a step that did not resample carries its weights forward
+    if (carry != nullptr && counters->carry_active) out.weight = __dmul_rn(carry[first_particle + p], out.weight);
     if (lane == 0) results[first_particle + p] = out;
     // The exchange step, fused: lane q stores the finished record straight into GPU q's copy of
     // the population array over NVLink (24 bytes per particle and peer), so that after one
@@ -146,12 +148,13 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               const SlotMeta* meta, size_t cells_per_grid, ParticleResult* results, uint32_t first_particle,
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
                               const double* term_table, float2* valid_beams, uint32_t* n_valid,
+                              const double* carry, const StepCounters* counters,
                               ParticleResult* const* peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
     k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
                                                          z_draws, seed, step, scan, valid_beams, n_valid);
     k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, alias_of, cells, meta, cells_per_grid,
                                                                                    results, first_particle, n_local,
-                                                                                   term_table, valid_beams, n_valid,
+                                                                                   term_table, valid_beams, n_valid, carry, counters,
                                                                                    peer_results, peer_offset, rank, world);
 }
 

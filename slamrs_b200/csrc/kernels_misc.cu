@@ -124,6 +124,20 @@ void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, 
     k_init_slots<<<(n + 255) / 256, 256, 0, stream>>>(slot_of, n_local, spare_list, n_spare, counters, rank, meta, alias_of);
 }
 
+// =============================================================================== k_init_uniform
+__global__ void __launch_bounds__(256)
+k_init_uniform(uint64_t seed, uint32_t first_particle, uint32_t n_local, float x0, float y0, float x1, float y1,
+               float* __restrict__ pose) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    slamrs_stream::uniform_pose(seed, first_particle + i, (double)x0, (double)y0, (double)x1, (double)y1, &pose[3 * i],
+                                &pose[3 * i + 1], &pose[3 * i + 2]);
+}
+void launch_init_uniform(cudaStream_t stream, uint64_t seed, uint32_t first_particle, uint32_t n_local, float x0, float y0,
+                         float x1, float y1, float* pose) {
+    k_init_uniform<<<(n_local + 255) / 256, 256, 0, stream>>>(seed, first_particle, n_local, x0, y0, x1, y1, pose);
+}
+
 // =============================================================================== k_sim_scan
 // The simulator's lidar on the device (slamrs/simulator/src/sim.rs:134-159 against the line
 // segments of scene/ray.rs:55-83): one thread per beam, nearest hit over all segments, beams whose

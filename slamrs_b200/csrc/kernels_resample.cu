@@ -365,7 +365,7 @@ __device__ bool exact_left_fold(cg::cluster_group& cluster, FoldShared<LREG>& sh
 template <int LREG, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __restrict__ w_norm,
-          double* __restrict__ cum, double* __restrict__ fold_scratch, StepCounters* counters) {
+          double* __restrict__ cum, double* __restrict__ fold_scratch, double resample_tau, StepCounters* counters) {
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t crank = cluster.block_rank(), C = cluster.num_blocks();
     __shared__ FoldShared<LREG> sh;
@@ -546,6 +546,8 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         double sq = 0.0;
         for (uint32_t r = 0; r < C; ++r) sq = __dadd_rn(sq, s_sq[r]);
         counters->n_eff = __ddiv_rn(1.0, sq);
+        // adaptive resampling (not in the reference, which always resamples): only when N_eff < tau * N
+        counters->do_resample = (resample_tau > 0.0 && !(__ddiv_rn(1.0, sq) < __dmul_rn(resample_tau, (double)n))) ? 0ull : 1ull;
         counters->fold_rounds = (unsigned long long)max(info_sum.rounds, info_cum.rounds);
         counters->fold_heads = (unsigned long long)max(info_sum.heads, info_cum.heads);
         counters->fold_fallback = (unsigned long long)(info_sum.fallback | (info_cum.fallback << 1));
@@ -557,7 +559,7 @@ static size_t weights_tile_bytes() { return sizeof(double) * FOLD_THREADS * (FOL
 // cluster size by population: 512 threads x 16 elements per CTA, 1 / 2 / 4 / 8 CTAs up to 65,536 particles;
 // beyond that the generic kernel (8 CTAs x 1024 threads, chunks re-read from global memory)
 void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t n_total, double* w_norm,
-                    double* cum, double* fold_scratch, StepCounters* counters) {
+                    double* cum, double* fold_scratch, double resample_tau, StepCounters* counters) {
     uint32_t c = 1u;
     while (c < (uint32_t)W_CLUSTER && (uint64_t)c * FOLD_THREADS * FOLD_LREG < n_total) c <<= 1;
     const bool regs = (uint64_t)c * FOLD_THREADS * FOLD_LREG >= n_total;
@@ -571,8 +573,8 @@ void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t
     attr[0].val.clusterDim.x = c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (regs) cudaLaunchKernelEx(&cfg, k_weights<FOLD_LREG, FOLD_THREADS>, results, n_total, w_norm, cum, fold_scratch, counters);
-    else cudaLaunchKernelEx(&cfg, k_weights<0, FOLD_GENERIC_THREADS>, results, n_total, w_norm, cum, fold_scratch, counters);
+    if (regs) cudaLaunchKernelEx(&cfg, k_weights<FOLD_LREG, FOLD_THREADS>, results, n_total, w_norm, cum, fold_scratch, resample_tau, counters);
+    else cudaLaunchKernelEx(&cfg, k_weights<0, FOLD_GENERIC_THREADS>, results, n_total, w_norm, cum, fold_scratch, resample_tau, counters);
 }
 size_t weights_scratch_doubles() { return 2u * FOLD_MAX_CHUNKS; }
 int weights_trace(long long* out64) {
@@ -623,8 +625,10 @@ __global__ void __launch_bounds__(256)
 k_resample_indices(const ParticleResult* __restrict__ results, const double* __restrict__ cum, uint32_t n,
                    const double* __restrict__ u01_caller, uint64_t seed, uint64_t step, uint32_t* __restrict__ idx,
                    float* __restrict__ pose_next, uint32_t first_particle, uint32_t n_local, bool build_alive,
-                   uint32_t* __restrict__ alive_list, RayLists ray, StepCounters* counters) {
+                   uint32_t* __restrict__ alive_list, RayLists ray, const double* __restrict__ w_norm,
+                   double* __restrict__ carry, StepCounters* counters) {
     __shared__ double s_coarse[RS_COARSE];
+    const bool resample = counters->do_resample != 0ull;   // (adaptive resampling: 0 = every particle stays in place)
     const uint32_t stride = (n + RS_COARSE - 1u) / RS_COARSE;      // weights per block
     const uint32_t n_coarse = (n + stride - 1u) / stride;
     for (uint32_t j = threadIdx.x; j < n_coarse; j += blockDim.x) s_coarse[j] = cum[min(n, (j + 1u) * stride) - 1u];
@@ -642,7 +646,9 @@ k_resample_indices(const ParticleResult* __restrict__ results, const double* __r
     bool ran_off = false;
     uint32_t src_idx = 0xffffffffu;
     if (m0 < n) {
-        src_idx = source_of(m0, &ran_off);
+        if (resample) src_idx = source_of(m0, &ran_off); else src_idx = m0;
+        if (carry != nullptr) carry[m0] = w_norm[m0];     // read by the next update only if this one did not resample
+        if (m0 == 0u) counters->carry_active = resample ? 0ull : 1ull;
         if (ran_off) atomicAdd(&counters->clamped, 1ull);
         idx[m0] = src_idx;
         const ParticleResult src = results[src_idx];
@@ -659,7 +665,7 @@ k_resample_indices(const ParticleResult* __restrict__ results, const double* __r
     uint32_t prev = __shfl_up_sync(0xffffffffu, src_idx, 1);
     if (lane == 0 && m0 > 0 && m0 < n) {
         bool dummy;
-        prev = source_of(m0 - 1u, &dummy);
+        prev = resample ? source_of(m0 - 1u, &dummy) : m0 - 1u;
     }
     const bool alive = m0 < n && (m0 == 0 || prev != src_idx) && src_idx >= first_particle &&
                        src_idx < first_particle + n_local;
@@ -703,10 +709,11 @@ k_resample_indices(const ParticleResult* __restrict__ results, const double* __r
 void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
                              uint32_t n_total, const double* u01_caller, uint64_t seed, uint64_t step,
                              uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
-                             bool build_alive, uint32_t* alive_list, RayLists ray, StepCounters* counters) {
+                             bool build_alive, uint32_t* alive_list, RayLists ray, const double* w_norm, double* carry,
+                             StepCounters* counters) {
     k_resample_indices<<<(n_total + 255) / 256, 256, 0, stream>>>(results, cum, n_total, u01_caller, seed, step, idx,
                                                                  pose_next, first_particle, n_local, build_alive,
-                                                                 alive_list, ray, counters);
+                                                                 alive_list, ray, w_norm, carry, counters);
 }
 
 // =============================================================================== k_mark_alive

@@ -179,4 +179,15 @@ SS_HD double resample_uniform(uint64_t seed, uint64_t step) {
     return u53(w.x[0], w.x[1]);
 }
 
+// Start pose of `particle` for a uniform initialisation over the box [x0, x1) x [y0, y1), heading in
+// [-pi, pi): three 53-bit uniforms from the stream's own counter domains (2: position, 3: heading)
+SS_HD void uniform_pose(uint64_t seed, uint32_t particle, double x0, double y0, double x1, double y1, float* px, float* py,
+                        float* ptheta) {
+    const Words4 a = philox4x32_10(particle, 0u, 0u, 2u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const Words4 b = philox4x32_10(particle, 0u, 0u, 3u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    *px = (float)dadd(x0, dmul(u53(a.x[0], a.x[1]), dadd(x1, -x0)));
+    *py = (float)dadd(y0, dmul(u53(a.x[2], a.x[3]), dadd(y1, -y0)));
+    *ptheta = (float)dadd(-0x1.921fb54442d18p+1, dmul(u53(b.x[0], b.x[1]), 0x1.921fb54442d18p+2));
+}
+
 }  // namespace slamrs_stream

@@ -117,6 +117,7 @@ class GpuPlacement:
     rng_mode: int = _lib.RNG_SHARED_STREAM
     spare_slots: int = 0
     flags: int = 0
+    resample_threshold: float = 0.0   # 0 = resample after every update (the reference); tau: only when N_eff < tau * N
     slot_cells: int = 0      # 0 = whole-grid slots; power of two >= 256 = windowed slots (see slamrs_gpu.h)
 
 
@@ -164,6 +165,7 @@ class GridMapSlam:
         cfg.spare_slots = int(pl.spare_slots)
         cfg.flags = int(pl.flags)
         cfg.slot_cells = int(pl.slot_cells)
+        cfg.resample_threshold = float(pl.resample_threshold)
         if pl.world_size > 1:
             if pl.nccl_id is None or len(pl.nccl_id) != _lib.NCCL_ID_BYTES:
                 raise ValueError("world_size > 1 needs the 128-byte nccl_id shared by all ranks")
@@ -355,6 +357,12 @@ class GridMapSlam:
         raw = np.zeros(int(n.value), np.uint32)
         _lib.check(self._L.slamrs_gpu_get_extents(self._h, particle, _ptr(box), _ptr(raw), C.byref(n)), self._h)
         return tuple(int(v) for v in box[:4]), int(box[4]), np.column_stack([raw & 0xFFFF, raw >> 16]).astype(np.int64)
+
+    def init_uniform(self, box) -> None:
+        """Uniform start poses over box = (x0, y0, x1, y1) metres, heading in [-pi, pi), from the shared stream
+        (global-localisation-style initialisation; README.md:45)."""
+        b = np.ascontiguousarray(box, np.float32).reshape(4)
+        _lib.check(self._L.slamrs_gpu_init_uniform(self._h, _ptr(b)), self._h)
 
     def set_poses(self, xyt) -> None:
         a = np.ascontiguousarray(xyt, np.float32).reshape(self.n_local, 3)

@@ -35,7 +35,7 @@ def test_config_struct_matches_header_layout():
     # uint32 x2, float x3, uint32 x2, (pad) uint64 x2, uint32, int32, uint32 x4, 128 bytes
     assert C.sizeof(_lib.Config) == 208
     assert _lib.Config.n_particles.offset == 32 and _lib.Config.nccl_id.offset == 80
-    assert C.sizeof(_lib.Stats) == 112
+    assert C.sizeof(_lib.Stats) == 120
 
 
 def test_product_does_not_touch_the_oracle():
