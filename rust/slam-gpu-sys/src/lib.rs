@@ -104,6 +104,7 @@ extern "C" {
     pub fn slamrs_gpu_map_extent(h: *mut slamrs_gpu_handle, out_x0y0x1y1: *mut i32) -> c_int;
     pub fn slamrs_gpu_map_window(h: *mut slamrs_gpu_handle, format: u32, x0: i32, y0: i32, x1: i32, y1: i32, out: *mut c_void) -> c_int;
     pub fn slamrs_gpu_effective_particles(h: *mut slamrs_gpu_handle, out: *mut f64) -> c_int;
+    pub fn slamrs_gpu_init_uniform(h: *mut slamrs_gpu_handle, box_x0y0x1y1: *const f32) -> c_int;
     pub fn slamrs_gpu_sim_scan(h: *mut slamrs_gpu_handle, segments_xyxy: *const f32, n_segments: u32, pose_xyt: *const f32, n_beams: u32, scanner_range: f32, out_n: *mut u32) -> c_int;
     pub fn slamrs_gpu_get_scan(h: *mut slamrs_gpu_handle, out_angle: *mut f32, out_dist: *mut f32, out_valid: *mut u8, cap: u32, out_n: *mut u32) -> c_int;
     pub fn slamrs_gpu_last_error(h: *const slamrs_gpu_handle) -> *const c_char;
