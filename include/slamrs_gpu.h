@@ -271,8 +271,8 @@ int slamrs_gpu_get_max_particle(slamrs_gpu_handle* h, uint64_t* out);
  * GLOBAL logical index and must be owned by this rank. */
 int slamrs_gpu_get_cells(slamrs_gpu_handle* h, uint64_t particle, uint32_t* out_cells);
 int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t* cells);
-/* the resampler's view of one particle's grid: informed bounding box {x0, y0, x1, y1} and the slot's row
- * rotation (out_box_shift[4]); per band of 8 slot rows the informed column range x0 | x1 << 16 (0: none),
+/* the resampler's view of one particle's grid: informed bounding box {x0, y0, x1, y1} (out_box_shift[4] is
+ * always 0: slots had a row rotation before they were tiled); per band of 8 slot rows the informed column range x0 | x1 << 16 (0: none),
  * *out_n_bands entries (slot height / 8) -- pass NULL to query the count first */
 int slamrs_gpu_get_extents(slamrs_gpu_handle* h, uint64_t particle, int32_t out_box_shift[5], uint32_t* out_bands,
                            uint32_t* out_n_bands);

@@ -1177,7 +1177,7 @@ int slamrs_gpu_get_cells(slamrs_gpu_handle* h, uint64_t particle, uint32_t* out_
     int32_t slot = 0;
     int rc = local_root_slot(h, particle, &slot);
     if (rc) return rc;
-    // the slot stores its rows rotated; the export kernel undoes that
+    // the slot stores its cells tile by tile (or windowed); the export kernel returns them in logical order
     launch_export_slot(h->stream, h->d_cells + (size_t)slot * h->cells_per_grid, h->d_meta + slot, h->geom, false, h->d_export);
     h->launches++;
     CU_TRY(h, cudaMemcpyAsync(out_cells, h->d_export, sizeof(uint32_t) * h->n_cells, cudaMemcpyDeviceToHost, h->stream));
@@ -1193,7 +1193,7 @@ int slamrs_gpu_set_cells(slamrs_gpu_handle* h, uint64_t particle, const uint32_t
     if (rc) return rc;
     rc = local_slot(h, particle, &slot);
     if (rc) return rc;
-    // extent of the informed cells of the new image (stored unrotated: SlotMeta::ox = 0)
+    // extent of the informed cells of the new image
     const int gw = (int)h->geom.gw, gh = (int)h->geom.gh;
     int x0 = gw, y0 = gh, x1 = -1, y1 = -1;
     for (int y = 0; y < gh; ++y) {
@@ -1252,7 +1252,7 @@ int slamrs_gpu_get_extents(slamrs_gpu_handle* h, uint64_t particle, int32_t out_
         CU_TRY(h, cudaMemcpyAsync(out_bands, h->d_bands + (size_t)slot * h->n_bands, sizeof(uint32_t) * h->n_bands,
                                   cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    out_box_shift[0] = m.x0; out_box_shift[1] = m.y0; out_box_shift[2] = m.x1; out_box_shift[3] = m.y1; out_box_shift[4] = m.ox;
+    out_box_shift[0] = m.x0; out_box_shift[1] = m.y0; out_box_shift[2] = m.x1; out_box_shift[3] = m.y1; out_box_shift[4] = 0;
     if (out_n_bands) *out_n_bands = h->n_bands;
     return SLAMRS_OK;
 }

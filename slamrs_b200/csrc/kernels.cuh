@@ -95,9 +95,7 @@ void launch_sort_beams(cudaStream_t stream, const float* dist, uint32_t n_beams,
 // maps the pool sees the extents of the grids it pulls.
 struct alignas(32) SlotMeta {
     int x0, y0, x1, y1;
-    int ox;              // row rotation: logical column x lives at physical column (x + ox) & xmask (MapGeom)
-    int oy;              // reserved
-    int pad0, pad1;
+    int pad0, pad1, pad2, pad3;   // (32 bytes: one sector per slot)
 };
 static_assert(sizeof(SlotMeta) == 32, "SlotMeta is read by peers as 32 bytes");
 
@@ -257,8 +255,8 @@ void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_
 size_t copy_job_bytes();
 // after a copy kernel: every destination slot now has its source's extent. With `record` the
 // step's moved bytes are also written into the history ring (last copy launch of a step).
-// `realign`: the destination's rotation is the page-aligning one the extent copy used; otherwise
-// (whole-grid copies move rows verbatim) it is the source's
+// `realign` = extent copy (the copy kernel wrote the band tables); otherwise (whole-grid copies move rows
+// verbatim) the band tables are copied here
 void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,
                          MapGeom geom, bool realign, StepCounters* counters, StepRecord* record);
 // add the bytes of a full-grid copy launch to counters->copy_bytes

@@ -76,20 +76,16 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
 // bytes that really moved are counted on the device and are what bench.py's roofline_copy uses.
 
 // A job works in PHYSICAL slot coordinates. x: 32-byte units of one slot row, on a ring when the slot
-// width is a power of two >= 256 (windowed slots wrap; the per-slot row rotation that also used the
-// ring is disabled since tiles -- every shift is 0); y: rows on the ring of the slot's rows (ring size =
+// width is a power of two >= 256 (windowed slots wrap); y: rows on the ring of the slot's rows (ring size =
 // slot height for windowed slots, unbounded otherwise). An "arc" is (start, length).
 struct alignas(16) CopyJob {
     const uint32_t* src;
     const uint32_t* src_bands;
     uint32_t fan;
-    uint32_t src_shift;         // row rotation of the source slot (cells)
-    uint32_t new_shift;         // row rotation every destination gets (page-aligns the source's box)
     uint32_t uy_start, uy_len;  // arc of slot rows to visit, both multiples of BAND_ROWS
-    uint32_t pad[3];
+    uint32_t pad;
     uint32_t* dst[COPY_FAN];
     uint32_t* dst_bands[COPY_FAN];
-    uint16_t dst_old_shift[COPY_FAN];
 };
 static_assert(sizeof(CopyJob) % 16 == 0, "CopyJob is fetched as 16-byte pieces");
 constexpr int COPY_JOB_V4 = (int)(sizeof(CopyJob) / 16);
@@ -151,14 +147,11 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
     if (lane < (int)COPY_FAN) {
         job->dst[lane] = lane < (int)fan ? it.dst : nullptr;
         job->dst_bands[lane] = lane < (int)fan ? it.dst_bands : nullptr;
-        job->dst_old_shift[lane] = (uint16_t)(lane < (int)fan ? dm.ox : 0);
     }
     if (lane == 0) {
         job->src = it.src; job->src_bands = it.src_bands; job->fan = fan;
-        job->src_shift = (uint32_t)sm.ox;
-        job->new_shift = meta_empty(sm) ? 0u : (uint32_t)align_shift(geom, sm.x0);
         job->uy_start = uy_start; job->uy_len = uy_len;
-        job->pad[0] = job->pad[1] = job->pad[2] = 0u;
+        job->pad = 0u;
         if (uy_len) atomicMax(&counters->copy_max_rows, (unsigned long long)uy_len);
     }
 }
@@ -217,19 +210,18 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
         if ((uint32_t)lane < fan) {
             const uint32_t e = s_job.dst_bands[lane][pb];
             if (e) {
-                a_start = (phys_col(geom, e & 0xffffu, (int)s_job.dst_old_shift[lane]) >> 3) & umask;
+                a_start = (phys_col(geom, e & 0xffffu) >> 3) & umask;
                 a_len = ((e >> 16) - (e & 0xffffu)) >> 3;
             }
         } else if (lane == 31) {
             src_entry = __ldg(&s_job.src_bands[pb]);
         }
         src_entry = __shfl_sync(0xffffffffu, src_entry, 31);
-        uint32_t n_start = 0u, n_len = 0u, rot = 0u;   // where the source's columns land in a destination
+        uint32_t n_start = 0u, n_len = 0u;   // the source's columns (same place in source and destination)
         if (src_entry) {
             const uint32_t sx0 = src_entry & 0xffffu;
             n_len = ((src_entry >> 16) - sx0) >> 3;
-            n_start = (phys_col(geom, sx0, (int)s_job.new_shift) >> 3) & umask;
-            rot = (n_start - ((phys_col(geom, sx0, (int)s_job.src_shift) >> 3) & umask)) & umask;
+            n_start = (phys_col(geom, sx0) >> 3) & umask;
             if (lane == 31) { a_start = n_start; a_len = n_len; }
         }
 #pragma unroll
@@ -262,7 +254,7 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
                         const uint32_t du = (u_start + cu) & umask;      // destination unit on the ring
                         off[u] = phys_unit(geom, py, du);
                         if (((du - n_start) & umask) < n_len) {
-                            v[u] = ld_stream_v8(src + phys_unit(geom, py, (du - rot) & umask));
+                            v[u] = ld_stream_v8(src + off[u]);
                             moved++;
                         }
                     }
@@ -308,9 +300,7 @@ __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigne
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (unsigned long long k = tid; k < n; k += stride) {
-        SlotMeta m = *items[k].src_meta;   // sources are never destinations of the same launch
-        if (realign && m.x1 > m.x0) m.ox = align_shift(geom, m.x0);   // the rotation k_copy_prepare chose
-        *items[k].dst_meta = m;
+        *items[k].dst_meta = *items[k].src_meta;   // sources are never destinations of the same launch
     }
     if (!realign) {   // whole-grid copies moved the rows verbatim: the band tables go with them
         const uint32_t nb = bands_per_slot(geom);

@@ -92,8 +92,7 @@ k_likelihood(MapGeom geom, ScanDevice scan, const int32_t* __restrict__ alias_of
     // a clone that has not been written since resampling shares its source's cells (PlanArgs::alias_of)
     const int32_t root = alias_of ? alias_of[r.slot] : r.slot;
     const uint32_t* grid = cells + (size_t)root * cells_per_grid;
-    const SlotMeta sm = meta[root];      // informed extent (outside it a windowed slot must not be read) ...
-    const int shift = sm.ox;             // ... and row rotation of this particle's slot
+    const SlotMeta sm = meta[root];      // informed extent (outside it a windowed slot must not be read)
 
     double lp = log(1.0);
     const uint32_t n_valid = *n_valid_ptr;   // valid beams only, compacted by k_motion (ascending beam index)
@@ -111,9 +110,9 @@ k_likelihood(MapGeom geom, ScanDevice scan, const int32_t* __restrict__ alias_of
                 const float gy = world_to_grid(ey, geom.pos_y, geom.res);
                 if (grid_is_valid(gx, gy, geom.gw, geom.gh)) {
                     const size_t column = (size_t)f32_as_usize(gx), row = (size_t)f32_as_usize(gy);
-                    // index(): map.rs:201-204, then the slot's row rotation
+                    // index(): map.rs:201-204, then the slot's layout
                     if (!geom.windowed || ((int)column >= sm.x0 && (int)column < sm.x1 && (int)row >= sm.y0 && (int)row < sm.y1))
-                        cell[u] = __ldg(&grid[phys_index(geom, (uint32_t)column, (uint32_t)row, shift)]);
+                        cell[u] = __ldg(&grid[phys_index(geom, (uint32_t)column, (uint32_t)row)]);
                 }
             }
         }

@@ -25,7 +25,6 @@ k_export(const uint32_t* __restrict__ cells, const SlotMeta* __restrict__ meta, 
     if (slot < 0) return;  // another GPU owns the estimate
     const uint32_t* grid = cells + (size_t)slot * cells_per_grid;
     const SlotMeta sm = meta[slot];
-    const int shift = sm.ox;
     const uint32_t ww = (uint32_t)(win.z - win.x), wh = (uint32_t)(win.w - win.y);
     const uint32_t n = ww * wh;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -33,7 +32,7 @@ k_export(const uint32_t* __restrict__ cells, const SlotMeta* __restrict__ meta, 
         const int x = win.x + (int)rx, y = win.y + (int)ry;
         // outside the informed extent every cell is the prior (and a windowed slot holds nothing else)
         const bool inside = x >= sm.x0 && x < sm.x1 && y >= sm.y0 && y < sm.y1;
-        const uint32_t cell = inside ? grid[phys_index(geom, (uint32_t)x, (uint32_t)y, shift)] : 0u;
+        const uint32_t cell = inside ? grid[phys_index(geom, (uint32_t)x, (uint32_t)y)] : 0u;
         // a never-informed cell is exactly the prior: log-odds 0 -> 1 - 1/(1 + exp(0)) = 0.5
         out[i] = export_value<T>(cell == 0u ? 0.5 : log_odds_probability(cell_log_odds(cell)));  // Map::likelihood
     }
@@ -61,17 +60,16 @@ void launch_estimate_extent(cudaStream_t stream, const SlotMeta* meta, const Ste
     k_estimate_extent<<<1, 1, 0, stream>>>(meta, counters, out4);
 }
 
-// one slot's grid in logical order (the row rotation undone)
+// one slot's grid in logical order
 __global__ void __launch_bounds__(256)
 k_export_slot(const uint32_t* __restrict__ grid, const SlotMeta* __restrict__ slot_meta, MapGeom geom, bool as_log_odds,
               void* __restrict__ out) {
     const SlotMeta sm = *slot_meta;
-    const int shift = sm.ox;
     const uint32_t n = geom.gw * geom.gh;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t y = i / geom.gw, x = i - y * geom.gw;
         const bool inside = (int)x >= sm.x0 && (int)x < sm.x1 && (int)y >= sm.y0 && (int)y < sm.y1;
-        const uint32_t cell = inside ? grid[phys_index(geom, x, y, shift)] : 0u;
+        const uint32_t cell = inside ? grid[phys_index(geom, x, y)] : 0u;
         if (as_log_odds) reinterpret_cast<double*>(out)[i] = cell_log_odds(cell);
         else reinterpret_cast<uint32_t*>(out)[i] = cell;
     }
@@ -90,7 +88,7 @@ k_import_slot(const uint32_t* __restrict__ image, uint32_t* __restrict__ grid, S
     const uint32_t n = bw * bh;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t y = (uint32_t)m.y0 + i / bw, x = (uint32_t)m.x0 + i % bw;
-        grid[phys_index(geom, x, y, m.ox)] = image[(size_t)y * geom.gw + x];
+        grid[phys_index(geom, x, y)] = image[(size_t)y * geom.gw + x];
     }
 }
 void launch_import_slot(cudaStream_t stream, const uint32_t* image, uint32_t* grid, SlotMeta m, MapGeom geom) {

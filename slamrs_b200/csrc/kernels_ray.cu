@@ -34,36 +34,6 @@ __device__ __forceinline__ void ext_add(int* s_ext, int xmin, int ymin, int xmax
 }
 // union the CTA's touched extent into the slot's box (x aligned to 8 cells); one thread, after a barrier
 constexpr int BOX_ALIGN = 8;   // x alignment of extents in cells: one 256-bit access
-// Row rotation of the slot a ray kernel writes: the slot's own once it holds a grid; for an empty slot
-// (first scan of a lineage) the one that puts the leftmost cell any ray can reach on a page
-// boundary. s_shift[0] receives it; all threads of the CTA call this, with a barrier inside.
-__device__ __forceinline__ int ray_slot_shift(const MapGeom& geom, const ScanDevice& scan, const SlotMeta* meta, float px,
-                                              float py, float ptheta, int cx0, int* s_shift) {
-    const SlotMeta m = *meta;
-    const bool empty = m.x1 <= m.x0 || m.y1 <= m.y0;
-    if (threadIdx.x == 0) s_shift[0] = empty ? 0x7fffffff : m.ox;
-    __syncthreads();
-    if (empty && geom.page_cells) {   // uniform over the CTA
-        int xmin = cx0;
-        for (uint32_t b = threadIdx.x; b < scan.n_beams; b += blockDim.x) {
-            float ex, ey;
-            beam_endpoint(px, py, ptheta, scan.angle[b], scan.dist[b], &ex, &ey);
-            const float gx = floorf(world_to_grid(ex, geom.pos_x, geom.res));
-            // a ray reaches at most two cells beyond its endpoint cell (map.rs:97); NaN / far-out -> 0
-            const int reach = (gx >= 2.0f && gx < 1.0e6f) ? (int)gx - 2 : 0;
-            xmin = min(xmin, reach);
-        }
-        atomicMin(&s_shift[0], max(0, xmin));
-        __syncthreads();
-        if (threadIdx.x == 0) s_shift[0] = align_shift(geom, s_shift[0] & ~7);
-        __syncthreads();
-    } else if (empty) {
-        if (threadIdx.x == 0) s_shift[0] = 0;
-        __syncthreads();
-    }
-    return s_shift[0];
-}
-
 // Windowed slots: would the informed extent still fit the slot after this scan? `reach` bounds how far
 // from the start cell a ray can write (measured range in cells + the slack the host adds). The test is
 // conservative (bounding square of the reach) and uniform over the CTA.
@@ -76,10 +46,9 @@ __device__ __forceinline__ bool window_would_overflow(const MapGeom& geom, const
     return (uint32_t)(x1 - x0) > geom.pw || (uint32_t)(y1 - y0) > geom.ph;
 }
 
-__device__ __forceinline__ void ext_commit(const int* s_ext, SlotMeta* meta, int gw, int shift) {
+__device__ __forceinline__ void ext_commit(const int* s_ext, SlotMeta* meta, int gw) {
     if (s_ext[2] < s_ext[0]) return;
     SlotMeta b = *meta;
-    b.ox = shift;
     const int am = BOX_ALIGN - 1;
     const int x0 = s_ext[0] & ~am, x1 = min(gw, (s_ext[2] + 1 + am) & ~am), y0 = s_ext[1], y1 = s_ext[3] + 1;
     if (b.x1 <= b.x0) { b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; }
@@ -164,7 +133,6 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     __shared__ int s_row_off[RAY_MAX_ROWS + 1];   // first window cell of each row (+ total at [wh])
     __shared__ int s_row_x[RAY_MAX_ROWS];         // x0 | (width << 16)
     __shared__ int s_ext[4];
-    __shared__ int s_shift[1];
     if ((unsigned long long)blockIdx.x >= counters->n_alive) return;
     const uint32_t p = alive_list[blockIdx.x];
     ext_init(s_ext);
@@ -183,7 +151,6 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
         if (threadIdx.x == 0) atomicAdd(&counters->window_overflow, 1ull);
         return;   // the grid is left as it was; the step reports SLAMRS_E_WINDOW
     }
-    const int shift = ray_slot_shift(geom, scan, &meta[slot_of[p]], px, py, ptheta, cx, s_shift);
     uint32_t* bands = bands_all + (size_t)slot_of[p] * bands_per_slot(geom);
     band_init(s_blo, s_bhi);
 
@@ -255,7 +222,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                     }
                 }
                 if (!in_window) {  // beyond the window (range larger than shared memory allows)
-                    global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, shift)], inc, &saturated);
+                    global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y)], inc, &saturated);
                     ext_add(s_ext, x, y, x, y);
                     band_add(s_blo, s_bhi, band0, y, x, x);
                     band_add_global(bands, geom, band0, x, y);
@@ -294,7 +261,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
                         exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 3);
                         eymin = min(eymin, wy0 + lo); eymax = max(eymax, wy0 + lo);
                         band_add(s_blo, s_bhi, band0, wy0 + lo, gx0, gx0 + 3);
-                        gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + lo), shift));
+                        gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + lo)));
                     }
                 }
             }
@@ -318,7 +285,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
             for (int c = threadIdx.x & 31; c < w; c += 32) {
                 const uint32_t d = s_win[off + c];
                 if (d != 0u) {
-                    uint32_t* g = grid + phys_index(geom, (uint32_t)(x0 + c), (uint32_t)(wy0 + ly), shift);
+                    uint32_t* g = grid + phys_index(geom, (uint32_t)(x0 + c), (uint32_t)(wy0 + ly));
                     *g = cell_sat_add(*g, d, &saturated);
                     exmin = min(exmin, x0 + c); exmax = max(exmax, x0 + c);
                     eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
@@ -330,7 +297,7 @@ k_ray_update(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ r
     ext_add(s_ext, exmin, eymin, exmax, eymax);
     __syncthreads();
     band_commit(s_blo, s_bhi, band0, bands, geom);
-    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw, shift);
+    if (threadIdx.x == 0) ext_commit(s_ext, &meta[slot_of[p]], (int)geom.gw);
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 }
@@ -392,7 +359,7 @@ __device__ unsigned long long g_ray_trace_items[2];
 __device__ __noinline__ void ray_walk_beams(const MapGeom& geom, const ScanDevice& scan, float px, float py, float ptheta, float sx,
                                             float sy, int cx0, int cy0, int rad, int wy0, int wh, int band0, uint32_t* s_win,
                                             const int2* s_row, const uint32_t* s_rowb, int* s_blo, int* s_bhi, int* s_ext,
-                                            uint32_t* __restrict__ grid, uint32_t* __restrict__ bands, int slot_shift, bool fused,
+                                            uint32_t* __restrict__ grid, uint32_t* __restrict__ bands, bool fused,
                                             uint32_t* s_nspill_p, uint32_t* __restrict__ my_spill, bool* saturated_p,
                                             uint32_t* spilled_p, uint32_t* cell_steps_p) {
     const int gw = (int)geom.gw, gh = (int)geom.gh;
@@ -407,7 +374,7 @@ __device__ __noinline__ void ray_walk_beams(const MapGeom& geom, const ScanDevic
             const uint32_t k = atomicAdd(s_nspill_p, 1u);
             if (k < RAY_SPILL_CAP) my_spill[k] = (uint32_t)x | ((uint32_t)y << 15) | (inc == CELL_OCC_INC ? 0x40000000u : 0u);
         } else {
-            global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y, slot_shift)], inc, &saturated);
+            global_cell_add(&grid[phys_index(geom, (uint32_t)x, (uint32_t)y)], inc, &saturated);
         }
     };
     const bool disc_in_grid = cx0 - rad >= 0 && cx0 + rad < gw && cy0 - rad >= 0 && cy0 + rad < gh;
@@ -766,17 +733,16 @@ __device__ __noinline__ void ray_fused_writeback(const MapGeom& geom, int32_t sl
         if (ns > RAY_SPILL_CAP && threadIdx.x == 0) atomicAdd(&counters->fuse_overflow, 1ull);
         for (uint32_t k = threadIdx.x; k < min(ns, RAY_SPILL_CAP); k += blockDim.x) {
             const uint32_t e = my_spill[k];
-            global_cell_add(&grid[phys_index(geom, e & 0x7fffu, (e >> 15) & 0x7fffu, 0)],
+            global_cell_add(&grid[phys_index(geom, e & 0x7fffu, (e >> 15) & 0x7fffu)],
                             (e & 0x40000000u) ? CELL_OCC_INC : CELL_FREE_INC, &saturated);
         }
     }
     if (threadIdx.x == 0) {
         // the slot now holds the source's extent plus what this scan touched
         SlotMeta nm = sm;
-        nm.ox = 0;
         if (!(nm.x1 > nm.x0 && nm.y1 > nm.y0)) { nm.x0 = nm.y0 = nm.x1 = nm.y1 = 0; }
         meta[slot] = nm;
-        ext_commit(s_ext, &meta[slot], gw, 0);
+        ext_commit(s_ext, &meta[slot], gw);
         __threadfence();
         atomicAdd(&done[root], 1u);        // the root has been read: its owner may write it
     }
@@ -814,7 +780,6 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     __shared__ int2 s_row[RAY_MAX_ROWS + 1];            // .x = first window cell of the row, .y = x0 | width << 16
     __shared__ uint32_t s_rowb[RAY_MAX_ROWS];           // shared byte address of column x = 0 of the row
     __shared__ int s_ext[4];
-    __shared__ int s_shift[1];
     __shared__ unsigned long long s_next;
     const unsigned long long n_items = counters->n_alive;
     const int gw = (int)geom.gw, gh = (int)geom.gh;
@@ -865,7 +830,6 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
             if (threadIdx.x == 0) atomicAdd(&counters->window_overflow, 1ull);
             continue;   // the grid is left as it was; the step reports SLAMRS_E_WINDOW
         }
-        const int slot_shift = fused ? 0 : ray_slot_shift(geom, scan, &meta[job.slot], px, py, ptheta, cx0, s_shift);
         uint32_t* bands = bands_all + (size_t)job.slot * n_bands_slot;
         band_init(s_blo, s_bhi);
 
@@ -912,7 +876,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         RAY_STAMP(1);
         if (start_inside)
             ray_walk_beams(geom, scan, px, py, ptheta, sx, sy, cx0, cy0, rad, wy0, wh, band0, s_win, s_row, s_rowb, s_blo, s_bhi, s_ext,
-                           grid, bands, slot_shift, fused, &s_nspill, my_spill, &saturated, &spilled, &cell_steps);
+                           grid, bands, fused, &s_nspill, my_spill, &saturated, &spilled, &cell_steps);
         __syncthreads();
         RAY_STAMP(2);
 
@@ -984,7 +948,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                             const int gx0 = (row.y & 0xffff) + 8 * lane;
                             exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
                             eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
-                            gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
+                            gp[j] = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly)));
                         }
                     }
                 }
@@ -1018,7 +982,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                 exmin = min(exmin, gx0); exmax = max(exmax, gx0 + 7);
                 eymin = min(eymin, wy0 + ly); eymax = max(eymax, wy0 + ly);
                 band_add(s_blo, s_bhi, band0, wy0 + ly, gx0, gx0 + 7);
-                uint4* gpt = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly), slot_shift));
+                uint4* gpt = reinterpret_cast<uint4*>(grid + phys_index(geom, (uint32_t)gx0, (uint32_t)(wy0 + ly)));
                 uint4 ta = gpt[0], tb = gpt[1];
                 merge_group(ta, tb, dd);
                 gpt[0] = ta;
@@ -1028,7 +992,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         ext_add(s_ext, exmin, eymin, exmax, eymax);
         __syncthreads();
         band_commit(s_blo, s_bhi, band0, bands, geom);
-        if (threadIdx.x == 0) ext_commit(s_ext, &meta[job.slot], (int)geom.gw, slot_shift);
+        if (threadIdx.x == 0) ext_commit(s_ext, &meta[job.slot], (int)geom.gw);
         RAY_STAMP(5);
 #ifdef SLAMRS_RAY_TRACE
         if (threadIdx.x == 0) atomicAdd(&g_ray_trace_items[1], 1ull);

@@ -67,25 +67,20 @@ __device__ __forceinline__ long long f32_as_isize(float v) {
 struct MapGeom {
     float pos_x, pos_y, res;
     uint32_t gw, gh;           // logical grid, cells
-    // Physical slot. A slot stores logical cell (x, y) at row (y & ymask), column (x + shift) & xmask,
-    // `shift` per slot (SlotMeta::ox, a multiple of 8 cells).
-    //  * Row rotation (superseded by tiles, kept for row-major power-of-two slots, of which there are none
-    //    today: every power of two >= 256 is tiled, so page_cells = 0 and every shift is 0): the resampler
-    //    picks the shift of every grid it writes so that the informed extent starts on a page_cells
-    //    boundary (1 KiB of cells), +15 % copy bandwidth on row-major slots (profiles/r1_copy_tuning.md).
+    // Physical slot. A slot stores logical cell (x, y) at row (y & ymask), column x & xmask.
     //  * Windowed slots (pw < gw or ph < gh, powers of two): a slot holds only a pw x ph torus of the
     //    logical grid. The mapping is injective on any extent that fits pw x ph, and a grid's informed
     //    extent is all a slot has to hold (everything else is the prior). Reads outside the extent
     //    return the prior without touching memory; an extent that would outgrow the window is an error
     //    (SLAMRS_E_WINDOW). This is what lets 32,768 particles with 2048 x 2048 maps share one B200.
     uint32_t pw, ph;           // slot width / height in cells (= gw, gh when not windowed)
-    uint32_t xmask, ymask, page_cells;
+    uint32_t xmask, ymask;
     uint32_t windowed;
     //  * Tiled slots (slot width a multiple of 32, height a multiple of 8): cells are stored tile by
     //    tile, a tile = 8 rows x 32 columns = 1 KiB = one DRAM page, tiles row-major. DRAM cost is per
     //    page touched, and the informed part of a band of 8 rows (~144 of 1024 columns) is 5 full tiles
-    //    instead of 8 half-used row segments. The resampler copies whole tiles. Tiles make the row
-    //    rotation pointless (every tile is page-aligned), so tiled slots have page_cells = 0.
+    //    instead of 8 half-used row segments. The resampler copies whole tiles. (Row-major slots -- sides
+    //    that are not multiples of 32 x 8 cells, e.g. the reference's 200^2 preset -- keep plain rows.)
     uint32_t tiled, tiles_per_row;
 };
 constexpr uint32_t TILE_COLS = 32, TILE_ROWS = 8, TILE_CELLS = TILE_COLS * TILE_ROWS;
@@ -103,17 +98,12 @@ __host__ __device__ inline MapGeom make_map_geom(float pos_x, float pos_y, float
 #endif
     g.tiled = (SLAMRS_TILED && g.pw % TILE_COLS == 0u && g.ph % TILE_ROWS == 0u) ? 1u : 0u;
     g.tiles_per_row = g.pw / TILE_COLS;
-    const bool ring = g.pw >= 256u && is_pow2_u32(g.pw);     // columns wrap (windowed slots, row rotation)
+    const bool ring = g.pw >= 256u && is_pow2_u32(g.pw);     // columns wrap (windowed slots)
     g.xmask = ring ? g.pw - 1u : 0xffffffffu;
-    g.page_cells = (ring && !g.tiled) ? 256u : 0u;
     g.ymask = (g.windowed && is_pow2_u32(g.ph)) ? g.ph - 1u : 0xffffffffu;
     return g;
 }
-// shift that puts logical column x0 (a multiple of 8) on a page boundary
-__host__ __device__ inline int align_shift(const MapGeom& g, int x0) {
-    return g.page_cells ? (int)((0u - (uint32_t)x0) & (g.page_cells - 1u)) : 0;
-}
-__host__ __device__ inline uint32_t phys_col(const MapGeom& g, uint32_t x, int shift) { return (x + (uint32_t)shift) & g.xmask; }
+__host__ __device__ inline uint32_t phys_col(const MapGeom& g, uint32_t x) { return x & g.xmask; }
 // Band extents. Besides its bounding box, every slot records per band of 8 rows the column range
 // [x0, x1) (multiples of 8) that may hold informed cells, packed x0 | x1 << 16, 0 = nothing in this
 // band. Walls occlude most of a lidar's disc: summed over the bands the ranges cover ~58 % of the
@@ -123,8 +113,8 @@ constexpr int BAND_ROWS = 8;
 __host__ __device__ inline uint32_t bands_per_slot(const MapGeom& g) { return (g.ph + BAND_ROWS - 1u) / BAND_ROWS; }
 __host__ __device__ inline uint32_t phys_band(const MapGeom& g, uint32_t y) { return (y & g.ymask) / BAND_ROWS; }
 // offset of logical cell (x, y) inside a slot
-__host__ __device__ inline size_t phys_index(const MapGeom& g, uint32_t x, uint32_t y, int shift) {
-    const uint32_t py = y & g.ymask, px = phys_col(g, x, shift);
+__host__ __device__ inline size_t phys_index(const MapGeom& g, uint32_t x, uint32_t y) {
+    const uint32_t py = y & g.ymask, px = phys_col(g, x);
     if (g.tiled)
         return ((size_t)(py / TILE_ROWS) * g.tiles_per_row + px / TILE_COLS) * TILE_CELLS + (py % TILE_ROWS) * TILE_COLS +
                px % TILE_COLS;
