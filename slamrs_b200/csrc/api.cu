@@ -86,6 +86,7 @@ struct slamrs_gpu_handle {
     RayItem* d_ray_items = nullptr;      // work list of the fused ray update (n_local)
     uint32_t* d_readers = nullptr;       // per slot: clones that read it in this step | per slot: clones that have (2 x n_slots)
     uint32_t* d_ray_spill = nullptr;     // scratch of the fused ray update
+    void* d_ray_xchg = nullptr;          // per surviving particle: lower half -> upper half exchange record
     StepCounters* d_counters = nullptr;
     StepCounters* h_counters = nullptr;  // pinned
     double* d_export = nullptr;
@@ -272,7 +273,7 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
     cudaFree(h->d_copies); cudaFree(h->d_leaders); cudaFree(h->d_alive); cudaFree(h->d_jobs);
-    cudaFree(h->d_ray_items); cudaFree(h->d_readers); cudaFree(h->d_ray_spill);
+    cudaFree(h->d_ray_items); cudaFree(h->d_readers); cudaFree(h->d_ray_spill); cudaFree(h->d_ray_xchg);
     cudaFree(h->d_alias); cudaFree(h->d_mat_items); cudaFree(h->d_mat_leaders); cudaFree(h->d_mat_roots);
     cudaFree(h->d_export); cudaFree(h->d_barrier); cudaFree(h->d_peer_cells); cudaFree(h->d_peer_meta);
     cudaFree(h->d_peer_results); cudaFree(h->d_peer_flags); cudaFree(h->d_peer_bands);
@@ -570,7 +571,8 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_mat_roots, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_alive, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_ray_items, sizeof(RayItem) * 2 * (size_t)h->n_local));   // clones | owners
-    CREATE_CU(cudaMalloc(&h->d_readers, sizeof(uint32_t) * 2 * (size_t)h->n_slots));
+    CREATE_CU(cudaMalloc(&h->d_readers, sizeof(uint32_t) * (2 * (size_t)h->n_slots + h->n_local)));   // readers | done | xflag
+    CREATE_CU(cudaMalloc(&h->d_ray_xchg, ray_half_xchg_bytes() * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_ray_spill, sizeof(uint32_t) * ray_spill_scratch_words(h->num_sms)));
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
     memset(h->h_counters, 0, sizeof(StepCounters));
@@ -713,8 +715,10 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     const bool force_generic = (h->cfg.flags & SLAMRS_FLAG_GENERIC_RAY_KERNEL) != 0;
     const bool fuse = h->defer && !all_particles &&
                       ray_update_can_fuse(h->geom, h->n_beams, h->cells_per_grid, force_generic, h->radius_cells);
-    if (fuse)   // per-slot reader / done counters of the fused ray update (off the critical path: long before their use)
-        CU_TRY(h, cudaMemsetAsync(h->d_readers, 0, sizeof(uint32_t) * 2 * (size_t)h->n_slots, s));
+    // per-slot reader / done counters and per-item hand-over flags of the ray update (off the critical path: long before their use)
+    const bool half_items = ray_update_can_fuse(h->geom, h->n_beams, h->cells_per_grid, force_generic, h->radius_cells);
+    if (half_items)
+        CU_TRY(h, cudaMemsetAsync(h->d_readers, 0, sizeof(uint32_t) * (2 * (size_t)h->n_slots + h->n_local), s));
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->defer ? h->d_alias : nullptr, h->d_cells, h->d_meta, h->cells_per_grid,
@@ -744,8 +748,8 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     //     ray kernel does it while it integrates the scan (fused: k_resample_indices lists the survivors as
     //     clones | owners, no copy kernels), or they are listed now and copied after PROF_MARK 3. Before the
     //     planner starts: both write the alias table.
-    RayLists ray{nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (fuse) ray = RayLists{h->d_ray_items, h->d_ray_items + h->n_local, h->d_slot[cur], h->d_alias, h->d_readers};
+    RayLists ray{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (fuse) ray = RayLists{h->d_ray_items, h->d_ray_items + h->n_local, h->d_slot[cur], h->d_alias, h->d_readers, h->d_meta};
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, !all_particles, h->d_alive, ray, h->d_wnorm, h->d_carry,
                             h->d_counters);
@@ -802,7 +806,8 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     CU_TRY(h, launch_ray_update(s, h->geom, scan, h->d_results, h->first, h->n_local, h->d_alive,
                                 fuse ? h->d_ray_items : nullptr, fuse ? h->d_ray_items + h->n_local : nullptr,
                                 fuse ? h->d_readers : nullptr,
-                                fuse ? h->d_readers + h->n_slots : nullptr, h->d_ray_spill, h->d_slot[cur],
+                                fuse ? h->d_readers + h->n_slots : nullptr, h->d_readers + 2 * (size_t)h->n_slots, h->d_ray_xchg,
+                                h->d_ray_spill, h->d_slot[cur],
                                 h->d_cells, h->d_meta, h->d_bands, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
                                 force_generic, h->num_sms));
     h->launches++;
@@ -1354,7 +1359,7 @@ int slamrs_gpu_debug_resample(int device, const double* raw_weights, uint32_t n,
         launch_weights(nullptr, res.p, n, wn.p, cum.p, fold.p, 0.0, cnt.p);
         cudaEventRecord(ev[1], nullptr);
         launch_resample_indices(nullptr, res.p, cum.p, n, u.p, 0, 0, idx.p, nullptr, 0, 0, false, nullptr,
-                                RayLists{nullptr, nullptr, nullptr, nullptr, nullptr}, wn.p, nullptr, cnt.p);
+                                RayLists{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, wn.p, nullptr, cnt.p);
         cudaEventRecord(ev[2], nullptr);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { for (auto& x : ev) cudaEventDestroy(x); return fail(nullptr, SLAMRS_E_CUDA, cudaGetErrorString(e)); }

@@ -110,7 +110,12 @@ struct CopyItem {
 
 // One work item of the ray update: a surviving local particle, its slot and the slot whose cells it
 // logically holds (root != slot: a clone that k_ray_update_packed makes private while it integrates the scan)
-struct RayItem { uint32_t particle; int32_t slot; int32_t root; uint32_t pad; };
+struct RayItem {
+    uint32_t particle;
+    int32_t slot, root;
+    int32_t old_y0, old_y1;   // clone: rows [old_y0, old_y1) the slot's previous tenant had informed (to be cleared)
+    uint32_t pad;
+};
 // Work lists of the fused ray update, filled by k_resample_indices: clones first (counters->ray_items_front of
 // them), then the particles that own their slot (counters->ray_items_back); readers[root]++ per clone (zeroed by
 // the caller); every listed clone's alias entry becomes the identity and counters->n_mat counts them.
@@ -121,6 +126,7 @@ struct RayLists {
     const int32_t* slot_of;
     int32_t* alias_of;
     uint32_t* readers;
+    SlotMeta* meta;
 };
 // ---- launch wrappers (all asynchronous on `stream`) ----
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
@@ -146,6 +152,7 @@ void launch_peer_goodbye(cudaStream_t stream, unsigned long long* const* peer_fl
 // the fused path applies (packed window kernel, whole-grid tiled slots)
 bool ray_update_can_fuse(const MapGeom& geom, uint32_t n_beams, size_t cells_per_grid, bool force_generic, int radius_cells);
 size_t ray_spill_scratch_words(int num_sms);
+size_t ray_half_xchg_bytes();               // per surviving particle: what its lower half hands to its upper half
 int ray_trace(unsigned long long* out18);   // tuning builds (-DSLAMRS_RAY_TRACE): cycles per phase, summed over CTAs   // scratch of the fused path (uint32 words)
 // returns the shared-memory window size in cells through *window_cells
 // alive_list / counters->n_alive select the local particles to integrate (see launch_mark_alive); with the work
@@ -154,6 +161,7 @@ int ray_trace(unsigned long long* out18);   // tuning builds (-DSLAMRS_RAY_TRACE
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
                               const RayItem* clones, const RayItem* owners, const uint32_t* readers, uint32_t* done,
+                              uint32_t* xflag /* per work item, zeroed by the caller */, void* xchg /* n_local * ray_half_xchg_bytes() */,
                               uint32_t* spill_scratch,
                               const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,

@@ -1006,6 +1006,697 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
     if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
 }
 
+// =============================================================================== k_ray_update_half
+// The packed ray update with HALF a particle per work item (whole-grid tiled slots). A particle's rays
+// either never leave the rows at or above its start row (y_inc >= 0: the "upper" half) or never leave the
+// rows at or below it (y_inc < 0: the "lower" half), so each half needs only half the disc window
+// (<= 54 KB at a 6 m / 5 cm window): four CTAs of 192 threads per SM instead of two of 384, 592 resident
+// work slots instead of 296. With ~450 survivors per step the full-item kernel ran two rounds, the
+// second on a third of the machine; 900 half items on 592 slots finish in about one item time
+// (profiles/r2_ray_half.md).
+//
+// Ownership. The lower half owns the rows below the start row, the upper half the start row and
+// everything above: each copies / writes only rows it owns, so the two CTAs never touch the same cell.
+// The one shared row is the start row, which every lower ray also crosses: the lower CTA hands its
+// window row for it to the upper CTA through a small exchange record (plus what the upper half needs to
+// write the extent of the band both halves share), and the upper CTA adds it when it writes that row.
+// The lower half is listed right before the upper half, so the upper CTA only ever waits for a CTA that
+// is already running.
+//
+// One write-back path for clones and owners: read the ROOT slot's tiles (a clone's source; an owner's own
+// slot), add the window, write the particle's OWN slot -- see k_ray_update_packed for the clone / owner
+// protocol (readers / done), which is unchanged except that a clone counts as two readers.
+constexpr int HALF_MAX_ROWS = RAY_MAX_RADIUS + 1;
+constexpr int HALF_MAX_BANDS = HALF_MAX_ROWS / BAND_ROWS + 2;
+constexpr uint32_t HALF_XCHG_GROUPS = 36;
+constexpr uint32_t HALF_XCHG_HITS = 60;
+struct alignas(16) HalfXchg {           // lower half -> upper half of the same particle
+    uint4 row[HALF_XCHG_GROUPS];        // the lower CTA's window row for the start row (packed 16-bit cells, 8 per group)
+    int band_lo, band_hi;               // columns the lower half touched in its rows of the shared band (hi < lo: none)
+    uint32_t n_hits;                    // exact-path hits of lower rays on the start row (applied by the upper CTA)
+    uint32_t pad;
+    uint32_t hits[HALF_XCHG_HITS];
+};
+static_assert(sizeof(HalfXchg) % 16 == 0, "exchange records are accessed as 16-byte pieces");
+
+// cells of the half-disc window of radius `radius`: rows start and end on multiples of 8 columns, so the size
+// depends on the start column modulo 8 -- the largest of the eight cases (clipping at the grid only shrinks it)
+__host__ __device__ inline int ray_window_cells_upper_bound_half(int radius) {
+    int worst = 0;
+    for (int a = 0; a < 8; ++a) {
+        int total = 0;
+        for (int dy = 0; dy <= radius; ++dy) {
+            const int hw = isqrt_small(radius * radius - dy * dy), cx = 4096 + a;
+            total += ((cx + hw + 1 + 7) & ~7) - ((cx - hw) & ~7);
+        }
+        worst = total > worst ? total : worst;
+    }
+    return worst;
+}
+
+// The walk of this half's beams (s_beam: indices into the scan) into the half-disc window. Same arithmetic as
+// ray_walk_beams; hits that bypass the window are always parked (the slot receives its cells at write-back).
+__device__ __noinline__ void ray_walk_half(const MapGeom& geom, const ScanDevice& scan, const uint16_t* s_beam, uint32_t n_mine,
+                                           float px, float py, float ptheta, float sx, float sy, int cx0, int cy0, int rad,
+                                           bool upper, int wy0, int wh, int band0, uint32_t* s_win, const int2* s_row,
+                                           const uint32_t* s_rowb, int* s_blo, int* s_bhi, int* s_ext, uint32_t* s_nspill_p,
+                                           uint32_t* __restrict__ my_spill, uint32_t* spilled_p, uint32_t* cell_steps_p) {
+    const int gw = (int)geom.gw, gh = (int)geom.gh;
+    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
+    uint32_t spilled = 0, cell_steps = 0;
+    auto exact_add = [&](int x, int y, uint32_t inc) {
+        const uint32_t k = atomicAdd(s_nspill_p, 1u);
+        if (k < RAY_SPILL_CAP) my_spill[k] = (uint32_t)x | ((uint32_t)y << 15) | (inc == CELL_OCC_INC ? 0x40000000u : 0u);
+    };
+    // the window holds every in-grid cell within `rad` of the start in this half's rows
+    const bool disc_in_grid = cx0 - rad >= 0 && cx0 + rad < gw && (upper ? cy0 + rad < gh : cy0 - rad >= 0);
+    uint32_t rowb_base = (uint32_t)__cvta_generic_to_shared(s_rowb);
+    asm volatile("" : "+r"(rowb_base));
+    auto load_rowb = [&](int row) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(rowb_base + 4u * (uint32_t)row) : "memory");
+        return v;
+    };
+    for (uint32_t t = threadIdx.x; t < n_mine; t += blockDim.x) {
+        const uint32_t b = s_beam[t];
+        const float dist = scan.dist[b];
+        float ex, ey;
+        beam_endpoint(px, py, ptheta, scan.angle[b], dist, &ex, &ey);
+        const float x1 = world_to_grid(ex, geom.pos_x, geom.res);
+        const float y1 = world_to_grid(ey, geom.pos_y, geom.res);
+        const RayClassifier cls = make_ray_classifier(__fdiv_rn(dist, geom.res), scan.valid[b] != 0);
+
+        // GridRayIterator::new (ray.rs:21-77) -- identical arithmetic to ray_walk_acc
+        const float delta_x = fabsf(__fsub_rn(x1, sx)), delta_y = fabsf(__fsub_rn(y1, sy));
+        const float fx0 = floorf(sx), fy0 = floorf(sy);
+        unsigned long long n = 1ull + 2ull;   // additional_steps = 2 (map.rs:97)
+        unsigned long long ax = 0ull, ay = 0ull;   // |endpoint cell - start cell| per axis
+        int x_inc, y_inc;
+        float error;
+        if (delta_x == 0.0f) {
+            x_inc = 0;
+            error = __int_as_float(0x7f800000);
+        } else if (x1 > sx) {
+            x_inc = 1;
+            ax = (unsigned long long)f32_as_isize(__fsub_rn(floorf(x1), (float)cx0));
+            error = __fmul_rn(__fsub_rn(__fadd_rn(fx0, 1.0f), sx), delta_y);
+        } else {
+            x_inc = -1;
+            ax = (unsigned long long)(long long)cx0 - (unsigned long long)f32_as_isize(floorf(x1));
+            error = __fmul_rn(__fsub_rn(sx, fx0), delta_y);
+        }
+        if (delta_y == 0.0f) {
+            y_inc = 0;
+            error = __fsub_rn(error, __int_as_float(0x7f800000));
+        } else if (y1 > sy) {
+            y_inc = 1;
+            ay = (unsigned long long)f32_as_isize(floorf(y1)) - (unsigned long long)(long long)cy0;
+            error = __fsub_rn(error, __fmul_rn(__fsub_rn(__fadd_rn(fy0, 1.0f), sy), delta_x));
+        } else {
+            y_inc = -1;
+            ay = (unsigned long long)(long long)cy0 - (unsigned long long)f32_as_isize(floorf(y1));
+            error = __fsub_rn(error, __fmul_rn(__fsub_rn(sy, fy0), delta_x));
+        }
+        n += ax + ay;   // wrapping isize arithmetic, then `as usize`
+        const unsigned long long cap = (unsigned long long)geom.gw + geom.gh + 8ull;
+        int remaining = (int)(n < cap ? n : cap);
+        cell_steps += (uint32_t)remaining;
+
+        const float x_step = (float)x_inc, y_step = (float)y_inc;
+        float cxf = __fadd_rn((float)cx0, 0.5f), cyf = __fadd_rn((float)cy0, 0.5f);
+        float dxs = __fsub_rn(sx, cxf), dys = __fsub_rn(sy, cyf);
+        float dx2 = __fmul_rn(dxs, dxs), dy2 = __fmul_rn(dys, dys);
+
+        bool fast = false;
+        if (disc_in_grid && ax < 4096ull && ay < 4096ull) {
+            const int cxa = (int)ax + 2, cya = (int)ay + 2;
+            fast = cxa * cxa + cya * cya <= rad * rad;
+        }
+        if (fast) {
+            uint32_t x2 = 2u * (uint32_t)cx0;         // twice the current column
+            const uint32_t x_inc2 = (uint32_t)(2 * x_inc);
+            int ly = cy0 - wy0;
+            uint32_t rb = load_rowb(ly);
+            while (remaining > 0) {                    // free run
+                const float acc = __fadd_rn(dx2, dy2);
+                if (!(acc < cls.free_below)) break;
+                const uint32_t c2 = rb + x2;           // shared byte address of the 16-bit window cell
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(c2 & ~3u), "r"((c2 & 2u) ? 0x10000u : 1u) : "memory");
+                if (error > 0.0f) {
+                    error = __fsub_rn(error, delta_x);
+                    cyf = __fadd_rn(cyf, y_step);
+                    dys = __fsub_rn(sy, cyf);
+                    dy2 = __fmul_rn(dys, dys);
+                    ly += y_inc;
+                    rb = load_rowb(ly);
+                } else {
+                    error = __fadd_rn(error, delta_y);
+                    cxf = __fadd_rn(cxf, x_step);
+                    dxs = __fsub_rn(sx, cxf);
+                    dx2 = __fmul_rn(dxs, dxs);
+                    x2 += x_inc2;
+                }
+                remaining -= 1;
+            }
+            if (cls.mid_inc != 0u) {                   // occupied run (hits only)
+                while (remaining > 0) {
+                    const float acc = __fadd_rn(dx2, dy2);
+                    if (acc > cls.prior_above) break;
+                    const uint32_t c2 = rb + x2;
+                    const uint32_t shift = ((c2 & 2u) << 3) + PK_FREE_BITS;
+                    uint32_t old;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(old) : "r"(c2 & ~3u) : "memory");
+                    bool done_here = false;
+                    for (;;) {
+                        if (((old >> shift) & PK_OCC_MAX) == PK_OCC_MAX) break;
+                        uint32_t seen;
+                        asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;"
+                                     : "=r"(seen) : "r"(c2 & ~3u), "r"(old), "r"(old + (1u << shift)) : "memory");
+                        if (seen == old) { done_here = true; break; }
+                        old = seen;
+                    }
+                    if (!done_here) {
+                        const int x = (int)(x2 >> 1), y = wy0 + ly;
+                        exact_add(x, y, CELL_OCC_INC);
+                        ext_add(s_ext, x, y, x, y);
+                        band_add(s_blo, s_bhi, band0, y, x, x);
+                        spilled++;
+                    }
+                    if (error > 0.0f) {
+                        error = __fsub_rn(error, delta_x);
+                        cyf = __fadd_rn(cyf, y_step);
+                        dys = __fsub_rn(sy, cyf);
+                        dy2 = __fmul_rn(dys, dys);
+                        ly += y_inc;
+                        rb = load_rowb(ly);
+                    } else {
+                        error = __fadd_rn(error, delta_y);
+                        cxf = __fadd_rn(cxf, x_step);
+                        dxs = __fsub_rn(sx, cxf);
+                        dx2 = __fmul_rn(dxs, dxs);
+                        x2 += x_inc2;
+                    }
+                    remaining -= 1;
+                }
+            }
+            continue;
+        }
+
+        // general walk: per-cell window and grid tests (rays that may leave the window or the grid)
+        int x = cx0, y = cy0;
+        int ly = y - wy0;
+        int2 row = s_row[ly];                      // the start cell is always inside the window
+        int lx = x - (row.y & 0xffff);
+        int row_w = row.y >> 16;
+        bool inside = true;
+        while (remaining > 0 && inside) {
+            const float acc = __fadd_rn(dx2, dy2);
+            const bool is_free = acc < cls.free_below;
+            const bool is_mid = !is_free && !(acc > cls.prior_above) && (cls.mid_inc != 0u);
+            if (is_free | is_mid) {
+                const bool in_win = (unsigned)lx < (unsigned)row_w;
+                const int cell = row.x + lx;
+                const uint32_t addr = win_base + ((uint32_t)(cell >> 1) << 2);
+                const uint32_t shift = (cell & 1) << 4;
+                if (is_free & in_win) {
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(1u << shift) : "memory");
+                } else {
+                    bool done_here = false;
+                    if (in_win) {
+                        uint32_t* wp = &s_win[cell >> 1];
+                        uint32_t old = *wp;
+                        for (;;) {
+                            if (((old >> (shift + PK_FREE_BITS)) & PK_OCC_MAX) == PK_OCC_MAX) break;
+                            const uint32_t seen = atomicCAS(wp, old, old + (1u << (shift + PK_FREE_BITS)));
+                            if (seen == old) { done_here = true; break; }
+                            old = seen;
+                        }
+                    }
+                    if (!done_here) {
+                        exact_add(x, y, is_free ? CELL_FREE_INC : CELL_OCC_INC);
+                        ext_add(s_ext, x, y, x, y);
+                        band_add(s_blo, s_bhi, band0, y, x, x);
+                        spilled++;
+                    }
+                }
+            }
+            if (error > 0.0f) {                    // GridRayIterator::next (ray.rs:96-104)
+                y += y_inc;
+                error = __fsub_rn(error, delta_x);
+                cyf = __fadd_rn(cyf, y_step);
+                dys = __fsub_rn(sy, cyf);
+                dy2 = __fmul_rn(dys, dys);
+                inside = (unsigned)y < (unsigned)gh;
+                ly += y_inc;
+                if ((unsigned)ly < (unsigned)wh) {
+                    row = s_row[ly];
+                    row_w = row.y >> 16;
+                    lx = x - (row.y & 0xffff);
+                } else {
+                    row_w = 0;
+                }
+            } else {
+                x += x_inc;
+                error = __fadd_rn(error, delta_y);
+                cxf = __fadd_rn(cxf, x_step);
+                dxs = __fsub_rn(sx, cxf);
+                dx2 = __fmul_rn(dxs, dxs);
+                inside = (unsigned)x < (unsigned)gw;
+                lx += x_inc;
+            }
+            remaining -= 1;
+        }
+        cell_steps -= (uint32_t)remaining;   // the walk ended at the grid border
+    }
+    *spilled_p += spilled;
+    *cell_steps_p += cell_steps;
+}
+
+// write-back of one half item: root tiles + window -> own slot, for the rows this half owns
+__device__ __noinline__ void ray_half_writeback(const MapGeom& geom, const RayItem& it, bool upper, int cy0, bool walked,
+                                                uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
+                                                uint32_t* __restrict__ bands_all, size_t cells_per_grid, const uint32_t* s_win,
+                                                const int2* s_row, int* s_blo, int* s_bhi, int* s_ext, const uint4* s_lrow,
+                                                const int* s_xinfo /* lower half's band range, valid for the upper half */,
+                                                uint32_t eo_shared, int wy0, int wh, int band0, bool* saturated_p,
+                                                uint32_t* moved_p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t n_bands_slot = bands_per_slot(geom);
+    const bool fused = it.root != it.slot;
+    uint32_t* grid = cells + (size_t)it.slot * cells_per_grid;
+    uint32_t* bands = bands_all + (size_t)it.slot * n_bands_slot;
+    const uint32_t* src = cells + (size_t)it.root * cells_per_grid;
+    const uint32_t* src_bands = bands_all + (size_t)it.root * n_bands_slot;
+    bool saturated = false;
+    uint32_t moved = 0;
+    const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
+    auto unpack = [](uint32_t packed16) { return (packed16 & PK_FREE_MASK) | ((packed16 >> PK_FREE_BITS) << 16); };
+    auto merge_group = [&](uint4& va, uint4& vb, const uint4& d) {
+        const uint32_t high_any = (va.x | va.y | va.z | va.w | vb.x | vb.y | vb.z | vb.w) & 0x80008000u;
+        if (high_any == 0u) {
+            va.x += unpack(d.x & 0xffffu); va.y += unpack(d.x >> 16);
+            va.z += unpack(d.y & 0xffffu); va.w += unpack(d.y >> 16);
+            vb.x += unpack(d.z & 0xffffu); vb.y += unpack(d.z >> 16);
+            vb.z += unpack(d.w & 0xffffu); vb.w += unpack(d.w >> 16);
+        } else {
+            va.x = cell_sat_add(va.x, unpack(d.x & 0xffffu), &saturated); va.y = cell_sat_add(va.y, unpack(d.x >> 16), &saturated);
+            va.z = cell_sat_add(va.z, unpack(d.y & 0xffffu), &saturated); va.w = cell_sat_add(va.w, unpack(d.y >> 16), &saturated);
+            vb.x = cell_sat_add(vb.x, unpack(d.z & 0xffffu), &saturated); vb.y = cell_sat_add(vb.y, unpack(d.z >> 16), &saturated);
+            vb.z = cell_sat_add(vb.z, unpack(d.w & 0xffffu), &saturated); vb.w = cell_sat_add(vb.w, unpack(d.w >> 16), &saturated);
+        }
+    };
+    // rows this half owns: the lower half everything below the start row, the upper half the rest
+    const int own_lo = upper ? cy0 : 0, own_hi = upper ? (int)geom.gh : cy0;     // [own_lo, own_hi)
+    if (own_hi <= own_lo) { *moved_p += 0; return; }
+    const int shared_band = (cy0 % BAND_ROWS) ? cy0 / BAND_ROWS : -1;            // the band both halves have rows in
+    // bands to visit: the source's rows, the rows the slot's previous tenant had informed, the touched rows -- clipped to the owned rows
+    const SlotMeta sm = meta[it.root];
+    int y_lo = 0x7fffffff, y_hi = -1;                                             // rows [y_lo, y_hi]
+    if (sm.x1 > sm.x0 && sm.y1 > sm.y0) { y_lo = min(y_lo, sm.y0); y_hi = max(y_hi, sm.y1 - 1); }
+    if (fused && it.old_y1 > it.old_y0) { y_lo = min(y_lo, it.old_y0); y_hi = max(y_hi, it.old_y1 - 1); }
+    if (s_ext[3] >= s_ext[1] && s_ext[2] >= s_ext[0]) { y_lo = min(y_lo, s_ext[1]); y_hi = max(y_hi, s_ext[3]); }
+    y_lo = max(y_lo, own_lo); y_hi = min(y_hi, own_hi - 1);
+    if (y_hi < y_lo) { return; }
+    const int by0 = y_lo / BAND_ROWS, by1 = y_hi / BAND_ROWS;
+    const uint32_t tpr = geom.tiles_per_row;
+    constexpr int DEPTH = 4;                   // tiles in flight per warp
+    const int rr = lane >> 2, uu = lane & 3;   // this lane's row of the band and 32-byte unit of the tile row
+    for (int bnd = by0 + warp; bnd <= by1; bnd += n_warps) {
+        const bool is_shared = bnd == shared_band;
+        const uint32_t es = src_bands[bnd];
+        const uint32_t eo = fused ? ((is_shared && !upper) ? eo_shared : bands[bnd]) : es;
+        const int lb = bnd - band0;
+        bool touched = (unsigned)lb < (unsigned)HALF_MAX_BANDS && s_bhi[lb] >= s_blo[lb];
+        uint32_t t0x = touched ? ((uint32_t)s_blo[lb] & ~7u) : 0xffffu, t1x = touched ? min(geom.gw, ((uint32_t)s_bhi[lb] + 8u) & ~7u) : 0u;
+        // the entry of the shared band also covers what the lower half touched in its rows of it
+        uint32_t n0 = t0x, n1 = t1x;
+        if (is_shared && upper && s_xinfo[1] >= s_xinfo[0]) { n0 = min(n0, (uint32_t)s_xinfo[0] & ~7u); n1 = max(n1, min(geom.gw, ((uint32_t)s_xinfo[1] + 8u) & ~7u)); }
+        if (es) { n0 = min(n0, es & 0xffffu); n1 = max(n1, es >> 16); }
+        // columns to write: a clone's rows get the source's cells and lose the previous tenant's; an owner's only change where hit
+        uint32_t u0 = t0x, u1 = t1x;
+        if (fused) { if (es) { u0 = min(u0, es & 0xffffu); u1 = max(u1, es >> 16); } if (eo) { u0 = min(u0, eo & 0xffffu); u1 = max(u1, eo >> 16); } }
+        __syncwarp();                                   // every lane has read the old entry
+        if (lane == 0 && (upper || !is_shared)) bands[bnd] = n1 > n0 ? (n0 | (n1 << 16)) : 0u;   // (the upper half writes the shared band's)
+        if (u1 <= u0) continue;
+        const int t_lo = (int)(u0 / TILE_COLS), t_hi = (int)((u1 + TILE_COLS - 1u) / TILE_COLS);
+        const int y = bnd * BAND_ROWS + rr, ly = y - wy0;
+        const bool own_row = y >= own_lo && y < own_hi;
+        int wfirst = 0, wx0 = 0, ww = 0;
+        if (walked && touched && (unsigned)ly < (unsigned)wh) { const int2 row = s_row[ly]; wfirst = row.x; wx0 = row.y & 0xffff; ww = row.y >> 16; }
+        const bool start_row = upper && walked && y == cy0;                         // also receives the lower half's window row
+        const uint32_t sx0 = es & 0xffffu, sx1 = es >> 16;                           // (0, 0 when the source has nothing here)
+        const size_t band_off = (size_t)bnd * tpr * TILE_CELLS + 8u * (uint32_t)lane;
+        for (int tt = t_lo; tt < t_hi; tt += DEPTH) {
+            uint4 va[DEPTH], vb[DEPTH], d[DEPTH];
+            bool need[DEPTH];
+#pragma unroll
+            for (int k = 0; k < DEPTH; ++k) {         // what the window adds to this lane's 8 cells of tile tt + k
+                const int t = tt + k;
+                const int lx = t * (int)TILE_COLS + 8 * uu - wx0;
+                d[k] = make_uint4(0u, 0u, 0u, 0u);
+                bool lower_too = false;
+                if (t < t_hi && own_row && (unsigned)lx < (unsigned)ww) {
+                    d[k] = win4[(wfirst + lx) >> 3];
+                    if (start_row && (uint32_t)(lx >> 3) < HALF_XCHG_GROUPS) {
+                        const uint4 dl = s_lrow[lx >> 3];
+                        lower_too = (dl.x | dl.y | dl.z | dl.w) != 0u;
+                    }
+                }
+                // a clone's rows are written everywhere (copy + clear); an owner's only where something was hit
+                need[k] = t < t_hi && own_row && (fused || lower_too || (d[k].x | d[k].y | d[k].z | d[k].w) != 0u);
+            }
+#pragma unroll
+            for (int k = 0; k < DEPTH; ++k) {
+                const int t = tt + k;
+                const uint32_t x = (uint32_t)t * TILE_COLS + 8u * (uint32_t)uu;
+                va[k] = make_uint4(0u, 0u, 0u, 0u); vb[k] = va[k];
+                if (need[k] && x >= sx0 && x < sx1) {
+                    const V8 s8 = ld_stream_v8(reinterpret_cast<const V8*>(src + band_off + (size_t)t * TILE_CELLS));
+                    va[k] = s8.a; vb[k] = s8.b;
+                    moved++;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < DEPTH; ++k) {
+                if (!need[k]) continue;
+                const int t = tt + k;
+                if ((d[k].x | d[k].y | d[k].z | d[k].w) != 0u) merge_group(va[k], vb[k], d[k]);
+                if (start_row) {
+                    const int lx = t * (int)TILE_COLS + 8 * uu - wx0;
+                    if ((unsigned)lx < (unsigned)ww && (uint32_t)(lx >> 3) < HALF_XCHG_GROUPS) {
+                        const uint4 dl = s_lrow[lx >> 3];
+                        if ((dl.x | dl.y | dl.z | dl.w) != 0u) merge_group(va[k], vb[k], dl);
+                    }
+                }
+                V8 o8; o8.a = va[k]; o8.b = vb[k];
+                st_stream_v8(reinterpret_cast<V8*>(grid + band_off + (size_t)t * TILE_CELLS), o8);
+                moved++;
+            }
+        }
+    }
+    if (saturated) *saturated_p = true;
+    *moved_p += moved;
+}
+
+__global__ void __maxnreg__(80)   // 4 CTAs of 192 threads per SM
+k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restrict__ results, uint32_t first_particle,
+                  const uint32_t* __restrict__ alive_list, const RayItem* __restrict__ clones, const RayItem* __restrict__ owners,
+                  const uint32_t* __restrict__ readers, uint32_t* __restrict__ done, uint32_t* __restrict__ xflag,
+                  HalfXchg* __restrict__ xchg, uint32_t* __restrict__ spill_scratch, const int32_t* __restrict__ slot_of,
+                  uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta, uint32_t* __restrict__ bands_all,
+                  size_t cells_per_grid, int radius, uint32_t window_bytes, StepCounters* counters) {
+    extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word; behind the window: this half's beam list
+    uint16_t* s_beam = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_win) + window_bytes);
+    __shared__ uint32_t s_nspill, s_nmine, s_eo_shared;
+    __shared__ int s_blo[HALF_MAX_BANDS], s_bhi[HALF_MAX_BANDS];
+    __shared__ int2 s_row[HALF_MAX_ROWS + 1];           // .x = first window cell of the row, .y = x0 | width << 16
+    __shared__ uint32_t s_rowb[HALF_MAX_ROWS];          // shared byte address of column x = 0 of the row
+    __shared__ int s_ext[4], s_xinfo[2];
+    __shared__ unsigned long long s_next;
+    __shared__ uint4 s_lrow[HALF_XCHG_GROUPS];
+    const unsigned long long n_items = counters->n_alive;
+    const int gw = (int)geom.gw, gh = (int)geom.gh;
+    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared(s_win);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t n_bands_slot = bands_per_slot(geom);
+    bool saturated = false;
+    uint32_t spilled = 0, cell_steps = 0, moved = 0;
+    uint32_t* my_spill = spill_scratch + (size_t)blockIdx.x * RAY_SPILL_CAP;
+
+    for (;;) {
+        __syncthreads();       // the previous item's shared state is no longer read
+        if (threadIdx.x == 0) s_next = atomicAdd(&counters->ray_work_head, 1ull);
+        __syncthreads();
+        const unsigned long long work = s_next;
+        if (work >= 2ull * n_items) break;
+        const unsigned long long item = work >> 1;
+        const bool upper = (work & 1ull) != 0ull;   // the lower half of a particle is listed first
+        RayItem it;
+        if (clones) {   // clones first: an owner is popped only after every clone that reads its slot
+            const unsigned long long n_clones = counters->ray_items_front;
+            it = item < n_clones ? clones[item] : owners[item - n_clones];
+        } else {
+            it.particle = alive_list[item]; it.slot = slot_of[it.particle]; it.root = it.slot; it.old_y0 = it.old_y1 = 0; it.pad = 0u;
+        }
+        const bool fused = it.root != it.slot;
+        uint32_t* grid = cells + (size_t)it.slot * cells_per_grid;
+        uint32_t* bands = bands_all + (size_t)it.slot * n_bands_slot;
+        const ParticleResult r = results[first_particle + it.particle];
+        const float px = r.x, py = r.y, ptheta = r.theta;
+        const float sx = world_to_grid(px, geom.pos_x, geom.res);
+        const float sy = world_to_grid(py, geom.pos_y, geom.res);
+        const long long lcx = f32_as_isize(floorf(sx)), lcy = f32_as_isize(floorf(sy));
+        // every ray starts in the same cell; outside the grid nothing is emitted (ray.rs:88-92)
+        const bool walked = !(lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh);
+        if (!walked && !fused) continue;
+        // (a clone whose pose left the grid integrates nothing but still gets its own cells: the upper half copies all rows)
+        const int cx0 = walked ? (int)lcx : 0, cy0 = walked ? (int)lcy : 0;
+        const int rad = walked ? radius : 0;
+        ext_init(s_ext);
+        if (threadIdx.x == 0) { s_nspill = 0u; s_nmine = 0u; s_xinfo[0] = 0x7fffffff; s_xinfo[1] = -1; s_eo_shared = 0u; }
+        for (int i = threadIdx.x; i < HALF_MAX_BANDS; i += blockDim.x) { s_blo[i] = 0x7fffffff; s_bhi[i] = -1; }
+        if (threadIdx.x < HALF_XCHG_GROUPS) s_lrow[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+
+        // ---- row table of the half-disc window (x ranges aligned to 8 cells = one 128-bit group)
+        const int wy0 = upper ? cy0 : max(0, cy0 - rad), wy1 = upper ? min(gh, cy0 + rad + 1) : cy0 + 1;
+        const int band0 = wy0 / BAND_ROWS;
+        const int wh = walked ? wy1 - wy0 : 0;
+        for (int ly = threadIdx.x; ly < wh; ly += blockDim.x) {
+            const int dy = wy0 + ly - cy0;
+            const int hw = isqrt_small(rad * rad - dy * dy);
+            const int x0 = max(0, cx0 - hw) & ~7;
+            const int x1 = min(gw, (min(gw, cx0 + hw + 1) + 7) & ~7);
+            s_row[ly].y = x0 | ((x1 - x0) << 16);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int carry = 0;
+            for (int base = 0; base < wh; base += 32) {
+                const int ly = base + (int)threadIdx.x;
+                const int w = ly < wh ? (s_row[ly].y >> 16) : 0;
+                int inc = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if ((int)threadIdx.x >= o) inc += t;
+                }
+                if (ly < wh) {
+                    const int first = carry + inc - w;
+                    s_row[ly].x = first;
+                    s_rowb[ly] = win_base + 2u * (uint32_t)(first - (s_row[ly].y & 0xffff));
+                }
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (threadIdx.x == 0) s_row[wh] = make_int2(carry, 0);
+        }
+        __syncthreads();
+        {
+            const int wcells = s_row[wh].x;
+            uint4* w4 = reinterpret_cast<uint4*>(s_win);
+            for (int i = threadIdx.x; i < (wcells >> 3); i += blockDim.x) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // ---- which beams are this half's: y_inc >= 0 (upper) or < 0 (lower), decided exactly as the iterator does
+        //      (ray.rs:54-72); a cheap test settles all but the nearly horizontal ones
+        if (walked) {
+            for (uint32_t t0 = 0; t0 < scan.n_beams; t0 += blockDim.x) {
+                const uint32_t t = t0 + threadIdx.x;
+                bool mine = false;
+                uint32_t b = 0u;
+                if (t < scan.n_beams) {
+                    b = scan.order ? scan.order[t] : t;
+                    const float dist = scan.dist[b];
+                    const float a = __fadd_rn(ptheta, scan.angle[b]);
+                    const float dyq = __fmul_rn(sinf(a), dist);
+                    const float margin = 1.0e-4f * (fabsf(py) + fabsf(geom.pos_y) + fabsf(dist) + geom.res);
+                    bool up;
+                    if (dyq > margin) up = true;
+                    else if (dyq < -margin) up = false;
+                    else {
+                        float ex, ey;
+                        beam_endpoint(px, py, ptheta, scan.angle[b], dist, &ex, &ey);
+                        const float y1 = world_to_grid(ey, geom.pos_y, geom.res);
+                        up = fabsf(__fsub_rn(y1, sy)) == 0.0f || y1 > sy;
+                    }
+                    mine = up == upper;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, mine);
+                if (m) {
+                    uint32_t base = 0u;
+                    if (lane == 0) base = atomicAdd(&s_nmine, (uint32_t)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (mine) s_beam[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)b;
+                }
+            }
+        }
+        __syncthreads();
+        if (walked)
+            ray_walk_half(geom, scan, s_beam, s_nmine, px, py, ptheta, sx, sy, cx0, cy0, rad, upper, wy0, wh, band0, s_win, s_row,
+                          s_rowb, s_blo, s_bhi, s_ext, &s_nspill, my_spill, &spilled, &cell_steps);
+        __syncthreads();
+
+        // ---- per band of the window the columns that really received hits (a lane scans one window row; the lower
+        //      half leaves the start row to the upper half)
+        const uint4* win4 = reinterpret_cast<const uint4*>(s_win);
+        {
+            const int rr = lane & 7, bq = lane >> 3;
+            int wxmin = 0x7fffffff, wymin = 0x7fffffff, wxmax = -1, wymax = -1;
+            const int n_wbands = wh > 0 ? (wy0 + wh - 1) / BAND_ROWS - band0 + 1 : 0;
+            for (int q = warp; 4 * q < n_wbands; q += n_warps) {
+                const int lb = 4 * q + bq;
+                const int y = (band0 + lb) * BAND_ROWS + rr, ly = y - wy0;
+                int first = 0x7fffffff, last = -1, rx0 = 0;
+                int2 row = make_int2(0, 0);
+                if (lb < n_wbands && (unsigned)ly < (unsigned)wh && (upper || y != cy0)) { row = s_row[ly]; rx0 = row.y & 0xffff; }
+                const int groups = row.y >> 19;
+                for (int g = 0; g < 34; ++g) {                 // (a window row is at most 34 groups wide)
+                    if (__all_sync(0xffffffffu, g >= groups)) break;
+                    if (g < groups) {
+                        const uint4 d = win4[(row.x >> 3) + g];
+                        if ((d.x | d.y | d.z | d.w) != 0u) { first = min(first, g); last = g; }
+                    }
+                }
+                int xlo = last >= 0 ? rx0 + 8 * first : 0x7fffffff, xhi = last >= 0 ? rx0 + 8 * last + 7 : -1;
+                if (last >= 0) { wymin = min(wymin, y); wymax = max(wymax, y); }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+                    xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+                }
+                wxmin = min(wxmin, xlo); wxmax = max(wxmax, xhi);
+                if (rr == 0 && xhi >= xlo && (unsigned)lb < (unsigned)HALF_MAX_BANDS) { atomicMin(&s_blo[lb], xlo); atomicMax(&s_bhi[lb], xhi); }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                wxmin = min(wxmin, __shfl_xor_sync(0xffffffffu, wxmin, o)); wxmax = max(wxmax, __shfl_xor_sync(0xffffffffu, wxmax, o));
+                wymin = min(wymin, __shfl_xor_sync(0xffffffffu, wymin, o)); wymax = max(wymax, __shfl_xor_sync(0xffffffffu, wymax, o));
+            }
+            if (lane == 0) ext_add(s_ext, wxmin, wymin, wxmax, wymax);
+        }
+        __syncthreads();
+
+        // ---- the start row is shared: the lower half hands its window row for it (and what the upper half needs
+        //      for the band both halves have rows in) to the upper half
+        const int shared_band = (cy0 % BAND_ROWS) ? cy0 / BAND_ROWS : -1;
+        if (walked && !upper) {
+            HalfXchg* x = xchg + item;
+            const int2 row = s_row[wh - 1];                        // the start row is this window's last
+            const int groups = row.y >> 19;
+            if (threadIdx.x < HALF_XCHG_GROUPS)
+                x->row[threadIdx.x] = (int)threadIdx.x < groups ? win4[(row.x >> 3) + threadIdx.x] : make_uint4(0u, 0u, 0u, 0u);
+            if (threadIdx.x == 0) {
+                const int lb = shared_band - band0;
+                const bool any = shared_band >= 0 && (unsigned)lb < (unsigned)HALF_MAX_BANDS && s_bhi[lb] >= s_blo[lb];
+                x->band_lo = any ? s_blo[lb] : 0x7fffffff;
+                x->band_hi = any ? s_bhi[lb] : -1;
+                // parked hits of lower rays on the start row travel too: the upper half writes that row
+                uint32_t nh = 0u;
+                const uint32_t ns = min(s_nspill, RAY_SPILL_CAP);
+                for (uint32_t k = 0; k < ns; ++k) {
+                    const uint32_t e = my_spill[k];
+                    if ((int)((e >> 15) & 0x7fffu) == cy0) { if (nh < HALF_XCHG_HITS) x->hits[nh] = e; nh++; }
+                }
+                if (nh > HALF_XCHG_HITS) atomicAdd(&counters->fuse_overflow, 1ull);
+                x->n_hits = min(nh, HALF_XCHG_HITS);
+                // the shared band's old entry, before the upper half replaces it
+                s_eo_shared = (fused && shared_band >= 0) ? bands[shared_band] : 0u;
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(xflag + item), "r"(1u) : "memory");
+        }
+        if (walked && upper) {
+            if (threadIdx.x == 0) {
+                uint32_t seen;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(xflag + item) : "memory");
+                    if (seen != 0u) break;
+                    __nanosleep(100);
+                }
+            }
+            __syncthreads();
+            const HalfXchg* x = xchg + item;
+            if (threadIdx.x < HALF_XCHG_GROUPS) s_lrow[threadIdx.x] = __ldcg(&x->row[threadIdx.x]);
+            if (threadIdx.x == 0) {
+                s_xinfo[0] = __ldcg(&x->band_lo); s_xinfo[1] = __ldcg(&x->band_hi);
+                const uint32_t nh = __ldcg(&x->n_hits);
+                for (uint32_t k = 0; k < nh; ++k) {
+                    const uint32_t at = atomicAdd(&s_nspill, 1u);
+                    if (at < RAY_SPILL_CAP) my_spill[at] = __ldcg(&x->hits[k]);
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {   // what the lower rays touched on the start row counts for this half's extents
+                const int2 row = s_row[0];
+                const int rx0 = row.y & 0xffff;
+                int first = 0x7fffffff, last = -1;
+                for (int g = lane; g < (int)HALF_XCHG_GROUPS; g += 32) {
+                    const uint4 d = s_lrow[g];
+                    if ((d.x | d.y | d.z | d.w) != 0u) { first = min(first, g); last = max(last, g); }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+                }
+                if (lane == 0 && last >= 0) {
+                    ext_add(s_ext, rx0 + 8 * first, cy0, rx0 + 8 * last + 7, cy0);
+                    band_add(s_blo, s_bhi, band0, cy0, rx0 + 8 * first, rx0 + 8 * last + 7);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- an owner whose slot clones read in this step waits for them before it writes
+        if (!fused && readers != nullptr) {
+            if (threadIdx.x == 0) {
+                const uint32_t want = readers[it.slot];
+                if (want != 0u) {
+                    uint32_t seen;
+                    for (;;) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + it.slot) : "memory");
+                        if (seen >= want) break;
+                        __nanosleep(100);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        ray_half_writeback(geom, it, upper, cy0, walked, cells, meta, bands_all, cells_per_grid, s_win, s_row, s_blo, s_bhi, s_ext,
+                           s_lrow, s_xinfo, s_eo_shared, wy0, wh, band0, &saturated, &moved);
+        __syncthreads();
+        {   // the parked exact-path hits, now that the slot holds its cells (the lower half's start-row hits went to the upper half)
+            const uint32_t ns = s_nspill;
+            if (ns > RAY_SPILL_CAP && threadIdx.x == 0) atomicAdd(&counters->fuse_overflow, 1ull);
+            for (uint32_t k = threadIdx.x; k < min(ns, RAY_SPILL_CAP); k += blockDim.x) {
+                const uint32_t e = my_spill[k];
+                const uint32_t x = e & 0x7fffu, y = (e >> 15) & 0x7fffu;
+                if (!upper && (int)y == cy0) continue;
+                global_cell_add(&grid[phys_index(geom, x, y)], (e & 0x40000000u) ? CELL_OCC_INC : CELL_FREE_INC, &saturated);
+            }
+        }
+        if (threadIdx.x == 0) {
+            // the slot's box: (a clone's was set to its source's when it was listed) + what this half touched
+            if (s_ext[2] >= s_ext[0]) {
+                SlotMeta* mp = &meta[it.slot];
+                while (atomicCAS(&mp->pad0, 0, 1) != 0) __nanosleep(50);     // the two halves of a particle update one box
+                __threadfence();
+                ext_commit(s_ext, mp, gw);
+                __threadfence();
+                atomicExch(&mp->pad0, 0);
+            }
+            if (fused) {
+                __threadfence();
+                atomicAdd(&done[it.root], 1u);        // this half has read the root: its owner may write it
+            }
+        }
+    }
+    if (saturated) atomicAdd(&counters->saturated, 1ull);
+    if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cell_steps += __shfl_down_sync(0xffffffffu, cell_steps, o); moved += __shfl_down_sync(0xffffffffu, moved, o); }
+    if ((threadIdx.x & 31) == 0 && cell_steps) atomicAdd(&counters->ray_cell_steps, (unsigned long long)cell_steps);
+    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
+}
+
 // =============================================================================== k_sort_beams
 // Bitonic sort of (|dist|, beam index) in shared memory, descending; one CTA, once per scan, on the side
 // stream while the likelihood kernel runs.
@@ -1070,21 +1761,43 @@ int ray_trace(unsigned long long* out18) {
 }
 size_t ray_spill_scratch_words(int num_sms) { return (size_t)num_sms * 4u * RAY_SPILL_CAP; }   // <= 4 CTAs per SM
 
+size_t ray_half_xchg_bytes() { return sizeof(HalfXchg); }
+
 cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan, const ParticleResult* results,
                               uint32_t first_particle, uint32_t n_local, const uint32_t* alive_list,
                               const RayItem* clones, const RayItem* owners, const uint32_t* readers, uint32_t* done,
-                              uint32_t* spill_scratch, const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
-                              size_t cells_per_grid, int radius_cells, StepCounters* counters,
+                              uint32_t* xflag, void* xchg, uint32_t* spill_scratch, const int32_t* slot_of, uint32_t* cells,
+                              SlotMeta* meta, uint32_t* bands, size_t cells_per_grid, int radius_cells, StepCounters* counters,
                               uint64_t* window_cells, bool force_generic, int num_sms) {
+    // half a particle per work item (whole-grid tiled slots whose window holds every reachable cell): 4 CTAs per SM
+    if (ray_update_can_fuse(geom, scan.n_beams, cells_per_grid, force_generic, radius_cells)) {
+        const int radius = ray_packed_radius(radius_cells);
+        const size_t wcells = (size_t)ray_window_cells_upper_bound_half(radius);
+        const size_t wbytes = (wcells * 2 + 15) & ~(size_t)15;
+        const size_t smem = wbytes + (((size_t)scan.n_beams * 2 + 15) & ~(size_t)15);
+        int threads = (int)(((scan.n_beams + 1u) / 2u + 31u) / 32u * 32u) + 0;
+        threads = threads < 128 ? 128 : (threads > RAY_MAX_THREADS ? RAY_MAX_THREADS : threads);
+        *window_cells = 2 * wcells;
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ray_update_half, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;   // (the spill scratch is sized for 4 CTAs per SM)
+        uint32_t grid = (uint32_t)(per_sm * num_sms);
+        if (grid > 2u * n_local) grid = 2u * n_local;
+        k_ray_update_half<<<grid, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, clones, owners, readers, done,
+                                                           xflag, (HalfXchg*)xchg, spill_scratch, slot_of, cells, meta, bands,
+                                                           cells_per_grid, radius, (uint32_t)wbytes, counters);
+        return cudaSuccess;
+    }
     int threads = (int)((scan.n_beams + 31u) / 32u * 32u);
     threads = threads < 128 ? 128 : (threads > RAY_MAX_THREADS ? RAY_MAX_THREADS : threads);
-    // preferred: the packed 16-bit window (two CTAs per SM at long range)
+    // the packed 16-bit window with a whole particle per CTA (two CTAs per SM at long range): row-major or windowed slots
     if (!force_generic && geom.gw % 8u == 0u && cells_per_grid % 8u == 0u && scan.n_beams <= RAY_PACKED_MAX_BEAMS) {
         const int radius = ray_packed_radius(radius_cells);
         const size_t wmax = (size_t)ray_window_cells_upper_bound_packed(radius);
         *window_cells = wmax;
-        // as many CTAs as are resident at once (every CTA must be running for the owners' waits to be safe),
-        // never more than there can be items
+        // as many CTAs as are resident at once, never more than there can be items
         int per_sm = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ray_update_packed, threads, wmax * 2);
         if (e != cudaSuccess) return e;
@@ -1092,8 +1805,9 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
         if (per_sm > 4) per_sm = 4;   // (the spill scratch is sized for 4 CTAs per SM)
         uint32_t grid = (uint32_t)(per_sm * num_sms);
         if (grid > n_local) grid = n_local;
-        k_ray_update_packed<<<grid, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, clones, owners, readers, done, spill_scratch,
-                                                                 slot_of, cells, meta, bands, cells_per_grid, radius, radius_cells, counters);
+        k_ray_update_packed<<<grid, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, nullptr, nullptr, nullptr,
+                                                                 nullptr, spill_scratch, slot_of, cells, meta, bands, cells_per_grid, radius,
+                                                                 radius_cells, counters);
         return cudaSuccess;
     }
     const bool vec = (geom.gw % 4u == 0u) && (cells_per_grid % 4u == 0u);
@@ -1117,6 +1831,8 @@ cudaError_t configure_ray_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_ray_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ray_update_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ray_update_half, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM / 2 + 8192);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_ray_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RAY_MAX_SMEM);
 }

@@ -681,14 +681,24 @@ k_resample_indices(const ParticleResult* __restrict__ results, const double* __r
         }
         return;
     }
-    RayItem it{0u, 0, 0, 0u};
+    RayItem it{0u, 0, 0, 0, 0, 0u};
     bool clone = false;
     if (alive) {
         it.particle = src_idx - first_particle;
         it.slot = ray.slot_of[it.particle];
         it.root = ray.alias_of[it.slot];
         clone = it.root != it.slot;
-        if (clone) { atomicAdd(&ray.readers[it.root], 1u); ray.alias_of[it.slot] = it.slot; }
+        if (clone) {
+            atomicAdd(&ray.readers[it.root], 2u);     // both halves of the clone read the root (k_ray_update_half)
+            ray.alias_of[it.slot] = it.slot;
+            // the slot takes its source's box now (the root's own update of it comes after its readers are done); what
+            // the slot's previous tenant had informed still has to be cleared: the item remembers its rows
+            const SlotMeta old = ray.meta[it.slot];
+            if (old.x1 > old.x0 && old.y1 > old.y0) { it.old_y0 = old.y0; it.old_y1 = old.y1; }
+            SlotMeta src = ray.meta[it.root];
+            src.pad0 = 0;
+            ray.meta[it.slot] = src;
+        }
     }
     const unsigned mc = __ballot_sync(0xffffffffu, alive && clone), mo = __ballot_sync(0xffffffffu, alive && !clone);
     unsigned long long bc = 0, bo = 0;
