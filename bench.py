@@ -467,7 +467,12 @@ def run_cuda(args, wl, rank, world, local):
     # Ray update (k_ray_update_packed): SURVEY.md 8(d)'s unit is the cell-step of the reference's ray iterator,
     # 4 B read + 4 B written each (8 B); the kernel counts the steps of the rays it integrates.
     ray_ms = ph["ray_update"]
-    ray_bytes = 8.0 * float(hist[:, 6].sum())
+    # ... plus the clone copies the same kernel performs (a surviving clone's cells are copied by the CTA that integrates
+    # its scan): bytes read + written, counted on the device (history value ray_copy_bytes)
+    ray_rmw_bytes = 8.0 * float(hist[:, 6].sum())
+    ray_copy_bytes = float(hist[:, 7].sum())
+    ray_bytes = ray_rmw_bytes + ray_copy_bytes
+    copy_bytes = max(0.0, copy_bytes - ray_copy_bytes)      # what the copy kernels proper moved (NVLink pulls, eager copies)
     st = main["stats"]
     line = {
         "metric": METRIC, "value": pbu * K / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -498,11 +503,13 @@ def run_cuda(args, wl, rank, world, local):
         "frac": (ray_bytes / (ray_ms * 1e-3) / 1e9) / peak if peak and ray_ms > 0 else None,
         "traffic": ncu_traffic("ray_traffic.json", ray_bytes / K), "peak_source": peak_src,
         "bytes_per_launch": ray_bytes / K, "ms_per_launch": ray_ms / K,
+        "ray_rmw_bytes_per_launch": ray_rmw_bytes / K, "clone_copy_bytes_per_launch": ray_copy_bytes / K,
         "cell_steps_per_launch": float(hist[:, 6].sum()) / K, "particles_integrated_per_launch": float(hist[:, 4].mean()),
-        "algorithmic_bytes": "8 B (4 read + 4 written) per step of the reference's ray iterator (SURVEY.md 8(d)), steps "
-                             "counted by the kernel over the rays it integrates. The kernel is bound by instruction issue "
-                             "and per-CTA latency, not by HBM: revisited cells are accumulated in shared memory and each "
-                             "informed 8-cell group is read and written once",
+        "algorithmic_bytes": "SURVEY.md 8(d): 8 B (4 read + 4 written) per step of the reference's ray iterator, steps counted "
+                             "by the kernel over the rays it integrates, + the bytes of the clone copies the kernel performs "
+                             "(2 x informed extent per copied grid, counted on the device). The kernel is bound by instruction "
+                             "issue and latency, not by HBM: revisited cells are accumulated in shared memory and every tile "
+                             "is read and written once",
         "step_frac": ((ray_bytes + copy_bytes) / (ms_value * 1e-3) / 1e9) / peak if peak else None}
     line["roofline_copy"]["peak_source"] = peak_src
     # the roofline the contract asks for is the dominant kernel's: whichever phase takes more of the step

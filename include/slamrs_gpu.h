@@ -248,11 +248,12 @@ int slamrs_gpu_set_profiling(slamrs_gpu_handle* h, int enabled);
 int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COUNT], uint64_t* out_steps);
 /* Per-step history (ring of the last 256 steps): for step indices first_step .. first_step+count-1
  * writes SLAMRS_HISTORY_VALUES values per step: {grids_copied, grids_pulled, distinct_sources,
- * source_reads, particles_integrated, copy_bytes, ray_cell_steps} where source_reads = number of
+ * source_reads, particles_integrated, copy_bytes, ray_cell_steps, ray_copy_bytes} where source_reads = number of
  * times the copy kernel read a source grid (one read feeds up to 16 destination grids), copy_bytes =
  * bytes the copy kernels really read + wrote, and ray_cell_steps = steps of the reference's ray
- * iterator (ray.rs:83-110) over all rays integrated in that step (0 with the generic ray kernel). */
-#define SLAMRS_HISTORY_VALUES 7
+ * iterator (ray.rs:83-110) over all rays integrated in that step (0 with the generic ray kernel).  ray_copy_bytes = the part of copy_bytes that the ray update itself moved (a surviving clone's cells are
+ * copied by the kernel that integrates its scan). */
+#define SLAMRS_HISTORY_VALUES 8
 int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_values);
 
 /* current generation, this rank's shard: n_local * {x, y, theta} */

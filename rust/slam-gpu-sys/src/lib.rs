@@ -28,7 +28,7 @@ pub const SLAMRS_FLAG_EAGER_COPY: u32 = 16;
 pub const SLAMRS_MAP_F64: u32 = 0;
 pub const SLAMRS_MAP_F32: u32 = 1;
 pub const SLAMRS_MAP_U8: u32 = 2;
-pub const SLAMRS_HISTORY_VALUES: usize = 7;
+pub const SLAMRS_HISTORY_VALUES: usize = 8;
 
 #[repr(C)]
 pub struct slamrs_gpu_handle {

@@ -19,7 +19,7 @@ FLAG_UPDATE_ALL_PARTICLES = 2
 FLAG_FULL_GRID_COPY = 4
 FLAG_NCCL_EXCHANGE = 8
 FLAG_EAGER_COPY = 16
-HISTORY_VALUES = 7
+HISTORY_VALUES = 8
 
 EXPORTS = [
     "slamrs_gpu_grid_cells", "slamrs_gpu_nccl_unique_id", "slamrs_gpu_create", "slamrs_gpu_destroy",

@@ -1073,7 +1073,7 @@ int slamrs_gpu_get_phase_ms(slamrs_gpu_handle* h, double out_ms[SLAMRS_PHASE_COU
 
 int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint32_t count, uint64_t* out_triples) {
     // seven values per step: grids_copied, grids_pulled, distinct_sources, source_reads, particles_integrated,
-    // copy_bytes, ray_cell_steps
+    // copy_bytes, ray_cell_steps, ray_copy_bytes
     if (!h || !out_triples || count > STEP_HISTORY) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     std::vector<StepRecord> ring(STEP_HISTORY);
@@ -1084,7 +1084,7 @@ int slamrs_gpu_get_step_history(slamrs_gpu_handle* h, uint64_t first_step, uint3
         if (r.step != first_step + i) return fail(h, SLAMRS_E_INVALID_ARG, "step no longer in the history ring");
         uint64_t* o = out_triples + (size_t)SLAMRS_HISTORY_VALUES * i;
         o[0] = r.n_copies; o[1] = r.n_pulls; o[2] = r.distinct; o[3] = r.n_leaders; o[4] = r.n_alive; o[5] = r.copy_bytes;
-        o[6] = r.ray_cell_steps;
+        o[6] = r.ray_cell_steps; o[7] = r.ray_copy_bytes;
     }
     return SLAMRS_OK;
 }

@@ -50,6 +50,7 @@ struct StepCounters {
     unsigned long long n_mat;            // shared grids made private before this step's ray update (copies)
     unsigned long long n_mat_leaders;    // fan-out sub-runs among them
     unsigned long long ray_cell_steps;   // ray-iterator steps integrated this step (packed ray kernel), for the roofline
+    unsigned long long ray_copy_bytes;   // bytes of clone copies the ray update read + wrote this step (part of copy_bytes)
     unsigned long long ray_work_head;    // next item of the ray update's work list (popped by its resident CTAs)
     unsigned long long ray_items_front;  // k_ray_items: clones listed so far (front of the list)
     unsigned long long ray_items_back;   // k_ray_items: slot owners listed so far (back of the list)
@@ -69,7 +70,7 @@ struct StepCounters {
 // per-step record kept on the device so that a pipelined caller can read, after the fact, how
 // many grids each step really moved (the roofline is computed from moved bytes only)
 struct StepRecord {
-    unsigned long long step, n_copies, n_pulls, distinct, n_leaders, n_alive, copy_bytes, ray_cell_steps;
+    unsigned long long step, n_copies, n_pulls, distinct, n_leaders, n_alive, copy_bytes, ray_cell_steps, ray_copy_bytes;
 };
 constexpr uint32_t STEP_HISTORY = 256;
 constexpr uint32_t COPY_FAN = 16;   // destinations written per source read in k_copy

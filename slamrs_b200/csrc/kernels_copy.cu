@@ -314,6 +314,7 @@ __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigne
         record->copy_bytes = counters->copy_bytes;
         record->n_alive = counters->n_alive;
         record->ray_cell_steps = counters->ray_cell_steps;
+        record->ray_copy_bytes = counters->ray_copy_bytes;
         record->n_copies += counters->n_mat;          // clones made private before the ray update
         record->n_leaders += counters->n_mat_leaders;
         // informed extent of the published map, for the windowed read-out (sources are not written here)

@@ -1003,7 +1003,10 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { cell_steps += __shfl_down_sync(0xffffffffu, cell_steps, o); moved += __shfl_down_sync(0xffffffffu, moved, o); }
     if ((threadIdx.x & 31) == 0 && cell_steps) atomicAdd(&counters->ray_cell_steps, (unsigned long long)cell_steps);
-    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
+    if ((threadIdx.x & 31) == 0 && moved) {
+        atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
+        atomicAdd(&counters->ray_copy_bytes, (unsigned long long)moved * 32ull);
+    }
 }
 
 // =============================================================================== k_ray_update_half
@@ -1035,6 +1038,7 @@ struct alignas(16) HalfXchg {           // lower half -> upper half of the same 
     int band_lo, band_hi;               // columns the lower half touched in its rows of the shared band (hi < lo: none)
     uint32_t n_hits;                    // exact-path hits of lower rays on the start row (applied by the upper CTA)
     uint32_t pad;
+    int ext[4];                         // what the lower half touched {xmin, ymin, xmax, ymax} (the upper half commits the slot's box)
     uint32_t hits[HALF_XCHG_HITS];
 };
 static_assert(sizeof(HalfXchg) % 16 == 0, "exchange records are accessed as 16-byte pieces");
@@ -1373,7 +1377,7 @@ __device__ __noinline__ void ray_half_writeback(const MapGeom& geom, const RayIt
                 if (need[k] && x >= sx0 && x < sx1) {
                     const V8 s8 = ld_stream_v8(reinterpret_cast<const V8*>(src + band_off + (size_t)t * TILE_CELLS));
                     va[k] = s8.a; vb[k] = s8.b;
-                    moved++;
+                    moved += fused ? 1u : 0u;   // (clone copies only: an owner's read-modify-write is the ray update's own traffic)
                 }
             }
 #pragma unroll
@@ -1390,7 +1394,7 @@ __device__ __noinline__ void ray_half_writeback(const MapGeom& geom, const RayIt
                 }
                 V8 o8; o8.a = va[k]; o8.b = vb[k];
                 st_stream_v8(reinterpret_cast<V8*>(grid + band_off + (size_t)t * TILE_CELLS), o8);
-                moved++;
+                moved += fused ? 1u : 0u;   // (clone copies only: an owner's read-modify-write is the ray update's own traffic)
             }
         }
     }
@@ -1411,7 +1415,7 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
     __shared__ int s_blo[HALF_MAX_BANDS], s_bhi[HALF_MAX_BANDS];
     __shared__ int2 s_row[HALF_MAX_ROWS + 1];           // .x = first window cell of the row, .y = x0 | width << 16
     __shared__ uint32_t s_rowb[HALF_MAX_ROWS];          // shared byte address of column x = 0 of the row
-    __shared__ int s_ext[4], s_xinfo[2];
+    __shared__ int s_ext[4], s_xinfo[2], s_lext[4];
     __shared__ unsigned long long s_next;
     __shared__ uint4 s_lrow[HALF_XCHG_GROUPS];
     const unsigned long long n_items = counters->n_alive;
@@ -1422,11 +1426,33 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
     bool saturated = false;
     uint32_t spilled = 0, cell_steps = 0, moved = 0;
     uint32_t* my_spill = spill_scratch + (size_t)blockIdx.x * RAY_SPILL_CAP;
+    // Global round trips that nothing in the item waits for are taken by one lane of the last warp (the shortest
+    // beams) while the CTA walks: popping the NEXT work item, and the previous item's box commit and "root has
+    // been read" signal.
+    const bool helper = threadIdx.x == blockDim.x - 32u;
+    SlotMeta* pend_meta = nullptr;      // helper lane: box of the previous item to union `pend_ext` into
+    uint32_t* pend_done = nullptr;      // helper lane: reader counter to bump for the previous item
+    int pend_ext[4] = {0, 0, -1, -1};
+    auto flush_pending = [&]() {
+        if (pend_meta != nullptr) {
+            SlotMeta b = *pend_meta;
+            const int am = BOX_ALIGN - 1;
+            const int x0 = pend_ext[0] & ~am, x1 = min(gw, (pend_ext[2] + 1 + am) & ~am), y0 = pend_ext[1], y1 = pend_ext[3] + 1;
+            if (b.x1 <= b.x0) { b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; }
+            else { b.x0 = min(b.x0, x0); b.y0 = min(b.y0, y0); b.x1 = max(b.x1, x1); b.y1 = max(b.y1, y1); }
+            *pend_meta = b;
+            pend_meta = nullptr;
+        }
+        if (pend_done != nullptr) {
+            __threadfence();
+            atomicAdd(pend_done, 1u);        // that half has read the root: its owner may write it
+            pend_done = nullptr;
+        }
+    };
+    if (threadIdx.x == 0) s_next = atomicAdd(&counters->ray_work_head, 1ull);
 
     for (;;) {
-        __syncthreads();       // the previous item's shared state is no longer read
-        if (threadIdx.x == 0) s_next = atomicAdd(&counters->ray_work_head, 1ull);
-        __syncthreads();
+        __syncthreads();       // the previous item's shared state is no longer read; s_next holds this item
         const unsigned long long work = s_next;
         if (work >= 2ull * n_items) break;
         const unsigned long long item = work >> 1;
@@ -1448,12 +1474,19 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
         const long long lcx = f32_as_isize(floorf(sx)), lcy = f32_as_isize(floorf(sy));
         // every ray starts in the same cell; outside the grid nothing is emitted (ray.rs:88-92)
         const bool walked = !(lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh);
-        if (!walked && !fused) continue;
+        if (!walked && !fused) {   // nothing to do (both halves agree); the next item still has to be popped
+            __syncthreads();
+            if (helper) s_next = atomicAdd(&counters->ray_work_head, 1ull);
+            continue;
+        }
         // (a clone whose pose left the grid integrates nothing but still gets its own cells: the upper half copies all rows)
         const int cx0 = walked ? (int)lcx : 0, cy0 = walked ? (int)lcy : 0;
         const int rad = walked ? radius : 0;
         ext_init(s_ext);
-        if (threadIdx.x == 0) { s_nspill = 0u; s_nmine = 0u; s_xinfo[0] = 0x7fffffff; s_xinfo[1] = -1; s_eo_shared = 0u; }
+        if (threadIdx.x == 0) {
+            s_nspill = 0u; s_nmine = 0u; s_xinfo[0] = 0x7fffffff; s_xinfo[1] = -1; s_eo_shared = 0u;
+            s_lext[0] = s_lext[1] = 0x7fffffff; s_lext[2] = s_lext[3] = -1;
+        }
         for (int i = threadIdx.x; i < HALF_MAX_BANDS; i += blockDim.x) { s_blo[i] = 0x7fffffff; s_bhi[i] = -1; }
         if (threadIdx.x < HALF_XCHG_GROUPS) s_lrow[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
 
@@ -1469,6 +1502,10 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             s_row[ly].y = x0 | ((x1 - x0) << 16);
         }
         __syncthreads();
+        if (threadIdx.x >= 32) {   // the other warps clear the window while warp 0 lays out its rows
+            uint4* w4 = reinterpret_cast<uint4*>(s_win);
+            for (int i = threadIdx.x - 32; i < (int)(window_bytes >> 4); i += blockDim.x - 32) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         if (threadIdx.x < 32) {
             int carry = 0;
             for (int base = 0; base < wh; base += 32) {
@@ -1490,11 +1527,6 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             if (threadIdx.x == 0) s_row[wh] = make_int2(carry, 0);
         }
         __syncthreads();
-        {
-            const int wcells = s_row[wh].x;
-            uint4* w4 = reinterpret_cast<uint4*>(s_win);
-            for (int i = threadIdx.x; i < (wcells >> 3); i += blockDim.x) w4[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
         // ---- which beams are this half's: y_inc >= 0 (upper) or < 0 (lower), decided exactly as the iterator does
         //      (ray.rs:54-72); a cheap test settles all but the nearly horizontal ones
         if (walked) {
@@ -1529,6 +1561,10 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             }
         }
         __syncthreads();
+        if (helper) {
+            flush_pending();
+            s_next = atomicAdd(&counters->ray_work_head, 1ull);   // (read only after the barrier that ends this item)
+        }
         if (walked)
             ray_walk_half(geom, scan, s_beam, s_nmine, px, py, ptheta, sx, sy, cx0, cy0, rad, upper, wy0, wh, band0, s_win, s_row,
                           s_rowb, s_blo, s_bhi, s_ext, &s_nspill, my_spill, &spilled, &cell_steps);
@@ -1588,6 +1624,7 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
                 const bool any = shared_band >= 0 && (unsigned)lb < (unsigned)HALF_MAX_BANDS && s_bhi[lb] >= s_blo[lb];
                 x->band_lo = any ? s_blo[lb] : 0x7fffffff;
                 x->band_hi = any ? s_bhi[lb] : -1;
+                x->ext[0] = s_ext[0]; x->ext[1] = s_ext[1]; x->ext[2] = s_ext[2]; x->ext[3] = s_ext[3];
                 // parked hits of lower rays on the start row travel too: the upper half writes that row
                 uint32_t nh = 0u;
                 const uint32_t ns = min(s_nspill, RAY_SPILL_CAP);
@@ -1618,6 +1655,7 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             if (threadIdx.x < HALF_XCHG_GROUPS) s_lrow[threadIdx.x] = __ldcg(&x->row[threadIdx.x]);
             if (threadIdx.x == 0) {
                 s_xinfo[0] = __ldcg(&x->band_lo); s_xinfo[1] = __ldcg(&x->band_hi);
+                s_lext[0] = __ldcg(&x->ext[0]); s_lext[1] = __ldcg(&x->ext[1]); s_lext[2] = __ldcg(&x->ext[2]); s_lext[3] = __ldcg(&x->ext[3]);
                 const uint32_t nh = __ldcg(&x->n_hits);
                 for (uint32_t k = 0; k < nh; ++k) {
                     const uint32_t at = atomicAdd(&s_nspill, 1u);
@@ -1673,28 +1711,27 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
                 global_cell_add(&grid[phys_index(geom, x, y)], (e & 0x40000000u) ? CELL_OCC_INC : CELL_FREE_INC, &saturated);
             }
         }
-        if (threadIdx.x == 0) {
-            // the slot's box: (a clone's was set to its source's when it was listed) + what this half touched
-            if (s_ext[2] >= s_ext[0]) {
-                SlotMeta* mp = &meta[it.slot];
-                while (atomicCAS(&mp->pad0, 0, 1) != 0) __nanosleep(50);     // the two halves of a particle update one box
-                __threadfence();
-                ext_commit(s_ext, mp, gw);
-                __threadfence();
-                atomicExch(&mp->pad0, 0);
+        if (helper) {
+            // The slot's box (a clone's was set to its source's when it was listed) grows by what both halves touched:
+            // the upper half commits for both (the lower half's extent came with the exchange record), so the box has
+            // one writer. Committed, like the reader signal, while the next item walks.
+            if (upper && walked) {
+                const int e0 = min(s_ext[0], s_lext[0]), e1 = min(s_ext[1], s_lext[1]), e2 = max(s_ext[2], s_lext[2]), e3 = max(s_ext[3], s_lext[3]);
+                if (e2 >= e0 && e3 >= e1) { pend_meta = &meta[it.slot]; pend_ext[0] = e0; pend_ext[1] = e1; pend_ext[2] = e2; pend_ext[3] = e3; }
             }
-            if (fused) {
-                __threadfence();
-                atomicAdd(&done[it.root], 1u);        // this half has read the root: its owner may write it
-            }
+            if (fused) pend_done = &done[it.root];
         }
     }
+    if (helper) flush_pending();
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { cell_steps += __shfl_down_sync(0xffffffffu, cell_steps, o); moved += __shfl_down_sync(0xffffffffu, moved, o); }
     if ((threadIdx.x & 31) == 0 && cell_steps) atomicAdd(&counters->ray_cell_steps, (unsigned long long)cell_steps);
-    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
+    if ((threadIdx.x & 31) == 0 && moved) {
+        atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
+        atomicAdd(&counters->ray_copy_bytes, (unsigned long long)moved * 32ull);
+    }
 }
 
 // =============================================================================== k_sort_beams

@@ -418,7 +418,7 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
     if (gt == 0) {   // per-step counters start from zero
         counters->clamped = 0ull; counters->saturated = 0ull; counters->spilled = 0ull;
         counters->n_alive = 0ull; counters->copy_bytes = 0ull; counters->copy_max_rows = 0ull;
-        counters->n_mat = 0ull; counters->n_mat_leaders = 0ull; counters->ray_cell_steps = 0ull;
+        counters->n_mat = 0ull; counters->n_mat_leaders = 0ull; counters->ray_cell_steps = 0ull; counters->ray_copy_bytes = 0ull;
         counters->ray_work_head = 0ull; counters->ray_items_front = 0ull; counters->ray_items_back = 0ull;
     }
     FOLD_STAMP(1);
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
         if (a.history) {
             StepRecord r;
             r.step = a.step; r.n_copies = n_copied; r.n_pulls = n_remote; r.distinct = distinct; r.n_leaders = n_lead;
-            r.n_alive = 0; r.copy_bytes = 0; r.ray_cell_steps = 0;   // filled in by the step's last kernel (k_commit_boxes)
+            r.n_alive = 0; r.copy_bytes = 0; r.ray_cell_steps = 0; r.ray_copy_bytes = 0;   // filled in by the step's last kernel (k_commit_boxes)
             a.history[a.step % STEP_HISTORY] = r;
         }
     }
