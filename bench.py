@@ -16,7 +16,9 @@ Legs of the CUDA arm
          CUDA events on the library's stream, max over ranks.
   e2e    K steps through the reference-facing call sequence of GridMapSlamNode::update
          (node.rs:47-60): update(host scan) -> estimated_pose() -> estimated_likelihood() into a
-         pinned host grid; host<->device copies inside the timed region.
+         pinned host grid; host<->device copies inside the timed region. `e2e` runs the read-out
+         pipelined by one step (estimated_likelihood_async + map_wait: map t is copied while
+         update(t+1) runs), `e2e_blocking` with every call blocking.
   roofline  the kernel that takes most of the step. With deferred copies (default) that is the ray
          update: 8 B per step of the reference's ray iterator, steps counted by the
          kernel, over the kernel's own CUDA-event time, against MEASURED_PEAKS.json's HBM copy
@@ -297,13 +299,31 @@ def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2
         e1.record(stream)
         slam.sync()
         barrier()
+        out["ms_e2e_sync"] = e0.elapsed_time(e1)
+        # the same call sequence, pipelined by one step as a node that publishes map t while step t+1 runs would: the
+        # 8 MB copy of map t overlaps update(t+1); every step's map still lands in host memory inside the timed region
+        pinned2 = [pinned, torch.empty(slam.grid_w * slam.grid_h, dtype=torch.float64).pin_memory()]
+        bufs = [p_.numpy() for p_ in pinned2]
+        slam.estimated_likelihood_async(bufs[1] if rank == 0 else None)   # (first use of the copy stream, untimed)
+        slam.map_wait()
+        barrier()
+        e0.record(stream)
+        for i, (obs, odo) in enumerate(scans[W + 2 * K:W + 3 * K]):   # the trajectory continues: fresh scans
+            slam.update(obs, odo)                  # GridMapSlam::update with HOST scan buffers (blocks until the step is done)
+            slam.estimated_pose()
+            slam.map_wait()                        # map i-1 has landed (it was copied while step i ran): publish it
+            slam.estimated_likelihood_async(bufs[i & 1] if rank == 0 else None)
+        slam.map_wait()
+        e1.record(stream)
+        slam.sync()
+        barrier()
         out["ms_e2e"] = e0.elapsed_time(e1)
         # the same loop with the cheaper read-out a visualizer needs: informed window only, f32
         pinned32 = torch.empty(slam.grid_w * slam.grid_h, dtype=torch.float32).pin_memory().numpy()
         barrier()
         e0.record(stream)
         win_bytes = 0
-        for obs, odo in scans[W + 2 * K:W + 3 * K]:   # the trajectory continues: fresh scans
+        for obs, odo in scans[W + 3 * K:W + 4 * K]:   # the trajectory continues: fresh scans
             slam.update(obs, odo)
             slam.estimated_pose()
             if rank == 0:
@@ -318,7 +338,7 @@ def measure_cuda(args, wl, rank, world, local, dev, nccl_id, scans, flags, do_e2
         out["e2e_window_bytes"] = win_bytes / max(1, K)
     if do_aged:
         # the same filter after AGED more scans: informed extents and survivor counts have grown
-        base = W + 3 * K if do_e2e else W + K
+        base = W + 4 * K if do_e2e else W + K
         n_more = len(scans) - base - K
         d_more = []
         for obs, odo in scans[base:]:
@@ -379,7 +399,7 @@ def run_cuda(args, wl, rank, world, local):
     sim = wl.simulator()
     AGED = 160
     do_aged = not args.no_aged
-    scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(W + 3 * K + ((AGED + K) if do_aged else 0))]
+    scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(W + 4 * K + ((AGED + K) if do_aged else 0))]
 
     clocks = ClockSampler(local)
     clocks.start()
@@ -437,7 +457,8 @@ def run_cuda(args, wl, rank, world, local):
                                                       eager["ms_value"] if eager else 0.0,
                                                       main["aged"]["ms"] if "aged" in main else 0.0,
                                                       c5["ms_value"] if c5 else 0.0,
-                                                      full["phase_ms"]["copy"] if full else 0.0])
+                                                      full["phase_ms"]["copy"] if full else 0.0,
+                                                      main.get("ms_e2e_sync", 0.0)])
     hist = main["hist"]
     tot = reduce_sum([hist[:, 0].sum(), hist[:, 1].sum(), hist[:, 4].sum(),
                       float(full["hist"][:, 5].sum()) if full else 0.0, float(hist[:, 5].sum()), 8.0 * float(hist[:, 6].sum()),
@@ -546,7 +567,14 @@ def run_cuda(args, wl, rank, world, local):
         gw, gh = main["grid"]
         line["e2e"] = {"value": pbu * K / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / K,
                        "h2d_bytes_per_step": int(wl.n_beams * (4 + 4 + 1)), "d2h_bytes_per_step": int(12 + 8 * gw * gh),
-                       "path": "update(host scan) + estimated_pose() + estimated_likelihood() per step (node.rs:47-60)"}
+                       "path": "update(host scan) + estimated_pose() + estimated_likelihood_async() per step, map_wait() before "
+                               "the next read-out (node.rs:47-60 with the 8 B/cell map of step t copied to pinned host memory "
+                               "while update(t+1) runs; every step's pose and whole map reach the host inside the timed region)"}
+        ms_sync = float(tmax[9 + len(_lib.PHASES)])
+        line["e2e_blocking"] = {"value": pbu * K / (ms_sync * 1e-3), "unit": UNIT, "ms_per_step": ms_sync / K,
+                                "d2h_bytes_per_step": int(12 + 8 * gw * gh),
+                                "path": "update(host scan) + estimated_pose() + estimated_likelihood() per step, each call "
+                                        "blocking (node.rs:47-60 as written)"}
         ms_win = float(tmax[4 + len(_lib.PHASES)])
         line["e2e_window_readout"] = {
             "value": pbu * K / (ms_win * 1e-3), "unit": UNIT, "ms_per_step": ms_win / K,

@@ -185,6 +185,14 @@ int slamrs_gpu_pose(slamrs_gpu_handle* h, float out_xyt[3]);
  * pool over NVLink, a rank that passes NULL takes part without receiving the map (the reference has
  * one consumer, node.rs:53-57). */
 int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells);
+/* The same read-out for a pipelined caller (a node that publishes map t while step t+1 runs): the conversion is
+ * queued behind the steps issued so far, the copy into out_cells (page-locked host memory, or the copy is not
+ * asynchronous) runs on a stream of its own, and the call returns at once; out_cells holds the map once
+ * slamrs_gpu_map_wait has returned. Steps issued in between overlap the copy and do not disturb it (the map is
+ * converted into one of two device buffers first); at most two read-outs may be pending. Collective like
+ * map_probability when world_size>1. */
+int slamrs_gpu_map_probability_async(slamrs_gpu_handle* h, double* out_cells);
+int slamrs_gpu_map_wait(slamrs_gpu_handle* h);
 
 /* Cheaper forms of the same read-out for consumers that do not need 8 bytes per cell of the whole
  * grid (the visualizer converts every cell to an f32 grey level,

@@ -101,6 +101,8 @@ extern "C" {
     pub fn slamrs_gpu_set_scan_device(h: *mut slamrs_gpu_handle, angle: *const f32, dist: *const f32, valid: *const u8, n_beams: u32, max_dist: f32) -> c_int;
     pub fn slamrs_gpu_pose(h: *mut slamrs_gpu_handle, out_xyt: *mut f32) -> c_int;
     pub fn slamrs_gpu_map_probability(h: *mut slamrs_gpu_handle, out_cells: *mut f64) -> c_int;
+    pub fn slamrs_gpu_map_probability_async(h: *mut slamrs_gpu_handle, out_cells: *mut f64) -> c_int;
+    pub fn slamrs_gpu_map_wait(h: *mut slamrs_gpu_handle) -> c_int;
     pub fn slamrs_gpu_map_extent(h: *mut slamrs_gpu_handle, out_x0y0x1y1: *mut i32) -> c_int;
     pub fn slamrs_gpu_map_window(h: *mut slamrs_gpu_handle, format: u32, x0: i32, y0: i32, x1: i32, y1: i32, out: *mut c_void) -> c_int;
     pub fn slamrs_gpu_effective_particles(h: *mut slamrs_gpu_handle, out: *mut f64) -> c_int;

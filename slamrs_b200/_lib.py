@@ -33,6 +33,7 @@ EXPORTS = [
     "slamrs_gpu_get_step_history", "slamrs_gpu_map_extent", "slamrs_gpu_map_window",
     "slamrs_gpu_effective_particles", "slamrs_gpu_sim_scan", "slamrs_gpu_get_scan", "slamrs_gpu_get_slots",
     "slamrs_gpu_get_extents", "slamrs_gpu_debug_resample", "slamrs_gpu_init_uniform",
+    "slamrs_gpu_map_probability_async", "slamrs_gpu_map_wait",
 ]
 MAP_F64, MAP_F32, MAP_U8 = 0, 1, 2
 PHASES = ["motion_likelihood", "all_gather", "resample", "materialize", "ray_update", "pull", "copy"]
@@ -92,6 +93,8 @@ def load():
     L.slamrs_gpu_sync.restype = i; L.slamrs_gpu_sync.argtypes = [vp]
     L.slamrs_gpu_pose.restype = i; L.slamrs_gpu_pose.argtypes = [vp, vp]
     L.slamrs_gpu_map_probability.restype = i; L.slamrs_gpu_map_probability.argtypes = [vp, vp]
+    L.slamrs_gpu_map_probability_async.restype = i; L.slamrs_gpu_map_probability_async.argtypes = [vp, vp]
+    L.slamrs_gpu_map_wait.restype = i; L.slamrs_gpu_map_wait.argtypes = [vp]
     L.slamrs_gpu_last_error.restype = C.c_char_p; L.slamrs_gpu_last_error.argtypes = [vp]
     L.slamrs_gpu_get_stats.restype = i; L.slamrs_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.slamrs_gpu_stream.restype = vp; L.slamrs_gpu_stream.argtypes = [vp]

@@ -75,6 +75,11 @@ struct slamrs_gpu_handle {
     float* d_dist = nullptr;
     uint8_t* d_valid = nullptr;
     uint32_t beam_cap = 0, n_beams = 0;
+    // host scans travel in ONE copy: d_angle | d_dist | d_valid are pieces of one allocation (d_angle is its base),
+    // filled from a page-locked staging buffer of the same layout
+    unsigned char* h_scan_stage = nullptr;
+    cudaEvent_t ev_scan_uploaded = nullptr;
+    bool scan_upload_pending = false;
     int radius_cells = 1;
     double* d_z = nullptr;
     double* d_u = nullptr;
@@ -90,6 +95,13 @@ struct slamrs_gpu_handle {
     StepCounters* d_counters = nullptr;
     StepCounters* h_counters = nullptr;  // pinned
     double* d_export = nullptr;
+    // pipelined map read-out (slamrs_gpu_map_probability_async): two export buffers, filled on the step's stream and
+    // copied to the host on a stream of their own, so the copy overlaps the next step
+    double* d_export_async[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_exported[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool async_pending[2] = {false, false};
+    int async_next = 0;
     double* d_term_table = nullptr;   // per-beam likelihood factor by hit-counter pair
     int* d_barrier = nullptr;
 
@@ -269,7 +281,9 @@ void free_all(slamrs_gpu_handle* h) {
     cudaFree(h->d_pose[0]); cudaFree(h->d_pose[1]);
     cudaFree(h->d_term_table);
     cudaFree(h->d_wnorm); cudaFree(h->d_cum); cudaFree(h->d_idx); cudaFree(h->d_fold); cudaFree(h->d_carry);
-    cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
+    cudaFree(h->d_angle);   // (d_dist and d_valid live in the same allocation)
+    if (h->h_scan_stage) cudaFreeHost(h->h_scan_stage);
+    if (h->ev_scan_uploaded) cudaEventDestroy(h->ev_scan_uploaded);
     cudaFree(h->d_z); cudaFree(h->d_u);
     cudaFree(h->d_keep); cudaFree(h->d_need); cudaFree(h->d_free); cudaFree(h->d_spare);
     cudaFree(h->d_copies); cudaFree(h->d_leaders); cudaFree(h->d_alive); cudaFree(h->d_jobs);
@@ -285,6 +299,12 @@ void free_all(slamrs_gpu_handle* h) {
     if (h->ev_plan) cudaEventDestroy(h->ev_plan);
     if (h->ev_sort) cudaEventDestroy(h->ev_sort);
     cudaFree(h->d_order); cudaFree(h->d_valid_list); cudaFree(h->d_n_valid);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(h->d_export_async[k]);
+        if (h->ev_exported[k]) cudaEventDestroy(h->ev_exported[k]);
+        if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
+    }
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -294,12 +314,18 @@ void free_all(slamrs_gpu_handle* h) {
 int ensure_beam_capacity(slamrs_gpu_handle* h, uint32_t n) {
     if (n <= h->beam_cap) return SLAMRS_OK;
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_angle); cudaFree(h->d_dist); cudaFree(h->d_valid);
-    h->d_angle = h->d_dist = nullptr; h->d_valid = nullptr; h->beam_cap = 0;
+    cudaFree(h->d_angle);
+    if (h->h_scan_stage) cudaFreeHost(h->h_scan_stage);
+    h->d_angle = h->d_dist = nullptr; h->d_valid = nullptr; h->h_scan_stage = nullptr; h->beam_cap = 0;
+    h->scan_upload_pending = false;
     const uint32_t cap = (n + 255u) & ~255u;
-    CU_TRY(h, cudaMalloc(&h->d_angle, sizeof(float) * cap));
-    CU_TRY(h, cudaMalloc(&h->d_dist, sizeof(float) * cap));
-    CU_TRY(h, cudaMalloc(&h->d_valid, cap));
+    unsigned char* base = nullptr;
+    CU_TRY(h, cudaMalloc(&base, 9u * (size_t)cap));
+    h->d_angle = reinterpret_cast<float*>(base);
+    h->d_dist = reinterpret_cast<float*>(base + 4u * (size_t)cap);
+    h->d_valid = base + 8u * (size_t)cap;
+    CU_TRY(h, cudaMallocHost(&h->h_scan_stage, 9u * (size_t)cap));
+    if (!h->ev_scan_uploaded) CU_TRY(h, cudaEventCreateWithFlags(&h->ev_scan_uploaded, cudaEventDisableTiming));
     h->beam_cap = cap;
     return SLAMRS_OK;
 }
@@ -367,8 +393,10 @@ int step_barrier(slamrs_gpu_handle* h) {
 // stream synchronisation) serves every read-out that follows the same step.
 int fetch_counters(slamrs_gpu_handle* h) {
     if (h->counters_fresh) return SLAMRS_OK;
-    CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(StepCounters), cudaMemcpyDeviceToHost, h->stream));
+    launch_publish_counters(h->stream, h->d_counters, h->h_counters);   // (not a memcpy: see k_publish_counters)
+    h->launches++;
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaGetLastError());
     h->counters_fresh = true;
     return SLAMRS_OK;
 }
@@ -577,6 +605,13 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
     memset(h->h_counters, 0, sizeof(StepCounters));
     CREATE_CU(cudaMalloc(&h->d_export, sizeof(double) * h->n_cells));
+    // the pipelined read-out's buffers exist from the start: no allocation (an implicit device synchronisation) later
+    CREATE_CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CREATE_CU(cudaMalloc(&h->d_export_async[k], sizeof(double) * h->n_cells));
+        CREATE_CU(cudaEventCreateWithFlags(&h->ev_exported[k], cudaEventDisableTiming));
+        CREATE_CU(cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
+    }
     CREATE_CU(cudaMalloc(&h->d_term_table, sizeof(double) * LK_TABLE_NF * LK_TABLE_NO));
     launch_fill_term_table(h->stream, h->d_term_table);
     h->launches++;
@@ -625,6 +660,9 @@ void slamrs_gpu_destroy(slamrs_gpu_handle* h) {
         if (ray_trace(tr) == 0) {
             fprintf(stderr, "ray trace: items fused %llu in-place %llu; cycles pop %llu setup %llu walk %llu fused_total %llu wait %llu inplace_wb %llu | fused: prepass %llu loop %llu barrier %llu\n",
                     tr[16], tr[17], tr[0], tr[1], tr[2], tr[3], tr[4], tr[5], tr[8], tr[9], tr[10]);
+            fprintf(stderr, "ray trace raw:");
+            for (int k = 0; k < 18; ++k) fprintf(stderr, " [%d]%llu", k, tr[k]);
+            fprintf(stderr, "\n");
         }
     }
     free_all(h);
@@ -639,9 +677,15 @@ int slamrs_gpu_upload_scan(slamrs_gpu_handle* h, const float* angle, const float
     int rc = ensure_beam_capacity(h, n_beams ? n_beams : 1);
     if (rc) return rc;
     if (n_beams) {
-        CU_TRY(h, cudaMemcpyAsync(h->d_angle, angle, sizeof(float) * n_beams, cudaMemcpyHostToDevice, h->stream));
-        CU_TRY(h, cudaMemcpyAsync(h->d_dist, dist, sizeof(float) * n_beams, cudaMemcpyHostToDevice, h->stream));
-        CU_TRY(h, cudaMemcpyAsync(h->d_valid, valid, n_beams, cudaMemcpyHostToDevice, h->stream));
+        // one asynchronous copy out of page-locked memory instead of three staged ones out of the caller's arrays
+        if (h->scan_upload_pending) CU_TRY(h, cudaEventSynchronize(h->ev_scan_uploaded));   // the staging buffer is free again
+        const size_t cap = h->beam_cap;
+        memcpy(h->h_scan_stage, angle, sizeof(float) * n_beams);
+        memcpy(h->h_scan_stage + 4u * cap, dist, sizeof(float) * n_beams);
+        memcpy(h->h_scan_stage + 8u * cap, valid, n_beams);
+        CU_TRY(h, cudaMemcpyAsync(h->d_angle, h->h_scan_stage, 8u * cap + n_beams, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaEventRecord(h->ev_scan_uploaded, h->stream));
+        h->scan_upload_pending = true;
     }
     h->n_beams = n_beams;
     h->scan_external = false;
@@ -892,8 +936,9 @@ int slamrs_gpu_pose(slamrs_gpu_handle* h, float out_xyt[3]) {
 }
 
 namespace {
-// exports [x0,x1) x [y0,y1) of the estimate's grid in `format` into the caller's host buffer
-int export_window(slamrs_gpu_handle* h, uint32_t format, int x0, int y0, int x1, int y1, void* out) {
+// exports [x0,x1) x [y0,y1) of the estimate's grid in `format` into the caller's host buffer; pipelined: the copy
+// runs on the handle's copy stream and the call returns once it is queued (slamrs_gpu_map_wait waits for it)
+int export_window(slamrs_gpu_handle* h, uint32_t format, int x0, int y0, int x1, int y1, void* out, bool pipelined = false) {
     if (format > SLAMRS_MAP_U8) return fail(h, SLAMRS_E_INVALID_ARG, "unknown map format");
     if (x0 < 0 || y0 < 0 || x1 > (int)h->geom.gw || y1 > (int)h->geom.gh || x1 < x0 || y1 < y0)
         return fail(h, SLAMRS_E_INVALID_ARG, "map window outside the grid");
@@ -909,13 +954,31 @@ int export_window(slamrs_gpu_handle* h, uint32_t format, int x0, int y0, int x1,
         rc = step_barrier(h);
         if (rc) return rc;
         if (out == nullptr) return SLAMRS_OK;   // took part, does not want the map
+    }
+    double* dst = h->d_export;
+    int k = 0;
+    if (pipelined) {
+        k = h->async_next;
+        h->async_next ^= 1;
+        if (h->async_pending[k]) CU_TRY(h, cudaStreamWaitEvent(s, h->ev_copied[k], 0));   // the buffer's previous copy has left it
+        dst = h->d_export_async[k];
+    }
+    if (h->world > 1) {
         const uint32_t owner = (uint32_t)h->h_counters->est_owner;
         launch_export(s, h->host_peer_cells[owner], h->host_peer_meta[owner], h->cells_per_grid, h->peer_counters[owner], h->geom,
-                      x0, y0, x1, y1, (int)format, h->d_export);
+                      x0, y0, x1, y1, (int)format, dst);
     } else {
-        launch_export(s, h->d_cells, h->d_meta, h->cells_per_grid, h->d_counters, h->geom, x0, y0, x1, y1, (int)format, h->d_export);
+        launch_export(s, h->d_cells, h->d_meta, h->cells_per_grid, h->d_counters, h->geom, x0, y0, x1, y1, (int)format, dst);
     }
     h->launches++;
+    if (pipelined) {
+        CU_TRY(h, cudaEventRecord(h->ev_exported[k], s));
+        CU_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_exported[k], 0));
+        CU_TRY(h, cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+        CU_TRY(h, cudaEventRecord(h->ev_copied[k], h->copy_stream));
+        h->async_pending[k] = true;
+        return SLAMRS_OK;
+    }
     CU_TRY(h, cudaMemcpyAsync(out, h->d_export, bytes, cudaMemcpyDeviceToHost, s));
     CU_TRY(h, cudaStreamSynchronize(s));
     CU_TRY(h, cudaGetLastError());
@@ -927,6 +990,24 @@ int slamrs_gpu_map_probability(slamrs_gpu_handle* h, double* out_cells) {
     if (!h || (!out_cells && h->world == 1)) return SLAMRS_E_INVALID_ARG;
     DeviceGuard g(h->device);
     return export_window(h, SLAMRS_MAP_F64, 0, 0, (int)h->geom.gw, (int)h->geom.gh, out_cells);
+}
+
+int slamrs_gpu_map_probability_async(slamrs_gpu_handle* h, double* out_cells) {
+    if (!h || (!out_cells && h->world == 1)) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    return export_window(h, SLAMRS_MAP_F64, 0, 0, (int)h->geom.gw, (int)h->geom.gh, out_cells, true);
+}
+
+int slamrs_gpu_map_wait(slamrs_gpu_handle* h) {
+    if (!h) return SLAMRS_E_INVALID_ARG;
+    DeviceGuard g(h->device);
+    for (int k = 0; k < 2; ++k) {
+        if (!h->async_pending[k]) continue;
+        CU_TRY(h, cudaEventSynchronize(h->ev_copied[k]));
+        h->async_pending[k] = false;
+    }
+    CU_TRY(h, cudaGetLastError());
+    return SLAMRS_OK;
 }
 
 int slamrs_gpu_map_extent(slamrs_gpu_handle* h, int32_t out_x0y0x1y1[4]) {

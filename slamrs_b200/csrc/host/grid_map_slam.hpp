@@ -131,6 +131,13 @@ public:
         return g;
     }
 
+    // Pipelined form for a node that publishes map t while step t+1 runs: the copy into `out` (size_x * size_y
+    // cells of page-locked host memory) overlaps whatever is issued next; `out` is complete after map_wait().
+    void estimated_likelihood_async(Probability* out) const {
+        check(slamrs_gpu_map_probability_async(h_, reinterpret_cast<double*>(out)), h_);
+    }
+    void map_wait() const { check(slamrs_gpu_map_wait(h_), h_); }
+
     // The informed part of the same map as f32 (what the visualizer converts every cell to,
     // visualize.rs:247): window = {x0, y0, x1, y1} in cells, values row-major; every cell outside
     // the window is exactly 0.5. Cuts the per-scan device-to-host copy from 8 B/cell of the whole grid.

@@ -247,6 +247,7 @@ void launch_copy(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
 void launch_export(cudaStream_t stream, const uint32_t* cells, const SlotMeta* meta, size_t cells_per_grid,
                    const StepCounters* counters, MapGeom geom, int x0, int y0, int x1, int y1, int format, void* out);
 void launch_estimate_extent(cudaStream_t stream, const SlotMeta* meta, const StepCounters* counters, int* out4);
+void launch_publish_counters(cudaStream_t stream, const StepCounters* counters, StepCounters* host_mirror);
 // one slot's grid in logical order: f64 log-odds (as_log_odds) or the raw packed counters
 void launch_export_slot(cudaStream_t stream, const uint32_t* grid, const SlotMeta* slot_meta, MapGeom geom,
                         bool as_log_odds, void* out);

@@ -60,6 +60,20 @@ void launch_estimate_extent(cudaStream_t stream, const SlotMeta* meta, const Ste
     k_estimate_extent<<<1, 1, 0, stream>>>(meta, counters, out4);
 }
 
+// The step counters reach the host through a kernel that stores them into the page-locked mirror (device-accessible
+// under UVA) instead of a device-to-host memcpy: a memcpy would queue on the copy engine behind a pipelined 8 MB map
+// read-out, and the host's wait for "step t+1 is done" would then include the copy of map t.
+__global__ void k_publish_counters(const StepCounters* __restrict__ counters, StepCounters* host_mirror) {
+    static_assert(sizeof(StepCounters) % sizeof(uint32_t) == 0, "copied word by word");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(counters);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(host_mirror);
+    for (uint32_t i = threadIdx.x; i < sizeof(StepCounters) / sizeof(uint32_t); i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+void launch_publish_counters(cudaStream_t stream, const StepCounters* counters, StepCounters* host_mirror) {
+    k_publish_counters<<<1, 128, 0, stream>>>(counters, host_mirror);
+}
+
 // one slot's grid in logical order
 __global__ void __launch_bounds__(256)
 k_export_slot(const uint32_t* __restrict__ grid, const SlotMeta* __restrict__ slot_meta, MapGeom geom, bool as_log_odds,

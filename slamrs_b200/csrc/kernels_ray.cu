@@ -2,6 +2,10 @@
 // (ray.rs:21-110) and the inverse sensor model (map.rs:148-172); hit counters accumulated in a
 // shared-memory disc window, written back with 128-bit read-modify-writes.
 #include "kernels_common.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
 
 namespace slamrs {
 
@@ -351,6 +355,16 @@ __device__ unsigned long long g_ray_trace[16];
 #endif
 #ifdef SLAMRS_RAY_TRACE
 __device__ unsigned long long g_ray_trace_items[2];
+// per work item of the LAST launch: globaltimer (ns) at each phase boundary of k_ray_update_half, + SM id and kind
+constexpr int RAY_LOG_ITEMS = 16384, RAY_LOG_COLS = 16;
+__device__ unsigned long long g_ray_log[RAY_LOG_ITEMS * RAY_LOG_COLS];
+__device__ __forceinline__ unsigned long long ray_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned ray_smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+#define RAY_LOG(w, k) do { if (threadIdx.x == 0 && (w) < (unsigned long long)RAY_LOG_ITEMS) g_ray_log[(w) * RAY_LOG_COLS + (k)] = ray_gtime(); } while (0)
+#define RAY_LOG_V(w, k, v) do { if (threadIdx.x == 0 && (w) < (unsigned long long)RAY_LOG_ITEMS) g_ray_log[(w) * RAY_LOG_COLS + (k)] = (v); } while (0)
+#else
+#define RAY_LOG(w, k) do { } while (0)
+#define RAY_LOG_V(w, k, v) do { } while (0)
 #endif
 
 // The walk of every beam of one particle into the shared-memory window (GridRayIterator, ray.rs:21-110, with
@@ -1450,11 +1464,16 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
         }
     };
     if (threadIdx.x == 0) s_next = atomicAdd(&counters->ray_work_head, 1ull);
+#ifdef SLAMRS_RAY_TRACE
+    long long t_prev = clock64();
+#endif
 
     for (;;) {
         __syncthreads();       // the previous item's shared state is no longer read; s_next holds this item
         const unsigned long long work = s_next;
         if (work >= 2ull * n_items) break;
+        RAY_STAMP(0);
+        RAY_LOG(work, 0);
         const unsigned long long item = work >> 1;
         const bool upper = (work & 1ull) != 0ull;   // the lower half of a particle is listed first
         RayItem it;
@@ -1527,6 +1546,8 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             if (threadIdx.x == 0) s_row[wh] = make_int2(carry, 0);
         }
         __syncthreads();
+        RAY_STAMP(1);
+        RAY_LOG(work, 1);
         // ---- which beams are this half's: y_inc >= 0 (upper) or < 0 (lower), decided exactly as the iterator does
         //      (ray.rs:54-72); a cheap test settles all but the nearly horizontal ones
         if (walked) {
@@ -1561,6 +1582,8 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             }
         }
         __syncthreads();
+        RAY_STAMP(2);
+        RAY_LOG(work, 2);
         if (helper) {
             flush_pending();
             s_next = atomicAdd(&counters->ray_work_head, 1ull);   // (read only after the barrier that ends this item)
@@ -1568,7 +1591,12 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
         if (walked)
             ray_walk_half(geom, scan, s_beam, s_nmine, px, py, ptheta, sx, sy, cx0, cy0, rad, upper, wy0, wh, band0, s_win, s_row,
                           s_rowb, s_blo, s_bhi, s_ext, &s_nspill, my_spill, &spilled, &cell_steps);
+#ifdef SLAMRS_RAY_TRACE
+        if (threadIdx.x == 0) atomicAdd(&g_ray_trace[12], (unsigned long long)(clock64() - t_prev));   // warp 0's own walk (longest beams)
+#endif
         __syncthreads();
+        RAY_STAMP(3);
+        RAY_LOG(work, 3);
 
         // ---- per band of the window the columns that really received hits (a lane scans one window row; the lower
         //      half leaves the start row to the upper half)
@@ -1609,6 +1637,8 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             if (lane == 0) ext_add(s_ext, wxmin, wymin, wxmax, wymax);
         }
         __syncthreads();
+        RAY_STAMP(4);
+        RAY_LOG(work, 4);
 
         // ---- the start row is shared: the lower half hands its window row for it (and what the upper half needs
         //      for the band both halves have rows in) to the upper half
@@ -1683,6 +1713,8 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             }
             __syncthreads();
         }
+        RAY_STAMP(5);
+        RAY_LOG(work, 5);
         // ---- an owner whose slot clones read in this step waits for them before it writes
         if (!fused && readers != nullptr) {
             if (threadIdx.x == 0) {
@@ -1698,9 +1730,20 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             }
             __syncthreads();
         }
+        RAY_STAMP(6);
+        RAY_LOG(work, 6);
         ray_half_writeback(geom, it, upper, cy0, walked, cells, meta, bands_all, cells_per_grid, s_win, s_row, s_blo, s_bhi, s_ext,
                            s_lrow, s_xinfo, s_eo_shared, wy0, wh, band0, &saturated, &moved);
+#ifdef SLAMRS_RAY_TRACE
+        if (threadIdx.x == 0) atomicAdd(&g_ray_trace[13], (unsigned long long)(clock64() - t_prev));   // warp 0's own write-back
+#endif
         __syncthreads();
+        RAY_STAMP(fused ? 7 : 11);
+        RAY_LOG(work, 7);
+        RAY_LOG_V(work, 9, (unsigned long long)ray_smid() | ((unsigned long long)blockIdx.x << 16) | (fused ? 1ull << 40 : 0ull) | (upper ? 1ull << 41 : 0ull) | ((unsigned long long)s_nmine << 44));
+#ifdef SLAMRS_RAY_TRACE
+        if (threadIdx.x == 0) atomicAdd(&g_ray_trace_items[fused ? 0 : 1], 1ull);
+#endif
         {   // the parked exact-path hits, now that the slot holds its cells (the lower half's start-row hits went to the upper half)
             const uint32_t ns = s_nspill;
             if (ns > RAY_SPILL_CAP && threadIdx.x == 0) atomicAdd(&counters->fuse_overflow, 1ull);
@@ -1721,8 +1764,13 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             }
             if (fused) pend_done = &done[it.root];
         }
+        RAY_STAMP(14);
+        RAY_LOG(work, 8);
     }
     if (helper) flush_pending();
+#ifdef SLAMRS_RAY_TRACE
+    if (threadIdx.x == 0) { atomicAdd(&g_ray_trace[15], (unsigned long long)(clock64() - t_prev)); }
+#endif
     if (saturated) atomicAdd(&counters->saturated, 1ull);
     if (spilled) atomicAdd(&counters->spilled, (unsigned long long)spilled);
 #pragma unroll
@@ -1783,6 +1831,24 @@ bool ray_update_can_fuse(const MapGeom& geom, uint32_t n_beams, size_t cells_per
            geom.tiled != 0u && geom.windowed == 0u && geom.gw < 32768u && geom.gh < 32768u &&
            ray_packed_radius(radius_cells) >= radius_cells;
 }
+#ifdef SLAMRS_RAY_TRACE
+// tuning builds: after the SLAMRS_RAY_TRACE_LAUNCH-th launch of k_ray_update_half, dump its per-item timeline
+static void ray_log_dump_after_launch(cudaStream_t stream) {
+    static int launches = 0;
+    const char* path = getenv("SLAMRS_RAY_TRACE_LOG");
+    const char* which = getenv("SLAMRS_RAY_TRACE_LAUNCH");
+    const int first = which ? atoi(which) : 20;
+    ++launches;
+    if (!path || launches < first || launches >= first + 4) return;
+    const std::string name = std::string(path) + "." + std::to_string(launches - first);
+    path = name.c_str();
+    cudaStreamSynchronize(stream);
+    std::vector<unsigned long long> log((size_t)RAY_LOG_ITEMS * RAY_LOG_COLS);
+    if (cudaMemcpyFromSymbol(log.data(), g_ray_log, log.size() * sizeof(unsigned long long)) == cudaSuccess) {
+        if (FILE* f = fopen(path, "wb")) { fwrite(log.data(), sizeof(unsigned long long), log.size(), f); fclose(f); }
+    }
+}
+#endif
 int ray_trace(unsigned long long* out18) {
 #ifdef SLAMRS_RAY_TRACE
     cudaError_t e = cudaMemcpyFromSymbol(out18, g_ray_trace, sizeof(unsigned long long) * 16);
@@ -1825,6 +1891,9 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
         k_ray_update_half<<<grid, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, clones, owners, readers, done,
                                                            xflag, (HalfXchg*)xchg, spill_scratch, slot_of, cells, meta, bands,
                                                            cells_per_grid, radius, (uint32_t)wbytes, counters);
+#ifdef SLAMRS_RAY_TRACE
+        ray_log_dump_after_launch(stream);
+#endif
         return cudaSuccess;
     }
     int threads = (int)((scan.n_beams + 31u) / 32u * 32u);

@@ -228,6 +228,19 @@ class GridMapSlam:
         _lib.check(self._L.slamrs_gpu_map_probability(self._h, _ptr(out)), self._h)
         return GridData((self.grid_w, self.grid_h), out)
 
+    def estimated_likelihood_async(self, out: Optional[np.ndarray]) -> None:
+        """Pipelined estimated_likelihood(): queues the conversion behind the steps issued so far and the copy into
+        `out` (flat f64, grid_w * grid_h, page-locked host memory) on the handle's copy stream, and returns; `out` holds
+        the map after map_wait(). The next update() may be issued first: the copy overlaps it. Multi-GPU: every rank
+        calls it, `out=None` on ranks that only take part."""
+        if out is not None and (out.dtype != np.float64 or out.size < self.grid_w * self.grid_h):
+            raise ValueError("out must be a flat float64 buffer of grid_w * grid_h cells")
+        _lib.check(self._L.slamrs_gpu_map_probability_async(self._h, None if out is None else _ptr(out)), self._h)
+
+    def map_wait(self) -> None:
+        """Blocks until every pending estimated_likelihood_async() copy has landed in its buffer."""
+        _lib.check(self._L.slamrs_gpu_map_wait(self._h), self._h)
+
     def skip_estimated_likelihood(self) -> None:
         """Multi-GPU: take part in the other ranks' estimated_likelihood() without receiving the map."""
         _lib.check(self._L.slamrs_gpu_map_probability(self._h, None), self._h)

@@ -103,3 +103,30 @@ def test_number_of_effective_particles(oracle):
             assert abs(got - ref) <= 1e-9 * ref, (step, got, ref)
             assert 1.0 <= got <= 64.0
     osl.close()
+
+
+def test_pipelined_map_readout_equals_the_blocking_one():
+    """estimated_likelihood_async(t) + update(t+1) + map_wait(): the map of step t, bit for bit, although the next
+    step was issued (and has changed the estimate's grid) before the copy was awaited; two read-outs in flight."""
+    import torch
+    cfg = GridMapSlamConfig(position=(-4.0, -4.0), width=8.0, height=8.0, resolution=0.02, n_particles=64)
+    scans = make_scans(2.0, 360, 2.0, 7)
+    n = 400 * 400
+    bufs = [torch.empty(n, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    with GridMapSlam(cfg) as a, GridMapSlam(cfg) as b:
+        assert a.grid_w * a.grid_h == n
+        want = []
+        for obs, odo in scans:
+            b.update(obs, odo)
+            want.append(b.estimated_likelihood().data.copy())
+        for t, (obs, odo) in enumerate(scans):
+            a.update(obs, odo)
+            if t >= 2:      # the buffer about to be reused still holds map t-2 (two read-outs pending at most)
+                a.map_wait()
+                assert np.array_equal(bufs[t & 1], want[t - 2])
+                assert np.array_equal(bufs[(t - 1) & 1], want[t - 1])
+            bufs[t & 1][:] = -1.0
+            a.estimated_likelihood_async(bufs[t & 1])
+        a.map_wait()
+        assert np.array_equal(bufs[(len(scans) - 1) & 1], want[-1])
+        assert np.array_equal(a.estimated_likelihood().data, want[-1])
