@@ -599,7 +599,7 @@ int slamrs_gpu_create(const slamrs_gpu_config* cfg, slamrs_gpu_handle** out) {
     CREATE_CU(cudaMalloc(&h->d_mat_roots, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_alive, sizeof(uint32_t) * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_ray_items, sizeof(RayItem) * 2 * (size_t)h->n_local));   // clones | owners
-    CREATE_CU(cudaMalloc(&h->d_readers, sizeof(uint32_t) * (2 * (size_t)h->n_slots + h->n_local)));   // readers | done | xflag
+    CREATE_CU(cudaMalloc(&h->d_readers, sizeof(uint32_t) * (2 * (size_t)h->n_slots + 2 * (size_t)h->n_local)));   // readers | done | xflag | xdone
     CREATE_CU(cudaMalloc(&h->d_ray_xchg, ray_half_xchg_bytes() * h->n_local));
     CREATE_CU(cudaMalloc(&h->d_ray_spill, sizeof(uint32_t) * ray_spill_scratch_words(h->num_sms)));
     CREATE_CU(cudaMallocHost(&h->h_counters, sizeof(StepCounters)));
@@ -761,8 +761,13 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
                       ray_update_can_fuse(h->geom, h->n_beams, h->cells_per_grid, force_generic, h->radius_cells);
     // per-slot reader / done counters and per-item hand-over flags of the ray update (off the critical path: long before their use)
     const bool half_items = ray_update_can_fuse(h->geom, h->n_beams, h->cells_per_grid, force_generic, h->radius_cells);
+    // Pulls without a second barrier (world > 1, default path): the ray update publishes, per integrated slot, that the
+    // slot is complete; the pull kernels run on the side stream behind the planner, wait per source for that mark and
+    // overlap the tail of the ray update. Every rank takes the same decision (same configuration, same scan).
+    const bool flag_pulls = h->world > 1 && fuse && half_items && h->boxed_copy && h->p2p_exchange;
+    const uint32_t pull_epoch = flag_pulls ? (uint32_t)(h->step + 1ull) : 0u;
     if (half_items)
-        CU_TRY(h, cudaMemsetAsync(h->d_readers, 0, sizeof(uint32_t) * (2 * (size_t)h->n_slots + h->n_local), s));
+        CU_TRY(h, cudaMemsetAsync(h->d_readers, 0, sizeof(uint32_t) * (2 * (size_t)h->n_slots + 2 * (size_t)h->n_local), s));
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->defer ? h->d_alias : nullptr, h->d_cells, h->d_meta, h->cells_per_grid,
@@ -792,8 +797,9 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     //     ray kernel does it while it integrates the scan (fused: k_resample_indices lists the survivors as
     //     clones | owners, no copy kernels), or they are listed now and copied after PROF_MARK 3. Before the
     //     planner starts: both write the alias table.
-    RayLists ray{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (fuse) ray = RayLists{h->d_ray_items, h->d_ray_items + h->n_local, h->d_slot[cur], h->d_alias, h->d_readers, h->d_meta};
+    RayLists ray{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0u, 0u};
+    if (fuse) ray = RayLists{h->d_ray_items, h->d_ray_items + h->n_local, h->d_slot[cur], h->d_alias, h->d_readers, h->d_meta,
+                             h->n_local, flag_pulls ? 1u : 0u};
     launch_resample_indices(s, h->d_results, h->d_cum, h->n_total, caller ? h->d_u : nullptr, h->cfg.seed, h->step,
                             h->d_idx, h->d_pose[nxt], h->first, h->n_local, !all_particles, h->d_alive, ray, h->d_wnorm, h->d_carry,
                             h->d_counters);
@@ -833,9 +839,14 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     pa.staged = plan_can_stage(h->n_local, h->n_spare);
     pa.alias_of = h->d_alias; pa.defer = h->defer;
     launch_plan(h->side_stream, pa);
+    h->launches += 3;   // k_weights, k_resample_indices, k_plan
+    if (flag_pulls) {
+        // the first uses of remote sources, a short list: each job waits for its source's owner (NVLink reads)
+        launch_pull(h->side_stream, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders,
+                    h->n_local, h->geom, h->d_counters, h->num_sms, pull_epoch, h->barrier_timeout_ns);
+        h->launches++;
+    }
     CU_TRY(h, cudaEventRecord(h->ev_plan, h->side_stream));
-    h->launches++;
-    h->launches += 2;
     PROF_MARK(h, 3);
     if (h->defer && !fuse) {
         int mrc = materialize_copies(h, all_particles);
@@ -853,19 +864,19 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
                                 fuse ? h->d_readers + h->n_slots : nullptr, h->d_readers + 2 * (size_t)h->n_slots, h->d_ray_xchg,
                                 h->d_ray_spill, h->d_slot[cur],
                                 h->d_cells, h->d_meta, h->d_bands, h->cells_per_grid, h->radius_cells, h->d_counters, &h->window_cells,
-                                force_generic, h->num_sms));
+                                force_generic, h->num_sms, h->d_readers + 2 * (size_t)h->n_slots + h->n_local, pull_epoch));
     h->launches++;
     PROF_MARK(h, 5);
     CU_TRY(h, cudaStreamWaitEvent(s, h->ev_plan, 0));   // join: the copy lists are ready
     // 6. grid traffic: one launch copies from local and (over NVLink) remote sources alike. Across
     //    GPUs one barrier first: every source grid, wherever it lives, has received the scan. No
     //    second barrier: nothing written in this step is a slot a peer reads in this step (k_plan).
-    if (h->world > 1) {
+    if (h->world > 1 && !flag_pulls) {
         int brc = step_barrier(h);
         if (brc) return brc;
     }
     PROF_MARK(h, 6);
-    if (h->defer && h->world == 1) {
+    if ((h->defer && h->world == 1) || flag_pulls) {
         // deferred copies on one GPU: the planner's list is empty (no remote sources), nothing to launch
     } else if (h->boxed_copy) {
         // deferred copies: what is left here are the first uses of remote sources, a short list
@@ -878,7 +889,7 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
         launch_account_full_copy(s, &h->d_counters->n_copies, &h->d_counters->n_leaders, grid_bytes, h->d_counters);
         h->launches++;
     }
-    if (!(h->defer && h->world == 1)) h->launches++;
+    if (!((h->defer && h->world == 1) || flag_pulls)) h->launches++;
     PROF_MARK(h, 7);
     launch_commit_boxes(s, h->d_copies, &h->d_counters->n_copies, h->n_local, h->geom, h->boxed_copy, h->d_counters,
                         h->d_history + (h->step % STEP_HISTORY));
@@ -1440,7 +1451,7 @@ int slamrs_gpu_debug_resample(int device, const double* raw_weights, uint32_t n,
         launch_weights(nullptr, res.p, n, wn.p, cum.p, fold.p, 0.0, cnt.p);
         cudaEventRecord(ev[1], nullptr);
         launch_resample_indices(nullptr, res.p, cum.p, n, u.p, 0, 0, idx.p, nullptr, 0, 0, false, nullptr,
-                                RayLists{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, wn.p, nullptr, cnt.p);
+                                RayLists{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0u, 0u}, wn.p, nullptr, cnt.p);
         cudaEventRecord(ev[2], nullptr);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { for (auto& x : ev) cudaEventDestroy(x); return fail(nullptr, SLAMRS_E_CUDA, cudaGetErrorString(e)); }

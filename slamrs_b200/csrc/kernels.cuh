@@ -52,8 +52,10 @@ struct StepCounters {
     unsigned long long ray_cell_steps;   // ray-iterator steps integrated this step (packed ray kernel), for the roofline
     unsigned long long ray_copy_bytes;   // bytes of clone copies the ray update read + wrote this step (part of copy_bytes)
     unsigned long long ray_work_head;    // next item of the ray update's work list (popped by its resident CTAs)
-    unsigned long long ray_items_front;  // k_ray_items: clones listed so far (front of the list)
-    unsigned long long ray_items_back;   // k_ray_items: slot owners listed so far (back of the list)
+    unsigned long long ray_items_front;  // ray work list: clones whose grid a peer GPU pulls in this step (listed first)
+    unsigned long long ray_items_back;   // ray work list: slot owners whose grid a peer GPU pulls (first among the owners)
+    unsigned long long ray_items_front_local;  // the other clones (behind the pulled ones)
+    unsigned long long ray_items_back_local;   // the other slot owners (last)
     unsigned long long fuse_overflow;    // fused ray update: more parked hits than its scratch holds (error, cannot happen by its bound)
     unsigned long long do_resample;      // k_weights: this step resamples (always 1 unless adaptive resampling is on)
     unsigned long long carry_active;     // the weights of the last step were carried over (it did not resample)
@@ -128,7 +130,22 @@ struct RayLists {
     int32_t* alias_of;
     uint32_t* readers;
     SlotMeta* meta;
+    uint32_t n_local;        // capacity of clones[] and of owners[]: pulled items fill them from the front, the others from the back
+    uint32_t mark_remote;    // world > 1: RayItem::pad = 1 for a particle that a new particle of ANOTHER rank selects (that
+                             // rank pulls the grid in this step: listed first, and the ray update signals its completion)
 };
+// work item k of the lists above: pulled clones, other clones, pulled owners, other owners
+__device__ __forceinline__ RayItem ray_item_at(const RayItem* __restrict__ clones, const RayItem* __restrict__ owners,
+                                               uint32_t n_local, const StepCounters* counters, unsigned long long k) {
+    const unsigned long long n_rc = counters->ray_items_front, n_lc = counters->ray_items_front_local;
+    if (k < n_rc) return clones[k];
+    k -= n_rc;
+    if (k < n_lc) return clones[n_local - 1u - k];
+    k -= n_lc;
+    const unsigned long long n_ro = counters->ray_items_back;
+    if (k < n_ro) return owners[k];
+    return owners[n_local - 1u - (k - n_ro)];
+}
 // ---- launch wrappers (all asynchronous on `stream`) ----
 void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, ScanDevice scan,
                               const float* pose_cur, const int32_t* slot_of, const int32_t* alias_of /* may be null */,
@@ -166,7 +183,11 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
                               uint32_t* spill_scratch,
                               const int32_t* slot_of, uint32_t* cells, SlotMeta* meta, uint32_t* bands,
                               size_t cells_per_grid, int radius_cells, StepCounters* counters,
-                              uint64_t* window_cells, bool force_generic, int num_sms);
+                              uint64_t* window_cells, bool force_generic, int num_sms,
+                              uint32_t* xdone /* per work item, zeroed by the caller */,
+
+                              uint32_t signal_epoch /* != 0 (half-item kernel only): every integrated slot's SlotMeta::pad0
+                                                       receives it once both halves are in place (peers that pull the slot wait for it) */);
 
 // fold_scratch: weights_scratch_doubles() doubles
 // resample_tau > 0: counters->do_resample = N_eff < tau * N (adaptive resampling), else 1
@@ -261,8 +282,15 @@ void launch_init_slots(cudaStream_t stream, int32_t* slot_of, uint32_t n_local, 
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
                        const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t max_items,
                        void* jobs /* max_items * copy_job_bytes() of scratch */, MapGeom geom,
-                       StepCounters* counters, int num_sms, bool short_list = false /* a few hundred items: one wave of CTAs */);
+                       StepCounters* counters, int num_sms, bool short_list = false /* a few hundred items: one wave of CTAs */,
+                       uint32_t wait_epoch = 0 /* != 0: a job waits until its source's SlotMeta::pad0 holds it (set by the
+                                                  owner's ray update, launch_ray_update's signal_epoch) */,
+                       unsigned long long timeout_ns = 0);
 size_t copy_job_bytes();
+// the same for a short list of REMOTE sources, one CTA per job, each job waiting for its own source (see k_pull)
+void launch_pull(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders, const unsigned long long* n_items,
+                 const unsigned long long* n_leaders, uint32_t max_items, MapGeom geom, StepCounters* counters, int num_sms,
+                 uint32_t wait_epoch, unsigned long long timeout_ns);
 // after a copy kernel: every destination slot now has its source's extent. With `record` the
 // step's moved bytes are also written into the history ring (last copy launch of a step).
 // `realign` = extent copy (the copy kernel wrote the band tables); otherwise (whole-grid copies move rows

@@ -113,15 +113,28 @@ __device__ __forceinline__ void row_arc(const MapGeom& geom, int y0, int y1, uin
     len = b1 - b0;
 }
 
-// one warp per job
-__global__ void __launch_bounds__(256)
-k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
-               const unsigned long long* __restrict__ n_items, const unsigned long long* __restrict__ n_leaders,
-               CopyJob* __restrict__ jobs, MapGeom geom, StepCounters* counters) {
-    const unsigned long long n = *n_items;
-    const unsigned long long nl = leaders ? *n_leaders : n;
-    const unsigned long long q = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= nl) return;
+// Waits until the owner of a source slot has published `wait_epoch` in its SlotMeta (pulls without a barrier across
+// the GPUs: the owner's ray update stores it once the slot is complete -- cells, band entries, box). Bounded like the
+// step barrier; a handle that has given up does not wait again. Called by one lane; the caller re-converges.
+__device__ __forceinline__ void wait_source_epoch(const SlotMeta* src_meta, uint32_t wait_epoch, unsigned long long timeout_ns,
+                                                  StepCounters* counters) {
+    if (*reinterpret_cast<volatile unsigned long long*>(&counters->barrier_timeout) != 0ull) return;
+    unsigned long long t0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&src_meta->pad0) : "memory");
+        if (seen == wait_epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) { counters->barrier_timeout = 1ull; break; }
+        __nanosleep(200);
+    }
+}
+
+// One warp turns the fan-out sub-run q of the copy list into a CopyJob (*job: global or shared memory).
+__device__ __forceinline__ void prepare_job(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
+                                            unsigned long long n, unsigned long long q, CopyJob* job, const MapGeom& geom,
+                                            StepCounters* counters, uint32_t wait_epoch, unsigned long long timeout_ns) {
     const int lane = threadIdx.x & 31;
     const uint32_t ymask = geom.ymask, yring = geom.ymask == 0xffffffffu ? 0xffffffffu : geom.ph;
     const unsigned long long k = leaders ? leaders[q] : q;
@@ -132,7 +145,15 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
     const unsigned same = __ballot_sync(0xffffffffu, have && (unsigned long long)(uintptr_t)it.src == src0);
     const uint32_t fan = (uint32_t)(__ffs(~same) - 1);   // leading run of items that share the source
     SlotMeta sm{0, 0, 0, 0, 0, 0, 0, 0}, dm{0, 0, 0, 0, 0, 0, 0, 0};
-    if (lane == 0) sm = *it.src_meta;
+    if (wait_epoch != 0u) {
+        if (lane == 0) wait_source_epoch(it.src_meta, wait_epoch, timeout_ns, counters);
+        __syncwarp();
+        __threadfence_system();
+    }
+    if (lane == 0) {   // (not through L1: a peer has just written it)
+        const int4 box = __ldcv(reinterpret_cast<const int4*>(it.src_meta));
+        sm.x0 = box.x; sm.y0 = box.y; sm.x1 = box.z; sm.y1 = box.w;
+    }
     if (lane < (int)fan) dm = *it.dst_meta;
     // rows: the destinations' old rows (to clear) and the source's rows, as band-aligned arcs
     uint32_t oy_start = 0u, oy_len = 0u;
@@ -143,7 +164,6 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
         const uint32_t bys = __shfl_sync(0xffffffffu, oy_start, (int)f), byl = __shfl_sync(0xffffffffu, oy_len, (int)f);
         if (lane == 0) arc_cover(uy_start, uy_len, bys, byl, ymask, yring);
     }
-    CopyJob* job = jobs + q;
     if (lane < (int)COPY_FAN) {
         job->dst[lane] = lane < (int)fan ? it.dst : nullptr;
         job->dst_bands[lane] = lane < (int)fan ? it.dst_bands : nullptr;
@@ -154,6 +174,19 @@ k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ 
         job->pad = 0u;
         if (uy_len) atomicMax(&counters->copy_max_rows, (unsigned long long)uy_len);
     }
+}
+
+// one warp per job
+__global__ void __launch_bounds__(256)
+k_copy_prepare(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
+               const unsigned long long* __restrict__ n_items, const unsigned long long* __restrict__ n_leaders,
+               CopyJob* __restrict__ jobs, MapGeom geom, StepCounters* counters, uint32_t wait_epoch,
+               unsigned long long timeout_ns) {
+    const unsigned long long n = *n_items;
+    const unsigned long long nl = leaders ? *n_leaders : n;
+    const unsigned long long q = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nl) return;
+    prepare_job(items, leaders, n, q, jobs + q, geom, counters, wait_epoch, timeout_ns);
 }
 
 // CTAs are single warps: a band is a few hundred 32-byte elements, and with more warps per CTA the
@@ -171,6 +204,88 @@ constexpr int BOX_CTAS_PER_SM = BOX_CTAS;
 #define BOX_SHORT_CTAS 48   // CTAs per SM for a short list (a few hundred jobs)
 #endif
 
+// One band (BAND_ROWS slot rows) of one job, by one warp: the source's columns of the band into every destination, the
+// rest of what the destinations had informed there cleared, the destinations' band entries rewritten.
+template <int UNROLL>
+__device__ __forceinline__ void copy_job_band(const CopyJob& s_job, uint32_t bi, const MapGeom& geom, uint32_t& moved,
+                                              const uint32_t* src_entries = nullptr /* [bi]: the source's band entries, prefetched */) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t row_units = geom.pw / 8u;
+    const bool tiled = geom.tiled != 0u;
+    constexpr uint32_t TILE_UNITS = TILE_COLS / 8u;   // 32-byte units per tile row
+    const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
+    const uint32_t uring = geom.xmask == 0xffffffffu ? 0xffffffffu : row_units;
+    if (bi * BAND_ROWS >= s_job.uy_len) return;
+    const uint32_t prow0 = (s_job.uy_start + bi * BAND_ROWS) & geom.ymask;   // first slot row of the band
+    const uint32_t pb = prow0 / BAND_ROWS;
+    const uint32_t fan = s_job.fan;
+    // ---- the 17 band entries: lane f < fan = destination f's old columns, lane 31 = the source's
+    uint32_t a_start = 0u, a_len = 0u;      // this lane's arc in destination units
+    uint32_t src_entry = 0u;
+    if ((uint32_t)lane < fan) {
+        const uint32_t e = s_job.dst_bands[lane][pb];
+        if (e) {
+            a_start = (phys_col(geom, e & 0xffffu) >> 3) & umask;
+            a_len = ((e >> 16) - (e & 0xffffu)) >> 3;
+        }
+    } else if (lane == 31) {
+        src_entry = src_entries ? src_entries[bi] : __ldg(&s_job.src_bands[pb]);
+    }
+    src_entry = __shfl_sync(0xffffffffu, src_entry, 31);
+    uint32_t n_start = 0u, n_len = 0u;   // the source's columns (same place in source and destination)
+    if (src_entry) {
+        const uint32_t sx0 = src_entry & 0xffffu;
+        n_len = ((src_entry >> 16) - sx0) >> 3;
+        n_start = (phys_col(geom, sx0) >> 3) & umask;
+        if (lane == 31) { a_start = n_start; a_len = n_len; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {   // cover of all arcs, reduced to lane 0
+        const uint32_t bs = __shfl_down_sync(0xffffffffu, a_start, o), bl = __shfl_down_sync(0xffffffffu, a_len, o);
+        arc_cover(a_start, a_len, bs, bl, umask, uring);
+    }
+    uint32_t u_start = __shfl_sync(0xffffffffu, a_start, 0), uw = __shfl_sync(0xffffffffu, a_len, 0);
+    if (tiled && uw != 0u) {   // whole tiles: every DRAM page the band touches is written in full
+        uw = ((u_start & (TILE_UNITS - 1u)) + uw + TILE_UNITS - 1u) & ~(TILE_UNITS - 1u);
+        u_start &= ~(TILE_UNITS - 1u);
+        if (uw >= uring) { u_start = 0u; uw = uring; }
+    }
+    if (uw != 0u) {
+        const uint32_t count = BAND_ROWS * uw;
+        const V8* src = reinterpret_cast<const V8*>(s_job.src);
+        for (uint32_t base = lane; base < count; base += BOX_THREADS * UNROLL) {
+            V8 v[UNROLL];
+            uint32_t off[UNROLL];   // unit offset inside a destination slot (< 2^28)
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t i = base + u * BOX_THREADS;
+                off[u] = 0xffffffffu;
+                v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
+                if (i < count) {
+                    // row-major slots: a lane walks the band's rows; tiled slots: 32 lanes = one tile (1 KiB)
+                    const uint32_t rr = tiled ? (i / TILE_UNITS) % BAND_ROWS : i / uw;
+                    const uint32_t cu = tiled ? i / (TILE_UNITS * BAND_ROWS) * TILE_UNITS + i % TILE_UNITS : i - rr * uw;
+                    const uint32_t py = prow0 + rr;                  // same slot row in source and destination
+                    const uint32_t du = (u_start + cu) & umask;      // destination unit on the ring
+                    off[u] = phys_unit(geom, py, du);
+                    if (((du - n_start) & umask) < n_len) {
+                        v[u] = ld_stream_v8(src + off[u]);
+                        moved++;
+                    }
+                }
+            }
+            for (uint32_t f = 0; f < fan; ++f) {
+                V8* dst = reinterpret_cast<V8*>(s_job.dst[f]);
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+                    if (off[u] != 0xffffffffu) { st_stream_v8(dst + off[u], v[u]); moved++; }
+            }
+        }
+    }
+    // the destinations now hold the source's columns in this band (or nothing)
+    if ((uint32_t)lane < fan) s_job.dst_bands[lane][pb] = src_entry;
+}
+
 template <int UNROLL, int MINB>
 __global__ void __launch_bounds__(BOX_THREADS, MINB)
 k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restrict__ n_jobs, MapGeom geom,
@@ -179,11 +294,6 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
     const unsigned long long nl = *n_jobs;
     if (nl == 0) return;
     const int lane = threadIdx.x;
-    const uint32_t row_units = geom.pw / 8u;
-    const bool tiled = geom.tiled != 0u;
-    constexpr uint32_t TILE_UNITS = TILE_COLS / 8u;   // 32-byte units per tile row
-    const uint32_t umask = geom.xmask == 0xffffffffu ? 0xffffffffu : (geom.xmask >> 3);
-    const uint32_t uring = geom.xmask == 0xffffffffu ? 0xffffffffu : row_units;
     const uint32_t bands = max(1u, (uint32_t)counters->copy_max_rows / BAND_ROWS);   // work items per job
     const uint32_t total = (uint32_t)min(nl * bands, 0xffffffffull);
     uint32_t moved = 0;   // 32-byte units read + written by this lane
@@ -200,75 +310,7 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
             if (wn < total) next_job = reinterpret_cast<const uint4*>(jobs + (uint32_t)wn / bands)[lane];
         }
         __syncwarp();
-        if (bi * BAND_ROWS >= s_job.uy_len) continue;
-        const uint32_t prow0 = (s_job.uy_start + bi * BAND_ROWS) & geom.ymask;   // first slot row of the band
-        const uint32_t pb = prow0 / BAND_ROWS;
-        const uint32_t fan = s_job.fan;
-        // ---- the 17 band entries: lane f < fan = destination f's old columns, lane 31 = the source's
-        uint32_t a_start = 0u, a_len = 0u;      // this lane's arc in destination units
-        uint32_t src_entry = 0u;
-        if ((uint32_t)lane < fan) {
-            const uint32_t e = s_job.dst_bands[lane][pb];
-            if (e) {
-                a_start = (phys_col(geom, e & 0xffffu) >> 3) & umask;
-                a_len = ((e >> 16) - (e & 0xffffu)) >> 3;
-            }
-        } else if (lane == 31) {
-            src_entry = __ldg(&s_job.src_bands[pb]);
-        }
-        src_entry = __shfl_sync(0xffffffffu, src_entry, 31);
-        uint32_t n_start = 0u, n_len = 0u;   // the source's columns (same place in source and destination)
-        if (src_entry) {
-            const uint32_t sx0 = src_entry & 0xffffu;
-            n_len = ((src_entry >> 16) - sx0) >> 3;
-            n_start = (phys_col(geom, sx0) >> 3) & umask;
-            if (lane == 31) { a_start = n_start; a_len = n_len; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {   // cover of all arcs, reduced to lane 0
-            const uint32_t bs = __shfl_down_sync(0xffffffffu, a_start, o), bl = __shfl_down_sync(0xffffffffu, a_len, o);
-            arc_cover(a_start, a_len, bs, bl, umask, uring);
-        }
-        uint32_t u_start = __shfl_sync(0xffffffffu, a_start, 0), uw = __shfl_sync(0xffffffffu, a_len, 0);
-        if (tiled && uw != 0u) {   // whole tiles: every DRAM page the band touches is written in full
-            uw = ((u_start & (TILE_UNITS - 1u)) + uw + TILE_UNITS - 1u) & ~(TILE_UNITS - 1u);
-            u_start &= ~(TILE_UNITS - 1u);
-            if (uw >= uring) { u_start = 0u; uw = uring; }
-        }
-        if (uw != 0u) {
-            const uint32_t count = BAND_ROWS * uw;
-            const V8* src = reinterpret_cast<const V8*>(s_job.src);
-            for (uint32_t base = lane; base < count; base += BOX_THREADS * UNROLL) {
-                V8 v[UNROLL];
-                uint32_t off[UNROLL];   // unit offset inside a destination slot (< 2^28)
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const uint32_t i = base + u * BOX_THREADS;
-                    off[u] = 0xffffffffu;
-                    v[u].a = make_uint4(0u, 0u, 0u, 0u); v[u].b = v[u].a;
-                    if (i < count) {
-                        // row-major slots: a lane walks the band's rows; tiled slots: 32 lanes = one tile (1 KiB)
-                        const uint32_t rr = tiled ? (i / TILE_UNITS) % BAND_ROWS : i / uw;
-                        const uint32_t cu = tiled ? i / (TILE_UNITS * BAND_ROWS) * TILE_UNITS + i % TILE_UNITS : i - rr * uw;
-                        const uint32_t py = prow0 + rr;                  // same slot row in source and destination
-                        const uint32_t du = (u_start + cu) & umask;      // destination unit on the ring
-                        off[u] = phys_unit(geom, py, du);
-                        if (((du - n_start) & umask) < n_len) {
-                            v[u] = ld_stream_v8(src + off[u]);
-                            moved++;
-                        }
-                    }
-                }
-                for (uint32_t f = 0; f < fan; ++f) {
-                    V8* dst = reinterpret_cast<V8*>(s_job.dst[f]);
-#pragma unroll
-                    for (int u = 0; u < UNROLL; ++u)
-                        if (off[u] != 0xffffffffu) { st_stream_v8(dst + off[u], v[u]); moved++; }
-                }
-            }
-        }
-        // the destinations now hold the source's columns in this band (or nothing)
-        if ((uint32_t)lane < fan) s_job.dst_bands[lane][pb] = src_entry;
+        copy_job_band<UNROLL>(s_job, bi, geom, moved);
     }
     // bytes actually moved, for the roofline: one atomic per warp = per CTA
 #pragma unroll
@@ -276,11 +318,63 @@ k_copy_boxed(const CopyJob* __restrict__ jobs, const unsigned long long* __restr
     if (lane == 0 && moved) atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
 }
 
+// =============================================================================== k_pull
+// Pulls of remote sources without a barrier across the GPUs (world > 1, default path): one CTA per job. Warp 0 waits
+// until the source's owner has published this step's epoch in the slot's SlotMeta (its ray update has left the slot
+// complete), builds the job in shared memory, and the CTA's warps copy its bands over NVLink. Runs on the side stream
+// behind the planner, concurrently with this GPU's own ray update: a pull starts as soon as ITS source is ready.
+constexpr int PULL_THREADS = 256;
+constexpr uint32_t PULL_SPLIT = 4;          // CTAs per job: a pull is bound by NVLink round trips, not by bytes
+constexpr uint32_t PULL_MAX_BANDS = 512;    // band entries of the source prefetched per job (more: read one by one)
+__global__ void __launch_bounds__(PULL_THREADS)
+k_pull(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders, const unsigned long long* __restrict__ n_items,
+       const unsigned long long* __restrict__ n_leaders, MapGeom geom, StepCounters* counters, uint32_t wait_epoch,
+       unsigned long long timeout_ns) {
+    __shared__ CopyJob s_job;
+    __shared__ uint32_t s_src_entries[PULL_MAX_BANDS];
+    const unsigned long long n = *n_items;
+    const unsigned long long nl = leaders ? *n_leaders : n;
+    const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    uint32_t moved = 0;
+    for (unsigned long long w = blockIdx.x; w < nl * PULL_SPLIT; w += gridDim.x) {
+        const unsigned long long q = w / PULL_SPLIT;
+        const uint32_t part = (uint32_t)(w - q * PULL_SPLIT);
+        __syncthreads();   // the previous job is no longer read
+        if (warp == 0) prepare_job(items, leaders, n, q, &s_job, geom, counters, wait_epoch, timeout_ns);
+        __syncthreads();
+        const uint32_t bands = s_job.uy_len / BAND_ROWS;
+        // the source's band entries of this CTA's bands in one round trip
+        const bool prefetched = bands <= PULL_MAX_BANDS;
+        if (prefetched) {
+            for (uint32_t bi = part * n_warps + threadIdx.x / 32u + (threadIdx.x & 31u) * PULL_SPLIT * n_warps; bi < bands;
+                 bi += 32u * PULL_SPLIT * n_warps) {
+                const uint32_t prow0 = (s_job.uy_start + bi * BAND_ROWS) & geom.ymask;
+                s_src_entries[bi] = __ldcv(&s_job.src_bands[prow0 / BAND_ROWS]);
+            }
+            __syncthreads();
+        }
+        for (uint32_t bi = part * n_warps + warp; bi < bands; bi += PULL_SPLIT * n_warps)
+            copy_job_band<4>(s_job, bi, geom, moved, prefetched ? s_src_entries : nullptr);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) moved += __shfl_down_sync(0xffffffffu, moved, o);
+    if ((threadIdx.x & 31) == 0 && moved) atomicAdd(&counters->copy_bytes, (unsigned long long)moved * 32ull);
+}
+void launch_pull(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders, const unsigned long long* n_items,
+                 const unsigned long long* n_leaders, uint32_t max_items, MapGeom geom, StepCounters* counters, int num_sms,
+                 uint32_t wait_epoch, unsigned long long timeout_ns) {
+    const unsigned long long want = (unsigned long long)(max_items ? max_items : 1u) * PULL_SPLIT;
+    const uint32_t grid = (uint32_t)(want < 2ull * (unsigned long long)num_sms ? want : 2ull * (unsigned long long)num_sms);
+    k_pull<<<grid, PULL_THREADS, 0, stream>>>(items, leaders, n_items, n_leaders, geom, counters, wait_epoch, timeout_ns);
+}
+
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,
                        const unsigned long long* n_items, const unsigned long long* n_leaders, uint32_t max_items,
-                       void* jobs, MapGeom geom, StepCounters* counters, int num_sms, bool short_list) {
+                       void* jobs, MapGeom geom, StepCounters* counters, int num_sms, bool short_list, uint32_t wait_epoch,
+                       unsigned long long timeout_ns) {
     const uint32_t blocks = (max_items + 7u) / 8u;
-    k_copy_prepare<<<blocks ? blocks : 1, 256, 0, stream>>>(items, leaders, n_items, n_leaders, (CopyJob*)jobs, geom, counters);
+    k_copy_prepare<<<blocks ? blocks : 1, 256, 0, stream>>>(items, leaders, n_items, n_leaders, (CopyJob*)jobs, geom, counters,
+                                                            wait_epoch, timeout_ns);
     // The list length is only known on the device, and a CTA without work still costs its launch.
     // A short list (the clones made private before the ray update, NVLink pulls) is bound by the dependent
     // round trips of its few items: more resident warps with fewer loads each (4 x 24 per SM) and one wave of

@@ -787,7 +787,8 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
                     const uint32_t* __restrict__ alive_list, const RayItem* __restrict__ clones, const RayItem* __restrict__ owners,
                     const uint32_t* __restrict__ readers, uint32_t* __restrict__ done, uint32_t* __restrict__ spill_scratch,
                     const int32_t* __restrict__ slot_of, uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta,
-                    uint32_t* __restrict__ bands_all, size_t cells_per_grid, int radius, int reach, StepCounters* counters) {
+                    uint32_t* __restrict__ bands_all, size_t cells_per_grid, int radius, int reach, StepCounters* counters,
+                    uint32_t n_local) {
     extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word
     __shared__ uint32_t s_nspill;
     __shared__ int s_blo[RAY_MAX_BANDS], s_bhi[RAY_MAX_BANDS];
@@ -817,8 +818,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         if (item >= n_items) break;
         RayJob job;
         if (clones) {   // clones first: an owner is popped only after every clone that reads its slot
-            const unsigned long long n_clones = counters->ray_items_front;
-            const RayItem it = item < n_clones ? clones[item] : owners[item - n_clones];
+            const RayItem it = ray_item_at(clones, owners, n_local, counters, item);
             job.particle = it.particle; job.slot = it.slot; job.root = it.root;
         }
         else { job.particle = alive_list[item]; job.slot = slot_of[job.particle]; job.root = job.slot; }
@@ -1422,7 +1422,8 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
                   const uint32_t* __restrict__ readers, uint32_t* __restrict__ done, uint32_t* __restrict__ xflag,
                   HalfXchg* __restrict__ xchg, uint32_t* __restrict__ spill_scratch, const int32_t* __restrict__ slot_of,
                   uint32_t* __restrict__ cells, SlotMeta* __restrict__ meta, uint32_t* __restrict__ bands_all,
-                  size_t cells_per_grid, int radius, uint32_t window_bytes, StepCounters* counters) {
+                  size_t cells_per_grid, int radius, uint32_t window_bytes, StepCounters* counters,
+                  uint32_t* __restrict__ xdone, uint32_t n_local, uint32_t signal_epoch) {
     extern __shared__ __align__(16) uint32_t s_win[];   // two 16-bit cells per word; behind the window: this half's beam list
     uint16_t* s_beam = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_win) + window_bytes);
     __shared__ uint32_t s_nspill, s_nmine, s_eo_shared;
@@ -1447,6 +1448,10 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
     SlotMeta* pend_meta = nullptr;      // helper lane: box of the previous item to union `pend_ext` into
     uint32_t* pend_done = nullptr;      // helper lane: reader counter to bump for the previous item
     int pend_ext[4] = {0, 0, -1, -1};
+    // world > 1 (signal_epoch != 0): a peer GPU that pulls this slot in this step waits for `signal_epoch` in the
+    // slot's SlotMeta::pad0. The half that finishes second publishes it, after the box commit.
+    uint32_t* pend_sig = nullptr;       // helper lane: xdone counter of the previous item
+    SlotMeta* pend_sig_meta = nullptr;
     auto flush_pending = [&]() {
         if (pend_meta != nullptr) {
             SlotMeta b = *pend_meta;
@@ -1461,6 +1466,14 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             __threadfence();
             atomicAdd(pend_done, 1u);        // that half has read the root: its owner may write it
             pend_done = nullptr;
+        }
+        if (pend_sig != nullptr) {
+            __threadfence_system();          // this half's cells, band entries and (upper half) the box
+            if (atomicAdd(pend_sig, 1u) == 1u) {   // the other half was first: everything of this slot is in place
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&pend_sig_meta->pad0), "r"(signal_epoch) : "memory");
+            }
+            pend_sig = nullptr;
         }
     };
     if (threadIdx.x == 0) s_next = atomicAdd(&counters->ray_work_head, 1ull);
@@ -1478,8 +1491,7 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
         const bool upper = (work & 1ull) != 0ull;   // the lower half of a particle is listed first
         RayItem it;
         if (clones) {   // clones first: an owner is popped only after every clone that reads its slot
-            const unsigned long long n_clones = counters->ray_items_front;
-            it = item < n_clones ? clones[item] : owners[item - n_clones];
+            it = ray_item_at(clones, owners, n_local, counters, item);
         } else {
             it.particle = alive_list[item]; it.slot = slot_of[it.particle]; it.root = it.slot; it.old_y0 = it.old_y1 = 0; it.pad = 0u;
         }
@@ -1495,7 +1507,11 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
         const bool walked = !(lcx < 0 || lcx >= (long long)geom.gw || lcy < 0 || lcy >= (long long)geom.gh);
         if (!walked && !fused) {   // nothing to do (both halves agree); the next item still has to be popped
             __syncthreads();
-            if (helper) s_next = atomicAdd(&counters->ray_work_head, 1ull);
+            if (helper) {
+                flush_pending();
+                s_next = atomicAdd(&counters->ray_work_head, 1ull);
+                if (signal_epoch != 0u && it.pad != 0u) { pend_sig = xdone + item; pend_sig_meta = &meta[it.slot]; }
+            }
             continue;
         }
         // (a clone whose pose left the grid integrates nothing but still gets its own cells: the upper half copies all rows)
@@ -1763,6 +1779,7 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
                 if (e2 >= e0 && e3 >= e1) { pend_meta = &meta[it.slot]; pend_ext[0] = e0; pend_ext[1] = e1; pend_ext[2] = e2; pend_ext[3] = e3; }
             }
             if (fused) pend_done = &done[it.root];
+            if (signal_epoch != 0u && it.pad != 0u) { pend_sig = xdone + item; pend_sig_meta = &meta[it.slot]; }
         }
         RAY_STAMP(14);
         RAY_LOG(work, 8);
@@ -1871,7 +1888,7 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
                               const RayItem* clones, const RayItem* owners, const uint32_t* readers, uint32_t* done,
                               uint32_t* xflag, void* xchg, uint32_t* spill_scratch, const int32_t* slot_of, uint32_t* cells,
                               SlotMeta* meta, uint32_t* bands, size_t cells_per_grid, int radius_cells, StepCounters* counters,
-                              uint64_t* window_cells, bool force_generic, int num_sms) {
+                              uint64_t* window_cells, bool force_generic, int num_sms, uint32_t* xdone, uint32_t signal_epoch) {
     // half a particle per work item (whole-grid tiled slots whose window holds every reachable cell): 4 CTAs per SM
     if (ray_update_can_fuse(geom, scan.n_beams, cells_per_grid, force_generic, radius_cells)) {
         const int radius = ray_packed_radius(radius_cells);
@@ -1890,7 +1907,7 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
         if (grid > 2u * n_local) grid = 2u * n_local;
         k_ray_update_half<<<grid, threads, smem, stream>>>(geom, scan, results, first_particle, alive_list, clones, owners, readers, done,
                                                            xflag, (HalfXchg*)xchg, spill_scratch, slot_of, cells, meta, bands,
-                                                           cells_per_grid, radius, (uint32_t)wbytes, counters);
+                                                           cells_per_grid, radius, (uint32_t)wbytes, counters, xdone, n_local, signal_epoch);
 #ifdef SLAMRS_RAY_TRACE
         ray_log_dump_after_launch(stream);
 #endif
@@ -1913,7 +1930,7 @@ cudaError_t launch_ray_update(cudaStream_t stream, MapGeom geom, ScanDevice scan
         if (grid > n_local) grid = n_local;
         k_ray_update_packed<<<grid, threads, wmax * 2, stream>>>(geom, scan, results, first_particle, alive_list, nullptr, nullptr, nullptr,
                                                                  nullptr, spill_scratch, slot_of, cells, meta, bands, cells_per_grid, radius,
-                                                                 radius_cells, counters);
+                                                                 radius_cells, counters, n_local);
         return cudaSuccess;
     }
     const bool vec = (geom.gw % 4u == 0u) && (cells_per_grid % 4u == 0u);

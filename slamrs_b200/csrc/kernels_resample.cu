@@ -420,6 +420,7 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
         counters->n_alive = 0ull; counters->copy_bytes = 0ull; counters->copy_max_rows = 0ull;
         counters->n_mat = 0ull; counters->n_mat_leaders = 0ull; counters->ray_cell_steps = 0ull; counters->ray_copy_bytes = 0ull;
         counters->ray_work_head = 0ull; counters->ray_items_front = 0ull; counters->ray_items_back = 0ull;
+        counters->ray_items_front_local = 0ull; counters->ray_items_back_local = 0ull;
     }
     FOLD_STAMP(1);
     // re-associated prefix of the raw weights: the only ordinary scan of the kernel
@@ -682,8 +683,20 @@ k_resample_indices(const ParticleResult* __restrict__ results, const double* __r
         return;
     }
     RayItem it{0u, 0, 0, 0, 0, 0u};
-    bool clone = false;
+    bool clone = false, remote = false;
+    if (alive && ray.mark_remote != 0u) {
+        // Does a new particle of another rank select this source (that rank pulls the grid in this step)? The index
+        // vector is non-decreasing and this thread is the source's FIRST selector: either it belongs to another rank
+        // itself, or the run of selectors reaches past the end of this rank's range.
+        const uint32_t end = first_particle + n_local;
+        remote = !(m0 >= first_particle && m0 < end);
+        if (!remote && end < n) {
+            bool dummy;
+            remote = (resample ? source_of(end, &dummy) : end) == src_idx;
+        }
+    }
     if (alive) {
+        it.pad = remote ? 1u : 0u;
         it.particle = src_idx - first_particle;
         it.slot = ray.slot_of[it.particle];
         it.root = ray.alias_of[it.slot];
@@ -700,20 +713,30 @@ k_resample_indices(const ParticleResult* __restrict__ results, const double* __r
             ray.meta[it.slot] = src;
         }
     }
-    const unsigned mc = __ballot_sync(0xffffffffu, alive && clone), mo = __ballot_sync(0xffffffffu, alive && !clone);
-    unsigned long long bc = 0, bo = 0;
+    // four classes, in the order the ray update pops them: pulled clones, other clones, pulled owners, other owners
+    // (a pulled grid is ready for its peer early; an owner still comes after every clone that reads its slot)
+    const unsigned mcr = __ballot_sync(0xffffffffu, alive && clone && remote), mcl = __ballot_sync(0xffffffffu, alive && clone && !remote);
+    const unsigned mor = __ballot_sync(0xffffffffu, alive && !clone && remote), mol = __ballot_sync(0xffffffffu, alive && !clone && !remote);
+    unsigned long long bcr = 0, bcl = 0, bor = 0, bol = 0;
     if (lane == 0) {
-        if (mc | mo) atomicAdd(&counters->n_alive, (unsigned long long)__popc(mc | mo));
+        const unsigned mc = mcr | mcl, all = mc | mor | mol;
+        if (all) atomicAdd(&counters->n_alive, (unsigned long long)__popc(all));
         if (mc) {
-            bc = atomicAdd(&counters->ray_items_front, (unsigned long long)__popc(mc));
             atomicAdd(&counters->n_mat, (unsigned long long)__popc(mc));
             atomicAdd(&counters->n_mat_leaders, (unsigned long long)__popc(mc));   // every clone reads its source itself
         }
-        if (mo) bo = atomicAdd(&counters->ray_items_back, (unsigned long long)__popc(mo));
+        if (mcr) bcr = atomicAdd(&counters->ray_items_front, (unsigned long long)__popc(mcr));
+        if (mcl) bcl = atomicAdd(&counters->ray_items_front_local, (unsigned long long)__popc(mcl));
+        if (mor) bor = atomicAdd(&counters->ray_items_back, (unsigned long long)__popc(mor));
+        if (mol) bol = atomicAdd(&counters->ray_items_back_local, (unsigned long long)__popc(mol));
     }
-    bc = __shfl_sync(0xffffffffu, bc, 0); bo = __shfl_sync(0xffffffffu, bo, 0);
-    if (alive && clone) ray.clones[bc + __popc(mc & ((1u << lane) - 1u))] = it;
-    if (alive && !clone) ray.owners[bo + __popc(mo & ((1u << lane) - 1u))] = it;
+    bcr = __shfl_sync(0xffffffffu, bcr, 0); bcl = __shfl_sync(0xffffffffu, bcl, 0);
+    bor = __shfl_sync(0xffffffffu, bor, 0); bol = __shfl_sync(0xffffffffu, bol, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (alive && clone && remote) ray.clones[bcr + __popc(mcr & below)] = it;
+    if (alive && clone && !remote) ray.clones[ray.n_local - 1u - (bcl + __popc(mcl & below))] = it;
+    if (alive && !clone && remote) ray.owners[bor + __popc(mor & below)] = it;
+    if (alive && !clone && !remote) ray.owners[ray.n_local - 1u - (bol + __popc(mol & below))] = it;
 }
 
 void launch_resample_indices(cudaStream_t stream, const ParticleResult* results, const double* cum,
