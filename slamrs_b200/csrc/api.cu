@@ -766,13 +766,14 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     // overlap the tail of the ray update. Every rank takes the same decision (same configuration, same scan).
     const bool flag_pulls = h->world > 1 && fuse && half_items && h->boxed_copy && h->p2p_exchange;
     const uint32_t pull_epoch = flag_pulls ? (uint32_t)(h->step + 1ull) : 0u;
-    if (half_items)
-        CU_TRY(h, cudaMemsetAsync(h->d_readers, 0, sizeof(uint32_t) * (2 * (size_t)h->n_slots + 2 * (size_t)h->n_local), s));
+    // (readers | done | xflag | xdone are cleared by k_motion)
+    const size_t n_zero = half_items ? 2 * (size_t)h->n_slots + 2 * (size_t)h->n_local : 0;
     // 1. motion sample + beam-endpoint likelihood (pre-update map) -> results[first .. first+n_local)
     PROF_MARK(h, 0);
     launch_motion_likelihood(s, h->geom, od, scan, h->d_pose[cur], h->d_slot[cur], h->defer ? h->d_alias : nullptr, h->d_cells, h->d_meta, h->cells_per_grid,
                              h->d_results, h->first, h->n_local, caller ? h->d_z : nullptr, h->cfg.seed, h->step, h->d_term_table, h->d_valid_list, h->d_n_valid,
-                             h->d_carry, h->d_counters, h->p2p_exchange ? h->d_peer_results : nullptr, res_off, h->rank, h->world);
+                             h->d_carry, h->d_counters, h->p2p_exchange ? h->d_peer_results : nullptr, res_off, h->rank, h->world,
+                             h->d_readers, (uint32_t)n_zero);
     h->launches += 2;   // k_motion + k_likelihood
     // 2. the one exchange step: every GPU needs every particle's weight, pose and slot. Default:
     //    k_likelihood has already stored each record into every peer (NVLink), only the barrier is
@@ -891,8 +892,9 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     }
     if (!((h->defer && h->world == 1) || flag_pulls)) h->launches++;
     PROF_MARK(h, 7);
-    launch_commit_boxes(s, h->d_copies, &h->d_counters->n_copies, h->n_local, h->geom, h->boxed_copy, h->d_counters,
-                        h->d_history + (h->step % STEP_HISTORY));
+    // (deferred copies on one GPU: the list is empty, the kernel only completes the step's history record)
+    launch_commit_boxes(s, h->d_copies, &h->d_counters->n_copies, (h->defer && h->world == 1) ? 1u : h->n_local, h->geom,
+                        h->boxed_copy, h->d_counters, h->d_history + (h->step % STEP_HISTORY));
     h->launches++;
     if (h->profiling) h->prof_recorded++;
     CU_TRY(h, cudaGetLastError());

@@ -158,7 +158,8 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               const StepCounters* counters,
                               ParticleResult* const* peer_results /* null: no fused exchange */,
                               uint32_t peer_offset /* records in front of this step's generation */, uint32_t rank,
-                              uint32_t world);
+                              uint32_t world, uint32_t* zero_words /* n_zero words that k_motion clears (may be null with 0) */,
+                              uint32_t n_zero);
 void launch_fill_term_table(cudaStream_t stream, double* table);
 constexpr uint32_t PEER_MAX_WORLD = 64;
 void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,

@@ -13,7 +13,9 @@ __global__ void __launch_bounds__(128)
 k_motion(OdomModel od, const float* __restrict__ pose_cur, const int32_t* __restrict__ slot_of,
          ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
          const double* __restrict__ z_draws, uint64_t seed, uint64_t step, ScanDevice scan,
-         float2* __restrict__ valid_beams, uint32_t* __restrict__ n_valid) {
+         float2* __restrict__ valid_beams, uint32_t* __restrict__ n_valid, uint32_t* __restrict__ zero_words, uint32_t n_zero) {
+    // the ray update's per-step flags and counters start from zero (instead of a memset in front of the step)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero_words[i] = 0u;
     // Block 0 also compacts the (angle, distance) pairs of the scan's VALID beams, in beam order, for
     // k_likelihood: only valid measurements contribute to Map::probability_of (map.rs:117-119), and
     // one coalesced 8-byte load per beam replaces the dependent valid[] -> angle[], dist[] loads that
@@ -148,9 +150,10 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               uint32_t n_local, const double* z_draws, uint64_t seed, uint64_t step,
                               const double* term_table, float2* valid_beams, uint32_t* n_valid,
                               const double* carry, const StepCounters* counters,
-                              ParticleResult* const* peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
+                              ParticleResult* const* peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world,
+                              uint32_t* zero_words, uint32_t n_zero) {
     k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
-                                                         z_draws, seed, step, scan, valid_beams, n_valid);
+                                                         z_draws, seed, step, scan, valid_beams, n_valid, zero_words, n_zero);
     k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, alias_of, cells, meta, cells_per_grid,
                                                                                    results, first_particle, n_local,
                                                                                    term_table, valid_beams, n_valid, carry, counters,

@@ -1432,6 +1432,8 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
     __shared__ uint32_t s_rowb[HALF_MAX_ROWS];          // shared byte address of column x = 0 of the row
     __shared__ int s_ext[4], s_xinfo[2], s_lext[4];
     __shared__ unsigned long long s_next;
+    __shared__ RayItem s_item;                          // the item s_next names and its particle's pose, fetched ahead
+    __shared__ float s_pose[3];
     __shared__ uint4 s_lrow[HALF_XCHG_GROUPS];
     const unsigned long long n_items = counters->n_alive;
     const int gw = (int)geom.gw, gh = (int)geom.gh;
@@ -1476,7 +1478,20 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             pend_sig = nullptr;
         }
     };
-    if (threadIdx.x == 0) s_next = atomicAdd(&counters->ray_work_head, 1ull);
+    // pops the next work item and fetches what every thread needs of it (one thread, while the others walk)
+    auto pop_next = [&]() {
+        const unsigned long long w = atomicAdd(&counters->ray_work_head, 1ull);
+        if (w < 2ull * n_items) {
+            RayItem nit;
+            if (clones) nit = ray_item_at(clones, owners, n_local, counters, w >> 1);   // clones first: an owner is popped only after every clone that reads its slot
+            else { nit.particle = alive_list[w >> 1]; nit.slot = slot_of[nit.particle]; nit.root = nit.slot; nit.old_y0 = nit.old_y1 = 0; nit.pad = 0u; }
+            const ParticleResult r = results[first_particle + nit.particle];
+            s_item = nit;
+            s_pose[0] = r.x; s_pose[1] = r.y; s_pose[2] = r.theta;
+        }
+        s_next = w;
+    };
+    if (threadIdx.x == 0) pop_next();
 #ifdef SLAMRS_RAY_TRACE
     long long t_prev = clock64();
 #endif
@@ -1489,17 +1504,11 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
         RAY_LOG(work, 0);
         const unsigned long long item = work >> 1;
         const bool upper = (work & 1ull) != 0ull;   // the lower half of a particle is listed first
-        RayItem it;
-        if (clones) {   // clones first: an owner is popped only after every clone that reads its slot
-            it = ray_item_at(clones, owners, n_local, counters, item);
-        } else {
-            it.particle = alive_list[item]; it.slot = slot_of[it.particle]; it.root = it.slot; it.old_y0 = it.old_y1 = 0; it.pad = 0u;
-        }
+        const RayItem it = s_item;
         const bool fused = it.root != it.slot;
         uint32_t* grid = cells + (size_t)it.slot * cells_per_grid;
         uint32_t* bands = bands_all + (size_t)it.slot * n_bands_slot;
-        const ParticleResult r = results[first_particle + it.particle];
-        const float px = r.x, py = r.y, ptheta = r.theta;
+        const float px = s_pose[0], py = s_pose[1], ptheta = s_pose[2];
         const float sx = world_to_grid(px, geom.pos_x, geom.res);
         const float sy = world_to_grid(py, geom.pos_y, geom.res);
         const long long lcx = f32_as_isize(floorf(sx)), lcy = f32_as_isize(floorf(sy));
@@ -1509,7 +1518,7 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
             __syncthreads();
             if (helper) {
                 flush_pending();
-                s_next = atomicAdd(&counters->ray_work_head, 1ull);
+                pop_next();
                 if (signal_epoch != 0u && it.pad != 0u) { pend_sig = xdone + item; pend_sig_meta = &meta[it.slot]; }
             }
             continue;
@@ -1602,7 +1611,7 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
         RAY_LOG(work, 2);
         if (helper) {
             flush_pending();
-            s_next = atomicAdd(&counters->ray_work_head, 1ull);   // (read only after the barrier that ends this item)
+            pop_next();   // (s_next, s_item, s_pose are read only after the barrier that ends this item)
         }
         if (walked)
             ray_walk_half(geom, scan, s_beam, s_nmine, px, py, ptheta, sx, sy, cx0, cy0, rad, upper, wy0, wh, band0, s_win, s_row,
@@ -1756,7 +1765,7 @@ k_ray_update_half(MapGeom geom, ScanDevice scan, const ParticleResult* __restric
         __syncthreads();
         RAY_STAMP(fused ? 7 : 11);
         RAY_LOG(work, 7);
-        RAY_LOG_V(work, 9, (unsigned long long)ray_smid() | ((unsigned long long)blockIdx.x << 16) | (fused ? 1ull << 40 : 0ull) | (upper ? 1ull << 41 : 0ull) | ((unsigned long long)s_nmine << 44));
+        RAY_LOG_V(work, 9, (unsigned long long)ray_smid() | ((unsigned long long)blockIdx.x << 16) | (fused ? 1ull << 40 : 0ull) | (upper ? 1ull << 41 : 0ull) | (it.pad ? 1ull << 42 : 0ull) | ((unsigned long long)s_nmine << 44));
 #ifdef SLAMRS_RAY_TRACE
         if (threadIdx.x == 0) atomicAdd(&g_ray_trace_items[fused ? 0 : 1], 1ull);
 #endif
@@ -1857,7 +1866,9 @@ static void ray_log_dump_after_launch(cudaStream_t stream) {
     const int first = which ? atoi(which) : 20;
     ++launches;
     if (!path || launches < first || launches >= first + 4) return;
-    const std::string name = std::string(path) + "." + std::to_string(launches - first);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::string name = std::string(path) + ".d" + std::to_string(dev) + "." + std::to_string(launches - first);
     path = name.c_str();
     cudaStreamSynchronize(stream);
     std::vector<unsigned long long> log((size_t)RAY_LOG_ITEMS * RAY_LOG_COLS);

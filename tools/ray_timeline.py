@@ -26,12 +26,17 @@ upper = (info >> 41) & 1
 cta = (info >> 16) & 0xffff
 smid = info & 0xffff
 nbeam = (info >> 44) & 0xfff
+remote = (info >> 42) & 1
 for k, n in enumerate(names):
     d = (L[:, k + 1] - L[:, k]) / 1e3
     print(f"  {n:14s} mean {d.mean():7.2f} us  p50 {np.median(d):7.2f}  max {d.max():7.2f}")
 tot = (L[:, 8] - L[:, 0]) / 1e3
 print(f"  {'item total':14s} mean {tot.mean():7.2f} us  p50 {np.median(tot):7.2f}  max {tot.max():7.2f}")
 print(f"  fused items {int(fused.sum())}, owners {int((1 - fused).sum())}; beams per half item mean {nbeam.mean():.0f}")
+if remote.any():
+    r = remote == 1
+    print(f"  pulled by a peer: {int(r.sum())} items, total mean {tot[r].mean():.2f} us (others {tot[~r].mean():.2f}); they end at "
+          f"{((L[r, 8] - start) / 1e3).min():.1f}..{((L[r, 8] - start) / 1e3).max():.1f} us")
 # rounds
 order = np.argsort(L[:, 0])
 per_cta = {}
