@@ -485,7 +485,7 @@ def run_cuda(args, wl, rank, world, local):
         "frac": (b / (ms * 1e-3) / 1e9) / peak if peak and ms > 0 else None, "bytes_per_launch": b / K, "ms_per_launch": ms / K}
     boxed = (int(args.flags) & _lib.FLAG_FULL_GRID_COPY) == 0 and wl.grid % 8 == 0
     deferred = boxed and (int(args.flags) & _lib.FLAG_EAGER_COPY) == 0
-    # Ray update (k_ray_update_packed): SURVEY.md 8(d)'s unit is the cell-step of the reference's ray iterator,
+    # Ray update (k_ray_update_half): SURVEY.md 8(d)'s unit is the cell-step of the reference's ray iterator,
     # 4 B read + 4 B written each (8 B); the kernel counts the steps of the rays it integrates.
     ray_ms = ph["ray_update"]
     # ... plus the clone copies the same kernel performs (a surviving clone's cells are copied by the CTA that integrates
@@ -518,8 +518,8 @@ def run_cuda(args, wl, rank, world, local):
                      "counter_saturated": st["counter_saturated"]},
     }
     ray_roofline = {
-        "bound": "hbm", "kernel": "k_ray_update_packed (Bresenham walk in a shared-memory window + 256-bit read-modify-write "
-                                  "of the informed cells)",
+        "bound": "hbm", "kernel": "k_ray_update_half (ray walk into a shared-memory half-disc window, then root tiles + window -> own slot "
+                                  "with 256-bit accesses: the scan's read-modify-write and the copy of a surviving clone)",
         "achieved": ray_bytes / (ray_ms * 1e-3) / 1e9 if ray_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
         "frac": (ray_bytes / (ray_ms * 1e-3) / 1e9) / peak if peak and ray_ms > 0 else None,
         "traffic": ncu_traffic("ray_traffic.json", ray_bytes / K), "peak_source": peak_src,
