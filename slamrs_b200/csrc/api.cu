@@ -844,7 +844,8 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     if (flag_pulls) {
         // the first uses of remote sources, a short list: each job waits for its source's owner (NVLink reads)
         launch_pull(h->side_stream, h->d_copies, h->d_leaders, &h->d_counters->n_copies, &h->d_counters->n_leaders,
-                    h->n_local, h->geom, h->d_counters, h->num_sms, pull_epoch, h->barrier_timeout_ns);
+                    h->n_local, h->geom, h->d_counters, h->num_sms, pull_epoch, h->barrier_timeout_ns, h->d_meta, h->d_readers,
+                    h->d_readers + h->n_slots);
         h->launches++;
     }
     CU_TRY(h, cudaEventRecord(h->ev_plan, h->side_stream));

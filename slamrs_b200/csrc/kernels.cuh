@@ -291,7 +291,9 @@ size_t copy_job_bytes();
 // the same for a short list of REMOTE sources, one CTA per job, each job waiting for its own source (see k_pull)
 void launch_pull(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders, const unsigned long long* n_items,
                  const unsigned long long* n_leaders, uint32_t max_items, MapGeom geom, StepCounters* counters, int num_sms,
-                 uint32_t wait_epoch, unsigned long long timeout_ns);
+                 uint32_t wait_epoch, unsigned long long timeout_ns, const SlotMeta* meta_base /* this GPU's slots */,
+                 const uint32_t* readers, const uint32_t* done /* the ray update's per-slot reader counts: a destination
+                                                                  that clones still read as their root is written after them */);
 // after a copy kernel: every destination slot now has its source's extent. With `record` the
 // step's moved bytes are also written into the history ring (last copy launch of a step).
 // `realign` = extent copy (the copy kernel wrote the band tables); otherwise (whole-grid copies move rows

@@ -134,7 +134,9 @@ __device__ __forceinline__ void wait_source_epoch(const SlotMeta* src_meta, uint
 // One warp turns the fan-out sub-run q of the copy list into a CopyJob (*job: global or shared memory).
 __device__ __forceinline__ void prepare_job(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
                                             unsigned long long n, unsigned long long q, CopyJob* job, const MapGeom& geom,
-                                            StepCounters* counters, uint32_t wait_epoch, unsigned long long timeout_ns) {
+                                            StepCounters* counters, uint32_t wait_epoch, unsigned long long timeout_ns,
+                                            const SlotMeta* meta_base = nullptr, const uint32_t* readers = nullptr,
+                                            const uint32_t* done = nullptr) {
     const int lane = threadIdx.x & 31;
     const uint32_t ymask = geom.ymask, yring = geom.ymask == 0xffffffffu ? 0xffffffffu : geom.ph;
     const unsigned long long k = leaders ? leaders[q] : q;
@@ -147,6 +149,28 @@ __device__ __forceinline__ void prepare_job(const CopyItem* __restrict__ items, 
     SlotMeta sm{0, 0, 0, 0, 0, 0, 0, 0}, dm{0, 0, 0, 0, 0, 0, 0, 0};
     if (wait_epoch != 0u) {
         if (lane == 0) wait_source_epoch(it.src_meta, wait_epoch, timeout_ns, counters);
+        // A destination is a slot no survivor owns -- but the cells it still holds may be the ROOT that surviving clones
+        // of a dropped particle read in this very ray update (they become private there). The pull runs concurrently
+        // with that kernel, so it waits until every such reader is done with the slot (the owners' own protocol:
+        // readers[] = clone halves listed for the slot, done[] = those that have finished).
+#ifndef SLAMRS_TEST_NO_READER_WAIT   /* (a build without this wait must fail tests/test_gpu_multi.py::test_sharded_state_at_scale...) */
+        if (readers != nullptr && lane < (int)fan) {
+            const size_t slot = (size_t)(it.dst_meta - meta_base);
+            const uint32_t want = readers[slot];
+            if (want != 0u && *reinterpret_cast<volatile unsigned long long*>(&counters->barrier_timeout) == 0ull) {
+                unsigned long long t0, now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for (;;) {
+                    uint32_t seen;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + slot) : "memory");
+                    if (seen >= want) break;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (now - t0 > timeout_ns) { counters->barrier_timeout = 1ull; break; }
+                    __nanosleep(200);
+                }
+            }
+        }
+#endif
         __syncwarp();
         __threadfence_system();
     }
@@ -329,7 +353,8 @@ constexpr uint32_t PULL_MAX_BANDS = 512;    // band entries of the source prefet
 __global__ void __launch_bounds__(PULL_THREADS)
 k_pull(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders, const unsigned long long* __restrict__ n_items,
        const unsigned long long* __restrict__ n_leaders, MapGeom geom, StepCounters* counters, uint32_t wait_epoch,
-       unsigned long long timeout_ns) {
+       unsigned long long timeout_ns, const SlotMeta* __restrict__ meta_base, const uint32_t* __restrict__ readers,
+       const uint32_t* __restrict__ done) {
     __shared__ CopyJob s_job;
     __shared__ uint32_t s_src_entries[PULL_MAX_BANDS];
     const unsigned long long n = *n_items;
@@ -340,7 +365,7 @@ k_pull(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
         const unsigned long long q = w / PULL_SPLIT;
         const uint32_t part = (uint32_t)(w - q * PULL_SPLIT);
         __syncthreads();   // the previous job is no longer read
-        if (warp == 0) prepare_job(items, leaders, n, q, &s_job, geom, counters, wait_epoch, timeout_ns);
+        if (warp == 0) prepare_job(items, leaders, n, q, &s_job, geom, counters, wait_epoch, timeout_ns, meta_base, readers, done);
         __syncthreads();
         const uint32_t bands = s_job.uy_len / BAND_ROWS;
         // the source's band entries of this CTA's bands in one round trip
@@ -362,10 +387,12 @@ k_pull(const CopyItem* __restrict__ items, const uint32_t* __restrict__ leaders,
 }
 void launch_pull(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders, const unsigned long long* n_items,
                  const unsigned long long* n_leaders, uint32_t max_items, MapGeom geom, StepCounters* counters, int num_sms,
-                 uint32_t wait_epoch, unsigned long long timeout_ns) {
+                 uint32_t wait_epoch, unsigned long long timeout_ns, const SlotMeta* meta_base, const uint32_t* readers,
+                 const uint32_t* done) {
     const unsigned long long want = (unsigned long long)(max_items ? max_items : 1u) * PULL_SPLIT;
     const uint32_t grid = (uint32_t)(want < 2ull * (unsigned long long)num_sms ? want : 2ull * (unsigned long long)num_sms);
-    k_pull<<<grid, PULL_THREADS, 0, stream>>>(items, leaders, n_items, n_leaders, geom, counters, wait_epoch, timeout_ns);
+    k_pull<<<grid, PULL_THREADS, 0, stream>>>(items, leaders, n_items, n_leaders, geom, counters, wait_epoch, timeout_ns, meta_base,
+                                              readers, done);
 }
 
 void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_t* leaders,

@@ -18,6 +18,15 @@ def make_scans(scene_scale, n_beams, scanner_range, steps, wheel_base=0.1, speed
     return [sim.next_scan(*speed) for _ in range(steps)]
 
 
+def at_scale_config(n):
+    """The bench's scene at half its grid side: 512^2 grids at 5 cm around a 20 m room, 6 m lidar."""
+    return GridMapSlamConfig(position=(-12.8, -12.8), width=25.6, height=25.6, resolution=0.05, n_particles=n)
+
+
+def at_scale_scans(steps):
+    return make_scans(10.0, 360, 6.0, steps)
+
+
 def oracle_slam(O, cfg: GridMapSlamConfig, track_counts=True):
     return O.OracleSlam(cfg.position, cfg.width, cfg.height, cfg.resolution, cfg.n_particles, track_counts)
 
