@@ -1155,6 +1155,35 @@ __device__ __noinline__ void ray_walk_half(const MapGeom& geom, const ScanDevice
             const uint32_t x_inc2 = (uint32_t)(2 * x_inc);
             int ly = cy0 - wy0;
             uint32_t rb = load_rowb(ly);
+            // The first cells of a walk are free whatever its direction: the cell reached after k steps is k cells from
+            // the start cell in the Manhattan sense, the start point lies inside the start cell, so both offsets to the
+            // cell centre are at most (cells + 0.5) and acc <= (k + 0.5)^2 + 0.25 < K^2 for k < K; with K^2 <= 0.999 x
+            // free_below (the margin dwarfs the f32 rounding of acc) those K cells pass `acc < free_below` without
+            // evaluating it. They take a loop without the distance arithmetic; the distance state is then rebuilt from
+            // the cell position -- cxf and cyf only ever held (integer + 0.5) exactly, so the rebuilt values are the
+            // accumulated ones bit for bit -- and the free run continues with the test.
+            {
+                const float kf = floorf(__fsqrt_rn(__fmul_rn(cls.free_below, 0.999f)));
+                int safe = (kf >= 1.0f && kf < 1.0e6f) ? (int)kf : 0;      // (NaN and tiny thresholds: none)
+                safe = min(safe, remaining);
+                remaining -= safe;
+                for (; safe > 0; --safe) {
+                    const uint32_t c2 = rb + x2;
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(c2 & ~3u), "r"((c2 & 2u) ? 0x10000u : 1u) : "memory");
+                    if (error > 0.0f) {
+                        error = __fsub_rn(error, delta_x);
+                        ly += y_inc;
+                        rb = load_rowb(ly);
+                    } else {
+                        error = __fadd_rn(error, delta_y);
+                        x2 += x_inc2;
+                    }
+                }
+                cxf = __fadd_rn((float)(x2 >> 1), 0.5f);
+                cyf = __fadd_rn((float)(wy0 + ly), 0.5f);
+                dxs = __fsub_rn(sx, cxf); dys = __fsub_rn(sy, cyf);
+                dx2 = __fmul_rn(dxs, dxs); dy2 = __fmul_rn(dys, dys);
+            }
             while (remaining > 0) {                    // free run
                 const float acc = __fadd_rn(dx2, dy2);
                 if (!(acc < cls.free_below)) break;
