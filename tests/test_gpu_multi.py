@@ -151,9 +151,10 @@ def test_sharded_state_at_scale_equals_single_gpu():
     """2 x 8,192 particles on 512^2 grids, 40 scans issued back to back (step_async, like the bench): ~400 survivors
     per GPU (two rounds of ray work items) and dozens of NVLink pulls per step, pulls running WHILE the ray update
     makes surviving clones private. A pull's destination is a slot no survivor owns, but the cells it still holds may
-    be the root those clones read: the pull has to wait for them (round 2 found that race at this scale; the small
-    configurations above never hit it). Index vector, poses and a sample of grids must equal the single-GPU run's bit
-    for bit after the last scan."""
+    be the root those clones read, so the pull waits for them (k_pull). NB this test passes with and without that wait
+    (a -DSLAMRS_TEST_NO_READER_WAIT build): what caught the race was bench.py's cross-mode state hash at 2 x 8,192
+    particles on 1024^2 grids, which exits non-zero on a mismatch. Here: index vector, poses and a sample of grids
+    must equal the single-GPU run's bit for bit after the last scan."""
     if _gpu_count() < 2:
         pytest.skip("needs 2 GPUs")
     n, steps = 16384, 40

@@ -78,8 +78,9 @@ def test_processes_at_scale_equal_single_gpu(tmp_path):
     """2 x 8,192 particles, 40 scans issued back to back, one process per GPU: ~400 survivors per GPU (two rounds of ray
     work items) and dozens of NVLink pulls per step, pulls running WHILE the ray update makes surviving clones private.
     A pull's destination is a slot no survivor owns, but the cells it still holds may be the root those clones read:
-    the pull waits for them (k_pull; round 2 found that race at this scale, the small configurations never hit it).
-    Final index vector, poses and a sample of grids must equal the single-GPU run's bit for bit."""
+    the pull waits for them (k_pull). NB this test passes with and without that wait; bench.py's cross-mode state hash
+    (2 x 8,192 particles, 1024^2 grids) is what caught the race and guards it. Final index vector, poses and a sample
+    of grids must equal the single-GPU run's bit for bit."""
     if _gpu_count() < 2:
         pytest.skip("needs 2 GPUs")
     from slamrs_b200 import GpuPlacement, GridMapSlam
