@@ -124,6 +124,7 @@ struct slamrs_gpu_handle {
     uint64_t prof_steps = 0;
     uint64_t step = 0;
     bool counters_fresh = false;   // h_counters mirrors d_counters (no step issued since the last fetch)
+    bool mirror_by_step = false;   // the last issued step writes the mirror itself (its last kernel): a fetch only synchronises
     bool est_box_stale = false;    // set_cells changed a grid after the step recorded the estimate's extent
     uint64_t launches = 0;
     uint64_t window_cells = 0;
@@ -373,6 +374,7 @@ int unshare_all(slamrs_gpu_handle* h) {
     if (rc) return rc;
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     h->counters_fresh = false;
+    h->mirror_by_step = false;
     return SLAMRS_OK;
 }
 
@@ -393,8 +395,10 @@ int step_barrier(slamrs_gpu_handle* h) {
 // stream synchronisation) serves every read-out that follows the same step.
 int fetch_counters(slamrs_gpu_handle* h) {
     if (h->counters_fresh) return SLAMRS_OK;
-    launch_publish_counters(h->stream, h->d_counters, h->h_counters);   // (not a memcpy: see k_publish_counters)
-    h->launches++;
+    if (!h->mirror_by_step) {
+        launch_publish_counters(h->stream, h->d_counters, h->h_counters);   // (not a memcpy: see k_publish_counters)
+        h->launches++;
+    }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaGetLastError());
     h->counters_fresh = true;
@@ -895,13 +899,14 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 7);
     // (deferred copies on one GPU: the list is empty, the kernel only completes the step's history record)
     launch_commit_boxes(s, h->d_copies, &h->d_counters->n_copies, (h->defer && h->world == 1) ? 1u : h->n_local, h->geom,
-                        h->boxed_copy, h->d_counters, h->d_history + (h->step % STEP_HISTORY));
+                        h->boxed_copy, h->d_counters, h->d_history + (h->step % STEP_HISTORY), h->h_counters);
     h->launches++;
     if (h->profiling) h->prof_recorded++;
     CU_TRY(h, cudaGetLastError());
     h->cur = nxt;
     h->step++;
     h->counters_fresh = false;
+    h->mirror_by_step = true;
     h->est_box_stale = false;
     return SLAMRS_OK;
 }

@@ -299,7 +299,9 @@ void launch_pull(cudaStream_t stream, const CopyItem* items, const uint32_t* lea
 // `realign` = extent copy (the copy kernel wrote the band tables); otherwise (whole-grid copies move rows
 // verbatim) the band tables are copied here
 void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,
-                         MapGeom geom, bool realign, StepCounters* counters, StepRecord* record);
+                         MapGeom geom, bool realign, StepCounters* counters, StepRecord* record,
+                         StepCounters* host_mirror = nullptr /* the step's last kernel: also leaves the counters in the host's
+                                                                page-locked mirror */);
 // add the bytes of a full-grid copy launch to counters->copy_bytes
 void launch_account_full_copy(cudaStream_t stream, const unsigned long long* n_items, const unsigned long long* n_leaders,
                               size_t bytes_per_grid, StepCounters* counters);

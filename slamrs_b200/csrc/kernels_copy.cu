@@ -416,7 +416,8 @@ void launch_copy_boxed(cudaStream_t stream, const CopyItem* items, const uint32_
 size_t copy_job_bytes() { return sizeof(CopyJob); }
 
 __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigned long long* __restrict__ n_items,
-                               MapGeom geom, bool realign, StepCounters* counters, StepRecord* record) {
+                               MapGeom geom, bool realign, StepCounters* counters, StepRecord* record,
+                               StepCounters* host_mirror) {
     const unsigned long long n = *n_items;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -448,11 +449,20 @@ __global__ void k_commit_boxes(const CopyItem* __restrict__ items, const unsigne
             counters->est_box[2] = empty ? 0 : m.x1; counters->est_box[3] = empty ? 0 : m.y1;
         }
     }
+    // The last kernel of a step leaves the step counters in the host's page-locked mirror (a store through the mapping,
+    // not a memcpy -- see k_publish_counters): the host's wait for the step is then a plain stream synchronisation.
+    if (host_mirror != nullptr && blockIdx.x == 0) {
+        __syncthreads();   // thread 0's est_box
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(counters);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(host_mirror);
+        for (uint32_t i = threadIdx.x; i < sizeof(StepCounters) / sizeof(uint32_t); i += blockDim.x) dst[i] = __ldcg(src + i);
+        __threadfence_system();
+    }
 }
 void launch_commit_boxes(cudaStream_t stream, const CopyItem* items, const unsigned long long* n_items, uint32_t max_items,
-                         MapGeom geom, bool realign, StepCounters* counters, StepRecord* record) {
+                         MapGeom geom, bool realign, StepCounters* counters, StepRecord* record, StepCounters* host_mirror) {
     const uint32_t blocks = realign ? (max_items + 255u) / 256u : 148u * 8u;
-    k_commit_boxes<<<blocks ? blocks : 1, 256, 0, stream>>>(items, n_items, geom, realign, counters, record);
+    k_commit_boxes<<<blocks ? blocks : 1, 256, 0, stream>>>(items, n_items, geom, realign, counters, record, host_mirror);
 }
 
 __global__ void k_account_full_copy(const unsigned long long* n_items, const unsigned long long* n_leaders,

@@ -7,16 +7,17 @@ from slamrs_b200.workloads import WORKLOADS
 
 wl = WORKLOADS["c3"]
 sim = wl.simulator()
-scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(30)]
+WARM = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+scans = [sim.next_scan(wl.speed_left, wl.speed_right) for _ in range(WARM + 25)]
 slam = GridMapSlam(wl.slam_config(), GpuPlacement(device=0))
-for obs, odo in scans[:5]:
+for obs, odo in scans[:WARM]:
     slam.update(obs, odo)
 bufs = [torch.empty(slam.grid_w * slam.grid_h, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
 mode = sys.argv[1] if len(sys.argv) > 1 else "async"
 rows = []
 extra = []
 t_all = time.perf_counter()
-for i, (obs, odo) in enumerate(scans[5:25]):
+for i, (obs, odo) in enumerate(scans[WARM:WARM + 20]):
     t0 = time.perf_counter()
     if mode == "split":
         a, d, v = slam._scan_arrays(obs)
