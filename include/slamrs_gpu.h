@@ -246,10 +246,12 @@ enum slamrs_phase {
     SLAMRS_PHASE_MOTION_LIKELIHOOD = 0,
     SLAMRS_PHASE_ALL_GATHER = 1,
     SLAMRS_PHASE_RESAMPLE = 2,   /* weights + indices + survivor list + list of shared grids to make private */
-    SLAMRS_PHASE_MATERIALIZE = 3,/* copies that give the surviving clones their own cells (deferred copies) */
+    SLAMRS_PHASE_MATERIALIZE = 3,/* separate copies that give surviving clones their own cells (row-major / windowed slots; the
+                                    default ray update makes them itself) */
     SLAMRS_PHASE_RAY_UPDATE = 4,
-    SLAMRS_PHASE_PULL = 5,       /* join with the planner + cross-GPU barrier */
-    SLAMRS_PHASE_COPY = 6,       /* eager fan-out copies / NVLink pulls of remote sources, commit */
+    SLAMRS_PHASE_PULL = 5,       /* join with the side stream (planner; multi-GPU: the NVLink pulls that ran beside the ray
+                                    update) + the cross-GPU barrier of the modes that still need one */
+    SLAMRS_PHASE_COPY = 6,       /* eager fan-out copies / whole-grid copies, commit */
     SLAMRS_PHASE_COUNT = 7
 };
 int slamrs_gpu_set_profiling(slamrs_gpu_handle* h, int enabled);
