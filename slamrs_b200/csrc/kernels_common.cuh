@@ -7,6 +7,25 @@
 
 namespace slamrs {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may become resident while the kernel in
+// front of it in the stream still runs -- once that one has let its dependents go (pdl_launch_dependents) -- and must
+// not touch anything the stream order protects before pdl_wait() returns (the prerequisite grid has completed and its
+// writes are visible). Without the launch attribute both are no-ops. Takes the launch latency and the ramp of the
+// short kernels of the step (motion -> likelihood -> weights -> indices) out of the critical path.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+
 namespace cg = cooperative_groups;
 
 

@@ -14,6 +14,7 @@ k_motion(OdomModel od, const float* __restrict__ pose_cur, const int32_t* __rest
          ParticleResult* __restrict__ results, uint32_t first_particle, uint32_t n_local,
          const double* __restrict__ z_draws, uint64_t seed, uint64_t step, ScanDevice scan,
          float2* __restrict__ valid_beams, uint32_t* __restrict__ n_valid, uint32_t* __restrict__ zero_words, uint32_t n_zero) {
+    pdl_launch_dependents();   // k_likelihood may take its place on the SMs now; it waits for this grid before it reads
     // the ray update's per-step flags and counters start from zero (instead of a memset in front of the step)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero_words[i] = 0u;
     // Block 0 also compacts the (angle, distance) pairs of the scan's VALID beams, in beam order, for
@@ -86,6 +87,8 @@ k_likelihood(MapGeom geom, ScanDevice scan, const int32_t* __restrict__ alias_of
              const double* __restrict__ term_table, const float2* __restrict__ valid_beams,
              const uint32_t* __restrict__ n_valid_ptr, const double* __restrict__ carry, const StepCounters* __restrict__ counters,
              ParticleResult* const* __restrict__ peer_results, uint32_t peer_offset, uint32_t rank, uint32_t world) {
+    pdl_launch_dependents();   // (k_weights, one CTA, may become resident)
+    pdl_wait();                // k_motion has completed: poses, motion log-densities, the compacted beam list
     const uint32_t p = blockIdx.x * LK_WARPS + (threadIdx.x >> 5);
     if (p >= n_local) return;
     const int lane = threadIdx.x & 31;
@@ -154,10 +157,9 @@ void launch_motion_likelihood(cudaStream_t stream, MapGeom geom, OdomModel od, S
                               uint32_t* zero_words, uint32_t n_zero) {
     k_motion<<<(n_local + 127u) / 128u, 128, 0, stream>>>(od, pose_cur, slot_of, results, first_particle, n_local,
                                                          z_draws, seed, step, scan, valid_beams, n_valid, zero_words, n_zero);
-    k_likelihood<<<(n_local + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32, 0, stream>>>(geom, scan, alias_of, cells, meta, cells_per_grid,
-                                                                                   results, first_particle, n_local,
-                                                                                   term_table, valid_beams, n_valid, carry, counters,
-                                                                                   peer_results, peer_offset, rank, world);
+    launch_pdl(k_likelihood, dim3((n_local + LK_WARPS - 1) / LK_WARPS), dim3(LK_WARPS * 32), 0, stream, geom, scan, alias_of, cells,
+               meta, cells_per_grid, results, first_particle, n_local, term_table, valid_beams, n_valid, carry, counters,
+               peer_results, peer_offset, rank, world);
 }
 
 __global__ void k_fill_term_table(double* __restrict__ table) {
@@ -187,6 +189,8 @@ constexpr unsigned long long PEER_GOODBYE = ~0ull;
 __global__ void __launch_bounds__(64)
 k_peer_barrier(unsigned long long* const* __restrict__ peer_flags, unsigned long long* my_flags, uint32_t rank,
                uint32_t world, unsigned long long epoch, unsigned long long timeout_ns, StepCounters* counters) {
+    pdl_launch_dependents();   // (k_weights may become resident; it waits for this grid)
+    pdl_wait();                // the kernel in front (k_likelihood and its peer stores) has completed
     const uint32_t q = threadIdx.x;
     if (q >= world) return;
     const bool leaving = epoch == PEER_GOODBYE;
@@ -220,7 +224,7 @@ k_peer_barrier(unsigned long long* const* __restrict__ peer_flags, unsigned long
 void launch_peer_barrier(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
                          uint32_t rank, uint32_t world, unsigned long long epoch, unsigned long long timeout_ns,
                          StepCounters* counters) {
-    k_peer_barrier<<<1, 64, 0, stream>>>(peer_flags, my_flags, rank, world, epoch, timeout_ns, counters);
+    launch_pdl(k_peer_barrier, dim3(1), dim3(64), 0, stream, peer_flags, my_flags, rank, world, epoch, timeout_ns, counters);
 }
 void launch_peer_goodbye(cudaStream_t stream, unsigned long long* const* peer_flags, unsigned long long* my_flags,
                          uint32_t rank, uint32_t world, unsigned long long timeout_ns, StepCounters* counters) {

@@ -375,6 +375,8 @@ k_weights(const ParticleResult* __restrict__ results, uint32_t n, double* __rest
     __shared__ long long s_ckey[W_CLUSTER];         // per-CTA argmax candidates (read by CTA 0)
     __shared__ uint32_t s_carg[W_CLUSTER];
     __shared__ double s_seq[2];
+    pdl_launch_dependents();   // (k_resample_indices may become resident)
+    pdl_wait();                // every weight of the step is in place (k_likelihood, or the barrier / all-gather behind it)
     FOLD_STAMP(0);
     const uint32_t gt = crank * THREADS + threadIdx.x;
     const uint32_t L = LREG ? (uint32_t)LREG : (n + C * THREADS - 1u) / (C * THREADS);
@@ -569,11 +571,13 @@ void launch_weights(cudaStream_t stream, const ParticleResult* results, uint32_t
     cfg.blockDim = dim3(regs ? FOLD_THREADS : FOLD_GENERIC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = regs ? weights_tile_bytes() : 0;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // (see launch_pdl)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     if (regs) cudaLaunchKernelEx(&cfg, k_weights<FOLD_LREG, FOLD_THREADS>, results, n_total, w_norm, cum, fold_scratch, resample_tau, counters);
     else cudaLaunchKernelEx(&cfg, k_weights<0, FOLD_GENERIC_THREADS>, results, n_total, w_norm, cum, fold_scratch, resample_tau, counters);
 }
@@ -629,6 +633,7 @@ k_resample_indices(const ParticleResult* __restrict__ results, const double* __r
                    uint32_t* __restrict__ alive_list, RayLists ray, const double* __restrict__ w_norm,
                    double* __restrict__ carry, StepCounters* counters) {
     __shared__ double s_coarse[RS_COARSE];
+    pdl_wait();                // k_weights has completed: normalised weights, running sum, counters
     const bool resample = counters->do_resample != 0ull;   // (adaptive resampling: 0 = every particle stays in place)
     const uint32_t stride = (n + RS_COARSE - 1u) / RS_COARSE;      // weights per block
     const uint32_t n_coarse = (n + stride - 1u) / stride;
@@ -744,9 +749,8 @@ void launch_resample_indices(cudaStream_t stream, const ParticleResult* results,
                              uint32_t* idx, float* pose_next, uint32_t first_particle, uint32_t n_local,
                              bool build_alive, uint32_t* alive_list, RayLists ray, const double* w_norm, double* carry,
                              StepCounters* counters) {
-    k_resample_indices<<<(n_total + 255) / 256, 256, 0, stream>>>(results, cum, n_total, u01_caller, seed, step, idx,
-                                                                 pose_next, first_particle, n_local, build_alive,
-                                                                 alive_list, ray, w_norm, carry, counters);
+    launch_pdl(k_resample_indices, dim3((n_total + 255) / 256), dim3(256), 0, stream, results, cum, n_total, u01_caller, seed, step, idx,
+               pose_next, first_particle, n_local, build_alive, alive_list, ray, w_norm, carry, counters);
 }
 
 // =============================================================================== k_mark_alive
