@@ -125,6 +125,7 @@ struct slamrs_gpu_handle {
     uint64_t step = 0;
     bool counters_fresh = false;   // h_counters mirrors d_counters (no step issued since the last fetch)
     bool mirror_by_step = false;   // the last issued step writes the mirror itself (its last kernel): a fetch only synchronises
+    bool mirror_wanted = false;    // set by slamrs_gpu_update around its step: the caller synchronises right behind it
     bool est_box_stale = false;    // set_cells changed a grid after the step recorded the estimate's extent
     uint64_t launches = 0;
     uint64_t window_cells = 0;
@@ -899,14 +900,15 @@ int slamrs_gpu_step_async(slamrs_gpu_handle* h, float dist_left, float dist_righ
     PROF_MARK(h, 7);
     // (deferred copies on one GPU: the list is empty, the kernel only completes the step's history record)
     launch_commit_boxes(s, h->d_copies, &h->d_counters->n_copies, (h->defer && h->world == 1) ? 1u : h->n_local, h->geom,
-                        h->boxed_copy, h->d_counters, h->d_history + (h->step % STEP_HISTORY), h->h_counters);
+                        h->boxed_copy, h->d_counters, h->d_history + (h->step % STEP_HISTORY),
+                        h->mirror_wanted ? h->h_counters : nullptr);   // (a store over PCIe: only when a sync follows at once)
     h->launches++;
     if (h->profiling) h->prof_recorded++;
     CU_TRY(h, cudaGetLastError());
     h->cur = nxt;
     h->step++;
     h->counters_fresh = false;
-    h->mirror_by_step = true;
+    h->mirror_by_step = h->mirror_wanted;
     h->est_box_stale = false;
     return SLAMRS_OK;
 }
@@ -938,7 +940,9 @@ int slamrs_gpu_update(slamrs_gpu_handle* h, const float* angle, const float* dis
                       const double* resample_u) {
     int rc = slamrs_gpu_upload_scan(h, angle, dist, valid, n_beams);
     if (rc) return rc;
+    h->mirror_wanted = true;   // the step's last kernel leaves the counters in the host mirror: the sync below launches nothing
     rc = slamrs_gpu_step_async(h, dist_left, dist_right, wheel_dist, z_draws, resample_u);
+    h->mirror_wanted = false;
     if (rc) return rc;
     return slamrs_gpu_sync(h);
 }
