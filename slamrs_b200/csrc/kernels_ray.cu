@@ -943,7 +943,7 @@ k_ray_update_packed(MapGeom geom, ScanDevice scan, const ParticleResult* __restr
         // beyond the 32nd of each row, one thread per row. One code path per group: the packed window
         // value is unpacked without a branch; only a grid counter at or above 2^15 (which one scan's
         // increment could saturate) takes the saturating form.
-        constexpr int RAY_WB_ROWS = 4;
+        constexpr int RAY_WB_ROWS = 2;   // (measured on a configs[4] shard: 2 -> 0.770 ms per step, 4 -> 0.800: four rows spilled)
         int exmin = 0x7fffffff, eymin = 0x7fffffff, exmax = -1, eymax = -1;   // this thread's touched extent
         for (int ly0 = warp; ly0 < wh; ly0 += n_warps * RAY_WB_ROWS) {
             uint4 d[RAY_WB_ROWS], va[RAY_WB_ROWS], vb[RAY_WB_ROWS];
